@@ -1,0 +1,202 @@
+/* fdbm_b200 -- C ABI of the B200-native enhancement hot path.
+ *
+ * Drop-in boundary for the reference's Python seams.  The reference
+ * (Dahan-Wang/Rethinking-Flow-and-Diffusion-Bridge-Models-for-Speech-Enhancement) has no C ABI
+ * of its own for this path -- it is PyTorch calls -- so every entry point below names the
+ * reference function (file:line, relative to the reference root) whose arithmetic it replaces.
+ *
+ * Conventions
+ *   - every function returns 0 on success, a negative FDBM_E* code on failure; the message is
+ *     available from fdbm_last_error() (thread-local).  Nothing aborts.
+ *   - all data pointers are DEVICE pointers owned by the caller; calls are stream-ordered on
+ *     `stream` (a cudaStream_t passed as void*), never synchronise, never allocate -- except
+ *     fdbm_plan_create / fdbm_plan_destroy, which own the packed weights and the workspace.
+ *   - spectrograms use the reference layout: complex64 [B, 1, F=257, T] with T contiguous,
+ *     passed as float* (interleaved re, im).  Waveforms are fp32 [B, n_samples].
+ *   - sm_100a only.  There is no fallback: on any other device fdbm_* returns FDBM_EARCH.
+ */
+#ifndef FDBM_B200_H
+#define FDBM_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FDBM_OK        0
+#define FDBM_EINVAL   -1   /* bad argument (shape, alignment, enum)            */
+#define FDBM_ECUDA    -2   /* CUDA runtime / driver error                      */
+#define FDBM_EARCH    -3   /* device is not sm_100                             */
+#define FDBM_ESTATE   -4   /* handle used in the wrong state                   */
+
+/* pad_spec modes, fdbm/util/other.py:76-90 */
+#define FDBM_PAD_ZERO        0
+#define FDBM_PAD_REFLECTION  1
+#define FDBM_PAD_REPLICATION 2
+/* transform_type, fdbm/data_module.py:173-199 */
+#define FDBM_TRANSFORM_EXPONENT 0
+#define FDBM_TRANSFORM_LOG      1
+#define FDBM_TRANSFORM_NONE     2
+/* sampler update kind, fdbm/bridge.py:83 (ODE) and :109 (SDE) */
+#define FDBM_STEP_ODE 0
+#define FDBM_STEP_SDE 1
+
+const char* fdbm_last_error(void);
+int fdbm_version(void);
+/* 0 when the current device is sm_100 (B200); FDBM_EARCH otherwise. */
+int fdbm_check_device(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * Spectral front end.  Replaces SpecsDataModule.stft (fdbm/data_module.py:223-225) +
+ * spec_fwd (:173-186) + pad_spec (fdbm/util/other.py:76-90) in one kernel:
+ * reflect-pad n_fft/2, frame (n_fft, hop), window, rFFT, amplitude compression
+ * |z|^e * exp(j angle z) * factor, right-pad the frame axis to `n_frames_out`.
+ *   wave    fp32  [B, n_samples]           (row stride = wave_stride elements)
+ *   window  fp32  [n_fft]                  (the reference's window tensor, data_module.py:13-19)
+ *   spec    cplx  [B, 1, n_fft/2+1, n_frames_out]
+ * n_fft must be 512; hop must divide n_fft (256 or 128); n_frames_out >= 1 + n_samples/hop.
+ * --------------------------------------------------------------------------------------------- */
+int fdbm_stft_compress(const float* wave, int batch, int64_t n_samples, int64_t wave_stride,
+                       const float* window, int n_fft, int hop,
+                       int transform_type, float spec_factor, float abs_exponent,
+                       int pad_mode, int n_frames_out, float* spec, void* stream);
+
+/* Spectral back end.  Replaces BridgeModel.to_audio (fdbm/model.py:376-377) = spec_back
+ * (fdbm/data_module.py:188-199) + torch.istft (:227-229): de-compress, irFFT, window,
+ * overlap-add, divide by the window-square envelope, drop n_fft/2 samples, cut to `length`.
+ *   spec  cplx [B, 1, n_fft/2+1, n_frames];   wave fp32 [B, length] (row stride wave_stride) */
+int fdbm_decompress_istft(const float* spec, int batch, int n_frames,
+                          const float* window, int n_fft, int hop,
+                          int transform_type, float spec_factor, float abs_exponent,
+                          int64_t length, int64_t wave_stride, float* wave, void* stream);
+
+/* Unfused pieces of the same front/back end, for callers that keep the reference's call sequence:
+ * spec_fwd / spec_back (fdbm/data_module.py:173-199; inverse = 0 / 1) over n_complex elements, and
+ * pad_spec (fdbm/util/other.py:76-90) over `rows` = B*1*F rows of n_frames -> n_frames_out frames. */
+int fdbm_spec_transform(const float* in, float* out, int64_t n_complex, int transform_type, float spec_factor,
+                        float abs_exponent, int inverse, void* stream);
+int fdbm_pad_spec(const float* in, int64_t rows, int n_frames, int pad_mode, int n_frames_out, float* out,
+                  void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Bridge sampler arithmetic.
+ * fdbm_prior_sample: Bridge.prior_sampling (fdbm/bridge.py:45-49)  x0 = b*y + sigma*z.
+ *   z == NULL and sigma != 0 draws z in-kernel (Philox4x32-10 keyed by seed, offset, element);
+ *   n_complex = number of complex elements.
+ * fdbm_bridge_step: loop body of ode_sampler_ei / sde_sampler_ei (fdbm/bridge.py:83, :109)
+ *   ODE: x <- (wx*x + ws*d) + wy*y          SDE: x <- (wx*x + ws*d) + wz*z
+ *   `coef` is a DEVICE pointer to the 3 fp32 weights of this step (row of the [N,3] table
+ *   built on the host with the reference's own op sequence, bridge.py:308-337,373-385), so a
+ *   captured CUDA graph can replay the step.  Evaluated without FMA contraction: bit-identical
+ *   to the reference's three multiplies and two adds.  In-place on x.
+ * --------------------------------------------------------------------------------------------- */
+int fdbm_prior_sample(const float* y, const float* z, float b, float sigma, uint64_t seed, uint64_t offset,
+                      int64_t n_complex, float* x, void* stream);
+int fdbm_bridge_step(float* x, const float* d, const float* y_or_z, const float* coef, int kind,
+                     uint64_t seed, uint64_t offset, int64_t n_complex, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * NCSN++ backbone.  Replaces NCSNpp_v2.forward (fdbm/backbones/ncsnpp_v2.py:241-401) and
+ * NCSNpp_v2_predictive.forward (ncsnpp_v2_predictive.py:222-362) with all their building blocks
+ * (ncsnpp_utils/layerspp.py:32-91,212-274; layers.py:100-124,546-555; up_or_down_sampling.py
+ * :195-257 and the reference's only native op, op/upfirdn2d_kernel.cu:107-207).
+ *
+ * A plan is built for one (architecture, batch, n_frames) shape.  Weights are passed as an array
+ * of host-visible descriptors {name, device pointer, numel} using the reference's state_dict
+ * names (all_modules.<i>.<Layer>.weight ..., output_layer.*); the plan packs them (bf16, tap-major)
+ * into its own buffer.  Re-pack with fdbm_plan_load_weights after parameters change (EMA swap,
+ * fdbm/model.py:146-160; optimizer step).
+ * --------------------------------------------------------------------------------------------- */
+typedef struct fdbm_plan fdbm_plan;
+
+typedef struct fdbm_tensor_ref {
+  const char* name;     /* state_dict key                                   */
+  const float* data;    /* device pointer, fp32, contiguous                 */
+  int64_t numel;
+} fdbm_tensor_ref;
+
+typedef struct fdbm_arch {
+  int nf;                 /* 128                                             */
+  int n_levels;           /* len(ch_mult) = 7                                */
+  int ch_mult[8];         /* 1,1,2,2,2,2,2                                   */
+  int num_res_blocks;     /* 2                                               */
+  int attn_resolution;    /* 16 (0 = none)                                   */
+  int predictive;         /* 0: forward(x,y,t), 4 input ch;  1: forward(y)   */
+  int image_size;         /* 256 (frequency bins seen by the backbone)       */
+} fdbm_arch;
+
+int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out);
+int fdbm_plan_destroy(fdbm_plan* plan);
+int fdbm_plan_load_weights(fdbm_plan* plan, const fdbm_tensor_ref* tensors, int n_tensors, void* stream);
+/* bytes of device memory the plan holds (weights + activations workspace) */
+int64_t fdbm_plan_device_bytes(const fdbm_plan* plan);
+/* number of kernel launches one forward issues (for bench.py's gpu_launches) */
+int fdbm_plan_num_launches(const fdbm_plan* plan);
+
+/* One backbone forward: out = D(x, y, t).  x, y, out: cplx [B,1,257,T]; t: fp32 [B] device.
+ * Predictive plans ignore y and t (pass NULL). */
+int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
+                        void* stream);
+
+/* Whole sampler: Bridge.ode_sampler_ei / sde_sampler_ei (fdbm/bridge.py:66-113) for n_steps steps.
+ *   y     cplx [B,1,257,T]   conditioning (noisy compressed spectrogram)
+ *   x     cplx [B,1,257,T]   in: x_start (prior sample), out: final sample
+ *   times fp32 [n_steps]     device; t_prev of every step (time_steps[:-1]) -- what the backbone sees
+ *   coef  fp32 [n_steps,3]   device; coefficient table
+ *   noise cplx [n_steps, B,1,257,T] or NULL (SDE only; NULL = in-kernel Philox with `seed`)
+ * The N-step loop is captured once per (plan, n_steps, kind, pointers) as a CUDA graph and replayed. */
+int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
+                     int n_steps, int kind, const float* noise, uint64_t seed, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Building blocks, exported for the parity tests (tests/ call them one by one through ctypes).
+ * Layout of activations inside the backbone: [B, T, F, C] ("NTFC": channels innermost, then
+ * frequency, then frames) -- fp32 for the residual stream, bf16 for GEMM operands.
+ * --------------------------------------------------------------------------------------------- */
+
+/* upfirdn2d replacement (op/upfirdn2d.cpp:12-23 restricted to the two modes the model uses,
+ * up_or_down_sampling.py:195-257): separable [1,3,3,1] FIR, mode 1 = down x2, mode 2 = up x2.
+ * in fp32 [B,T,F,C] -> out fp32 [B,T',F',C]. */
+int fdbm_fir_resample(const float* in, int batch, int T, int F, int C, int mode, float* out, void* stream);
+
+/* per-(b,channel) sum / sum-of-squares of an fp32 NTFC tensor -> double [B, C, 2] (zeroed inside). */
+int fdbm_channel_stats(const float* in, int batch, int T, int F, int C, double* sums, void* stream);
+
+/* GroupNorm(min(C/4,32) groups, eps 1e-6) [+SiLU] [+FIR up/down] over the channel concatenation of
+ * up to two fp32 NTFC sources -> bf16 NTFC operand(s).  Replaces nn.GroupNorm + nn.SiLU +
+ * upsample_2d/downsample_2d + torch.cat in ResnetBlockBigGANpp.forward (layerspp.py:242-257).
+ *   act_out  bf16 [B,T',F',C1+C2]  = FIR(SiLU(GN(cat(src1,src2))))       (silu: 0/1)
+ *   raw_out  bf16 [B,T',F',C1+C2]  = FIR(cat(src1,src2)) or NULL          (operand of Conv_2) */
+int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1,
+                       const float* src2, const double* sums2, int C2,
+                       const float* gamma, const float* beta, int batch, int T, int F,
+                       int silu, int mode, void* act_out, void* raw_out, void* stream);
+
+/* Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators):
+ *   out[b,t,f,:] = scale * ( sum_taps W_tap . in1[b,t+dt,f+df,:]  (+ W2 . in2[b,t,f,:])
+ *                            + bias (+ bias_b[b,:]) (+ residual[b,t,f,:]) )
+ * Replaces nn.Conv2d 3x3 / 1x1 and NIN (layers.py:100-124, 546-555) together with the bias,
+ * time-embedding FiLM add (layerspp.py:263), shortcut add and 1/sqrt(2) rescale (:270-274).
+ *   in1   bf16 [B,T,F,C1], ksize 3 or 1;  in2 bf16 [B,T,F,C2] (1x1) or NULL
+ *   wpack bf16 packed by fdbm_pack_conv_weights;  bias fp32 [Cout];  bias_b fp32 [B,Cout] or NULL
+ *   residual fp32 [B,T,F,Cout] or NULL;  out_f32 fp32 and/or out_bf16 bf16 [B,T,F,Cout] (either may be NULL)
+ *   sums double [B,Cout,2] or NULL: receives the per-channel sum / sum of squares of the fp32 result. */
+int fdbm_conv_igemm(const void* in1, int C1, int ksize, const void* in2, int C2,
+                    const void* wpack, const float* bias, const float* bias_b, const float* residual,
+                    float scale, int batch, int T, int F, int Cout,
+                    float* out_f32, void* out_bf16, double* sums, void* stream);
+/* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
+ * -> bf16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major.  Returns bytes via *bytes when wpack==NULL. */
+int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,
+                           void* wpack, int64_t* bytes, void* stream);
+
+/* Single-head attention over all T*F positions (AttnBlockpp core, layerspp.py:82-86):
+ * q,k,v bf16 [B, L, C] (L = T*F) -> o bf16 [B, L, C], scale C^-0.5. */
+int fdbm_attention(const void* q, const void* k, const void* v, int batch, int L, int C, void* o, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FDBM_B200_H */

@@ -1,0 +1,281 @@
+// HBM-bound passes around the convolutions, all on [B,T,F,C] (channels-innermost) activations:
+//   - fir_resample      : upfirdn2d with the [1,3,3,1] kernel, x2 down / x2 up
+//                         (up_or_down_sampling.py:195-257, op/upfirdn2d_kernel.cu:107-207)
+//   - channel_stats     : per-(b,channel) sum / sum of squares (feeds GroupNorm)
+//   - groupnorm_act     : GroupNorm(eps 1e-6) [+SiLU] [+FIR up/down] of the channel concatenation of
+//                         up to two fp32 sources -> bf16 GEMM operand(s)  (layerspp.py:242-257)
+#include "common.cuh"
+
+namespace fdbm {
+namespace {
+
+// ------------------------------------------------------------------------------------------------
+// Resampling taps.  Down x2 (pad 1,1): o[i] = (x[2i-1] + 3x[2i] + 3x[2i+1] + x[2i+2]) / 8.
+// Up x2 (zero insertion, pad 2,1, gain 4): o[2i] = (x[i-1] + 3x[i]) / 4, o[2i+1] = (3x[i] + x[i+1]) / 4.
+// Samples outside the image are zero.
+// ------------------------------------------------------------------------------------------------
+struct Taps1D {
+  int n;          // number of taps
+  int pos[4];     // input positions
+  float w[4];
+};
+
+__device__ __forceinline__ Taps1D taps_for(int o, int mode) {
+  Taps1D t;
+  if (mode == 1) {            // down
+    t.n = 4;
+    t.pos[0] = 2 * o - 1; t.pos[1] = 2 * o; t.pos[2] = 2 * o + 1; t.pos[3] = 2 * o + 2;
+    t.w[0] = 0.125f; t.w[1] = 0.375f; t.w[2] = 0.375f; t.w[3] = 0.125f;
+  } else if (mode == 2) {     // up
+    const int i = o >> 1;
+    t.n = 2;
+    if (o & 1) { t.pos[0] = i; t.pos[1] = i + 1; t.w[0] = 0.75f; t.w[1] = 0.25f; }
+    else       { t.pos[0] = i - 1; t.pos[1] = i; t.w[0] = 0.25f; t.w[1] = 0.75f; }
+    t.pos[2] = t.pos[3] = -1; t.w[2] = t.w[3] = 0.f;
+  } else {
+    t.n = 1; t.pos[0] = o; t.w[0] = 1.f;
+    t.pos[1] = t.pos[2] = t.pos[3] = -1; t.w[1] = t.w[2] = t.w[3] = 0.f;
+  }
+  return t;
+}
+
+__host__ __device__ inline int out_dim(int n, int mode) { return mode == 1 ? n / 2 : (mode == 2 ? n * 2 : n); }
+
+__global__ void __launch_bounds__(256)
+fir_resample_kernel(const float* __restrict__ in, int B, int T, int F, int C, int mode, float* __restrict__ out) {
+  const int To = out_dim(T, mode), Fo = out_dim(F, mode);
+  const int64_t total = static_cast<int64_t>(B) * To * Fo * C;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int c = static_cast<int>(i % C);
+    int64_t p = i / C;
+    const int fo = static_cast<int>(p % Fo); p /= Fo;
+    const int to = static_cast<int>(p % To);
+    const int b = static_cast<int>(p / To);
+    const Taps1D tt = taps_for(to, mode), tf = taps_for(fo, mode);
+    float acc = 0.f;
+    for (int a = 0; a < tt.n; ++a) {
+      if (tt.pos[a] < 0 || tt.pos[a] >= T) continue;
+      for (int q = 0; q < tf.n; ++q) {
+        if (tf.pos[q] < 0 || tf.pos[q] >= F) continue;
+        acc += tt.w[a] * tf.w[q] * in[((static_cast<int64_t>(b) * T + tt.pos[a]) * F + tf.pos[q]) * C + c];
+      }
+    }
+    out[i] = acc;
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// channel_stats: block = 256 threads = (pixel lanes) x (C/4 float4 lanes); each block reduces a
+// contiguous run of pixels of one batch item, then adds its partial to sums[b][c][0..1] (double).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+channel_stats_kernel(const float* __restrict__ in, int64_t P, int C, int64_t px_per_block, double* __restrict__ sums) {
+  __shared__ float4 red_s[256], red_q[256];
+  const int cg = C / 4;
+  const int pl = 256 / cg;
+  const int ci = threadIdx.x % cg, pi = threadIdx.x / cg;
+  const int b = blockIdx.y;
+  const int64_t p0 = blockIdx.x * px_per_block;
+  const int64_t p1 = min(P, p0 + px_per_block);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f), q = s;
+  if (pi < pl) {
+    const float4* base = reinterpret_cast<const float4*>(in + static_cast<int64_t>(b) * P * C) + ci;
+    for (int64_t p = p0 + pi; p < p1; p += pl) {
+      const float4 v = base[p * cg];
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      q.x += v.x * v.x; q.y += v.y * v.y; q.z += v.z * v.z; q.w += v.w * v.w;
+    }
+  }
+  red_s[threadIdx.x] = s;
+  red_q[threadIdx.x] = q;
+  __syncthreads();
+  if (threadIdx.x < cg) {
+    double ds[4] = {0, 0, 0, 0}, dq[4] = {0, 0, 0, 0};
+    for (int j = 0; j < pl; ++j) {
+      const float4 a = red_s[j * cg + threadIdx.x], c2 = red_q[j * cg + threadIdx.x];
+      ds[0] += a.x; ds[1] += a.y; ds[2] += a.z; ds[3] += a.w;
+      dq[0] += c2.x; dq[1] += c2.y; dq[2] += c2.z; dq[3] += c2.w;
+    }
+    double* o = sums + (static_cast<int64_t>(b) * C + threadIdx.x * 4) * 2;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      atomicAdd(o + 2 * j, ds[j]);
+      atomicAdd(o + 2 * j + 1, dq[j]);
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// groupnorm_act
+// ------------------------------------------------------------------------------------------------
+constexpr int GN_MAXC = 512;
+
+__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
+  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+groupnorm_act_kernel(const float* __restrict__ src1, const double* __restrict__ sums1, int C1,
+                     const float* __restrict__ src2, const double* __restrict__ sums2, int C2,
+                     const float* __restrict__ gamma, const float* __restrict__ beta, int T, int F, int silu,
+                     int64_t items_per_block, uint4* __restrict__ act_out, uint4* __restrict__ raw_out) {
+  __shared__ float sA[GN_MAXC], sB[GN_MAXC];
+  __shared__ float s_mean[32], s_rstd[32];
+  const int C = C1 + C2;
+  const int b = blockIdx.y;
+  const int G = min(C / 4, 32);
+  const int cpg = C / G;
+  if (threadIdx.x < G) {
+    double s = 0, q = 0;
+    for (int j = 0; j < cpg; ++j) {
+      const int c = threadIdx.x * cpg + j;
+      const double* e = c < C1 ? sums1 + (static_cast<int64_t>(b) * C1 + c) * 2
+                               : sums2 + (static_cast<int64_t>(b) * C2 + (c - C1)) * 2;
+      s += e[0];
+      q += e[1];
+    }
+    const double cnt = static_cast<double>(cpg) * T * F;
+    const double mean = s / cnt;
+    double var = q / cnt - mean * mean;
+    if (var < 0) var = 0;
+    s_mean[threadIdx.x] = static_cast<float>(mean);
+    s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-6));
+  }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += 256) {
+    const int g = c / cpg;
+    const float a = gamma[c] * s_rstd[g];
+    sA[c] = a;
+    sB[c] = beta[c] - s_mean[g] * a;
+  }
+  __syncthreads();
+
+  const int To = out_dim(T, MODE), Fo = out_dim(F, MODE);
+  const int cg8 = C / 8;
+  const int64_t n_items = static_cast<int64_t>(To) * Fo * cg8;
+  const int64_t i0 = blockIdx.x * items_per_block;
+  const int64_t i1 = min(n_items, i0 + items_per_block);
+  const float* s1 = src1 + static_cast<int64_t>(b) * T * F * C1;
+  const float* s2 = src2 ? src2 + static_cast<int64_t>(b) * T * F * C2 : nullptr;
+  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
+    const int g8 = static_cast<int>(i % cg8);
+    const int64_t p = i / cg8;
+    const int fo = static_cast<int>(p % Fo), to = static_cast<int>(p / Fo);
+    const int c0 = g8 * 8;
+    const float* src; int Cs, cs;
+    if (c0 < C1) { src = s1; Cs = C1; cs = c0; } else { src = s2; Cs = C2; cs = c0 - C1; }
+    float a[8], bb[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { a[j] = sA[c0 + j]; bb[j] = sB[c0 + j]; }
+    float acc[8], raw[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) { acc[j] = 0.f; raw[j] = 0.f; }
+    const Taps1D tt = taps_for(to, MODE), tf = taps_for(fo, MODE);
+#pragma unroll
+    for (int u = 0; u < (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1)); ++u) {
+      if (tt.pos[u] < 0 || tt.pos[u] >= T) continue;
+#pragma unroll
+      for (int v = 0; v < (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1)); ++v) {
+        if (tf.pos[v] < 0 || tf.pos[v] >= F) continue;
+        const float w = tt.w[u] * tf.w[v];
+        const float4* ptr = reinterpret_cast<const float4*>(src + (static_cast<int64_t>(tt.pos[u]) * F + tf.pos[v]) * Cs + cs);
+        const float4 x0 = ptr[0], x1 = ptr[1];
+        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+          float y = fmaf(x[j], a[j], bb[j]);
+          if (silu) y = silu_f(y);
+          acc[j] = fmaf(w, y, acc[j]);
+          raw[j] = fmaf(w, x[j], raw[j]);
+        }
+      }
+    }
+    const int64_t o = (static_cast<int64_t>(b) * To * Fo + p) * cg8 + g8;
+    act_out[o] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
+                            pack_bf16x2(acc[6], acc[7]));
+    if (raw_out)
+      raw_out[o] = make_uint4(pack_bf16x2(raw[0], raw[1]), pack_bf16x2(raw[2], raw[3]), pack_bf16x2(raw[4], raw[5]),
+                              pack_bf16x2(raw[6], raw[7]));
+  }
+}
+
+}  // namespace
+
+int launch_fir_resample(const float* in, int B, int T, int F, int C, int mode, float* out, cudaStream_t s) {
+  const int64_t total = static_cast<int64_t>(B) * out_dim(T, mode) * out_dim(F, mode) * C;
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(num_sms()) * 16));
+  fir_resample_kernel<<<grid, 256, 0, s>>>(in, B, T, F, C, mode, out);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+int launch_channel_stats(const float* in, int B, int T, int F, int C, double* sums, cudaStream_t s) {
+  FDBM_REQUIRE(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "channel_stats: unsupported channel count %d", C);
+  FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * B * C, s));
+  const int64_t P = static_cast<int64_t>(T) * F;
+  const int pl = 256 / (C / 4);
+  // ~4 waves of blocks over the batch, at least 8 pixels per pixel-lane
+  int64_t blocks_x = std::max<int64_t>(1, (static_cast<int64_t>(num_sms()) * 8) / B);
+  blocks_x = std::min<int64_t>(blocks_x, std::max<int64_t>(1, P / (pl * 8)));
+  const int64_t ppb = ceil_div64(P, blocks_x);
+  dim3 grid(static_cast<unsigned>(ceil_div64(P, ppb)), B);
+  channel_stats_kernel<<<grid, 256, 0, s>>>(in, P, C, ppb, sums);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+int launch_groupnorm_act(const float* src1, const double* sums1, int C1, const float* src2, const double* sums2,
+                         int C2, const float* gamma, const float* beta, int B, int T, int F, int silu, int mode,
+                         __nv_bfloat16* act_out, __nv_bfloat16* raw_out, cudaStream_t s) {
+  const int C = C1 + C2;
+  FDBM_REQUIRE(C <= GN_MAXC && C1 % 8 == 0 && C2 % 8 == 0 && C % std::min(C / 4, 32) == 0,
+               "groupnorm_act: unsupported channels %d+%d", C1, C2);
+  FDBM_REQUIRE(mode >= 0 && mode <= 2, "groupnorm_act: bad mode %d", mode);
+  FDBM_REQUIRE(mode != 1 || (T % 2 == 0 && F % 2 == 0), "groupnorm_act: down-sampling needs even T, F");
+  const int64_t n_items = static_cast<int64_t>(out_dim(T, mode)) * out_dim(F, mode) * (C / 8);
+  int64_t blocks_x = std::max<int64_t>(1, (static_cast<int64_t>(num_sms()) * 8) / B);
+  blocks_x = std::min<int64_t>(blocks_x, ceil_div64(n_items, 256));
+  const int64_t ipb = ceil_div64(ceil_div64(n_items, blocks_x), 256) * 256;
+  dim3 grid(static_cast<unsigned>(ceil_div64(n_items, ipb)), B);
+  uint4* ao = reinterpret_cast<uint4*>(act_out);
+  uint4* ro = reinterpret_cast<uint4*>(raw_out);
+  if (mode == 0)
+    groupnorm_act_kernel<0><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ipb, ao, ro);
+  else if (mode == 1)
+    groupnorm_act_kernel<1><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ipb, ao, ro);
+  else
+    groupnorm_act_kernel<2><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ipb, ao, ro);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+}  // namespace fdbm
+
+using namespace fdbm;
+
+extern "C" int fdbm_fir_resample(const float* in, int batch, int T, int F, int C, int mode, float* out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(in && out && batch > 0 && T > 0 && F > 0 && C > 0, "fdbm_fir_resample: bad arguments");
+  FDBM_REQUIRE(mode == 1 || mode == 2, "fdbm_fir_resample: mode must be 1 (down) or 2 (up)");
+  FDBM_REQUIRE(mode != 1 || (T % 2 == 0 && F % 2 == 0), "fdbm_fir_resample: down-sampling needs even T, F");
+  return launch_fir_resample(in, batch, T, F, C, mode, out, as_stream(stream));
+}
+
+extern "C" int fdbm_channel_stats(const float* in, int batch, int T, int F, int C, double* sums, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(in && sums && batch > 0 && T > 0 && F > 0, "fdbm_channel_stats: bad arguments");
+  return launch_channel_stats(in, batch, T, F, C, sums, as_stream(stream));
+}
+
+extern "C" int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1, const float* src2,
+                                  const double* sums2, int C2, const float* gamma, const float* beta, int batch, int T,
+                                  int F, int silu, int mode, void* act_out, void* raw_out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(src1 && sums1 && gamma && beta && act_out && batch > 0, "fdbm_groupnorm_act: null pointer");
+  FDBM_REQUIRE((C2 == 0) == (src2 == nullptr) && (C2 == 0 || sums2), "fdbm_groupnorm_act: src2/C2 mismatch");
+  return launch_groupnorm_act(src1, sums1, C1, src2, sums2, C2, gamma, beta, batch, T, F, silu, mode,
+                              reinterpret_cast<__nv_bfloat16*>(act_out), reinterpret_cast<__nv_bfloat16*>(raw_out),
+                              as_stream(stream));
+}

@@ -1,0 +1,618 @@
+// The NCSN++ forward as a static launch plan (fdbm/backbones/ncsnpp_v2.py:241-401 and
+// ncsnpp_v2_predictive.py:222-362), plus the N-step sampler loop of fdbm/bridge.py:66-113.
+//
+// fdbm_plan_create walks the reference constructor's module list (ncsnpp_v2.py:95-239) once for a
+// fixed (batch, n_frames) and records, in execution order, every kernel launch with its buffers
+// resolved inside one device arena (first-fit with explicit frees, so the skip stack and the
+// temporaries of a residual block reuse memory).  Forward / sampler replay that list; the sampler
+// captures all N steps (backbone + bridge update) into one CUDA graph per argument set.
+#include <functional>
+#include <map>
+#include <string>
+#include <unordered_map>
+#include <vector>
+#include "common.cuh"
+
+using namespace fdbm;
+
+namespace {
+
+struct Mod {
+  enum Kind { FOURIER, LINEAR, CONV3, RES, ATTN, COMBINE, GN } kind;
+  int idx, cin, cout;
+  bool up, down;
+};
+
+struct Slot { int64_t off; int64_t numel; bool loaded; };     // fp32 parameter inside `params`
+
+struct Act {                 // one fp32 residual-stream tensor [B,T,F,C] with its channel sums
+  float* data = nullptr;
+  double* sums = nullptr;
+  int C = 0, T = 0, F = 0;
+};
+
+struct GraphKey {
+  const void* p[6]; int n_steps, kind; uint64_t seed;
+  bool operator==(const GraphKey& o) const {
+    for (int i = 0; i < 6; ++i) if (p[i] != o.p[i]) return false;
+    return n_steps == o.n_steps && kind == o.kind && seed == o.seed;
+  }
+};
+
+// first-fit arena over one cudaMalloc
+class Arena {
+ public:
+  void reset(int64_t cap) { free_.clear(); free_[0] = cap; cap_ = cap; peak_ = 0; }
+  int64_t alloc(int64_t bytes) {
+    bytes = (bytes + 1023) / 1024 * 1024;
+    for (auto it = free_.begin(); it != free_.end(); ++it) {
+      if (it->second >= bytes) {
+        const int64_t off = it->first, rest = it->second - bytes;
+        free_.erase(it);
+        if (rest) free_[off + bytes] = rest;
+        live_[off] = bytes;
+        peak_ = std::max(peak_, off + bytes);
+        return off;
+      }
+    }
+    return -1;
+  }
+  void release(int64_t off) {
+    auto it = live_.find(off);
+    if (it == live_.end()) return;
+    int64_t o = off, n = it->second;
+    live_.erase(it);
+    auto nx = free_.lower_bound(o);
+    if (nx != free_.end() && o + n == nx->first) { n += nx->second; nx = free_.erase(nx); }
+    if (nx != free_.begin()) {
+      auto pv = std::prev(nx);
+      if (pv->first + pv->second == o) { o = pv->first; n += pv->second; free_.erase(pv); }
+    }
+    free_[o] = n;
+  }
+  int64_t peak() const { return peak_; }
+ private:
+  std::map<int64_t, int64_t> free_, live_;
+  int64_t cap_ = 0, peak_ = 0;
+};
+
+__global__ void add_vec_kernel(const float* a, const float* b, float* o, int n) {
+  const int i = blockIdx.x * 256 + threadIdx.x;
+  if (i < n) o[i] = a[i] + (b ? b[i] : 0.f);
+}
+
+}  // namespace
+
+struct fdbm_plan {
+  fdbm_arch arch;
+  int B = 0, T = 0, F = 0, F_io = 257, Cin = 4;
+  std::vector<Mod> mods;
+  // parameters
+  std::unordered_map<std::string, Slot> slots;
+  int64_t params_numel = 0;
+  float* params = nullptr;            // fp32 originals + derived fp32 (combined biases)
+  __nv_bfloat16* wpacked = nullptr;   // packed conv weights
+  int64_t wpacked_bytes = 0;
+  int dense_rows = 0;
+  bool weights_ready = false;
+  // activations
+  uint8_t* arena = nullptr;
+  int64_t arena_bytes = 0;
+  // per-call arguments the recorded ops read
+  const float* cur_x = nullptr; const float* cur_y = nullptr; const float* cur_t = nullptr; int cur_t_stride = 1;
+  float* cur_out = nullptr;
+  float* d_buf = nullptr;             // backbone output inside the sampler loop
+  std::vector<std::function<int(cudaStream_t)>> ops;        // one forward
+  std::vector<std::function<int(cudaStream_t)>> pack_ops;   // weight packing after load_weights
+  int n_launches = 0;
+  // graph cache
+  bool have_graph = false; GraphKey graph_key{}; cudaGraphExec_t graph_exec = nullptr;
+};
+
+namespace {
+
+std::vector<Mod> build_modules(const fdbm_arch& a) {
+  std::vector<Mod> m;
+  auto add = [&](Mod::Kind k, int cin, int cout, bool up = false, bool down = false) {
+    m.push_back(Mod{k, static_cast<int>(m.size()), cin, cout, up, down});
+  };
+  const int nf = a.nf, C = a.predictive ? 2 : 4, L = a.n_levels;
+  if (!a.predictive) { add(Mod::FOURIER, 0, nf); add(Mod::LINEAR, 2 * nf, 4 * nf); add(Mod::LINEAR, 4 * nf, 4 * nf); }
+  add(Mod::CONV3, C, nf);
+  std::vector<int> hs_c{nf};
+  int in_ch = nf;
+  for (int lvl = 0; lvl < L; ++lvl) {
+    const int res = a.image_size >> lvl;
+    for (int b = 0; b < a.num_res_blocks; ++b) {
+      const int out_ch = nf * a.ch_mult[lvl];
+      add(Mod::RES, in_ch, out_ch);
+      in_ch = out_ch;
+      if (res == a.attn_resolution) add(Mod::ATTN, in_ch, in_ch);
+      hs_c.push_back(in_ch);
+    }
+    if (lvl != L - 1) {
+      add(Mod::RES, in_ch, in_ch, false, true);
+      add(Mod::COMBINE, C, in_ch);
+      hs_c.push_back(in_ch);
+    }
+  }
+  in_ch = hs_c.back();
+  add(Mod::RES, in_ch, in_ch); add(Mod::ATTN, in_ch, in_ch); add(Mod::RES, in_ch, in_ch);
+  for (int lvl = L - 1; lvl >= 0; --lvl) {
+    const int res = a.image_size >> lvl;
+    for (int b = 0; b < a.num_res_blocks + 1; ++b) {
+      const int out_ch = nf * a.ch_mult[lvl];
+      add(Mod::RES, in_ch + hs_c.back(), out_ch);
+      hs_c.pop_back();
+      in_ch = out_ch;
+    }
+    if (res == a.attn_resolution) add(Mod::ATTN, in_ch, in_ch);
+    add(Mod::GN, in_ch, in_ch);
+    add(Mod::CONV3, in_ch, C);
+    if (lvl != 0) add(Mod::RES, in_ch, in_ch, true, false);
+  }
+  return m;
+}
+
+struct Builder {
+  fdbm_plan* P;
+  Arena arena;
+  int64_t wp_off = 0;                  // running offset (bytes) into wpacked
+  int dense_off = 0;                   // running row offset into the Dense_0 table
+  bool dry = true;                     // first pass: sizes only
+
+  // ---------------- parameters
+  int64_t param(const std::string& name, int64_t numel) {
+    auto it = P->slots.find(name);
+    if (it != P->slots.end()) return it->second.off;
+    const int64_t off = P->params_numel;
+    P->slots[name] = Slot{off, numel, false};
+    P->params_numel += (numel + 3) / 4 * 4;              // keep every tensor 16-byte aligned
+    return off;
+  }
+  int64_t derived(int64_t numel) {                       // fp32 scratch parameter (not loaded by name)
+    const int64_t off = P->params_numel;
+    P->params_numel += (numel + 3) / 4 * 4;
+    return off;
+  }
+  float* pp(int64_t off) const { return P->params + off; }     // call OUTSIDE recorded lambdas only
+  std::string pre(const Mod& m) const { return "all_modules." + std::to_string(m.idx) + "."; }
+
+  // ---------------- activations
+  template <typename Tp> Tp* alloc(int64_t n_elems) {
+    const int64_t off = arena.alloc(n_elems * static_cast<int64_t>(sizeof(Tp)));
+    if (off < 0) return nullptr;
+    return reinterpret_cast<Tp*>(P->arena + off);
+  }
+  void release(const void* p) { if (p) arena.release(reinterpret_cast<const uint8_t*>(p) - P->arena); }
+  Act new_act(int C, int T, int F) {
+    Act a; a.C = C; a.T = T; a.F = F;
+    a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
+    a.sums = alloc<double>(static_cast<int64_t>(P->B) * C * 2);
+    return a;
+  }
+  void free_act(Act& a) { release(a.data); release(a.sums); a.data = nullptr; a.sums = nullptr; }
+
+  void op(std::function<int(cudaStream_t)> f, int launches = 1) {
+    if (dry) return;
+    P->ops.push_back(std::move(f));
+    P->n_launches += launches;
+  }
+  void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
+
+  // packed weights for conv (w1: name, C1, ksize (3, 1 or -1 = NIN [in][out])), optional fused 1x1 w2
+  __nv_bfloat16* pack(const std::string& w1, int C1, int ksize, const std::string& w2, int C2, int Cout,
+                      int rows_total = 0, int row_off = 0, __nv_bfloat16* into = nullptr) {
+    const int k = ksize == -1 ? 1 : ksize;
+    if (rows_total == 0) rows_total = Cout;
+    __nv_bfloat16* dst = into;
+    if (!dst) {
+      dst = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
+      wp_off += (conv_wpack_bytes(C1, k, C2, rows_total) + 1023) / 1024 * 1024;
+    }
+    const float* p1 = pp(param(w1, static_cast<int64_t>(Cout) * C1 * k * k));
+    const float* p2 = C2 ? pp(param(w2, static_cast<int64_t>(Cout) * C2)) : nullptr;
+    pack_op([=](cudaStream_t s) {
+      return launch_pack_conv_weights(p1, C1, ksize, p2, C2, Cout, rows_total, row_off, dst, s);
+    });
+    return dst;
+  }
+
+  // ---------------- layers
+  // ResnetBlockBigGANpp (layerspp.py:242-274) on the concatenation of x1 (and x2)
+  Act resblock(const Mod& m, const Act& x1, const Act* x2, const float* dense, int dense_stride) {
+    const int B = P->B, Cin = m.cin, Cout = m.cout;
+    const int mode = m.down ? 1 : (m.up ? 2 : 0);
+    const int T = x1.T, F = x1.F;
+    const int To = mode == 1 ? T / 2 : (mode == 2 ? T * 2 : T), Fo = mode == 1 ? F / 2 : (mode == 2 ? F * 2 : F);
+    const bool shortcut = (Cin != Cout) || m.up || m.down;
+    const std::string p = pre(m);
+    const float* g0w = pp(param(p + "GroupNorm_0.weight", Cin)); const float* g0b = pp(param(p + "GroupNorm_0.bias", Cin));
+    const float* c0b = pp(param(p + "Conv_0.bias", Cout));
+    const float* g1w = pp(param(p + "GroupNorm_1.weight", Cout)); const float* g1b = pp(param(p + "GroupNorm_1.bias", Cout));
+    const float* c1b = pp(param(p + "Conv_1.bias", Cout));
+    __nv_bfloat16* w0 = pack(p + "Conv_0.weight", Cin, 3, "", 0, Cout);
+    __nv_bfloat16* w1 = shortcut ? pack(p + "Conv_1.weight", Cout, 3, p + "Conv_2.weight", Cin, Cout)
+                                 : pack(p + "Conv_1.weight", Cout, 3, "", 0, Cout);
+    const float* bias1 = c1b;
+    if (shortcut) {                                   // Conv_1.bias + Conv_2.bias, summed once at load time
+      const float* c2b = pp(param(p + "Conv_2.bias", Cout));
+      float* bsum = pp(derived(Cout));
+      bias1 = bsum;
+      pack_op([=](cudaStream_t s) {
+        add_vec_kernel<<<ceil_div(Cout, 256), 256, 0, s>>>(c1b, c2b, bsum, Cout);
+        FDBM_LAUNCH_CHECK();
+        return FDBM_OK;
+      });
+    }
+    int dense_row = -1;
+    if (!P->arch.predictive) {
+      param(p + "Dense_0.weight", static_cast<int64_t>(Cout) * 4 * P->arch.nf);   // slots are laid out by build_dense()
+      dense_row = dense_off;
+      dense_off += Cout;
+    }
+
+    const int64_t npx = static_cast<int64_t>(B) * To * Fo;
+    __nv_bfloat16* a0 = alloc<__nv_bfloat16>(npx * Cin);
+    __nv_bfloat16* xr = shortcut ? alloc<__nv_bfloat16>(npx * Cin) : nullptr;
+    {
+      const float* s1 = x1.data; const double* q1 = x1.sums; const int C1 = x1.C;
+      const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr; const int C2 = x2 ? x2->C : 0;
+      op([=](cudaStream_t s) {
+        return launch_groupnorm_act(s1, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
+      });
+    }
+    Act h1 = new_act(Cout, To, Fo);
+    {
+      ConvArgs c{};
+      c.in1 = a0; c.C1 = Cin; c.ksize = 3; c.in2 = nullptr; c.C2 = 0; c.wpack = w0;
+      c.bias = c0b; c.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c.bias_b_stride = dense_stride;
+      c.residual = nullptr; c.scale = 1.0f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
+      c.out_f32 = h1.data; c.out_bf16 = nullptr; c.out_ld = Cout; c.sums = h1.sums;
+      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, 2);
+    }
+    release(a0);
+    __nv_bfloat16* a1 = alloc<__nv_bfloat16>(npx * Cout);
+    {
+      const float* s1 = h1.data; const double* q1 = h1.sums;
+      op([=](cudaStream_t s) {
+        return launch_groupnorm_act(s1, q1, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, a1, nullptr, s);
+      });
+    }
+    Act out = new_act(Cout, To, Fo);
+    {
+      ConvArgs c{};
+      c.in1 = a1; c.C1 = Cout; c.ksize = 3; c.in2 = xr; c.C2 = shortcut ? Cin : 0; c.wpack = w1;
+      c.bias = bias1; c.bias_b = nullptr; c.bias_b_stride = 0; c.residual = shortcut ? nullptr : x1.data;
+      c.scale = 0.70710678118654752f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
+      c.out_f32 = out.data; c.out_bf16 = nullptr; c.out_ld = Cout; c.sums = out.sums;
+      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, 2);
+    }
+    free_act(h1);
+    release(a1);
+    release(xr);
+    return out;
+  }
+
+  // AttnBlockpp (layerspp.py:75-91)
+  Act attn(const Mod& m, const Act& x) {
+    const int B = P->B, C = m.cin, T = x.T, F = x.F;
+    const std::string p = pre(m);
+    const float* gw = pp(param(p + "GroupNorm_0.weight", C)); const float* gb = pp(param(p + "GroupNorm_0.bias", C));
+    // q, k, v projections as one GEMM with 3C outputs; biases are three consecutive slots
+    const float* bq = pp(param(p + "NIN_0.b", C));
+    param(p + "NIN_1.b", C); param(p + "NIN_2.b", C);
+    const float* b3 = pp(param(p + "NIN_3.b", C));
+    __nv_bfloat16* wqkv = pack(p + "NIN_0.W", C, -1, "", 0, C, 3 * C, 0);
+    pack(p + "NIN_1.W", C, -1, "", 0, C, 3 * C, C, wqkv);
+    pack(p + "NIN_2.W", C, -1, "", 0, C, 3 * C, 2 * C, wqkv);
+    __nv_bfloat16* w3 = pack(p + "NIN_3.W", C, -1, "", 0, C);
+    const int64_t npx = static_cast<int64_t>(B) * T * F;
+    __nv_bfloat16* a = alloc<__nv_bfloat16>(npx * C);
+    {
+      const float* s1 = x.data; const double* q1 = x.sums;
+      op([=](cudaStream_t s) {
+        return launch_groupnorm_act(s1, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, a, nullptr, s);
+      });
+    }
+    __nv_bfloat16* qkv = alloc<__nv_bfloat16>(npx * 3 * C);
+    {
+      ConvArgs c{};
+      c.in1 = a; c.C1 = C; c.ksize = 1; c.wpack = wqkv; c.bias = bq; c.scale = 1.0f; c.B = B; c.T = T; c.F = F; c.Cout = 3 * C;
+      c.out_bf16 = qkv; c.out_ld = 3 * C;
+      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); });
+    }
+    release(a);
+    __nv_bfloat16* o = alloc<__nv_bfloat16>(npx * C);
+    op([=](cudaStream_t s) { return launch_attention(qkv, qkv + C, qkv + 2 * C, 3 * C, B, T * F, C, o, C, s); });
+    release(qkv);
+    Act out = new_act(C, T, F);
+    {
+      ConvArgs c{};
+      c.in1 = o; c.C1 = C; c.ksize = 1; c.wpack = w3; c.bias = b3; c.residual = x.data; c.scale = 0.70710678118654752f;
+      c.B = B; c.T = T; c.F = F; c.Cout = C; c.out_f32 = out.data; c.out_ld = C; c.sums = out.sums;
+      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, 2);
+    }
+    release(o);
+    return out;
+  }
+
+  int build() {
+    fdbm_plan& pl = *P;
+    const fdbm_arch& A = pl.arch;
+    const int B = pl.B, nf = A.nf, Cp = pl.Cin, L = A.n_levels;
+    size_t mi = 0;
+    auto next = [&]() -> const Mod& { return pl.mods[mi++]; };
+    wp_off = 0; dense_off = 0;
+
+    // ---- time embedding + all Dense_0 projections (one table [B, dense_rows])
+    float* temb_act = nullptr; float* dense = nullptr;
+    if (!A.predictive) {
+      const Mod& mf = next(); const Mod& l1 = next(); const Mod& l2 = next();
+      const float* fw = pp(param(pre(mf) + "W", nf));
+      const float* w1 = pp(param(pre(l1) + "weight", static_cast<int64_t>(4 * nf) * 2 * nf)); const float* b1 = pp(param(pre(l1) + "bias", 4 * nf));
+      const float* w2 = pp(param(pre(l2) + "weight", static_cast<int64_t>(4 * nf) * 4 * nf)); const float* b2 = pp(param(pre(l2) + "bias", 4 * nf));
+      // Dense_0 weights / biases of all residual blocks, contiguous and in execution order
+      int rows = 0; int64_t dw0 = -1, db0 = -1;
+      for (const Mod& m : pl.mods) if (m.kind == Mod::RES) {
+        const int64_t o = param(pre(m) + "Dense_0.weight", static_cast<int64_t>(m.cout) * 4 * nf);
+        if (dw0 < 0) dw0 = o;
+        rows += m.cout;
+      }
+      for (const Mod& m : pl.mods) if (m.kind == Mod::RES) {
+        const int64_t o = param(pre(m) + "Dense_0.bias", m.cout);
+        if (db0 < 0) db0 = o;
+      }
+      pl.dense_rows = rows;
+      temb_act = alloc<float>(static_cast<int64_t>(B) * 4 * nf);
+      dense = alloc<float>(static_cast<int64_t>(B) * rows);
+      const float* dwp = pp(dw0); const float* dbp = pp(db0);
+      fdbm_plan* plp = P;
+      op([=](cudaStream_t s) {
+        return launch_temb(plp->cur_t, fw, nf, w1, b1, w2, b2, B, plp->cur_t_stride, temb_act, s);
+      });
+      op([=](cudaStream_t s) { return launch_dense_all(temb_act, dwp, dbp, B, 4 * nf, rows, dense, s); });
+    }
+    const int dstride = pl.dense_rows;
+
+    // ---- input packing and first convolution
+    int T = pl.T, F = pl.F;
+    float* pyr_in = alloc<float>(static_cast<int64_t>(B) * T * F * Cp);
+    {
+      fdbm_plan* plp = P; const int Tc = T, Fc = F; float* dst = pyr_in; const bool pred = A.predictive;
+      op([=](cudaStream_t s) { return launch_pack_input(plp->cur_x, pred ? nullptr : plp->cur_y, B, Tc, plp->F_io, Fc, Cp, dst, s); });
+    }
+    std::vector<Act> hs;
+    {
+      const Mod& m = next();
+      const float* w = pp(param(pre(m) + "weight", static_cast<int64_t>(nf) * Cp * 9)); const float* b = pp(param(pre(m) + "bias", nf));
+      Act h0 = new_act(nf, T, F);
+      const int Tc = T, Fc = F; float* src = pyr_in;
+      op([=](cudaStream_t s) {
+        if (int rc = launch_conv_in(src, Cp, w, b, B, Tc, Fc, nf, h0.data, s)) return rc;
+        return launch_channel_stats(h0.data, B, Tc, Fc, nf, h0.sums, s);
+      }, 2);
+      hs.push_back(h0);
+    }
+    // ---- down path
+    for (int lvl = 0; lvl < L; ++lvl) {
+      for (int blk = 0; blk < A.num_res_blocks; ++blk) {
+        Act h = resblock(next(), hs.back(), nullptr, dense, dstride);
+        if (h.F == A.attn_resolution) { Act h2 = attn(next(), h); free_act(h); h = h2; }
+        hs.push_back(h);
+      }
+      if (lvl != L - 1) {
+        Act h = resblock(next(), hs.back(), nullptr, dense, dstride);
+        float* pyr_next = alloc<float>(static_cast<int64_t>(B) * (T / 2) * (F / 2) * Cp);
+        {
+          const int Tc = T, Fc = F; float* src = pyr_in;
+          op([=](cudaStream_t s) { return launch_fir_resample(src, B, Tc, Fc, Cp, 1, pyr_next, s); });
+        }
+        release(pyr_in);
+        pyr_in = pyr_next;
+        T /= 2; F /= 2;
+        const Mod& m = next();
+        const float* w = pp(param(pre(m) + "Conv_0.weight", static_cast<int64_t>(m.cout) * Cp)); const float* b = pp(param(pre(m) + "Conv_0.bias", m.cout));
+        {
+          const int Tc = T, Fc = F, C = m.cout; float* src = pyr_in;
+          op([=](cudaStream_t s) {
+            if (int rc = launch_combine(h.data, src, Cp, w, b, B, Tc, Fc, C, s)) return rc;
+            return launch_channel_stats(h.data, B, Tc, Fc, C, h.sums, s);
+          }, 2);
+        }
+        hs.push_back(h);
+      }
+    }
+    release(pyr_in);
+    // ---- bottleneck
+    Act h = hs.back();                      // still owned by the skip stack
+    {
+      Act a = resblock(next(), h, nullptr, dense, dstride);
+      Act b2 = attn(next(), a); free_act(a);
+      Act c = resblock(next(), b2, nullptr, dense, dstride); free_act(b2);
+      h = c;
+    }
+    // ---- up path
+    float* pyramid = nullptr;
+    for (int lvl = L - 1; lvl >= 0; --lvl) {
+      for (int blk = 0; blk < A.num_res_blocks + 1; ++blk) {
+        Act skip = hs.back(); hs.pop_back();
+        Act o = resblock(next(), h, &skip, dense, dstride);
+        free_act(h); free_act(skip);
+        h = o;
+      }
+      if (h.F == A.attn_resolution) { Act h2 = attn(next(), h); free_act(h); h = h2; }
+      {
+        const Mod& mg = next(); const Mod& mc = next();
+        const int C = mg.cin, Tc = h.T, Fc = h.F;
+        const float* gw = pp(param(pre(mg) + "weight", C)); const float* gb = pp(param(pre(mg) + "bias", C));
+        const float* w = pp(param(pre(mc) + "weight", static_cast<int64_t>(Cp) * C * 9)); const float* b = pp(param(pre(mc) + "bias", Cp));
+        __nv_bfloat16* a = alloc<__nv_bfloat16>(static_cast<int64_t>(B) * Tc * Fc * C);
+        float* pyr_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
+        float* prev = pyramid;
+        const float* src = h.data; const double* sums = h.sums;
+        op([=](cudaStream_t s) {
+          if (int rc = launch_groupnorm_act(src, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s)) return rc;
+          return launch_pyramid_conv(a, C, w, b, prev, Cp, B, Tc, Fc, pyr_new, s);
+        }, 2);
+        release(a);
+        release(pyramid);
+        pyramid = pyr_new;
+      }
+      if (lvl != 0) { Act o = resblock(next(), h, nullptr, dense, dstride); free_act(h); h = o; }
+    }
+    free_act(h);
+    if (mi != pl.mods.size() || !hs.empty()) { set_error("plan: module walk out of sync (%zu of %zu)", mi, pl.mods.size()); return FDBM_EINVAL; }
+    {
+      const float* w = pp(param("output_layer.weight", 2 * Cp)); const float* b = pp(param("output_layer.bias", 2));
+      const int Tc = pl.T, Fc = pl.F; fdbm_plan* plp = P; float* pyr = pyramid;
+      op([=](cudaStream_t s) { return launch_output_layer(pyr, Cp, w, b, B, Tc, Fc, plp->F_io, plp->cur_out, s); });
+    }
+    release(pyramid);
+    return FDBM_OK;
+  }
+};
+
+int run_ops(fdbm_plan* plan, cudaStream_t s) {
+  for (auto& f : plan->ops) if (int rc = f(s)) return rc;
+  return FDBM_OK;
+}
+
+}  // namespace
+
+extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(arch && out, "fdbm_plan_create: null pointer");
+  FDBM_REQUIRE(batch > 0 && n_frames > 0, "fdbm_plan_create: batch and n_frames must be positive");
+  FDBM_REQUIRE(arch->n_levels >= 1 && arch->n_levels <= 8, "fdbm_plan_create: n_levels out of range");
+  FDBM_REQUIRE(arch->nf % 64 == 0 && arch->nf >= 128, "fdbm_plan_create: nf must be a multiple of 64 and >= 128 (got %d)", arch->nf);
+  FDBM_REQUIRE(arch->image_size == 256, "fdbm_plan_create: image_size must be 256 (n_fft = 512 with the Nyquist bin dropped)");
+  const int down = 1 << (arch->n_levels - 1);
+  FDBM_REQUIRE(n_frames % down == 0, "fdbm_plan_create: n_frames %d must be a multiple of %d (pad_spec pads to 64)", n_frames, down);
+  for (int i = 0; i < arch->n_levels; ++i)
+    FDBM_REQUIRE((arch->nf * arch->ch_mult[i]) % 128 == 0, "fdbm_plan_create: level %d channel count must be a multiple of 128", i);
+
+  fdbm_plan* P = new fdbm_plan();
+  P->arch = *arch; P->B = batch; P->T = n_frames; P->F = arch->image_size; P->F_io = arch->image_size + 1;
+  P->Cin = arch->predictive ? 2 : 4;
+  P->mods = build_modules(*arch);
+  auto fail = [&](int rc) { fdbm_plan_destroy(P); return rc; };
+
+  // pass 1 (dry): sizes.  A 1 TiB virtual arena never fails; its peak is the real requirement.
+  Builder b1{P};
+  b1.dry = true;
+  P->arena = reinterpret_cast<uint8_t*>(uintptr_t(1) << 30);      // fake non-null base for the sizing pass
+  b1.arena.reset(int64_t(1) << 40);
+  if (int rc = b1.build()) return fail(rc);
+  P->arena_bytes = b1.arena.peak();
+  P->arena = nullptr;
+  P->wpacked_bytes = b1.wp_off;
+  const int64_t params_numel = P->params_numel;
+  // d_buf for the sampler
+  const int64_t spec_elems = static_cast<int64_t>(batch) * P->F_io * n_frames * 2;
+  cudaError_t e;
+  if ((e = cudaMalloc(&P->arena, P->arena_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(arena)", __FILE__, __LINE__));
+  if ((e = cudaMalloc(&P->params, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(params)", __FILE__, __LINE__));
+  if ((e = cudaMalloc(&P->wpacked, P->wpacked_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wpacked)", __FILE__, __LINE__));
+  if ((e = cudaMalloc(&P->d_buf, spec_elems * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(d_buf)", __FILE__, __LINE__));
+  if ((e = cudaMemset(P->params, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+
+  // pass 2: identical walk, now recording launches against real addresses
+  P->params_numel = 0;
+  P->slots.clear();
+  Builder b2{P};
+  b2.dry = false;
+  b2.arena.reset(P->arena_bytes);
+  if (int rc = b2.build()) return fail(rc);
+  if (P->params_numel != params_numel || b2.wp_off != P->wpacked_bytes) {
+    set_error("plan: second pass diverged from the sizing pass");
+    return fail(FDBM_EINVAL);
+  }
+  *out = P;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_destroy(fdbm_plan* plan) {
+  if (!plan) return FDBM_OK;
+  if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+  cudaFree(plan->arena); cudaFree(plan->params); cudaFree(plan->wpacked); cudaFree(plan->d_buf);
+  delete plan;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_load_weights(fdbm_plan* plan, const fdbm_tensor_ref* tensors, int n_tensors, void* stream) {
+  FDBM_REQUIRE(plan && tensors && n_tensors > 0, "fdbm_plan_load_weights: bad arguments");
+  cudaStream_t s = as_stream(stream);
+  for (int i = 0; i < n_tensors; ++i) {
+    FDBM_REQUIRE(tensors[i].name && tensors[i].data, "fdbm_plan_load_weights: tensor %d has a null field", i);
+    auto it = plan->slots.find(tensors[i].name);
+    FDBM_REQUIRE(it != plan->slots.end(), "fdbm_plan_load_weights: unexpected tensor '%s'", tensors[i].name);
+    FDBM_REQUIRE(it->second.numel == tensors[i].numel, "fdbm_plan_load_weights: '%s' has %lld elements, expected %lld",
+                 tensors[i].name, (long long)tensors[i].numel, (long long)it->second.numel);
+    FDBM_CUDA(cudaMemcpyAsync(plan->params + it->second.off, tensors[i].data, sizeof(float) * tensors[i].numel,
+                              cudaMemcpyDeviceToDevice, s));
+    it->second.loaded = true;
+  }
+  for (auto& kv : plan->slots)
+    FDBM_REQUIRE(kv.second.loaded, "fdbm_plan_load_weights: tensor '%s' was never provided", kv.first.c_str());
+  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
+  plan->weights_ready = true;
+  return FDBM_OK;
+}
+
+extern "C" int64_t fdbm_plan_device_bytes(const fdbm_plan* plan) {
+  if (!plan) return 0;
+  return plan->arena_bytes + plan->params_numel * 4 + plan->wpacked_bytes +
+         static_cast<int64_t>(plan->B) * plan->F_io * plan->T * 8;
+}
+
+extern "C" int fdbm_plan_num_launches(const fdbm_plan* plan) { return plan ? plan->n_launches : 0; }
+
+extern "C" int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
+                                   void* stream) {
+  FDBM_REQUIRE(plan && x && out, "fdbm_ncsnpp_forward: null pointer");
+  if (!plan->weights_ready) { set_error("fdbm_ncsnpp_forward: weights not loaded"); return FDBM_ESTATE; }
+  FDBM_REQUIRE(plan->arch.predictive || (y && t), "fdbm_ncsnpp_forward: y and t are required");
+  plan->cur_x = x; plan->cur_y = y; plan->cur_t = t; plan->cur_t_stride = 1; plan->cur_out = out;
+  return run_ops(plan, as_stream(stream));
+}
+
+extern "C" int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
+                                int n_steps, int kind, const float* noise, uint64_t seed, void* stream) {
+  FDBM_REQUIRE(plan && y && x && times && coef && n_steps > 0, "fdbm_sampler_run: bad arguments");
+  FDBM_REQUIRE(!plan->arch.predictive, "fdbm_sampler_run: predictive plans have no sampling loop");
+  FDBM_REQUIRE(kind == FDBM_STEP_ODE || kind == FDBM_STEP_SDE, "fdbm_sampler_run: bad kind");
+  if (!plan->weights_ready) { set_error("fdbm_sampler_run: weights not loaded"); return FDBM_ESTATE; }
+  cudaStream_t s = as_stream(stream);
+  const int64_t n_complex = static_cast<int64_t>(plan->B) * plan->F_io * plan->T;
+  auto body = [&](cudaStream_t st) -> int {
+    for (int i = 0; i < n_steps; ++i) {
+      plan->cur_x = x; plan->cur_y = y; plan->cur_t = times + i; plan->cur_t_stride = 0; plan->cur_out = plan->d_buf;
+      if (int rc = run_ops(plan, st)) return rc;
+      const float* third = kind == FDBM_STEP_ODE ? y : (noise ? noise + 2 * n_complex * i : nullptr);
+      if (int rc = fdbm_bridge_step(x, plan->d_buf, third, coef + 3 * i, kind, seed, static_cast<uint64_t>(i) + 1,
+                                    n_complex, st))
+        return rc;
+    }
+    return FDBM_OK;
+  };
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  FDBM_CUDA(cudaStreamIsCapturing(s, &cap));
+  if (cap != cudaStreamCaptureStatusNone) return body(s);          // caller is capturing: just record into it
+  GraphKey key{{y, x, times, coef, noise, nullptr}, n_steps, kind, seed};
+  if (!(plan->have_graph && plan->graph_key == key)) {
+    if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; plan->have_graph = false; }
+    cudaGraph_t graph = nullptr;
+    FDBM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
+    const int rc = body(s);
+    const cudaError_t e = cudaStreamEndCapture(s, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    const cudaError_t e2 = cudaGraphInstantiate(&plan->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
+    plan->graph_key = key; plan->have_graph = true;
+  }
+  FDBM_CUDA(cudaGraphLaunch(plan->graph_exec, s));
+  return FDBM_OK;
+}

@@ -1,0 +1,98 @@
+"""ctypes binding of libfdbm_b200.so (the C ABI declared in include/fdbm_b200.h).
+
+There is no fallback: if the shared library is missing or a call fails, a RuntimeError is raised
+(mirrors the TORCH_CHECK behaviour of the reference's only native op, op/upfirdn2d.cpp:8-16).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libfdbm_b200.so")
+
+FDBM_PAD = {"zero_pad": 0, "reflection": 1, "replication": 2}
+FDBM_TRANSFORM = {"exponent": 0, "log": 1, "none": 2}
+FDBM_STEP = {"ode_ei": 0, "sde_ei": 1}
+
+# every symbol include/fdbm_b200.h declares; tests/test_abi.py checks the library exports all of them
+EXPORTS = [
+    "fdbm_last_error", "fdbm_version", "fdbm_check_device",
+    "fdbm_stft_compress", "fdbm_decompress_istft", "fdbm_spec_transform", "fdbm_pad_spec",
+    "fdbm_prior_sample", "fdbm_bridge_step",
+    "fdbm_plan_create", "fdbm_plan_destroy", "fdbm_plan_load_weights", "fdbm_plan_device_bytes",
+    "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run",
+    "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm",
+    "fdbm_pack_conv_weights", "fdbm_attention",
+]
+
+
+class TensorRef(C.Structure):
+    _fields_ = [("name", C.c_char_p), ("data", C.c_void_p), ("numel", C.c_int64)]
+
+
+class Arch(C.Structure):
+    _fields_ = [("nf", C.c_int), ("n_levels", C.c_int), ("ch_mult", C.c_int * 8), ("num_res_blocks", C.c_int),
+                ("attn_resolution", C.c_int), ("predictive", C.c_int), ("image_size", C.c_int)]
+
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    """Load the shared library once.  Raises RuntimeError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(or `make -C <package>/csrc`).  fdbm_b200 has no CPU or PyTorch fallback.")
+    lib = C.CDLL(LIB_PATH)
+    p, i, i64, f, u64 = C.c_void_p, C.c_int, C.c_int64, C.c_float, C.c_uint64
+    sig = {
+        "fdbm_last_error": (C.c_char_p, []),
+        "fdbm_version": (i, []),
+        "fdbm_check_device": (i, []),
+        "fdbm_stft_compress": (i, [p, i, i64, i64, p, i, i, i, f, f, i, i, p, p]),
+        "fdbm_decompress_istft": (i, [p, i, i, p, i, i, i, f, f, i64, i64, p, p]),
+        "fdbm_spec_transform": (i, [p, p, i64, i, f, f, i, p]),
+        "fdbm_pad_spec": (i, [p, i64, i, i, i, p, p]),
+        "fdbm_prior_sample": (i, [p, p, f, f, u64, u64, i64, p, p]),
+        "fdbm_bridge_step": (i, [p, p, p, p, i, u64, u64, i64, p]),
+        "fdbm_plan_create": (i, [C.POINTER(Arch), i, i, C.POINTER(p)]),
+        "fdbm_plan_destroy": (i, [p]),
+        "fdbm_plan_load_weights": (i, [p, C.POINTER(TensorRef), i, p]),
+        "fdbm_plan_device_bytes": (i64, [p]),
+        "fdbm_plan_num_launches": (i, [p]),
+        "fdbm_ncsnpp_forward": (i, [p, p, p, p, p, p]),
+        "fdbm_sampler_run": (i, [p, p, p, p, p, i, i, p, u64, p]),
+        "fdbm_fir_resample": (i, [p, i, i, i, i, i, p, p]),
+        "fdbm_channel_stats": (i, [p, i, i, i, i, p, p]),
+        "fdbm_groupnorm_act": (i, [p, p, i, p, p, i, p, p, i, i, i, i, i, p, p, p]),
+        "fdbm_conv_igemm": (i, [p, i, i, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
+        "fdbm_pack_conv_weights": (i, [p, i, i, p, i, i, p, C.POINTER(i64), p]),
+        "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
+    }
+    for name, (res, args) in sig.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    _lib = lib
+    return lib
+
+
+def check(rc: int, what: str = "fdbm") -> None:
+    if rc != 0:
+        msg = load().fdbm_last_error()
+        raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def ptr(t) -> int:
+    """Device pointer of a torch tensor (None -> NULL)."""
+    return None if t is None else t.data_ptr()
+
+
+def current_stream() -> int:
+    import torch
+    return torch.cuda.current_stream().cuda_stream

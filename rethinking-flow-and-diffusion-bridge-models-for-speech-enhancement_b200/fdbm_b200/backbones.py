@@ -1,0 +1,258 @@
+"""NCSN++ backbones behind the reference's BackboneRegistry API.
+
+`BackboneRegistry.get_by_name("ncsnpp_v2")(**kwargs)` returns an nn.Module whose parameters have
+the reference's names and shapes (`all_modules.<i>.<Layer>.weight`, `output_layer.*`; 647 tensors for
+the default model) so reference checkpoints load unchanged, and whose `forward(x, y, t)` /
+`forward(y)` (predictive) runs the whole U-Net in libfdbm_b200 (fdbm/backbones/ncsnpp_v2.py:36-401,
+ncsnpp_v2_predictive.py:36-362).  The module itself holds no arithmetic: it owns the parameters and
+a cache of C-side plans keyed by (batch, n_frames); packed weights are refreshed whenever a
+parameter's version counter changes (optimizer step, EMA swap -- fdbm/model.py:146-160).
+
+Inference only in this round: forward runs under no_grad semantics (outputs carry no autograd graph).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import _lib
+from ._lib import Arch, TensorRef, check, current_stream, ptr
+from .registry import BackboneRegistry
+
+
+def _module_table(nf, ch_mult, num_res_blocks, attn_resolutions, image_size, predictive):
+    """(kind, cin, cout, up, down) per entry of the reference's `all_modules` (ncsnpp_v2.py:95-239)."""
+    mods = []
+    C_io = 2 if predictive else 4
+    if not predictive:
+        mods += [("fourier", 0, nf, False, False), ("linear", 2 * nf, 4 * nf, False, False),
+                 ("linear", 4 * nf, 4 * nf, False, False)]
+    mods.append(("conv3", C_io, nf, False, False))
+    hs_c, in_ch, L = [nf], nf, len(ch_mult)
+    for lvl in range(L):
+        for _ in range(num_res_blocks):
+            out_ch = nf * ch_mult[lvl]
+            mods.append(("res", in_ch, out_ch, False, False))
+            in_ch = out_ch
+            if image_size // (2 ** lvl) in attn_resolutions:
+                mods.append(("attn", in_ch, in_ch, False, False))
+            hs_c.append(in_ch)
+        if lvl != L - 1:
+            mods.append(("res", in_ch, in_ch, False, True))
+            mods.append(("combine", C_io, in_ch, False, False))
+            hs_c.append(in_ch)
+    in_ch = hs_c[-1]
+    mods += [("res", in_ch, in_ch, False, False), ("attn", in_ch, in_ch, False, False), ("res", in_ch, in_ch, False, False)]
+    for lvl in reversed(range(L)):
+        for _ in range(num_res_blocks + 1):
+            out_ch = nf * ch_mult[lvl]
+            mods.append(("res", in_ch + hs_c.pop(), out_ch, False, False))
+            in_ch = out_ch
+        if image_size // (2 ** lvl) in attn_resolutions:
+            mods.append(("attn", in_ch, in_ch, False, False))
+        mods.append(("gn", in_ch, in_ch, False, False))
+        mods.append(("conv3", in_ch, C_io, False, False))
+        if lvl != 0:
+            mods.append(("res", in_ch, in_ch, True, False))
+    assert not hs_c
+    return mods
+
+
+def _fan_avg_uniform(shape, scale=1.0):
+    """default_init (layers.py:54-91): variance_scaling(scale, 'fan_avg', 'uniform'), scale 0 -> 1e-10."""
+    scale = 1e-10 if scale == 0 else scale
+    rf = np.prod(shape) / shape[0] / shape[1]
+    var = scale / ((shape[1] * rf + shape[0] * rf) / 2)
+    return (torch.rand(*shape) * 2.0 - 1.0) * math.sqrt(3 * var)
+
+
+class _Holder(nn.Module):
+    """Parameter container; sub-holders are created on demand so dotted names match the reference."""
+
+    def add(self, dotted, tensor, requires_grad=True):
+        head, _, rest = dotted.partition(".")
+        if rest:
+            if not hasattr(self, head):
+                self.add_module(head, _Holder())
+            getattr(self, head).add(rest, tensor, requires_grad)
+        else:
+            self.register_parameter(head, nn.Parameter(tensor, requires_grad=requires_grad))
+
+
+class _NCSNppBase(nn.Module):
+    predictive = False
+
+    @staticmethod
+    def add_argparse_args(parser):
+        parser.add_argument("--nf", type=int, default=128)
+        parser.add_argument("--ch_mult", type=int, nargs="+", default=[1, 1, 2, 2, 2, 2, 2])
+        parser.add_argument("--num_res_blocks", type=int, default=2)
+        parser.add_argument("--attn_resolutions", type=int, nargs="+", default=[16])
+        return parser
+
+    def __init__(self, nf=128, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=(16,),
+                 init_scale=0.0, fourier_scale=16, image_size=256, **unused_kwargs):
+        super().__init__()
+        for key, want in (("nonlinearity", "swish"), ("resblock_type", "biggan"), ("progressive", "output_skip"),
+                          ("progressive_input", "input_skip"), ("progressive_combine", "sum"),
+                          ("embedding_type", "fourier"), ("fir", True), ("skip_rescale", True)):
+            if key in unused_kwargs and unused_kwargs[key] != want:
+                raise NotImplementedError(f"fdbm_b200 implements the reference's default NCSN++ variant only ({key}={want!r})")
+        attn = [r for r in attn_resolutions if r > 0]
+        if len(attn) > 1:
+            raise NotImplementedError("at most one attention resolution is supported")
+        self.nf, self.ch_mult, self.num_res_blocks = nf, tuple(ch_mult), num_res_blocks
+        self.attn_resolutions, self.image_size = tuple(attn), image_size
+        self.num_resolutions = len(ch_mult)
+        self._table = _module_table(nf, self.ch_mult, num_res_blocks, self.attn_resolutions, image_size, self.predictive)
+        C_io = 2 if self.predictive else 4
+
+        # parameters, with the reference's initialisation (ncsnpp_v2.py:93-239, layerspp.py, layers.py:88-124)
+        self.output_layer = nn.Conv2d(C_io, 2, 1)
+        holders = []
+        for kind, cin, cout, up, down in self._table:
+            h = _Holder()
+            if kind == "fourier":
+                h.add("W", torch.randn(cout) * fourier_scale, requires_grad=False)
+            elif kind == "linear":
+                h.add("weight", _fan_avg_uniform((cout, cin))); h.add("bias", torch.zeros(cout))
+            elif kind == "conv3":
+                scale = init_scale if cout == C_io else 1.0        # pyramid output convs use init_scale
+                h.add("weight", _fan_avg_uniform((cout, cin, 3, 3), scale)); h.add("bias", torch.zeros(cout))
+            elif kind == "gn":
+                h.add("weight", torch.ones(cin)); h.add("bias", torch.zeros(cin))
+            elif kind == "combine":
+                h.add("Conv_0.weight", _fan_avg_uniform((cout, cin, 1, 1))); h.add("Conv_0.bias", torch.zeros(cout))
+            elif kind == "attn":
+                h.add("GroupNorm_0.weight", torch.ones(cin)); h.add("GroupNorm_0.bias", torch.zeros(cin))
+                for i in range(4):
+                    h.add(f"NIN_{i}.W", _fan_avg_uniform((cin, cin), init_scale if i == 3 else 0.1))
+                    h.add(f"NIN_{i}.b", torch.zeros(cin))
+            elif kind == "res":
+                h.add("GroupNorm_0.weight", torch.ones(cin)); h.add("GroupNorm_0.bias", torch.zeros(cin))
+                h.add("Conv_0.weight", _fan_avg_uniform((cout, cin, 3, 3))); h.add("Conv_0.bias", torch.zeros(cout))
+                if not self.predictive:
+                    h.add("Dense_0.weight", _fan_avg_uniform((cout, 4 * nf))); h.add("Dense_0.bias", torch.zeros(cout))
+                h.add("GroupNorm_1.weight", torch.ones(cout)); h.add("GroupNorm_1.bias", torch.zeros(cout))
+                h.add("Conv_1.weight", _fan_avg_uniform((cout, cout, 3, 3), init_scale)); h.add("Conv_1.bias", torch.zeros(cout))
+                if cin != cout or up or down:
+                    h.add("Conv_2.weight", _fan_avg_uniform((cout, cin, 1, 1))); h.add("Conv_2.bias", torch.zeros(cout))
+            holders.append(h)
+        self.all_modules = nn.ModuleList(holders)
+        self._plans = {}          # (device index, batch, n_frames) -> [plan handle, weight version]
+
+    # ---- plan / weight management --------------------------------------------------------------
+    def _arch(self) -> Arch:
+        a = Arch()
+        a.nf, a.n_levels, a.num_res_blocks = self.nf, len(self.ch_mult), self.num_res_blocks
+        for i, m in enumerate(self.ch_mult):
+            a.ch_mult[i] = m
+        a.attn_resolution = self.attn_resolutions[0] if self.attn_resolutions else 0
+        a.predictive, a.image_size = int(self.predictive), self.image_size
+        return a
+
+    def _weight_version(self) -> int:
+        return sum(p._version for p in self.parameters()) + sum(p.data_ptr() % 65537 for p in self.parameters())
+
+    def _plan(self, device, batch, n_frames):
+        lib = _lib.load()
+        key = (device.index, batch, n_frames)
+        entry = self._plans.get(key)
+        if entry is None:
+            handle = C.c_void_p()
+            arch = self._arch()
+            check(lib.fdbm_plan_create(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create")
+            entry = [handle, None]
+            self._plans[key] = entry
+        version = self._weight_version()
+        if entry[1] != version:
+            named = [(n, p) for n, p in self.named_parameters()]
+            refs = (TensorRef * len(named))()
+            keep = []
+            for i, (n, p) in enumerate(named):
+                if p.device != device or p.dtype != torch.float32:
+                    raise RuntimeError(f"parameter {n} must be fp32 on {device}")
+                d = p.detach().contiguous()
+                keep.append(d)
+                refs[i].name, refs[i].data, refs[i].numel = n.encode(), d.data_ptr(), d.numel()
+            check(lib.fdbm_plan_load_weights(entry[0], refs, len(named), current_stream()), "fdbm_plan_load_weights")
+            entry[1] = version
+        return entry[0]
+
+    def invalidate_weights(self):
+        """Force a re-pack on the next call.  Needed after writes through `param.data` (e.g. torch_ema's
+        in-place swap, fdbm/model.py:146-160), which do not bump the parameter's version counter."""
+        for entry in self._plans.values():
+            entry[1] = None
+
+    def train(self, mode: bool = True):
+        self.invalidate_weights()          # the reference swaps EMA weights in train()/eval()
+        return super().train(mode)
+
+    def release_plans(self):
+        lib = _lib.load()
+        for handle, _ in self._plans.values():
+            lib.fdbm_plan_destroy(handle)
+        self._plans.clear()
+
+    def __del__(self):
+        try:
+            self.release_plans()
+        except Exception:
+            pass
+
+    def plan_info(self, batch, n_frames, device=None):
+        device = device or next(self.parameters()).device
+        h = self._plan(device, batch, n_frames)
+        lib = _lib.load()
+        return {"device_bytes": lib.fdbm_plan_device_bytes(h), "launches": lib.fdbm_plan_num_launches(h)}
+
+    def _check_spec(self, s, name):
+        if not (s.is_cuda and s.dtype == torch.complex64 and s.dim() == 4 and s.shape[1] == 1
+                and s.shape[2] == self.image_size + 1):
+            raise RuntimeError(f"{name} must be a complex64 CUDA tensor [B,1,{self.image_size + 1},T], got "
+                               f"{tuple(s.shape)} {s.dtype} on {s.device}")
+        return s.contiguous()
+
+    # ---- sampler hook used by fdbm_b200.bridge.Bridge -----------------------------------------
+    def run_sampler(self, y, x, times, table, kind, noise, seed):
+        """In-place N-step sampler on x (fdbm/bridge.py:66-113) as one CUDA graph."""
+        if self.predictive:
+            raise RuntimeError("predictive backbones have no sampling loop")
+        y = self._check_spec(y, "y")
+        if not x.is_contiguous():
+            raise RuntimeError("x must be contiguous")
+        plan = self._plan(y.device, y.shape[0], y.shape[3])
+        check(_lib.load().fdbm_sampler_run(plan, ptr(y), ptr(x), ptr(times), ptr(table), times.numel(), kind, ptr(noise),
+                                           seed, current_stream()), "fdbm_sampler_run")
+        return x
+
+
+@BackboneRegistry.register("ncsnpp_v2")
+class NCSNpp_v2(_NCSNppBase):
+    """fdbm/backbones/ncsnpp_v2.py:36-401."""
+
+    def forward(self, x, y, t):
+        x, y = self._check_spec(x, "x"), self._check_spec(y, "y")
+        t = t.to(device=x.device, dtype=torch.float32).contiguous()
+        out = torch.empty_like(x)
+        plan = self._plan(x.device, x.shape[0], x.shape[3])
+        check(_lib.load().fdbm_ncsnpp_forward(plan, ptr(x), ptr(y), ptr(t), ptr(out), current_stream()), "fdbm_ncsnpp_forward")
+        return out
+
+
+@BackboneRegistry.register("ncsnpp_v2_predictive")
+class NCSNpp_v2_predictive(_NCSNppBase):
+    """fdbm/backbones/ncsnpp_v2_predictive.py:36-362."""
+    predictive = True
+
+    def forward(self, x):
+        x = self._check_spec(x, "x")
+        out = torch.empty_like(x)
+        plan = self._plan(x.device, x.shape[0], x.shape[3])
+        check(_lib.load().fdbm_ncsnpp_forward(plan, ptr(x), None, None, ptr(out), current_stream()), "fdbm_ncsnpp_forward")
+        return out

@@ -1,0 +1,138 @@
+"""End-to-end parity of the CUDA backbone / sampler / enhance path against the reference's
+golden outputs (tests/golden, produced by the reference itself) and the CPU oracle.
+
+Tolerances (BASELINE.json north_star): enhanced spectrogram within 5e-3 relative L2 in bf16
+(GEMM operands are bf16, accumulation and the residual stream fp32), waveform SI-SDR within
+0.05 dB of the reference."""
+import numpy as np
+import pytest
+import torch
+
+from helpers import load_npz, rel_l2
+
+pytestmark = pytest.mark.gpu
+
+TOL_BF16 = 5e-3
+
+
+@pytest.fixture(scope="module")
+def nets():
+    import fdbm_oracle as O
+    from fdbm_b200 import BackboneRegistry
+    cfg = O.NcsnppConfig()
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    net = BackboneRegistry.get_by_name("ncsnpp_v2")()
+    missing = net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    return O, cfg, sd, net
+
+
+def test_state_dict_names_match_reference(nets):
+    O, cfg, sd, net = nets
+    mine = {k: tuple(v.shape) for k, v in net.state_dict().items()}
+    assert mine == {k: tuple(v.shape) for k, v in sd.items()}
+    assert len(mine) == 647                                        # 647 tensors
+
+
+def test_backbone_forward_golden_T64(nets, golden_dir):
+    O, cfg, sd, net = nets
+    g = load_npz(f"{golden_dir}/bridge_T64.npz")
+    xt, Y, t = (torch.from_numpy(g[k]).cuda() for k in ("xt", "Y", "t"))
+    D = net(xt, Y, t)
+    ref = torch.from_numpy(g["D"])
+    assert D.shape == ref.shape and D.dtype == torch.complex64
+    assert float(D[:, :, 256].abs().max()) == 0.0                  # Nyquist row is exactly zero (ncsnpp_v2.py:398)
+    err = rel_l2(D, ref)
+    print(f"backbone T=64 rel L2 vs reference golden: {err:.3e}")
+    assert err < TOL_BF16
+    # batch invariance: the same utterance twice in a batch gives the same rows
+    D2 = net(xt.repeat(2, 1, 1, 1), Y.repeat(2, 1, 1, 1), t.repeat(2))
+    assert torch.equal(D2[0], D[0]) and torch.equal(D2[1], D[0])
+    # deterministic
+    assert torch.equal(net(xt, Y, t), D)
+
+
+@pytest.mark.parametrize("path,st", [("sb", "ode_ei"), ("sb", "sde_ei"), ("fm", "ode_ei")])
+def test_sampler_golden_T64(nets, golden_dir, path, st):
+    O, cfg, sd, net = nets
+    from fdbm_b200 import Bridge, SpecsDataModule
+    g = load_npz(f"{golden_dir}/bridge_T64.npz")
+    Y = torch.from_numpy(g["Y"]).cuda()
+    br = Bridge(path, N=5, sampler_type=st)
+    noise = torch.from_numpy(g[f"noise_{path}_{st}"]).cuda() if f"noise_{path}_{st}" in g else None
+    if noise is not None:                                          # replay the reference's noise draws
+        seq = iter(list(noise))
+        orig = torch.randn_like
+        torch.randn_like = lambda x, **k: next(seq)
+        try:
+            s = br.sampler(net, Y)
+        finally:
+            torch.randn_like = orig
+    else:
+        s = br.sampler(net, Y)
+    ref = torch.from_numpy(g[f"sample_{path}_{st}"])
+    err = rel_l2(s, ref)
+    dm = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    w = dm.to_audio(s[:, 0], 16000)[0].cpu().numpy()
+    wref = g[f"wave_{path}_{st}"].reshape(-1)
+    sdr = O.si_sdr(wref, w)
+    print(f"sampler {path}/{st}: spec rel L2 {err:.3e}, SI-SDR(new vs ref) {sdr:.1f} dB")
+    assert err < 2 * TOL_BF16                                       # 5 backbone passes compound
+    assert sdr > 35.0
+
+
+def test_backbone_full_size_vs_oracle(nets):
+    """BASELINE config 1 shape: [1,1,257,256] (4 s).  Oracle on CPU takes a few seconds."""
+    O, cfg, sd, net = nets
+    scfg = O.SpecConfig()
+    _, noisy = O.synth_pair(0)
+    y = (noisy / noisy.abs().max())[None]
+    Y = O.pad_spec(O.spec_fwd(O.stft(y, scfg), scfg)[None], "reflection")
+    g = torch.Generator().manual_seed(21)
+    xt = Y + 0.2 * torch.view_as_complex(torch.randn(1, 1, 257, 256, 2, generator=g))
+    t = torch.tensor([0.4])
+    with torch.no_grad():
+        ref = O.ncsnpp_forward(sd, cfg, xt, Y, t)
+    D = net(xt.cuda(), Y.cuda(), t.cuda())
+    err = rel_l2(D, ref)
+    print(f"backbone T=256 rel L2 vs oracle: {err:.3e}")
+    assert err < TOL_BF16
+
+
+def test_predictive_golden(golden_dir):
+    import fdbm_oracle as O
+    from fdbm_b200 import BackboneRegistry
+    cfg = O.NcsnppConfig(predictive=True)
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    net = BackboneRegistry.get_by_name("ncsnpp_v2_predictive")()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    g = load_npz(f"{golden_dir}/predictive_T64.npz")
+    D = net(torch.from_numpy(g["Y"]).cuda())
+    err = rel_l2(D, g["D"])
+    print(f"predictive T=64 rel L2 vs reference golden: {err:.3e}")
+    assert err < TOL_BF16
+
+
+def test_enhance_si_sdr_matches_oracle(nets):
+    """infer_single flow on one synthetic 1 s utterance: waveform SI-SDR (vs clean) within 0.05 dB of
+    the oracle's, and the two enhanced waveforms agree to > 35 dB."""
+    O, cfg, sd, net = nets
+    from fdbm_b200 import EnhancementModel
+    clean, noisy = O.synth_pair(3, n_samples=16000)
+    model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=5, sampler_type="ode_ei"))
+    model.dnn.load_state_dict(sd)
+    model = model.cuda().eval()
+    got = model.enhance(noisy[None])
+    ob = O.Bridge("sb", N=5, sampler_type="ode_ei")
+    with torch.no_grad():
+        ref = O.enhance(noisy[None], lambda a, b, c: O.ncsnpp_forward(sd, cfg, a, b, c), ob, O.SpecConfig()).numpy()
+    c = clean.numpy()
+    d = abs(O.si_sdr(c, got) - O.si_sdr(c, ref))
+    agree = O.si_sdr(ref, got)
+    print(f"enhance: |dSI-SDR| vs clean {d:.4f} dB, SI-SDR(new vs oracle) {agree:.1f} dB")
+    assert d < 0.05
+    assert agree > 35.0
+    # batched path = per-utterance path
+    both = model.enhance_batch(torch.stack([noisy, noisy]).cuda())
+    assert rel_l2(both[0], got) < 1e-5 and torch.equal(both[0], both[1])
