@@ -1,0 +1,302 @@
+#!/usr/bin/env python
+"""bench.py -- enhanced audio-seconds per second of the N-step bridge sampler hot path.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
+
+One "step" = one pass of the whole hot path (fused STFT+compress+pad -> 5-step SB/ode_ei sampler on
+the NCSN++ backbone -> fused decompress+iSTFT) over this GPU's batch of 256 synthetic 4 s / 16 kHz
+utterances (BASELINE.json configs[1], `infer_folder`).  Utterances are independent units: every rank
+enhances its own 256 (weak scaling, no data-path collective); the value is the whole-job aggregate.
+
+Prints ONE JSON line (see the task contract): value (device-resident inputs), e2e (host buffers,
+H2D/D2H inside the timed region), roofline of the dominant kernel (tcgen05 implicit-GEMM convolution,
+timed launch by launch with CUDA events through fdbm_plan_profile_forward), cpu_baseline (the CPU
+oracle = port of the reference path, on this box's host cores), clocks, gpu_launches.
+
+`--impl reference` times the reference's own CPU path (the oracle port -- the Python reference cannot
+travel to the GPU box) with all host threads on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+PKG = os.path.join(ROOT, "rethinking-flow-and-diffusion-bridge-models-for-speech-enhancement_b200")
+sys.path.insert(0, PKG)
+
+SR = 16000
+UTT_SECONDS = 4.0
+N_SAMPLES = int(SR * UTT_SECONDS)
+UTTS_PER_GPU = 256
+BRIDGE_STEPS = 5
+GFLOP_PER_FORWARD = 532.1          # one ncsnpp_v2 forward on a 4 s utterance (2*MAC)
+METRIC = "enhanced audio-sec/sec (5-step SB bridge, ncsnpp_v2)"
+UNIT = "audio-s/s"
+
+
+def synth_batch(n, device, seed=1234):
+    """Synthetic noisy utterances (SURVEY.md section 8(d) recipe, vectorised): 8 harmonics of f0~U(100,300) Hz
+    with 1/k roll-off and a 3 Hz envelope, plus white noise at SNR~U(0,15) dB.  fp32 [n, N_SAMPLES]."""
+    import math
+    import torch
+    g = torch.Generator(device="cpu").manual_seed(seed)
+    f0 = 100 + 200 * torch.rand(n, 1, generator=g)
+    phi = 2 * math.pi * torch.rand(n, 8, generator=g)
+    phi_e = 2 * math.pi * torch.rand(n, 1, generator=g)
+    snr = 15 * torch.rand(n, 1, generator=g)
+    t = torch.arange(N_SAMPLES, dtype=torch.float32, device=device)[None] / SR
+    f0, phi, phi_e, snr = (v.to(device) for v in (f0, phi, phi_e, snr))
+    clean = torch.zeros(n, N_SAMPLES, device=device)
+    for k in range(1, 9):
+        clean += (1.0 / k) * torch.sin(2 * math.pi * k * f0 * t + phi[:, k - 1:k])
+    clean *= 0.3 * 0.5 * (1 + torch.sin(2 * math.pi * 3 * t + phi_e))
+    gn = torch.Generator(device=device).manual_seed(seed + 1)
+    noise = torch.randn(n, N_SAMPLES, generator=gn, device=device)
+    noise *= torch.sqrt(clean.pow(2).mean(1, keepdim=True) / (noise.pow(2).mean(1, keepdim=True) * 10 ** (snr / 10)))
+    return (clean + noise).contiguous()
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.path = index, None, None
+
+    def start(self):
+        try:
+            fd, self.path = tempfile.mkstemp(suffix=".csv")
+            os.close(fd)
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                         stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
+        except Exception:
+            self.proc = None
+
+    def stop(self):
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        try:
+            for line in open(self.path):
+                f = [x.strip() for x in line.split(",")]
+                if len(f) < 9:
+                    continue
+                try:
+                    sm.append(float(f[1])); mx.append(float(f[2]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), f[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except Exception:
+            pass
+        if sm:
+            sm.sort()
+            out = {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        return out
+
+
+def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None):
+    """The reference's CPU path (oracle port): B=1 utterance loop exactly like infer_folder.py:90-146.
+    Returns (audio-s/s, ms per step, description of the sample, cores)."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fdbm_oracle as O
+    cores = threads or os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    cfg = O.NcsnppConfig()
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    bridge = O.Bridge("sb", N=BRIDGE_STEPS, sampler_type="ode_ei")
+    model = lambda a, b, c: O.ncsnpp_forward(sd, cfg, a, b, c)
+
+    def run(n_samples):
+        _, noisy = O.synth_pair(0, n_samples=n_samples)
+        t0 = time.perf_counter()
+        with torch.no_grad():
+            O.enhance(noisy[None], model, bridge, O.SpecConfig())
+        return time.perf_counter() - t0
+
+    # probe with 1 s of audio, then pick the largest utterance length whose K+W repetitions fit the budget
+    probe = run(SR)
+    n_runs = max(1, steps + warmup)
+    seconds = UTT_SECONDS
+    while seconds > 1.0 and probe * seconds * n_runs > seconds_budget * max(1, n_runs) ** 0.5 * 2.5:
+        seconds /= 2
+    n_samples = int(SR * seconds)
+    for _ in range(warmup):
+        run(n_samples)
+    times = [run(n_samples) for _ in range(max(1, steps))]
+    dt = sum(times) / len(times)
+    sample = (f"1 of {UTTS_PER_GPU} utterances per step, {seconds:g} s of audio each (B=1 loop like the reference), "
+              f"N={BRIDGE_STEPS}, fp32, torch CPU with {cores} threads")
+    return seconds / dt, dt * 1e3, sample, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "8")))
+    ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="utterances per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    config = {"workload": f"infer_folder: {args.utts} synthetic {UTT_SECONDS:g} s 16 kHz utterances per GPU, ncsnpp_v2 "
+                          f"(65.6 M params, random init re-sensitised), Bridge('sb','bb') ode_ei N={BRIDGE_STEPS}, "
+                          "fused STFT/compress/pad and decompress/iSTFT",
+              "utterances_per_gpu": args.utts, "bridge_steps": BRIDGE_STEPS}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return 0
+        v, ms, sample, cores = cpu_reference_leg(steps=args.steps, warmup=args.warmup)
+        print(json.dumps({
+            "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32", "data": "synthetic", "config": config,
+            "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "gpu_launches": 0}))
+        return 0
+
+    import torch
+    import torch.distributed as dist
+    from fdbm_b200 import EnhancementModel, _lib, sensitise_
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().fdbm_check_device(), "fdbm_check_device")
+
+    mb = args.micro_batch
+    model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
+    sensitise_(model.dnn, seed=0)
+    model = model.to(dev).eval()
+    waves = synth_batch(args.utts, dev, seed=1234 + 100000 * rank)        # rank r owns its own utterances
+    host_in = torch.empty(waves.shape, dtype=torch.float32, pin_memory=True).copy_(waves)
+    host_out = torch.empty_like(host_in, pin_memory=True)
+
+    def step_device():
+        return model.enhance_many(waves, micro_batch=mb)
+
+    def step_e2e():
+        for i in range(0, args.utts, mb):
+            chunk = host_in[i:i + mb].to(dev, non_blocking=True)
+            n = chunk.shape[0]
+            if n < mb:
+                chunk = torch.cat([chunk, chunk[-1:].expand(mb - n, -1)], dim=0)
+            host_out[i:i + n].copy_(model.enhance_batch(chunk)[:n], non_blocking=True)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms_total = timed(step_device, args.steps)
+    clock_info = clocks.stop() if rank == 0 else None
+    step_e2e()
+    ms_e2e = timed(step_e2e, args.steps)
+
+    audio_s = args.utts * UTT_SECONDS * world
+    value = audio_s * args.steps / (ms_total * 1e-3)
+    e2e = audio_s * args.steps / (ms_e2e * 1e-3)
+
+    # roofline of the dominant kernel: every launch of one forward timed with CUDA events
+    roofline, shares = None, None
+    info = model.dnn.plan_info(mb, 256)
+    if rank == 0:
+        Y = model.data_module.stft_compress(waves[:mb] / waves[:mb].abs().amax(1, keepdim=True), pad_mode="reflection")
+        t = torch.full((mb,), 0.5, device=dev)
+        prof = [model.dnn.profile_forward(Y, Y, t) for _ in range(3)][-1]
+        kind_ms = {}
+        for ms, kind, _ in prof:
+            kind_ms[kind] = kind_ms.get(kind, 0.0) + ms
+        conv_ms = kind_ms.get(0, 0.0)
+        conv_flops = sum(f for _, k, f in prof if k == 0)
+        n_conv = sum(1 for _, k, _ in prof if k == 0)
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved = conv_flops / (conv_ms * 1e-3) / 1e12
+        roofline = {"bound": "tensor", "kernel": "conv_igemm_kernel (tcgen05 implicit GEMM, 16-bit operands, fp32 accumulate)",
+                    "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
+                    "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
+                    if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
+                    "traffic": None, "launches_per_forward": n_conv,
+                    "avg_launch_ms": conv_ms / max(1, n_conv),
+                    "algorithmic_gflop_per_forward_per_utt": conv_flops / mb / 1e9}
+        tot = sum(kind_ms.values())
+        names = {0: "conv_igemm", 1: "groupnorm_act", 2: "channel_stats", 3: "skinny", 4: "attention", 5: "temb"}
+        shares = {names[k]: round(v / tot, 4) for k, v in sorted(kind_ms.items())}
+        shares["forward_ms_per_microbatch"] = tot
+
+    n_micro = (args.utts + mb - 1) // mb
+    launches_per_step = n_micro * (1 + 1 + BRIDGE_STEPS * (info["launches"] + 1) + 1)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, ms, sample, cores = cpu_reference_leg(seconds_budget=25.0)
+        cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_utterance": ms}
+
+    if rank == 0:
+        config.update({"micro_batch": mb, "parallelism": f"utterance-sharded x{world}",
+                       "l2": f"working set per step >> L2: {info['device_bytes'] / 2**30:.1f} GiB of activations+weights "
+                             f"per micro-batch, {n_micro} micro-batches per step (no explicit flush needed)"})
+        print(json.dumps({
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if _lib.load().fdbm_operand_is_bf16() else "fp16", "data": "synthetic", "config": config,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.utts * N_SAMPLES * 4,
+                    "d2h_bytes_per_step": args.utts * N_SAMPLES * 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": launches_per_step * args.steps,
+            "per_backbone_forward_ms_per_utt": ms_total / args.steps / (args.utts * BRIDGE_STEPS),
+            "model_tflops": GFLOP_PER_FORWARD * BRIDGE_STEPS * args.utts * world * args.steps / (ms_total * 1e-3) / 1e3,
+            "roofline": roofline, "kernel_share": shares, "cpu_baseline": cpu_baseline, "clocks": clock_info}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
+if __name__ == "__main__":
+    sys.exit(main())

@@ -47,6 +47,9 @@ const char* fdbm_last_error(void);
 int fdbm_version(void);
 /* 0 when the current device is sm_100 (B200); FDBM_EARCH otherwise. */
 int fdbm_check_device(void);
+/* 16-bit GEMM operand format of this build: 0 = IEEE fp16 (default), 1 = bfloat16.  Both feed the
+ * same tcgen05 kind::f16 tensor-core path at the same rate; "h16" below means this format. */
+int fdbm_operand_is_bf16(void);
 
 /* ---------------------------------------------------------------------------------------------
  * Spectral front end.  Replaces SpecsDataModule.stft (fdbm/data_module.py:223-225) +
@@ -105,7 +108,7 @@ int fdbm_bridge_step(float* x, const float* d, const float* y_or_z, const float*
  *
  * A plan is built for one (architecture, batch, n_frames) shape.  Weights are passed as an array
  * of host-visible descriptors {name, device pointer, numel} using the reference's state_dict
- * names (all_modules.<i>.<Layer>.weight ..., output_layer.*); the plan packs them (bf16, tap-major)
+ * names (all_modules.<i>.<Layer>.weight ..., output_layer.*); the plan packs them (h16, tap-major)
  * into its own buffer.  Re-pack with fdbm_plan_load_weights after parameters change (EMA swap,
  * fdbm/model.py:146-160; optimizer step).
  * --------------------------------------------------------------------------------------------- */
@@ -143,17 +146,30 @@ int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float* y, const f
 /* Whole sampler: Bridge.ode_sampler_ei / sde_sampler_ei (fdbm/bridge.py:66-113) for n_steps steps.
  *   y     cplx [B,1,257,T]   conditioning (noisy compressed spectrogram)
  *   x     cplx [B,1,257,T]   in: x_start (prior sample), out: final sample
- *   times fp32 [n_steps]     device; t_prev of every step (time_steps[:-1]) -- what the backbone sees
- *   coef  fp32 [n_steps,3]   device; coefficient table
- *   noise cplx [n_steps, B,1,257,T] or NULL (SDE only; NULL = in-kernel Philox with `seed`)
- * The N-step loop is captured once per (plan, n_steps, kind, pointers) as a CUDA graph and replayed. */
+ *   times fp32 [n_steps]     HOST; t_prev of every step (time_steps[:-1]) -- what the backbone sees
+ *   coef  fp32 [n_steps,3]   HOST; coefficient table
+ *   noise cplx [n_steps, B,1,257,T] device, or NULL (SDE only; NULL = in-kernel Philox with `seed`)
+ * y, x (and noise) are staged into plan-owned buffers, so the N-step loop is captured ONCE per
+ * (plan, n_steps, kind) as a CUDA graph and replayed for every later call whatever the pointers. */
 int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
                      int n_steps, int kind, const float* noise, uint64_t seed, void* stream);
+
+/* Measurement aid for bench.py: run one forward launch by launch with a CUDA event pair around every
+ * kernel.  ms[i] = device time, kinds[i] = FDBM_OP_*, flops[i] = algorithmic FLOPs (2*MAC, convolutions
+ * only) of launch i.  Returns the number of launches (<= max_ops) or a negative error.  Synchronises. */
+#define FDBM_OP_CONV   0   /* tcgen05 implicit-GEMM convolution           */
+#define FDBM_OP_NORM   1   /* GroupNorm (+SiLU, +FIR) operand pass        */
+#define FDBM_OP_STATS  2   /* per-channel statistics                      */
+#define FDBM_OP_SKINNY 3   /* K or N <= 4 layers, FIR, packing            */
+#define FDBM_OP_ATTN   4   /* attention core                              */
+#define FDBM_OP_SMALL  5   /* time embedding, Dense_0 table               */
+int fdbm_plan_profile_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
+                              float* ms, int* kinds, double* flops, int max_ops, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Building blocks, exported for the parity tests (tests/ call them one by one through ctypes).
  * Layout of activations inside the backbone: [B, T, F, C] ("NTFC": channels innermost, then
- * frequency, then frames) -- fp32 for the residual stream, bf16 for GEMM operands.
+ * frequency, then frames) -- fp32 for the residual stream, h16 for GEMM operands.
  * --------------------------------------------------------------------------------------------- */
 
 /* upfirdn2d replacement (op/upfirdn2d.cpp:12-23 restricted to the two modes the model uses,
@@ -165,10 +181,10 @@ int fdbm_fir_resample(const float* in, int batch, int T, int F, int C, int mode,
 int fdbm_channel_stats(const float* in, int batch, int T, int F, int C, double* sums, void* stream);
 
 /* GroupNorm(min(C/4,32) groups, eps 1e-6) [+SiLU] [+FIR up/down] over the channel concatenation of
- * up to two fp32 NTFC sources -> bf16 NTFC operand(s).  Replaces nn.GroupNorm + nn.SiLU +
+ * up to two fp32 NTFC sources -> h16 NTFC operand(s).  Replaces nn.GroupNorm + nn.SiLU +
  * upsample_2d/downsample_2d + torch.cat in ResnetBlockBigGANpp.forward (layerspp.py:242-257).
- *   act_out  bf16 [B,T',F',C1+C2]  = FIR(SiLU(GN(cat(src1,src2))))       (silu: 0/1)
- *   raw_out  bf16 [B,T',F',C1+C2]  = FIR(cat(src1,src2)) or NULL          (operand of Conv_2) */
+ *   act_out  h16 [B,T',F',C1+C2]  = FIR(SiLU(GN(cat(src1,src2))))       (silu: 0/1)
+ *   raw_out  h16 [B,T',F',C1+C2]  = FIR(cat(src1,src2)) or NULL          (operand of Conv_2) */
 int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1,
                        const float* src2, const double* sums2, int C2,
                        const float* gamma, const float* beta, int batch, int T, int F,
@@ -179,21 +195,21 @@ int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1,
  *                            + bias (+ bias_b[b,:]) (+ residual[b,t,f,:]) )
  * Replaces nn.Conv2d 3x3 / 1x1 and NIN (layers.py:100-124, 546-555) together with the bias,
  * time-embedding FiLM add (layerspp.py:263), shortcut add and 1/sqrt(2) rescale (:270-274).
- *   in1   bf16 [B,T,F,C1], ksize 3 or 1;  in2 bf16 [B,T,F,C2] (1x1) or NULL
- *   wpack bf16 packed by fdbm_pack_conv_weights;  bias fp32 [Cout];  bias_b fp32 [B,Cout] or NULL
- *   residual fp32 [B,T,F,Cout] or NULL;  out_f32 fp32 and/or out_bf16 bf16 [B,T,F,Cout] (either may be NULL)
+ *   in1   h16 [B,T,F,C1], ksize 3 or 1;  in2 h16 [B,T,F,C2] (1x1) or NULL
+ *   wpack h16 packed by fdbm_pack_conv_weights;  bias fp32 [Cout];  bias_b fp32 [B,Cout] or NULL
+ *   residual fp32 [B,T,F,Cout] or NULL;  out_f32 fp32 and/or out_h16 h16 [B,T,F,Cout] (either may be NULL)
  *   sums double [B,Cout,2] or NULL: receives the per-channel sum / sum of squares of the fp32 result. */
 int fdbm_conv_igemm(const void* in1, int C1, int ksize, const void* in2, int C2,
                     const void* wpack, const float* bias, const float* bias_b, const float* residual,
                     float scale, int batch, int T, int F, int Cout,
-                    float* out_f32, void* out_bf16, double* sums, void* stream);
+                    float* out_f32, void* out_h16, double* sums, void* stream);
 /* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
- * -> bf16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major.  Returns bytes via *bytes when wpack==NULL. */
+ * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]).  Returns bytes via *bytes when wpack==NULL. */
 int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,
                            void* wpack, int64_t* bytes, void* stream);
 
 /* Single-head attention over all T*F positions (AttnBlockpp core, layerspp.py:82-86):
- * q,k,v bf16 [B, L, C] (L = T*F) -> o bf16 [B, L, C], scale C^-0.5. */
+ * q,k,v h16 [B, L, C] (L = T*F) -> o h16 [B, L, C], scale C^-0.5. */
 int fdbm_attention(const void* q, const void* k, const void* v, int batch, int L, int C, void* o, void* stream);
 
 #ifdef __cplusplus

@@ -14,6 +14,7 @@ void set_error(const char* fmt, ...) {
 }
 
 int cuda_fail(cudaError_t e, const char* what, const char* file, int line) {
+  cudaGetLastError();        // reset the (non-sticky) error so that the caller's next CUDA call is not poisoned
   set_error("CUDA error '%s' (%d) in %s at %s:%d", cudaGetErrorString(e), static_cast<int>(e), what, file, line);
   return FDBM_ECUDA;
 }
@@ -52,3 +53,4 @@ int num_sms() {
 extern "C" const char* fdbm_last_error(void) { return fdbm::g_error; }
 extern "C" int fdbm_version(void) { return 100; }
 extern "C" int fdbm_check_device(void) { return fdbm::require_sm100(); }
+extern "C" int fdbm_operand_is_bf16(void) { return fdbm::kOperandIsBf16; }

@@ -52,8 +52,10 @@ prior_sample_kernel(const float2* __restrict__ y, const float2* __restrict__ z, 
 template <int KIND>
 __global__ void __launch_bounds__(256)
 bridge_step_kernel(float4* __restrict__ x, const float4* __restrict__ d, const float4* __restrict__ yz,
-                   const float* __restrict__ coef, uint64_t seed, uint64_t offset, int64_t n_pairs) {
+                   const float* __restrict__ coef, uint64_t seed, uint64_t offset, const uint64_t* __restrict__ rng,
+                   int64_t n_pairs) {
   const float wx = coef[0], ws = coef[1], w3 = coef[2];
+  if (rng) { seed = rng[0]; offset += rng[1]; }           // graph replays read the seed from device memory
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n_pairs; i += 256ll * gridDim.x) {
     const float4 xv = x[i], dv = d[i];
     float4 t;
@@ -96,8 +98,8 @@ extern "C" int fdbm_prior_sample(const float* y, const float* z, float b, float 
   return FDBM_OK;
 }
 
-extern "C" int fdbm_bridge_step(float* x, const float* d, const float* y_or_z, const float* coef, int kind,
-                                uint64_t seed, uint64_t offset, int64_t n_complex, void* stream) {
+static int bridge_step_impl(float* x, const float* d, const float* y_or_z, const float* coef, int kind, uint64_t seed,
+                            uint64_t offset, const uint64_t* rng, int64_t n_complex, cudaStream_t stream) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(x && d && coef && n_complex > 0, "fdbm_bridge_step: null pointer or empty");
   FDBM_REQUIRE(n_complex % 2 == 0, "fdbm_bridge_step: n_complex must be even (16-byte vectors)");
@@ -108,13 +110,25 @@ extern "C" int fdbm_bridge_step(float* x, const float* d, const float* y_or_z, c
   const int64_t n_pairs = n_complex / 2;
   const int grid = grid_for(n_pairs);
   if (kind == FDBM_STEP_ODE)
-    bridge_step_kernel<FDBM_STEP_ODE><<<grid, 256, 0, as_stream(stream)>>>(
+    bridge_step_kernel<FDBM_STEP_ODE><<<grid, 256, 0, stream>>>(
         reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(d), reinterpret_cast<const float4*>(y_or_z), coef,
-        seed, offset, n_pairs);
+        seed, offset, rng, n_pairs);
   else
-    bridge_step_kernel<FDBM_STEP_SDE><<<grid, 256, 0, as_stream(stream)>>>(
+    bridge_step_kernel<FDBM_STEP_SDE><<<grid, 256, 0, stream>>>(
         reinterpret_cast<float4*>(x), reinterpret_cast<const float4*>(d), reinterpret_cast<const float4*>(y_or_z), coef,
-        seed, offset, n_pairs);
+        seed, offset, rng, n_pairs);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
+}
+
+namespace fdbm {
+int launch_bridge_step_rng(float* x, const float* d, const float* third, const float* coef, int kind,
+                           const uint64_t* rng, uint64_t offset, int64_t n_complex, cudaStream_t s) {
+  return bridge_step_impl(x, d, third, coef, kind, 0, offset, rng, n_complex, s);
+}
+}  // namespace fdbm
+
+extern "C" int fdbm_bridge_step(float* x, const float* d, const float* y_or_z, const float* coef, int kind,
+                                uint64_t seed, uint64_t offset, int64_t n_complex, void* stream) {
+  return bridge_step_impl(x, d, y_or_z, coef, kind, seed, offset, nullptr, n_complex, as_stream(stream));
 }

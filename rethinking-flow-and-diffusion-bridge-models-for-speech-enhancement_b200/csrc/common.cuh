@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
@@ -41,6 +42,32 @@ __host__ __device__ constexpr int64_t ceil_div64(int64_t a, int64_t b) { return 
 
 __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)); }
 
+// 16-bit GEMM operand format.  Default IEEE fp16: same tcgen05 kind::f16 rate as bf16 but an 11-bit
+// significand (TF32's precision) -- GEMM operands here are GroupNorm-ed activations and weights, far
+// inside fp16's range; conversions saturate.  Build with -DFDBM_OPERAND_BF16 for bfloat16.
+#ifdef FDBM_OPERAND_BF16
+typedef op_t op_t;
+typedef op_t2 op2_t;
+constexpr int kOperandIsBf16 = 1;
+__device__ __forceinline__ op_t f2op(float v) { return __float2bfloat16(v); }
+__device__ __forceinline__ float op2f(op_t v) { return __bfloat162float(v); }
+__device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2bfloat162_rn(a, b); }
+__device__ __forceinline__ float2 op22f2(op2_t v) { return __bfloat1622float2(v); }
+#else
+typedef __half op_t;
+typedef __half2 op2_t;
+constexpr int kOperandIsBf16 = 0;
+__device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
+__device__ __forceinline__ op_t f2op(float v) { return __float2half_rn(sat16(v)); }
+__device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
+__device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2half2_rn(sat16(a), sat16(b)); }
+__device__ __forceinline__ float2 op22f2(op2_t v) { return __half22float2(v); }
+#endif
+__device__ __forceinline__ uint32_t pack_op2(float a, float b) {
+  op2_t v = f2op2(a, b);
+  return *reinterpret_cast<uint32_t*>(&v);
+}
+
 // --------------------------------------------------------------------------------------------
 // Internal launchers (device pointers, no argument validation beyond what kernels need).
 // The C ABI in api.cu validates and forwards; the backbone plan calls these directly.
@@ -49,14 +76,14 @@ int launch_fir_resample(const float* in, int B, int T, int F, int C, int mode, f
 int launch_channel_stats(const float* in, int B, int T, int F, int C, double* sums, cudaStream_t s);
 int launch_groupnorm_act(const float* src1, const double* sums1, int C1, const float* src2, const double* sums2,
                          int C2, const float* gamma, const float* beta, int B, int T, int F, int silu, int mode,
-                         __nv_bfloat16* act_out, __nv_bfloat16* raw_out, cudaStream_t s);
+                         op_t* act_out, op_t* raw_out, cudaStream_t s);
 int launch_pack_input(const float* x, const float* y, int B, int T, int F_in, int F, int Cin, float* out,
                       cudaStream_t s);
 int launch_conv_in(const float* in, int Cin, const float* w, const float* bias, int B, int T, int F, int Cout,
                    float* out, cudaStream_t s);
 int launch_combine(float* h, const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F,
                    int C, cudaStream_t s);
-int launch_pyramid_conv(const __nv_bfloat16* act, int C, const float* w, const float* bias, const float* prev,
+int launch_pyramid_conv(const op_t* act, int C, const float* w, const float* bias, const float* prev,
                         int Cp, int B, int T, int F, float* out, cudaStream_t s);
 int launch_output_layer(const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F,
                         int F_out, float* out, cudaStream_t s);
@@ -64,21 +91,21 @@ int launch_temb(const float* t, const float* fourier_w, int nf, const float* w1,
                 const float* b2, int B, int t_stride, float* temb_act, cudaStream_t s);
 int launch_dense_all(const float* temb_act, const float* w, const float* bias, int B, int K, int rows, float* out,
                      cudaStream_t s);
-int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld, int B, int L,
-                     int C, __nv_bfloat16* o, int ldo, cudaStream_t s);
+int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B, int L,
+                     int C, op_t* o, int ldo, cudaStream_t s);
 
 struct ConvArgs {
-  const __nv_bfloat16* in1; int C1; int ksize;
-  const __nv_bfloat16* in2; int C2;
-  const __nv_bfloat16* wpack;
+  const op_t* in1; int C1; int ksize;
+  const op_t* in2; int C2;
+  const op_t* wpack;
   const float* bias; const float* bias_b; int bias_b_stride; const float* residual;
   float scale; int B, T, F, Cout;
-  float* out_f32; __nv_bfloat16* out_bf16; int out_ld;      // out_ld: row stride (elements) of outputs, >= Cout
+  float* out_f32; op_t* out_h16; int out_ld;      // out_ld: row stride (elements) of outputs, >= Cout
   double* sums;
 };
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s);
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,
-                             int row_offset, __nv_bfloat16* wpack, cudaStream_t s);
+                             int row_offset, op_t* wpack, cudaStream_t s);
 
 }  // namespace fdbm

@@ -52,7 +52,7 @@ struct ConvParams {
   const float* residual;
   float scale;
   float* out_f32;
-  __nv_bfloat16* out_bf16;
+  op_t* out_h16;
 };
 
 struct TileCoord { int b, t0, f0; bool valid; };
@@ -151,7 +151,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   } else if (warp == 2) {
     // ------------------------------------------------------------------ MMA issuer (one thread)
     if (lane == 0) {
-      const uint32_t idesc = make_idesc_bf16(128, BN);
+      const uint32_t idesc = make_idesc_f16(128, BN, kOperandIsBf16);
       uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int ct = item / p.n_nblocks;
@@ -178,7 +178,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
               const uint32_t d_tmem = tmem_base + (as * MT + j) * BN;
 #pragma unroll
               for (int k = 0; k < 4; ++k) {
-                mma_bf16(d_tmem, make_desc_sw128(a_addr + k * 32, A_SBO), make_desc_sw128(b_addr + k * 32, 1024), idesc,
+                mma_f16(d_tmem, make_desc_sw128(a_addr + k * 32, A_SBO), make_desc_sw128(b_addr + k * 32, 1024), idesc,
                          (first && k == 0) ? 0u : 1u);
               }
             }
@@ -221,7 +221,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             const float4* bb4 = p.bias_b ? reinterpret_cast<const float4*>(p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + nb) : nullptr;
             const float4* res4 = p.residual ? reinterpret_cast<const float4*>(p.residual + pix * p.Cout + nb) : nullptr;
             float4* of = p.out_f32 ? reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + nb) : nullptr;
-            uint2* ob = p.out_bf16 ? reinterpret_cast<uint2*>(p.out_bf16 + pix * p.Cout + nb) : nullptr;
+            uint2* ob = p.out_h16 ? reinterpret_cast<uint2*>(p.out_h16 + pix * p.Cout + nb) : nullptr;
 #pragma unroll
             for (int g = 0; g < 8; ++g) {
               float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
@@ -233,8 +233,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
               o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale;
               if (of) of[g] = o;
               if (ob) {
-                __nv_bfloat162 lo = __floats2bfloat162_rn(o.x, o.y), hi = __floats2bfloat162_rn(o.z, o.w);
-                ob[g] = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+                ob[g] = make_uint2(pack_op2(o.x, o.y), pack_op2(o.z, o.w));
               }
             }
           }
@@ -255,7 +254,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
 // weight packing: fp32 (OIHW, or [in][out] for NIN) -> bf16 [kt][rows_total][64]
 __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ w1, int C1, int ksize, int io_layout, const float* __restrict__ w2,
-                    int C2, int Cout, int rows_total, int row_offset, __nv_bfloat16* __restrict__ out) {
+                    int C2, int Cout, int rows_total, int row_offset, op_t* __restrict__ out) {
   const int taps = ksize * ksize;
   const int n_kt = (C1 / 64) * taps + C2 / 64;
   const int64_t total = static_cast<int64_t>(n_kt) * Cout * 64;
@@ -276,7 +275,7 @@ pack_weights_kernel(const float* __restrict__ w1, int C1, int ksize, int io_layo
       const int ci = (kt - (C1 / 64) * taps) * 64 + j;
       v = w2[static_cast<int64_t>(co) * C2 + ci];
     }
-    out[(static_cast<int64_t>(kt) * rows_total + row_offset + co) * 64 + j] = __float2bfloat16(v);
+    out[(static_cast<int64_t>(kt) * rows_total + row_offset + co) * 64 + j] = f2op(v);
   }
 }
 
@@ -297,28 +296,28 @@ EncodeFn get_encode() {
   return fn;
 }
 
-int make_act_map(CUtensorMap* map, const __nv_bfloat16* ptr, int B, int T, int F, int C) {
+int make_act_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C) {
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FDBM_ECUDA; }
   cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
   cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * F, (cuuint64_t)C * 2 * F * T};
   cuuint32_t box[4] = {64, HALO_F, HALO_T, 1};
   cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 4, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, es,
+  CUresult r = enc(map, (kOperandIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 4, const_cast<op_t*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation [%d,%d,%d,%d]) failed: %d", B, T, F, C, (int)r); return FDBM_ECUDA; }
   return FDBM_OK;
 }
 
-int make_weight_map(CUtensorMap* map, const __nv_bfloat16* ptr, int64_t rows) {
+int make_weight_map(CUtensorMap* map, const op_t* ptr, int64_t rows) {
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FDBM_ECUDA; }
   cuuint64_t dims[2] = {64, (cuuint64_t)rows};
   cuuint64_t strides[1] = {128};
   cuuint32_t box[2] = {64, BN};
   cuuint32_t es[2] = {1, 1};
-  CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<__nv_bfloat16*>(ptr), dims, strides, box, es,
+  CUresult r = enc(map, (kOperandIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 2, const_cast<op_t*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
   if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(weights, %lld rows) failed: %d", (long long)rows, (int)r); return FDBM_ECUDA; }
@@ -332,7 +331,7 @@ int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout) {
 }
 
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,
-                             int row_offset, __nv_bfloat16* wpack, cudaStream_t s) {
+                             int row_offset, op_t* wpack, cudaStream_t s) {
   FDBM_REQUIRE(C1 % 64 == 0 && C2 % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1),
                "pack_conv_weights: channels must be multiples of 64, ksize 1 or 3");
   const int io = ksize == -1;                     // ksize -1: NIN weight, [in][out] layout, 1x1
@@ -349,7 +348,7 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   FDBM_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_igemm: ksize must be 1 or 3");
   FDBM_REQUIRE(a.Cout % BN == 0, "conv_igemm: Cout must be a multiple of %d (got %d)", BN, a.Cout);
   FDBM_REQUIRE((a.C2 == 0) == (a.in2 == nullptr), "conv_igemm: in2 / C2 mismatch");
-  FDBM_REQUIRE(a.out_f32 || a.out_bf16, "conv_igemm: no output");
+  FDBM_REQUIRE(a.out_f32 || a.out_h16, "conv_igemm: no output");
   static bool attr_set = false;
   if (!attr_set) {
     FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -369,7 +368,7 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.n_nblocks = a.Cout / BN;
   p.n_items = ceil_div(p.n_mtiles, MT) * p.n_nblocks;
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
-  p.out_f32 = a.out_f32; p.out_bf16 = a.out_bf16;
+  p.out_f32 = a.out_f32; p.out_h16 = a.out_h16;
   const int grid = std::min(p.n_items, num_sms());
   conv_igemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a1, map_a2, map_b, p);
   FDBM_LAUNCH_CHECK();
@@ -391,21 +390,21 @@ extern "C" int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const 
   if (!wpack) return FDBM_OK;
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(w1 && ((C2 == 0) == (w2 == nullptr)), "fdbm_pack_conv_weights: null pointer");
-  return launch_pack_conv_weights(w1, C1, ksize, w2, C2, Cout, Cout, 0, reinterpret_cast<__nv_bfloat16*>(wpack),
+  return launch_pack_conv_weights(w1, C1, ksize, w2, C2, Cout, Cout, 0, reinterpret_cast<op_t*>(wpack),
                                   as_stream(stream));
 }
 
 extern "C" int fdbm_conv_igemm(const void* in1, int C1, int ksize, const void* in2, int C2, const void* wpack,
                                const float* bias, const float* bias_b, const float* residual, float scale, int batch,
-                               int T, int F, int Cout, float* out_f32, void* out_bf16, double* sums, void* stream) {
+                               int T, int F, int Cout, float* out_f32, void* out_h16, double* sums, void* stream) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(in1 && wpack && bias && batch > 0 && T > 0 && F > 0, "fdbm_conv_igemm: bad arguments");
   ConvArgs a;
-  a.in1 = reinterpret_cast<const __nv_bfloat16*>(in1); a.C1 = C1; a.ksize = ksize;
-  a.in2 = reinterpret_cast<const __nv_bfloat16*>(in2); a.C2 = C2;
-  a.wpack = reinterpret_cast<const __nv_bfloat16*>(wpack);
+  a.in1 = reinterpret_cast<const op_t*>(in1); a.C1 = C1; a.ksize = ksize;
+  a.in2 = reinterpret_cast<const op_t*>(in2); a.C2 = C2;
+  a.wpack = reinterpret_cast<const op_t*>(wpack);
   a.bias = bias; a.bias_b = bias_b; a.bias_b_stride = Cout; a.residual = residual; a.scale = scale;
   a.B = batch; a.T = T; a.F = F; a.Cout = Cout;
-  a.out_f32 = out_f32; a.out_bf16 = reinterpret_cast<__nv_bfloat16*>(out_bf16); a.out_ld = Cout; a.sums = sums;
+  a.out_f32 = out_f32; a.out_h16 = reinterpret_cast<op_t*>(out_h16); a.out_ld = Cout; a.sums = sums;
   return launch_conv_igemm(a, as_stream(stream));
 }

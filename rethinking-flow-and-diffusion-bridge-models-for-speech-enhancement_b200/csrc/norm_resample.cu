@@ -110,10 +110,6 @@ channel_stats_kernel(const float* __restrict__ in, int64_t P, int C, int64_t px_
 // ------------------------------------------------------------------------------------------------
 constexpr int GN_MAXC = 512;
 
-__device__ __forceinline__ uint32_t pack_bf16x2(float a, float b) {
-  __nv_bfloat162 v = __floats2bfloat162_rn(a, b);
-  return *reinterpret_cast<uint32_t*>(&v);
-}
 
 template <int MODE>
 __global__ void __launch_bounds__(256)
@@ -193,11 +189,11 @@ groupnorm_act_kernel(const float* __restrict__ src1, const double* __restrict__ 
       }
     }
     const int64_t o = (static_cast<int64_t>(b) * To * Fo + p) * cg8 + g8;
-    act_out[o] = make_uint4(pack_bf16x2(acc[0], acc[1]), pack_bf16x2(acc[2], acc[3]), pack_bf16x2(acc[4], acc[5]),
-                            pack_bf16x2(acc[6], acc[7]));
+    act_out[o] = make_uint4(pack_op2(acc[0], acc[1]), pack_op2(acc[2], acc[3]), pack_op2(acc[4], acc[5]),
+                            pack_op2(acc[6], acc[7]));
     if (raw_out)
-      raw_out[o] = make_uint4(pack_bf16x2(raw[0], raw[1]), pack_bf16x2(raw[2], raw[3]), pack_bf16x2(raw[4], raw[5]),
-                              pack_bf16x2(raw[6], raw[7]));
+      raw_out[o] = make_uint4(pack_op2(raw[0], raw[1]), pack_op2(raw[2], raw[3]), pack_op2(raw[4], raw[5]),
+                              pack_op2(raw[6], raw[7]));
   }
 }
 
@@ -228,7 +224,7 @@ int launch_channel_stats(const float* in, int B, int T, int F, int C, double* su
 
 int launch_groupnorm_act(const float* src1, const double* sums1, int C1, const float* src2, const double* sums2,
                          int C2, const float* gamma, const float* beta, int B, int T, int F, int silu, int mode,
-                         __nv_bfloat16* act_out, __nv_bfloat16* raw_out, cudaStream_t s) {
+                         op_t* act_out, op_t* raw_out, cudaStream_t s) {
   const int C = C1 + C2;
   FDBM_REQUIRE(C <= GN_MAXC && C1 % 8 == 0 && C2 % 8 == 0 && C % std::min(C / 4, 32) == 0,
                "groupnorm_act: unsupported channels %d+%d", C1, C2);
@@ -276,6 +272,6 @@ extern "C" int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1
   FDBM_REQUIRE(src1 && sums1 && gamma && beta && act_out && batch > 0, "fdbm_groupnorm_act: null pointer");
   FDBM_REQUIRE((C2 == 0) == (src2 == nullptr) && (C2 == 0 || sums2), "fdbm_groupnorm_act: src2/C2 mismatch");
   return launch_groupnorm_act(src1, sums1, C1, src2, sums2, C2, gamma, beta, batch, T, F, silu, mode,
-                              reinterpret_cast<__nv_bfloat16*>(act_out), reinterpret_cast<__nv_bfloat16*>(raw_out),
+                              reinterpret_cast<op_t*>(act_out), reinterpret_cast<op_t*>(raw_out),
                               as_stream(stream));
 }

@@ -91,7 +91,7 @@ struct fdbm_plan {
   std::unordered_map<std::string, Slot> slots;
   int64_t params_numel = 0;
   float* params = nullptr;            // fp32 originals + derived fp32 (combined biases)
-  __nv_bfloat16* wpacked = nullptr;   // packed conv weights
+  op_t* wpacked = nullptr;   // packed conv weights
   int64_t wpacked_bytes = 0;
   int dense_rows = 0;
   bool weights_ready = false;
@@ -102,12 +102,17 @@ struct fdbm_plan {
   const float* cur_x = nullptr; const float* cur_y = nullptr; const float* cur_t = nullptr; int cur_t_stride = 1;
   float* cur_out = nullptr;
   float* d_buf = nullptr;             // backbone output inside the sampler loop
-  std::vector<std::function<int(cudaStream_t)>> ops;        // one forward
+  std::vector<std::function<int(cudaStream_t)>> ops;        // one forward: exactly one kernel launch per entry
+  std::vector<int> op_kind;                                  // FDBM_OP_* of every entry
+  std::vector<double> op_flops;                              // algorithmic FLOPs (2*MAC) of every entry (convs)
   std::vector<std::function<int(cudaStream_t)>> pack_ops;   // weight packing after load_weights
   int n_launches = 0;
   // graph cache
   bool have_graph = false; GraphKey graph_key{}; cudaGraphExec_t graph_exec = nullptr;
+  cudaStream_t capture_stream = nullptr;   // private stream: capture works even when the caller is on the legacy stream
 };
+
+void fdbm_plan_release_sampler_state(fdbm_plan* plan);
 
 namespace {
 
@@ -193,21 +198,34 @@ struct Builder {
   }
   void free_act(Act& a) { release(a.data); release(a.sums); a.data = nullptr; a.sums = nullptr; }
 
-  void op(std::function<int(cudaStream_t)> f, int launches = 1) {
+  void op(std::function<int(cudaStream_t)> f, int kind, double flops = 0.0) {
     if (dry) return;
     P->ops.push_back(std::move(f));
-    P->n_launches += launches;
+    P->op_kind.push_back(kind);
+    P->op_flops.push_back(flops);
+    P->n_launches += 1;
+  }
+  // convolution + (optional) channel statistics of its fp32 output, as two recorded launches
+  void conv_op(ConvArgs c) {
+    double* sums = c.sums;
+    c.sums = nullptr;
+    const double flops = 2.0 * c.B * c.T * c.F * c.Cout * (static_cast<double>(c.ksize) * c.ksize * c.C1 + c.C2);
+    op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV, flops);
+    if (sums) {
+      const float* src = c.out_f32; const int B = c.B, T = c.T, F = c.F, C = c.Cout;
+      op([=](cudaStream_t s) { return launch_channel_stats(src, B, T, F, C, sums, s); }, FDBM_OP_STATS);
+    }
   }
   void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
 
   // packed weights for conv (w1: name, C1, ksize (3, 1 or -1 = NIN [in][out])), optional fused 1x1 w2
-  __nv_bfloat16* pack(const std::string& w1, int C1, int ksize, const std::string& w2, int C2, int Cout,
-                      int rows_total = 0, int row_off = 0, __nv_bfloat16* into = nullptr) {
+  op_t* pack(const std::string& w1, int C1, int ksize, const std::string& w2, int C2, int Cout,
+                      int rows_total = 0, int row_off = 0, op_t* into = nullptr) {
     const int k = ksize == -1 ? 1 : ksize;
     if (rows_total == 0) rows_total = Cout;
-    __nv_bfloat16* dst = into;
+    op_t* dst = into;
     if (!dst) {
-      dst = reinterpret_cast<__nv_bfloat16*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
+      dst = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
       wp_off += (conv_wpack_bytes(C1, k, C2, rows_total) + 1023) / 1024 * 1024;
     }
     const float* p1 = pp(param(w1, static_cast<int64_t>(Cout) * C1 * k * k));
@@ -231,8 +249,8 @@ struct Builder {
     const float* c0b = pp(param(p + "Conv_0.bias", Cout));
     const float* g1w = pp(param(p + "GroupNorm_1.weight", Cout)); const float* g1b = pp(param(p + "GroupNorm_1.bias", Cout));
     const float* c1b = pp(param(p + "Conv_1.bias", Cout));
-    __nv_bfloat16* w0 = pack(p + "Conv_0.weight", Cin, 3, "", 0, Cout);
-    __nv_bfloat16* w1 = shortcut ? pack(p + "Conv_1.weight", Cout, 3, p + "Conv_2.weight", Cin, Cout)
+    op_t* w0 = pack(p + "Conv_0.weight", Cin, 3, "", 0, Cout);
+    op_t* w1 = shortcut ? pack(p + "Conv_1.weight", Cout, 3, p + "Conv_2.weight", Cin, Cout)
                                  : pack(p + "Conv_1.weight", Cout, 3, "", 0, Cout);
     const float* bias1 = c1b;
     if (shortcut) {                                   // Conv_1.bias + Conv_2.bias, summed once at load time
@@ -253,14 +271,14 @@ struct Builder {
     }
 
     const int64_t npx = static_cast<int64_t>(B) * To * Fo;
-    __nv_bfloat16* a0 = alloc<__nv_bfloat16>(npx * Cin);
-    __nv_bfloat16* xr = shortcut ? alloc<__nv_bfloat16>(npx * Cin) : nullptr;
+    op_t* a0 = alloc<op_t>(npx * Cin);
+    op_t* xr = shortcut ? alloc<op_t>(npx * Cin) : nullptr;
     {
       const float* s1 = x1.data; const double* q1 = x1.sums; const int C1 = x1.C;
       const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr; const int C2 = x2 ? x2->C : 0;
       op([=](cudaStream_t s) {
         return launch_groupnorm_act(s1, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
-      });
+      }, FDBM_OP_NORM);
     }
     Act h1 = new_act(Cout, To, Fo);
     {
@@ -268,16 +286,16 @@ struct Builder {
       c.in1 = a0; c.C1 = Cin; c.ksize = 3; c.in2 = nullptr; c.C2 = 0; c.wpack = w0;
       c.bias = c0b; c.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c.bias_b_stride = dense_stride;
       c.residual = nullptr; c.scale = 1.0f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
-      c.out_f32 = h1.data; c.out_bf16 = nullptr; c.out_ld = Cout; c.sums = h1.sums;
-      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, 2);
+      c.out_f32 = h1.data; c.out_h16 = nullptr; c.out_ld = Cout; c.sums = h1.sums;
+      conv_op(c);
     }
     release(a0);
-    __nv_bfloat16* a1 = alloc<__nv_bfloat16>(npx * Cout);
+    op_t* a1 = alloc<op_t>(npx * Cout);
     {
       const float* s1 = h1.data; const double* q1 = h1.sums;
       op([=](cudaStream_t s) {
         return launch_groupnorm_act(s1, q1, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, a1, nullptr, s);
-      });
+      }, FDBM_OP_NORM);
     }
     Act out = new_act(Cout, To, Fo);
     {
@@ -285,8 +303,8 @@ struct Builder {
       c.in1 = a1; c.C1 = Cout; c.ksize = 3; c.in2 = xr; c.C2 = shortcut ? Cin : 0; c.wpack = w1;
       c.bias = bias1; c.bias_b = nullptr; c.bias_b_stride = 0; c.residual = shortcut ? nullptr : x1.data;
       c.scale = 0.70710678118654752f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
-      c.out_f32 = out.data; c.out_bf16 = nullptr; c.out_ld = Cout; c.sums = out.sums;
-      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, 2);
+      c.out_f32 = out.data; c.out_h16 = nullptr; c.out_ld = Cout; c.sums = out.sums;
+      conv_op(c);
     }
     free_act(h1);
     release(a1);
@@ -303,35 +321,35 @@ struct Builder {
     const float* bq = pp(param(p + "NIN_0.b", C));
     param(p + "NIN_1.b", C); param(p + "NIN_2.b", C);
     const float* b3 = pp(param(p + "NIN_3.b", C));
-    __nv_bfloat16* wqkv = pack(p + "NIN_0.W", C, -1, "", 0, C, 3 * C, 0);
+    op_t* wqkv = pack(p + "NIN_0.W", C, -1, "", 0, C, 3 * C, 0);
     pack(p + "NIN_1.W", C, -1, "", 0, C, 3 * C, C, wqkv);
     pack(p + "NIN_2.W", C, -1, "", 0, C, 3 * C, 2 * C, wqkv);
-    __nv_bfloat16* w3 = pack(p + "NIN_3.W", C, -1, "", 0, C);
+    op_t* w3 = pack(p + "NIN_3.W", C, -1, "", 0, C);
     const int64_t npx = static_cast<int64_t>(B) * T * F;
-    __nv_bfloat16* a = alloc<__nv_bfloat16>(npx * C);
+    op_t* a = alloc<op_t>(npx * C);
     {
       const float* s1 = x.data; const double* q1 = x.sums;
       op([=](cudaStream_t s) {
         return launch_groupnorm_act(s1, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, a, nullptr, s);
-      });
+      }, FDBM_OP_NORM);
     }
-    __nv_bfloat16* qkv = alloc<__nv_bfloat16>(npx * 3 * C);
+    op_t* qkv = alloc<op_t>(npx * 3 * C);
     {
       ConvArgs c{};
       c.in1 = a; c.C1 = C; c.ksize = 1; c.wpack = wqkv; c.bias = bq; c.scale = 1.0f; c.B = B; c.T = T; c.F = F; c.Cout = 3 * C;
-      c.out_bf16 = qkv; c.out_ld = 3 * C;
-      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); });
+      c.out_h16 = qkv; c.out_ld = 3 * C;
+      conv_op(c);
     }
     release(a);
-    __nv_bfloat16* o = alloc<__nv_bfloat16>(npx * C);
-    op([=](cudaStream_t s) { return launch_attention(qkv, qkv + C, qkv + 2 * C, 3 * C, B, T * F, C, o, C, s); });
+    op_t* o = alloc<op_t>(npx * C);
+    op([=](cudaStream_t s) { return launch_attention(qkv, qkv + C, qkv + 2 * C, 3 * C, B, T * F, C, o, C, s); }, FDBM_OP_ATTN);
     release(qkv);
     Act out = new_act(C, T, F);
     {
       ConvArgs c{};
       c.in1 = o; c.C1 = C; c.ksize = 1; c.wpack = w3; c.bias = b3; c.residual = x.data; c.scale = 0.70710678118654752f;
       c.B = B; c.T = T; c.F = F; c.Cout = C; c.out_f32 = out.data; c.out_ld = C; c.sums = out.sums;
-      op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, 2);
+      conv_op(c);
     }
     release(o);
     return out;
@@ -370,8 +388,8 @@ struct Builder {
       fdbm_plan* plp = P;
       op([=](cudaStream_t s) {
         return launch_temb(plp->cur_t, fw, nf, w1, b1, w2, b2, B, plp->cur_t_stride, temb_act, s);
-      });
-      op([=](cudaStream_t s) { return launch_dense_all(temb_act, dwp, dbp, B, 4 * nf, rows, dense, s); });
+      }, FDBM_OP_SMALL);
+      op([=](cudaStream_t s) { return launch_dense_all(temb_act, dwp, dbp, B, 4 * nf, rows, dense, s); }, FDBM_OP_SMALL);
     }
     const int dstride = pl.dense_rows;
 
@@ -380,7 +398,7 @@ struct Builder {
     float* pyr_in = alloc<float>(static_cast<int64_t>(B) * T * F * Cp);
     {
       fdbm_plan* plp = P; const int Tc = T, Fc = F; float* dst = pyr_in; const bool pred = A.predictive;
-      op([=](cudaStream_t s) { return launch_pack_input(plp->cur_x, pred ? nullptr : plp->cur_y, B, Tc, plp->F_io, Fc, Cp, dst, s); });
+      op([=](cudaStream_t s) { return launch_pack_input(plp->cur_x, pred ? nullptr : plp->cur_y, B, Tc, plp->F_io, Fc, Cp, dst, s); }, FDBM_OP_SKINNY);
     }
     std::vector<Act> hs;
     {
@@ -388,10 +406,8 @@ struct Builder {
       const float* w = pp(param(pre(m) + "weight", static_cast<int64_t>(nf) * Cp * 9)); const float* b = pp(param(pre(m) + "bias", nf));
       Act h0 = new_act(nf, T, F);
       const int Tc = T, Fc = F; float* src = pyr_in;
-      op([=](cudaStream_t s) {
-        if (int rc = launch_conv_in(src, Cp, w, b, B, Tc, Fc, nf, h0.data, s)) return rc;
-        return launch_channel_stats(h0.data, B, Tc, Fc, nf, h0.sums, s);
-      }, 2);
+      op([=](cudaStream_t s) { return launch_conv_in(src, Cp, w, b, B, Tc, Fc, nf, h0.data, s); }, FDBM_OP_SKINNY);
+      op([=](cudaStream_t s) { return launch_channel_stats(h0.data, B, Tc, Fc, nf, h0.sums, s); }, FDBM_OP_STATS);
       hs.push_back(h0);
     }
     // ---- down path
@@ -406,7 +422,7 @@ struct Builder {
         float* pyr_next = alloc<float>(static_cast<int64_t>(B) * (T / 2) * (F / 2) * Cp);
         {
           const int Tc = T, Fc = F; float* src = pyr_in;
-          op([=](cudaStream_t s) { return launch_fir_resample(src, B, Tc, Fc, Cp, 1, pyr_next, s); });
+          op([=](cudaStream_t s) { return launch_fir_resample(src, B, Tc, Fc, Cp, 1, pyr_next, s); }, FDBM_OP_SKINNY);
         }
         release(pyr_in);
         pyr_in = pyr_next;
@@ -415,10 +431,8 @@ struct Builder {
         const float* w = pp(param(pre(m) + "Conv_0.weight", static_cast<int64_t>(m.cout) * Cp)); const float* b = pp(param(pre(m) + "Conv_0.bias", m.cout));
         {
           const int Tc = T, Fc = F, C = m.cout; float* src = pyr_in;
-          op([=](cudaStream_t s) {
-            if (int rc = launch_combine(h.data, src, Cp, w, b, B, Tc, Fc, C, s)) return rc;
-            return launch_channel_stats(h.data, B, Tc, Fc, C, h.sums, s);
-          }, 2);
+          op([=](cudaStream_t s) { return launch_combine(h.data, src, Cp, w, b, B, Tc, Fc, C, s); }, FDBM_OP_SKINNY);
+          op([=](cudaStream_t s) { return launch_channel_stats(h.data, B, Tc, Fc, C, h.sums, s); }, FDBM_OP_STATS);
         }
         hs.push_back(h);
       }
@@ -447,14 +461,14 @@ struct Builder {
         const int C = mg.cin, Tc = h.T, Fc = h.F;
         const float* gw = pp(param(pre(mg) + "weight", C)); const float* gb = pp(param(pre(mg) + "bias", C));
         const float* w = pp(param(pre(mc) + "weight", static_cast<int64_t>(Cp) * C * 9)); const float* b = pp(param(pre(mc) + "bias", Cp));
-        __nv_bfloat16* a = alloc<__nv_bfloat16>(static_cast<int64_t>(B) * Tc * Fc * C);
+        op_t* a = alloc<op_t>(static_cast<int64_t>(B) * Tc * Fc * C);
         float* pyr_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
         float* prev = pyramid;
         const float* src = h.data; const double* sums = h.sums;
         op([=](cudaStream_t s) {
-          if (int rc = launch_groupnorm_act(src, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s)) return rc;
-          return launch_pyramid_conv(a, C, w, b, prev, Cp, B, Tc, Fc, pyr_new, s);
-        }, 2);
+          return launch_groupnorm_act(src, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s);
+        }, FDBM_OP_NORM);
+        op([=](cudaStream_t s) { return launch_pyramid_conv(a, C, w, b, prev, Cp, B, Tc, Fc, pyr_new, s); }, FDBM_OP_SKINNY);
         release(a);
         release(pyramid);
         pyramid = pyr_new;
@@ -466,7 +480,7 @@ struct Builder {
     {
       const float* w = pp(param("output_layer.weight", 2 * Cp)); const float* b = pp(param("output_layer.bias", 2));
       const int Tc = pl.T, Fc = pl.F; fdbm_plan* plp = P; float* pyr = pyramid;
-      op([=](cudaStream_t s) { return launch_output_layer(pyr, Cp, w, b, B, Tc, Fc, plp->F_io, plp->cur_out, s); });
+      op([=](cudaStream_t s) { return launch_output_layer(pyr, Cp, w, b, B, Tc, Fc, plp->F_io, plp->cur_out, s); }, FDBM_OP_SKINNY);
     }
     release(pyramid);
     return FDBM_OK;
@@ -535,6 +549,8 @@ extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, 
 extern "C" int fdbm_plan_destroy(fdbm_plan* plan) {
   if (!plan) return FDBM_OK;
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
+  if (plan->capture_stream) cudaStreamDestroy(plan->capture_stream);
+  fdbm_plan_release_sampler_state(plan);
   cudaFree(plan->arena); cudaFree(plan->params); cudaFree(plan->wpacked); cudaFree(plan->d_buf);
   delete plan;
   return FDBM_OK;
@@ -577,6 +593,47 @@ extern "C" int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float*
   return run_ops(plan, as_stream(stream));
 }
 
+extern "C" int fdbm_plan_profile_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
+                                         float* ms, int* kinds, double* flops, int max_ops, void* stream) {
+  FDBM_REQUIRE(plan && x && out && ms && kinds && flops, "fdbm_plan_profile_forward: null pointer");
+  if (!plan->weights_ready) { set_error("fdbm_plan_profile_forward: weights not loaded"); return FDBM_ESTATE; }
+  FDBM_REQUIRE(plan->arch.predictive || (y && t), "fdbm_plan_profile_forward: y and t are required");
+  const int n = static_cast<int>(plan->ops.size());
+  FDBM_REQUIRE(max_ops >= n, "fdbm_plan_profile_forward: need room for %d entries", n);
+  cudaStream_t s = as_stream(stream);
+  plan->cur_x = x; plan->cur_y = y; plan->cur_t = t; plan->cur_t_stride = 1; plan->cur_out = out;
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) FDBM_CUDA(cudaEventCreate(&e));
+  int rc = FDBM_OK;
+  FDBM_CUDA(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n && rc == FDBM_OK; ++i) {
+    rc = plan->ops[i](s);
+    if (rc == FDBM_OK && cudaEventRecord(ev[i + 1], s) != cudaSuccess) rc = FDBM_ECUDA;
+  }
+  if (rc == FDBM_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__);
+  for (int i = 0; i < n && rc == FDBM_OK; ++i) {
+    cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]);
+    kinds[i] = plan->op_kind[i];
+    flops[i] = plan->op_flops[i];
+  }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc == FDBM_OK ? n : rc;
+}
+
+namespace {
+
+struct SamplerState {               // plan-owned staging so that one captured graph serves every call
+  float* y = nullptr; float* x = nullptr; float* noise = nullptr; int64_t noise_elems = 0;
+  float* times = nullptr; float* coef = nullptr; uint64_t* rng = nullptr; int cap_steps = 0;
+  std::vector<float> h_times, h_coef;
+};
+std::map<fdbm_plan*, SamplerState>& sampler_states() { static std::map<fdbm_plan*, SamplerState> m; return m; }
+
+}  // namespace
+
+namespace fdbm { int launch_bridge_step_rng(float* x, const float* d, const float* third, const float* coef, int kind,
+                                            const uint64_t* rng, uint64_t offset, int64_t n_complex, cudaStream_t s); }
+
 extern "C" int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
                                 int n_steps, int kind, const float* noise, uint64_t seed, void* stream) {
   FDBM_REQUIRE(plan && y && x && times && coef && n_steps > 0, "fdbm_sampler_run: bad arguments");
@@ -585,34 +642,84 @@ extern "C" int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const
   if (!plan->weights_ready) { set_error("fdbm_sampler_run: weights not loaded"); return FDBM_ESTATE; }
   cudaStream_t s = as_stream(stream);
   const int64_t n_complex = static_cast<int64_t>(plan->B) * plan->F_io * plan->T;
-  auto body = [&](cudaStream_t st) -> int {
+  const size_t spec_bytes = static_cast<size_t>(n_complex) * 8;
+  SamplerState& st = sampler_states()[plan];
+  if (!st.y) {
+    FDBM_CUDA(cudaMalloc(&st.y, spec_bytes));
+    FDBM_CUDA(cudaMalloc(&st.x, spec_bytes));
+    FDBM_CUDA(cudaMalloc(&st.rng, 2 * sizeof(uint64_t)));
+  }
+  if (st.cap_steps < n_steps) {
+    cudaFree(st.times); cudaFree(st.coef);
+    FDBM_CUDA(cudaMalloc(&st.times, sizeof(float) * n_steps));
+    FDBM_CUDA(cudaMalloc(&st.coef, sizeof(float) * 3 * n_steps));
+    st.cap_steps = n_steps;
+    st.h_times.clear();
+  }
+  const bool want_noise = kind == FDBM_STEP_SDE && noise != nullptr;
+  if (want_noise && st.noise_elems < 2 * n_complex * n_steps) {
+    cudaFree(st.noise);
+    FDBM_CUDA(cudaMalloc(&st.noise, spec_bytes * n_steps));
+    st.noise_elems = 2 * n_complex * n_steps;
+    plan->have_graph = false;
+  }
+  // stage the call's arguments into the plan-owned buffers (all stream-ordered)
+  FDBM_CUDA(cudaMemcpyAsync(st.y, y, spec_bytes, cudaMemcpyDeviceToDevice, s));
+  FDBM_CUDA(cudaMemcpyAsync(st.x, x, spec_bytes, cudaMemcpyDeviceToDevice, s));
+  if (want_noise) FDBM_CUDA(cudaMemcpyAsync(st.noise, noise, spec_bytes * n_steps, cudaMemcpyDeviceToDevice, s));
+  const std::vector<float> ht(times, times + n_steps), hc(coef, coef + 3 * n_steps);
+  if (ht != st.h_times || hc != st.h_coef) {
+    FDBM_CUDA(cudaMemcpyAsync(st.times, times, sizeof(float) * n_steps, cudaMemcpyHostToDevice, s));
+    FDBM_CUDA(cudaMemcpyAsync(st.coef, coef, sizeof(float) * 3 * n_steps, cudaMemcpyHostToDevice, s));
+    FDBM_CUDA(cudaStreamSynchronize(s));                 // the host arrays may be temporaries of the caller
+    st.h_times = ht; st.h_coef = hc;
+  }
+  const uint64_t rng_host[2] = {seed, 0};
+  FDBM_CUDA(cudaMemcpyAsync(st.rng, rng_host, sizeof(rng_host), cudaMemcpyHostToDevice, s));
+
+  auto body = [&](cudaStream_t cs) -> int {
     for (int i = 0; i < n_steps; ++i) {
-      plan->cur_x = x; plan->cur_y = y; plan->cur_t = times + i; plan->cur_t_stride = 0; plan->cur_out = plan->d_buf;
-      if (int rc = run_ops(plan, st)) return rc;
-      const float* third = kind == FDBM_STEP_ODE ? y : (noise ? noise + 2 * n_complex * i : nullptr);
-      if (int rc = fdbm_bridge_step(x, plan->d_buf, third, coef + 3 * i, kind, seed, static_cast<uint64_t>(i) + 1,
-                                    n_complex, st))
+      plan->cur_x = st.x; plan->cur_y = st.y; plan->cur_t = st.times + i; plan->cur_t_stride = 0; plan->cur_out = plan->d_buf;
+      if (int rc = run_ops(plan, cs)) return rc;
+      const float* third = kind == FDBM_STEP_ODE ? st.y : (want_noise ? st.noise + 2 * n_complex * i : nullptr);
+      if (int rc = launch_bridge_step_rng(st.x, plan->d_buf, third, st.coef + 3 * i, kind, st.rng,
+                                          static_cast<uint64_t>(i) + 1, n_complex, cs))
         return rc;
     }
     return FDBM_OK;
   };
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   FDBM_CUDA(cudaStreamIsCapturing(s, &cap));
-  if (cap != cudaStreamCaptureStatusNone) return body(s);          // caller is capturing: just record into it
-  GraphKey key{{y, x, times, coef, noise, nullptr}, n_steps, kind, seed};
-  if (!(plan->have_graph && plan->graph_key == key)) {
-    if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; plan->have_graph = false; }
-    cudaGraph_t graph = nullptr;
-    FDBM_CUDA(cudaStreamBeginCapture(s, cudaStreamCaptureModeThreadLocal));
-    const int rc = body(s);
-    const cudaError_t e = cudaStreamEndCapture(s, &graph);
-    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-    const cudaError_t e2 = cudaGraphInstantiate(&plan->graph_exec, graph, 0);
-    cudaGraphDestroy(graph);
-    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
-    plan->graph_key = key; plan->have_graph = true;
+  if (cap != cudaStreamCaptureStatusNone) {                       // caller is capturing: record into its graph
+    if (int rc = body(s)) return rc;
+  } else {
+    GraphKey key{{st.y, st.x, st.times, st.coef, want_noise ? st.noise : nullptr, nullptr}, n_steps, kind, 0};
+    if (!(plan->have_graph && plan->graph_key == key)) {
+      if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; plan->have_graph = false; }
+      cudaGraph_t graph = nullptr;
+      if (!plan->capture_stream) FDBM_CUDA(cudaStreamCreateWithFlags(&plan->capture_stream, cudaStreamNonBlocking));
+      cudaStream_t cs = plan->capture_stream;
+      FDBM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+      const int rc = body(cs);
+      const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+      const cudaError_t e2 = cudaGraphInstantiate(&plan->graph_exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (e2 != cudaSuccess) return cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
+      plan->graph_key = key; plan->have_graph = true;
+    }
+    FDBM_CUDA(cudaGraphLaunch(plan->graph_exec, s));
   }
-  FDBM_CUDA(cudaGraphLaunch(plan->graph_exec, s));
+  FDBM_CUDA(cudaMemcpyAsync(x, st.x, spec_bytes, cudaMemcpyDeviceToDevice, s));
   return FDBM_OK;
+}
+
+void fdbm_plan_release_sampler_state(fdbm_plan* plan) {
+  auto& m = sampler_states();
+  auto it = m.find(plan);
+  if (it == m.end()) return;
+  SamplerState& st = it->second;
+  cudaFree(st.y); cudaFree(st.x); cudaFree(st.noise); cudaFree(st.times); cudaFree(st.coef); cudaFree(st.rng);
+  m.erase(it);
 }

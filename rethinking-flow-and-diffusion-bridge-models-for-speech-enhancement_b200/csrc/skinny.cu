@@ -120,7 +120,7 @@ combine_kernel(float4* __restrict__ h, const float* __restrict__ pyr, int Cp, co
 // ------------------------------------------------------------------------------------------------
 template <int VEC, int CP>
 __global__ void __launch_bounds__(256)
-pyramid_conv_kernel(const __nv_bfloat16* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias,
+pyramid_conv_kernel(const op_t* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias,
                     const float* __restrict__ prev, int B, int T, int F, float* __restrict__ out) {
   constexpr int C = VEC * 32;
   extern __shared__ float ws[];                  // [9][VEC][32][CP]
@@ -147,18 +147,18 @@ pyramid_conv_kernel(const __nv_bfloat16* __restrict__ act, const float* __restri
     for (int tap = 0; tap < 9; ++tap) {
       const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
       if (ff < 0 || ff >= F || tt < 0 || tt >= T) continue;
-      const __nv_bfloat16* src = act + ((static_cast<int64_t>(b) * T + tt) * F + ff) * C + lane * VEC;
+      const op_t* src = act + ((static_cast<int64_t>(b) * T + tt) * F + ff) * C + lane * VEC;
       float xv[VEC];
       if (VEC == 8) {
         const uint4 raw = *reinterpret_cast<const uint4*>(src);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f2 = __bfloat1622float2(h2[j]); xv[2 * j] = f2.x; xv[2 * j + 1] = f2.y; }
+        for (int j = 0; j < 4; ++j) { const float2 f2 = op22f2(h2[j]); xv[2 * j] = f2.x; xv[2 * j + 1] = f2.y; }
       } else {
         const uint2 raw = *reinterpret_cast<const uint2*>(src);
-        const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+        const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
-        for (int j = 0; j < 2; ++j) { const float2 f2 = __bfloat1622float2(h2[j]); xv[2 * j] = f2.x; xv[2 * j + 1] = f2.y; }
+        for (int j = 0; j < 2; ++j) { const float2 f2 = op22f2(h2[j]); xv[2 * j] = f2.x; xv[2 * j + 1] = f2.y; }
       }
 #pragma unroll
       for (int j = 0; j < VEC; ++j) {
@@ -262,7 +262,7 @@ int launch_combine(float* h, const float* pyr, int Cp, const float* w, const flo
 }
 
 template <int VEC, int CP>
-static int launch_pyr(const __nv_bfloat16* act, const float* w, const float* bias, const float* prev, int B, int T,
+static int launch_pyr(const op_t* act, const float* w, const float* bias, const float* prev, int B, int T,
                       int F, float* out, cudaStream_t s) {
   const size_t smem = sizeof(float) * 9 * VEC * 32 * CP;
   static bool attr = false;
@@ -277,7 +277,7 @@ static int launch_pyr(const __nv_bfloat16* act, const float* w, const float* bia
   return FDBM_OK;
 }
 
-int launch_pyramid_conv(const __nv_bfloat16* act, int C, const float* w, const float* bias, const float* prev, int Cp,
+int launch_pyramid_conv(const op_t* act, int C, const float* w, const float* bias, const float* prev, int Cp,
                         int B, int T, int F, float* out, cudaStream_t s) {
   FDBM_REQUIRE((C == 128 || C == 256) && (Cp == 4 || Cp == 2), "pyramid_conv: unsupported channels %d -> %d", C, Cp);
   FDBM_REQUIRE(prev == nullptr || (T % 2 == 0 && F % 2 == 0), "pyramid_conv: odd size with a coarser level");

@@ -102,8 +102,8 @@ __device__ __forceinline__ void fence_before_sync() {
 __device__ __forceinline__ void fence_after_sync() {
   asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
 }
-// D[tmem] (+)= A[smem] * B[smem]^T, bf16 x bf16 -> fp32, issued by ONE thread.
-__device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+// D[tmem] (+)= A[smem] * B[smem]^T, 16-bit x 16-bit -> fp32, issued by ONE thread.
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
                                          uint32_t accumulate) {
   asm volatile(
       "{\n\t.reg .pred p;\n\t"
@@ -147,11 +147,11 @@ __device__ __forceinline__ uint64_t make_desc_sw128(uint32_t smem_addr, uint32_t
   d |= static_cast<uint64_t>(2) << 61;                              // SWIZZLE_128B
   return d;
 }
-// Instruction descriptor for kind::f16: D=fp32, A=B=bf16, both K-major, dense.
-__host__ __device__ constexpr uint32_t make_idesc_bf16(int M, int N) {
-  return (1u << 4)                          // c_format  = F32
-         | (1u << 7)                        // a_format  = BF16
-         | (1u << 10)                       // b_format  = BF16
+// Instruction descriptor for kind::f16: D=fp32, A and B fp16 (format 0) or bf16 (format 1), both K-major, dense.
+__host__ __device__ constexpr uint32_t make_idesc_f16(int M, int N, int is_bf16) {
+  return (1u << 4)                                               // c_format  = F32
+         | (static_cast<uint32_t>(is_bf16) << 7)                 // a_format
+         | (static_cast<uint32_t>(is_bf16) << 10)                // b_format
          | (static_cast<uint32_t>(N >> 3) << 17) | (static_cast<uint32_t>(M >> 4) << 24);
 }
 

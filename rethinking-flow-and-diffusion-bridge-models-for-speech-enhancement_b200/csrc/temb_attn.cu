@@ -85,9 +85,9 @@ dense_all_kernel(const float* __restrict__ act, const float* __restrict__ w, con
 constexpr int ATT_WARPS = 8;
 
 __global__ void __launch_bounds__(ATT_WARPS * 32)
-attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __restrict__ k,
-                 const __nv_bfloat16* __restrict__ v, int ld, int L, int C, float scale,
-                 __nv_bfloat16* __restrict__ o, int ldo) {
+attention_kernel(const op_t* __restrict__ q, const op_t* __restrict__ k,
+                 const op_t* __restrict__ v, int ld, int L, int C, float scale,
+                 op_t* __restrict__ o, int ldo) {
   extern __shared__ float sm[];                       // per warp: q[C] | p[L]
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
@@ -96,7 +96,7 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
   float* sq = sm + warp * (C + L);
   float* sp = sq + C;
   const int64_t base = static_cast<int64_t>(b) * L;
-  for (int c = lane; c < C; c += 32) sq[c] = __bfloat162float(q[(base + qi) * ld + c]) * scale;
+  for (int c = lane; c < C; c += 32) sq[c] = op2f(q[(base + qi) * ld + c]) * scale;
   __syncwarp();
   float mx = -INFINITY;
   for (int j = lane; j < L; j += 32) {
@@ -104,10 +104,10 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
     float acc = 0.f;
     for (int c8 = 0; c8 < C / 8; ++c8) {
       const uint4 raw = kr[c8];
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float2 f2 = __bfloat1622float2(h2[u]);
+        const float2 f2 = op22f2(h2[u]);
         acc = fmaf(f2.x, sq[c8 * 8 + 2 * u], acc);
         acc = fmaf(f2.y, sq[c8 * 8 + 2 * u + 1], acc);
       }
@@ -134,17 +134,17 @@ attention_kernel(const __nv_bfloat16* __restrict__ q, const __nv_bfloat16* __res
     for (int j = 0; j < L; ++j) {
       const float pj = sp[j];
       const uint4 raw = *reinterpret_cast<const uint4*>(v + (base + j) * ld + c0);
-      const __nv_bfloat162* h2 = reinterpret_cast<const __nv_bfloat162*>(&raw);
+      const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
 #pragma unroll
       for (int u = 0; u < 4; ++u) {
-        const float2 f2 = __bfloat1622float2(h2[u]);
+        const float2 f2 = op22f2(h2[u]);
         acc[2 * u] = fmaf(pj, f2.x, acc[2 * u]);
         acc[2 * u + 1] = fmaf(pj, f2.y, acc[2 * u + 1]);
       }
     }
-    __nv_bfloat162 ov[4];
+    op2_t ov[4];
 #pragma unroll
-    for (int u = 0; u < 4; ++u) ov[u] = __floats2bfloat162_rn(acc[2 * u] * inv, acc[2 * u + 1] * inv);
+    for (int u = 0; u < 4; ++u) ov[u] = f2op2(acc[2 * u] * inv, acc[2 * u + 1] * inv);
     *reinterpret_cast<uint4*>(o + (base + qi) * ldo + c0) = *reinterpret_cast<uint4*>(ov);
   }
 }
@@ -166,8 +166,8 @@ int launch_dense_all(const float* temb_act, const float* w, const float* bias, i
   return FDBM_OK;
 }
 
-int launch_attention(const __nv_bfloat16* q, const __nv_bfloat16* k, const __nv_bfloat16* v, int ld, int B, int L,
-                     int C, __nv_bfloat16* o, int ldo, cudaStream_t s) {
+int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B, int L,
+                     int C, op_t* o, int ldo, cudaStream_t s) {
   FDBM_REQUIRE(C % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "attention: channels / strides must be multiples of 8");
   const size_t smem = sizeof(float) * ATT_WARPS * (C + L);
   FDBM_REQUIRE(smem <= 200 * 1024, "attention: sequence length %d too long for the shared-memory score buffer", L);
@@ -190,7 +190,7 @@ extern "C" int fdbm_attention(const void* q, const void* k, const void* v, int b
                               void* stream) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(q && k && v && o && batch > 0 && L > 0, "fdbm_attention: bad arguments");
-  return launch_attention(reinterpret_cast<const __nv_bfloat16*>(q), reinterpret_cast<const __nv_bfloat16*>(k),
-                          reinterpret_cast<const __nv_bfloat16*>(v), C, batch, L, C,
-                          reinterpret_cast<__nv_bfloat16*>(o), C, as_stream(stream));
+  return launch_attention(reinterpret_cast<const op_t*>(q), reinterpret_cast<const op_t*>(k),
+                          reinterpret_cast<const op_t*>(v), C, batch, L, C,
+                          reinterpret_cast<op_t*>(o), C, as_stream(stream));
 }

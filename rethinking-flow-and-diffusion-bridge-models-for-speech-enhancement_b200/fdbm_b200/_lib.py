@@ -17,11 +17,11 @@ FDBM_STEP = {"ode_ei": 0, "sde_ei": 1}
 
 # every symbol include/fdbm_b200.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTS = [
-    "fdbm_last_error", "fdbm_version", "fdbm_check_device",
+    "fdbm_last_error", "fdbm_version", "fdbm_check_device", "fdbm_operand_is_bf16",
     "fdbm_stft_compress", "fdbm_decompress_istft", "fdbm_spec_transform", "fdbm_pad_spec",
     "fdbm_prior_sample", "fdbm_bridge_step",
     "fdbm_plan_create", "fdbm_plan_destroy", "fdbm_plan_load_weights", "fdbm_plan_device_bytes",
-    "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run",
+    "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run", "fdbm_plan_profile_forward",
     "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm",
     "fdbm_pack_conv_weights", "fdbm_attention",
 ]
@@ -54,6 +54,7 @@ def load() -> C.CDLL:
         "fdbm_last_error": (C.c_char_p, []),
         "fdbm_version": (i, []),
         "fdbm_check_device": (i, []),
+        "fdbm_operand_is_bf16": (i, []),
         "fdbm_stft_compress": (i, [p, i, i64, i64, p, i, i, i, f, f, i, i, p, p]),
         "fdbm_decompress_istft": (i, [p, i, i, p, i, i, i, f, f, i64, i64, p, p]),
         "fdbm_spec_transform": (i, [p, p, i64, i, f, f, i, p]),
@@ -67,6 +68,7 @@ def load() -> C.CDLL:
         "fdbm_plan_num_launches": (i, [p]),
         "fdbm_ncsnpp_forward": (i, [p, p, p, p, p, p]),
         "fdbm_sampler_run": (i, [p, p, p, p, p, i, i, p, u64, p]),
+        "fdbm_plan_profile_forward": (i, [p, p, p, p, p, p, p, p, i, p]),
         "fdbm_fir_resample": (i, [p, i, i, i, i, i, p, p]),
         "fdbm_channel_stats": (i, [p, i, i, i, i, p, p]),
         "fdbm_groupnorm_act": (i, [p, p, i, p, p, i, p, p, i, i, i, i, i, p, p, p]),
@@ -86,6 +88,12 @@ def check(rc: int, what: str = "fdbm") -> None:
     if rc != 0:
         msg = load().fdbm_last_error()
         raise RuntimeError(f"{what} failed (code {rc}): {msg.decode() if msg else 'unknown error'}")
+
+
+def operand_dtype():
+    """torch dtype of the library's 16-bit GEMM operands (fp16 unless built with -DFDBM_OPERAND_BF16)."""
+    import torch
+    return torch.bfloat16 if load().fdbm_operand_is_bf16() else torch.float16
 
 
 def ptr(t) -> int:

@@ -70,6 +70,38 @@ def _fan_avg_uniform(shape, scale=1.0):
     return (torch.rand(*shape) * 2.0 - 1.0) * math.sqrt(3 * var)
 
 
+@torch.no_grad()
+def sensitise_(net: nn.Module, seed: int = 0) -> nn.Module:
+    """Re-randomise a backbone in place so that every kernel influences the output: the reference's
+    default initialisation zeroes 56 weight tensors (init_scale=0 -> 1e-10), which makes the network
+    output a constant ('two things a fresh reader must know').  Weights get the same
+    fan_avg-uniform law with scale 1, biases N(0, 0.02), GroupNorm affine 1 + N(0, 0.1) / N(0, 0.1).
+    Used for benchmarks and smoke tests with random-init weights; never needed for trained checkpoints."""
+    g = torch.Generator().manual_seed(seed)
+    for name, p in net.named_parameters():
+        if name.endswith(".W") and p.dim() == 1:
+            continue                                                     # Fourier features keep their draw
+        if p.dim() >= 2:
+            shape = tuple(p.shape)
+            rf = int(np.prod(shape[2:])) if len(shape) > 2 else 1
+            var = 1.0 / ((shape[1] * rf + shape[0] * rf) / 2)
+            new = (torch.rand(shape, generator=g) * 2 - 1) * math.sqrt(3 * var)
+        elif "GroupNorm" in name or (name.count(".") == 2 and name.endswith(("weight", "bias")) and p.dim() == 1
+                                     and _is_gn_entry(net, name)):
+            new = torch.randn(p.shape, generator=g) * 0.1 + (1.0 if name.endswith("weight") else 0.0)
+        else:
+            new = torch.randn(p.shape, generator=g) * 0.02
+        p.copy_(new.to(p.device, p.dtype))
+    return net
+
+
+def _is_gn_entry(net, name):
+    parts = name.split(".")
+    if parts[0] != "all_modules":
+        return False
+    return net._table[int(parts[1])][0] == "gn"
+
+
 class _Holder(nn.Module):
     """Parameter container; sub-holders are created on demand so dotted names match the reference."""
 
@@ -211,6 +243,21 @@ class _NCSNppBase(nn.Module):
         lib = _lib.load()
         return {"device_bytes": lib.fdbm_plan_device_bytes(h), "launches": lib.fdbm_plan_num_launches(h)}
 
+    def profile_forward(self, x, y=None, t=None, max_ops=4096):
+        """One forward with a CUDA event pair around every kernel launch (bench.py's roofline leg).
+        Returns [(milliseconds, kind, algorithmic_flops), ...] in launch order; kinds are FDBM_OP_*."""
+        x = self._check_spec(x, "x")
+        plan = self._plan(x.device, x.shape[0], x.shape[3])
+        out = torch.empty_like(x)
+        ms = (C.c_float * max_ops)(); kinds = (C.c_int * max_ops)(); flops = (C.c_double * max_ops)()
+        y = None if y is None else self._check_spec(y, "y")
+        t = None if t is None else t.to(device=x.device, dtype=torch.float32).contiguous()
+        n = _lib.load().fdbm_plan_profile_forward(plan, ptr(x), ptr(y), ptr(t), ptr(out), ms, kinds, flops, max_ops,
+                                                  current_stream())
+        if n < 0:
+            check(n, "fdbm_plan_profile_forward")
+        return [(ms[i], kinds[i], flops[i]) for i in range(n)]
+
     def _check_spec(self, s, name):
         if not (s.is_cuda and s.dtype == torch.complex64 and s.dim() == 4 and s.shape[1] == 1
                 and s.shape[2] == self.image_size + 1):
@@ -226,6 +273,9 @@ class _NCSNppBase(nn.Module):
         y = self._check_spec(y, "y")
         if not x.is_contiguous():
             raise RuntimeError("x must be contiguous")
+        if times.is_cuda or table.is_cuda or times.dtype != torch.float32 or table.dtype != torch.float32:
+            raise RuntimeError("times / table must be fp32 host tensors")
+        times, table = times.contiguous(), table.contiguous()
         plan = self._plan(y.device, y.shape[0], y.shape[3])
         check(_lib.load().fdbm_sampler_run(plan, ptr(y), ptr(x), ptr(times), ptr(table), times.numel(), kind, ptr(noise),
                                            seed, current_stream()), "fdbm_sampler_run")

@@ -115,8 +115,8 @@ class Bridge:
     def _run(self, model, y, st):
         with torch.no_grad():
             y = y.contiguous()
-            table = self.coefficient_table(st).to(y.device)
-            times = self.time_grid()[:-1].float().contiguous().to(y.device)      # t_prev of every step
+            table = self.coefficient_table(st)                                     # host, fp32 [N,3]
+            times = self.time_grid()[:-1].float().contiguous()                     # host: t_prev of every step
             xt = self.prior_sampling(y)
             kind = FDBM_STEP[st]
             noise = None
@@ -128,6 +128,7 @@ class Bridge:
                 return xt
             lib = _lib.load()
             B = xt.shape[0]
+            table, times = table.to(y.device), times.to(y.device)
             for i in range(self.N):
                 est = model(xt, y, times[i] * torch.ones(B, device=y.device)).contiguous()
                 third = y if st == "ode_ei" else (noise[i] if noise is not None else None)

@@ -20,6 +20,11 @@ def lib():
     return lb
 
 
+def _h16():
+    from fdbm_b200 import _lib
+    return _lib.operand_dtype()
+
+
 def _stream():
     return torch.cuda.current_stream().cuda_stream
 
@@ -188,28 +193,28 @@ def test_groupnorm_act(lib, C1, C2, mode):
         sums2 = torch.empty(B, C2, 2, dtype=torch.float64, device="cuda")
         _check(lib, lib.fdbm_channel_stats(s2.data_ptr(), B, T, Fq, C2, sums2.data_ptr(), _stream()))
     To, Fo = act.shape[3], act.shape[2]
-    a_out = torch.empty(B, To, Fo, Cc, dtype=torch.bfloat16, device="cuda")
+    a_out = torch.empty(B, To, Fo, Cc, dtype=_h16(), device="cuda")
     r_out = torch.empty_like(a_out)
     gd, bd = gamma.cuda(), beta.cuda()
     _check(lib, lib.fdbm_groupnorm_act(s1.data_ptr(), sums1.data_ptr(), C1, s2.data_ptr() if C2 else None,
                                        sums2.data_ptr() if C2 else None, C2, gd.data_ptr(),
                                        bd.data_ptr(), B, T, Fq, 1, mode, a_out.data_ptr(), r_out.data_ptr(),
                                        _stream()))
-    assert rel_l2(ntfc_to_nchw(a_out.float()), act) < 4e-3            # bf16 output rounding (2^-9)
+    assert rel_l2(ntfc_to_nchw(a_out.float()), act) < 4e-3            # 16-bit output rounding
     assert rel_l2(ntfc_to_nchw(r_out.float()), raw) < 4e-3
     assert float((ntfc_to_nchw(a_out.float()).cpu() - act).abs().max()) < 0.03
 
 
 def _conv_case(lib, B, T, Fq, C1, k, C2, Cout, residual, bias_b, seed):
     g = torch.Generator().manual_seed(seed)
-    x1 = torch.randn(B, C1, Fq, T, generator=g).bfloat16().float()
-    w1 = (torch.randn(Cout, C1, k, k, generator=g) / (C1 * k * k) ** 0.5).bfloat16().float()
+    x1 = torch.randn(B, C1, Fq, T, generator=g).to(_h16()).float()
+    w1 = (torch.randn(Cout, C1, k, k, generator=g) / (C1 * k * k) ** 0.5).to(_h16()).float()
     bias = torch.randn(Cout, generator=g)
     ref = F.conv2d(x1.double(), w1.double(), None, padding=k // 2)
     x2 = w2 = None
     if C2:
-        x2 = torch.randn(B, C2, Fq, T, generator=g).bfloat16().float()
-        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).bfloat16().float()
+        x2 = torch.randn(B, C2, Fq, T, generator=g).to(_h16()).float()
+        w2 = (torch.randn(Cout, C2, 1, 1, generator=g) / C2 ** 0.5).to(_h16()).float()
         ref = ref + F.conv2d(x2.double(), w2.double())
     ref = ref + bias.double()[None, :, None, None]
     bb = res = None
@@ -224,15 +229,15 @@ def _conv_case(lib, B, T, Fq, C1, k, C2, Cout, residual, bias_b, seed):
 
     nbytes = C.c_int64()
     _check(lib, lib.fdbm_pack_conv_weights(None, C1, k, None, C2, Cout, None, C.byref(nbytes), None))
-    wpack = torch.empty(nbytes.value // 2, dtype=torch.bfloat16, device="cuda")
+    wpack = torch.empty(nbytes.value // 2, dtype=_h16(), device="cuda")
     w1d = w1.cuda()
     w2d = w2.cuda() if C2 else None
     _check(lib, lib.fdbm_pack_conv_weights(w1d.data_ptr(), C1, k, w2d.data_ptr() if C2 else None, C2, Cout,
                                            wpack.data_ptr(), None, _stream()))
-    in1 = nchw_to_ntfc(x1).bfloat16().cuda()
-    in2 = nchw_to_ntfc(x2).bfloat16().cuda() if C2 else None
+    in1 = nchw_to_ntfc(x1).to(_h16()).cuda()
+    in2 = nchw_to_ntfc(x2).to(_h16()).cuda() if C2 else None
     out = torch.full((B, T, Fq, Cout), float("nan"), device="cuda")
-    out16 = torch.empty(B, T, Fq, Cout, dtype=torch.bfloat16, device="cuda")
+    out16 = torch.empty(B, T, Fq, Cout, dtype=_h16(), device="cuda")
     sums = torch.empty(B, Cout, 2, dtype=torch.float64, device="cuda")
     biasd = bias.cuda()
     bbd = bb.cuda() if bias_b else None
@@ -268,10 +273,10 @@ def test_conv_igemm(lib, B, T, Fq, C1, k, C2, Cout, residual, bias_b):
 def test_attention(lib):
     g = torch.Generator().manual_seed(4)
     B, L, Cc = 2, 96, 256
-    q, k, v = (torch.randn(B, L, Cc, generator=g).bfloat16() for _ in range(3))
+    q, k, v = (torch.randn(B, L, Cc, generator=g).to(_h16()) for _ in range(3))
     w = torch.softmax(torch.einsum("bqc,bkc->bqk", q.float(), k.float()) * Cc ** -0.5, dim=-1)
     ref = torch.einsum("bqk,bkc->bqc", w, v.float())
-    o = torch.empty(B, L, Cc, dtype=torch.bfloat16, device="cuda")
+    o = torch.empty(B, L, Cc, dtype=_h16(), device="cuda")
     qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
     _check(lib, lib.fdbm_attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), B, L, Cc, o.data_ptr(), _stream()))
     assert rel_l2(o.float(), ref) < 5e-3

@@ -1,0 +1,93 @@
+"""The CPU oracle against the golden vectors produced by the reference itself
+(oracle/make_golden.py, run in the build container where /root/reference exists)."""
+import numpy as np
+import torch
+
+import fdbm_oracle as O
+from helpers import load_npz, rel_l2
+
+
+def test_spectral_chain(golden_dir):
+    g = load_npz(f"{golden_dir}/spectral_1s.npz")
+    cfg = O.SpecConfig()
+    y = torch.from_numpy(g["wave"])
+    S = O.stft(y, cfg)
+    assert torch.equal(S, torch.from_numpy(g["stft"]))                 # bit-identical to torch.stft on CPU
+    Y = O.spec_fwd(S, cfg)
+    assert rel_l2(Y, g["spec"]) < 1e-7
+    assert torch.equal(O.pad_spec(torch.from_numpy(g["spec"])[None], "reflection"), torch.from_numpy(g["spec_reflect"]))
+    assert torch.equal(O.pad_spec(torch.from_numpy(g["spec"])[None], "zero_pad"), torch.from_numpy(g["spec_zero"]))
+    w = O.istft(O.spec_back(torch.from_numpy(g["spec_reflect"]).squeeze(), cfg), cfg, 16000)
+    assert rel_l2(w, g["wave_back"].reshape(-1)) < 1e-6
+
+
+def test_frame_index_matches_unfold():
+    n = 5000
+    x = torch.arange(n, dtype=torch.float32)
+    idx = O.frame_index(n, 512, 256)
+    ref = torch.nn.functional.pad(x[None, None], (256, 256), mode="reflect")[0, 0].unfold(-1, 512, 256)
+    assert torch.equal(x[torch.from_numpy(idx)], ref)
+
+
+def test_coefficient_tables_bit_exact(golden_dir):
+    g = load_npz(f"{golden_dir}/coeff_tables.npz")
+    n = 0
+    for key, ref in g.items():
+        if key.endswith("_pathparam"):
+            continue
+        path, sched, st1, st2, N = key.split("_")
+        kw = {} if path == "fm" else {"noise_schedule": sched}
+        b = O.Bridge(path, N=int(N[1:]), sampler_type=f"{st1}_{st2}", **kw)
+        assert np.array_equal(b.coefficient_table().numpy(), ref), key
+        n += 1
+    assert n == 36
+    # the values SURVEY.md section 8 (A6) quotes for the default sampler
+    t = O.Bridge("sb", N=5, sampler_type="ode_ei").coefficient_table()
+    assert abs(float(t[0, 0]) - 3999.45) < 0.01 and abs(float(t[4, 1]) - 0.979906) < 1e-5
+
+
+def test_fir_identities(golden_dir):
+    g = load_npz(f"{golden_dir}/fir.npz")
+    x = torch.from_numpy(g["x"])
+    assert float((O.fir_down2(x) - torch.from_numpy(g["down"])).abs().max()) < 5e-7
+    assert float((O.fir_up2(x) - torch.from_numpy(g["up"])).abs().max()) < 5e-7
+
+
+def test_backbone_forward_golden(golden_dir):
+    torch.set_num_threads(max(1, torch.get_num_threads()))
+    g = load_npz(f"{golden_dir}/bridge_T64.npz")
+    cfg = O.NcsnppConfig()
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    assert len(sd) == 647 and sum(v.numel() for v in sd.values()) == 65590822
+    with torch.no_grad():
+        D = O.ncsnpp_forward(sd, cfg, torch.from_numpy(g["xt"]), torch.from_numpy(g["Y"]), torch.from_numpy(g["t"]))
+    assert rel_l2(D, g["D"]) < 2e-5
+    assert float(torch.from_numpy(g["D"]).abs().std()) > 0.5           # sensitised weights: O(1) output, not a constant
+
+
+def test_predictive_forward_golden(golden_dir):
+    g = load_npz(f"{golden_dir}/predictive_T64.npz")
+    cfg = O.NcsnppConfig(predictive=True)
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    with torch.no_grad():
+        D = O.ncsnpp_forward(sd, cfg, torch.from_numpy(g["Y"]))
+    assert rel_l2(D, g["D"]) < 2e-5
+
+
+def test_sampler_golden_sb_ode(golden_dir):
+    g = load_npz(f"{golden_dir}/bridge_T64.npz")
+    cfg = O.NcsnppConfig()
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    b = O.Bridge("sb", N=5, sampler_type="ode_ei")
+    s = b.sampler(lambda a, c, t: O.ncsnpp_forward(sd, cfg, a, c, t), torch.from_numpy(g["Y"]))
+    assert rel_l2(s, g["sample_sb_ode_ei"]) < 2e-4
+    w = O.istft(O.spec_back(s.squeeze(), O.SpecConfig()), O.SpecConfig(), 16000)
+    assert O.si_sdr(g["wave_sb_ode_ei"].reshape(-1), w.numpy()) > 60.0
+
+
+def test_si_sdr_and_synth():
+    c, n = O.synth_pair(0, 16000)
+    assert c.shape == (16000,) and n.shape == (16000,)
+    assert -1.0 < O.si_sdr(c.numpy(), n.numpy()) < 16.0                # SNR drawn from U(0, 15) dB
+    c2, _ = O.synth_pair(0, 16000)
+    assert torch.equal(c, c2)

@@ -65,12 +65,12 @@ probe_kernel(const __grid_constant__ CUtensorMap map_a, const __grid_constant__ 
     }
     mbar_wait(&full_bar, 0);
     fence_after_sync();
-    const uint32_t idesc = make_idesc_bf16(128, N_);
+    const uint32_t idesc = make_idesc_f16(128, N_, 1);
     for (int kb = 0; kb < KB; ++kb) {
       for (int k = 0; k < 4; ++k) {
         uint64_t da = make_desc_sw128(smem_u32(sA + kb * A_STRIDE) + p.a_start_off + k * 32, p.a_sbo, p.base_offset);
         uint64_t db = make_desc_sw128(smem_u32(sB + kb * N_ * 128) + k * 32, 1024, 0);
-        mma_bf16(tmem, da, db, idesc, (kb | k) != 0);
+        mma_f16(tmem, da, db, idesc, (kb | k) != 0);
       }
     }
     mma_commit(&done_bar);
