@@ -17,7 +17,8 @@
 //   * a CTA owns 2 M-tiles x 128 output channels: every weight tile (128 x 64 bf16, TMA, 6-deep ring)
 //     is used by two MMAs; accumulators live in TMEM (2 stages x 2 tiles x 128 columns = 512).
 //   * warp-specialised, persistent: warp0 = A producer, warp1 = B producer, warp2 = MMA issuer,
-//     warp3 = TMEM owner, warps4-7 = epilogue (tcgen05.ld -> bias / FiLM / residual / scale -> global),
+//     warp3 = TMEM owner, warps4-7 = epilogue (tcgen05.ld -> smem transpose -> bias / FiLM / residual /
+//     scale -> coalesced global stores, + per-channel sum / sum-of-squares for the next GroupNorm),
 //     overlapping the next tile's main loop through the second accumulator stage.
 #include <cuda.h>
 #include <mutex>
@@ -40,7 +41,10 @@ constexpr int BN = 128;
 constexpr int B_TILE_BYTES = BN * 128;
 constexpr int A_SBO = HALO_F * 128;                          // 1280: distance between 8-pixel row groups
 constexpr int NUM_THREADS = 256;
-constexpr int SMEM_BYTES = 1024 + A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + 256;
+constexpr int STAGE_BYTES = 4 * 32 * 32 * 4;                    // epilogue transposition tiles, one per warp
+constexpr int STAT_SLOTS = 2;                                  // n-blocks whose statistics a CTA keeps in flight
+constexpr int STAT_BYTES = 4 * BN * 8;                         // per-warp channel (sum, sum of squares) partials
+constexpr int SMEM_BYTES = 1024 + A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + STAGE_BYTES + STAT_BYTES + 256;
 
 struct ConvParams {
   int B, T, F, Cout;
@@ -53,6 +57,7 @@ struct ConvParams {
   float scale;
   float* out_f32;
   op_t* out_h16;
+  double* sums;
 };
 
 struct TileCoord { int b, t0, f0; bool valid; };
@@ -75,7 +80,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_STAGES * MT * A_TILE_STRIDE;
-  uint64_t* bars = reinterpret_cast<uint64_t*>(sB + B_STAGES * B_TILE_BYTES);
+  uint8_t* s_stage = sB + B_STAGES * B_TILE_BYTES;
+  uint8_t* s_stat = s_stage + STAGE_BYTES;
+  uint64_t* bars = reinterpret_cast<uint64_t*>(s_stage + STAGE_BYTES + STAT_BYTES);
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + A_STAGES;
   uint64_t* b_full = a_empty + A_STAGES;
@@ -149,101 +156,191 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       }
     }
   } else if (warp == 2) {
-    // ------------------------------------------------------------------ MMA issuer (one thread)
-    if (lane == 0) {
-      const uint32_t idesc = make_idesc_f16(128, BN, kOperandIsBf16);
-      uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
-      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int ct = item / p.n_nblocks;
-        bool valid[MT];
-        for (int j = 0; j < MT; ++j) valid[j] = (ct * MT + j) < p.n_mtiles;
-        mbar_wait(acc_empty + as, pacc ^ 1);
+    // ------------------------------------------------------------------ MMA issuer
+    // The whole warp walks the pipeline (so every operand is provably warp-uniform and the compiler emits
+    // no per-thread "waterfall" around the uniform-datapath UTCHMMA); one elected lane issues.  Descriptors
+    // are built once: only the 14-bit start-address field changes, by a plain add per MMA.
+    const uint32_t idesc = make_idesc_f16(128, BN, kOperandIsBf16);
+    const uint64_t a_hi = make_desc_sw128(0, A_SBO) & 0xFFFFFFFF00000000ull;
+    const uint64_t b_hi = make_desc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;
+    const uint32_t lo_const = 1u << 16;                                   // LBO field (unused by swizzled K-major)
+    const uint32_t sA_lo = (smem_u32(sA) & 0x3FFFF) >> 4, sB_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+      const int ct = item / p.n_nblocks;
+      const bool valid1 = (ct * MT + 1) < p.n_mtiles;                    // M-tile 0 of an item is always valid
+      mbar_wait(acc_empty + as, pacc ^ 1);
+      fence_after_sync();
+      uint32_t accumulate = 0;
+      const uint32_t d0 = tmem_base + (as * MT) * BN, d1 = d0 + BN;
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const int ntaps = kb < p.kb1 ? p.taps1 : 1;
+        mbar_wait(a_full + sa, pa);
         fence_after_sync();
-        bool first = true;
-        for (int kb = 0; kb < n_kb; ++kb) {
-          const int ntaps = kb < p.kb1 ? p.taps1 : 1;
-          mbar_wait(a_full + sa, pa);
+        const uint32_t a_base0 = sA_lo + ((sa * MT) * A_TILE_STRIDE >> 4), a_base1 = a_base0 + (A_TILE_STRIDE >> 4);
+        int df = ntaps == 9 ? 0 : 1, dt = ntaps == 9 ? 0 : 1;           // tap -> (df, dt); 1x1 reads the box centre
+        for (int tap = 0; tap < ntaps; ++tap) {
+          mbar_wait(b_full + sb, pb);
           fence_after_sync();
-          for (int tap = 0; tap < ntaps; ++tap) {
-            mbar_wait(b_full + sb, pb);
-            fence_after_sync();
-            // tap -> (df, dt); a 1x1 conv reads the centre of the halo box
-            const int df = ntaps == 9 ? tap / 3 : 1, dt = ntaps == 9 ? tap % 3 : 1;
-            const uint32_t a_off = (dt * HALO_F + df) * 128;
-            const uint32_t b_addr = smem_u32(sB + sb * B_TILE_BYTES);
+          const uint32_t a_off = ((dt * HALO_F + df) * 128) >> 4;
+          const uint32_t b_lo = (sB_lo + (sb * B_TILE_BYTES >> 4)) | lo_const;
+          const uint32_t a_lo0 = (a_base0 + a_off) | lo_const, a_lo1 = (a_base1 + a_off) | lo_const;
+          if (elect_one()) {
 #pragma unroll
-            for (int j = 0; j < MT; ++j) {
-              if (!valid[j]) continue;
-              const uint32_t a_addr = smem_u32(sA + (sa * MT + j) * A_TILE_STRIDE) + a_off;
-              const uint32_t d_tmem = tmem_base + (as * MT + j) * BN;
+            for (int k = 0; k < 4; ++k)
+              mma_f16(d0, a_hi | (a_lo0 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
+            if (valid1) {
 #pragma unroll
-              for (int k = 0; k < 4; ++k) {
-                mma_f16(d_tmem, make_desc_sw128(a_addr + k * 32, A_SBO), make_desc_sw128(b_addr + k * 32, 1024), idesc,
-                         (first && k == 0) ? 0u : 1u);
-              }
+              for (int k = 0; k < 4; ++k)
+                mma_f16(d1, a_hi | (a_lo1 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
             }
-            first = false;
             mma_commit(b_empty + sb);
-            if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+            if (tap == ntaps - 1) mma_commit(a_empty + sa);
+            if (tap == ntaps - 1 && kb == n_kb - 1) mma_commit(acc_full + as);
           }
-          mma_commit(a_empty + sa);
-          if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
+          __syncwarp();
+          accumulate = 1;
+          if (++dt == 3) { dt = 0; ++df; }                                 // tap = df * 3 + dt
+          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
         }
-        mma_commit(acc_full + as);
-        if (++as == 2) { as = 0; pacc ^= 1; }
+        if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
       }
+      if (++as == 2) { as = 0; pacc ^= 1; }
     }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
+    // tcgen05.ld hands every thread one pixel row (32 consecutive channels).  Writing that straight to
+    // global memory would touch 32 different 128-byte lines per store instruction, so each warp first
+    // transposes its 32x32 block through a swizzled shared-memory tile; afterwards 8 lanes cover the
+    // 128 contiguous bytes of one pixel and every global access (bias, residual, outputs) is coalesced.
     const int q = warp & 3;                              // TMEM lane quadrant of this warp
-    const int m = q * 32 + lane;                         // pixel row inside the M-tile
-    const int r = m >> 3, c = m & 7;
+    float4* stage = reinterpret_cast<float4*>(s_stage) + q * (32 * 8);       // [32 pixels][8 float4], XOR-swizzled
+    const int cc = lane & 7;                             // channel quad inside the 32-channel chunk (transposed phase)
+    const int rsub = lane >> 3;                          // pixel sub-row (transposed phase)
+    const int et = threadIdx.x - 128;                    // 0..127 among the epilogue threads
     uint32_t as = 0, pacc = 0;
+    const bool do_stats = p.sums != nullptr;             // host guarantees n_nblocks <= STAT_SLOTS when sums are requested
+    // GroupNorm statistics: every warp leaves its 32-pixel partial sums (fp32, fixed summation order) in its
+    // own shared-memory slot; after each M-tile thread c adds the four warps' partials of channel c into
+    // DOUBLE registers that live across the CTA's items, and only those go to global memory (double atomics).
+    // E[x^2] - mean^2 amplifies rounding noise in these sums ~1000x on some layers, so no fp32 atomics here.
+    float2* wstat = reinterpret_cast<float2*>(s_stat);   // [4 warps][BN channels] (sum, sum of squares)
+    double acc_s[STAT_SLOTS], acc_q[STAT_SLOTS];
+#pragma unroll
+    for (int u = 0; u < STAT_SLOTS; ++u) { acc_s[u] = 0.0; acc_q[u] = 0.0; }
+    int stat_b = -1;                                     // utterance the register statistics currently belong to
+    auto flush_stats = [&]() {
+#pragma unroll
+      for (int u = 0; u < STAT_SLOTS; ++u) {
+        if (u < p.n_nblocks) {
+          double* dst = p.sums + (static_cast<int64_t>(stat_b) * p.Cout + u * BN + et) * 2;
+          atomicAdd(dst, acc_s[u]);
+          atomicAdd(dst + 1, acc_q[u]);
+        }
+        acc_s[u] = 0.0; acc_q[u] = 0.0;
+      }
+    };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int ct = item / p.n_nblocks;
-      const int n0 = (item % p.n_nblocks) * BN;
+      const int nblk = item % p.n_nblocks;
+      const int n0 = nblk * BN;
       mbar_wait(acc_full + as, pacc);
       fence_after_sync();
       for (int j = 0; j < MT; ++j) {
         const TileCoord tc = decode_tile(p, ct * MT + j);
         if (!tc.valid) continue;                          // warp-uniform
-        const int t = tc.t0 + r, f = tc.f0 + c;
-        const bool ok = t < p.T && f < p.F;
-        const int64_t pix = (static_cast<int64_t>(tc.b) * p.T + t) * p.F + f;
-#pragma unroll 1
+        if (do_stats && stat_b != tc.b) {
+          if (stat_b >= 0) flush_stats();
+          stat_b = tc.b;
+        }
+        // pixel coordinates of the 8 rows this lane handles in the transposed phase
+        int64_t poff[8];
+        uint32_t okmask = 0;
+#pragma unroll
+        for (int it = 0; it < 8; ++it) {
+          const int m = q * 32 + it * 4 + rsub;
+          const int t = tc.t0 + (m >> 3), f = tc.f0 + (m & 7);
+          const bool ok = t < p.T && f < p.F;
+          okmask |= ok ? (1u << it) : 0u;
+          poff[it] = ((static_cast<int64_t>(tc.b) * p.T + (ok ? t : 0)) * p.F + (ok ? f : 0)) * p.Cout + n0 + cc * 4;
+        }
+        // bias (+ per-utterance FiLM bias) of all four 32-channel chunks: one exposed latency per M-tile
+        float4 bv[BN / 32];
+#pragma unroll
         for (int ch = 0; ch < BN / 32; ++ch) {
+          bv[ch] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32 + cc * 4));
+          if (p.bias_b) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + n0 + ch * 32 + cc * 4));
+            bv[ch].x += e.x; bv[ch].y += e.y; bv[ch].z += e.z; bv[ch].w += e.w;
+          }
+        }
+#pragma unroll
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          // residual rows of this chunk: eight independent 16-byte loads in flight while TMEM is read
+          float4 res[8];
+          if (p.residual) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              res[it] = (okmask >> it) & 1 ? __ldg(reinterpret_cast<const float4*>(p.residual + poff[it] + ch * 32))
+                                           : make_float4(0.f, 0.f, 0.f, 0.f);
+          }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
           tmem_ld_wait();
-          if (ok) {
-            const int nb = n0 + ch * 32;
-            const float4* bias4 = reinterpret_cast<const float4*>(p.bias + nb);
-            const float4* bb4 = p.bias_b ? reinterpret_cast<const float4*>(p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + nb) : nullptr;
-            const float4* res4 = p.residual ? reinterpret_cast<const float4*>(p.residual + pix * p.Cout + nb) : nullptr;
-            float4* of = p.out_f32 ? reinterpret_cast<float4*>(p.out_f32 + pix * p.Cout + nb) : nullptr;
-            uint2* ob = p.out_h16 ? reinterpret_cast<uint2*>(p.out_h16 + pix * p.Cout + nb) : nullptr;
 #pragma unroll
-            for (int g = 0; g < 8; ++g) {
-              float4 o = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
-                                     __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
-              const float4 bv = __ldg(bias4 + g);
-              o.x += bv.x; o.y += bv.y; o.z += bv.z; o.w += bv.w;
-              if (bb4) { const float4 e = __ldg(bb4 + g); o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
-              if (res4) { const float4 e = res4[g]; o.x += e.x; o.y += e.y; o.z += e.z; o.w += e.w; }
-              o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale;
-              if (of) of[g] = o;
-              if (ob) {
-                ob[g] = make_uint2(pack_op2(o.x, o.y), pack_op2(o.z, o.w));
-              }
+          for (int g = 0; g < 8; ++g)
+            stage[lane * 8 + (g ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
+                                                             __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
+          __syncwarp();
+          float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {
+            const int rr = it * 4 + rsub;                 // pixel row inside this warp's quadrant
+            float4 o = stage[rr * 8 + (cc ^ (rr & 7))];
+            o.x += bv[ch].x; o.y += bv[ch].y; o.z += bv[ch].z; o.w += bv[ch].w;
+            if (p.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
+            o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale;
+            if ((okmask >> it) & 1) {
+              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + poff[it] + ch * 32) = o;
+              if (p.out_h16) *reinterpret_cast<uint2*>(p.out_h16 + poff[it] + ch * 32) = make_uint2(pack_op2(o.x, o.y), pack_op2(o.z, o.w));
+              ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
+              ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
+              ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
             }
           }
+          if (do_stats) {
+#pragma unroll
+            for (int sft = 8; sft <= 16; sft <<= 1) {
+              ssum.x += __shfl_xor_sync(0xffffffffu, ssum.x, sft); ssum.y += __shfl_xor_sync(0xffffffffu, ssum.y, sft);
+              ssum.z += __shfl_xor_sync(0xffffffffu, ssum.z, sft); ssum.w += __shfl_xor_sync(0xffffffffu, ssum.w, sft);
+              ssq.x += __shfl_xor_sync(0xffffffffu, ssq.x, sft); ssq.y += __shfl_xor_sync(0xffffffffu, ssq.y, sft);
+              ssq.z += __shfl_xor_sync(0xffffffffu, ssq.z, sft); ssq.w += __shfl_xor_sync(0xffffffffu, ssq.w, sft);
+            }
+            if (rsub == 0) {
+              float4* d = reinterpret_cast<float4*>(wstat + q * BN + ch * 32 + cc * 4);
+              d[0] = make_float4(ssum.x, ssq.x, ssum.y, ssq.y);
+              d[1] = make_float4(ssum.z, ssq.z, ssum.w, ssq.w);
+            }
+          }
+          __syncwarp();                                   // staging tile is rewritten by the next chunk
+        }
+        if (do_stats) {                                   // block-uniform
+          asm volatile("bar.sync 1, 128;" ::: "memory");
+          double s = 0.0, sq = 0.0;
+#pragma unroll
+          for (int w = 0; w < 4; ++w) { const float2 e = wstat[w * BN + et]; s += e.x; sq += e.y; }
+#pragma unroll
+          for (int u = 0; u < STAT_SLOTS; ++u) if (u == nblk) { acc_s[u] += s; acc_q[u] += sq; }
+          asm volatile("bar.sync 1, 128;" ::: "memory");
         }
       }
+      // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
       fence_before_sync();
       __syncwarp();
       if (lane == 0) mbar_arrive(acc_empty + as);
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
+    if (do_stats && stat_b >= 0) flush_stats();
   }
 
   fence_before_sync();
@@ -368,14 +465,14 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.n_nblocks = a.Cout / BN;
   p.n_items = ceil_div(p.n_mtiles, MT) * p.n_nblocks;
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
-  p.out_f32 = a.out_f32; p.out_h16 = a.out_h16;
+  p.out_f32 = a.out_f32; p.out_h16 = a.out_h16; p.sums = a.sums;
+  if (a.sums) {
+    FDBM_REQUIRE(p.n_nblocks <= STAT_SLOTS, "conv_igemm: channel sums support Cout <= %d", STAT_SLOTS * BN);
+    FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));
+  }
   const int grid = std::min(p.n_items, num_sms());
   conv_igemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a1, map_a2, map_b, p);
   FDBM_LAUNCH_CHECK();
-  if (a.sums) {
-    FDBM_REQUIRE(a.out_f32, "conv_igemm: channel sums need the fp32 output");
-    return launch_channel_stats(a.out_f32, a.B, a.T, a.F, a.Cout, a.sums, s);
-  }
   return FDBM_OK;
 }
 

@@ -111,12 +111,12 @@ channel_stats_kernel(const float* __restrict__ in, int64_t P, int C, int64_t px_
 constexpr int GN_MAXC = 512;
 
 
-template <int MODE>
+template <int MODE, bool SRC16>
 __global__ void __launch_bounds__(256)
-groupnorm_act_kernel(const float* __restrict__ src1, const double* __restrict__ sums1, int C1,
+groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ sums1, int C1,
                      const float* __restrict__ src2, const double* __restrict__ sums2, int C2,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int T, int F, int silu,
-                     int64_t items_per_block, uint4* __restrict__ act_out, uint4* __restrict__ raw_out) {
+                     int px_per_block, uint4* __restrict__ act_out, uint4* __restrict__ raw_out) {
   __shared__ float sA[GN_MAXC], sB[GN_MAXC];
   __shared__ float s_mean[32], s_rstd[32];
   const int C = C1 + C2;
@@ -148,47 +148,60 @@ groupnorm_act_kernel(const float* __restrict__ src1, const double* __restrict__ 
   }
   __syncthreads();
 
-  const int To = out_dim(T, MODE), Fo = out_dim(F, MODE);
+  // thread -> fixed group of 8 channels, a lane of pixels: scale/shift live in registers for the whole loop
   const int cg8 = C / 8;
-  const int64_t n_items = static_cast<int64_t>(To) * Fo * cg8;
-  const int64_t i0 = blockIdx.x * items_per_block;
-  const int64_t i1 = min(n_items, i0 + items_per_block);
-  const float* s1 = src1 + static_cast<int64_t>(b) * T * F * C1;
-  const float* s2 = src2 ? src2 + static_cast<int64_t>(b) * T * F * C2 : nullptr;
-  for (int64_t i = i0 + threadIdx.x; i < i1; i += 256) {
-    const int g8 = static_cast<int>(i % cg8);
-    const int64_t p = i / cg8;
-    const int fo = static_cast<int>(p % Fo), to = static_cast<int>(p / Fo);
-    const int c0 = g8 * 8;
-    const float* src; int Cs, cs;
-    if (c0 < C1) { src = s1; Cs = C1; cs = c0; } else { src = s2; Cs = C2; cs = c0 - C1; }
-    float a[8], bb[8];
+  const int npl = 256 / cg8;                           // pixel lanes per block (idle threads when 256 % cg8 != 0)
+  const int g8 = threadIdx.x % cg8, pl = threadIdx.x / cg8;
+  if (pl >= npl) return;
+  const int c0 = g8 * 8;
+  float a[8], bb[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) { a[j] = sA[c0 + j]; bb[j] = sB[c0 + j]; }
+  for (int j = 0; j < 8; ++j) { a[j] = sA[c0 + j]; bb[j] = sB[c0 + j]; }
+  const bool from2 = c0 >= C1;
+  const int Cs = from2 ? C2 : C1, cs = from2 ? c0 - C1 : c0;
+  const float* sf = from2 ? src2 + static_cast<int64_t>(b) * T * F * C2
+                          : reinterpret_cast<const float*>(src1) + (SRC16 ? 0 : static_cast<int64_t>(b) * T * F * C1);
+  const op_t* sh = reinterpret_cast<const op_t*>(src1) + static_cast<int64_t>(b) * T * F * C1;
+
+  const int To = out_dim(T, MODE), Fo = out_dim(F, MODE);
+  const int n_px = To * Fo;
+  const int p0 = blockIdx.x * px_per_block;
+  const int p1 = min(n_px, p0 + px_per_block);
+  constexpr int NT = MODE == 1 ? 4 : (MODE == 2 ? 2 : 1);
+  for (int p = p0 + pl; p < p1; p += npl) {
+    const int fo = p % Fo, to = p / Fo;
     float acc[8], raw[8];
 #pragma unroll
     for (int j = 0; j < 8; ++j) { acc[j] = 0.f; raw[j] = 0.f; }
     const Taps1D tt = taps_for(to, MODE), tf = taps_for(fo, MODE);
 #pragma unroll
-    for (int u = 0; u < (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1)); ++u) {
+    for (int u = 0; u < NT; ++u) {
       if (tt.pos[u] < 0 || tt.pos[u] >= T) continue;
 #pragma unroll
-      for (int v = 0; v < (MODE == 1 ? 4 : (MODE == 2 ? 2 : 1)); ++v) {
+      for (int v = 0; v < NT; ++v) {
         if (tf.pos[v] < 0 || tf.pos[v] >= F) continue;
         const float w = tt.w[u] * tf.w[v];
-        const float4* ptr = reinterpret_cast<const float4*>(src + (static_cast<int64_t>(tt.pos[u]) * F + tf.pos[v]) * Cs + cs);
-        const float4 x0 = ptr[0], x1 = ptr[1];
-        const float x[8] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+        const int64_t off = (static_cast<int64_t>(tt.pos[u]) * F + tf.pos[v]) * Cs + cs;
+        float x[8];
+        if (SRC16 && !from2) {
+          const uint4 rawv = *reinterpret_cast<const uint4*>(sh + off);
+          const op2_t* h2 = reinterpret_cast<const op2_t*>(&rawv);
+#pragma unroll
+          for (int j = 0; j < 4; ++j) { const float2 f2 = op22f2(h2[j]); x[2 * j] = f2.x; x[2 * j + 1] = f2.y; }
+        } else {
+          const float4 x0 = *reinterpret_cast<const float4*>(sf + off), x1 = *reinterpret_cast<const float4*>(sf + off + 4);
+          x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
+        }
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float y = fmaf(x[j], a[j], bb[j]);
-          if (silu) y = silu_f(y);
+          if (silu) y = __fdividef(y, 1.0f + __expf(-y));
           acc[j] = fmaf(w, y, acc[j]);
           raw[j] = fmaf(w, x[j], raw[j]);
         }
       }
     }
-    const int64_t o = (static_cast<int64_t>(b) * To * Fo + p) * cg8 + g8;
+    const int64_t o = (static_cast<int64_t>(b) * n_px + p) * cg8 + g8;
     act_out[o] = make_uint4(pack_op2(acc[0], acc[1]), pack_op2(acc[2], acc[3]), pack_op2(acc[4], acc[5]),
                             pack_op2(acc[6], acc[7]));
     if (raw_out)
@@ -222,27 +235,32 @@ int launch_channel_stats(const float* in, int B, int T, int F, int C, double* su
   return FDBM_OK;
 }
 
-int launch_groupnorm_act(const float* src1, const double* sums1, int C1, const float* src2, const double* sums2,
-                         int C2, const float* gamma, const float* beta, int B, int T, int F, int silu, int mode,
-                         op_t* act_out, op_t* raw_out, cudaStream_t s) {
+int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, int C1, const float* src2,
+                         const double* sums2, int C2, const float* gamma, const float* beta, int B, int T, int F,
+                         int silu, int mode, op_t* act_out, op_t* raw_out, cudaStream_t s) {
   const int C = C1 + C2;
-  FDBM_REQUIRE(C <= GN_MAXC && C1 % 8 == 0 && C2 % 8 == 0 && C % std::min(C / 4, 32) == 0,
+  FDBM_REQUIRE(C <= GN_MAXC && C1 % 8 == 0 && C2 % 8 == 0 && C % std::min(C / 4, 32) == 0 && C / 8 <= 256,
                "groupnorm_act: unsupported channels %d+%d", C1, C2);
   FDBM_REQUIRE(mode >= 0 && mode <= 2, "groupnorm_act: bad mode %d", mode);
   FDBM_REQUIRE(mode != 1 || (T % 2 == 0 && F % 2 == 0), "groupnorm_act: down-sampling needs even T, F");
-  const int64_t n_items = static_cast<int64_t>(out_dim(T, mode)) * out_dim(F, mode) * (C / 8);
-  int64_t blocks_x = std::max<int64_t>(1, (static_cast<int64_t>(num_sms()) * 8) / B);
-  blocks_x = std::min<int64_t>(blocks_x, ceil_div64(n_items, 256));
-  const int64_t ipb = ceil_div64(ceil_div64(n_items, blocks_x), 256) * 256;
-  dim3 grid(static_cast<unsigned>(ceil_div64(n_items, ipb)), B);
+  FDBM_REQUIRE(!src1_h16 || C2 == 0, "groupnorm_act: a 16-bit source cannot be concatenated");
+  const int n_px = out_dim(T, mode) * out_dim(F, mode);
+  const int npl = 256 / (C / 8);
+  // ~8 resident blocks per SM over the batch; every pixel lane gets at least 4 pixels
+  int blocks_x = std::max(1, (num_sms() * 8) / B);
+  blocks_x = std::min(blocks_x, std::max(1, n_px / (npl * 4)));
+  const int ppb = ceil_div(ceil_div(n_px, blocks_x), npl) * npl;
+  dim3 grid(ceil_div(n_px, ppb), B);
   uint4* ao = reinterpret_cast<uint4*>(act_out);
   uint4* ro = reinterpret_cast<uint4*>(raw_out);
-  if (mode == 0)
-    groupnorm_act_kernel<0><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ipb, ao, ro);
-  else if (mode == 1)
-    groupnorm_act_kernel<1><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ipb, ao, ro);
-  else
-    groupnorm_act_kernel<2><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ipb, ao, ro);
+#define FDBM_GN_LAUNCH(M, H) \
+  groupnorm_act_kernel<M, H><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ppb, ao, ro)
+  if (src1_h16) {
+    if (mode == 0) FDBM_GN_LAUNCH(0, true); else if (mode == 1) FDBM_GN_LAUNCH(1, true); else FDBM_GN_LAUNCH(2, true);
+  } else {
+    if (mode == 0) FDBM_GN_LAUNCH(0, false); else if (mode == 1) FDBM_GN_LAUNCH(1, false); else FDBM_GN_LAUNCH(2, false);
+  }
+#undef FDBM_GN_LAUNCH
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -271,7 +289,7 @@ extern "C" int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(src1 && sums1 && gamma && beta && act_out && batch > 0, "fdbm_groupnorm_act: null pointer");
   FDBM_REQUIRE((C2 == 0) == (src2 == nullptr) && (C2 == 0 || sums2), "fdbm_groupnorm_act: src2/C2 mismatch");
-  return launch_groupnorm_act(src1, sums1, C1, src2, sums2, C2, gamma, beta, batch, T, F, silu, mode,
+  return launch_groupnorm_act(src1, 0, sums1, C1, src2, sums2, C2, gamma, beta, batch, T, F, silu, mode,
                               reinterpret_cast<op_t*>(act_out), reinterpret_cast<op_t*>(raw_out),
                               as_stream(stream));
 }

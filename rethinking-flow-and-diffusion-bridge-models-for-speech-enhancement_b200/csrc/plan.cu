@@ -205,16 +205,10 @@ struct Builder {
     P->op_flops.push_back(flops);
     P->n_launches += 1;
   }
-  // convolution + (optional) channel statistics of its fp32 output, as two recorded launches
+  // convolution; the channel statistics of its output come out of the same kernel's epilogue
   void conv_op(ConvArgs c) {
-    double* sums = c.sums;
-    c.sums = nullptr;
     const double flops = 2.0 * c.B * c.T * c.F * c.Cout * (static_cast<double>(c.ksize) * c.ksize * c.C1 + c.C2);
     op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV, flops);
-    if (sums) {
-      const float* src = c.out_f32; const int B = c.B, T = c.T, F = c.F, C = c.Cout;
-      op([=](cudaStream_t s) { return launch_channel_stats(src, B, T, F, C, sums, s); }, FDBM_OP_STATS);
-    }
   }
   void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
 
@@ -277,24 +271,27 @@ struct Builder {
       const float* s1 = x1.data; const double* q1 = x1.sums; const int C1 = x1.C;
       const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr; const int C2 = x2 ? x2->C : 0;
       op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
+        return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
       }, FDBM_OP_NORM);
     }
-    Act h1 = new_act(Cout, To, Fo);
+    // Conv_0 output only feeds GroupNorm_1: keep it in the 16-bit operand format (its statistics are taken
+    // from the fp32 accumulators in the conv epilogue, before rounding)
+    op_t* h1 = alloc<op_t>(npx * Cout);
+    double* h1_sums = alloc<double>(static_cast<int64_t>(B) * Cout * 2);
     {
       ConvArgs c{};
       c.in1 = a0; c.C1 = Cin; c.ksize = 3; c.in2 = nullptr; c.C2 = 0; c.wpack = w0;
       c.bias = c0b; c.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c.bias_b_stride = dense_stride;
       c.residual = nullptr; c.scale = 1.0f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
-      c.out_f32 = h1.data; c.out_h16 = nullptr; c.out_ld = Cout; c.sums = h1.sums;
+      c.out_f32 = nullptr; c.out_h16 = h1; c.out_ld = Cout; c.sums = h1_sums;
       conv_op(c);
     }
     release(a0);
     op_t* a1 = alloc<op_t>(npx * Cout);
     {
-      const float* s1 = h1.data; const double* q1 = h1.sums;
+      const op_t* s1 = h1; const double* q1 = h1_sums;
       op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, q1, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, a1, nullptr, s);
+        return launch_groupnorm_act(s1, 1, q1, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, a1, nullptr, s);
       }, FDBM_OP_NORM);
     }
     Act out = new_act(Cout, To, Fo);
@@ -306,7 +303,7 @@ struct Builder {
       c.out_f32 = out.data; c.out_h16 = nullptr; c.out_ld = Cout; c.sums = out.sums;
       conv_op(c);
     }
-    free_act(h1);
+    release(h1); release(h1_sums);
     release(a1);
     release(xr);
     return out;
@@ -330,7 +327,7 @@ struct Builder {
     {
       const float* s1 = x.data; const double* q1 = x.sums;
       op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, a, nullptr, s);
+        return launch_groupnorm_act(s1, 0, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, a, nullptr, s);
       }, FDBM_OP_NORM);
     }
     op_t* qkv = alloc<op_t>(npx * 3 * C);
@@ -466,7 +463,7 @@ struct Builder {
         float* prev = pyramid;
         const float* src = h.data; const double* sums = h.sums;
         op([=](cudaStream_t s) {
-          return launch_groupnorm_act(src, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s);
+          return launch_groupnorm_act(src, 0, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s);
         }, FDBM_OP_NORM);
         op([=](cudaStream_t s) { return launch_pyramid_conv(a, C, w, b, prev, Cp, B, Tc, Fc, pyr_new, s); }, FDBM_OP_SKINNY);
         release(a);
