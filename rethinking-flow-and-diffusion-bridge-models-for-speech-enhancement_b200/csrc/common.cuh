@@ -79,6 +79,7 @@ int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, in
                          int silu, int mode, op_t* act_out, op_t* raw_out, cudaStream_t s);
 int launch_pack_input(const float* x, const float* y, int B, int T, int F_in, int F, int Cin, float* out,
                       cudaStream_t s);
+int launch_im2col_input(const float* in, int Cin, int B, int T, int F, op_t* out, cudaStream_t s);
 int launch_conv_in(const float* in, int Cin, const float* w, const float* bias, int B, int T, int F, int Cout,
                    float* out, cudaStream_t s);
 int launch_combine(float* h, const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F,
@@ -102,9 +103,12 @@ struct ConvArgs {
   float scale; int B, T, F, Cout;
   float* out_f32; op_t* out_h16; int out_ld;      // out_ld: row stride (elements) of outputs, >= Cout
   double* sums;
+  // pyramid epilogue (ncsnpp_v2.py:338-359): out = conv(...)[:, :pyr_C] + bias + FIR-up x2(pyr_prev); fp32 [B,T,F,pyr_C]
+  float* pyr_out = nullptr; const float* pyr_prev = nullptr; int pyr_C = 0;
 };
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s);
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);
+// ksize 3 / 1: OIHW; -1: NIN matrix [in][out]; -2: first conv, OIHW [Cout][C1<=4][3][3] as one im2col K-block of 64
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,
                              int row_offset, op_t* wpack, cudaStream_t s);
 

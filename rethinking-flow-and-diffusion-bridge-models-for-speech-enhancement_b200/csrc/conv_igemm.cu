@@ -58,6 +58,9 @@ struct ConvParams {
   float* out_f32;
   op_t* out_h16;
   double* sums;
+  float* pyr_out;
+  const float* pyr_prev;
+  int pyr_C;
 };
 
 struct TileCoord { int b, t0, f0; bool valid; };
@@ -253,6 +256,44 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
           if (stat_b >= 0) flush_stats();
           stat_b = tc.b;
         }
+        if (p.pyr_out) {
+          // progressive-output epilogue: the first pyr_C accumulator columns are the image-space residual;
+          // thread = pixel, add bias and the FIR-upsampled coarser pyramid level, write fp32 [B,T,F,pyr_C]
+          uint32_t v[32];
+          tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN, v);
+          tmem_ld_wait();
+          const int m = q * 32 + lane;
+          const int t = tc.t0 + (m >> 3), f = tc.f0 + (m & 7);
+          if (t < p.T && f < p.F) {
+            float o[4];
+#pragma unroll
+            for (int c = 0; c < 4; ++c) o[c] = c < p.pyr_C ? __uint_as_float(v[c]) + __ldg(p.bias + c) : 0.f;
+            if (p.pyr_prev) {
+              const int Tp = p.T >> 1, Fp = p.F >> 1;
+              const int t_a = (t & 1) ? (t >> 1) : (t >> 1) - 1, f_a = (f & 1) ? (f >> 1) : (f >> 1) - 1;
+              const float wt_a = (t & 1) ? 0.75f : 0.25f, wf_a = (f & 1) ? 0.75f : 0.25f;
+              const float* pb = p.pyr_prev + static_cast<int64_t>(tc.b) * Tp * Fp * p.pyr_C;
+#pragma unroll
+              for (int u = 0; u < 2; ++u) {
+                const int tt = t_a + u;
+                if (tt < 0 || tt >= Tp) continue;
+                const float wt = u ? 1.0f - wt_a : wt_a;
+#pragma unroll
+                for (int w = 0; w < 2; ++w) {
+                  const int ff = f_a + w;
+                  if (ff < 0 || ff >= Fp) continue;
+                  const float wgt = wt * (w ? 1.0f - wf_a : wf_a);
+                  const float* src = pb + (static_cast<int64_t>(tt) * Fp + ff) * p.pyr_C;
+                  for (int c = 0; c < p.pyr_C; ++c) o[c] = fmaf(wgt, __ldg(src + c), o[c]);
+                }
+              }
+            }
+            float* dst = p.pyr_out + ((static_cast<int64_t>(tc.b) * p.T + t) * p.F + f) * p.pyr_C;
+            if (p.pyr_C == 4) *reinterpret_cast<float4*>(dst) = make_float4(o[0], o[1], o[2], o[3]);
+            else for (int c = 0; c < p.pyr_C; ++c) dst[c] = o[c];
+          }
+          continue;
+        }
         // pixel coordinates of the 8 rows this lane handles in the transposed phase
         int64_t poff[8];
         uint32_t okmask = 0;
@@ -353,14 +394,17 @@ __global__ void __launch_bounds__(256)
 pack_weights_kernel(const float* __restrict__ w1, int C1, int ksize, int io_layout, const float* __restrict__ w2,
                     int C2, int Cout, int rows_total, int row_offset, op_t* __restrict__ out) {
   const int taps = ksize * ksize;
-  const int n_kt = (C1 / 64) * taps + C2 / 64;
+  const int n_kt = io_layout == 2 ? 1 : (C1 / 64) * taps + C2 / 64;
   const int64_t total = static_cast<int64_t>(n_kt) * Cout * 64;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
     const int j = static_cast<int>(i % 64);
     const int co = static_cast<int>((i / 64) % Cout);
     const int kt = static_cast<int>(i / (64ll * Cout));
     float v;
-    if (kt < (C1 / 64) * taps) {
+    if (io_layout == 2) {                           // first conv: k = tap * C1 + ci, zero beyond 9 * C1
+      const int tap = j / C1, ci = j % C1;
+      v = tap < 9 ? w1[((static_cast<int64_t>(co) * C1 + ci) * 3 + tap / 3) * 3 + tap % 3] : 0.f;
+    } else if (kt < (C1 / 64) * taps) {
       const int kb = kt / taps, tap = kt % taps;
       const int ci = kb * 64 + j;
       if (io_layout) v = w1[static_cast<int64_t>(ci) * Cout + co];
@@ -429,11 +473,13 @@ int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout) {
 
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,
                              int row_offset, op_t* wpack, cudaStream_t s) {
-  FDBM_REQUIRE(C1 % 64 == 0 && C2 % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1),
+  FDBM_REQUIRE((ksize == -2 && C1 <= 4 && C2 == 0) ||
+               (C1 % 64 == 0 && C2 % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1)),
                "pack_conv_weights: channels must be multiples of 64, ksize 1 or 3");
-  const int io = ksize == -1;                     // ksize -1: NIN weight, [in][out] layout, 1x1
+  const int io = ksize == -1 ? 1 : (ksize == -2 ? 2 : 0);   // -1: NIN [in][out];  -2: first conv as one im2col K-block
   const int k = io ? 1 : ksize;
-  const int64_t total = (static_cast<int64_t>(C1 / 64) * k * k + C2 / 64) * Cout * 64;
+  const int64_t total = io == 2 ? static_cast<int64_t>(Cout) * 64
+                                : (static_cast<int64_t>(C1 / 64) * k * k + C2 / 64) * Cout * 64;
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096));
   pack_weights_kernel<<<grid, 256, 0, s>>>(w1, C1, k, io, w2, C2, Cout, n_rows_total, row_offset, wpack);
   FDBM_LAUNCH_CHECK();
@@ -445,7 +491,9 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   FDBM_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_igemm: ksize must be 1 or 3");
   FDBM_REQUIRE(a.Cout % BN == 0, "conv_igemm: Cout must be a multiple of %d (got %d)", BN, a.Cout);
   FDBM_REQUIRE((a.C2 == 0) == (a.in2 == nullptr), "conv_igemm: in2 / C2 mismatch");
-  FDBM_REQUIRE(a.out_f32 || a.out_h16, "conv_igemm: no output");
+  FDBM_REQUIRE(a.out_f32 || a.out_h16 || a.pyr_out, "conv_igemm: no output");
+  FDBM_REQUIRE(!a.pyr_out || (a.pyr_C >= 1 && a.pyr_C <= 4 && a.Cout == BN && !a.sums), "conv_igemm: bad pyramid epilogue arguments");
+  FDBM_REQUIRE(!a.pyr_prev || (a.T % 2 == 0 && a.F % 2 == 0), "conv_igemm: pyramid level with odd size");
   static bool attr_set = false;
   if (!attr_set) {
     FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
@@ -466,6 +514,7 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.n_items = ceil_div(p.n_mtiles, MT) * p.n_nblocks;
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
   p.out_f32 = a.out_f32; p.out_h16 = a.out_h16; p.sums = a.sums;
+  p.pyr_out = a.pyr_out; p.pyr_prev = a.pyr_prev; p.pyr_C = a.pyr_C;
   if (a.sums) {
     FDBM_REQUIRE(p.n_nblocks <= STAT_SLOTS, "conv_igemm: channel sums support Cout <= %d", STAT_SLOTS * BN);
     FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));

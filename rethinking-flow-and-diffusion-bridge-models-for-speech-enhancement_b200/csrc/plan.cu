@@ -206,8 +206,8 @@ struct Builder {
     P->n_launches += 1;
   }
   // convolution; the channel statistics of its output come out of the same kernel's epilogue
-  void conv_op(ConvArgs c) {
-    const double flops = 2.0 * c.B * c.T * c.F * c.Cout * (static_cast<double>(c.ksize) * c.ksize * c.C1 + c.C2);
+  void conv_op(ConvArgs c, double flops = 0.0) {
+    if (flops == 0.0) flops = 2.0 * c.B * c.T * c.F * c.Cout * (static_cast<double>(c.ksize) * c.ksize * c.C1 + c.C2);
     op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV, flops);
   }
   void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
@@ -401,10 +401,19 @@ struct Builder {
     {
       const Mod& m = next();
       const float* w = pp(param(pre(m) + "weight", static_cast<int64_t>(nf) * Cp * 9)); const float* b = pp(param(pre(m) + "bias", nf));
+      // first conv (4 -> nf, 3x3) on the tensor cores: im2col to one 64-wide K-block, then a K=64 GEMM
+      op_t* wp = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
+      wp_off += (static_cast<int64_t>(nf) * 64 * 2 + 1023) / 1024 * 1024;
+      pack_op([=](cudaStream_t s) { return launch_pack_conv_weights(w, Cp, -2, nullptr, 0, nf, nf, 0, wp, s); });
       Act h0 = new_act(nf, T, F);
       const int Tc = T, Fc = F; float* src = pyr_in;
-      op([=](cudaStream_t s) { return launch_conv_in(src, Cp, w, b, B, Tc, Fc, nf, h0.data, s); }, FDBM_OP_SKINNY);
-      op([=](cudaStream_t s) { return launch_channel_stats(h0.data, B, Tc, Fc, nf, h0.sums, s); }, FDBM_OP_STATS);
+      op_t* cols = alloc<op_t>(static_cast<int64_t>(B) * T * F * 64);
+      op([=](cudaStream_t s) { return launch_im2col_input(src, Cp, B, Tc, Fc, cols, s); }, FDBM_OP_SKINNY);
+      ConvArgs c{};
+      c.in1 = cols; c.C1 = 64; c.ksize = 1; c.wpack = wp; c.bias = b; c.scale = 1.0f; c.B = B; c.T = T; c.F = F; c.Cout = nf;
+      c.out_f32 = h0.data; c.out_ld = nf; c.sums = h0.sums;
+      conv_op(c, 2.0 * B * T * F * nf * 9.0 * Cp);
+      release(cols);
       hs.push_back(h0);
     }
     // ---- down path
@@ -458,6 +467,14 @@ struct Builder {
         const int C = mg.cin, Tc = h.T, Fc = h.F;
         const float* gw = pp(param(pre(mg) + "weight", C)); const float* gb = pp(param(pre(mg) + "bias", C));
         const float* w = pp(param(pre(mc) + "weight", static_cast<int64_t>(Cp) * C * 9)); const float* b = pp(param(pre(mc) + "bias", Cp));
+        // C -> 4 conv on the tensor cores: weight rows padded with zeros to one 128-wide N block
+        op_t* wp = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
+        const int64_t wbytes = conv_wpack_bytes(C, 3, 0, 128);
+        wp_off += (wbytes + 1023) / 1024 * 1024;
+        pack_op([=](cudaStream_t s) {
+          FDBM_CUDA(cudaMemsetAsync(wp, 0, wbytes, s));
+          return launch_pack_conv_weights(w, C, 3, nullptr, 0, Cp, 128, 0, wp, s);
+        });
         op_t* a = alloc<op_t>(static_cast<int64_t>(B) * Tc * Fc * C);
         float* pyr_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
         float* prev = pyramid;
@@ -465,7 +482,10 @@ struct Builder {
         op([=](cudaStream_t s) {
           return launch_groupnorm_act(src, 0, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s);
         }, FDBM_OP_NORM);
-        op([=](cudaStream_t s) { return launch_pyramid_conv(a, C, w, b, prev, Cp, B, Tc, Fc, pyr_new, s); }, FDBM_OP_SKINNY);
+        ConvArgs c{};
+        c.in1 = a; c.C1 = C; c.ksize = 3; c.wpack = wp; c.bias = b; c.scale = 1.0f; c.B = B; c.T = Tc; c.F = Fc; c.Cout = 128;
+        c.pyr_out = pyr_new; c.pyr_prev = prev; c.pyr_C = Cp;
+        conv_op(c, 2.0 * B * Tc * Fc * Cp * 9.0 * C);
         release(a);
         release(pyramid);
         pyramid = pyr_new;

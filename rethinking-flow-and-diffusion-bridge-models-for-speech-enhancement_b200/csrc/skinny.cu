@@ -44,6 +44,36 @@ pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ y, in
 }
 
 // ------------------------------------------------------------------------------------------------
+// im2col of the 4 (or 2) channel input for the first 3x3 convolution: [B,T,F,Cin] fp32 -> [B,T,F,64] h16
+// with k = (kf*3 + kt)*Cin + ci (zero border, zero for k >= 9*Cin).  The convolution itself then runs on
+// the tensor cores as a K=64 GEMM with the fused-statistics epilogue (conv_igemm, ksize 1).
+// ------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+im2col_input_kernel(const float* __restrict__ in, int Cin, int B, int T, int F, uint4* __restrict__ out) {
+  const int64_t total = static_cast<int64_t>(B) * T * F * 8;           // 8 groups of 8 k-values per pixel
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int g = static_cast<int>(i & 7);
+    const int64_t p = i >> 3;
+    const int f = static_cast<int>(p % F);
+    const int t = static_cast<int>((p / F) % T);
+    const int b = static_cast<int>(p / (static_cast<int64_t>(F) * T));
+    float v[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int k = g * 8 + j;
+      const int tap = k / Cin, ci = k % Cin;
+      float x = 0.f;
+      if (tap < 9) {
+        const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
+        if (ff >= 0 && ff < F && tt >= 0 && tt < T) x = in[((static_cast<int64_t>(b) * T + tt) * F + ff) * Cin + ci];
+      }
+      v[j] = x;
+    }
+    out[i] = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // conv_in: a warp computes one pixel; lane l owns output channels 4l..4l+3 (+128 per repeat).
 // Weights sit in shared memory as [tap*Cin + ci][Cout].
 // ------------------------------------------------------------------------------------------------
@@ -236,6 +266,15 @@ int launch_pack_input(const float* x, const float* y, int B, int T, int F_in, in
   dim3 grid(ceil_div(T, 32), ceil_div(F, 32), B);
   pack_input_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y), T, F_in,
                                          F, Cin, out);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+int launch_im2col_input(const float* in, int Cin, int B, int T, int F, op_t* out, cudaStream_t s) {
+  FDBM_REQUIRE(Cin == 4 || Cin == 2, "im2col_input: Cin must be 2 or 4");
+  const int64_t total = static_cast<int64_t>(B) * T * F * 8;
+  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(num_sms()) * 16));
+  im2col_input_kernel<<<grid, 256, 0, s>>>(in, Cin, B, T, F, reinterpret_cast<uint4*>(out));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
