@@ -203,6 +203,15 @@ int fdbm_conv_igemm(const void* in1, int C1, int ksize, const void* in2, int C2,
                     const void* wpack, const float* bias, const float* bias_b, const float* residual,
                     float scale, int batch, int T, int F, int Cout,
                     float* out_f32, void* out_h16, double* sums, void* stream);
+/* The same convolution with GroupNorm(32 groups, eps 1e-6) (+ SiLU when silu != 0) applied to in1 ON LOAD
+ * (layerspp.py:242-246,266-268: h = Conv(act(GroupNorm(h)))): in1 is the RAW h16 tensor, sums1 double [B,C1,2]
+ * its per-channel sum / sum of squares over T*F pixels (as produced by `sums` of the producing convolution),
+ * gamma/beta fp32 [C1].  The tile is normalised in shared memory between the TMA landing and the MMA, so the
+ * stand-alone normalisation pass disappears.  `table` is caller-provided scratch of B*C1*2 floats. */
+int fdbm_conv_igemm_gn(const void* in1, int C1, int ksize, const double* sums1, const float* gamma,
+                       const float* beta, int silu, float* table, const void* wpack, const float* bias,
+                       const float* residual, float scale, int batch, int T, int F, int Cout,
+                       float* out_f32, void* out_h16, double* sums, void* stream);
 /* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
  * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]).  Returns bytes via *bytes when wpack==NULL. */
 int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,

@@ -46,13 +46,17 @@ __device__ __forceinline__ float silu_f(float v) { return v / (1.0f + __expf(-v)
 // significand (TF32's precision) -- GEMM operands here are GroupNorm-ed activations and weights, far
 // inside fp16's range; conversions saturate.  Build with -DFDBM_OPERAND_BF16 for bfloat16.
 #ifdef FDBM_OPERAND_BF16
-typedef op_t op_t;
-typedef op_t2 op2_t;
+typedef __nv_bfloat16 op_t;
+typedef __nv_bfloat162 op2_t;
 constexpr int kOperandIsBf16 = 1;
 __device__ __forceinline__ op_t f2op(float v) { return __float2bfloat16(v); }
 __device__ __forceinline__ float op2f(op_t v) { return __bfloat162float(v); }
 __device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2bfloat162_rn(a, b); }
 __device__ __forceinline__ float2 op22f2(op2_t v) { return __bfloat1622float2(v); }
+__device__ __forceinline__ op2_t op2_tanh(op2_t v) {
+  uint32_t r; asm("tanh.approx.bf16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&v)));
+  return *reinterpret_cast<op2_t*>(&r);
+}
 #else
 typedef __half op_t;
 typedef __half2 op2_t;
@@ -62,6 +66,10 @@ __device__ __forceinline__ op_t f2op(float v) { return __float2half_rn(sat16(v))
 __device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
 __device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2half2_rn(sat16(a), sat16(b)); }
 __device__ __forceinline__ float2 op22f2(op2_t v) { return __half22float2(v); }
+__device__ __forceinline__ op2_t op2_tanh(op2_t v) {          // MUFU.TANH on both halves, max abs error ~2^-11
+  uint32_t r; asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&v)));
+  return *reinterpret_cast<op2_t*>(&r);
+}
 #endif
 __device__ __forceinline__ uint32_t pack_op2(float a, float b) {
   op2_t v = f2op2(a, b);
@@ -92,19 +100,29 @@ int launch_temb(const float* t, const float* fourier_w, int nf, const float* w1,
                 const float* b2, int B, int t_stride, float* temb_act, cudaStream_t s);
 int launch_dense_all(const float* temb_act, const float* w, const float* bias, int B, int K, int rows, float* out,
                      cudaStream_t s);
+int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2, const float* gamma, const float* beta,
+                       int B, int64_t pixels, float2* table, cudaStream_t s);
 int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B, int L,
                      int C, op_t* o, int ldo, cudaStream_t s);
 
+// One K segment of the implicit GEMM: an activation tensor [B,T,F,C] (16-bit) read with 9 taps (3x3) or 1.
+// norm_tab != nullptr: GroupNorm (+SiLU if act) is applied on load, norm_tab[b * tab_stride + c] = (scale, shift).
+struct ConvSeg {
+  const op_t* in = nullptr; int C = 0; int taps = 9;
+  const float2* norm_tab = nullptr; int tab_stride = 0; int act = 0;
+};
 struct ConvArgs {
-  const op_t* in1; int C1; int ksize;
-  const op_t* in2; int C2;
-  const op_t* wpack;
-  const float* bias; const float* bias_b; int bias_b_stride; const float* residual;
-  float scale; int B, T, F, Cout;
-  float* out_f32; op_t* out_h16; int out_ld;      // out_ld: row stride (elements) of outputs, >= Cout
-  double* sums;
+  ConvSeg seg[3]; int n_seg = 0;
+  const op_t* wpack = nullptr;
+  const float* bias = nullptr; const float* bias_b = nullptr; int bias_b_stride = 0; const float* residual = nullptr;
+  float scale = 1.0f; int B = 0, T = 0, F = 0, Cout = 0;
+  float* out_f32 = nullptr; op_t* out_h16 = nullptr;
+  double* sums = nullptr;
   // pyramid epilogue (ncsnpp_v2.py:338-359): out = conv(...)[:, :pyr_C] + bias + FIR-up x2(pyr_prev); fp32 [B,T,F,pyr_C]
   float* pyr_out = nullptr; const float* pyr_prev = nullptr; int pyr_C = 0;
+  // Combine epilogue (layerspp.py:52-59): out += comb_b[n] + sum_k comb_w[n][k] * comb_pyr[b,t,f,k], applied after
+  // `scale`; comb_pyr is the fp32 input pyramid [B,T,F,comb_C] at the output resolution
+  const float* comb_pyr = nullptr; const float* comb_w = nullptr; const float* comb_b = nullptr; int comb_C = 0;
 };
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s);
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);

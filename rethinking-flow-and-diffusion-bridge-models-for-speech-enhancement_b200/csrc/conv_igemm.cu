@@ -35,20 +35,37 @@ constexpr int TILE_T = 16, TILE_F = 8;
 constexpr int HALO_T = TILE_T + 2, HALO_F = TILE_F + 2;
 constexpr int A_TILE_BYTES = HALO_T * HALO_F * 128;          // 23040 bytes landed per TMA box
 constexpr int A_TILE_STRIDE = 23552;                         // rounded up to 1024
-constexpr int A_STAGES = 2;
-constexpr int B_STAGES = 6;
+#ifndef FDBM_A_STAGES
+#define FDBM_A_STAGES 3
+#define FDBM_B_STAGES 4
+#endif
+constexpr int A_STAGES = FDBM_A_STAGES;
+constexpr int B_STAGES = FDBM_B_STAGES;
 constexpr int BN = 128;
 constexpr int B_TILE_BYTES = BN * 128;
 constexpr int A_SBO = HALO_F * 128;                          // 1280: distance between 8-pixel row groups
-constexpr int NUM_THREADS = 256;
+constexpr int NUM_THREADS = 384;                              // 4 pipeline warps + 4 epilogue warps + 4 operand-transform warps
+constexpr int MAX_SEG = 3;
+// 384 threads cap ptxas at 168 registers per thread; setmaxnreg moves registers from the pipeline and
+// transform warpgroups to the epilogue warpgroup (128 * (96 + 240 + 168) <= 65536)
+constexpr int PIPE_REGS = 96, EPI_REGS = 240, XFORM_REGS = 168;
 constexpr int STAGE_BYTES = 4 * 32 * 32 * 4;                    // epilogue transposition tiles, one per warp
 constexpr int STAT_SLOTS = 2;                                  // n-blocks whose statistics a CTA keeps in flight
 constexpr int STAT_BYTES = 4 * BN * 8;                         // per-warp channel (sum, sum of squares) partials
 constexpr int SMEM_BYTES = 1024 + A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + STAGE_BYTES + STAT_BYTES + 256;
 
+// One K segment = one activation tensor contributing C channels (kb = C/64 K-blocks) with 9 taps or 1.
+// norm != 0: GroupNorm (+SiLU when act != 0) is applied to the tile in shared memory between the TMA
+// landing and the MMA ("normalise on load"); tab[b * tab_stride + c] = (scale, shift) of channel c.
+struct SegParams {
+  int kb_begin, kb_end, taps, norm, act, tab_stride;
+  const float2* tab;
+};
+
 struct ConvParams {
   int B, T, F, Cout;
-  int kb1, taps1, kb2;
+  int n_seg, n_kb;
+  SegParams seg[MAX_SEG];
   int tiles_t, tiles_f, n_mtiles, n_nblocks, n_items;
   const float* bias;
   const float* bias_b;
@@ -61,6 +78,10 @@ struct ConvParams {
   float* pyr_out;
   const float* pyr_prev;
   int pyr_C;
+  const float* comb_pyr;
+  const float* comb_w;
+  const float* comb_b;
+  int comb_C;
 };
 
 struct TileCoord { int b, t0, f0; bool valid; };
@@ -76,9 +97,13 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int mi) {
   return c;
 }
 
+// COMB: the epilogue also applies the Combine 1x1 convolution of the input pyramid (kept out of the standard
+// instantiation: even as a not-taken branch it doubled the epilogue's time).
+template <bool COMB>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
-conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_constant__ CUtensorMap map_a2,
-                  const __grid_constant__ CUtensorMap map_b, const ConvParams p) {
+conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
+                  const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
+                  const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   uint8_t* sA = smem;
@@ -92,21 +117,24 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   uint64_t* b_empty = b_full + B_STAGES;
   uint64_t* acc_full = b_empty + B_STAGES;
   uint64_t* acc_empty = acc_full + 2;
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(acc_empty + 2);
+  uint64_t* a_ready = acc_empty + 2;                   // A stage transformed (or passed through) -> MMA may read it
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + A_STAGES);
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int n_kb = p.kb1 + p.kb2;
+  const int n_kb = p.n_kb;
+  auto seg_of = [&](int kb) { int sgi = 0; while (sgi + 1 < p.n_seg && kb >= p.seg[sgi].kb_end) ++sgi; return sgi; };
 
   if (threadIdx.x == 0) {
-    for (int i = 0; i < A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); }
+    for (int i = 0; i < A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(a_ready + i, 128); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
-    tma_prefetch_desc(&map_a1);
+    tma_prefetch_desc(&map_a0);
     tma_prefetch_desc(&map_b);
-    if (p.kb2) tma_prefetch_desc(&map_a2);
+    if (p.n_seg > 1) tma_prefetch_desc(&map_a1);
+    if (p.n_seg > 2) tma_prefetch_desc(&map_a2);
   }
   if (warp == 3) {
     tmem_alloc(tmem_slot, 512);
@@ -117,6 +145,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
 
+  if (warp < 4) {
+  reg_dec<PIPE_REGS>();
   if (warp == 0) {
     // ------------------------------------------------------------------ A producer
     if (lane == 0) {
@@ -129,8 +159,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         for (int kb = 0; kb < n_kb; ++kb) {
           mbar_wait(a_empty + stage, phase ^ 1);
           mbar_expect_tx(a_full + stage, n_valid * A_TILE_BYTES);
-          const CUtensorMap* map = kb < p.kb1 ? &map_a1 : &map_a2;
-          const int c0 = (kb < p.kb1 ? kb : kb - p.kb1) * 64;
+          const int sgi = seg_of(kb);
+          const CUtensorMap* map = sgi == 0 ? &map_a0 : (sgi == 1 ? &map_a1 : &map_a2);
+          const int c0 = (kb - p.seg[sgi].kb_begin) * 64;
           for (int j = 0; j < MT; ++j) {
             if (!tc[j].valid) continue;
             tma_load_4d(sA + (stage * MT + j) * A_TILE_STRIDE, map, a_full + stage, c0, tc[j].f0 - 1, tc[j].t0 - 1,
@@ -148,7 +179,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
         const int n0 = (item % p.n_nblocks) * BN;
         int kt = 0;
         for (int kb = 0; kb < n_kb; ++kb) {
-          const int ntaps = kb < p.kb1 ? p.taps1 : 1;
+          const int ntaps = p.seg[seg_of(kb)].taps;
           for (int tap = 0; tap < ntaps; ++tap, ++kt) {
             mbar_wait(b_empty + stage, phase ^ 1);
             mbar_expect_tx(b_full + stage, B_TILE_BYTES);
@@ -177,8 +208,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       uint32_t accumulate = 0;
       const uint32_t d0 = tmem_base + (as * MT) * BN, d1 = d0 + BN;
       for (int kb = 0; kb < n_kb; ++kb) {
-        const int ntaps = kb < p.kb1 ? p.taps1 : 1;
-        mbar_wait(a_full + sa, pa);
+        const SegParams& sg = p.seg[seg_of(kb)];
+        const int ntaps = sg.taps;
+        mbar_wait(sg.norm ? a_ready + sa : a_full + sa, pa);   // normalised-on-load stages are released by the transform warps
         fence_after_sync();
         const uint32_t a_base0 = sA_lo + ((sa * MT) * A_TILE_STRIDE >> 4), a_base1 = a_base0 + (A_TILE_STRIDE >> 4);
         int df = ntaps == 9 ? 0 : 1, dt = ntaps == 9 ? 0 : 1;           // tap -> (df, dt); 1x1 reads the box centre
@@ -210,17 +242,110 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
       }
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
+  }
+  } else if (warp >= 8) {
+    reg_dec<XFORM_REGS>();
+    // ------------------------------------------------------------------ operand transform (4 warps)
+    // GroupNorm (+SiLU) on load: when a segment is flagged `norm`, the raw 16-bit tile that TMA just
+    // landed is rewritten in place as act(x * scale[b,c] + shift[b,c]) before the MMA reads it, which
+    // removes the stand-alone normalisation pass (one read + one write of the tensor) from HBM.
+    // Thread -> fixed 8-channel group g (its scale/shift live in registers) and a lane of pixels; the
+    // physical 16-byte slot of group g in pixel row p is g ^ (p & 7) (TMA 128-byte swizzle).  Halo pixels
+    // outside the image stay zero: the convolution pads the *normalised* tensor with zeros.
+    // Arithmetic: the affine part in fp32 (an all-16-bit HFMA2 variant was 5% faster but doubled the backbone's
+    // error), SiLU(y) = h + h * tanh(h) with h = y/2 (the 1/2 is folded into scale/shift) in packed 16-bit: one
+    // MUFU.TANH per TWO elements.  -DFDBM_XF_EXACT selects fp32 ex2/rcp (A/B reference, ~2x the transform time).
+    // The transform shares each SM sub-partition with an epilogue warp and has ~4600 cycles per K-block; the
+    // (scale, shift) entries are fetched BEFORE waiting for the tile so that their latency is off the critical path.
+    const int tt = threadIdx.x - 256;
+    const int g = tt & 7, p_lane = tt >> 3;              // 16 pixel lanes
+    uint32_t stage = 0, phase = 0;
+    const bool any_norm = (p.seg[0].norm | p.seg[1].norm | p.seg[2].norm) != 0;   // else: the MMA warp never waits on a_ready
+    for (int item = blockIdx.x; any_norm && item < p.n_items; item += gridDim.x) {
+      const int ct = item / p.n_nblocks;
+      TileCoord tc[MT];
+      for (int j = 0; j < MT; ++j) tc[j] = decode_tile(p, ct * MT + j);
+      for (int kb = 0; kb < n_kb; ++kb) {
+        const SegParams& sg = p.seg[seg_of(kb)];
+        float sc[MT][8], sh[MT][8];
+        if (sg.norm) {
+          const int c0 = (kb - sg.kb_begin) * 64 + g * 8;
+          const float pre = sg.act ? 0.5f : 1.0f;
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            const float4* tp = reinterpret_cast<const float4*>(sg.tab + static_cast<int64_t>(tc[j].valid ? tc[j].b : 0) * sg.tab_stride + c0);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float4 e = __ldg(tp + u);
+              sc[j][2 * u] = pre * e.x; sh[j][2 * u] = pre * e.y; sc[j][2 * u + 1] = pre * e.z; sh[j][2 * u + 1] = pre * e.w;
+            }
+          }
+        }
+        mbar_wait(a_full + stage, phase);
+        if (sg.norm) {
+#pragma unroll
+          for (int j = 0; j < MT; ++j) {
+            if (!tc[j].valid) continue;
+            // halo rows / columns that lie inside the image (the rest is the convolution's zero padding)
+            const int r_lo = tc[j].t0 == 0 ? 1 : 0, r_hi = min(HALO_T, p.T - tc[j].t0 + 1);
+            const int c_lo = tc[j].f0 == 0 ? 1 : 0, c_hi = min(HALO_F, p.F - tc[j].f0 + 1);
+            uint8_t* tile = sA + (stage * MT + j) * A_TILE_STRIDE;
+            if (sg.act) {
+#pragma unroll 4
+              for (int px = p_lane; px < HALO_T * HALO_F; px += 16) {
+                const int hr = px / HALO_F, hc = px - hr * HALO_F;
+                if (hr < r_lo || hr >= r_hi || hc < c_lo || hc >= c_hi) continue;
+                uint4* slot = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
+                uint4 raw = *slot;
+                op2_t* h2 = reinterpret_cast<op2_t*>(&raw);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float2 v = op22f2(h2[u]);
+#ifdef FDBM_XF_EXACT
+                  v.x = 2.0f * fmaf(v.x, sc[j][2 * u], sh[j][2 * u]); v.y = 2.0f * fmaf(v.y, sc[j][2 * u + 1], sh[j][2 * u + 1]);
+                  h2[u] = f2op2(__fdividef(v.x, 1.0f + __expf(-v.x)), __fdividef(v.y, 1.0f + __expf(-v.y)));
+#else
+                  const op2_t h = f2op2(fmaf(v.x, sc[j][2 * u], sh[j][2 * u]), fmaf(v.y, sc[j][2 * u + 1], sh[j][2 * u + 1]));
+                  h2[u] = __hfma2(h, op2_tanh(h), h);
+#endif
+                }
+                *slot = raw;
+              }
+            } else {
+#pragma unroll 4
+              for (int px = p_lane; px < HALO_T * HALO_F; px += 16) {
+                const int hr = px / HALO_F, hc = px - hr * HALO_F;
+                if (hr < r_lo || hr >= r_hi || hc < c_lo || hc >= c_hi) continue;
+                uint4* slot = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
+                uint4 raw = *slot;
+                op2_t* h2 = reinterpret_cast<op2_t*>(&raw);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  float2 v = op22f2(h2[u]);
+                  h2[u] = f2op2(fmaf(v.x, sc[j][2 * u], sh[j][2 * u]), fmaf(v.y, sc[j][2 * u + 1], sh[j][2 * u + 1]));
+                }
+                *slot = raw;
+              }
+            }
+          }
+          fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core's async proxy
+        }
+        mbar_arrive(a_ready + stage);
+        if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+      }
+    }
   } else if (warp >= 4) {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     // tcgen05.ld hands every thread one pixel row (32 consecutive channels).  Writing that straight to
     // global memory would touch 32 different 128-byte lines per store instruction, so each warp first
     // transposes its 32x32 block through a swizzled shared-memory tile; afterwards 8 lanes cover the
     // 128 contiguous bytes of one pixel and every global access (bias, residual, outputs) is coalesced.
+    reg_inc<EPI_REGS>();
     const int q = warp & 3;                              // TMEM lane quadrant of this warp
     float4* stage = reinterpret_cast<float4*>(s_stage) + q * (32 * 8);       // [32 pixels][8 float4], XOR-swizzled
     const int cc = lane & 7;                             // channel quad inside the 32-channel chunk (transposed phase)
     const int rsub = lane >> 3;                          // pixel sub-row (transposed phase)
-    const int et = threadIdx.x - 128;                    // 0..127 among the epilogue threads
+    const int et = threadIdx.x - 128;                    // 0..127 among the epilogue threads (warps 4..7)
     uint32_t as = 0, pacc = 0;
     const bool do_stats = p.sums != nullptr;             // host guarantees n_nblocks <= STAT_SLOTS when sums are requested
     // GroupNorm statistics: every warp leaves its 32-pixel partial sums (fp32, fixed summation order) in its
@@ -325,6 +450,17 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
               res[it] = (okmask >> it) & 1 ? __ldg(reinterpret_cast<const float4*>(p.residual + poff[it] + ch * 32))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+          float4 cw[4], cbias = make_float4(0.f, 0.f, 0.f, 0.f);
+          if constexpr (COMB) {                               // Combine: 1x1 conv of the <=4-channel input pyramid
+            const int c = n0 + ch * 32 + cc * 4;
+            cbias = __ldg(reinterpret_cast<const float4*>(p.comb_b + c));
+#pragma unroll
+            for (int u = 0; u < 4; ++u) {
+              const float* wr = p.comb_w + (c + u) * p.comb_C;
+              cw[u] = make_float4(__ldg(wr), p.comb_C > 1 ? __ldg(wr + 1) : 0.f, p.comb_C > 2 ? __ldg(wr + 2) : 0.f,
+                                  p.comb_C > 3 ? __ldg(wr + 3) : 0.f);
+            }
+          }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
           tmem_ld_wait();
@@ -341,6 +477,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a1, const __grid_const
             o.x += bv[ch].x; o.y += bv[ch].y; o.z += bv[ch].z; o.w += bv[ch].w;
             if (p.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
             o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale;
+            if (COMB && ((okmask >> it) & 1)) {
+              const int m = q * 32 + it * 4 + rsub;
+              const float* pq = p.comb_pyr + ((static_cast<int64_t>(tc.b) * p.T + tc.t0 + (m >> 3)) * p.F + tc.f0 + (m & 7)) * p.comb_C;
+              const float p0 = __ldg(pq), p1 = p.comb_C > 1 ? __ldg(pq + 1) : 0.f, p2 = p.comb_C > 2 ? __ldg(pq + 2) : 0.f,
+                          p3 = p.comb_C > 3 ? __ldg(pq + 3) : 0.f;
+              o.x += cbias.x + cw[0].x * p0 + cw[0].y * p1 + cw[0].z * p2 + cw[0].w * p3;
+              o.y += cbias.y + cw[1].x * p0 + cw[1].y * p1 + cw[1].z * p2 + cw[1].w * p3;
+              o.z += cbias.z + cw[2].x * p0 + cw[2].y * p1 + cw[2].z * p2 + cw[2].w * p3;
+              o.w += cbias.w + cw[3].x * p0 + cw[3].y * p1 + cw[3].z * p2 + cw[3].w * p3;
+            }
             if ((okmask >> it) & 1) {
               if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + poff[it] + ch * 32) = o;
               if (p.out_h16) *reinterpret_cast<uint2*>(p.out_h16 + poff[it] + ch * 32) = make_uint2(pack_op2(o.x, o.y), pack_op2(o.z, o.w));
@@ -487,26 +633,39 @@ int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2
 }
 
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
-  FDBM_REQUIRE(a.C1 > 0 && a.C1 % 64 == 0 && a.C2 % 64 == 0, "conv_igemm: channels must be multiples of 64 (%d, %d)", a.C1, a.C2);
-  FDBM_REQUIRE(a.ksize == 1 || a.ksize == 3, "conv_igemm: ksize must be 1 or 3");
+  FDBM_REQUIRE(a.n_seg >= 1 && a.n_seg <= MAX_SEG, "conv_igemm: 1..%d K segments", MAX_SEG);
   FDBM_REQUIRE(a.Cout % BN == 0, "conv_igemm: Cout must be a multiple of %d (got %d)", BN, a.Cout);
-  FDBM_REQUIRE((a.C2 == 0) == (a.in2 == nullptr), "conv_igemm: in2 / C2 mismatch");
   FDBM_REQUIRE(a.out_f32 || a.out_h16 || a.pyr_out, "conv_igemm: no output");
   FDBM_REQUIRE(!a.pyr_out || (a.pyr_C >= 1 && a.pyr_C <= 4 && a.Cout == BN && !a.sums), "conv_igemm: bad pyramid epilogue arguments");
   FDBM_REQUIRE(!a.pyr_prev || (a.T % 2 == 0 && a.F % 2 == 0), "conv_igemm: pyramid level with odd size");
   static bool attr_set = false;
   if (!attr_set) {
-    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
-  CUtensorMap map_a1, map_a2, map_b;
-  if (int rc = make_act_map(&map_a1, a.in1, a.B, a.T, a.F, a.C1)) return rc;
-  if (a.in2) { if (int rc = make_act_map(&map_a2, a.in2, a.B, a.T, a.F, a.C2)) return rc; }
-  else map_a2 = map_a1;
+  FDBM_REQUIRE(!a.comb_pyr || (a.comb_w && a.comb_b && a.comb_C >= 1 && a.comb_C <= 4 && !a.pyr_out), "conv_igemm: bad Combine epilogue arguments");
+  CUtensorMap map_a[MAX_SEG], map_b;
   ConvParams p;
   p.B = a.B; p.T = a.T; p.F = a.F; p.Cout = a.Cout;
-  p.kb1 = a.C1 / 64; p.taps1 = a.ksize * a.ksize; p.kb2 = a.C2 / 64;
-  const int n_kt = p.kb1 * p.taps1 + p.kb2;
+  p.n_seg = a.n_seg;
+  int kb = 0, n_kt = 0;
+  for (int i = 0; i < MAX_SEG; ++i) {
+    if (i < a.n_seg) {
+      const ConvSeg& sg = a.seg[i];
+      FDBM_REQUIRE(sg.in && sg.C > 0 && sg.C % 64 == 0 && (sg.taps == 9 || sg.taps == 1),
+                   "conv_igemm: segment %d needs a tensor, C %% 64 == 0 and 9 or 1 taps (C=%d, taps=%d)", i, sg.C, sg.taps);
+      if (int rc = make_act_map(&map_a[i], sg.in, a.B, a.T, a.F, sg.C)) return rc;
+      p.seg[i].kb_begin = kb; kb += sg.C / 64; p.seg[i].kb_end = kb; p.seg[i].taps = sg.taps;
+      p.seg[i].norm = sg.norm_tab != nullptr; p.seg[i].act = sg.act; p.seg[i].tab = sg.norm_tab;
+      p.seg[i].tab_stride = sg.tab_stride;
+      n_kt += (sg.C / 64) * sg.taps;
+    } else {
+      map_a[i] = map_a[0];
+      p.seg[i] = SegParams{kb, kb, 1, 0, 0, 0, nullptr};
+    }
+  }
+  p.n_kb = kb;
   if (int rc = make_weight_map(&map_b, a.wpack, static_cast<int64_t>(n_kt) * a.Cout)) return rc;
   p.tiles_t = ceil_div(a.T, TILE_T); p.tiles_f = ceil_div(a.F, TILE_F);
   p.n_mtiles = a.B * p.tiles_t * p.tiles_f;
@@ -515,12 +674,14 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
   p.out_f32 = a.out_f32; p.out_h16 = a.out_h16; p.sums = a.sums;
   p.pyr_out = a.pyr_out; p.pyr_prev = a.pyr_prev; p.pyr_C = a.pyr_C;
+  p.comb_pyr = a.comb_pyr; p.comb_w = a.comb_w; p.comb_b = a.comb_b; p.comb_C = a.comb_C;
   if (a.sums) {
     FDBM_REQUIRE(p.n_nblocks <= STAT_SLOTS, "conv_igemm: channel sums support Cout <= %d", STAT_SLOTS * BN);
     FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));
   }
   const int grid = std::min(p.n_items, num_sms());
-  conv_igemm_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a1, map_a2, map_b, p);
+  if (a.comb_pyr) conv_igemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
+  else conv_igemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -545,12 +706,40 @@ extern "C" int fdbm_conv_igemm(const void* in1, int C1, int ksize, const void* i
                                int T, int F, int Cout, float* out_f32, void* out_h16, double* sums, void* stream) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(in1 && wpack && bias && batch > 0 && T > 0 && F > 0, "fdbm_conv_igemm: bad arguments");
+  FDBM_REQUIRE(ksize == 1 || ksize == 3, "fdbm_conv_igemm: ksize must be 1 or 3");
+  FDBM_REQUIRE((C2 == 0) == (in2 == nullptr), "fdbm_conv_igemm: in2 / C2 mismatch");
   ConvArgs a;
-  a.in1 = reinterpret_cast<const op_t*>(in1); a.C1 = C1; a.ksize = ksize;
-  a.in2 = reinterpret_cast<const op_t*>(in2); a.C2 = C2;
+  a.seg[0].in = reinterpret_cast<const op_t*>(in1); a.seg[0].C = C1; a.seg[0].taps = ksize * ksize;
+  a.n_seg = 1;
+  if (in2) { a.seg[1].in = reinterpret_cast<const op_t*>(in2); a.seg[1].C = C2; a.seg[1].taps = 1; a.n_seg = 2; }
   a.wpack = reinterpret_cast<const op_t*>(wpack);
   a.bias = bias; a.bias_b = bias_b; a.bias_b_stride = Cout; a.residual = residual; a.scale = scale;
   a.B = batch; a.T = T; a.F = F; a.Cout = Cout;
-  a.out_f32 = out_f32; a.out_h16 = reinterpret_cast<op_t*>(out_h16); a.out_ld = Cout; a.sums = sums;
+  a.out_f32 = out_f32; a.out_h16 = reinterpret_cast<op_t*>(out_h16); a.sums = sums;
+  return launch_conv_igemm(a, as_stream(stream));
+}
+
+// Same convolution with GroupNorm (+SiLU) applied to in1 on load: in1 is the RAW 16-bit tensor, sums1 its
+// per-channel (sum, sum of squares) over `T*F` pixels, gamma/beta the GroupNorm affine.  `table` is caller-provided
+// scratch of B*C1 float2.  Replaces groupnorm_act + conv_igemm for operands that need no resampling.
+extern "C" int fdbm_conv_igemm_gn(const void* in1, int C1, int ksize, const double* sums1, const float* gamma,
+                                  const float* beta, int silu, float* table, const void* wpack, const float* bias,
+                                  const float* residual, float scale, int batch, int T, int F, int Cout, float* out_f32,
+                                  void* out_h16, double* sums, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(in1 && sums1 && gamma && beta && table && wpack && bias && batch > 0 && T > 0 && F > 0,
+               "fdbm_conv_igemm_gn: bad arguments");
+  FDBM_REQUIRE(ksize == 1 || ksize == 3, "fdbm_conv_igemm_gn: ksize must be 1 or 3");
+  float2* tab = reinterpret_cast<float2*>(table);
+  if (int rc = launch_gn_finalize(sums1, C1, nullptr, 0, gamma, beta, batch, static_cast<int64_t>(T) * F, tab, as_stream(stream)))
+    return rc;
+  ConvArgs a;
+  a.seg[0].in = reinterpret_cast<const op_t*>(in1); a.seg[0].C = C1; a.seg[0].taps = ksize * ksize;
+  a.seg[0].norm_tab = tab; a.seg[0].tab_stride = C1; a.seg[0].act = silu;
+  a.n_seg = 1;
+  a.wpack = reinterpret_cast<const op_t*>(wpack);
+  a.bias = bias; a.residual = residual; a.scale = scale;
+  a.B = batch; a.T = T; a.F = F; a.Cout = Cout;
+  a.out_f32 = out_f32; a.out_h16 = reinterpret_cast<op_t*>(out_h16); a.sums = sums;
   return launch_conv_igemm(a, as_stream(stream));
 }

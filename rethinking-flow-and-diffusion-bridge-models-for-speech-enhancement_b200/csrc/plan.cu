@@ -25,8 +25,9 @@ struct Mod {
 
 struct Slot { int64_t off; int64_t numel; bool loaded; };     // fp32 parameter inside `params`
 
-struct Act {                 // one fp32 residual-stream tensor [B,T,F,C] with its channel sums
+struct Act {                 // one residual-stream tensor [B,T,F,C]: fp32 master, 16-bit GEMM-operand copy, channel sums
   float* data = nullptr;
+  op_t* h16 = nullptr;
   double* sums = nullptr;
   int C = 0, T = 0, F = 0;
 };
@@ -193,10 +194,24 @@ struct Builder {
   Act new_act(int C, int T, int F) {
     Act a; a.C = C; a.T = T; a.F = F;
     a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
+    a.h16 = alloc<op_t>(static_cast<int64_t>(P->B) * T * F * C);
     a.sums = alloc<double>(static_cast<int64_t>(P->B) * C * 2);
     return a;
   }
-  void free_act(Act& a) { release(a.data); release(a.sums); a.data = nullptr; a.sums = nullptr; }
+  void free_act(Act& a) { release(a.data); release(a.h16); release(a.sums); a.data = nullptr; a.h16 = nullptr; a.sums = nullptr; }
+  // (scale, shift) table of a GroupNorm over the channel concatenation x1 (+ x2): a tiny launch; the consuming
+  // convolution applies it while the operand tile sits in shared memory
+  float2* norm_table(const double* q1, int C1, const double* q2, int C2, const float* gamma, const float* beta, int T, int F) {
+    const int B = P->B;
+    float2* tab = alloc<float2>(static_cast<int64_t>(B) * (C1 + C2));
+    const int64_t px = static_cast<int64_t>(T) * F;
+    op([=](cudaStream_t s) { return launch_gn_finalize(q1, C1, q2, C2, gamma, beta, B, px, tab, s); }, FDBM_OP_STATS);
+    return tab;
+  }
+  static ConvSeg seg(const op_t* in, int C, int taps, const float2* tab = nullptr, int tab_stride = 0, int act = 0) {
+    ConvSeg sg; sg.in = in; sg.C = C; sg.taps = taps; sg.norm_tab = tab; sg.tab_stride = tab_stride; sg.act = act;
+    return sg;
+  }
 
   void op(std::function<int(cudaStream_t)> f, int kind, double flops = 0.0) {
     if (dry) return;
@@ -207,7 +222,11 @@ struct Builder {
   }
   // convolution; the channel statistics of its output come out of the same kernel's epilogue
   void conv_op(ConvArgs c, double flops = 0.0) {
-    if (flops == 0.0) flops = 2.0 * c.B * c.T * c.F * c.Cout * (static_cast<double>(c.ksize) * c.ksize * c.C1 + c.C2);
+    if (flops == 0.0) {
+      double k = 0.0;
+      for (int i = 0; i < c.n_seg; ++i) k += static_cast<double>(c.seg[i].taps) * c.seg[i].C;
+      flops = 2.0 * c.B * c.T * c.F * c.Cout * k;
+    }
     op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV, flops);
   }
   void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
@@ -232,7 +251,9 @@ struct Builder {
 
   // ---------------- layers
   // ResnetBlockBigGANpp (layerspp.py:242-274) on the concatenation of x1 (and x2)
-  Act resblock(const Mod& m, const Act& x1, const Act* x2, const float* dense, int dense_stride) {
+  struct CombineArgs { const float* pyr; const float* w; const float* b; int Cp; };
+  Act resblock(const Mod& m, const Act& x1, const Act* x2, const float* dense, int dense_stride,
+               const CombineArgs* comb = nullptr) {
     const int B = P->B, Cin = m.cin, Cout = m.cout;
     const int mode = m.down ? 1 : (m.up ? 2 : 0);
     const int T = x1.T, F = x1.F;
@@ -265,46 +286,53 @@ struct Builder {
     }
 
     const int64_t npx = static_cast<int64_t>(B) * To * Fo;
-    op_t* a0 = alloc<op_t>(npx * Cin);
-    op_t* xr = shortcut ? alloc<op_t>(npx * Cin) : nullptr;
-    {
-      const float* s1 = x1.data; const double* q1 = x1.sums; const int C1 = x1.C;
-      const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr; const int C2 = x2 ? x2->C : 0;
-      op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
-      }, FDBM_OP_NORM);
-    }
+    const int C1 = x1.C, C2 = x2 ? x2->C : 0;
     // Conv_0 output only feeds GroupNorm_1: keep it in the 16-bit operand format (its statistics are taken
     // from the fp32 accumulators in the conv epilogue, before rounding)
     op_t* h1 = alloc<op_t>(npx * Cout);
     double* h1_sums = alloc<double>(static_cast<int64_t>(B) * Cout * 2);
-    {
-      ConvArgs c{};
-      c.in1 = a0; c.C1 = Cin; c.ksize = 3; c.in2 = nullptr; c.C2 = 0; c.wpack = w0;
-      c.bias = c0b; c.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c.bias_b_stride = dense_stride;
-      c.residual = nullptr; c.scale = 1.0f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
-      c.out_f32 = nullptr; c.out_h16 = h1; c.out_ld = Cout; c.sums = h1_sums;
-      conv_op(c);
-    }
-    release(a0);
-    op_t* a1 = alloc<op_t>(npx * Cout);
-    {
-      const op_t* s1 = h1; const double* q1 = h1_sums;
+    op_t* a0 = nullptr; op_t* xr = nullptr; float2* tab0 = nullptr;
+    ConvArgs c0;
+    c0.wpack = w0; c0.bias = c0b; c0.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c0.bias_b_stride = dense_stride;
+    c0.B = B; c0.T = To; c0.F = Fo; c0.Cout = Cout; c0.out_h16 = h1; c0.sums = h1_sums;
+    if (mode == 0) {
+      // GroupNorm_0 + SiLU applied by Conv_0 on load, straight from the 16-bit copies of the residual stream
+      tab0 = norm_table(x1.sums, C1, x2 ? x2->sums : nullptr, C2, g0w, g0b, T, F);
+      c0.seg[0] = seg(x1.h16, C1, 9, tab0, Cin, 1); c0.n_seg = 1;
+      if (x2) { c0.seg[1] = seg(x2->h16, C2, 9, tab0 + C1, Cin, 1); c0.n_seg = 2; }
+    } else {
+      // resampling blocks: one pass does GroupNorm_0 + SiLU + FIR up/down of h and the FIR of the raw shortcut operand
+      a0 = alloc<op_t>(npx * Cin);
+      xr = alloc<op_t>(npx * Cin);
+      const float* s1 = x1.data; const double* q1 = x1.sums;
+      const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr;
       op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, 1, q1, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, a1, nullptr, s);
+        return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
       }, FDBM_OP_NORM);
+      c0.seg[0] = seg(a0, Cin, 9); c0.n_seg = 1;
     }
+    conv_op(c0);
+    release(a0); release(tab0);
+    float2* tab1 = norm_table(h1_sums, Cout, nullptr, 0, g1w, g1b, To, Fo);
     Act out = new_act(Cout, To, Fo);
     {
-      ConvArgs c{};
-      c.in1 = a1; c.C1 = Cout; c.ksize = 3; c.in2 = xr; c.C2 = shortcut ? Cin : 0; c.wpack = w1;
-      c.bias = bias1; c.bias_b = nullptr; c.bias_b_stride = 0; c.residual = shortcut ? nullptr : x1.data;
+      ConvArgs c;
+      c.seg[0] = seg(h1, Cout, 9, tab1, Cout, 1); c.n_seg = 1;
+      if (shortcut) {
+        if (mode == 0) {
+          c.seg[c.n_seg++] = seg(x1.h16, C1, 1);
+          if (x2) c.seg[c.n_seg++] = seg(x2->h16, C2, 1);
+        } else {
+          c.seg[c.n_seg++] = seg(xr, Cin, 1);
+        }
+      }
+      c.wpack = w1; c.bias = bias1; c.residual = shortcut ? nullptr : x1.data;
       c.scale = 0.70710678118654752f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
-      c.out_f32 = out.data; c.out_h16 = nullptr; c.out_ld = Cout; c.sums = out.sums;
+      c.out_f32 = out.data; c.out_h16 = out.h16; c.sums = out.sums;
+      if (comb) { c.comb_pyr = comb->pyr; c.comb_w = comb->w; c.comb_b = comb->b; c.comb_C = comb->Cp; }
       conv_op(c);
     }
-    release(h1); release(h1_sums);
-    release(a1);
+    release(h1); release(h1_sums); release(tab1);
     release(xr);
     return out;
   }
@@ -323,29 +351,25 @@ struct Builder {
     pack(p + "NIN_2.W", C, -1, "", 0, C, 3 * C, 2 * C, wqkv);
     op_t* w3 = pack(p + "NIN_3.W", C, -1, "", 0, C);
     const int64_t npx = static_cast<int64_t>(B) * T * F;
-    op_t* a = alloc<op_t>(npx * C);
-    {
-      const float* s1 = x.data; const double* q1 = x.sums;
-      op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, 0, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, a, nullptr, s);
-      }, FDBM_OP_NORM);
-    }
+    float2* tab = norm_table(x.sums, C, nullptr, 0, gw, gb, T, F);
     op_t* qkv = alloc<op_t>(npx * 3 * C);
     {
-      ConvArgs c{};
-      c.in1 = a; c.C1 = C; c.ksize = 1; c.wpack = wqkv; c.bias = bq; c.scale = 1.0f; c.B = B; c.T = T; c.F = F; c.Cout = 3 * C;
-      c.out_h16 = qkv; c.out_ld = 3 * C;
+      ConvArgs c;
+      c.seg[0] = seg(x.h16, C, 1, tab, C, 0); c.n_seg = 1;      // GroupNorm_0 (no activation) on load
+      c.wpack = wqkv; c.bias = bq; c.B = B; c.T = T; c.F = F; c.Cout = 3 * C;
+      c.out_h16 = qkv;
       conv_op(c);
     }
-    release(a);
+    release(tab);
     op_t* o = alloc<op_t>(npx * C);
     op([=](cudaStream_t s) { return launch_attention(qkv, qkv + C, qkv + 2 * C, 3 * C, B, T * F, C, o, C, s); }, FDBM_OP_ATTN);
     release(qkv);
     Act out = new_act(C, T, F);
     {
-      ConvArgs c{};
-      c.in1 = o; c.C1 = C; c.ksize = 1; c.wpack = w3; c.bias = b3; c.residual = x.data; c.scale = 0.70710678118654752f;
-      c.B = B; c.T = T; c.F = F; c.Cout = C; c.out_f32 = out.data; c.out_ld = C; c.sums = out.sums;
+      ConvArgs c;
+      c.seg[0] = seg(o, C, 1); c.n_seg = 1;
+      c.wpack = w3; c.bias = b3; c.residual = x.data; c.scale = 0.70710678118654752f;
+      c.B = B; c.T = T; c.F = F; c.Cout = C; c.out_f32 = out.data; c.out_h16 = out.h16; c.sums = out.sums;
       conv_op(c);
     }
     release(o);
@@ -409,9 +433,10 @@ struct Builder {
       const int Tc = T, Fc = F; float* src = pyr_in;
       op_t* cols = alloc<op_t>(static_cast<int64_t>(B) * T * F * 64);
       op([=](cudaStream_t s) { return launch_im2col_input(src, Cp, B, Tc, Fc, cols, s); }, FDBM_OP_SKINNY);
-      ConvArgs c{};
-      c.in1 = cols; c.C1 = 64; c.ksize = 1; c.wpack = wp; c.bias = b; c.scale = 1.0f; c.B = B; c.T = T; c.F = F; c.Cout = nf;
-      c.out_f32 = h0.data; c.out_ld = nf; c.sums = h0.sums;
+      ConvArgs c;
+      c.seg[0] = seg(cols, 64, 1); c.n_seg = 1;
+      c.wpack = wp; c.bias = b; c.B = B; c.T = T; c.F = F; c.Cout = nf;
+      c.out_f32 = h0.data; c.out_h16 = h0.h16; c.sums = h0.sums;
       conv_op(c, 2.0 * B * T * F * nf * 9.0 * Cp);
       release(cols);
       hs.push_back(h0);
@@ -424,7 +449,9 @@ struct Builder {
         hs.push_back(h);
       }
       if (lvl != L - 1) {
-        Act h = resblock(next(), hs.back(), nullptr, dense, dstride);
+        // input pyramid one level down, then the down-sampling block whose Conv_1 epilogue also applies the
+        // Combine (layerspp.py:52-59): h = resblock(...) + conv1x1(4 -> C)(pyramid)
+        const Mod& mr = next();
         float* pyr_next = alloc<float>(static_cast<int64_t>(B) * (T / 2) * (F / 2) * Cp);
         {
           const int Tc = T, Fc = F; float* src = pyr_in;
@@ -432,14 +459,13 @@ struct Builder {
         }
         release(pyr_in);
         pyr_in = pyr_next;
+        const Mod& m = pl.mods[mi];               // the Combine module follows the block
+        CombineArgs cb;
+        cb.pyr = pyr_in; cb.Cp = Cp;
+        cb.w = pp(param(pre(m) + "Conv_0.weight", static_cast<int64_t>(m.cout) * Cp)); cb.b = pp(param(pre(m) + "Conv_0.bias", m.cout));
+        Act h = resblock(mr, hs.back(), nullptr, dense, dstride, &cb);
+        next();
         T /= 2; F /= 2;
-        const Mod& m = next();
-        const float* w = pp(param(pre(m) + "Conv_0.weight", static_cast<int64_t>(m.cout) * Cp)); const float* b = pp(param(pre(m) + "Conv_0.bias", m.cout));
-        {
-          const int Tc = T, Fc = F, C = m.cout; float* src = pyr_in;
-          op([=](cudaStream_t s) { return launch_combine(h.data, src, Cp, w, b, B, Tc, Fc, C, s); }, FDBM_OP_SKINNY);
-          op([=](cudaStream_t s) { return launch_channel_stats(h.data, B, Tc, Fc, C, h.sums, s); }, FDBM_OP_STATS);
-        }
         hs.push_back(h);
       }
     }
@@ -475,18 +501,15 @@ struct Builder {
           FDBM_CUDA(cudaMemsetAsync(wp, 0, wbytes, s));
           return launch_pack_conv_weights(w, C, 3, nullptr, 0, Cp, 128, 0, wp, s);
         });
-        op_t* a = alloc<op_t>(static_cast<int64_t>(B) * Tc * Fc * C);
         float* pyr_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
         float* prev = pyramid;
-        const float* src = h.data; const double* sums = h.sums;
-        op([=](cudaStream_t s) {
-          return launch_groupnorm_act(src, 0, sums, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, a, nullptr, s);
-        }, FDBM_OP_NORM);
-        ConvArgs c{};
-        c.in1 = a; c.C1 = C; c.ksize = 3; c.wpack = wp; c.bias = b; c.scale = 1.0f; c.B = B; c.T = Tc; c.F = Fc; c.Cout = 128;
+        float2* tab = norm_table(h.sums, C, nullptr, 0, gw, gb, Tc, Fc);
+        ConvArgs c;
+        c.seg[0] = seg(h.h16, C, 9, tab, C, 1); c.n_seg = 1;     // GroupNorm + SiLU on load
+        c.wpack = wp; c.bias = b; c.B = B; c.T = Tc; c.F = Fc; c.Cout = 128;
         c.pyr_out = pyr_new; c.pyr_prev = prev; c.pyr_C = Cp;
         conv_op(c, 2.0 * B * Tc * Fc * Cp * 9.0 * C);
-        release(a);
+        release(tab);
         release(pyramid);
         pyramid = pyr_new;
       }

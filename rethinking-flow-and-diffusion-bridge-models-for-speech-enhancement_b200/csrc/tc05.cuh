@@ -23,6 +23,15 @@ __device__ __forceinline__ bool elect_one() {
 }
 
 // ------------------------------------------------------------------ mbarrier
+// register re-distribution between warpgroups (all four warps of an aligned group must execute it)
+#if 0
+template <int N> __device__ __forceinline__ void reg_dec() {}
+template <int N> __device__ __forceinline__ void reg_inc() {}
+#else
+template <int N> __device__ __forceinline__ void reg_dec() { asm volatile("setmaxnreg.dec.sync.aligned.u32 %0;" :: "n"(N)); }
+template <int N> __device__ __forceinline__ void reg_inc() { asm volatile("setmaxnreg.inc.sync.aligned.u32 %0;" :: "n"(N)); }
+#endif
+
 __device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
   asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }

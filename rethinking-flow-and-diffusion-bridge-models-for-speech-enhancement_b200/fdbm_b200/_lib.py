@@ -9,7 +9,7 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libfdbm_b200.so")
+LIB_PATH = os.environ.get("FDBM_B200_LIB") or os.path.join(_HERE, "libfdbm_b200.so")   # env override: developer A/B builds
 
 FDBM_PAD = {"zero_pad": 0, "reflection": 1, "replication": 2}
 FDBM_TRANSFORM = {"exponent": 0, "log": 1, "none": 2}
@@ -22,7 +22,7 @@ EXPORTS = [
     "fdbm_prior_sample", "fdbm_bridge_step",
     "fdbm_plan_create", "fdbm_plan_destroy", "fdbm_plan_load_weights", "fdbm_plan_device_bytes",
     "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run", "fdbm_plan_profile_forward",
-    "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm",
+    "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm", "fdbm_conv_igemm_gn",
     "fdbm_pack_conv_weights", "fdbm_attention",
 ]
 
@@ -73,10 +73,13 @@ def load() -> C.CDLL:
         "fdbm_channel_stats": (i, [p, i, i, i, i, p, p]),
         "fdbm_groupnorm_act": (i, [p, p, i, p, p, i, p, p, i, i, i, i, i, p, p, p]),
         "fdbm_conv_igemm": (i, [p, i, i, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
+        "fdbm_conv_igemm_gn": (i, [p, i, i, p, p, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
         "fdbm_pack_conv_weights": (i, [p, i, i, p, i, i, p, C.POINTER(i64), p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
     }
     for name, (res, args) in sig.items():
+        if not hasattr(lib, name) and os.environ.get("FDBM_B200_LIB"):
+            continue                      # developer A/B build of an older revision
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args

@@ -270,6 +270,48 @@ def test_conv_igemm(lib, B, T, Fq, C1, k, C2, Cout, residual, bias_b):
     _conv_case(lib, B, T, Fq, C1, k, C2, Cout, residual, bias_b, seed=B * 1000 + T + C1)
 
 
+@pytest.mark.parametrize("B,T,Fq,C1,k,Cout,silu", [
+    (2, 16, 16, 128, 3, 128, 1),       # GroupNorm_1 + SiLU + Conv_1 shape class
+    (1, 20, 12, 256, 3, 256, 1),       # ragged tiles: halo pixels outside the image must stay exactly zero
+    (2, 16, 16, 256, 1, 256, 0),       # attention GroupNorm (no activation) + NIN
+])
+def test_conv_igemm_groupnorm_on_load(lib, B, T, Fq, C1, k, Cout, silu):
+    """conv(act(GroupNorm(x))) with the normalisation applied to the operand tile in shared memory
+    (layerspp.py:242-246): compared with torch GroupNorm -> SiLU -> conv2d in fp64 on the same 16-bit x."""
+    g = torch.Generator().manual_seed(B * 100 + T + C1 + k)
+    x = (torch.randn(B, C1, Fq, T, generator=g) * 1.7 + 0.4).to(_h16()).float()
+    gamma = 1 + 0.1 * torch.randn(C1, generator=g)
+    beta = 0.1 * torch.randn(C1, generator=g)
+    w = (torch.randn(Cout, C1, k, k, generator=g) / (C1 * k * k) ** 0.5).to(_h16()).float()
+    bias = torch.randn(Cout, generator=g)
+    a = F.group_norm(x.double(), 32, gamma.double(), beta.double(), eps=1e-6)
+    if silu:
+        a = F.silu(a)
+    ref = (F.conv2d(a, w.double(), bias.double(), padding=k // 2)).float()
+
+    nbytes = C.c_int64()
+    _check(lib, lib.fdbm_pack_conv_weights(None, C1, k, None, 0, Cout, None, C.byref(nbytes), None))
+    wpack = torch.empty(nbytes.value // 2, dtype=_h16(), device="cuda")
+    wd = w.cuda()
+    _check(lib, lib.fdbm_pack_conv_weights(wd.data_ptr(), C1, k, None, 0, Cout, wpack.data_ptr(), None, _stream()))
+    xd = nchw_to_ntfc(x).to(_h16()).cuda()
+    sums1 = torch.stack([x.double().sum((2, 3)), x.double().pow(2).sum((2, 3))], -1).cuda()
+    gd, bd, biasd = gamma.cuda(), beta.cuda(), bias.cuda()
+    table = torch.empty(B * C1 * 2, device="cuda")
+    out = torch.full((B, T, Fq, Cout), float("nan"), device="cuda")
+    sums = torch.empty(B, Cout, 2, dtype=torch.float64, device="cuda")
+    _check(lib, lib.fdbm_conv_igemm_gn(xd.data_ptr(), C1, k, sums1.data_ptr(), gd.data_ptr(), bd.data_ptr(), silu,
+                                       table.data_ptr(), wpack.data_ptr(), biasd.data_ptr(), None, 1.0, B, T, Fq,
+                                       Cout, out.data_ptr(), None, sums.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    got = ntfc_to_nchw(out).cpu()
+    assert torch.isfinite(got).all()
+    err = rel_l2(got, ref)
+    assert err < 1e-3, f"normalise-on-load conv differs from GroupNorm->SiLU->conv2d: rel L2 {err}"   # operand rounding 2^-12
+    want = torch.stack([ref.double().sum((2, 3)), ref.double().pow(2).sum((2, 3))], -1)
+    assert rel_l2(sums, want) < 2e-3
+
+
 def test_attention(lib):
     g = torch.Generator().manual_seed(4)
     B, L, Cc = 2, 96, 256

@@ -29,7 +29,18 @@ for (T, F, C1, k, C2, Cout, res, f32o, sm) in shapes:
     out = torch.empty(B, T, F, Cout, device="cuda") if f32o else None
     o16 = None if f32o else torch.empty(B, T, F, Cout, dtype=h16, device="cuda")
     sums = torch.empty(B, Cout, 2, dtype=torch.float64, device="cuda") if sm else None
+    gn = len(sys.argv) > 3 and sys.argv[3] == "gn" and C2 == 0
+    if gn:
+        s1 = torch.stack([x1.double().sum((1, 2)), x1.double().pow(2).sum((1, 2))], -1).contiguous()
+        gam = torch.ones(C1, device="cuda"); bet = torch.zeros(C1, device="cuda"); tab = torch.empty(B * C1 * 2, device="cuda")
     def run():
+        if gn:
+            rc = lib.fdbm_conv_igemm_gn(x1.data_ptr(), C1, k, s1.data_ptr(), gam.data_ptr(), bet.data_ptr(), 1, tab.data_ptr(),
+                                        wp.data_ptr(), bias.data_ptr(), resid.data_ptr() if res else None, 0.7071, B, T, F, Cout,
+                                        out.data_ptr() if f32o else None, o16.data_ptr() if o16 is not None else None,
+                                        sums.data_ptr() if sm else None, st())
+            assert rc == 0, lib.fdbm_last_error()
+            return
         rc = lib.fdbm_conv_igemm(x1.data_ptr(), C1, k, x2.data_ptr() if C2 else None, C2, wp.data_ptr(), bias.data_ptr(), None,
                                  resid.data_ptr() if res else None, 0.7071, B, T, F, Cout, out.data_ptr() if f32o else None,
                                  o16.data_ptr() if o16 is not None else None, sums.data_ptr() if sm else None, st())
@@ -41,4 +52,4 @@ for (T, F, C1, k, C2, Cout, res, f32o, sm) in shapes:
     e1.record(); torch.cuda.synchronize()
     ms = e0.elapsed_time(e1) / reps
     fl = 2.0 * B * T * F * Cout * (k * k * C1 + C2)
-    print(f"B={B} T={T} F={F} C1={C1} k={k} C2={C2} Cout={Cout} res={int(res)} f32={int(f32o)}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s")
+    print(("gn " if gn else "   ") + f"B={B} T={T} F={F} C1={C1} k={k} C2={C2} Cout={Cout} res={int(res)} f32={int(f32o)}: {ms*1e3:8.1f} us  {fl/ms/1e9:7.1f} TFLOP/s")
