@@ -39,6 +39,16 @@ METRIC = "enhanced audio-sec/sec (5-step SB bridge, ncsnpp_v2)"
 UNIT = "audio-s/s"
 
 
+def set_workload(seconds, steps, predictive):
+    """BASELINE.json configs[2] (predictive) and configs[4] (step sweep, 30 s utterances) reuse this script."""
+    global UTT_SECONDS, N_SAMPLES, BRIDGE_STEPS, METRIC, GFLOP_PER_FORWARD
+    UTT_SECONDS, N_SAMPLES, BRIDGE_STEPS = float(seconds), int(SR * seconds), (1 if predictive else int(steps))
+    frames = -(-(1 + N_SAMPLES // 256) // 64) * 64
+    GFLOP_PER_FORWARD = (533.0 if predictive else 532.1) * frames / 256.0
+    METRIC = ("enhanced audio-sec/sec (predictive ncsnpp_v2_predictive, single pass)" if predictive
+              else f"enhanced audio-sec/sec ({BRIDGE_STEPS}-step SB bridge, ncsnpp_v2)")
+
+
 def synth_batch(n, device, seed=1234):
     """Synthetic noisy utterances (SURVEY.md section 8(d) recipe, vectorised): 8 harmonics of f0~U(100,300) Hz
     with 1/k roll-off and a 3 Hz envelope, plus white noise at SNR~U(0,15) dB.  fp32 [n, N_SAMPLES]."""
@@ -147,6 +157,65 @@ def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None):
     return seconds / dt, dt * 1e3, sample, cores
 
 
+# dram bytes (read + write) of all conv_igemm launches of ONE forward at micro-batch 32, T=256, from the ncu --set full
+# capture summarised in profiles/r01c_conv_traffic.txt (22.149 GB read + 18.759 GB written)
+NCU_CONV_DRAM_GB_PER_FORWARD_MB32 = 40.908
+
+
+def hbm_kernel_leg(model, waves, dev, reps=20):
+    """The HBM-bound kernels of the path timed alone with CUDA events on the whole per-GPU batch (inputs >> L2):
+    fused STFT+compress+pad, fused decompress+iSTFT and the bridge update; algorithmic bytes / time."""
+    import torch
+    from fdbm_b200 import _lib
+    lib = _lib.load()
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6500.0))
+    n, ts = waves.shape
+    dm = model.data_module
+    y = waves / waves.abs().amax(1, keepdim=True)
+
+    def timeit(fn):
+        for _ in range(3):
+            fn()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        e0.record()
+        for _ in range(reps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    Y = dm.stft_compress(y, pad_mode=model.pad_mode)
+    frames = Y.shape[-1]
+    spec_bytes = Y.numel() * 8
+    out = {}
+    ms = timeit(lambda: dm.stft_compress(y, pad_mode=model.pad_mode))
+    out["stft_compress"] = {"bytes": n * ts * 4 + spec_bytes, "ms": ms}
+    ms = timeit(lambda: dm.to_audio(Y[:, 0], ts))
+    out["decompress_istft"] = {"bytes": spec_bytes + n * ts * 4, "ms": ms}
+    x = Y.clone()
+    d = Y.clone()
+    coef = torch.tensor([0.8, 0.2, -0.1], device=dev)
+    xr, dr, yr = (torch.view_as_real(v) for v in (x, d, Y))
+
+    def step():
+        _lib.check(lib.fdbm_bridge_step(xr.data_ptr(), dr.data_ptr(), yr.data_ptr(), coef.data_ptr(), 0, 0, 0,
+                                        x.numel(), _lib.current_stream()), "fdbm_bridge_step")
+    ms = timeit(step)
+    out["bridge_step_ode"] = {"bytes": 4 * spec_bytes, "ms": ms}
+    for v in out.values():
+        v["GB/s"] = v["bytes"] / (v["ms"] * 1e-3) / 1e9
+        v["frac_of_measured_hbm_peak"] = v["GB/s"] / peak
+    out["peak_GB/s"] = peak
+    out["batch"] = f"{n} utterances x {ts / SR:g} s ({frames} frames)"
+    return out
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -156,14 +225,22 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "32")))
     ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive"],
+                    help="BASELINE.json configs[1] (default, the headline metric) or configs[2]")
+    ap.add_argument("--bridge-steps", type=int, default=5, help="configs[4]: sampling-step sweep 1/5/10/30")
+    ap.add_argument("--seconds", type=float, default=4.0, help="configs[4]: utterance length (30 s long-form)")
     args = ap.parse_args()
+    predictive = args.workload == "predictive"
+    set_workload(args.seconds, args.bridge_steps, predictive)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": f"infer_folder: {args.utts} synthetic {UTT_SECONDS:g} s 16 kHz utterances per GPU, ncsnpp_v2 "
-                          f"(65.6 M params, random init re-sensitised), Bridge('sb','bb') ode_ei N={BRIDGE_STEPS}, "
-                          "fused STFT/compress/pad and decompress/iSTFT",
+    config = {"workload": (f"{args.workload}: {args.utts} synthetic {UTT_SECONDS:g} s 16 kHz utterances per GPU, " +
+                           ("ncsnpp_v2_predictive (random init re-sensitised), one backbone pass, "
+                            if predictive else
+                            f"ncsnpp_v2 (65.6 M params, random init re-sensitised), Bridge('sb','bb') ode_ei N={BRIDGE_STEPS}, ") +
+                           "fused STFT/compress/pad and decompress/iSTFT"),
               "utterances_per_gpu": args.utts, "bridge_steps": BRIDGE_STEPS}
 
     if args.impl == "reference":
@@ -182,6 +259,7 @@ def main():
     import torch
     import torch.distributed as dist
     from fdbm_b200 import EnhancementModel, _lib, sensitise_
+    from fdbm_b200.model import PredictiveEnhancementModel
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     if world > 1:
@@ -189,7 +267,10 @@ def main():
     _lib.check(_lib.load().fdbm_check_device(), "fdbm_check_device")
 
     mb = args.micro_batch
-    model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
+    if predictive:
+        model = PredictiveEnhancementModel("ncsnpp_v2_predictive")
+    else:
+        model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
     sensitise_(model.dnn, seed=0)
     model = model.to(dev).eval()
     waves = synth_batch(args.utts, dev, seed=1234 + 100000 * rank)        # rank r owns its own utterances
@@ -241,11 +322,14 @@ def main():
 
     # roofline of the dominant kernel: every launch of one forward timed with CUDA events
     roofline, shares = None, None
-    info = model.dnn.plan_info(mb, 256)
+    n_frames = -(-(1 + N_SAMPLES // 256) // 64) * 64
+    info = model.dnn.plan_info(mb, n_frames)
+    hbm_kernels = None
     if rank == 0:
-        Y = model.data_module.stft_compress(waves[:mb] / waves[:mb].abs().amax(1, keepdim=True), pad_mode="reflection")
+        Y = model.data_module.stft_compress(waves[:mb] / waves[:mb].abs().amax(1, keepdim=True), pad_mode=model.pad_mode)
         t = torch.full((mb,), 0.5, device=dev)
-        prof = [model.dnn.profile_forward(Y, Y, t) for _ in range(3)][-1]
+        prof = [(model.dnn.profile_forward(Y) if predictive else model.dnn.profile_forward(Y, Y, t)) for _ in range(3)][-1]
+        hbm_kernels = hbm_kernel_leg(model, waves, dev)
         kind_ms = {}
         for ms, kind, _ in prof:
             kind_ms[kind] = kind_ms.get(kind, 0.0) + ms
@@ -263,7 +347,10 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                    "traffic": None, "launches_per_forward": n_conv,
+                    "traffic": NCU_CONV_DRAM_GB_PER_FORWARD_MB32 * 1e9 / max(1, n_conv) if (mb == 32 and n_frames == 256 and not predictive) else None,
+                    "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one "
+                                    "forward at micro-batch 32, ncu --set full, profiles/r01c_conv_traffic.txt) / launches",
+                    "launches_per_forward": n_conv,
                     "avg_launch_ms": conv_ms / max(1, n_conv),
                     "algorithmic_gflop_per_forward_per_utt": conv_flops / mb / 1e9}
         tot = sum(kind_ms.values())
@@ -292,7 +379,8 @@ def main():
             "gpu_launches": launches_per_step * args.steps,
             "per_backbone_forward_ms_per_utt": ms_total / args.steps / (args.utts * BRIDGE_STEPS),
             "model_tflops": GFLOP_PER_FORWARD * BRIDGE_STEPS * args.utts * world * args.steps / (ms_total * 1e-3) / 1e3,
-            "roofline": roofline, "kernel_share": shares, "cpu_baseline": cpu_baseline, "clocks": clock_info}))
+            "roofline": roofline, "kernel_share": shares, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
+            "clocks": clock_info}))
     if world > 1:
         dist.destroy_process_group()
     return 0

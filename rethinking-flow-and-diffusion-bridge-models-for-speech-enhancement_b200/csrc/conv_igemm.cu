@@ -469,32 +469,39 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             stage[lane * 8 + (g ^ (lane & 7))] = make_float4(__uint_as_float(v[4 * g]), __uint_as_float(v[4 * g + 1]),
                                                              __uint_as_float(v[4 * g + 2]), __uint_as_float(v[4 * g + 3]));
           __syncwarp();
-          float4 ssum = make_float4(0.f, 0.f, 0.f, 0.f), ssq = ssum;
+          // packed fp32x2 arithmetic (FFMA2 / FADD2): the single epilogue warp of an SM sub-partition is bound by
+          // its own instruction latencies, so halving the instruction count is what speeds it up.
+          // out = acc * scale + (bias * scale) (+ residual * scale)
+          float2 ssum_lo = make_float2(0.f, 0.f), ssum_hi = ssum_lo, ssq_lo = ssum_lo, ssq_hi = ssum_lo;
+          const float2 sc2 = make_float2(p.scale, p.scale);
+          const float2 bs_lo = __fmul2_rn(make_float2(bv[ch].x, bv[ch].y), sc2), bs_hi = __fmul2_rn(make_float2(bv[ch].z, bv[ch].w), sc2);
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
             const int rr = it * 4 + rsub;                 // pixel row inside this warp's quadrant
-            float4 o = stage[rr * 8 + (cc ^ (rr & 7))];
-            o.x += bv[ch].x; o.y += bv[ch].y; o.z += bv[ch].z; o.w += bv[ch].w;
-            if (p.residual) { o.x += res[it].x; o.y += res[it].y; o.z += res[it].z; o.w += res[it].w; }
-            o.x *= p.scale; o.y *= p.scale; o.z *= p.scale; o.w *= p.scale;
+            const float4 a = stage[rr * 8 + (cc ^ (rr & 7))];
+            float2 o_lo = __ffma2_rn(make_float2(a.x, a.y), sc2, bs_lo), o_hi = __ffma2_rn(make_float2(a.z, a.w), sc2, bs_hi);
+            if (p.residual) {
+              o_lo = __ffma2_rn(make_float2(res[it].x, res[it].y), sc2, o_lo);
+              o_hi = __ffma2_rn(make_float2(res[it].z, res[it].w), sc2, o_hi);
+            }
             if (COMB && ((okmask >> it) & 1)) {
               const int m = q * 32 + it * 4 + rsub;
               const float* pq = p.comb_pyr + ((static_cast<int64_t>(tc.b) * p.T + tc.t0 + (m >> 3)) * p.F + tc.f0 + (m & 7)) * p.comb_C;
               const float p0 = __ldg(pq), p1 = p.comb_C > 1 ? __ldg(pq + 1) : 0.f, p2 = p.comb_C > 2 ? __ldg(pq + 2) : 0.f,
                           p3 = p.comb_C > 3 ? __ldg(pq + 3) : 0.f;
-              o.x += cbias.x + cw[0].x * p0 + cw[0].y * p1 + cw[0].z * p2 + cw[0].w * p3;
-              o.y += cbias.y + cw[1].x * p0 + cw[1].y * p1 + cw[1].z * p2 + cw[1].w * p3;
-              o.z += cbias.z + cw[2].x * p0 + cw[2].y * p1 + cw[2].z * p2 + cw[2].w * p3;
-              o.w += cbias.w + cw[3].x * p0 + cw[3].y * p1 + cw[3].z * p2 + cw[3].w * p3;
+              o_lo.x += cbias.x + cw[0].x * p0 + cw[0].y * p1 + cw[0].z * p2 + cw[0].w * p3;
+              o_lo.y += cbias.y + cw[1].x * p0 + cw[1].y * p1 + cw[1].z * p2 + cw[1].w * p3;
+              o_hi.x += cbias.z + cw[2].x * p0 + cw[2].y * p1 + cw[2].z * p2 + cw[2].w * p3;
+              o_hi.y += cbias.w + cw[3].x * p0 + cw[3].y * p1 + cw[3].z * p2 + cw[3].w * p3;
             }
             if ((okmask >> it) & 1) {
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + poff[it] + ch * 32) = o;
-              if (p.out_h16) *reinterpret_cast<uint2*>(p.out_h16 + poff[it] + ch * 32) = make_uint2(pack_op2(o.x, o.y), pack_op2(o.z, o.w));
-              ssum.x += o.x; ssum.y += o.y; ssum.z += o.z; ssum.w += o.w;
-              ssq.x = fmaf(o.x, o.x, ssq.x); ssq.y = fmaf(o.y, o.y, ssq.y);
-              ssq.z = fmaf(o.z, o.z, ssq.z); ssq.w = fmaf(o.w, o.w, ssq.w);
+              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + poff[it] + ch * 32) = make_float4(o_lo.x, o_lo.y, o_hi.x, o_hi.y);
+              if (p.out_h16) *reinterpret_cast<uint2*>(p.out_h16 + poff[it] + ch * 32) = make_uint2(pack_op2(o_lo.x, o_lo.y), pack_op2(o_hi.x, o_hi.y));
+              ssum_lo = __fadd2_rn(ssum_lo, o_lo); ssum_hi = __fadd2_rn(ssum_hi, o_hi);
+              ssq_lo = __ffma2_rn(o_lo, o_lo, ssq_lo); ssq_hi = __ffma2_rn(o_hi, o_hi, ssq_hi);
             }
           }
+          float4 ssum = make_float4(ssum_lo.x, ssum_lo.y, ssum_hi.x, ssum_hi.y), ssq = make_float4(ssq_lo.x, ssq_lo.y, ssq_hi.x, ssq_hi.y);
           if (do_stats) {
 #pragma unroll
             for (int sft = 8; sft <= 16; sft <<= 1) {

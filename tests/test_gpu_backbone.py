@@ -107,6 +107,25 @@ def test_backbone_full_size_vs_oracle(nets):
     assert err < TOL_BF16
 
 
+def test_backbone_long_form_30s(nets):
+    """BASELINE.json configs[4]: a 30 s utterance = 1876 -> 1920 frames; attention runs over 16 x 120 = 1920 tokens,
+    ragged 16-frame tiles appear at every level.  Compared with the oracle on the same input."""
+    O, cfg, sd, net = nets
+    g = torch.Generator().manual_seed(30)
+    _, noisy = O.synth_pair(9, n_samples=16000 * 30)
+    sc = O.SpecConfig()
+    Y = O.pad_spec(O.spec_fwd(O.stft(noisy[None] / noisy.abs().max(), sc), sc)[:, None], mode="reflection")
+    assert Y.shape[-1] == 1920
+    xt = Y + 0.2 * torch.view_as_complex(torch.randn(1, 1, 257, 1920, 2, generator=g))
+    t = torch.tensor([0.7])
+    with torch.no_grad():
+        ref = O.ncsnpp_forward(sd, cfg, xt, Y, t)
+    D = net(xt.cuda(), Y.cuda(), t.cuda())
+    err = rel_l2(D, ref)
+    print(f"backbone T=1920 (30 s) rel L2 vs oracle: {err:.3e}")
+    assert err < TOL_BF16
+
+
 def test_predictive_golden(golden_dir):
     import fdbm_oracle as O
     from fdbm_b200 import BackboneRegistry
