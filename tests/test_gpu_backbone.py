@@ -144,31 +144,35 @@ def test_predictive_golden(golden_dir):
 
 
 def test_enhance_si_sdr_matches_oracle(nets):
-    """infer_single flow on synthetic 1 s utterances: the SI-SDR (vs clean) of the enhanced waveforms, averaged over the
-    utterances as an evaluation reports it, within 0.05 dB of the oracle's (north-star bound); each pair of enhanced
-    waveforms agrees to > 35 dB.  (With a random-weight network a single utterance's SI-SDR moves by up to ~0.1 dB
-    between rounding realisations of the 16-bit operands, so the single-utterance figure is printed, bounded at 0.15.)"""
+    """infer_single flow on synthetic 1 s utterances, north-star bound "waveform SI-SDR within 0.05 dB of the reference".
+    With random weights the enhanced waveform is unrelated to the clean one (SI-SDR vs clean is -20 ... -46 dB, printed
+    for information): that figure is ill-conditioned and says nothing about parity.  The bound is therefore checked
+    against a target the REFERENCE output scores 15 dB on (target = reference output + independent noise 15 dB below it,
+    the regime of a trained model): SI-SDR(target, ours) must be within 0.05 dB of SI-SDR(target, reference).  The two
+    enhanced waveforms must also agree to > 35 dB."""
     O, cfg, sd, net = nets
+    import numpy as np
     from fdbm_b200 import EnhancementModel
     model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=5, sampler_type="ode_ei"))
     model.dnn.load_state_dict(sd)
     model = model.cuda().eval()
     ob = O.Bridge("sb", N=5, sampler_type="ode_ei")
-    new_sdr, ref_sdr = [], []
+    rng = np.random.default_rng(0)
     for utt in (3, 4, 5, 6):
         clean, noisy = O.synth_pair(utt, n_samples=16000)
         got = model.enhance(noisy[None])
         with torch.no_grad():
             ref = O.enhance(noisy[None], lambda a, b, c: O.ncsnpp_forward(sd, cfg, a, b, c), ob, O.SpecConfig()).numpy()
         c = clean.numpy()
-        new_sdr.append(O.si_sdr(c, got)); ref_sdr.append(O.si_sdr(c, ref))
+        n = rng.standard_normal(ref.shape).astype(np.float64)
+        n -= ref * (n @ ref) / (ref @ ref)
+        target = ref + n * np.sqrt((ref @ ref) / (n @ n) / 10 ** 1.5)
+        s_ref, s_new = O.si_sdr(target, ref), O.si_sdr(target, got)
         agree = O.si_sdr(ref, got)
-        print(f"enhance utt {utt}: SI-SDR new {new_sdr[-1]:.3f} ref {ref_sdr[-1]:.3f} dB, SI-SDR(new vs oracle) {agree:.1f} dB")
-        assert abs(new_sdr[-1] - ref_sdr[-1]) < 0.15
+        print(f"enhance utt {utt}: vs 15 dB target: ref {s_ref:.3f} ours {s_new:.3f} dB (d {abs(s_new - s_ref):.4f}); "
+              f"SI-SDR(ours vs oracle) {agree:.1f} dB; vs clean (ill-conditioned) ref {O.si_sdr(c, ref):.2f} ours {O.si_sdr(c, got):.2f} dB")
+        assert abs(s_new - s_ref) < 0.05
         assert agree > 35.0
-    d = abs(sum(new_sdr) / len(new_sdr) - sum(ref_sdr) / len(ref_sdr))
-    print(f"enhance: |d mean SI-SDR| vs clean {d:.4f} dB over {len(new_sdr)} utterances")
-    assert d < 0.05
     # batched path = per-utterance path
     both = model.enhance_batch(torch.stack([noisy, noisy]).cuda())
     print(f"batched vs single {rel_l2(both[0], got):.2e}, within batch {rel_l2(both[0], both[1]):.2e}")
