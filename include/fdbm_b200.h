@@ -212,6 +212,22 @@ int fdbm_conv_igemm_gn(const void* in1, int C1, int ksize, const double* sums1, 
                        const float* beta, int silu, float* table, const void* wpack, const float* bias,
                        const float* residual, float scale, int batch, int T, int F, int Cout,
                        float* out_f32, void* out_h16, double* sums, void* stream);
+/* ---- training step: gradients of the convolutions -------------------------------------
+ * dgrad: dX = conv(dY, W') with W'[ci][co][df][dt] = W[co][ci][2-df][2-dt] -- pack W with
+ * fdbm_pack_conv_weights_dgrad (w fp32 OIHW [Cout,Cin,k,k]; ksize -1: NIN matrix [Cin][Cout]) and call
+ * fdbm_conv_igemm(in1 = dY, C1 = Cout, ksize, ..., Cout = Cin): the same tcgen05 kernel, epilogue included
+ * (`residual` = the gradient already accumulated for that tensor).  Replaces the autograd of nn.Conv2d / NIN
+ * (layers.py:100-124,546-555).  *bytes receives the packed size; wpack == NULL only queries it. */
+int fdbm_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, void* wpack, int64_t* bytes,
+                                 void* stream);
+/* wgrad: dw[n,c,df,dt] += scale * sum_{b,t,f} dY[b,t,f,n] * X[b,t+dt-1,f+df-1,c]   (fp32 OIHW, accumulated)
+ *   dy h16 [B,T,F,Cout] (Cout % 128 == 0), x h16 [B,T,F,Cin] (Cin % 64 == 0), ksize 3 or 1.
+ * tcgen05 kernel with MN-major operands (pixels are the GEMM K), split over pixels; the fp32 partials of the
+ * splits go through `workspace` (fdbm_conv_wgrad_workspace_bytes) and are summed in a fixed order. */
+int64_t fdbm_conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int batch, int T, int F);
+int fdbm_conv_wgrad(const void* dy, int Cout, const void* x, int Cin, int ksize, int batch, int T, int F,
+                    float scale, float* dw, float* workspace, void* stream);
+
 /* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
  * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]).  Returns bytes via *bytes when wpack==NULL. */
 int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,

@@ -1,5 +1,6 @@
 // Shared host/device helpers for libfdbm_b200: error reporting, launch checks, small math.
 #pragma once
+#include <cuda.h>
 #include <cuda_runtime.h>
 #include <cuda_bf16.h>
 #include <cuda_fp16.h>
@@ -125,6 +126,11 @@ struct ConvArgs {
   const float* comb_pyr = nullptr; const float* comb_w = nullptr; const float* comb_b = nullptr; int comb_C = 0;
 };
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s);
+int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s);
+int64_t conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int B, int T, int F);
+int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksize, int B, int T, int F, float scale,
+                      int io_layout, float* dw, float* workspace, cudaStream_t s);
+int make_act_tile_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C, int box_f, int box_t);
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);
 // ksize 3 / 1: OIHW; -1: NIN matrix [in][out]; -2: first conv, OIHW [Cout][C1<=4][3][3] as one im2col K-block of 64
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,

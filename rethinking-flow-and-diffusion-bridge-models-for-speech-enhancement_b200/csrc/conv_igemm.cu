@@ -26,6 +26,7 @@
 #include "tc05.cuh"
 
 namespace fdbm {
+int make_act_tile_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C, int box_f, int box_t);
 namespace {
 
 using namespace tc05;
@@ -573,6 +574,29 @@ pack_weights_kernel(const float* __restrict__ w1, int C1, int ksize, int io_layo
   }
 }
 
+// dgrad packing: the input gradient of a convolution is itself a convolution of dY with the weights transposed
+// (in <-> out) and flipped (tap (df,dt) -> (2-df,2-dt)):  W'[ci][co][df'][dt'] = W[co][ci][2-df'][2-dt'].
+// Output rows = Cin of the forward conv, K = Cout of the forward conv.
+__global__ void __launch_bounds__(256)
+pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ksize, int io_layout, op_t* __restrict__ out) {
+  const int taps = ksize * ksize;
+  const int64_t total = static_cast<int64_t>(Cout / 64) * taps * Cin * 64;
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
+    const int j = static_cast<int>(i % 64);
+    const int ci = static_cast<int>((i / 64) % Cin);
+    const int kt = static_cast<int>(i / (64ll * Cin));
+    const int kb = kt / taps, tap = kt % taps;
+    const int co = kb * 64 + j;
+    float v;
+    if (io_layout) v = w[static_cast<int64_t>(ci) * Cout + co];          // NIN [in][out]
+    else {
+      const int kf = ksize == 3 ? 2 - tap / 3 : 0, ktm = ksize == 3 ? 2 - tap % 3 : 0;
+      v = w[((static_cast<int64_t>(co) * Cin + ci) * ksize + kf) * ksize + ktm];
+    }
+    out[i] = f2op(v);
+  }
+}
+
 typedef CUresult (*EncodeFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                              const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                              CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
@@ -591,17 +615,7 @@ EncodeFn get_encode() {
 }
 
 int make_act_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C) {
-  EncodeFn enc = get_encode();
-  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FDBM_ECUDA; }
-  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
-  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * F, (cuuint64_t)C * 2 * F * T};
-  cuuint32_t box[4] = {64, HALO_F, HALO_T, 1};
-  cuuint32_t es[4] = {1, 1, 1, 1};
-  CUresult r = enc(map, (kOperandIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 4, const_cast<op_t*>(ptr), dims, strides, box, es,
-                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation [%d,%d,%d,%d]) failed: %d", B, T, F, C, (int)r); return FDBM_ECUDA; }
-  return FDBM_OK;
+  return make_act_tile_map(map, ptr, B, T, F, C, HALO_F, HALO_T);
 }
 
 int make_weight_map(CUtensorMap* map, const op_t* ptr, int64_t rows) {
@@ -620,6 +634,21 @@ int make_weight_map(CUtensorMap* map, const op_t* ptr, int64_t rows) {
 
 }  // namespace
 
+// TMA map of a 16-bit activation tensor [B,T,F,C] with a box of 64 channels x box_f bins x box_t frames, 128-byte swizzle
+int make_act_tile_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C, int box_f, int box_t) {
+  EncodeFn enc = get_encode();
+  if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FDBM_ECUDA; }
+  cuuint64_t dims[4] = {(cuuint64_t)C, (cuuint64_t)F, (cuuint64_t)T, (cuuint64_t)B};
+  cuuint64_t strides[3] = {(cuuint64_t)C * 2, (cuuint64_t)C * 2 * F, (cuuint64_t)C * 2 * F * T};
+  cuuint32_t box[4] = {64, (cuuint32_t)box_f, (cuuint32_t)box_t, 1};
+  cuuint32_t es[4] = {1, 1, 1, 1};
+  CUresult r = enc(map, (kOperandIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 4, const_cast<op_t*>(ptr), dims, strides, box, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("cuTensorMapEncodeTiled(activation [%d,%d,%d,%d]) failed: %d", B, T, F, C, (int)r); return FDBM_ECUDA; }
+  return FDBM_OK;
+}
+
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout) {
   return (static_cast<int64_t>(C1 / 64) * ksize * ksize + C2 / 64) * Cout * 64 * 2;
 }
@@ -635,6 +664,18 @@ int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2
                                 : (static_cast<int64_t>(C1 / 64) * k * k + C2 / 64) * Cout * 64;
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096));
   pack_weights_kernel<<<grid, 256, 0, s>>>(w1, C1, k, io, w2, C2, Cout, n_rows_total, row_offset, wpack);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+// packs W (OIHW [Cout,Cin,k,k], or NIN [Cin][Cout] when ksize == -1) for the dgrad convolution dX = conv(dY, W'):
+// use with launch_conv_igemm(seg = {dY, C = Cout, taps}, Cout' = Cin)
+int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s) {
+  FDBM_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1),
+               "pack_conv_weights_dgrad: channels must be multiples of 64, ksize 1, 3 or -1 (NIN)");
+  const int k = ksize == -1 ? 1 : ksize;
+  const int64_t total = static_cast<int64_t>(Cout / 64) * k * k * Cin * 64;
+  pack_weights_dgrad_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096)), 256, 0, s>>>(w, Cout, Cin, k, ksize == -1, wpack);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -706,6 +747,16 @@ extern "C" int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const 
   FDBM_REQUIRE(w1 && ((C2 == 0) == (w2 == nullptr)), "fdbm_pack_conv_weights: null pointer");
   return launch_pack_conv_weights(w1, C1, ksize, w2, C2, Cout, Cout, 0, reinterpret_cast<op_t*>(wpack),
                                   as_stream(stream));
+}
+
+extern "C" int fdbm_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, void* wpack, int64_t* bytes,
+                                            void* stream) {
+  const int k = ksize == -1 ? 1 : ksize;
+  if (bytes) *bytes = conv_wpack_bytes(Cout, k, 0, Cin);
+  if (!wpack) return FDBM_OK;
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(w, "fdbm_pack_conv_weights_dgrad: null weights");
+  return launch_pack_conv_weights_dgrad(w, Cout, Cin, ksize, reinterpret_cast<op_t*>(wpack), as_stream(stream));
 }
 
 extern "C" int fdbm_conv_igemm(const void* in1, int C1, int ksize, const void* in2, int C2, const void* wpack,

@@ -24,6 +24,7 @@ EXPORTS = [
     "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run", "fdbm_plan_profile_forward",
     "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm", "fdbm_conv_igemm_gn",
     "fdbm_pack_conv_weights", "fdbm_attention",
+    "fdbm_pack_conv_weights_dgrad", "fdbm_conv_wgrad_workspace_bytes", "fdbm_conv_wgrad",
 ]
 
 
@@ -75,6 +76,9 @@ def load() -> C.CDLL:
         "fdbm_conv_igemm": (i, [p, i, i, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
         "fdbm_conv_igemm_gn": (i, [p, i, i, p, p, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
         "fdbm_pack_conv_weights": (i, [p, i, i, p, i, i, p, C.POINTER(i64), p]),
+        "fdbm_pack_conv_weights_dgrad": (i, [p, i, i, i, p, C.POINTER(i64), p]),
+        "fdbm_conv_wgrad_workspace_bytes": (i64, [i, i, i, i, i, i]),
+        "fdbm_conv_wgrad": (i, [p, i, p, i, i, i, i, i, f, p, p, p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
     }
     for name, (res, args) in sig.items():

@@ -322,3 +322,61 @@ def test_attention(lib):
     qd, kd, vd = q.cuda(), k.cuda(), v.cuda()
     _check(lib, lib.fdbm_attention(qd.data_ptr(), kd.data_ptr(), vd.data_ptr(), B, L, Cc, o.data_ptr(), _stream()))
     assert rel_l2(o.float(), ref) < 5e-3
+
+
+# ------------------------------------------------------------------------------------------------
+# training step: convolution gradients vs torch autograd (fp64) on the same 16-bit operands
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("B,T,Fq,Cin,k,Cout", [
+    (1, 16, 8, 64, 3, 128),          # one pixel tile, one 64-channel box: the minimal MN-major case
+    (2, 16, 16, 128, 3, 128),        # ResnetBlock Conv_0 / Conv_1 class
+    (2, 20, 12, 256, 3, 128),        # ragged tiles (zero-filled halo and tile tails), two Cin blocks
+    (1, 32, 32, 128, 1, 256),        # 1x1 shortcut (Conv_2), two Cout blocks
+    (3, 64, 64, 128, 3, 128),        # many tiles per split
+])
+def test_conv_wgrad(lib, B, T, Fq, Cin, k, Cout):
+    g = torch.Generator().manual_seed(7 * B + T + Cin + k)
+    x = torch.randn(B, Cin, Fq, T, generator=g).to(_h16()).double()
+    dy = torch.randn(B, Cout, Fq, T, generator=g).to(_h16()).double()
+    w = torch.zeros(Cout, Cin, k, k, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w, None, padding=k // 2).backward(dy)
+    ref = w.grad.float()
+    xd = nchw_to_ntfc(x.float()).to(_h16()).cuda()
+    dyd = nchw_to_ntfc(dy.float()).to(_h16()).cuda()
+    ws = torch.empty(lib.fdbm_conv_wgrad_workspace_bytes(Cout, Cin, k, B, T, Fq) // 4, device="cuda")
+    dw = torch.full((Cout, Cin, k, k), 0.5, device="cuda")                 # accumulates: dw += scale * grad
+    _check(lib, lib.fdbm_conv_wgrad(dyd.data_ptr(), Cout, xd.data_ptr(), Cin, k, B, T, Fq, 2.0, dw.data_ptr(),
+                                    ws.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    got = (dw.cpu() - 0.5) / 2.0
+    err = rel_l2(got, ref)
+    assert err < 2e-5, f"wgrad differs from autograd: rel L2 {err}"
+
+
+@pytest.mark.parametrize("B,T,Fq,Cin,k,Cout", [
+    (2, 16, 16, 128, 3, 128),
+    (1, 20, 12, 256, 3, 128),        # ragged tiles; Cin (= dgrad output channels) in two N blocks
+    (1, 16, 16, 128, 1, 256),        # 1x1
+])
+def test_conv_dgrad(lib, B, T, Fq, Cin, k, Cout):
+    """dX = conv(dY, W transposed + flipped) through the forward tcgen05 kernel, accumulated onto an existing gradient."""
+    g = torch.Generator().manual_seed(11 * B + T + Cin + k)
+    w = (torch.randn(Cout, Cin, k, k, generator=g) / (Cin * k * k) ** 0.5).to(_h16()).double()
+    dy = torch.randn(B, Cout, Fq, T, generator=g).to(_h16()).double()
+    x = torch.zeros(B, Cin, Fq, T, dtype=torch.float64, requires_grad=True)
+    F.conv2d(x, w, None, padding=k // 2).backward(dy)
+    prev = torch.randn(B, Cin, Fq, T, generator=g)
+    ref = (x.grad + prev.double()).float()
+    nbytes = C.c_int64()
+    _check(lib, lib.fdbm_pack_conv_weights_dgrad(None, Cout, Cin, k, None, C.byref(nbytes), None))
+    wpack = torch.empty(nbytes.value // 2, dtype=_h16(), device="cuda")
+    wd = w.float().cuda()
+    _check(lib, lib.fdbm_pack_conv_weights_dgrad(wd.data_ptr(), Cout, Cin, k, wpack.data_ptr(), None, _stream()))
+    dyd = nchw_to_ntfc(dy.float()).to(_h16()).cuda()
+    acc = nchw_to_ntfc(prev).cuda().contiguous()
+    zero_bias = torch.zeros(Cin, device="cuda")
+    _check(lib, lib.fdbm_conv_igemm(dyd.data_ptr(), Cout, k, None, 0, wpack.data_ptr(), zero_bias.data_ptr(), None,
+                                    acc.data_ptr(), 1.0, B, T, Fq, Cin, acc.data_ptr(), None, None, _stream()))
+    torch.cuda.synchronize()
+    err = rel_l2(ntfc_to_nchw(acc).cpu(), ref)
+    assert err < 2e-5, f"dgrad differs from autograd: rel L2 {err}"
