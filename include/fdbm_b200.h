@@ -228,6 +228,26 @@ int64_t fdbm_conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int batch,
 int fdbm_conv_wgrad(const void* dy, int Cout, const void* x, int Cin, int ksize, int batch, int T, int F,
                     float scale, float* dw, float* workspace, void* stream);
 
+/* GroupNorm(32 groups, eps 1e-6) (+ SiLU) backward (autograd of layerspp.py:242-246): a = act(GroupNorm(x)).
+ *   g_a h16 [B,T,F,C] gradient w.r.t. a;  x the normalised tensor, fp32 or h16 (x_is_h16);  sums double [B,C,2] of x
+ *   table: scratch of 2*B*C + 2*B*32 floats;  S: scratch of 2*B*C doubles
+ *   outputs: g_x_acc fp32 [B,T,F,C] (+=, may be NULL), g_x_h16 (=, may be NULL), dgamma / dbeta fp32 [C] (+=, may be NULL) */
+int fdbm_groupnorm_act_bwd(const void* g_a, const void* x, int x_is_h16, const double* sums, const float* gamma,
+                           const float* beta, int silu, int batch, int T, int F, int C, float* table, double* S,
+                           float* g_x_acc, void* g_x_h16, float* dgamma, float* dbeta, void* stream);
+/* FIR x2 resampling of a h16 tensor with a scale: out = scale * upfirdn(in); mode 1 down, 2 up.  The adjoints of
+ * upsample_2d / downsample_2d (up_or_down_sampling.py:195-257) are adjoint(down) = up / 4, adjoint(up) = 4 * down. */
+int fdbm_fir_resample_h16(const void* in, int batch, int T, int F, int C, int mode, float scale, void* out, void* stream);
+/* Backward of the attention core (layerspp.py:82-86): qkv h16 [B,L,3C] as produced by the forward, d_o h16 [B,L,C]
+ * -> g_qkv h16 [B,L,3C].  scratch: 2*B*L*L floats. */
+int fdbm_attention_bwd(const void* qkv, int batch, int L, int C, const void* d_o, float* scratch, void* g_qkv, void* stream);
+/* Adam (model.py:101 configure_optimizers) with clip_grad_norm_ (gradient_clip_val) and the EMA update
+ * (model.py:129-132) on flat fp32 buffers.  grads carry a factor grad_div (loss scale x world size) that is divided
+ * out; a non-finite gradient norm skips the step.  scratch: one double. */
+int fdbm_adam_ema_step(float* params, const float* grads, float* m, float* v, float* ema, int64_t n, double* scratch,
+                       float grad_div, float clip_norm, float lr, float beta1, float beta2, float eps, int step,
+                       float ema_decay, void* stream);
+
 /* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
  * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]).  Returns bytes via *bytes when wpack==NULL. */
 int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,

@@ -130,6 +130,23 @@ int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize,
 int64_t conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int B, int T, int F);
 int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksize, int B, int T, int F, float scale,
                       int io_layout, float* dw, float* workspace, cudaStream_t s);
+// ---- training-step passes (train_kernels.cu)
+int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s);
+int launch_gn_bwd_reduce(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
+                         const float2* tab, const float2* stats, int act, int B, int64_t P, double* S, cudaStream_t s);
+int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
+                        const float2* tab, const float2* stats, const float* gamma, int act, int B, int64_t P, const double* S,
+                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s);
+int launch_gn_param_grad(const double* S, int B, int C, float inv_scale, float* dgamma, float* dbeta, cudaStream_t s);
+int launch_gn_stats(const double* sums1, int C1, const double* sums2, int C2, int B, int64_t pixels, float2* stats, cudaStream_t s);
+int launch_fir_resample16(const op_t* in, int in_ld, int in_coff, int B, int T, int F, int C, int mode, float scale,
+                          op_t* out16, float* acc_dst, cudaStream_t s);
+int launch_col_sums16(const op_t* in, int ld, int c_off, int B, int64_t P, int C, double* sums, cudaStream_t s);
+int launch_col_sums_to(const double* sums, int B, int C, float inv_scale, float* dst, float* per_b, int per_b_ld, cudaStream_t s);
+int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, float* scratch, op_t* g_qkv, cudaStream_t s);
+int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const unsigned char* trainable, int64_t n,
+                    double* sumsq_scratch, float grad_div, float clip, float lr, float beta1, float beta2, float eps, int step,
+                    float ema_decay, cudaStream_t s);
 int make_act_tile_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C, int box_f, int box_t);
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);
 // ksize 3 / 1: OIHW; -1: NIN matrix [in][out]; -2: first conv, OIHW [Cout][C1<=4][3][3] as one im2col K-block of 64

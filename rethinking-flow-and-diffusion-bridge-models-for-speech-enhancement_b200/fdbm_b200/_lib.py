@@ -25,6 +25,7 @@ EXPORTS = [
     "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm", "fdbm_conv_igemm_gn",
     "fdbm_pack_conv_weights", "fdbm_attention",
     "fdbm_pack_conv_weights_dgrad", "fdbm_conv_wgrad_workspace_bytes", "fdbm_conv_wgrad",
+    "fdbm_groupnorm_act_bwd", "fdbm_fir_resample_h16", "fdbm_attention_bwd", "fdbm_adam_ema_step",
 ]
 
 
@@ -79,6 +80,10 @@ def load() -> C.CDLL:
         "fdbm_pack_conv_weights_dgrad": (i, [p, i, i, i, p, C.POINTER(i64), p]),
         "fdbm_conv_wgrad_workspace_bytes": (i64, [i, i, i, i, i, i]),
         "fdbm_conv_wgrad": (i, [p, i, p, i, i, i, i, i, f, p, p, p]),
+        "fdbm_groupnorm_act_bwd": (i, [p, p, i, p, p, p, i, i, i, i, i, p, p, p, p, p, p, p]),
+        "fdbm_fir_resample_h16": (i, [p, i, i, i, i, i, f, p, p]),
+        "fdbm_attention_bwd": (i, [p, i, i, i, p, p, p, p]),
+        "fdbm_adam_ema_step": (i, [p, p, p, p, p, i64, p, f, f, f, f, f, f, i, f, p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
     }
     for name, (res, args) in sig.items():

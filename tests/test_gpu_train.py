@@ -1,0 +1,133 @@
+"""Training-step kernels against torch autograd in fp64 on the same 16-bit operands."""
+import ctypes as C
+
+import pytest
+import torch
+import torch.nn.functional as F
+
+from helpers import rel_l2, nchw_to_ntfc, ntfc_to_nchw
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def lib():
+    from fdbm_b200 import _lib
+    return _lib.load()
+
+
+def _h16():
+    from fdbm_b200 import _lib
+    return _lib.operand_dtype()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _check(lib, rc):
+    assert rc == 0, lib.fdbm_last_error().decode()
+
+
+@pytest.mark.parametrize("B,T,Fq,Cc,silu,x16", [
+    (2, 16, 16, 128, 1, 0),      # GroupNorm_0 + SiLU on the fp32 residual stream
+    (2, 20, 12, 256, 1, 1),      # GroupNorm_1 + SiLU on the 16-bit Conv_0 output
+    (1, 16, 16, 256, 0, 0),      # attention GroupNorm (no activation)
+])
+def test_groupnorm_act_bwd(lib, B, T, Fq, Cc, silu, x16):
+    g = torch.Generator().manual_seed(B + T + Cc + silu)
+    x = (torch.randn(B, Cc, Fq, T, generator=g) * 1.5 + 0.3)
+    if x16:
+        x = x.to(_h16()).float()
+    ga = torch.randn(B, Cc, Fq, T, generator=g).to(_h16()).float()
+    gamma = 1 + 0.1 * torch.randn(Cc, generator=g)
+    beta = 0.1 * torch.randn(Cc, generator=g)
+    xr = x.double().requires_grad_(True); gr = gamma.double().requires_grad_(True); br = beta.double().requires_grad_(True)
+    a = F.group_norm(xr, 32, gr, br, eps=1e-6)
+    if silu:
+        a = F.silu(a)
+    a.backward(ga.double())
+    xs = nchw_to_ntfc(x)
+    xd = (xs.to(_h16()) if x16 else xs).cuda().contiguous()
+    gad = nchw_to_ntfc(ga).to(_h16()).cuda().contiguous()
+    sums = torch.stack([x.double().sum((2, 3)), x.double().pow(2).sum((2, 3))], -1).cuda()
+    gd, bd = gamma.cuda(), beta.cuda()
+    table = torch.empty(2 * B * Cc + 2 * B * 32, device="cuda")
+    S = torch.empty(2 * B * Cc, dtype=torch.float64, device="cuda")
+    prev = torch.randn(B, T, Fq, Cc, generator=g)
+    acc = prev.cuda().contiguous()
+    out16 = torch.empty(B, T, Fq, Cc, dtype=_h16(), device="cuda")
+    dg = torch.zeros(Cc, device="cuda"); db = torch.zeros(Cc, device="cuda")
+    _check(lib, lib.fdbm_groupnorm_act_bwd(gad.data_ptr(), xd.data_ptr(), x16, sums.data_ptr(), gd.data_ptr(), bd.data_ptr(), silu,
+                                           B, T, Fq, Cc, table.data_ptr(), S.data_ptr(), acc.data_ptr(), out16.data_ptr(),
+                                           dg.data_ptr(), db.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    gx = (acc.cpu() - prev)
+    assert rel_l2(ntfc_to_nchw(gx), xr.grad.float()) < 2e-5
+    assert rel_l2(ntfc_to_nchw(out16.float()), xr.grad.float()) < 1e-3
+    assert rel_l2(dg, gr.grad.float()) < 1e-4
+    assert rel_l2(db, br.grad.float()) < 1e-4
+
+
+@pytest.mark.parametrize("mode", [1, 2])
+def test_fir_resample_h16_is_the_adjoint(lib, mode):
+    """<FIR(x), y> == <x, FIR_adjoint(y)> with adjoint(down) = up / 4 and adjoint(up) = 4 * down."""
+    import sys, os
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import fdbm_oracle as O
+    g = torch.Generator().manual_seed(mode)
+    B, Cc, Fq, T = 2, 64, 16, 24
+    x = torch.randn(B, Cc, Fq, T, generator=g).to(_h16()).double().requires_grad_(True)
+    y = (O.fir_down2(x) if mode == 1 else O.fir_up2(x))
+    gy = torch.randn(y.shape, generator=g).to(_h16()).double()
+    y.backward(gy)
+    gyd = nchw_to_ntfc(gy.float()).to(_h16()).cuda().contiguous()
+    To, Fo = gy.shape[3], gy.shape[2]
+    out = torch.empty(B, T, Fq, Cc, dtype=_h16(), device="cuda")
+    adj_mode, scale = (2, 0.25) if mode == 1 else (1, 4.0)
+    _check(lib, lib.fdbm_fir_resample_h16(gyd.data_ptr(), B, To, Fo, Cc, adj_mode, scale, out.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    assert rel_l2(ntfc_to_nchw(out.float()), x.grad.float()) < 1e-3
+
+
+def test_attention_bwd(lib):
+    g = torch.Generator().manual_seed(5)
+    B, L, Cc = 2, 96, 256
+    qkv = torch.randn(B, L, 3 * Cc, generator=g).to(_h16())
+    do = torch.randn(B, L, Cc, generator=g).to(_h16())
+    t = qkv.double().requires_grad_(True)
+    q, k, v = t[..., :Cc], t[..., Cc:2 * Cc], t[..., 2 * Cc:]
+    w = torch.softmax(torch.einsum("bqc,bkc->bqk", q, k) * Cc ** -0.5, dim=-1)
+    torch.einsum("bqk,bkc->bqc", w, v).backward(do.double())
+    qd, dod = qkv.cuda(), do.cuda()
+    scratch = torch.empty(2 * B * L * L, device="cuda")
+    gq = torch.empty(B, L, 3 * Cc, dtype=_h16(), device="cuda")
+    _check(lib, lib.fdbm_attention_bwd(qd.data_ptr(), B, L, Cc, dod.data_ptr(), scratch.data_ptr(), gq.data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    for i, name in enumerate("qkv"):
+        err = rel_l2(gq[..., i * Cc:(i + 1) * Cc].float(), t.grad[..., i * Cc:(i + 1) * Cc].float())
+        assert err < 2e-3, f"d{name}: {err}"
+
+
+def test_adam_ema_step_matches_torch(lib):
+    g = torch.Generator().manual_seed(9)
+    n = 100003
+    p0 = torch.randn(n, generator=g)
+    grads = [torch.randn(n, generator=g) * s for s in (0.01, 10.0, 0.1)]       # the second one triggers clipping
+    ref = torch.nn.Parameter(p0.clone().double())
+    opt = torch.optim.Adam([ref], lr=1e-3)
+    ema_ref = p0.clone().double()
+    p = p0.clone().cuda(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda"); ema = p0.clone().cuda()
+    scratch = torch.zeros(1, dtype=torch.float64, device="cuda")
+    scale = 64.0
+    for step, gr in enumerate(grads, 1):
+        ref.grad = gr.double().clone()
+        torch.nn.utils.clip_grad_norm_([ref], 3.0)
+        opt.step()
+        ema_ref = 0.999 * ema_ref + 0.001 * ref.detach()
+        gd = (gr * scale).cuda()
+        _check(lib, lib.fdbm_adam_ema_step(p.data_ptr(), gd.data_ptr(), m.data_ptr(), v.data_ptr(), ema.data_ptr(), n,
+                                           scratch.data_ptr(), scale, 3.0, 1e-3, 0.9, 0.999, 1e-8, step, 0.999, _stream()))
+    torch.cuda.synchronize()
+    assert rel_l2(p, ref.detach().float()) < 1e-6
+    assert rel_l2(ema, ema_ref.float()) < 1e-6
