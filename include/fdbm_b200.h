@@ -154,6 +154,24 @@ int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float* y, const f
 int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
                      int n_steps, int kind, const float* noise, uint64_t seed, void* stream);
 
+/* ---- training step (model.py:258-275 `_step`, configure_optimizers :101, EMA :129-132) ----
+ * A TRAINING plan keeps every forward tensor (nothing in its arena is reused) and records the backward launch list:
+ * per residual block  grad_prepare -> [1x1 dgrad/wgrad of the shortcut] -> GroupNorm_1 recompute -> Conv_1 wgrad, dgrad
+ * -> GroupNorm_1 backward -> Conv_0 wgrad, dgrad -> [FIR adjoint] -> GroupNorm_0 backward, plus attention, progressive
+ * input/output, Combine and time-embedding backward.  fdbm_ncsnpp_forward on such a plan is the training forward.
+ *   fdbm_ncsnpp_backward: g_out = loss_scale * dL/dD, cplx [B,1,257,T] (activation gradients are h16 operands, hence the
+ *   scale); parameter gradients land UN-scaled in the flat fp32 buffer (accumulate != 0 adds to it).
+ *   fdbm_plan_buffers: the flat fp32 parameter / gradient / EMA buffers (same layout; fdbm_plan_param_info gives the
+ *   element offset of a tensor by its reference name) -- the caller all-reduces `grads` across ranks (DDP).
+ *   fdbm_plan_optimizer_step: Adam + clip_grad_norm_ + EMA on the flat buffers, then re-packs the 16-bit weights. */
+int fdbm_plan_create_train(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out);
+int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float loss_scale, int accumulate, void* stream);
+int fdbm_plan_param_info(const fdbm_plan* plan, const char* name, int64_t* offset, int64_t* numel);
+int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads, float** ema, int64_t* numel);
+int fdbm_plan_num_backward_launches(const fdbm_plan* plan);
+int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, float lr, float beta1, float beta2,
+                             float eps, int step, float ema_decay, void* stream);
+
 /* Measurement aid for bench.py: run one forward launch by launch with a CUDA event pair around every
  * kernel.  ms[i] = device time, kinds[i] = FDBM_OP_*, flops[i] = algorithmic FLOPs (2*MAC, convolutions
  * only) of launch i.  Returns the number of launches (<= max_ops) or a negative error.  Synchronises. */

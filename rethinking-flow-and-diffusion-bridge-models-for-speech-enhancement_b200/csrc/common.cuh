@@ -82,6 +82,7 @@ __device__ __forceinline__ uint32_t pack_op2(float a, float b) {
 // The C ABI in api.cu validates and forwards; the backbone plan calls these directly.
 // --------------------------------------------------------------------------------------------
 int launch_fir_resample(const float* in, int B, int T, int F, int C, int mode, float* out, cudaStream_t s);
+int launch_fir_resample_scaled(const float* in, int B, int T, int F, int C, int mode, float scale, float* out, cudaStream_t s);
 int launch_channel_stats(const float* in, int B, int T, int F, int C, double* sums, cudaStream_t s);
 int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, int C1, const float* src2,
                          const double* sums2, int C2, const float* gamma, const float* beta, int B, int T, int F,
@@ -126,7 +127,8 @@ struct ConvArgs {
   const float* comb_pyr = nullptr; const float* comb_w = nullptr; const float* comb_b = nullptr; int comb_C = 0;
 };
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s);
-int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s);
+int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s, int Cin_total = 0,
+                                   int ci_off = 0);
 int64_t conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int B, int T, int F);
 int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksize, int B, int T, int F, float scale,
                       int io_layout, float* dw, float* workspace, cudaStream_t s);
@@ -147,6 +149,23 @@ int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, 
 int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const unsigned char* trainable, int64_t n,
                     double* sumsq_scratch, float grad_div, float clip, float lr, float beta1, float beta2, float eps, int step,
                     float ema_decay, cudaStream_t s);
+struct WgradCall {
+  const op_t* dy = nullptr; int dy_ld = 0, dy_coff = 0, Cout = 0;
+  const op_t* x = nullptr; int x_ld = 0, x_coff = 0, Cin = 0;
+  int ksize = 3, B = 0, T = 0, F = 0;
+  float scale = 1.0f;
+  int layout = 0, Cin_total = 0, ci_off = 0, aux = 0;
+  float* dw = nullptr; float* workspace = nullptr;
+};
+int launch_conv_wgrad_ex(const WgradCall& c, cudaStream_t s);
+int launch_output_layer_bwd(const float* g_out, const float* pyr, int Cp, const float* w, int B, int T, int F, int F_out, float inv,
+                            float* g_pyr, float* dw, float* db, cudaStream_t s);
+int launch_small_col_sums(const float* g, int64_t n_px, int Cp, float inv, float* db, cudaStream_t s);
+int launch_combine_bwd(const float* g, const float* pyr, int Cp, int64_t n_px, int C, float inv, float* dw, float* db, cudaStream_t s);
+int launch_pack_pyr_dgrad(const float* w, int C, int Cp, op_t* out, cudaStream_t s);
+int launch_dense_temb_bwd(const float* d, const float* act, const float* w, int B, int K, int rows, float* dw, float* db, float* g_act,
+                          const float* t, const float* fw, int nf, const float* w1, const float* b1, const float* w2, const float* b2,
+                          int t_stride, float* dw1, float* db1, float* dw2, float* db2, cudaStream_t s);
 int make_act_tile_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C, int box_f, int box_t);
 int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);
 // ksize 3 / 1: OIHW; -1: NIN matrix [in][out]; -2: first conv, OIHW [Cout][C1<=4][3][3] as one im2col K-block of 64

@@ -578,7 +578,8 @@ pack_weights_kernel(const float* __restrict__ w1, int C1, int ksize, int io_layo
 // (in <-> out) and flipped (tap (df,dt) -> (2-df,2-dt)):  W'[ci][co][df'][dt'] = W[co][ci][2-df'][2-dt'].
 // Output rows = Cin of the forward conv, K = Cout of the forward conv.
 __global__ void __launch_bounds__(256)
-pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ksize, int io_layout, op_t* __restrict__ out) {
+pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ksize, int io_layout, int Cin_total, int ci_off,
+                          op_t* __restrict__ out) {
   const int taps = ksize * ksize;
   const int64_t total = static_cast<int64_t>(Cout / 64) * taps * Cin * 64;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -588,10 +589,10 @@ pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ks
     const int kb = kt / taps, tap = kt % taps;
     const int co = kb * 64 + j;
     float v;
-    if (io_layout) v = w[static_cast<int64_t>(ci) * Cout + co];          // NIN [in][out]
+    if (io_layout) v = w[static_cast<int64_t>(ci_off + ci) * Cout + co];          // NIN [in][out]
     else {
       const int kf = ksize == 3 ? 2 - tap / 3 : 0, ktm = ksize == 3 ? 2 - tap % 3 : 0;
-      v = w[((static_cast<int64_t>(co) * Cin + ci) * ksize + kf) * ksize + ktm];
+      v = w[((static_cast<int64_t>(co) * Cin_total + ci_off + ci) * ksize + kf) * ksize + ktm];
     }
     out[i] = f2op(v);
   }
@@ -670,12 +671,13 @@ int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2
 
 // packs W (OIHW [Cout,Cin,k,k], or NIN [Cin][Cout] when ksize == -1) for the dgrad convolution dX = conv(dY, W'):
 // use with launch_conv_igemm(seg = {dY, C = Cout, taps}, Cout' = Cin)
-int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s) {
+// (Cin_total, ci_off): W has Cin_total input channels and only the slice ci_off.. +Cin is packed (concatenated inputs)
+int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s, int Cin_total, int ci_off) {
   FDBM_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1),
                "pack_conv_weights_dgrad: channels must be multiples of 64, ksize 1, 3 or -1 (NIN)");
   const int k = ksize == -1 ? 1 : ksize;
   const int64_t total = static_cast<int64_t>(Cout / 64) * k * k * Cin * 64;
-  pack_weights_dgrad_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096)), 256, 0, s>>>(w, Cout, Cin, k, ksize == -1, wpack);
+  pack_weights_dgrad_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096)), 256, 0, s>>>(w, Cout, Cin, k, ksize == -1, Cin_total ? Cin_total : Cin, ci_off, wpack);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

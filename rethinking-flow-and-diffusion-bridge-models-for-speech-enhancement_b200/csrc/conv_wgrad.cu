@@ -40,6 +40,7 @@ struct WgradParams {
   int n_cin;                   // channels of the Cin block handled per CTA: 128 or 64
   int tiles_t, tiles_f, n_tiles, n_splits, tiles_per_split;
   int cin_blocks;
+  int dy_coff, x_coff;         // channel offsets inside the (wider) dY / X tensors
   float* partial;              // [split][tap][Cout][Cin]
 };
 
@@ -100,10 +101,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
         mbar_wait(empty + stage, phase ^ 1);
         mbar_expect_tx(full + stage, 2 * DY_BOX_BYTES + n_x_boxes * X_BOX_BYTES);
         uint8_t* s = smem + stage * STAGE_BYTES;
-        tma_load_4d(s, &map_dy, full + stage, co_blk * 128, f0, t0, b);
-        tma_load_4d(s + DY_BOX_BYTES, &map_dy, full + stage, co_blk * 128 + 64, f0, t0, b);
+        tma_load_4d(s, &map_dy, full + stage, p.dy_coff + co_blk * 128, f0, t0, b);
+        tma_load_4d(s + DY_BOX_BYTES, &map_dy, full + stage, p.dy_coff + co_blk * 128 + 64, f0, t0, b);
         for (int h = 0; h < n_x_boxes; ++h)
-          tma_load_4d(s + 2 * DY_BOX_BYTES + h * X_BOX_STRIDE, &map_x, full + stage, ci_blk * p.n_cin + h * 64, f0 - 1, t0 - 1, b);
+          tma_load_4d(s + 2 * DY_BOX_BYTES + h * X_BOX_STRIDE, &map_x, full + stage, p.x_coff + ci_blk * p.n_cin + h * 64, f0 - 1, t0 - 1, b);
         if (++stage == STAGES) { stage = 0; phase ^= 1; }
       }
     }
@@ -166,10 +167,14 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   if (warp == 1) tmem_dealloc(tmem_base, 512);
 }
 
-// dW[co][ci][tap] (OIHW; tap = df*3 + dt, or [co][ci] for 1x1 / NIN transposed on request) += scale * sum_split partial
+// dW += scale * sum over splits of the partials [split][tap][Cout][Cin], written in the layout the parameter has:
+//   0: OIHW [Cout][Cin_total][k][k], this call covering input channels ci_off..  (tap = df*3 + dt)
+//   1: NIN matrix [Cin_total][Cout]
+//   2: first conv: D[co][k], k = tap*aux + ci (im2col K-block)  -> OIHW [Cout][aux][3][3]
+//   3: pyramid conv: D[c][k], k = tap'*aux + o, tap = 8 - tap'   -> OIHW [aux][Cout][3][3]   (see train_small.cu)
 __global__ void __launch_bounds__(256)
-wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int taps, int Cout, int Cin, float scale, int io_layout,
-                    float* __restrict__ dw) {
+wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int taps, int Cout, int Cin, float scale, int layout,
+                    int Cin_total, int ci_off, int aux, float* __restrict__ dw) {
   const int64_t n = static_cast<int64_t>(taps) * Cout * Cin;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
     float acc = 0.f;
@@ -177,7 +182,11 @@ wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int taps, i
     const int ci = static_cast<int>(i % Cin);
     const int co = static_cast<int>((i / Cin) % Cout);
     const int tap = static_cast<int>(i / (static_cast<int64_t>(Cin) * Cout));
-    const int64_t o = io_layout ? static_cast<int64_t>(ci) * Cout + co : (static_cast<int64_t>(co) * Cin + ci) * taps + tap;
+    int64_t o;
+    if (layout == 0) o = (static_cast<int64_t>(co) * Cin_total + ci_off + ci) * taps + tap;
+    else if (layout == 1) o = static_cast<int64_t>(ci_off + ci) * Cout + co;
+    else if (layout == 2) { if (ci >= 9 * aux) continue; o = (static_cast<int64_t>(co) * aux + ci % aux) * 9 + ci / aux; }
+    else { if (ci >= 9 * aux) continue; o = (static_cast<int64_t>(ci % aux) * Cout + co) * 9 + (8 - ci / aux); }
     dw[o] += scale * acc;
   }
 }
@@ -197,40 +206,49 @@ int64_t conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int B, int T, i
   return static_cast<int64_t>(splits) * taps * Cout * Cin * 4;
 }
 
-// dw += scale * wgrad(dy, x).  dy h16 [B,T,F,Cout], x h16 [B,T,F,Cin], dw fp32 OIHW [Cout,Cin,k,k]
-// (io_layout != 0: NIN matrix [Cin][Cout], ksize 1).  workspace: conv_wgrad_workspace_bytes().
-int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksize, int B, int T, int F, float scale,
-                      int io_layout, float* dw, float* workspace, cudaStream_t s) {
-  FDBM_REQUIRE(Cout % 128 == 0 && Cin % 64 == 0, "conv_wgrad: Cout %% 128 and Cin %% 64 required (got %d, %d)", Cout, Cin);
-  FDBM_REQUIRE(ksize == 1 || ksize == 3, "conv_wgrad: ksize must be 1 or 3");
-  FDBM_REQUIRE(!io_layout || ksize == 1, "conv_wgrad: the [in][out] layout is for 1x1 only");
+// dw += scale * wgrad(dy, x).  dy h16 [B,T,F,dy_ld] (channels dy_coff.. +Cout), x h16 [B,T,F,x_ld] (channels x_coff.. +Cin),
+// dw in `layout` (see wgrad_reduce_kernel).  workspace: conv_wgrad_workspace_bytes().
+int launch_conv_wgrad_ex(const WgradCall& c, cudaStream_t s) {
+  FDBM_REQUIRE(c.Cout % 128 == 0 && c.Cin % 64 == 0, "conv_wgrad: Cout %% 128 and Cin %% 64 required (got %d, %d)", c.Cout, c.Cin);
+  FDBM_REQUIRE(c.ksize == 1 || c.ksize == 3, "conv_wgrad: ksize must be 1 or 3");
+  FDBM_REQUIRE(c.layout == 0 || c.ksize == 1, "conv_wgrad: layouts 1..3 are for 1x1 only");
+  FDBM_REQUIRE(c.dy_coff % 64 == 0 && c.x_coff % 64 == 0, "conv_wgrad: channel offsets must be multiples of 64");
   static bool attr_set = false;
   if (!attr_set) {
     FDBM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   WgradParams p;
-  p.B = B; p.T = T; p.F = F; p.Cout = Cout; p.Cin = Cin; p.taps = ksize * ksize;
-  p.n_cin = Cin % 128 == 0 ? 128 : 64;
-  p.cin_blocks = Cin / p.n_cin;
-  p.tiles_t = ceil_div(T, TILE_T); p.tiles_f = ceil_div(F, TILE_F);
-  p.n_tiles = B * p.tiles_t * p.tiles_f;
+  p.B = c.B; p.T = c.T; p.F = c.F; p.Cout = c.Cout; p.Cin = c.Cin; p.taps = c.ksize * c.ksize;
+  p.n_cin = c.Cin % 128 == 0 ? 128 : 64;
+  p.cin_blocks = c.Cin / p.n_cin;
+  p.tiles_t = ceil_div(c.T, TILE_T); p.tiles_f = ceil_div(c.F, TILE_F);
+  p.n_tiles = c.B * p.tiles_t * p.tiles_f;
   const int groups = p.taps == 9 ? 3 : 1;
-  const int blocks = (Cout / 128) * p.cin_blocks;
+  const int blocks = (c.Cout / 128) * p.cin_blocks;
   p.n_splits = pick_splits(p.n_tiles, groups, blocks);
   p.tiles_per_split = ceil_div(p.n_tiles, p.n_splits);
-  p.partial = workspace;
+  p.dy_coff = c.dy_coff; p.x_coff = c.x_coff;
+  p.partial = c.workspace;
   CUtensorMap map_dy, map_x;
-  if (int rc = make_act_tile_map(&map_dy, dy, B, T, F, Cout, TILE_F, TILE_T)) return rc;
-  if (int rc = make_act_tile_map(&map_x, x, B, T, F, Cin, HALO_F, HALO_T)) return rc;
+  if (int rc = make_act_tile_map(&map_dy, c.dy, c.B, c.T, c.F, c.dy_ld, TILE_F, TILE_T)) return rc;
+  if (int rc = make_act_tile_map(&map_x, c.x, c.B, c.T, c.F, c.x_ld, HALO_F, HALO_T)) return rc;
   dim3 grid(p.n_splits, groups, blocks);
   conv_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_dy, map_x, p);
   FDBM_LAUNCH_CHECK();
-  const int64_t n = static_cast<int64_t>(p.taps) * Cout * Cin;
-  wgrad_reduce_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 2048)), 256, 0, s>>>(workspace, p.n_splits, p.taps, Cout, Cin,
-                                                                                                   scale, io_layout, dw);
+  const int64_t n = static_cast<int64_t>(p.taps) * c.Cout * c.Cin;
+  wgrad_reduce_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 2048)), 256, 0, s>>>(
+      c.workspace, p.n_splits, p.taps, c.Cout, c.Cin, c.scale, c.layout, c.Cin_total ? c.Cin_total : c.Cin, c.ci_off, c.aux, c.dw);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
+}
+
+int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksize, int B, int T, int F, float scale,
+                      int io_layout, float* dw, float* workspace, cudaStream_t s) {
+  WgradCall c;
+  c.dy = dy; c.dy_ld = Cout; c.Cout = Cout; c.x = x; c.x_ld = Cin; c.Cin = Cin; c.ksize = ksize; c.B = B; c.T = T; c.F = F;
+  c.scale = scale; c.layout = io_layout ? 1 : 0; c.dw = dw; c.workspace = workspace;
+  return launch_conv_wgrad_ex(c, s);
 }
 
 }  // namespace fdbm

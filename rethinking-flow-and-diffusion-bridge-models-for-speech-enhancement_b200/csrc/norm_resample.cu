@@ -42,7 +42,7 @@ __device__ __forceinline__ Taps1D taps_for(int o, int mode) {
 __host__ __device__ inline int out_dim(int n, int mode) { return mode == 1 ? n / 2 : (mode == 2 ? n * 2 : n); }
 
 __global__ void __launch_bounds__(256)
-fir_resample_kernel(const float* __restrict__ in, int B, int T, int F, int C, int mode, float* __restrict__ out) {
+fir_resample_kernel(const float* __restrict__ in, int B, int T, int F, int C, int mode, float scale, float* __restrict__ out) {
   const int To = out_dim(T, mode), Fo = out_dim(F, mode);
   const int64_t total = static_cast<int64_t>(B) * To * Fo * C;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
@@ -60,7 +60,7 @@ fir_resample_kernel(const float* __restrict__ in, int B, int T, int F, int C, in
         acc += tt.w[a] * tf.w[q] * in[((static_cast<int64_t>(b) * T + tt.pos[a]) * F + tf.pos[q]) * C + c];
       }
     }
-    out[i] = acc;
+    out[i] = acc * scale;
   }
 }
 
@@ -256,9 +256,13 @@ int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2,
 }
 
 int launch_fir_resample(const float* in, int B, int T, int F, int C, int mode, float* out, cudaStream_t s) {
+  return launch_fir_resample_scaled(in, B, T, F, C, mode, 1.0f, out, s);
+}
+
+int launch_fir_resample_scaled(const float* in, int B, int T, int F, int C, int mode, float scale, float* out, cudaStream_t s) {
   const int64_t total = static_cast<int64_t>(B) * out_dim(T, mode) * out_dim(F, mode) * C;
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(num_sms()) * 16));
-  fir_resample_kernel<<<grid, 256, 0, s>>>(in, B, T, F, C, mode, out);
+  fir_resample_kernel<<<grid, 256, 0, s>>>(in, B, T, F, C, mode, scale, out);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

@@ -29,6 +29,7 @@ struct Act {                 // one residual-stream tensor [B,T,F,C]: fp32 maste
   float* data = nullptr;
   op_t* h16 = nullptr;
   double* sums = nullptr;
+  float* grad = nullptr;      // training plans: fp32 gradient accumulator (loss-scaled), zeroed at the start of backward
   int C = 0, T = 0, F = 0;
 };
 
@@ -108,6 +109,19 @@ struct fdbm_plan {
   std::vector<double> op_flops;                              // algorithmic FLOPs (2*MAC) of every entry (convs)
   std::vector<std::function<int(cudaStream_t)>> pack_ops;   // weight packing after load_weights
   int n_launches = 0;
+  // training (fdbm_plan_create_train): nothing in the arena is reused, every forward tensor stays live for backward
+  bool train = false;
+  float* grads = nullptr;              // flat fp32 parameter gradients, same layout as `params`
+  op_t* wpacked_d = nullptr;           // dgrad packs (weights transposed + flipped)
+  int64_t wpacked_d_bytes = 0;
+  float* wgrad_ws = nullptr;           // split partials of the wgrad kernel
+  int64_t wgrad_ws_bytes = 0;
+  std::vector<std::function<int(cudaStream_t)>> bwd_ops;
+  std::vector<std::pair<void*, size_t>> zero_list;      // activation-gradient buffers cleared when backward starts
+  const float* cur_gout = nullptr;     // dL/dD of the current backward call (loss-scaled), cplx [B,1,257,T]
+  float cur_inv = 1.0f;                // 1 / loss scale
+  float* adam_m = nullptr; float* adam_v = nullptr; float* ema = nullptr; double* opt_scratch = nullptr;
+  int n_bwd_launches = 0;
   // graph cache
   bool have_graph = false; GraphKey graph_key{}; cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t capture_stream = nullptr;   // private stream: capture works even when the caller is on the legacy stream
@@ -167,6 +181,80 @@ struct Builder {
   int dense_off = 0;                   // running row offset into the Dense_0 table
   bool dry = true;                     // first pass: sizes only
 
+  // ---------------- training: backward ops are recorded per forward composite ("group") and replayed in reverse
+  typedef std::function<int(cudaStream_t)> Op;
+  std::vector<std::vector<Op>> groups;
+  int64_t wd_off = 0;                  // running offset (bytes) into wpacked_d
+  int64_t ws_need = 0;                 // largest wgrad workspace
+  op_t *T1 = nullptr, *T2 = nullptr, *T3 = nullptr, *T4 = nullptr, *T5 = nullptr;     // shared backward scratch (16-bit)
+  double *Sbuf = nullptr, *sumsA = nullptr;
+  float *att_scratch = nullptr, *d_dense = nullptr, *g_temb = nullptr;
+  const float* zero_bias = nullptr;
+  bool train() const { return P->train; }
+  void bgroup() { if (train()) groups.emplace_back(); }
+  void bop(Op f) { if (train() && !dry) groups.back().push_back(std::move(f)); }
+  float* gp(int64_t off) const { return P->grads + off; }
+  float* galloc(int64_t n) {
+    float* g = alloc<float>(n);
+    if (!dry) P->zero_list.emplace_back(g, static_cast<size_t>(n) * sizeof(float));
+    return g;
+  }
+  op_t* pack_d(int64_t w_off, int Cout, int Cin, int ksize, int Cin_total = 0, int ci_off = 0, op_t* into = nullptr) {
+    const int k = ksize == -1 ? 1 : ksize;
+    op_t* dst = into;
+    if (!dst) {
+      dst = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked_d) + wd_off);
+      wd_off += (conv_wpack_bytes(Cout, k, 0, Cin) + 1023) / 1024 * 1024;
+    }
+    const float* w = pp(w_off);
+    pack_op([=](cudaStream_t s) { return launch_pack_conv_weights_dgrad(w, Cout, Cin, ksize, dst, s, Cin_total, ci_off); });
+    return dst;
+  }
+  // dX (+)= conv(dY, W'): 16-bit output and/or fp32 in-place accumulation
+  void dgrad_op(const op_t* dy, int Cdy, int taps, const op_t* wd, int Cdx, int T, int F, op_t* out16, float* acc) {
+    ConvArgs c;
+    c.seg[0] = seg(dy, Cdy, taps); c.n_seg = 1;
+    c.wpack = wd; c.bias = zero_bias; c.residual = acc; c.scale = 1.0f;
+    c.B = P->B; c.T = T; c.F = F; c.Cout = Cdx; c.out_f32 = acc; c.out_h16 = out16;
+    bop([=](cudaStream_t s) { return launch_conv_igemm(c, s); });
+  }
+  void wgrad_op(WgradCall c, int64_t dw_off) {
+    c.B = P->B;
+    ws_need = std::max(ws_need, conv_wgrad_workspace_bytes(c.Cout, c.Cin, c.ksize, c.B, c.T, c.F));
+    fdbm_plan* plp = P;
+    bop([=](cudaStream_t s) {
+      WgradCall cc = c;
+      cc.scale = plp->cur_inv; cc.dw = plp->grads + dw_off; cc.workspace = plp->wgrad_ws;
+      return launch_conv_wgrad_ex(cc, s);
+    });
+  }
+  // GroupNorm(+SiLU) backward of one normalised (possibly concatenated) tensor: g_a [B,P,Ctot] 16-bit -> x.grad +=
+  void gn_bwd(const op_t* g_a, const Act& x1, const Act* x2, const float2* tab, const float2* stats, int64_t gw_off,
+              int64_t gb_off, int act) {
+    const int B = P->B, C1 = x1.C, C2 = x2 ? x2->C : 0, Ct = C1 + C2;
+    const int64_t px = static_cast<int64_t>(x1.T) * x1.F;
+    const float* gamma = pp(gw_off);
+    double* S = Sbuf;
+    fdbm_plan* plp = P;
+    const Act a1 = x1; const Act a2 = x2 ? *x2 : Act();
+    bop([=](cudaStream_t s) {
+      FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Ct, s));
+      if (int rc = launch_gn_bwd_reduce(g_a, Ct, 0, a1.data, 0, C1, Ct, 0, tab, stats, act, B, px, S, s)) return rc;
+      if (C2) if (int rc = launch_gn_bwd_reduce(g_a, Ct, C1, a2.data, 0, C2, Ct, C1, tab, stats, act, B, px, S, s)) return rc;
+      if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.data, 0, C1, Ct, 0, tab, stats, gamma, act, B, px, S, a1.grad, nullptr, nullptr, s)) return rc;
+      if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.data, 0, C2, Ct, C1, tab, stats, gamma, act, B, px, S, a2.grad, nullptr, nullptr, s)) return rc;
+      return launch_gn_param_grad(S, B, Ct, plp->cur_inv, plp->grads + gw_off, plp->grads + gb_off, s);
+    });
+  }
+  float2* norm_stats(const double* q1, int C1, const double* q2, int C2, int T, int F) {
+    if (!train()) return nullptr;
+    const int B = P->B;
+    float2* st = alloc<float2>(static_cast<int64_t>(B) * 32);
+    const int64_t px = static_cast<int64_t>(T) * F;
+    op([=](cudaStream_t s) { return launch_gn_stats(q1, C1, q2, C2, B, px, st, s); }, FDBM_OP_STATS);
+    return st;
+  }
+
   // ---------------- parameters
   int64_t param(const std::string& name, int64_t numel) {
     auto it = P->slots.find(name);
@@ -190,12 +278,13 @@ struct Builder {
     if (off < 0) return nullptr;
     return reinterpret_cast<Tp*>(P->arena + off);
   }
-  void release(const void* p) { if (p) arena.release(reinterpret_cast<const uint8_t*>(p) - P->arena); }
+  void release(const void* p) { if (p && !P->train) arena.release(reinterpret_cast<const uint8_t*>(p) - P->arena); }
   Act new_act(int C, int T, int F) {
     Act a; a.C = C; a.T = T; a.F = F;
     a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
     a.h16 = alloc<op_t>(static_cast<int64_t>(P->B) * T * F * C);
     a.sums = alloc<double>(static_cast<int64_t>(P->B) * C * 2);
+    if (P->train) a.grad = galloc(static_cast<int64_t>(P->B) * T * F * C);
     return a;
   }
   void free_act(Act& a) { release(a.data); release(a.h16); release(a.sums); a.data = nullptr; a.h16 = nullptr; a.sums = nullptr; }
@@ -250,8 +339,8 @@ struct Builder {
   }
 
   // ---------------- layers
+  struct CombineArgs { const float* pyr; const float* w; const float* b; int Cp; int64_t w_off, b_off; };
   // ResnetBlockBigGANpp (layerspp.py:242-274) on the concatenation of x1 (and x2)
-  struct CombineArgs { const float* pyr; const float* w; const float* b; int Cp; };
   Act resblock(const Mod& m, const Act& x1, const Act* x2, const float* dense, int dense_stride,
                const CombineArgs* comb = nullptr) {
     const int B = P->B, Cin = m.cin, Cout = m.cout;
@@ -260,16 +349,21 @@ struct Builder {
     const int To = mode == 1 ? T / 2 : (mode == 2 ? T * 2 : T), Fo = mode == 1 ? F / 2 : (mode == 2 ? F * 2 : F);
     const bool shortcut = (Cin != Cout) || m.up || m.down;
     const std::string p = pre(m);
-    const float* g0w = pp(param(p + "GroupNorm_0.weight", Cin)); const float* g0b = pp(param(p + "GroupNorm_0.bias", Cin));
-    const float* c0b = pp(param(p + "Conv_0.bias", Cout));
-    const float* g1w = pp(param(p + "GroupNorm_1.weight", Cout)); const float* g1b = pp(param(p + "GroupNorm_1.bias", Cout));
-    const float* c1b = pp(param(p + "Conv_1.bias", Cout));
+    const int64_t o_g0w = param(p + "GroupNorm_0.weight", Cin), o_g0b = param(p + "GroupNorm_0.bias", Cin);
+    const int64_t o_c0w = param(p + "Conv_0.weight", static_cast<int64_t>(Cout) * Cin * 9), o_c0b = param(p + "Conv_0.bias", Cout);
+    const int64_t o_g1w = param(p + "GroupNorm_1.weight", Cout), o_g1b = param(p + "GroupNorm_1.bias", Cout);
+    const int64_t o_c1w = param(p + "Conv_1.weight", static_cast<int64_t>(Cout) * Cout * 9), o_c1b = param(p + "Conv_1.bias", Cout);
+    const float* g0w = pp(o_g0w); const float* g0b = pp(o_g0b); const float* c0b = pp(o_c0b);
+    const float* g1w = pp(o_g1w); const float* g1b = pp(o_g1b); const float* c1b = pp(o_c1b);
     op_t* w0 = pack(p + "Conv_0.weight", Cin, 3, "", 0, Cout);
     op_t* w1 = shortcut ? pack(p + "Conv_1.weight", Cout, 3, p + "Conv_2.weight", Cin, Cout)
                                  : pack(p + "Conv_1.weight", Cout, 3, "", 0, Cout);
     const float* bias1 = c1b;
+    int64_t o_c2w = -1, o_c2b = -1;
     if (shortcut) {                                   // Conv_1.bias + Conv_2.bias, summed once at load time
-      const float* c2b = pp(param(p + "Conv_2.bias", Cout));
+      o_c2w = param(p + "Conv_2.weight", static_cast<int64_t>(Cout) * Cin);
+      o_c2b = param(p + "Conv_2.bias", Cout);
+      const float* c2b = pp(o_c2b);
       float* bsum = pp(derived(Cout));
       bias1 = bsum;
       pack_op([=](cudaStream_t s) {
@@ -295,9 +389,11 @@ struct Builder {
     ConvArgs c0;
     c0.wpack = w0; c0.bias = c0b; c0.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c0.bias_b_stride = dense_stride;
     c0.B = B; c0.T = To; c0.F = Fo; c0.Cout = Cout; c0.out_h16 = h1; c0.sums = h1_sums;
+    // the (scale, shift) table of GroupNorm_0 is needed by the on-load path and by every backward pass
+    if (mode == 0 || train()) tab0 = norm_table(x1.sums, C1, x2 ? x2->sums : nullptr, C2, g0w, g0b, T, F);
+    float2* stats0 = norm_stats(x1.sums, C1, x2 ? x2->sums : nullptr, C2, T, F);
     if (mode == 0) {
       // GroupNorm_0 + SiLU applied by Conv_0 on load, straight from the 16-bit copies of the residual stream
-      tab0 = norm_table(x1.sums, C1, x2 ? x2->sums : nullptr, C2, g0w, g0b, T, F);
       c0.seg[0] = seg(x1.h16, C1, 9, tab0, Cin, 1); c0.n_seg = 1;
       if (x2) { c0.seg[1] = seg(x2->h16, C2, 9, tab0 + C1, Cin, 1); c0.n_seg = 2; }
     } else {
@@ -314,6 +410,7 @@ struct Builder {
     conv_op(c0);
     release(a0); release(tab0);
     float2* tab1 = norm_table(h1_sums, Cout, nullptr, 0, g1w, g1b, To, Fo);
+    float2* stats1 = norm_stats(h1_sums, Cout, nullptr, 0, To, Fo);
     Act out = new_act(Cout, To, Fo);
     {
       ConvArgs c;
@@ -334,24 +431,101 @@ struct Builder {
     }
     release(h1); release(h1_sums); release(tab1);
     release(xr);
+
+    if (train()) {
+      // ------------------------------------------------------------------ backward of the block (recorded, replayed in reverse)
+      bgroup();
+      fdbm_plan* plp = P;
+      const int64_t pxo = static_cast<int64_t>(To) * Fo;
+      const Act xa = x1; const Act xb = x2 ? *x2 : Act();
+      op_t *t1 = T1, *t2 = T2, *t3 = T3, *t4 = T4, *t5 = T5;
+      double* sA = sumsA; double* S = Sbuf; float* dd = d_dense;
+      if (comb) {
+        const CombineArgs cb = *comb; const float* og = out.grad;
+        bop([=](cudaStream_t s) {
+          return launch_combine_bwd(og, cb.pyr, cb.Cp, static_cast<int64_t>(B) * pxo, Cout, plp->cur_inv, plp->grads + cb.w_off, plp->grads + cb.b_off, s);
+        });
+      }
+      {   // gs = dL/d(out) / sqrt(2) as a 16-bit operand; identity shortcut: x.grad += gs; bias gradients
+        const float* og = out.grad; float* xg = shortcut ? nullptr : xa.grad;
+        bop([=](cudaStream_t s) {
+          if (int rc = launch_grad_prepare(og, B, pxo, Cout, 0.70710678118654752f, t1, xg, sA, s)) return rc;
+          if (int rc = launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c1b, nullptr, 0, s)) return rc;
+          if (o_c2b >= 0) return launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c2b, nullptr, 0, s);
+          return FDBM_OK;
+        });
+      }
+      if (shortcut) {
+        if (mode == 0) {
+          op_t* wd1 = pack_d(o_c2w, Cout, C1, 1, Cin, 0);
+          dgrad_op(t1, Cout, 1, wd1, C1, To, Fo, nullptr, xa.grad);
+          WgradCall w; w.dy = t1; w.dy_ld = Cout; w.Cout = Cout; w.x = xa.h16; w.x_ld = C1; w.Cin = C1; w.ksize = 1; w.T = To; w.F = Fo;
+          w.Cin_total = Cin; w.ci_off = 0;
+          wgrad_op(w, o_c2w);
+          if (x2) {
+            op_t* wd2 = pack_d(o_c2w, Cout, C2, 1, Cin, C1);
+            dgrad_op(t1, Cout, 1, wd2, C2, To, Fo, nullptr, xb.grad);
+            w.x = xb.h16; w.x_ld = C2; w.Cin = C2; w.ci_off = C1;
+            wgrad_op(w, o_c2w);
+          }
+        } else {
+          op_t* wd = pack_d(o_c2w, Cout, Cin, 1);
+          dgrad_op(t1, Cout, 1, wd, Cin, To, Fo, t3, nullptr);
+          float* xg = xa.grad;
+          // adjoint of the FIR on the shortcut operand: adjoint(down) = up / 4, adjoint(up) = 4 * down
+          bop([=](cudaStream_t s) { return launch_fir_resample16(t3, Cin, 0, B, To, Fo, Cin, mode == 1 ? 2 : 1, mode == 1 ? 0.25f : 4.0f, nullptr, xg, s); });
+          WgradCall w; w.dy = t1; w.dy_ld = Cout; w.Cout = Cout; w.x = xr; w.x_ld = Cin; w.Cin = Cin; w.ksize = 1; w.T = To; w.F = Fo;
+          wgrad_op(w, o_c2w);
+        }
+      }
+      // Conv_1: wgrad needs a1 = SiLU(GroupNorm_1(h1)) (recomputed from the saved 16-bit h1), dgrad gives g_a1
+      bop([=](cudaStream_t s) { return launch_groupnorm_act(h1, 1, h1_sums, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, t2, nullptr, s); });
+      { WgradCall w; w.dy = t1; w.dy_ld = Cout; w.Cout = Cout; w.x = t2; w.x_ld = Cout; w.Cin = Cout; w.ksize = 3; w.T = To; w.F = Fo; wgrad_op(w, o_c1w); }
+      dgrad_op(t1, Cout, 9, pack_d(o_c1w, Cout, Cout, 3), Cout, To, Fo, t3, nullptr);
+      bop([=](cudaStream_t s) {     // GroupNorm_1 backward: g_h1 (16-bit) + its per-(b,c) sums (Conv_0 bias and FiLM gradients)
+        FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Cout, s));
+        if (int rc = launch_gn_bwd_reduce(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, 1, B, pxo, S, s)) return rc;
+        if (int rc = launch_gn_bwd_apply(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, g1w, 1, B, pxo, S, nullptr, t4, sA, s)) return rc;
+        if (int rc = launch_gn_param_grad(S, B, Cout, plp->cur_inv, plp->grads + o_g1w, plp->grads + o_g1b, s)) return rc;
+        return launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c0b, dense_row >= 0 ? dd + dense_row : nullptr, dense_stride, s);
+      });
+      // Conv_0: a0 recomputed (or the saved resampled one), wgrad, dgrad, GroupNorm_0 backward into x.grad
+      const op_t* a0b = a0;
+      if (mode == 0) {
+        const float* s1 = xa.data; const double* q1 = xa.sums; const float* s2 = x2 ? xb.data : nullptr; const double* q2 = x2 ? xb.sums : nullptr;
+        bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, 0, t2, nullptr, s); });
+        a0b = t2;
+      }
+      { WgradCall w; w.dy = t4; w.dy_ld = Cout; w.Cout = Cout; w.x = a0b; w.x_ld = Cin; w.Cin = Cin; w.ksize = 3; w.T = To; w.F = Fo; wgrad_op(w, o_c0w); }
+      dgrad_op(t4, Cout, 9, pack_d(o_c0w, Cout, Cin, 3), Cin, To, Fo, t3, nullptr);
+      const op_t* g_act = t3;
+      if (mode != 0) {
+        bop([=](cudaStream_t s) { return launch_fir_resample16(t3, Cin, 0, B, To, Fo, Cin, mode == 1 ? 2 : 1, mode == 1 ? 0.25f : 4.0f, t5, nullptr, s); });
+        g_act = t5;
+      }
+      gn_bwd(g_act, x1, x2, tab0, stats0, o_g0w, o_g0b, 1);
+    }
     return out;
   }
-
   // AttnBlockpp (layerspp.py:75-91)
   Act attn(const Mod& m, const Act& x) {
     const int B = P->B, C = m.cin, T = x.T, F = x.F;
     const std::string p = pre(m);
-    const float* gw = pp(param(p + "GroupNorm_0.weight", C)); const float* gb = pp(param(p + "GroupNorm_0.bias", C));
+    const int64_t o_gw = param(p + "GroupNorm_0.weight", C), o_gb = param(p + "GroupNorm_0.bias", C);
+    const float* gw = pp(o_gw); const float* gb = pp(o_gb);
     // q, k, v projections as one GEMM with 3C outputs; biases are three consecutive slots
-    const float* bq = pp(param(p + "NIN_0.b", C));
-    param(p + "NIN_1.b", C); param(p + "NIN_2.b", C);
-    const float* b3 = pp(param(p + "NIN_3.b", C));
+    const int64_t o_b0 = param(p + "NIN_0.b", C), o_b1 = param(p + "NIN_1.b", C), o_b2 = param(p + "NIN_2.b", C), o_b3 = param(p + "NIN_3.b", C);
+    const float* bq = pp(o_b0);
+    const float* b3 = pp(o_b3);
+    const int64_t o_w0 = param(p + "NIN_0.W", static_cast<int64_t>(C) * C), o_w1 = param(p + "NIN_1.W", static_cast<int64_t>(C) * C),
+                  o_w2 = param(p + "NIN_2.W", static_cast<int64_t>(C) * C), o_w3 = param(p + "NIN_3.W", static_cast<int64_t>(C) * C);
     op_t* wqkv = pack(p + "NIN_0.W", C, -1, "", 0, C, 3 * C, 0);
     pack(p + "NIN_1.W", C, -1, "", 0, C, 3 * C, C, wqkv);
     pack(p + "NIN_2.W", C, -1, "", 0, C, 3 * C, 2 * C, wqkv);
     op_t* w3 = pack(p + "NIN_3.W", C, -1, "", 0, C);
     const int64_t npx = static_cast<int64_t>(B) * T * F;
     float2* tab = norm_table(x.sums, C, nullptr, 0, gw, gb, T, F);
+    float2* stats = norm_stats(x.sums, C, nullptr, 0, T, F);
     op_t* qkv = alloc<op_t>(npx * 3 * C);
     {
       ConvArgs c;
@@ -373,6 +547,44 @@ struct Builder {
       conv_op(c);
     }
     release(o);
+    if (train()) {
+      bgroup();
+      fdbm_plan* plp = P;
+      const int64_t px = static_cast<int64_t>(T) * F;
+      op_t *t1 = T1, *t2 = T2, *t3 = T3, *t4 = T4;
+      double* sA = sumsA; float* asc = att_scratch;
+      const Act xa = x;
+      { const float* og = out.grad; float* xg = xa.grad;
+        bop([=](cudaStream_t s) {
+          if (int rc = launch_grad_prepare(og, B, px, C, 0.70710678118654752f, t1, xg, sA, s)) return rc;
+          return launch_col_sums_to(sA, B, C, plp->cur_inv, plp->grads + o_b3, nullptr, 0, s);
+        }); }
+      { WgradCall w; w.dy = t1; w.dy_ld = C; w.Cout = C; w.x = o; w.x_ld = C; w.Cin = C; w.ksize = 1; w.T = T; w.F = F; w.layout = 1; wgrad_op(w, o_w3); }
+      dgrad_op(t1, C, 1, pack_d(o_w3, C, C, -1), C, T, F, t3, nullptr);
+      const int64_t o_b[3] = {o_b0, o_b1, o_b2};
+      const int64_t ob0 = o_b[0], ob1 = o_b[1], ob2 = o_b[2];
+      bop([=](cudaStream_t s) {
+        if (int rc = launch_attention_bwd(qkv, B, T * F, C, t3, asc, t4, s)) return rc;
+        const int64_t obs[3] = {ob0, ob1, ob2};
+        for (int i = 0; i < 3; ++i) {
+          if (int rc = launch_col_sums16(t4, 3 * C, i * C, B, px, C, sA, s)) return rc;
+          if (int rc = launch_col_sums_to(sA, B, C, plp->cur_inv, plp->grads + obs[i], nullptr, 0, s)) return rc;
+        }
+        return FDBM_OK;
+      });
+      { const float* s1 = xa.data; const double* q1 = xa.sums;
+        bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 0, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, t2, nullptr, s); }); }
+      const int64_t o_w[3] = {o_w0, o_w1, o_w2};
+      for (int i = 0; i < 3; ++i) {
+        WgradCall w; w.dy = t4; w.dy_ld = 3 * C; w.dy_coff = i * C; w.Cout = C; w.x = t2; w.x_ld = C; w.Cin = C; w.ksize = 1; w.T = T; w.F = F; w.layout = 1;
+        wgrad_op(w, o_w[i]);
+      }
+      // dgrad of the fused q|k|v projection: K = 3C over the three transposed NIN matrices
+      op_t* wd = pack_d(o_w0, C, C, -1);
+      pack_d(o_w1, C, C, -1); pack_d(o_w2, C, C, -1);          // consecutive regions: K blocks q, k, v
+      dgrad_op(t4, 3 * C, 1, wd, C, T, F, t3, nullptr);
+      gn_bwd(t3, x, nullptr, tab, stats, o_gw, o_gb, 0);
+    }
     return out;
   }
 
@@ -382,15 +594,26 @@ struct Builder {
     const int B = pl.B, nf = A.nf, Cp = pl.Cin, L = A.n_levels;
     size_t mi = 0;
     auto next = [&]() -> const Mod& { return pl.mods[mi++]; };
-    wp_off = 0; dense_off = 0;
+    wp_off = 0; dense_off = 0; wd_off = 0; ws_need = 0; groups.clear();
+    if (train()) {
+      // shared backward scratch: the largest 16-bit operand of the network is [B, T, F, 2 nf] at level 0
+      const int64_t big = static_cast<int64_t>(B) * pl.T * pl.F * 2 * nf;
+      T1 = alloc<op_t>(big); T2 = alloc<op_t>(big); T3 = alloc<op_t>(big); T4 = alloc<op_t>(big); T5 = alloc<op_t>(big);
+      Sbuf = alloc<double>(static_cast<int64_t>(B) * 1024 * 2);
+      sumsA = alloc<double>(static_cast<int64_t>(B) * 1024);
+      const int Lmax = (pl.T >> 4) * (pl.F >> 4);                     // attention runs at the 16-bin level
+      att_scratch = alloc<float>(2ll * B * Lmax * Lmax);
+      zero_bias = pp(derived(1024));
+    }
 
     // ---- time embedding + all Dense_0 projections (one table [B, dense_rows])
     float* temb_act = nullptr; float* dense = nullptr;
     if (!A.predictive) {
       const Mod& mf = next(); const Mod& l1 = next(); const Mod& l2 = next();
       const float* fw = pp(param(pre(mf) + "W", nf));
-      const float* w1 = pp(param(pre(l1) + "weight", static_cast<int64_t>(4 * nf) * 2 * nf)); const float* b1 = pp(param(pre(l1) + "bias", 4 * nf));
-      const float* w2 = pp(param(pre(l2) + "weight", static_cast<int64_t>(4 * nf) * 4 * nf)); const float* b2 = pp(param(pre(l2) + "bias", 4 * nf));
+      const int64_t o_w1 = param(pre(l1) + "weight", static_cast<int64_t>(4 * nf) * 2 * nf), o_b1 = param(pre(l1) + "bias", 4 * nf);
+      const int64_t o_w2 = param(pre(l2) + "weight", static_cast<int64_t>(4 * nf) * 4 * nf), o_b2 = param(pre(l2) + "bias", 4 * nf);
+      const float* w1 = pp(o_w1); const float* b1 = pp(o_b1); const float* w2 = pp(o_w2); const float* b2 = pp(o_b2);
       // Dense_0 weights / biases of all residual blocks, contiguous and in execution order
       int rows = 0; int64_t dw0 = -1, db0 = -1;
       for (const Mod& m : pl.mods) if (m.kind == Mod::RES) {
@@ -411,6 +634,17 @@ struct Builder {
         return launch_temb(plp->cur_t, fw, nf, w1, b1, w2, b2, B, plp->cur_t_stride, temb_act, s);
       }, FDBM_OP_SMALL);
       op([=](cudaStream_t s) { return launch_dense_all(temb_act, dwp, dbp, B, 4 * nf, rows, dense, s); }, FDBM_OP_SMALL);
+      if (train()) {
+        // first group = last to run in backward: by then every block has left its FiLM gradient in d_dense
+        d_dense = alloc<float>(static_cast<int64_t>(B) * rows);
+        g_temb = alloc<float>(static_cast<int64_t>(B) * 4 * nf);
+        float* dd = d_dense; float* gt = g_temb;
+        bgroup();
+        bop([=](cudaStream_t s) {
+          return launch_dense_temb_bwd(dd, temb_act, dwp, B, 4 * nf, rows, plp->grads + dw0, plp->grads + db0, gt, plp->cur_t, fw, nf, w1, b1, w2,
+                                       b2, plp->cur_t_stride, plp->grads + o_w1, plp->grads + o_b1, plp->grads + o_w2, plp->grads + o_b2, s);
+        });
+      }
     }
     const int dstride = pl.dense_rows;
 
@@ -424,7 +658,8 @@ struct Builder {
     std::vector<Act> hs;
     {
       const Mod& m = next();
-      const float* w = pp(param(pre(m) + "weight", static_cast<int64_t>(nf) * Cp * 9)); const float* b = pp(param(pre(m) + "bias", nf));
+      const int64_t o_w = param(pre(m) + "weight", static_cast<int64_t>(nf) * Cp * 9), o_b = param(pre(m) + "bias", nf);
+      const float* w = pp(o_w); const float* b = pp(o_b);
       // first conv (4 -> nf, 3x3) on the tensor cores: im2col to one 64-wide K-block, then a K=64 GEMM
       op_t* wp = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
       wp_off += (static_cast<int64_t>(nf) * 64 * 2 + 1023) / 1024 * 1024;
@@ -439,6 +674,18 @@ struct Builder {
       c.out_f32 = h0.data; c.out_h16 = h0.h16; c.sums = h0.sums;
       conv_op(c, 2.0 * B * T * F * nf * 9.0 * Cp);
       release(cols);
+      if (train()) {
+        bgroup();
+        fdbm_plan* plp = P; op_t* t1 = T1; double* sA = sumsA; const float* g0 = h0.grad;
+        const int64_t px = static_cast<int64_t>(T) * F;
+        bop([=](cudaStream_t s) {
+          if (int rc = launch_grad_prepare(g0, B, px, nf, 1.0f, t1, nullptr, sA, s)) return rc;
+          return launch_col_sums_to(sA, B, nf, plp->cur_inv, plp->grads + o_b, nullptr, 0, s);
+        });
+        WgradCall wc; wc.dy = t1; wc.dy_ld = nf; wc.Cout = nf; wc.x = cols; wc.x_ld = 64; wc.Cin = 64; wc.ksize = 1; wc.T = T; wc.F = F;
+        wc.layout = 2; wc.aux = Cp;
+        wgrad_op(wc, o_w);
+      }
       hs.push_back(h0);
     }
     // ---- down path
@@ -462,7 +709,8 @@ struct Builder {
         const Mod& m = pl.mods[mi];               // the Combine module follows the block
         CombineArgs cb;
         cb.pyr = pyr_in; cb.Cp = Cp;
-        cb.w = pp(param(pre(m) + "Conv_0.weight", static_cast<int64_t>(m.cout) * Cp)); cb.b = pp(param(pre(m) + "Conv_0.bias", m.cout));
+        cb.w_off = param(pre(m) + "Conv_0.weight", static_cast<int64_t>(m.cout) * Cp); cb.b_off = param(pre(m) + "Conv_0.bias", m.cout);
+        cb.w = pp(cb.w_off); cb.b = pp(cb.b_off);
         Act h = resblock(mr, hs.back(), nullptr, dense, dstride, &cb);
         next();
         T /= 2; F /= 2;
@@ -480,6 +728,7 @@ struct Builder {
     }
     // ---- up path
     float* pyramid = nullptr;
+    float* gpyr = nullptr;                   // training: gradient buffer of the current pyramid level
     for (int lvl = L - 1; lvl >= 0; --lvl) {
       for (int blk = 0; blk < A.num_res_blocks + 1; ++blk) {
         Act skip = hs.back(); hs.pop_back();
@@ -491,8 +740,10 @@ struct Builder {
       {
         const Mod& mg = next(); const Mod& mc = next();
         const int C = mg.cin, Tc = h.T, Fc = h.F;
-        const float* gw = pp(param(pre(mg) + "weight", C)); const float* gb = pp(param(pre(mg) + "bias", C));
-        const float* w = pp(param(pre(mc) + "weight", static_cast<int64_t>(Cp) * C * 9)); const float* b = pp(param(pre(mc) + "bias", Cp));
+        const int64_t o_gw = param(pre(mg) + "weight", C), o_gb = param(pre(mg) + "bias", C);
+        const int64_t o_w = param(pre(mc) + "weight", static_cast<int64_t>(Cp) * C * 9), o_b = param(pre(mc) + "bias", Cp);
+        const float* gw = pp(o_gw); const float* gb = pp(o_gb);
+        const float* w = pp(o_w); const float* b = pp(o_b);
         // C -> 4 conv on the tensor cores: weight rows padded with zeros to one 128-wide N block
         op_t* wp = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
         const int64_t wbytes = conv_wpack_bytes(C, 3, 0, 128);
@@ -504,12 +755,38 @@ struct Builder {
         float* pyr_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
         float* prev = pyramid;
         float2* tab = norm_table(h.sums, C, nullptr, 0, gw, gb, Tc, Fc);
+        float2* stats = norm_stats(h.sums, C, nullptr, 0, Tc, Fc);
         ConvArgs c;
         c.seg[0] = seg(h.h16, C, 9, tab, C, 1); c.n_seg = 1;     // GroupNorm + SiLU on load
         c.wpack = wp; c.bias = b; c.B = B; c.T = Tc; c.F = Fc; c.Cout = 128;
         c.pyr_out = pyr_new; c.pyr_prev = prev; c.pyr_C = Cp;
         conv_op(c, 2.0 * B * Tc * Fc * Cp * 9.0 * C);
         release(tab);
+        if (train()) {
+          // progressive output backward (ncsnpp_v2.py:338-359): g_pyr of this level arrives from the finer level (or from
+          // the output layer); the coarser level receives adjoint(FIR up) = 4 * FIR down of it
+          float* g_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
+          float* g_prev = gpyr;
+          gpyr = g_new;
+          bgroup();
+          fdbm_plan* plp = P; op_t *t1 = T1, *t2 = T2, *t3 = T3;
+          const int64_t px = static_cast<int64_t>(Tc) * Fc;
+          op_t* wd = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked_d) + wd_off);
+          wd_off += (static_cast<int64_t>(C) * 64 * 2 + 1023) / 1024 * 1024;
+          pack_op([=](cudaStream_t s) { return launch_pack_pyr_dgrad(w, C, Cp, wd, s); });
+          bop([=](cudaStream_t s) {
+            if (g_prev) if (int rc = launch_fir_resample_scaled(g_new, B, Tc, Fc, Cp, 1, 4.0f, g_prev, s)) return rc;
+            if (int rc = launch_small_col_sums(g_new, static_cast<int64_t>(B) * px, Cp, plp->cur_inv, plp->grads + o_b, s)) return rc;
+            return launch_im2col_input(g_new, Cp, B, Tc, Fc, t1, s);
+          });
+          dgrad_op(t1, 64, 1, wd, C, Tc, Fc, t3, nullptr);
+          { const float* s1 = h.data; const double* q1 = h.sums;
+            bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 0, q1, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, t2, nullptr, s); }); }
+          WgradCall wc; wc.dy = t2; wc.dy_ld = C; wc.Cout = C; wc.x = t1; wc.x_ld = 64; wc.Cin = 64; wc.ksize = 1; wc.T = Tc; wc.F = Fc;
+          wc.layout = 3; wc.aux = Cp;
+          wgrad_op(wc, o_w);
+          gn_bwd(t3, h, nullptr, tab, stats, o_gw, o_gb, 1);
+        }
         release(pyramid);
         pyramid = pyr_new;
       }
@@ -518,11 +795,23 @@ struct Builder {
     free_act(h);
     if (mi != pl.mods.size() || !hs.empty()) { set_error("plan: module walk out of sync (%zu of %zu)", mi, pl.mods.size()); return FDBM_EINVAL; }
     {
-      const float* w = pp(param("output_layer.weight", 2 * Cp)); const float* b = pp(param("output_layer.bias", 2));
+      const int64_t o_w = param("output_layer.weight", 2 * Cp), o_b = param("output_layer.bias", 2);
+      const float* w = pp(o_w); const float* b = pp(o_b);
       const int Tc = pl.T, Fc = pl.F; fdbm_plan* plp = P; float* pyr = pyramid;
       op([=](cudaStream_t s) { return launch_output_layer(pyr, Cp, w, b, B, Tc, Fc, plp->F_io, plp->cur_out, s); }, FDBM_OP_SKINNY);
+      if (train()) {
+        bgroup();
+        float* g0 = gpyr;
+        bop([=](cudaStream_t s) {
+          return launch_output_layer_bwd(plp->cur_gout, pyr, Cp, w, B, Tc, Fc, plp->F_io, plp->cur_inv, g0, plp->grads + o_w, plp->grads + o_b, s);
+        });
+      }
     }
     release(pyramid);
+    if (train() && !dry) {
+      for (auto g = groups.rbegin(); g != groups.rend(); ++g)
+        for (auto& f : *g) P->bwd_ops.push_back(std::move(f));
+    }
     return FDBM_OK;
   }
 };
@@ -534,7 +823,7 @@ int run_ops(fdbm_plan* plan, cudaStream_t s) {
 
 }  // namespace
 
-extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out) {
+static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool train, fdbm_plan** out) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(arch && out, "fdbm_plan_create: null pointer");
   FDBM_REQUIRE(batch > 0 && n_frames > 0, "fdbm_plan_create: batch and n_frames must be positive");
@@ -549,6 +838,7 @@ extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, 
   fdbm_plan* P = new fdbm_plan();
   P->arch = *arch; P->B = batch; P->T = n_frames; P->F = arch->image_size; P->F_io = arch->image_size + 1;
   P->Cin = arch->predictive ? 2 : 4;
+  P->train = train;
   P->mods = build_modules(*arch);
   auto fail = [&](int rc) { fdbm_plan_destroy(P); return rc; };
 
@@ -561,6 +851,8 @@ extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, 
   P->arena_bytes = b1.arena.peak();
   P->arena = nullptr;
   P->wpacked_bytes = b1.wp_off;
+  P->wpacked_d_bytes = b1.wd_off;
+  P->wgrad_ws_bytes = b1.ws_need;
   const int64_t params_numel = P->params_numel;
   // d_buf for the sampler
   const int64_t spec_elems = static_cast<int64_t>(batch) * P->F_io * n_frames * 2;
@@ -570,6 +862,12 @@ extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, 
   if ((e = cudaMalloc(&P->wpacked, P->wpacked_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wpacked)", __FILE__, __LINE__));
   if ((e = cudaMalloc(&P->d_buf, spec_elems * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(d_buf)", __FILE__, __LINE__));
   if ((e = cudaMemset(P->params, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+  if (train) {
+    if ((e = cudaMalloc(&P->grads, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(grads)", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->wpacked_d, std::max<int64_t>(P->wpacked_d_bytes, 1024))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wpacked_d)", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->wgrad_ws, std::max<int64_t>(P->wgrad_ws_bytes, 1024))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wgrad_ws)", __FILE__, __LINE__));
+    if ((e = cudaMemset(P->grads, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+  }
 
   // pass 2: identical walk, now recording launches against real addresses
   P->params_numel = 0;
@@ -578,11 +876,77 @@ extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, 
   b2.dry = false;
   b2.arena.reset(P->arena_bytes);
   if (int rc = b2.build()) return fail(rc);
-  if (P->params_numel != params_numel || b2.wp_off != P->wpacked_bytes) {
+  P->n_bwd_launches = static_cast<int>(P->bwd_ops.size());
+  if (P->params_numel != params_numel || b2.wp_off != P->wpacked_bytes || b2.wd_off != P->wpacked_d_bytes) {
     set_error("plan: second pass diverged from the sizing pass");
     return fail(FDBM_EINVAL);
   }
   *out = P;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out) {
+  return plan_create_impl(arch, batch, n_frames, false, out);
+}
+
+extern "C" int fdbm_plan_create_train(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out) {
+  FDBM_REQUIRE(arch && !arch->predictive, "fdbm_plan_create_train: the training step is built for the bridge backbone (predictive = 0)");
+  return plan_create_impl(arch, batch, n_frames, true, out);
+}
+
+// dL/dparams of the last fdbm_ncsnpp_forward on a training plan.  g_out = loss_scale * dL/dD, cplx [B,1,257,T].
+extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float loss_scale, int accumulate, void* stream) {
+  FDBM_REQUIRE(plan && g_out && loss_scale > 0.f, "fdbm_ncsnpp_backward: bad arguments");
+  if (!plan->train) { set_error("fdbm_ncsnpp_backward: not a training plan (use fdbm_plan_create_train)"); return FDBM_ESTATE; }
+  if (!plan->weights_ready || !plan->cur_x) { set_error("fdbm_ncsnpp_backward: no forward pass to differentiate"); return FDBM_ESTATE; }
+  cudaStream_t s = as_stream(stream);
+  plan->cur_gout = g_out; plan->cur_inv = 1.0f / loss_scale;
+  if (!accumulate) FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
+  for (auto& z : plan->zero_list) FDBM_CUDA(cudaMemsetAsync(z.first, 0, z.second, s));
+  for (auto& f : plan->bwd_ops) if (int rc = f(s)) return rc;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_param_info(const fdbm_plan* plan, const char* name, int64_t* offset, int64_t* numel) {
+  FDBM_REQUIRE(plan && name, "fdbm_plan_param_info: null pointer");
+  auto it = plan->slots.find(name);
+  FDBM_REQUIRE(it != plan->slots.end(), "fdbm_plan_param_info: unknown tensor '%s'", name);
+  if (offset) *offset = it->second.off;
+  if (numel) *numel = it->second.numel;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads, float** ema, int64_t* numel) {
+  FDBM_REQUIRE(plan, "fdbm_plan_buffers: null plan");
+  if (params) *params = plan->params;
+  if (grads) *grads = plan->grads;
+  if (ema) *ema = plan->ema;
+  if (numel) *numel = plan->params_numel;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_num_backward_launches(const fdbm_plan* plan) { return plan ? plan->n_bwd_launches : 0; }
+
+// Adam + clip + EMA on the flat buffers, then the packed 16-bit weights are rebuilt from the updated parameters.
+extern "C" int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, float lr, float beta1, float beta2,
+                                        float eps, int step, float ema_decay, void* stream) {
+  FDBM_REQUIRE(plan && step >= 1 && grad_div > 0.f, "fdbm_plan_optimizer_step: bad arguments");
+  if (!plan->train) { set_error("fdbm_plan_optimizer_step: not a training plan"); return FDBM_ESTATE; }
+  cudaStream_t s = as_stream(stream);
+  const int64_t n = plan->params_numel;
+  if (!plan->adam_m) {
+    FDBM_CUDA(cudaMalloc(&plan->adam_m, n * sizeof(float)));
+    FDBM_CUDA(cudaMalloc(&plan->adam_v, n * sizeof(float)));
+    FDBM_CUDA(cudaMalloc(&plan->ema, n * sizeof(float)));
+    FDBM_CUDA(cudaMalloc(&plan->opt_scratch, sizeof(double)));
+    FDBM_CUDA(cudaMemsetAsync(plan->adam_m, 0, n * sizeof(float), s));
+    FDBM_CUDA(cudaMemsetAsync(plan->adam_v, 0, n * sizeof(float), s));
+    FDBM_CUDA(cudaMemcpyAsync(plan->ema, plan->params, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
+  }
+  if (int rc = launch_adam_ema(plan->params, plan->grads, plan->adam_m, plan->adam_v, plan->ema, nullptr, n, plan->opt_scratch, grad_div,
+                               clip_norm, lr, beta1, beta2, eps, step, ema_decay, s))
+    return rc;
+  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
 }
 
@@ -592,6 +956,8 @@ extern "C" int fdbm_plan_destroy(fdbm_plan* plan) {
   if (plan->capture_stream) cudaStreamDestroy(plan->capture_stream);
   fdbm_plan_release_sampler_state(plan);
   cudaFree(plan->arena); cudaFree(plan->params); cudaFree(plan->wpacked); cudaFree(plan->d_buf);
+  cudaFree(plan->grads); cudaFree(plan->wpacked_d); cudaFree(plan->wgrad_ws);
+  cudaFree(plan->adam_m); cudaFree(plan->adam_v); cudaFree(plan->ema); cudaFree(plan->opt_scratch);
   delete plan;
   return FDBM_OK;
 }

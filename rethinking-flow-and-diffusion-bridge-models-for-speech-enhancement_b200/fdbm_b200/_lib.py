@@ -26,6 +26,8 @@ EXPORTS = [
     "fdbm_pack_conv_weights", "fdbm_attention",
     "fdbm_pack_conv_weights_dgrad", "fdbm_conv_wgrad_workspace_bytes", "fdbm_conv_wgrad",
     "fdbm_groupnorm_act_bwd", "fdbm_fir_resample_h16", "fdbm_attention_bwd", "fdbm_adam_ema_step",
+    "fdbm_plan_create_train", "fdbm_ncsnpp_backward", "fdbm_plan_param_info", "fdbm_plan_buffers",
+    "fdbm_plan_num_backward_launches", "fdbm_plan_optimizer_step",
 ]
 
 
@@ -84,6 +86,12 @@ def load() -> C.CDLL:
         "fdbm_fir_resample_h16": (i, [p, i, i, i, i, i, f, p, p]),
         "fdbm_attention_bwd": (i, [p, i, i, i, p, p, p, p]),
         "fdbm_adam_ema_step": (i, [p, p, p, p, p, i64, p, f, f, f, f, f, f, i, f, p]),
+        "fdbm_plan_create_train": (i, [C.POINTER(Arch), i, i, C.POINTER(p)]),
+        "fdbm_ncsnpp_backward": (i, [p, p, f, i, p]),
+        "fdbm_plan_param_info": (i, [p, C.c_char_p, C.POINTER(i64), C.POINTER(i64)]),
+        "fdbm_plan_buffers": (i, [p, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]),
+        "fdbm_plan_num_backward_launches": (i, [p]),
+        "fdbm_plan_optimizer_step": (i, [p, f, f, f, f, f, f, i, f, p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
     }
     for name, (res, args) in sig.items():

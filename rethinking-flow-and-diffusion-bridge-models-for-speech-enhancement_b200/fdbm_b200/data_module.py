@@ -113,6 +113,22 @@ class SpecsDataModule:
         """fdbm/data_module.py:188-199."""
         return self._spec_transform(spec, inverse=1)
 
+    # ---- differentiable torch forms (loss head of the training step, fdbm/model.py:187-218) -----
+    def spec_back_torch(self, spec: torch.Tensor) -> torch.Tensor:
+        """fdbm/data_module.py:188-199 with torch ops (autograd-capable; `exponent` transform)."""
+        if self.transform_type != "exponent":
+            raise NotImplementedError("the training loss head supports transform_type='exponent'")
+        spec = spec / self.spec_factor
+        if self.spec_abs_exponent != 1:
+            e = self.spec_abs_exponent
+            spec = spec.abs() ** (1 / e) * torch.exp(1j * spec.angle())
+        return spec
+
+    def istft_torch(self, spec: torch.Tensor, length=None) -> torch.Tensor:
+        """fdbm/data_module.py:227-229 through torch.istft (autograd-capable)."""
+        return torch.istft(spec, n_fft=self.n_fft, hop_length=self.hop_length, window=self._get_window(spec), center=True,
+                           length=length)
+
     # ---- fused forms ---------------------------------------------------------------------------
     def stft_compress(self, sig: torch.Tensor, pad_mode: str = "zero_pad", n_frames_out=None) -> torch.Tensor:
         """pad_spec(spec_fwd(stft(sig)))[:, None] in one kernel: [B, Ts] -> [B, 1, F, T_pad]."""

@@ -1,0 +1,172 @@
+"""Training step of the bridge model (fdbm/model.py:258-275 `_step` / `sample_prior`, :187-218 hybrid loss,
+:101 Adam, :129-132 EMA, train.py:161 gradient_clip_val=3.0) on the CUDA backbone.
+
+    x_t = a_t x + b_t y + sigma_t z            Bridge.probability_path (bridge.py:40-43)
+    D   = dnn(x_t, y, t)                       fdbm_ncsnpp_forward on a TRAINING plan (all activations kept)
+    L   = 70 MSE(|X|^0.3) + 30 MSE(X/|X|^0.7) - mean log10 SI-SNR(istft)     (data_prediction_hybrid)
+    dL/dparams                                 fdbm_ncsnpp_backward: tcgen05 dgrad / wgrad + GroupNorm / FIR / attention backward
+    all-reduce(grads) / world                  torch.distributed (NCCL over NVLink), one flat 262 MB buffer
+    Adam + clip + EMA                          fdbm_plan_optimizer_step on the flat buffers, weights re-packed
+
+The loss head (spec_back, powers, iSTFT, SI-SNR: < 0.01 % of the step's FLOPs) is evaluated with torch ops and
+torch autograd in this round; everything from dL/dD down to the parameter update runs in libfdbm_b200.
+Gradients of activations are 16-bit GEMM operands, so dL/dD is multiplied by `loss_scale` first (divided out of
+the fp32 parameter gradients); a non-finite gradient norm skips the update (GradScaler semantics).
+"""
+from __future__ import annotations
+
+import ctypes as C
+from typing import Dict, Optional
+
+import torch
+
+from . import _lib
+from ._lib import check, current_stream, ptr
+
+
+class _DevBuf:
+    def __init__(self, pointer: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (pointer, False), "version": 2}
+
+
+def hybrid_loss(x_hat: torch.Tensor, x: torch.Tensor, data_module) -> torch.Tensor:
+    """fdbm/model.py:187-218 (`data_prediction_hybrid`, pesq_weight = 0) with torch ops (differentiable)."""
+    B, Cc, F, T = x.shape
+    x_nc = data_module.spec_back_torch(x)
+    x_hat_nc = data_module.spec_back_torch(x_hat)
+    x_mag = torch.abs(x_nc + 1e-12)
+    x_hat_mag = torch.abs(x_hat_nc + 1e-12)
+    losses_mag = torch.mean(torch.square(x_mag.pow(0.3) - x_hat_mag.pow(0.3)))
+    losses_ri = torch.square(torch.norm(x_nc / x_mag.pow(0.7) - x_hat_nc / x_hat_mag.pow(0.7), p=2)) / (B * Cc * F * T)
+    x_hat_td = data_module.istft_torch(x_hat_nc.squeeze(1))
+    x_td = data_module.istft_torch(x_nc.squeeze(1))
+    x_td_norm = torch.sum(x_td * x_hat_td, dim=-1, keepdim=True) * x_td / (torch.sum(x_td.pow(2), dim=-1, keepdim=True) + 1e-12)
+    sisnr = torch.log10((torch.sum(x_td_norm.pow(2), dim=-1, keepdim=True) /
+                         (torch.sum((x_hat_td - x_td_norm).pow(2), dim=-1, keepdim=True) + 1e-12)).clamp(min=1e-12)).mean()
+    return 70 * losses_mag + 30 * losses_ri - sisnr
+
+
+class TrainStep:
+    """One data-parallel optimisation step; `dnn` is the fdbm_b200 NCSNpp_v2 whose parameters are trained."""
+
+    def __init__(self, dnn, bridge, data_module, batch: int, n_frames: int = 256, lr: float = 1e-4, ema_decay: float = 0.999,
+                 clip_norm: float = 3.0, t_eps: float = 0.03, loss_scale: float = 4096.0, betas=(0.9, 0.999), eps: float = 1e-8):
+        self.dnn, self.bridge, self.dm = dnn, bridge, data_module
+        self.batch, self.n_frames = batch, n_frames
+        self.lr, self.ema_decay, self.clip_norm, self.t_eps, self.loss_scale = lr, ema_decay, clip_norm, t_eps, loss_scale
+        self.betas, self.eps = betas, eps
+        self.step_count = 0
+        self.lib = _lib.load()
+        dev = next(dnn.parameters()).device
+        if dev.type != "cuda":
+            raise RuntimeError("TrainStep needs the backbone on a CUDA device (there is no CPU path)")
+        self.device = dev
+        handle = C.c_void_p()
+        arch = dnn._arch()
+        check(self.lib.fdbm_plan_create_train(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create_train")
+        self.plan = handle
+        self._load_from_module()
+        p, g, e, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+        check(self.lib.fdbm_plan_buffers(self.plan, C.byref(p), C.byref(g), C.byref(e), C.byref(n)), "fdbm_plan_buffers")
+        self.numel = n.value
+        self.flat_params = torch.as_tensor(_DevBuf(p.value, n.value), device=dev)
+        self.flat_grads = torch.as_tensor(_DevBuf(g.value, n.value), device=dev)
+
+    def _load_from_module(self):
+        named = list(self.dnn.named_parameters())
+        refs = (_lib.TensorRef * len(named))()
+        keep = []
+        for i, (n, p) in enumerate(named):
+            d = p.detach().contiguous()
+            keep.append(d)
+            refs[i].name, refs[i].data, refs[i].numel = n.encode(), d.data_ptr(), d.numel()
+        check(self.lib.fdbm_plan_load_weights(self.plan, refs, len(named), current_stream()), "fdbm_plan_load_weights")
+        torch.cuda.current_stream().synchronize()
+
+    def close(self):
+        if self.plan is not None:
+            self.lib.fdbm_plan_destroy(self.plan)
+            self.plan = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- pieces -------------------------------------------------------------------------------------------------
+    def _slot(self, name: str):
+        off, n = C.c_int64(), C.c_int64()
+        check(self.lib.fdbm_plan_param_info(self.plan, name.encode(), C.byref(off), C.byref(n)), "fdbm_plan_param_info")
+        return off.value, n.value
+
+    def grads(self) -> Dict[str, torch.Tensor]:
+        """Parameter gradients of the last backward, by reference-style name (views into the flat buffer)."""
+        out = {}
+        for name, p in self.dnn.named_parameters():
+            off, n = self._slot(name)
+            out[name] = self.flat_grads[off:off + n].view(p.shape)
+        return out
+
+    def params(self) -> Dict[str, torch.Tensor]:
+        out = {}
+        for name, p in self.dnn.named_parameters():
+            off, n = self._slot(name)
+            out[name] = self.flat_params[off:off + n].view(p.shape)
+        return out
+
+    def sync_module(self):
+        """Copy the trained parameters back into the nn.Module (state_dict / checkpoint compatibility)."""
+        with torch.no_grad():
+            for name, p in self.dnn.named_parameters():
+                off, n = self._slot(name)
+                p.copy_(self.flat_params[off:off + n].view(p.shape))
+        self.dnn.invalidate_weights()
+
+    def sample_prior(self, x, y, t=None, z=None):
+        """fdbm/model.py:267-275."""
+        if z is None:
+            z = torch.randn_like(x)
+        if t is None:
+            t = torch.rand(x.shape[0], device=x.device) * (self.bridge.T - self.t_eps) + self.t_eps
+        mean, std = self.bridge.probability_path(x, y, t)
+        return t, mean, z, mean + std[:, None, None, None] * z
+
+    def forward(self, x_t, y, t):
+        out = torch.empty_like(x_t)
+        check(self.lib.fdbm_ncsnpp_forward(self.plan, ptr(x_t.contiguous()), ptr(y.contiguous()), ptr(t.float().contiguous()), ptr(out),
+                                           current_stream()), "fdbm_ncsnpp_forward")
+        return out
+
+    def backward(self, g_out: torch.Tensor, accumulate: bool = False):
+        g = (g_out * self.loss_scale).contiguous()
+        check(self.lib.fdbm_ncsnpp_backward(self.plan, ptr(torch.view_as_real(g)), self.loss_scale, int(accumulate), current_stream()),
+              "fdbm_ncsnpp_backward")
+        self._keep = g
+
+    def loss_and_backward(self, x, y, t=None, z=None) -> torch.Tensor:
+        """`_step` (model.py:258-265) + backward.  x, y: complex64 [B,1,257,T] clean / noisy compressed spectrograms."""
+        t, _, _, x_t = self.sample_prior(x, y, t, z)
+        self._x_t, self._y, self._t = x_t.contiguous(), y.contiguous(), t.float().contiguous()
+        D = self.forward(self._x_t, self._y, self._t)
+        D_leaf = D.detach().requires_grad_(True)
+        loss = hybrid_loss(D_leaf, x, self.dm)
+        (g,) = torch.autograd.grad(loss, D_leaf)
+        self.backward(g)
+        return loss.detach()
+
+    def optimizer_step(self):
+        """DDP gradient all-reduce (mean) over the flat buffer, then Adam + clip + EMA and the weight re-pack."""
+        import torch.distributed as dist
+        world = 1
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            world = dist.get_world_size()
+            dist.all_reduce(self.flat_grads)                      # sum over ranks; the mean's 1/world goes into grad_div
+        self.step_count += 1
+        check(self.lib.fdbm_plan_optimizer_step(self.plan, float(world), self.clip_norm, self.lr, self.betas[0], self.betas[1], self.eps,
+                                                self.step_count, self.ema_decay, current_stream()), "fdbm_plan_optimizer_step")
+
+    def training_step(self, x, y) -> torch.Tensor:
+        loss = self.loss_and_backward(x, y)
+        self.optimizer_step()
+        return loss

@@ -131,3 +131,98 @@ def test_adam_ema_step_matches_torch(lib):
     torch.cuda.synchronize()
     assert rel_l2(p, ref.detach().float()) < 1e-6
     assert rel_l2(ema, ema_ref.float()) < 1e-6
+
+
+# ------------------------------------------------------------------------------------------------
+# the whole training step: dL/dparams of the hybrid loss through the CUDA backbone vs torch autograd
+# through the CPU oracle (same weights, x, y, t, z)
+# ------------------------------------------------------------------------------------------------
+def _train_setup(B=2, T=64, seed=0):
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "oracle"))
+    import fdbm_oracle as O
+    from fdbm_b200 import BackboneRegistry, Bridge, SpecsDataModule
+    from fdbm_b200.training import TrainStep
+    cfg = O.NcsnppConfig()
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    net = BackboneRegistry.get_by_name("ncsnpp_v2")()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda()
+    g = torch.Generator().manual_seed(seed)
+    dm = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    # compressed spectrogram-like data: random phases, magnitudes with a wide dynamic range
+    def spec():
+        mag = torch.rand(B, 1, 257, T, generator=g) ** 3 * 0.6
+        ph = 2 * 3.14159265 * torch.rand(B, 1, 257, T, generator=g)
+        return torch.polar(mag, ph)
+    x, y = spec(), spec()
+    y = x + 0.5 * y
+    t = 0.03 + 0.97 * torch.rand(B, generator=g)
+    z = torch.view_as_complex(torch.randn(B, 1, 257, T, 2, generator=g))
+    bridge = Bridge("sb", N=5, sampler_type="ode_ei")
+    return O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z
+
+
+def test_training_step_gradients_match_autograd():
+    from fdbm_b200.training import hybrid_loss
+    O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z = _train_setup()
+    B, T = x.shape[0], x.shape[3]
+    # reference: the CPU oracle under torch autograd
+    sdr = {k: v.clone().requires_grad_(v.dim() > 0 and not k.endswith("all_modules.0.W")) for k, v in sd.items()}
+    mean, std = bridge.probability_path(x, y, t)
+    x_t = mean + std[:, None, None, None] * z
+    D_ref = O.ncsnpp_forward(sdr, cfg, x_t, y, t)
+    loss_ref = hybrid_loss(D_ref, x, dm)
+    loss_ref.backward()
+    # ours
+    ts = TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_scale=1024.0)
+    loss = ts.loss_and_backward(x.cuda(), y.cuda(), t.cuda(), z.cuda())
+    torch.cuda.synchronize()
+    grads = ts.grads()
+    print(f"loss ours {float(loss):.6f} ref {float(loss_ref):.6f}")
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref)) + 1e-3
+    num = den = 0.0
+    worst = []
+    for name, gr in sdr.items():
+        if gr.grad is None:
+            continue
+        got = grads[name].float().cpu()
+        e = float((got - gr.grad).pow(2).sum()); n = float(gr.grad.pow(2).sum())
+        num += e; den += n
+        worst.append(((e / max(n, 1e-30)) ** 0.5, name, n ** 0.5))
+    worst.sort(reverse=True)
+    for w in worst[:12]:
+        print(f"  rel {w[0]:.3e}  |g| {w[2]:.3e}  {w[1]}")
+    total = (num / den) ** 0.5
+    print(f"training step: global gradient rel L2 {total:.3e} over {len(worst)} tensors")
+    assert total < 3e-2
+    big = [w for w in worst if w[2] > 1e-3 * den ** 0.5]
+    assert max(w[0] for w in big) < 0.1, "a parameter tensor with a significant gradient is off"
+    ts.close()
+
+
+def test_training_step_updates_like_torch_adam():
+    """Two optimisation steps: parameters move exactly as torch.optim.Adam + clip_grad_norm_(3.0) would move them given
+    OUR gradients (the optimiser arithmetic), the EMA follows, and the loss of the next forward changes."""
+    O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z = _train_setup(seed=1)
+    B, T = x.shape[0], x.shape[3]
+    ts = TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_scale=1024.0, lr=1e-3)
+    ref = {n: torch.nn.Parameter(p.detach().clone().double()) for n, p in net.named_parameters()}
+    opt = torch.optim.Adam(list(ref.values()), lr=1e-3)
+    losses = []
+    for _ in range(2):
+        losses.append(float(ts.loss_and_backward(x.cuda(), y.cuda(), t.cuda(), z.cuda())))
+        g = {n: v.clone() for n, v in ts.grads().items()}
+        for n, p in ref.items():
+            p.grad = g[n].double()
+        torch.nn.utils.clip_grad_norm_(list(ref.values()), 3.0)
+        opt.step()
+        ts.optimizer_step()
+    torch.cuda.synchronize()
+    got = ts.params()
+    num = sum(float((got[n].double() - p.detach()).pow(2).sum()) for n, p in ref.items())
+    den = sum(float((p.detach() - sd[n].double().cuda()).pow(2).sum()) for n, p in ref.items())
+    print(f"losses {losses}, parameter update rel error {(num / den) ** 0.5:.3e}")
+    assert (num / den) ** 0.5 < 1e-3
+    assert losses[1] != losses[0]
+    ts.close()
