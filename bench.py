@@ -216,6 +216,109 @@ def hbm_kernel_leg(model, waves, dev, reps=20):
     return out
 
 
+def train_main(args):
+    """BASELINE.json configs[3]: the bridge training step (fdbm/model.py:258-275 + hybrid loss + Adam/EMA, train.py:161
+    clipping) on `--train-batch` synthetic 65 280-sample crops (exactly 256 frames, data_module.py:58) per GPU, DDP
+    gradient all-reduce over NCCL.  One step = sample_prior -> forward -> loss -> backward -> all-reduce -> Adam+EMA."""
+    import torch
+    import torch.distributed as dist
+    from fdbm_b200 import BackboneRegistry, Bridge, SpecsDataModule, _lib, sensitise_
+    from fdbm_b200.training import TrainStep
+    rank = int(os.environ.get("RANK", "0")); local_rank = int(os.environ.get("LOCAL_RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1"))
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.check(_lib.load().fdbm_check_device(), "fdbm_check_device")
+    B, crop = args.train_batch, 255 * 256
+    net = sensitise_(BackboneRegistry.get_by_name("ncsnpp_v2")(), seed=0).to(dev)
+    dm = SpecsDataModule(n_fft=512, hop_length=256, num_frames=256, window="sqrthann")
+    bridge = Bridge("sb", N=BRIDGE_STEPS, sampler_type="ode_ei")
+    ts = TrainStep(net, bridge, dm, batch=B, n_frames=256, loss_scale=1024.0)
+    global N_SAMPLES
+    N_SAMPLES = crop
+    noisy = synth_batch(B, dev, seed=4321 + 1000 * rank)
+    clean = synth_batch(B, dev, seed=8765 + 1000 * rank) * 0.5
+    noisy = clean + 0.3 * noisy
+    norm = noisy.abs().amax(1, keepdim=True)
+    X = dm.stft_compress(clean / norm, pad_mode="zero_pad", n_frames_out=256)
+    Y = dm.stft_compress(noisy / norm, pad_mode="zero_pad", n_frames_out=256)
+    hx = torch.empty(X.shape, dtype=X.dtype, pin_memory=True).copy_(X)
+    hy = torch.empty(Y.shape, dtype=Y.dtype, pin_memory=True).copy_(Y)
+    hloss = torch.empty(1, pin_memory=True)
+
+    def step_device():
+        return ts.training_step(X, Y)
+
+    def step_e2e():
+        x = hx.to(dev, non_blocking=True); y = hy.to(dev, non_blocking=True)
+        hloss.copy_(ts.training_step(x, y).reshape(1), non_blocking=True)
+
+    def timed(fn, steps):
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+        return float(ms.item())
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clocks = ClockSampler(local_rank)
+    if rank == 0:
+        clocks.start()
+    ms = timed(step_device, args.steps)
+    clock_info = clocks.stop() if rank == 0 else None
+    ms_e2e = timed(step_e2e, args.steps)
+    # phase split of one step (events around forward / backward / optimiser)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    torch.cuda.synchronize()
+    ev[0].record(); t, _, _, x_t = ts.sample_prior(X, Y); D = ts.forward(x_t.contiguous(), Y, t)
+    ev[1].record(); ts.loss_and_backward(X, Y)
+    ev[2].record(); ts.optimizer_step()
+    ev[3].record(); torch.cuda.synchronize()
+    lib = _lib.load()
+    if rank == 0:
+        samples = B * world * args.steps
+        value = samples / (ms * 1e-3)
+        gflop_step = 3 * 532.1 * B * world
+        peaks = {}
+        try:
+            peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+        except Exception:
+            pass
+        peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+        achieved = gflop_step / world / (ms / args.steps * 1e-3) / 1e3
+        print(json.dumps({
+            "metric": "bridge training step throughput (ncsnpp_v2, hybrid loss, Adam+EMA, DDP)", "value": value, "unit": "crops/s",
+            "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "bf16" if lib.fdbm_operand_is_bf16() else "fp16 (loss-scaled gradients, fp32 master weights)", "data": "synthetic",
+            "config": {"workload": f"train: {B} crops of 65 280 samples (256 frames) per GPU, ncsnpp_v2 65.6 M params, "
+                                   "data_prediction_hybrid loss, Adam lr 1e-4, clip 3.0, EMA 0.999", "global_batch": B * world,
+                       "parallelism": f"dp{world}", "l2": "activations kept for backward >> L2"},
+            "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": 2 * X.numel() * 8,
+                    "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
+            "gpu_launches": (lib.fdbm_plan_num_launches(ts.plan) + lib.fdbm_plan_num_backward_launches(ts.plan)) * args.steps,
+            "phase_ms": {"forward": ev[0].elapsed_time(ev[1]), "forward+loss+backward": ev[1].elapsed_time(ev[2]),
+                         "allreduce+adam+ema+repack": ev[2].elapsed_time(ev[3])},
+            "model_tflops_per_gpu": achieved,
+            "roofline": {"bound": "tensor", "kernel": "conv_igemm (fwd, dgrad) + conv_wgrad, whole step", "achieved": achieved, "peak": peak,
+                         "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                         "note": "algorithmic 3 x 532.1 GFLOP per crop (fwd + dgrad + wgrad) over the WHOLE step time"},
+            "plan_device_GiB": lib.fdbm_plan_device_bytes(ts.plan) / 2 ** 30, "clocks": clock_info}))
+    if world > 1:
+        dist.destroy_process_group()
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -225,13 +328,16 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "32")))
     ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive"],
-                    help="BASELINE.json configs[1] (default, the headline metric) or configs[2]")
+    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train"],
+                    help="BASELINE.json configs[1] (default, the headline metric), configs[2] or configs[3] (training step)")
+    ap.add_argument("--train-batch", type=int, default=16, help="training crops per GPU per step (configs[3]: 8 x 16)")
     ap.add_argument("--bridge-steps", type=int, default=5, help="configs[4]: sampling-step sweep 1/5/10/30")
     ap.add_argument("--seconds", type=float, default=4.0, help="configs[4]: utterance length (30 s long-form)")
     args = ap.parse_args()
     predictive = args.workload == "predictive"
     set_workload(args.seconds, args.bridge_steps, predictive)
+    if args.workload == "train":
+        return train_main(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

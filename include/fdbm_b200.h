@@ -169,6 +169,9 @@ int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float loss_scale, 
 int fdbm_plan_param_info(const fdbm_plan* plan, const char* name, int64_t* offset, int64_t* numel);
 int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads, float** ema, int64_t* numel);
 int fdbm_plan_num_backward_launches(const fdbm_plan* plan);
+/* measurement aid: backward of the last forward with a CUDA event pair around every recorded op; returns the op count */
+int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, float loss_scale, float* ms, int* kinds, int max_ops,
+                               void* stream);
 int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, float lr, float beta1, float beta2,
                              float eps, int step, float ema_decay, void* stream);
 
@@ -181,6 +184,7 @@ int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, f
 #define FDBM_OP_SKINNY 3   /* K or N <= 4 layers, FIR, packing            */
 #define FDBM_OP_ATTN   4   /* attention core                              */
 #define FDBM_OP_SMALL  5   /* time embedding, Dense_0 table               */
+#define FDBM_OP_WGRAD  6   /* tcgen05 weight-gradient kernel (training)   */
 int fdbm_plan_profile_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
                               float* ms, int* kinds, double* flops, int max_ops, void* stream);
 

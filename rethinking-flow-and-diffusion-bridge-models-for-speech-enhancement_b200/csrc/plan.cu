@@ -117,6 +117,7 @@ struct fdbm_plan {
   float* wgrad_ws = nullptr;           // split partials of the wgrad kernel
   int64_t wgrad_ws_bytes = 0;
   std::vector<std::function<int(cudaStream_t)>> bwd_ops;
+  std::vector<int> bwd_kind;
   std::vector<std::pair<void*, size_t>> zero_list;      // activation-gradient buffers cleared when backward starts
   const float* cur_gout = nullptr;     // dL/dD of the current backward call (loss-scaled), cplx [B,1,257,T]
   float cur_inv = 1.0f;                // 1 / loss scale
@@ -183,7 +184,7 @@ struct Builder {
 
   // ---------------- training: backward ops are recorded per forward composite ("group") and replayed in reverse
   typedef std::function<int(cudaStream_t)> Op;
-  std::vector<std::vector<Op>> groups;
+  std::vector<std::vector<std::pair<Op, int>>> groups;
   int64_t wd_off = 0;                  // running offset (bytes) into wpacked_d
   int64_t ws_need = 0;                 // largest wgrad workspace
   op_t *T1 = nullptr, *T2 = nullptr, *T3 = nullptr, *T4 = nullptr, *T5 = nullptr;     // shared backward scratch (16-bit)
@@ -192,7 +193,7 @@ struct Builder {
   const float* zero_bias = nullptr;
   bool train() const { return P->train; }
   void bgroup() { if (train()) groups.emplace_back(); }
-  void bop(Op f) { if (train() && !dry) groups.back().push_back(std::move(f)); }
+  void bop(Op f, int kind = FDBM_OP_NORM) { if (train() && !dry) groups.back().emplace_back(std::move(f), kind); }
   float* gp(int64_t off) const { return P->grads + off; }
   float* galloc(int64_t n) {
     float* g = alloc<float>(n);
@@ -216,7 +217,7 @@ struct Builder {
     c.seg[0] = seg(dy, Cdy, taps); c.n_seg = 1;
     c.wpack = wd; c.bias = zero_bias; c.residual = acc; c.scale = 1.0f;
     c.B = P->B; c.T = T; c.F = F; c.Cout = Cdx; c.out_f32 = acc; c.out_h16 = out16;
-    bop([=](cudaStream_t s) { return launch_conv_igemm(c, s); });
+    bop([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV);
   }
   void wgrad_op(WgradCall c, int64_t dw_off) {
     c.B = P->B;
@@ -226,7 +227,7 @@ struct Builder {
       WgradCall cc = c;
       cc.scale = plp->cur_inv; cc.dw = plp->grads + dw_off; cc.workspace = plp->wgrad_ws;
       return launch_conv_wgrad_ex(cc, s);
-    });
+    }, FDBM_OP_WGRAD);
   }
   // GroupNorm(+SiLU) backward of one normalised (possibly concatenated) tensor: g_a [B,P,Ctot] 16-bit -> x.grad +=
   void gn_bwd(const op_t* g_a, const Act& x1, const Act* x2, const float2* tab, const float2* stats, int64_t gw_off,
@@ -810,7 +811,7 @@ struct Builder {
     release(pyramid);
     if (train() && !dry) {
       for (auto g = groups.rbegin(); g != groups.rend(); ++g)
-        for (auto& f : *g) P->bwd_ops.push_back(std::move(f));
+        for (auto& f : *g) { P->bwd_ops.push_back(std::move(f.first)); P->bwd_kind.push_back(f.second); }
     }
     return FDBM_OK;
   }
@@ -905,6 +906,30 @@ extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float l
   for (auto& z : plan->zero_list) FDBM_CUDA(cudaMemsetAsync(z.first, 0, z.second, s));
   for (auto& f : plan->bwd_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
+}
+
+// measurement aid: the backward of the last forward, one CUDA event pair per recorded op (an op may be 1-5 launches)
+extern "C" int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, float loss_scale, float* ms, int* kinds, int max_ops,
+                                          void* stream) {
+  FDBM_REQUIRE(plan && g_out && ms && kinds && plan->train, "fdbm_plan_profile_backward: bad arguments");
+  const int n = static_cast<int>(plan->bwd_ops.size());
+  FDBM_REQUIRE(max_ops >= n, "fdbm_plan_profile_backward: need room for %d entries", n);
+  cudaStream_t s = as_stream(stream);
+  plan->cur_gout = g_out; plan->cur_inv = 1.0f / loss_scale;
+  FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
+  for (auto& z : plan->zero_list) FDBM_CUDA(cudaMemsetAsync(z.first, 0, z.second, s));
+  std::vector<cudaEvent_t> ev(n + 1);
+  for (auto& e : ev) FDBM_CUDA(cudaEventCreate(&e));
+  int rc = FDBM_OK;
+  FDBM_CUDA(cudaEventRecord(ev[0], s));
+  for (int i = 0; i < n && rc == FDBM_OK; ++i) {
+    rc = plan->bwd_ops[i](s);
+    if (rc == FDBM_OK && cudaEventRecord(ev[i + 1], s) != cudaSuccess) rc = FDBM_ECUDA;
+  }
+  if (rc == FDBM_OK && cudaStreamSynchronize(s) != cudaSuccess) rc = cuda_fail(cudaGetLastError(), "cudaStreamSynchronize", __FILE__, __LINE__);
+  for (int i = 0; i < n && rc == FDBM_OK; ++i) { cudaEventElapsedTime(&ms[i], ev[i], ev[i + 1]); kinds[i] = plan->bwd_kind[i]; }
+  for (auto& e : ev) cudaEventDestroy(e);
+  return rc == FDBM_OK ? n : rc;
 }
 
 extern "C" int fdbm_plan_param_info(const fdbm_plan* plan, const char* name, int64_t* offset, int64_t* numel) {

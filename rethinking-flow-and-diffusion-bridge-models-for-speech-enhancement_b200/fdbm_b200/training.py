@@ -46,6 +46,19 @@ def hybrid_loss(x_hat: torch.Tensor, x: torch.Tensor, data_module) -> torch.Tens
     return 70 * losses_mag + 30 * losses_ri - sisnr
 
 
+def allreduce_gradients_(flat_grads: torch.Tensor, group=None) -> int:
+    """DDP gradient exchange (fdbm/model.py trains under Lightning DDP): ONE all-reduce(sum) of the flat gradient buffer
+    (NCCL over NVLink on the GPU box, gloo in the CPU test).  Returns the world size; the mean's 1/world is folded into
+    the optimiser's `grad_div`, so the buffer keeps the SUM."""
+    import torch.distributed as dist
+    if not (dist.is_available() and dist.is_initialized()):
+        return 1
+    world = dist.get_world_size(group)
+    if world > 1:
+        dist.all_reduce(flat_grads, op=dist.ReduceOp.SUM, group=group)
+    return world
+
+
 class TrainStep:
     """One data-parallel optimisation step; `dnn` is the fdbm_b200 NCSNpp_v2 whose parameters are trained."""
 
@@ -157,11 +170,7 @@ class TrainStep:
 
     def optimizer_step(self):
         """DDP gradient all-reduce (mean) over the flat buffer, then Adam + clip + EMA and the weight re-pack."""
-        import torch.distributed as dist
-        world = 1
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            world = dist.get_world_size()
-            dist.all_reduce(self.flat_grads)                      # sum over ranks; the mean's 1/world goes into grad_div
+        world = allreduce_gradients_(self.flat_grads)            # sum over ranks; the mean's 1/world goes into grad_div
         self.step_count += 1
         check(self.lib.fdbm_plan_optimizer_step(self.plan, float(world), self.clip_norm, self.lr, self.betas[0], self.betas[1], self.eps,
                                                 self.step_count, self.ema_decay, current_stream()), "fdbm_plan_optimizer_step")

@@ -136,3 +136,35 @@ def test_utterance_sharding_and_gather_world2():
         assert p.exitcode == 0
     for _, order in res:
         assert order == [0.0, 1.0, 2.0, 3.0, 4.0]                             # every rank sees all utterances, in order
+
+
+def _allreduce_worker(rank, world, port, q):
+    import torch.distributed as dist
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))),
+                                    "rethinking-flow-and-diffusion-bridge-models-for-speech-enhancement_b200"))
+    from fdbm_b200.training import allreduce_gradients_
+    flat = torch.arange(10, dtype=torch.float32) * (rank + 1)               # rank r holds (r + 1) * [0..9]
+    w = allreduce_gradients_(flat)
+    q.put((rank, w, flat.tolist()))
+    dist.destroy_process_group()
+
+
+def test_ddp_gradient_allreduce_world2():
+    """The training step's DDP exchange: one all-reduce(sum) of the flat gradient buffer; 1/world goes into grad_div."""
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + os.getpid() % 2000
+    procs = [ctx.Process(target=_allreduce_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=120) for _ in procs]
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    for _, w, flat in res:
+        assert w == 2
+        assert flat == [3.0 * i for i in range(10)]
