@@ -168,6 +168,8 @@ int fdbm_plan_create_train(const fdbm_arch* arch, int batch, int n_frames, fdbm_
 int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float loss_scale, int accumulate, void* stream);
 int fdbm_plan_param_info(const fdbm_plan* plan, const char* name, int64_t* offset, int64_t* numel);
 int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads, float** ema, int64_t* numel);
+/* rebuild the packed 16-bit weights after the caller wrote the flat parameter buffer (DDP broadcast, checkpoint restore) */
+int fdbm_plan_repack_weights(fdbm_plan* plan, void* stream);
 int fdbm_plan_num_backward_launches(const fdbm_plan* plan);
 /* measurement aid: backward of the last forward with a CUDA event pair around every recorded op; returns the op count */
 int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, float loss_scale, float* ms, int* kinds, int max_ops,
@@ -265,7 +267,8 @@ int fdbm_fir_resample_h16(const void* in, int batch, int T, int F, int C, int mo
 int fdbm_attention_bwd(const void* qkv, int batch, int L, int C, const void* d_o, float* scratch, void* g_qkv, void* stream);
 /* Adam (model.py:101 configure_optimizers) with clip_grad_norm_ (gradient_clip_val) and the EMA update
  * (model.py:129-132) on flat fp32 buffers.  grads carry a factor grad_div (loss scale x world size) that is divided
- * out; a non-finite gradient norm skips the step.  scratch: one double. */
+ * out; a non-finite gradient norm skips the step.  scratch: 1025 doubles (the squared norm is reduced in a fixed
+ * order so that every DDP rank derives the same clipping coefficient). */
 int fdbm_adam_ema_step(float* params, const float* grads, float* m, float* v, float* ema, int64_t n, double* scratch,
                        float grad_div, float clip_norm, float lr, float beta1, float beta2, float eps, int step,
                        float ema_decay, void* stream);

@@ -950,6 +950,15 @@ extern "C" int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads,
   return FDBM_OK;
 }
 
+// re-derive the packed 16-bit weights (forward and dgrad packs) from the flat fp32 parameter buffer, e.g. after the caller
+// has written it directly (DDP parameter broadcast from rank 0, checkpoint restore)
+extern "C" int fdbm_plan_repack_weights(fdbm_plan* plan, void* stream) {
+  FDBM_REQUIRE(plan, "fdbm_plan_repack_weights: null plan");
+  if (!plan->weights_ready) { set_error("fdbm_plan_repack_weights: weights not loaded"); return FDBM_ESTATE; }
+  for (auto& f : plan->pack_ops) if (int rc = f(as_stream(stream))) return rc;
+  return FDBM_OK;
+}
+
 extern "C" int fdbm_plan_num_backward_launches(const fdbm_plan* plan) { return plan ? plan->n_bwd_launches : 0; }
 
 // Adam + clip + EMA on the flat buffers, then the packed 16-bit weights are rebuilt from the updated parameters.
@@ -963,7 +972,7 @@ extern "C" int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float c
     FDBM_CUDA(cudaMalloc(&plan->adam_m, n * sizeof(float)));
     FDBM_CUDA(cudaMalloc(&plan->adam_v, n * sizeof(float)));
     FDBM_CUDA(cudaMalloc(&plan->ema, n * sizeof(float)));
-    FDBM_CUDA(cudaMalloc(&plan->opt_scratch, sizeof(double)));
+    FDBM_CUDA(cudaMalloc(&plan->opt_scratch, 1025 * sizeof(double)));
     FDBM_CUDA(cudaMemsetAsync(plan->adam_m, 0, n * sizeof(float), s));
     FDBM_CUDA(cudaMemsetAsync(plan->adam_v, 0, n * sizeof(float), s));
     FDBM_CUDA(cudaMemcpyAsync(plan->ema, plan->params, n * sizeof(float), cudaMemcpyDeviceToDevice, s));

@@ -470,15 +470,28 @@ attention_bwd_kv_kernel(const op_t* __restrict__ q, int ld, const op_t* __restri
 // ------------------------------------------------------------------------------------------------
 // Optimiser: total squared gradient norm (double), then Adam with clipping and EMA on flat buffers.
 // ------------------------------------------------------------------------------------------------
+// deterministic (fixed grid, fixed summation order): every DDP rank must derive bit-identical clipping coefficients
+// from the bit-identical all-reduced gradients, or the replicas drift apart
+constexpr int SUMSQ_BLOCKS = 1024;
 __global__ void __launch_bounds__(256)
-sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ out) {
+sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partial) {
   __shared__ double red[256];
   double s = 0;
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) { const double v = g[i]; s += v * v; }
   red[threadIdx.x] = s;
   __syncthreads();
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
-  if (threadIdx.x == 0) atomicAdd(out, red[0]);
+  if (threadIdx.x == 0) partial[1 + blockIdx.x] = red[0];
+}
+__global__ void __launch_bounds__(256)
+sumsq_final_kernel(double* __restrict__ partial, int n_blocks) {
+  __shared__ double red[256];
+  double s = 0;
+  for (int i = threadIdx.x; i < n_blocks; i += 256) s += partial[1 + i];
+  red[threadIdx.x] = s;
+  __syncthreads();
+  for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
+  if (threadIdx.x == 0) partial[0] = red[0];
 }
 
 __global__ void __launch_bounds__(256)
@@ -626,8 +639,9 @@ int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, 
 int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const unsigned char* trainable, int64_t n,
                     double* sumsq_scratch, float grad_div, float clip, float lr, float beta1, float beta2, float eps, int step,
                     float ema_decay, cudaStream_t s) {
-  FDBM_CUDA(cudaMemsetAsync(sumsq_scratch, 0, sizeof(double), s));
-  sumsq_kernel<<<grid_for(n), 256, 0, s>>>(g, n, sumsq_scratch);
+  sumsq_kernel<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, sumsq_scratch);
+  FDBM_LAUNCH_CHECK();
+  sumsq_final_kernel<<<1, 256, 0, s>>>(sumsq_scratch, SUMSQ_BLOCKS);
   FDBM_LAUNCH_CHECK();
   const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
   adam_ema_kernel<<<grid_for(n), 256, 0, s>>>(p, g, m, v, ema, trainable, n, sumsq_scratch, grad_div, clip, lr, beta1, beta2, eps, bc1, bc2, ema_decay);

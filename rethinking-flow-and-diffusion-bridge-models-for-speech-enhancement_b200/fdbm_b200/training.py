@@ -84,6 +84,14 @@ class TrainStep:
         self.numel = n.value
         self.flat_params = torch.as_tensor(_DevBuf(p.value, n.value), device=dev)
         self.flat_grads = torch.as_tensor(_DevBuf(g.value, n.value), device=dev)
+        self.broadcast_parameters()
+
+    def broadcast_parameters(self, src: int = 0):
+        """DDP start-up semantics: every replica starts from rank `src`'s parameters."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
+            dist.broadcast(self.flat_params, src)
+            check(self.lib.fdbm_plan_repack_weights(self.plan, current_stream()), "fdbm_plan_repack_weights")
 
     def _load_from_module(self):
         named = list(self.dnn.named_parameters())

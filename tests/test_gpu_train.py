@@ -118,7 +118,7 @@ def test_adam_ema_step_matches_torch(lib):
     opt = torch.optim.Adam([ref], lr=1e-3)
     ema_ref = p0.clone().double()
     p = p0.clone().cuda(); m = torch.zeros(n, device="cuda"); v = torch.zeros(n, device="cuda"); ema = p0.clone().cuda()
-    scratch = torch.zeros(1, dtype=torch.float64, device="cuda")
+    scratch = torch.zeros(1025, dtype=torch.float64, device="cuda")
     scale = 64.0
     for step, gr in enumerate(grads, 1):
         ref.grad = gr.double().clone()
