@@ -177,6 +177,16 @@ int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, float loss_s
 int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, float lr, float beta1, float beta2,
                              float eps, int step, float ema_decay, void* stream);
 
+/* Loss head of the training step: BridgeModel._loss, "data_prediction_hybrid" (fdbm/model.py:187-218, pesq_weight 0):
+ *   L = 70 mean((|X|^0.3 - |X^|^0.3)^2) + 30 sum |X/|X|^0.7 - X^/|X^|^0.7|^2 / N - mean_b log10 SI-SNR(istft X, istft X^)
+ * with X = spec_back(x), X^ = spec_back(x_hat).  Forward and gradient in one call (no autograd):
+ *   x_hat, x  cplx [B,1,n_fft/2+1,T];  *loss fp32 (device);  g_out = loss_scale * dL/dx_hat, cplx like x_hat
+ * n_fft == 2*hop (sqrt-Hann, overlap-add envelope 1), exponent transform.  workspace: fdbm_hybrid_loss_workspace_bytes. */
+int64_t fdbm_hybrid_loss_workspace_bytes(int batch, int n_frames, int n_fft, int hop);
+int fdbm_hybrid_loss(const float* x_hat, const float* x, int batch, int n_frames, const float* window, int n_fft, int hop,
+                     int transform_type, float spec_factor, float abs_exponent, float loss_scale, void* workspace,
+                     float* loss, float* g_out, void* stream);
+
 /* Measurement aid for bench.py: run one forward launch by launch with a CUDA event pair around every
  * kernel.  ms[i] = device time, kinds[i] = FDBM_OP_*, flops[i] = algorithmic FLOPs (2*MAC, convolutions
  * only) of launch i.  Returns the number of launches (<= max_ops) or a negative error.  Synchronises. */

@@ -109,7 +109,7 @@ template <bool APPLY>
 __global__ void __launch_bounds__(256)
 gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   __shared__ float s_m1[32], s_m2[32];
-  __shared__ float s_red[APPLY ? 1 : 256 * 16];
+  __shared__ float s_red[256 * 16];
   const int b = blockIdx.y;
   const int G = min(a.C_tot / 4, 32), cpg = a.C_tot / G;
   if (APPLY) {
@@ -188,14 +188,7 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   }
   if (APPLY && !a.out_sums) return;
   // block reduction over the pixel lanes, then one double atomic per channel and block
-  float* red = APPLY ? nullptr : s_red;
-  if (APPLY) {
-    // reuse: warp-level is not enough (channels spread over lanes); go through global atomics per thread group
-#pragma unroll
-    for (int j = 0; j < 8; ++j)
-      if (pl < npl) atomicAdd(a.out_sums + static_cast<int64_t>(b) * a.C + c0 + j, static_cast<double>(s1[j]));
-    return;
-  }
+  float* red = s_red;
 #pragma unroll
   for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
   __syncthreads();
@@ -206,9 +199,13 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
       d1 += red[(l * cg8 + gg) * 16 + j];
       d2 += red[(l * cg8 + gg) * 16 + 8 + j];
     }
-    double* o = a.S + (static_cast<int64_t>(b) * a.C_tot + a.c_off + gg * 8 + j) * 2;
-    atomicAdd(o, d1);
-    atomicAdd(o + 1, d2);
+    if (APPLY) {
+      atomicAdd(a.out_sums + static_cast<int64_t>(b) * a.C + gg * 8 + j, d1);
+    } else {
+      double* o = a.S + (static_cast<int64_t>(b) * a.C_tot + a.c_off + gg * 8 + j) * 2;
+      atomicAdd(o, d1);
+      atomicAdd(o + 1, d2);
+    }
   }
 }
 

@@ -130,14 +130,15 @@ dense_bwd_w_kernel(const float* __restrict__ d, const float* __restrict__ act, i
     if (k == 0) db[r] += sb;
   }
 }
-// g_act[b][k] = sum_r d[b][r] * w[r][k]     (block per (k-chunk of 256, b))
+// g_act[b][k] = sum_r d[b][r] * w[r][k]     (block per (k-chunk of 256, b, row split); fp32 atomics into a zeroed buffer)
 __global__ void __launch_bounds__(256)
-dense_bwd_act_kernel(const float* __restrict__ d, const float* __restrict__ w, int K, int rows, float* __restrict__ g_act) {
+dense_bwd_act_kernel(const float* __restrict__ d, const float* __restrict__ w, int K, int rows, int rows_per_split, float* __restrict__ g_act) {
   const int b = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
   if (k >= K) return;
+  const int r0 = blockIdx.z * rows_per_split, r1 = min(rows, r0 + rows_per_split);
   float s = 0.f;
-  for (int r = 0; r < rows; ++r) s = fmaf(d[static_cast<int64_t>(b) * rows + r], w[static_cast<int64_t>(r) * K + k], s);
-  g_act[static_cast<int64_t>(b) * K + k] = s;
+  for (int r = r0; r < r1; ++r) s = fmaf(d[static_cast<int64_t>(b) * rows + r], w[static_cast<int64_t>(r) * K + k], s);
+  atomicAdd(g_act + static_cast<int64_t>(b) * K + k, s);
 }
 
 // time-embedding MLP backward (layerspp.py:32-41, ncsnpp_v2.py:108-113,252-270): one block per utterance recomputes the
@@ -229,7 +230,9 @@ int launch_dense_temb_bwd(const float* d, const float* act, const float* w, int 
                           int t_stride, float* dw1, float* db1, float* dw2, float* db2, cudaStream_t s) {
   dense_bwd_w_kernel<<<grid_for(static_cast<int64_t>(rows) * K), 256, 0, s>>>(d, act, B, K, rows, dw, db);
   FDBM_LAUNCH_CHECK();
-  dense_bwd_act_kernel<<<dim3(ceil_div(K, 256), B), 256, 0, s>>>(d, w, K, rows, g_act);
+  FDBM_CUDA(cudaMemsetAsync(g_act, 0, sizeof(float) * B * K, s));
+  const int splits = 32;
+  dense_bwd_act_kernel<<<dim3(ceil_div(K, 256), B, splits), 256, 0, s>>>(d, w, K, rows, ceil_div(rows, splits), g_act);
   FDBM_LAUNCH_CHECK();
   temb_bwd_kernel<<<B, 512, sizeof(float) * (2 * nf + 16 * nf), s>>>(t, fw, nf, w1, b1, w2, b2, t_stride, g_act, dw1, db1, dw2, db2);
   FDBM_LAUNCH_CHECK();

@@ -28,6 +28,7 @@ EXPORTS = [
     "fdbm_groupnorm_act_bwd", "fdbm_fir_resample_h16", "fdbm_attention_bwd", "fdbm_adam_ema_step",
     "fdbm_plan_create_train", "fdbm_ncsnpp_backward", "fdbm_plan_param_info", "fdbm_plan_buffers",
     "fdbm_plan_num_backward_launches", "fdbm_plan_optimizer_step", "fdbm_plan_profile_backward", "fdbm_plan_repack_weights",
+    "fdbm_hybrid_loss_workspace_bytes", "fdbm_hybrid_loss",
 ]
 
 
@@ -92,6 +93,8 @@ def load() -> C.CDLL:
         "fdbm_plan_buffers": (i, [p, C.POINTER(p), C.POINTER(p), C.POINTER(p), C.POINTER(i64)]),
         "fdbm_plan_num_backward_launches": (i, [p]),
         "fdbm_plan_repack_weights": (i, [p, p]),
+        "fdbm_hybrid_loss_workspace_bytes": (i64, [i, i, i, i]),
+        "fdbm_hybrid_loss": (i, [p, p, i, i, p, i, i, i, f, f, f, p, p, p, p]),
         "fdbm_plan_profile_backward": (i, [p, p, f, p, p, i, p]),
         "fdbm_plan_optimizer_step": (i, [p, f, f, f, f, f, f, i, f, p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),

@@ -8,8 +8,9 @@
     all-reduce(grads) / world                  torch.distributed (NCCL over NVLink), one flat 262 MB buffer
     Adam + clip + EMA                          fdbm_plan_optimizer_step on the flat buffers, weights re-packed
 
-The loss head (spec_back, powers, iSTFT, SI-SNR: < 0.01 % of the step's FLOPs) is evaluated with torch ops and
-torch autograd in this round; everything from dL/dD down to the parameter update runs in libfdbm_b200.
+The loss head and its gradient are one library call (fdbm_hybrid_loss: spectral terms, fused de-compress + iSTFT,
+SI-SNR, iSTFT adjoint through the fused STFT kernel); `hybrid_loss` below is the same loss in torch ops, kept as the
+differentiable reference the tests compare against.  Nothing in the step goes through torch autograd.
 Gradients of activations are 16-bit GEMM operands, so dL/dD is multiplied by `loss_scale` first (divided out of
 the fp32 parameter gradients); a non-finite gradient norm skips the update (GradScaler semantics).
 """
@@ -170,11 +171,28 @@ class TrainStep:
         t, _, _, x_t = self.sample_prior(x, y, t, z)
         self._x_t, self._y, self._t = x_t.contiguous(), y.contiguous(), t.float().contiguous()
         D = self.forward(self._x_t, self._y, self._t)
-        D_leaf = D.detach().requires_grad_(True)
-        loss = hybrid_loss(D_leaf, x, self.dm)
-        (g,) = torch.autograd.grad(loss, D_leaf)
-        self.backward(g)
-        return loss.detach()
+        loss, g = self.loss_and_grad(D, x)
+        check(self.lib.fdbm_ncsnpp_backward(self.plan, ptr(torch.view_as_real(g)), self.loss_scale, 0, current_stream()),
+              "fdbm_ncsnpp_backward")
+        self._keep = g
+        return loss
+
+    def loss_and_grad(self, D: torch.Tensor, x: torch.Tensor):
+        """fdbm/model.py:187-218 and its gradient w.r.t. D, already multiplied by the loss scale: one library call."""
+        from ._lib import FDBM_TRANSFORM
+        B, _, Fb, T = D.shape
+        dm = self.dm
+        need = self.lib.fdbm_hybrid_loss_workspace_bytes(B, T, dm.n_fft, dm.hop_length)
+        if getattr(self, "_loss_ws", None) is None or self._loss_ws.numel() < need:
+            self._loss_ws = torch.empty(need, dtype=torch.uint8, device=D.device)
+        loss = torch.empty((), device=D.device)
+        g = torch.empty_like(D)
+        D, x = D.contiguous(), x.contiguous()
+        check(self.lib.fdbm_hybrid_loss(ptr(torch.view_as_real(D)), ptr(torch.view_as_real(x)), B, T, ptr(dm._get_window(D)), dm.n_fft,
+                                        dm.hop_length, FDBM_TRANSFORM[dm.transform_type], float(dm.spec_factor), float(dm.spec_abs_exponent),
+                                        self.loss_scale, ptr(self._loss_ws), ptr(loss), ptr(torch.view_as_real(g)), current_stream()),
+              "fdbm_hybrid_loss")
+        return loss, g
 
     def optimizer_step(self):
         """DDP gradient all-reduce (mean) over the flat buffer, then Adam + clip + EMA and the weight re-pack."""

@@ -133,6 +133,42 @@ def test_adam_ema_step_matches_torch(lib):
     assert rel_l2(ema, ema_ref.float()) < 1e-6
 
 
+def test_hybrid_loss_and_gradient_match_torch_autograd(lib):
+    """fdbm_hybrid_loss (fdbm/model.py:187-218) vs the same loss in torch ops under autograd, fp64 on the CPU."""
+    from fdbm_b200 import SpecsDataModule
+    from fdbm_b200.training import hybrid_loss
+    g = torch.Generator().manual_seed(21)
+    B, T = 3, 64
+    def spec():
+        mag = torch.rand(B, 1, 257, T, generator=g) ** 3 * 0.6
+        ph = 2 * 3.14159265 * torch.rand(B, 1, 257, T, generator=g)
+        return torch.polar(mag, ph)
+    x = spec()
+    xh = x + 0.3 * spec()
+    xh[:, :, 256] = 0                                             # the backbone leaves the Nyquist row at exactly zero
+    dm = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    dm.window = dm.window.double()
+    leaf = xh.to(torch.complex128).requires_grad_(True)
+    ref = hybrid_loss(leaf, x.to(torch.complex128), dm)
+    (gref,) = torch.autograd.grad(ref, leaf)
+    gref[:, :, 256] = 0                                           # row 256 is dropped by the output layer's backward
+    dm32 = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    ws = torch.empty(lib.fdbm_hybrid_loss_workspace_bytes(B, T, 512, 256), dtype=torch.uint8, device="cuda")
+    loss = torch.empty((), device="cuda")
+    xd, xhd = x.cuda().contiguous(), xh.cuda().contiguous()
+    gout = torch.empty_like(xhd)
+    scale = 512.0
+    _check(lib, lib.fdbm_hybrid_loss(torch.view_as_real(xhd).data_ptr(), torch.view_as_real(xd).data_ptr(), B, T,
+                                     dm32._get_window(xd).data_ptr(), 512, 256, 0, 0.15, 0.5, scale, ws.data_ptr(), loss.data_ptr(),
+                                     torch.view_as_real(gout).data_ptr(), _stream()))
+    torch.cuda.synchronize()
+    got = (gout.cpu() / scale)
+    got[:, :, 256] = 0
+    print(f"hybrid loss ours {float(loss):.6f} ref {float(ref):.6f}; gradient rel L2 {rel_l2(torch.view_as_real(got), torch.view_as_real(gref.to(torch.complex64))):.3e}")
+    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)) + 1e-5
+    assert rel_l2(torch.view_as_real(got), torch.view_as_real(gref.to(torch.complex64))) < 1e-3
+
+
 # ------------------------------------------------------------------------------------------------
 # the whole training step: dL/dparams of the hybrid loss through the CUDA backbone vs torch autograd
 # through the CPU oracle (same weights, x, y, t, z)
