@@ -65,7 +65,10 @@ constexpr int kOperandIsBf16 = 0;
 __device__ __forceinline__ float sat16(float v) { return fminf(fmaxf(v, -65504.0f), 65504.0f); }
 __device__ __forceinline__ op_t f2op(float v) { return __float2half_rn(sat16(v)); }
 __device__ __forceinline__ float op2f(op_t v) { return __half2float(v); }
-__device__ __forceinline__ op2_t f2op2(float a, float b) { return __floats2half2_rn(sat16(a), sat16(b)); }
+__device__ __forceinline__ op2_t f2op2(float a, float b) {     // one F2FP.SATFINITE: round to nearest, clamp to +-65504
+  uint32_t r; asm("cvt.rn.satfinite.f16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return *reinterpret_cast<op2_t*>(&r);
+}
 __device__ __forceinline__ float2 op22f2(op2_t v) { return __half22float2(v); }
 __device__ __forceinline__ op2_t op2_tanh(op2_t v) {          // MUFU.TANH on both halves, max abs error ~2^-11
   uint32_t r; asm("tanh.approx.f16x2 %0, %1;" : "=r"(r) : "r"(*reinterpret_cast<uint32_t*>(&v)));

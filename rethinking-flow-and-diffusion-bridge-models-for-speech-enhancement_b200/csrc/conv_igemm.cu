@@ -106,7 +106,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
                   const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
-  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  // (offset arithmetic on the __shared__ array itself, so the compiler keeps the shared address space: LDS/STS, not generic LD/ST)
+  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_STAGES * MT * A_TILE_STRIDE;
   uint8_t* s_stage = sB + B_STAGES * B_TILE_BYTES;
@@ -290,43 +291,49 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             // halo rows / columns that lie inside the image (the rest is the convolution's zero padding)
             const int r_lo = tc[j].t0 == 0 ? 1 : 0, r_hi = min(HALO_T, p.T - tc[j].t0 + 1);
             const int c_lo = tc[j].f0 == 0 ? 1 : 0, c_hi = min(HALO_F, p.F - tc[j].f0 + 1);
+            const bool interior = r_lo == 0 && c_lo == 0 && r_hi == HALO_T && c_hi == HALO_F;   // warp-uniform
             uint8_t* tile = sA + (stage * MT + j) * A_TILE_STRIDE;
-            if (sg.act) {
-#pragma unroll 4
-              for (int px = p_lane; px < HALO_T * HALO_F; px += 16) {
-                const int hr = px / HALO_F, hc = px - hr * HALO_F;
-                if (hr < r_lo || hr >= r_hi || hc < c_lo || hc >= c_hi) continue;
-                uint4* slot = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
-                uint4 raw = *slot;
-                op2_t* h2 = reinterpret_cast<op2_t*>(&raw);
+            // four pixel slots per pass: all four 16-byte loads are in flight before the first is consumed, and the
+            // pass has no branches (a slot-at-a-time loop was one long dependent chain: ~200 cycles per slot)
+            constexpr int N_PASS = (HALO_T * HALO_F + 63) / 64;
+#pragma unroll 1
+            for (int pass = 0; pass < N_PASS; ++pass) {
+              uint4 raw[4];
+              uint4* slot[4];
+              bool on[4];
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  float2 v = op22f2(h2[u]);
+              for (int u = 0; u < 4; ++u) {
+                const int px = p_lane + 16 * (pass * 4 + u);
+                on[u] = px < HALO_T * HALO_F;
+                if (!interior) {
+                  const int hr = px / HALO_F, hc = px - hr * HALO_F;
+                  on[u] = on[u] && hr >= r_lo && hr < r_hi && hc >= c_lo && hc < c_hi;
+                }
+                slot[u] = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
+                raw[u] = on[u] ? *slot[u] : make_uint4(0u, 0u, 0u, 0u);
+              }
+#pragma unroll
+              for (int u = 0; u < 4; ++u) {
+                op2_t* h2 = reinterpret_cast<op2_t*>(&raw[u]);
+#pragma unroll
+                for (int w = 0; w < 4; ++w) {
+                  float2 v = op22f2(h2[w]);
+                  if (sg.act) {
 #ifdef FDBM_XF_EXACT
-                  v.x = 2.0f * fmaf(v.x, sc[j][2 * u], sh[j][2 * u]); v.y = 2.0f * fmaf(v.y, sc[j][2 * u + 1], sh[j][2 * u + 1]);
-                  h2[u] = f2op2(__fdividef(v.x, 1.0f + __expf(-v.x)), __fdividef(v.y, 1.0f + __expf(-v.y)));
+                    v.x = 2.0f * fmaf(v.x, sc[j][2 * w], sh[j][2 * w]); v.y = 2.0f * fmaf(v.y, sc[j][2 * w + 1], sh[j][2 * w + 1]);
+                    h2[w] = f2op2(__fdividef(v.x, 1.0f + __expf(-v.x)), __fdividef(v.y, 1.0f + __expf(-v.y)));
 #else
-                  const op2_t h = f2op2(fmaf(v.x, sc[j][2 * u], sh[j][2 * u]), fmaf(v.y, sc[j][2 * u + 1], sh[j][2 * u + 1]));
-                  h2[u] = __hfma2(h, op2_tanh(h), h);
+                    const op2_t h = f2op2(fmaf(v.x, sc[j][2 * w], sh[j][2 * w]), fmaf(v.y, sc[j][2 * w + 1], sh[j][2 * w + 1]));
+                    h2[w] = __hfma2(h, op2_tanh(h), h);
 #endif
+                  } else {
+                    h2[w] = f2op2(fmaf(v.x, sc[j][2 * w], sh[j][2 * w]), fmaf(v.y, sc[j][2 * w + 1], sh[j][2 * w + 1]));
+                  }
                 }
-                *slot = raw;
               }
-            } else {
-#pragma unroll 4
-              for (int px = p_lane; px < HALO_T * HALO_F; px += 16) {
-                const int hr = px / HALO_F, hc = px - hr * HALO_F;
-                if (hr < r_lo || hr >= r_hi || hc < c_lo || hc >= c_hi) continue;
-                uint4* slot = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
-                uint4 raw = *slot;
-                op2_t* h2 = reinterpret_cast<op2_t*>(&raw);
 #pragma unroll
-                for (int u = 0; u < 4; ++u) {
-                  float2 v = op22f2(h2[u]);
-                  h2[u] = f2op2(fmaf(v.x, sc[j][2 * u], sh[j][2 * u]), fmaf(v.y, sc[j][2 * u + 1], sh[j][2 * u + 1]));
-                }
-                *slot = raw;
-              }
+              for (int u = 0; u < 4; ++u)
+                if (on[u]) *slot[u] = raw[u];
             }
           }
           fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core's async proxy
@@ -420,37 +427,66 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           continue;
         }
-        // pixel coordinates of the 8 rows this lane handles in the transposed phase
-        int64_t poff[8];
+        // pixel rows of this lane in the transposed phase: 64-bit tile base + 32-bit row offsets
+        const bool full = tc.t0 + TILE_T <= p.T && tc.f0 + TILE_F <= p.F;       // warp-uniform
+        const int64_t tile_base = ((static_cast<int64_t>(tc.b) * p.T + tc.t0) * p.F + tc.f0) * p.Cout + n0 + cc * 4;
+        int roff[8];
         uint32_t okmask = 0;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = q * 32 + it * 4 + rsub;
-          const int t = tc.t0 + (m >> 3), f = tc.f0 + (m & 7);
-          const bool ok = t < p.T && f < p.F;
+          const bool ok = tc.t0 + (m >> 3) < p.T && tc.f0 + (m & 7) < p.F;
           okmask |= ok ? (1u << it) : 0u;
-          poff[it] = ((static_cast<int64_t>(tc.b) * p.T + (ok ? t : 0)) * p.F + (ok ? f : 0)) * p.Cout + n0 + cc * 4;
+          roff[it] = ok ? ((m >> 3) * p.F + (m & 7)) * p.Cout : 0;
         }
-        // bias (+ per-utterance FiLM bias) of all four 32-channel chunks: one exposed latency per M-tile
-        float4 bv[BN / 32];
+        const float* res_p = p.residual ? p.residual + tile_base : nullptr;
+        float* of_p = p.out_f32 ? p.out_f32 + tile_base : nullptr;
+        op_t* oh_p = p.out_h16 ? p.out_h16 + tile_base : nullptr;
+        if (res_p) {
+          // pull the NEXT tile's residual rows (fp32, 512 B per pixel) into L2 now: by the time its epilogue runs,
+          // the register loads below see L2 latency instead of HBM latency
+          int nmi = ct * MT + j + 1, nblk_n = nblk;
+          if (j + 1 == MT) {
+            const int nitem = item + gridDim.x;
+            nmi = nitem < p.n_items ? (nitem / p.n_nblocks) * MT : p.n_mtiles;
+            nblk_n = nitem % p.n_nblocks;
+          }
+          const TileCoord nt = decode_tile(p, nmi);
+          const int t = nt.t0 + (et >> 3), f = nt.f0 + (et & 7);
+          if (nt.valid && t < p.T && f < p.F) {
+            const float* pr = p.residual + ((static_cast<int64_t>(nt.b) * p.T + t) * p.F + f) * p.Cout + nblk_n * BN;
+#pragma unroll
+            for (int u = 0; u < 4; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + u * 32));
+          }
+        }
+        // bias (+ per-utterance FiLM bias) of all four 32-channel chunks, pre-multiplied by the output scale
+        const float2 sc2 = make_float2(p.scale, p.scale);
+        float2 bs_lo[BN / 32], bs_hi[BN / 32];
 #pragma unroll
         for (int ch = 0; ch < BN / 32; ++ch) {
-          bv[ch] = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32 + cc * 4));
+          float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32 + cc * 4));
           if (p.bias_b) {
             const float4 e = __ldg(reinterpret_cast<const float4*>(p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + n0 + ch * 32 + cc * 4));
-            bv[ch].x += e.x; bv[ch].y += e.y; bv[ch].z += e.z; bv[ch].w += e.w;
+            bv.x += e.x; bv.y += e.y; bv.z += e.z; bv.w += e.w;
           }
+          bs_lo[ch] = __fmul2_rn(make_float2(bv.x, bv.y), sc2); bs_hi[ch] = __fmul2_rn(make_float2(bv.z, bv.w), sc2);
         }
+        // residual rows: register double buffer, chunk ch+1 is requested before chunk ch is processed
+        float4 res[8];
+        auto load_res = [&](float4 (&r)[8], int ch) {
+          if (full) {
 #pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          // residual rows of this chunk: eight independent 16-byte loads in flight while TMEM is read
-          float4 res[8];
-          if (p.residual) {
+            for (int it = 0; it < 8; ++it) r[it] = __ldg(reinterpret_cast<const float4*>(res_p + roff[it] + ch * 32));
+          } else {
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-              res[it] = (okmask >> it) & 1 ? __ldg(reinterpret_cast<const float4*>(p.residual + poff[it] + ch * 32))
+              r[it] = ((okmask >> it) & 1) ? __ldg(reinterpret_cast<const float4*>(res_p + roff[it] + ch * 32))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
+        };
+        if (res_p) load_res(res, 0);
+#pragma unroll
+        for (int ch = 0; ch < BN / 32; ++ch) {
           float4 cw[4], cbias = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (COMB) {                               // Combine: 1x1 conv of the <=4-channel input pyramid
             const int c = n0 + ch * 32 + cc * 4;
@@ -464,6 +500,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
+          float4 res_nxt[8];
+          if (res_p && ch + 1 < BN / 32) load_res(res_nxt, ch + 1);
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -473,33 +511,57 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           // packed fp32x2 arithmetic (FFMA2 / FADD2): the single epilogue warp of an SM sub-partition is bound by
           // its own instruction latencies, so halving the instruction count is what speeds it up.
           // out = acc * scale + (bias * scale) (+ residual * scale)
-          float2 ssum_lo = make_float2(0.f, 0.f), ssum_hi = ssum_lo, ssq_lo = ssum_lo, ssq_hi = ssum_lo;
-          const float2 sc2 = make_float2(p.scale, p.scale);
-          const float2 bs_lo = __fmul2_rn(make_float2(bv[ch].x, bv[ch].y), sc2), bs_hi = __fmul2_rn(make_float2(bv[ch].z, bv[ch].w), sc2);
+          float2 o_lo[8], o_hi[8];
+#pragma unroll
+          for (int it = 0; it < 8; ++it) {                  // eight independent shared-memory reads in flight
+            const int rr = it * 4 + rsub;                   // pixel row inside this warp's quadrant
+            const float4 a = stage[rr * 8 + (cc ^ (rr & 7))];
+            o_lo[it] = make_float2(a.x, a.y); o_hi[it] = make_float2(a.z, a.w);
+          }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            const int rr = it * 4 + rsub;                 // pixel row inside this warp's quadrant
-            const float4 a = stage[rr * 8 + (cc ^ (rr & 7))];
-            float2 o_lo = __ffma2_rn(make_float2(a.x, a.y), sc2, bs_lo), o_hi = __ffma2_rn(make_float2(a.z, a.w), sc2, bs_hi);
-            if (p.residual) {
-              o_lo = __ffma2_rn(make_float2(res[it].x, res[it].y), sc2, o_lo);
-              o_hi = __ffma2_rn(make_float2(res[it].z, res[it].w), sc2, o_hi);
+            o_lo[it] = __ffma2_rn(o_lo[it], sc2, bs_lo[ch]); o_hi[it] = __ffma2_rn(o_hi[it], sc2, bs_hi[ch]);
+            if (res_p) {
+              o_lo[it] = __ffma2_rn(make_float2(res[it].x, res[it].y), sc2, o_lo[it]);
+              o_hi[it] = __ffma2_rn(make_float2(res[it].z, res[it].w), sc2, o_hi[it]);
             }
-            if (COMB && ((okmask >> it) & 1)) {
+            if (COMB && (full || ((okmask >> it) & 1))) {
               const int m = q * 32 + it * 4 + rsub;
               const float* pq = p.comb_pyr + ((static_cast<int64_t>(tc.b) * p.T + tc.t0 + (m >> 3)) * p.F + tc.f0 + (m & 7)) * p.comb_C;
               const float p0 = __ldg(pq), p1 = p.comb_C > 1 ? __ldg(pq + 1) : 0.f, p2 = p.comb_C > 2 ? __ldg(pq + 2) : 0.f,
                           p3 = p.comb_C > 3 ? __ldg(pq + 3) : 0.f;
-              o_lo.x += cbias.x + cw[0].x * p0 + cw[0].y * p1 + cw[0].z * p2 + cw[0].w * p3;
-              o_lo.y += cbias.y + cw[1].x * p0 + cw[1].y * p1 + cw[1].z * p2 + cw[1].w * p3;
-              o_hi.x += cbias.z + cw[2].x * p0 + cw[2].y * p1 + cw[2].z * p2 + cw[2].w * p3;
-              o_hi.y += cbias.w + cw[3].x * p0 + cw[3].y * p1 + cw[3].z * p2 + cw[3].w * p3;
+              o_lo[it].x += cbias.x + cw[0].x * p0 + cw[0].y * p1 + cw[0].z * p2 + cw[0].w * p3;
+              o_lo[it].y += cbias.y + cw[1].x * p0 + cw[1].y * p1 + cw[1].z * p2 + cw[1].w * p3;
+              o_hi[it].x += cbias.z + cw[2].x * p0 + cw[2].y * p1 + cw[2].z * p2 + cw[2].w * p3;
+              o_hi[it].y += cbias.w + cw[3].x * p0 + cw[3].y * p1 + cw[3].z * p2 + cw[3].w * p3;
             }
-            if ((okmask >> it) & 1) {
-              if (p.out_f32) *reinterpret_cast<float4*>(p.out_f32 + poff[it] + ch * 32) = make_float4(o_lo.x, o_lo.y, o_hi.x, o_hi.y);
-              if (p.out_h16) *reinterpret_cast<uint2*>(p.out_h16 + poff[it] + ch * 32) = make_uint2(pack_op2(o_lo.x, o_lo.y), pack_op2(o_hi.x, o_hi.y));
-              ssum_lo = __fadd2_rn(ssum_lo, o_lo); ssum_hi = __fadd2_rn(ssum_hi, o_hi);
-              ssq_lo = __ffma2_rn(o_lo, o_lo, ssq_lo); ssq_hi = __ffma2_rn(o_hi, o_hi, ssq_hi);
+          }
+          float2 ssum_lo = make_float2(0.f, 0.f), ssum_hi = ssum_lo, ssq_lo = ssum_lo, ssq_hi = ssum_lo;
+          if (full) {                                       // whole tile inside the image: no per-row predicates
+            if (of_p) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                *reinterpret_cast<float4*>(of_p + roff[it] + ch * 32) = make_float4(o_lo[it].x, o_lo[it].y, o_hi[it].x, o_hi[it].y);
+            }
+            if (oh_p) {
+#pragma unroll
+              for (int it = 0; it < 8; ++it)
+                *reinterpret_cast<uint2*>(oh_p + roff[it] + ch * 32) = make_uint2(pack_op2(o_lo[it].x, o_lo[it].y), pack_op2(o_hi[it].x, o_hi[it].y));
+            }
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              ssum_lo = __fadd2_rn(ssum_lo, o_lo[it]); ssum_hi = __fadd2_rn(ssum_hi, o_hi[it]);
+              ssq_lo = __ffma2_rn(o_lo[it], o_lo[it], ssq_lo); ssq_hi = __ffma2_rn(o_hi[it], o_hi[it], ssq_hi);
+            }
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) {
+              if ((okmask >> it) & 1) {
+                if (of_p) *reinterpret_cast<float4*>(of_p + roff[it] + ch * 32) = make_float4(o_lo[it].x, o_lo[it].y, o_hi[it].x, o_hi[it].y);
+                if (oh_p) *reinterpret_cast<uint2*>(oh_p + roff[it] + ch * 32) = make_uint2(pack_op2(o_lo[it].x, o_lo[it].y), pack_op2(o_hi[it].x, o_hi[it].y));
+                ssum_lo = __fadd2_rn(ssum_lo, o_lo[it]); ssum_hi = __fadd2_rn(ssum_hi, o_hi[it]);
+                ssq_lo = __ffma2_rn(o_lo[it], o_lo[it], ssq_lo); ssq_hi = __ffma2_rn(o_hi[it], o_hi[it], ssq_hi);
+              }
             }
           }
           float4 ssum = make_float4(ssum_lo.x, ssum_lo.y, ssum_hi.x, ssum_hi.y), ssq = make_float4(ssq_lo.x, ssq_lo.y, ssq_hi.x, ssq_hi.y);
@@ -518,6 +580,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
           __syncwarp();                                   // staging tile is rewritten by the next chunk
+          if (res_p && ch + 1 < BN / 32) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) res[it] = res_nxt[it];
+          }
         }
         if (do_stats) {                                   // block-uniform
           asm volatile("bar.sync 1, 128;" ::: "memory");
