@@ -179,13 +179,22 @@ def hbm_kernel_leg(model, waves, dev, reps=20):
     y = waves / waves.abs().amax(1, keepdim=True)
 
     def timeit(fn):
+        # `reps` back-to-back launches captured in one CUDA graph: the kernels are tens of microseconds long, so
+        # launching them from Python would time the host, not the kernel
         for _ in range(3):
             fn()
+        torch.cuda.synchronize()
+        side = torch.cuda.Stream()
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.stream(side):
+            with torch.cuda.graph(g, stream=side):
+                for _ in range(reps):
+                    fn()
+        g.replay()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
-            fn()
+        g.replay()
         e1.record()
         torch.cuda.synchronize()
         return e0.elapsed_time(e1) / reps
