@@ -224,6 +224,13 @@ int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1,
                        const float* gamma, const float* beta, int batch, int T, int F,
                        int silu, int mode, void* act_out, void* raw_out, void* stream);
 
+/* The same pass for the resampling blocks (mode 1 = down x2, 2 = up x2) from the 16-bit copies of the residual
+ * stream: act_out = FIR(SiLU(GN(cat(src1,src2)))), raw_out = FIR(cat(src1,src2)), both h16 [B,T',F',C1+C2].
+ * src1/src2 h16 NTFC, sums double [B,C,2] of the sources, `table` scratch of 2*B*(C1+C2) floats. */
+int fdbm_gn_resample_h16(const void* src1, const double* sums1, int C1, const void* src2, const double* sums2, int C2,
+                         const float* gamma, const float* beta, float* table, int batch, int T, int F, int mode,
+                         void* act_out, void* raw_out, void* stream);
+
 /* Implicit-GEMM convolution on tcgen05 tensor cores (TMA-fed, TMEM accumulators):
  *   out[b,t,f,:] = scale * ( sum_taps W_tap . in1[b,t+dt,f+df,:]  (+ W2 . in2[b,t,f,:])
  *                            + bias (+ bias_b[b,:]) (+ residual[b,t,f,:]) )

@@ -210,6 +210,172 @@ groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ s
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// gn_resample16: the resampling ResnetBlocks' input pass (layerspp.py:242-257 with up/down):
+//   act_out = FIR(SiLU(GroupNorm(cat(src1, src2)))),  raw_out = FIR(cat(src1, src2))   (x2 down or x2 up)
+// from the 16-bit copies of the residual stream and the (scale, shift) table of gn_finalize.
+// A thread owns 4 channels and a 2-column strip and walks down the frame axis keeping the horizontally
+// filtered rows it still needs in registers, so every input pixel is fetched (and activated) by 1.5 (down)
+// or 2 (up) threads instead of 16 / 4 and the pass is bound by its HBM bytes.  SiLU(y) = h + h tanh(h),
+// h = y/2, in packed 16-bit (one MUFU per element) -- the same arithmetic as the convolution's
+// normalise-on-load path.
+// ------------------------------------------------------------------------------------------------
+constexpr int RS_ROWS = 16;       // output rows (down) / input rows (up) per thread
+
+template <int MODE>
+__global__ void __launch_bounds__(256)
+gn_resample16_kernel(const op_t* __restrict__ src1, int C1, const op_t* __restrict__ src2, int C2,
+                     const float2* __restrict__ tab, int B, int T, int F, op_t* __restrict__ act_out,
+                     op_t* __restrict__ raw_out) {
+  const int C = C1 + C2, C4 = C / 4;
+  const int To = MODE == 1 ? T / 2 : T * 2, Fo = MODE == 1 ? F / 2 : F * 2;
+  const int nstrip = MODE == 1 ? (Fo + 1) / 2 : (F + 1) / 2;
+  const int nrows = MODE == 1 ? To : T;
+  const int nchunk = (nrows + RS_ROWS - 1) / RS_ROWS;
+  int64_t idx = blockIdx.x * 256ll + threadIdx.x;
+  if (idx >= static_cast<int64_t>(B) * nchunk * nstrip * C4) return;
+  const int cg = static_cast<int>(idx % C4); idx /= C4;
+  const int strip = static_cast<int>(idx % nstrip); idx /= nstrip;
+  const int chunk = static_cast<int>(idx % nchunk);
+  const int b = static_cast<int>(idx / nchunk);
+  const int c0 = cg * 4;
+  const bool from2 = c0 >= C1;
+  const int Cs = from2 ? C2 : C1;
+  const op_t* sp = (from2 ? src2 : src1) + static_cast<int64_t>(b) * T * F * Cs + (from2 ? c0 - C1 : c0);
+  float sc[4], sh[4];
+  {
+    const float4* tp = reinterpret_cast<const float4*>(tab + static_cast<int64_t>(b) * C + c0);
+    const float4 e0 = __ldg(tp), e1 = __ldg(tp + 1);
+    sc[0] = 0.5f * e0.x; sh[0] = 0.5f * e0.y; sc[1] = 0.5f * e0.z; sh[1] = 0.5f * e0.w;
+    sc[2] = 0.5f * e1.x; sh[2] = 0.5f * e1.y; sc[3] = 0.5f * e1.z; sh[3] = 0.5f * e1.w;
+  }
+  // one pixel: raw values and SiLU(GroupNorm(.)) of this thread's 4 channels; zeros outside the image
+  auto load_px = [&](int t, int f, float (&a)[4], float (&r)[4]) {
+    if (t < 0 || t >= T || f < 0 || f >= F) {
+#pragma unroll
+      for (int j = 0; j < 4; ++j) { a[j] = 0.f; r[j] = 0.f; }
+      return;
+    }
+    const uint2 rawv = __ldg(reinterpret_cast<const uint2*>(sp + (static_cast<int64_t>(t) * F + f) * Cs));
+    const op2_t* h2 = reinterpret_cast<const op2_t*>(&rawv);
+#pragma unroll
+    for (int w = 0; w < 2; ++w) {
+      const float2 v = op22f2(h2[w]);
+      r[2 * w] = v.x; r[2 * w + 1] = v.y;
+      const op2_t h = f2op2(fmaf(v.x, sc[2 * w], sh[2 * w]), fmaf(v.y, sc[2 * w + 1], sh[2 * w + 1]));
+      const float2 av = op22f2(__hfma2(h, op2_tanh(h), h));
+      a[2 * w] = av.x; a[2 * w + 1] = av.y;
+    }
+  };
+  auto store_px = [&](int to, int fo, const float (&a)[4], const float (&r)[4]) {
+    if (fo >= Fo) return;
+    const int64_t o = ((static_cast<int64_t>(b) * To + to) * Fo + fo) * C + c0;
+    *reinterpret_cast<uint2*>(act_out + o) = make_uint2(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]));
+    *reinterpret_cast<uint2*>(raw_out + o) = make_uint2(pack_op2(r[0], r[1]), pack_op2(r[2], r[3]));
+  };
+
+  if (MODE == 1) {
+    // down: o[i] = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8 per axis; output columns fo0, fo0 + 1
+    const int fo0 = 2 * strip, fi0 = 2 * fo0 - 1;
+    // horizontally filtered row t -> ha/hr[2 output columns][4 channels]
+    auto hrow = [&](int t, float (&ha)[2][4], float (&hr)[2][4]) {
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { ha[j][c] = 0.f; hr[j][c] = 0.f; }
+      if (t < 0 || t >= T) return;
+#pragma unroll
+      for (int k = 0; k < 6; ++k) {
+        float a[4], r[4];
+        load_px(t, fi0 + k, a, r);
+        if (k < 4) {
+          const float w = (k == 0 || k == 3) ? 0.125f : 0.375f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { ha[0][c] = fmaf(w, a[c], ha[0][c]); hr[0][c] = fmaf(w, r[c], hr[0][c]); }
+        }
+        if (k >= 2) {
+          const float w = (k == 2 || k == 5) ? 0.125f : 0.375f;
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { ha[1][c] = fmaf(w, a[c], ha[1][c]); hr[1][c] = fmaf(w, r[c], hr[1][c]); }
+        }
+      }
+    };
+    const int to0 = chunk * RS_ROWS, to1 = min(To, to0 + RS_ROWS);
+    float ca[2][4], cr[2][4], na[2][4], nr[2][4], ha[2][4], hr[2][4];
+    hrow(2 * to0 - 1, ha, hr);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { ca[j][c] = 0.125f * ha[j][c]; cr[j][c] = 0.125f * hr[j][c]; }
+    hrow(2 * to0, ha, hr);
+#pragma unroll
+    for (int j = 0; j < 2; ++j)
+#pragma unroll
+      for (int c = 0; c < 4; ++c) { ca[j][c] = fmaf(0.375f, ha[j][c], ca[j][c]); cr[j][c] = fmaf(0.375f, hr[j][c], cr[j][c]); }
+#pragma unroll 1
+    for (int to = to0; to < to1; ++to) {
+      hrow(2 * to + 1, ha, hr);
+#pragma unroll
+      for (int j = 0; j < 2; ++j)
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ca[j][c] = fmaf(0.375f, ha[j][c], ca[j][c]); cr[j][c] = fmaf(0.375f, hr[j][c], cr[j][c]);
+          na[j][c] = 0.125f * ha[j][c]; nr[j][c] = 0.125f * hr[j][c];
+        }
+      hrow(2 * to + 2, ha, hr);
+#pragma unroll
+      for (int j = 0; j < 2; ++j) {
+#pragma unroll
+        for (int c = 0; c < 4; ++c) {
+          ca[j][c] = fmaf(0.125f, ha[j][c], ca[j][c]); cr[j][c] = fmaf(0.125f, hr[j][c], cr[j][c]);
+          na[j][c] = fmaf(0.375f, ha[j][c], na[j][c]); nr[j][c] = fmaf(0.375f, hr[j][c], nr[j][c]);
+        }
+        store_px(to, fo0 + j, ca[j], cr[j]);
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { ca[j][c] = na[j][c]; cr[j][c] = nr[j][c]; }
+      }
+    }
+  } else {
+    // up: o[2i] = (x[i-1] + 3 x[i]) / 4, o[2i+1] = (3 x[i] + x[i+1]) / 4 per axis; input columns f0, f0 + 1 -> 4 output columns
+    const int f0 = 2 * strip;
+    auto hrow = [&](int t, float (&ha)[4][4], float (&hr)[4][4]) {
+      float a[4][4], r[4][4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) load_px(t, f0 - 1 + k, a[k], r[k]);
+#pragma unroll
+      for (int c = 0; c < 4; ++c) {
+        ha[0][c] = 0.25f * a[0][c] + 0.75f * a[1][c]; hr[0][c] = 0.25f * r[0][c] + 0.75f * r[1][c];
+        ha[1][c] = 0.75f * a[1][c] + 0.25f * a[2][c]; hr[1][c] = 0.75f * r[1][c] + 0.25f * r[2][c];
+        ha[2][c] = 0.25f * a[1][c] + 0.75f * a[2][c]; hr[2][c] = 0.25f * r[1][c] + 0.75f * r[2][c];
+        ha[3][c] = 0.75f * a[2][c] + 0.25f * a[3][c]; hr[3][c] = 0.75f * r[2][c] + 0.25f * r[3][c];
+      }
+    };
+    const int i0 = chunk * RS_ROWS, i1 = min(T, i0 + RS_ROWS);
+    float pa[4][4], pr[4][4], qa[4][4], qr[4][4];
+    hrow(i0 - 1, pa, pr);
+#pragma unroll 1
+    for (int i = i0; i <= i1; ++i) {
+      hrow(i, qa, qr);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        float oa[4], orr[4];
+        if (i > i0) {                                    // odd output row of the previous input row
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { oa[c] = 0.75f * pa[k][c] + 0.25f * qa[k][c]; orr[c] = 0.75f * pr[k][c] + 0.25f * qr[k][c]; }
+          store_px(2 * i - 1, 2 * f0 + k, oa, orr);
+        }
+        if (i < i1) {                                    // even output row of this input row
+#pragma unroll
+          for (int c = 0; c < 4; ++c) { oa[c] = 0.25f * pa[k][c] + 0.75f * qa[k][c]; orr[c] = 0.25f * pr[k][c] + 0.75f * qr[k][c]; }
+          store_px(2 * i, 2 * f0 + k, oa, orr);
+        }
+#pragma unroll
+        for (int c = 0; c < 4; ++c) { pa[k][c] = qa[k][c]; pr[k][c] = qr[k][c]; }
+      }
+    }
+  }
+}
+
 // (scale, shift) per (utterance, channel) of a GroupNorm over the concatenation of up to two tensors:
 // scale = gamma * rstd(group), shift = beta - mean(group) * scale.  Consumed by the convolution's
 // normalise-on-load stage.  One block per utterance.
@@ -251,6 +417,23 @@ int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2,
   const int C = C1 + C2;
   FDBM_REQUIRE(C % std::min(C / 4, 32) == 0 && C >= 4, "gn_finalize: unsupported channels %d+%d", C1, C2);
   gn_finalize_kernel<<<B, 256, 0, s>>>(sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+int launch_gn_resample16(const op_t* src1, int C1, const op_t* src2, int C2, const float2* tab, int B, int T, int F,
+                         int mode, op_t* act_out, op_t* raw_out, cudaStream_t s) {
+  const int C = C1 + C2;
+  FDBM_REQUIRE(src1 && tab && act_out && raw_out && C1 % 4 == 0 && C2 % 4 == 0 && (C2 == 0) == (src2 == nullptr),
+               "gn_resample16: bad arguments (channels %d+%d)", C1, C2);
+  FDBM_REQUIRE(mode == 1 || mode == 2, "gn_resample16: mode must be 1 (down) or 2 (up)");
+  FDBM_REQUIRE(mode != 1 || (T % 2 == 0 && F % 2 == 0), "gn_resample16: down-sampling needs even T, F");
+  const int nstrip = mode == 1 ? (F / 2 + 1) / 2 : (F + 1) / 2;
+  const int nrows = mode == 1 ? T / 2 : T;
+  const int64_t total = static_cast<int64_t>(B) * ceil_div(nrows, RS_ROWS) * nstrip * (C / 4);
+  const unsigned grid = static_cast<unsigned>(ceil_div64(total, 256));
+  if (mode == 1) gn_resample16_kernel<1><<<grid, 256, 0, s>>>(src1, C1, src2, C2, tab, B, T, F, act_out, raw_out);
+  else gn_resample16_kernel<2><<<grid, 256, 0, s>>>(src1, C1, src2, C2, tab, B, T, F, act_out, raw_out);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -339,4 +522,17 @@ extern "C" int fdbm_groupnorm_act(const float* src1, const double* sums1, int C1
   return launch_groupnorm_act(src1, 0, sums1, C1, src2, sums2, C2, gamma, beta, batch, T, F, silu, mode,
                               reinterpret_cast<op_t*>(act_out), reinterpret_cast<op_t*>(raw_out),
                               as_stream(stream));
+}
+
+extern "C" int fdbm_gn_resample_h16(const void* src1, const double* sums1, int C1, const void* src2, const double* sums2,
+                                    int C2, const float* gamma, const float* beta, float* table, int batch, int T, int F,
+                                    int mode, void* act_out, void* raw_out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(src1 && sums1 && gamma && beta && table && act_out && raw_out && batch > 0, "fdbm_gn_resample_h16: null pointer");
+  FDBM_REQUIRE((C2 == 0) == (src2 == nullptr) && (C2 == 0 || sums2), "fdbm_gn_resample_h16: src2/C2 mismatch");
+  float2* tab = reinterpret_cast<float2*>(table);
+  if (int rc = launch_gn_finalize(sums1, C1, sums2, C2, gamma, beta, batch, static_cast<int64_t>(T) * F, tab, as_stream(stream)))
+    return rc;
+  return launch_gn_resample16(reinterpret_cast<const op_t*>(src1), C1, reinterpret_cast<const op_t*>(src2), C2, tab, batch, T, F,
+                              mode, reinterpret_cast<op_t*>(act_out), reinterpret_cast<op_t*>(raw_out), as_stream(stream));
 }

@@ -391,7 +391,7 @@ struct Builder {
     c0.wpack = w0; c0.bias = c0b; c0.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c0.bias_b_stride = dense_stride;
     c0.B = B; c0.T = To; c0.F = Fo; c0.Cout = Cout; c0.out_h16 = h1; c0.sums = h1_sums;
     // the (scale, shift) table of GroupNorm_0 is needed by the on-load path and by every backward pass
-    if (mode == 0 || train()) tab0 = norm_table(x1.sums, C1, x2 ? x2->sums : nullptr, C2, g0w, g0b, T, F);
+    tab0 = norm_table(x1.sums, C1, x2 ? x2->sums : nullptr, C2, g0w, g0b, T, F);
     float2* stats0 = norm_stats(x1.sums, C1, x2 ? x2->sums : nullptr, C2, T, F);
     if (mode == 0) {
       // GroupNorm_0 + SiLU applied by Conv_0 on load, straight from the 16-bit copies of the residual stream
@@ -403,9 +403,14 @@ struct Builder {
       xr = alloc<op_t>(npx * Cin);
       const float* s1 = x1.data; const double* q1 = x1.sums;
       const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr;
-      op([=](cudaStream_t s) {
-        return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
-      }, FDBM_OP_NORM);
+      if (train()) {                                  // (the backward pass recomputes from the fp32 stream: keep both sides identical)
+        op([=](cudaStream_t s) {
+          return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
+        }, FDBM_OP_NORM);
+      } else {
+        const op_t* h1s = x1.h16; const op_t* h2s = x2 ? x2->h16 : nullptr;
+        op([=](cudaStream_t s) { return launch_gn_resample16(h1s, C1, h2s, C2, tab0, B, T, F, mode, a0, xr, s); }, FDBM_OP_NORM);
+      }
       c0.seg[0] = seg(a0, Cin, 9); c0.n_seg = 1;
     }
     conv_op(c0);

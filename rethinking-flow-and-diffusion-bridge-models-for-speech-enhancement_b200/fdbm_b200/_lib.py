@@ -22,7 +22,7 @@ EXPORTS = [
     "fdbm_prior_sample", "fdbm_bridge_step",
     "fdbm_plan_create", "fdbm_plan_destroy", "fdbm_plan_load_weights", "fdbm_plan_device_bytes",
     "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run", "fdbm_plan_profile_forward",
-    "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_conv_igemm", "fdbm_conv_igemm_gn",
+    "fdbm_fir_resample", "fdbm_channel_stats", "fdbm_groupnorm_act", "fdbm_gn_resample_h16", "fdbm_conv_igemm", "fdbm_conv_igemm_gn",
     "fdbm_pack_conv_weights", "fdbm_attention",
     "fdbm_pack_conv_weights_dgrad", "fdbm_conv_wgrad_workspace_bytes", "fdbm_conv_wgrad",
     "fdbm_groupnorm_act_bwd", "fdbm_fir_resample_h16", "fdbm_attention_bwd", "fdbm_adam_ema_step",
@@ -77,6 +77,7 @@ def load() -> C.CDLL:
         "fdbm_fir_resample": (i, [p, i, i, i, i, i, p, p]),
         "fdbm_channel_stats": (i, [p, i, i, i, i, p, p]),
         "fdbm_groupnorm_act": (i, [p, p, i, p, p, i, p, p, i, i, i, i, i, p, p, p]),
+        "fdbm_gn_resample_h16": (i, [p, p, i, p, p, i, p, p, p, i, i, i, i, p, p, p]),
         "fdbm_conv_igemm": (i, [p, i, i, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
         "fdbm_conv_igemm_gn": (i, [p, i, i, p, p, p, i, p, p, p, p, f, i, i, i, i, p, p, p, p]),
         "fdbm_pack_conv_weights": (i, [p, i, i, p, i, i, p, C.POINTER(i64), p]),

@@ -205,6 +205,37 @@ def test_groupnorm_act(lib, C1, C2, mode):
     assert float((ntfc_to_nchw(a_out.float()).cpu() - act).abs().max()) < 0.03
 
 
+@pytest.mark.parametrize("C1,C2,mode,T,Fq", [(128, 0, 1, 12, 16), (256, 0, 1, 36, 8), (256, 0, 2, 12, 16), (256, 128, 2, 20, 6),
+                                             (256, 256, 2, 4, 4), (128, 0, 1, 4, 4)])
+def test_gn_resample_h16(lib, C1, C2, mode, T, Fq):
+    """Resampling blocks' input pass from the 16-bit stream (layerspp.py:242-257 with up/down): compared with
+    torch GroupNorm -> SiLU -> FIR on the same 16-bit input."""
+    import fdbm_oracle as O
+    g = torch.Generator().manual_seed(C1 + C2 + mode + T)
+    B = 2
+    Cc = C1 + C2
+    x = (torch.randn(B, Cc, Fq, T, generator=g) * 1.5 + 0.3).to(_h16()).float()
+    gamma = 1 + 0.1 * torch.randn(Cc, generator=g)
+    beta = 0.1 * torch.randn(Cc, generator=g)
+    act = _gn_ref(x, gamma, beta, True)
+    act, raw = (O.fir_down2(act), O.fir_down2(x)) if mode == 1 else (O.fir_up2(act), O.fir_up2(x))
+    s1 = nchw_to_ntfc(x[:, :C1]).to(_h16()).cuda()
+    s2 = nchw_to_ntfc(x[:, C1:]).to(_h16()).cuda() if C2 else None
+    sums1 = torch.stack([x[:, :C1].double().sum((2, 3)), x[:, :C1].double().pow(2).sum((2, 3))], -1).cuda()
+    sums2 = torch.stack([x[:, C1:].double().sum((2, 3)), x[:, C1:].double().pow(2).sum((2, 3))], -1).cuda() if C2 else None
+    To, Fo = act.shape[3], act.shape[2]
+    a_out = torch.full((B, To, Fo, Cc), float("nan"), dtype=_h16(), device="cuda")
+    r_out = torch.full_like(a_out, float("nan"))
+    gd, bd = gamma.cuda(), beta.cuda()
+    table = torch.empty(B * Cc * 2, device="cuda")
+    _check(lib, lib.fdbm_gn_resample_h16(s1.data_ptr(), sums1.data_ptr(), C1, s2.data_ptr() if C2 else None,
+                                         sums2.data_ptr() if C2 else None, C2, gd.data_ptr(), bd.data_ptr(), table.data_ptr(),
+                                         B, T, Fq, mode, a_out.data_ptr(), r_out.data_ptr(), _stream()))
+    assert rel_l2(ntfc_to_nchw(r_out.float()), raw) < 1e-3            # 16-bit output rounding only
+    assert rel_l2(ntfc_to_nchw(a_out.float()), act) < 4e-3            # + packed 16-bit SiLU
+    assert float((ntfc_to_nchw(a_out.float()).cpu() - act).abs().max()) < 0.03
+
+
 def _conv_case(lib, B, T, Fq, C1, k, C2, Cout, residual, bias_b, seed):
     g = torch.Generator().manual_seed(seed)
     x1 = torch.randn(B, C1, Fq, T, generator=g).to(_h16()).float()
