@@ -122,6 +122,7 @@ struct ConvArgs {
   ConvSeg seg[3]; int n_seg = 0;
   const op_t* wpack = nullptr;
   const float* bias = nullptr; const float* bias_b = nullptr; int bias_b_stride = 0; const float* residual = nullptr;
+  const op_t* residual_h16 = nullptr;      // identity shortcut read from the 16-bit copy of the stream (instead of `residual`)
   float scale = 1.0f; int B = 0, T = 0, F = 0, Cout = 0;
   float* out_f32 = nullptr; op_t* out_h16 = nullptr;
   double* sums = nullptr;

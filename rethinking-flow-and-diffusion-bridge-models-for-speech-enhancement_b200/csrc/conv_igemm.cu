@@ -38,22 +38,27 @@ constexpr int A_TILE_BYTES = HALO_T * HALO_F * 128;          // 23040 bytes land
 constexpr int A_TILE_STRIDE = 23552;                         // rounded up to 1024
 #ifndef FDBM_A_STAGES
 #define FDBM_A_STAGES 3
-#define FDBM_B_STAGES 4
+#define FDBM_B_STAGES 3
 #endif
 constexpr int A_STAGES = FDBM_A_STAGES;
 constexpr int B_STAGES = FDBM_B_STAGES;
 constexpr int BN = 128;
 constexpr int B_TILE_BYTES = BN * 128;
 constexpr int A_SBO = HALO_F * 128;                          // 1280: distance between 8-pixel row groups
-constexpr int NUM_THREADS = 384;                              // 4 pipeline warps + 4 epilogue warps + 4 operand-transform warps
+// warps 0-3 pipeline (TMA A, TMA B, MMA issue, TMEM owner), warps 4-7 epilogue of M-tile 0, warps 8-11 operand
+// transform, warps 12-15 epilogue of M-tile 1.  One epilogue warpgroup for both tiles was the bottleneck of every
+// K <= 1408 layer (13 us of epilogue per 8 us of MMA per item); each tile now has the whole item time.
+constexpr int NUM_THREADS = 512;
+constexpr int EPI_GROUPS = 2;
 constexpr int MAX_SEG = 3;
-// 384 threads cap ptxas at 168 registers per thread; setmaxnreg moves registers from the pipeline and
-// transform warpgroups to the epilogue warpgroup (128 * (96 + 240 + 168) <= 65536)
-constexpr int PIPE_REGS = 96, EPI_REGS = 240, XFORM_REGS = 168;
-constexpr int STAGE_BYTES = 4 * 32 * 32 * 4;                    // epilogue transposition tiles, one per warp
+// 512 threads start at 128 registers each; setmaxnreg moves registers from the pipeline and transform
+// warpgroups to the two epilogue warpgroups (128 * (56 + 120 + 2 * 168) = 65536)
+constexpr int PIPE_REGS = 56, EPI_REGS = 168, XFORM_REGS = 120;
+constexpr int STAGE_BYTES = EPI_GROUPS * 4 * 32 * 32 * 4;       // epilogue transposition tiles, one per warp
 constexpr int STAT_SLOTS = 2;                                  // n-blocks whose statistics a CTA keeps in flight
-constexpr int STAT_BYTES = 4 * BN * 8;                         // per-warp channel (sum, sum of squares) partials
-constexpr int SMEM_BYTES = 1024 + A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + STAGE_BYTES + STAT_BYTES + 256;
+constexpr int STAT_BYTES = EPI_GROUPS * 4 * BN * 8;            // per-warp channel (sum, sum of squares) partials
+// no alignment slack: the dynamic segment is declared __align__(1024) and the kernel traps if it is not
+constexpr int SMEM_BYTES = A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + STAGE_BYTES + STAT_BYTES + 256;
 
 // One K segment = one activation tensor contributing C channels (kb = C/64 K-blocks) with 9 taps or 1.
 // norm != 0: GroupNorm (+SiLU when act != 0) is applied to the tile in shared memory between the TMA
@@ -72,6 +77,7 @@ struct ConvParams {
   const float* bias_b;
   int bias_b_stride;
   const float* residual;
+  const op_t* residual_h16;
   float scale;
   float* out_f32;
   op_t* out_h16;
@@ -100,14 +106,16 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int mi) {
 
 // COMB: the epilogue also applies the Combine 1x1 convolution of the input pyramid (kept out of the standard
 // instantiation: even as a not-taken branch it doubled the epilogue's time).
-template <bool COMB>
+// RES16: the identity-shortcut operand is the 16-bit copy of the residual stream (inference plans)
+template <bool COMB, bool RES16>
 __global__ void __launch_bounds__(NUM_THREADS, 1)
 conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_constant__ CUtensorMap map_a1,
                   const __grid_constant__ CUtensorMap map_a2, const __grid_constant__ CUtensorMap map_b,
                   const ConvParams p) {
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // (offset arithmetic on the __shared__ array itself, so the compiler keeps the shared address space: LDS/STS, not generic LD/ST)
-  uint8_t* smem = smem_raw + ((1024u - (smem_u32(smem_raw) & 1023u)) & 1023u);
+  uint8_t* smem = smem_raw;
+  if (smem_u32(smem_raw) & 1023u) __trap();
   uint8_t* sA = smem;
   uint8_t* sB = smem + A_STAGES * MT * A_TILE_STRIDE;
   uint8_t* s_stage = sB + B_STAGES * B_TILE_BYTES;
@@ -129,7 +137,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (threadIdx.x == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(a_ready + i, 128); }
     for (int i = 0; i < B_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
-    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4); }
+    for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * EPI_GROUPS); }
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -245,7 +253,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       if (++as == 2) { as = 0; pacc ^= 1; }
     }
   }
-  } else if (warp >= 8) {
+  } else if (warp >= 8 && warp < 12) {
     reg_dec<XFORM_REGS>();
     // ------------------------------------------------------------------ operand transform (4 warps)
     // GroupNorm (+SiLU) on load: when a segment is flagged `norm`, the raw 16-bit tile that TMA just
@@ -342,7 +350,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
       }
     }
-  } else if (warp >= 4) {
+  } else {
     // ------------------------------------------------------------------ epilogue (4 warps = 128 TMEM lanes)
     // tcgen05.ld hands every thread one pixel row (32 consecutive channels).  Writing that straight to
     // global memory would touch 32 different 128-byte lines per store instruction, so each warp first
@@ -350,17 +358,18 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // 128 contiguous bytes of one pixel and every global access (bias, residual, outputs) is coalesced.
     reg_inc<EPI_REGS>();
     const int q = warp & 3;                              // TMEM lane quadrant of this warp
-    float4* stage = reinterpret_cast<float4*>(s_stage) + q * (32 * 8);       // [32 pixels][8 float4], XOR-swizzled
+    const int eg = warp >= 12 ? 1 : 0;                   // epilogue group = M-tile of the item this warpgroup drains
+    float4* stage = reinterpret_cast<float4*>(s_stage) + (eg * 4 + q) * (32 * 8);   // [32 pixels][8 float4], XOR-swizzled
     const int cc = lane & 7;                             // channel quad inside the 32-channel chunk (transposed phase)
     const int rsub = lane >> 3;                          // pixel sub-row (transposed phase)
-    const int et = threadIdx.x - 128;                    // 0..127 among the epilogue threads (warps 4..7)
+    const int et = (threadIdx.x & 127);                  // 0..127 inside the epilogue group
     uint32_t as = 0, pacc = 0;
     const bool do_stats = p.sums != nullptr;             // host guarantees n_nblocks <= STAT_SLOTS when sums are requested
     // GroupNorm statistics: every warp leaves its 32-pixel partial sums (fp32, fixed summation order) in its
     // own shared-memory slot; after each M-tile thread c adds the four warps' partials of channel c into
     // DOUBLE registers that live across the CTA's items, and only those go to global memory (double atomics).
     // E[x^2] - mean^2 amplifies rounding noise in these sums ~1000x on some layers, so no fp32 atomics here.
-    float2* wstat = reinterpret_cast<float2*>(s_stat);   // [4 warps][BN channels] (sum, sum of squares)
+    float2* wstat = reinterpret_cast<float2*>(s_stat) + eg * 4 * BN;   // [4 warps][BN channels] (sum, sum of squares)
     double acc_s[STAT_SLOTS], acc_q[STAT_SLOTS];
 #pragma unroll
     for (int u = 0; u < STAT_SLOTS; ++u) { acc_s[u] = 0.0; acc_q[u] = 0.0; }
@@ -382,7 +391,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int n0 = nblk * BN;
       mbar_wait(acc_full + as, pacc);
       fence_after_sync();
-      for (int j = 0; j < MT; ++j) {
+      for (int j = eg; j <= eg; ++j) {
         const TileCoord tc = decode_tile(p, ct * MT + j);
         if (!tc.valid) continue;                          // warp-uniform
         if (do_stats && stat_b != tc.b) {
@@ -430,61 +439,65 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         // pixel rows of this lane in the transposed phase: 64-bit tile base + 32-bit row offsets
         const bool full = tc.t0 + TILE_T <= p.T && tc.f0 + TILE_F <= p.F;       // warp-uniform
         const int64_t tile_base = ((static_cast<int64_t>(tc.b) * p.T + tc.t0) * p.F + tc.f0) * p.Cout + n0 + cc * 4;
-        int roff[8];
+        // row `it` of this lane is pixel m = q*32 + it*4 + rsub of the tile: frame q*4 + (it >> 1), bin (it & 1)*4 + rsub
+        const int roff0 = ((q * 4) * p.F + rsub) * p.Cout, roff_t = p.F * p.Cout, roff_f = 4 * p.Cout;
+        auto roff = [&](int it) { return roff0 + (it >> 1) * roff_t + (it & 1) * roff_f; };
         uint32_t okmask = 0;
 #pragma unroll
         for (int it = 0; it < 8; ++it) {
           const int m = q * 32 + it * 4 + rsub;
           const bool ok = tc.t0 + (m >> 3) < p.T && tc.f0 + (m & 7) < p.F;
           okmask |= ok ? (1u << it) : 0u;
-          roff[it] = ok ? ((m >> 3) * p.F + (m & 7)) * p.Cout : 0;
         }
-        const float* res_p = p.residual ? p.residual + tile_base : nullptr;
+        const float* res_p = !RES16 && p.residual ? p.residual + tile_base : nullptr;
+        const op_t* res16_p = RES16 ? p.residual_h16 + tile_base : nullptr;
         float* of_p = p.out_f32 ? p.out_f32 + tile_base : nullptr;
         op_t* oh_p = p.out_h16 ? p.out_h16 + tile_base : nullptr;
-        if (res_p) {
-          // pull the NEXT tile's residual rows (fp32, 512 B per pixel) into L2 now: by the time its epilogue runs,
+        if (RES16 || res_p) {
+          // pull the NEXT tile's residual rows (512 or 256 B per pixel) into L2 now: by the time its epilogue runs,
           // the register loads below see L2 latency instead of HBM latency
-          int nmi = ct * MT + j + 1, nblk_n = nblk;
-          if (j + 1 == MT) {
-            const int nitem = item + gridDim.x;
-            nmi = nitem < p.n_items ? (nitem / p.n_nblocks) * MT : p.n_mtiles;
-            nblk_n = nitem % p.n_nblocks;
-          }
+          const int nitem = item + gridDim.x;
+          const int nmi = nitem < p.n_items ? (nitem / p.n_nblocks) * MT + j : p.n_mtiles;
+          const int nblk_n = nitem % p.n_nblocks;
           const TileCoord nt = decode_tile(p, nmi);
           const int t = nt.t0 + (et >> 3), f = nt.f0 + (et & 7);
           if (nt.valid && t < p.T && f < p.F) {
-            const float* pr = p.residual + ((static_cast<int64_t>(nt.b) * p.T + t) * p.F + f) * p.Cout + nblk_n * BN;
+            const int64_t po = ((static_cast<int64_t>(nt.b) * p.T + t) * p.F + f) * p.Cout + nblk_n * BN;
+            if (RES16) {
 #pragma unroll
-            for (int u = 0; u < 4; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(pr + u * 32));
+              for (int u = 0; u < 2; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual_h16 + po + u * 64));
+            } else {
+#pragma unroll
+              for (int u = 0; u < 4; ++u) asm volatile("prefetch.global.L2 [%0];" ::"l"(p.residual + po + u * 32));
+            }
           }
         }
-        // bias (+ per-utterance FiLM bias) of all four 32-channel chunks, pre-multiplied by the output scale
         const float2 sc2 = make_float2(p.scale, p.scale);
-        float2 bs_lo[BN / 32], bs_hi[BN / 32];
-#pragma unroll
-        for (int ch = 0; ch < BN / 32; ++ch) {
-          float4 bv = __ldg(reinterpret_cast<const float4*>(p.bias + n0 + ch * 32 + cc * 4));
-          if (p.bias_b) {
-            const float4 e = __ldg(reinterpret_cast<const float4*>(p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + n0 + ch * 32 + cc * 4));
-            bv.x += e.x; bv.y += e.y; bv.z += e.z; bv.w += e.w;
-          }
-          bs_lo[ch] = __fmul2_rn(make_float2(bv.x, bv.y), sc2); bs_hi[ch] = __fmul2_rn(make_float2(bv.z, bv.w), sc2);
-        }
-        // residual rows: register double buffer, chunk ch+1 is requested before chunk ch is processed
+        const float* bias_p = p.bias + n0 + cc * 4;
+        const float* biasb_p = p.bias_b ? p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + n0 + cc * 4 : nullptr;
         float4 res[8];
-        auto load_res = [&](float4 (&r)[8], int ch) {
+        uint2 res16[8];
+        auto load_res16 = [&](int ch) {
           if (full) {
 #pragma unroll
-            for (int it = 0; it < 8; ++it) r[it] = __ldg(reinterpret_cast<const float4*>(res_p + roff[it] + ch * 32));
+            for (int it = 0; it < 8; ++it) res16[it] = __ldg(reinterpret_cast<const uint2*>(res16_p + roff(it) + ch * 32));
           } else {
 #pragma unroll
             for (int it = 0; it < 8; ++it)
-              r[it] = ((okmask >> it) & 1) ? __ldg(reinterpret_cast<const float4*>(res_p + roff[it] + ch * 32))
+              res16[it] = ((okmask >> it) & 1) ? __ldg(reinterpret_cast<const uint2*>(res16_p + roff(it) + ch * 32)) : make_uint2(0u, 0u);
+          }
+        };
+        auto load_res = [&](float4 (&r)[8], int ch) {
+          if (full) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) r[it] = __ldg(reinterpret_cast<const float4*>(res_p + roff(it) + ch * 32));
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              r[it] = ((okmask >> it) & 1) ? __ldg(reinterpret_cast<const float4*>(res_p + roff(it) + ch * 32))
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
-        if (res_p) load_res(res, 0);
 #pragma unroll
         for (int ch = 0; ch < BN / 32; ++ch) {
           float4 cw[4], cbias = make_float4(0.f, 0.f, 0.f, 0.f);
@@ -498,10 +511,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                                   p.comb_C > 3 ? __ldg(wr + 3) : 0.f);
             }
           }
+          // bias (+ per-utterance FiLM bias) of this chunk, pre-multiplied by the output scale (L1-resident)
+          float4 bv = __ldg(reinterpret_cast<const float4*>(bias_p + ch * 32));
+          if (biasb_p) {
+            const float4 e = __ldg(reinterpret_cast<const float4*>(biasb_p + ch * 32));
+            bv.x += e.x; bv.y += e.y; bv.z += e.z; bv.w += e.w;
+          }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
-          float4 res_nxt[8];
-          if (res_p && ch + 1 < BN / 32) load_res(res_nxt, ch + 1);
+          if (RES16) load_res16(ch);                      // L2 hits (prefetched one tile ahead), in flight while TMEM is read
+          else if (res_p) load_res(res, ch);
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -511,6 +530,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           // packed fp32x2 arithmetic (FFMA2 / FADD2): the single epilogue warp of an SM sub-partition is bound by
           // its own instruction latencies, so halving the instruction count is what speeds it up.
           // out = acc * scale + (bias * scale) (+ residual * scale)
+          const float2 bs_lo = __fmul2_rn(make_float2(bv.x, bv.y), sc2), bs_hi = __fmul2_rn(make_float2(bv.z, bv.w), sc2);
           float2 o_lo[8], o_hi[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {                  // eight independent shared-memory reads in flight
@@ -520,8 +540,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
 #pragma unroll
           for (int it = 0; it < 8; ++it) {
-            o_lo[it] = __ffma2_rn(o_lo[it], sc2, bs_lo[ch]); o_hi[it] = __ffma2_rn(o_hi[it], sc2, bs_hi[ch]);
-            if (res_p) {
+            o_lo[it] = __ffma2_rn(o_lo[it], sc2, bs_lo); o_hi[it] = __ffma2_rn(o_hi[it], sc2, bs_hi);
+            if (RES16) {
+              const op2_t* r2 = reinterpret_cast<const op2_t*>(&res16[it]);
+              o_lo[it] = __ffma2_rn(op22f2(r2[0]), sc2, o_lo[it]);
+              o_hi[it] = __ffma2_rn(op22f2(r2[1]), sc2, o_hi[it]);
+            } else if (res_p) {
               o_lo[it] = __ffma2_rn(make_float2(res[it].x, res[it].y), sc2, o_lo[it]);
               o_hi[it] = __ffma2_rn(make_float2(res[it].z, res[it].w), sc2, o_hi[it]);
             }
@@ -541,12 +565,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             if (of_p) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                *reinterpret_cast<float4*>(of_p + roff[it] + ch * 32) = make_float4(o_lo[it].x, o_lo[it].y, o_hi[it].x, o_hi[it].y);
+                *reinterpret_cast<float4*>(of_p + roff(it) + ch * 32) = make_float4(o_lo[it].x, o_lo[it].y, o_hi[it].x, o_hi[it].y);
             }
             if (oh_p) {
 #pragma unroll
               for (int it = 0; it < 8; ++it)
-                *reinterpret_cast<uint2*>(oh_p + roff[it] + ch * 32) = make_uint2(pack_op2(o_lo[it].x, o_lo[it].y), pack_op2(o_hi[it].x, o_hi[it].y));
+                *reinterpret_cast<uint2*>(oh_p + roff(it) + ch * 32) = make_uint2(pack_op2(o_lo[it].x, o_lo[it].y), pack_op2(o_hi[it].x, o_hi[it].y));
             }
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
@@ -557,8 +581,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
             for (int it = 0; it < 8; ++it) {
               if ((okmask >> it) & 1) {
-                if (of_p) *reinterpret_cast<float4*>(of_p + roff[it] + ch * 32) = make_float4(o_lo[it].x, o_lo[it].y, o_hi[it].x, o_hi[it].y);
-                if (oh_p) *reinterpret_cast<uint2*>(oh_p + roff[it] + ch * 32) = make_uint2(pack_op2(o_lo[it].x, o_lo[it].y), pack_op2(o_hi[it].x, o_hi[it].y));
+                if (of_p) *reinterpret_cast<float4*>(of_p + roff(it) + ch * 32) = make_float4(o_lo[it].x, o_lo[it].y, o_hi[it].x, o_hi[it].y);
+                if (oh_p) *reinterpret_cast<uint2*>(oh_p + roff(it) + ch * 32) = make_uint2(pack_op2(o_lo[it].x, o_lo[it].y), pack_op2(o_hi[it].x, o_hi[it].y));
                 ssum_lo = __fadd2_rn(ssum_lo, o_lo[it]); ssum_hi = __fadd2_rn(ssum_hi, o_hi[it]);
                 ssq_lo = __ffma2_rn(o_lo[it], o_lo[it], ssq_lo); ssq_hi = __ffma2_rn(o_hi[it], o_hi[it], ssq_hi);
               }
@@ -580,19 +604,15 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
           __syncwarp();                                   // staging tile is rewritten by the next chunk
-          if (res_p && ch + 1 < BN / 32) {
-#pragma unroll
-            for (int it = 0; it < 8; ++it) res[it] = res_nxt[it];
-          }
         }
         if (do_stats) {                                   // block-uniform
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
           double s = 0.0, sq = 0.0;
 #pragma unroll
           for (int w = 0; w < 4; ++w) { const float2 e = wstat[w * BN + et]; s += e.x; sq += e.y; }
 #pragma unroll
           for (int u = 0; u < STAT_SLOTS; ++u) if (u == nblk) { acc_s[u] += s; acc_q[u] += sq; }
-          asm volatile("bar.sync 1, 128;" ::: "memory");
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
         }
       }
       // all TMEM reads of this accumulator stage are done: hand it back to the MMA warp
@@ -756,8 +776,9 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   FDBM_REQUIRE(!a.pyr_prev || (a.T % 2 == 0 && a.F % 2 == 0), "conv_igemm: pyramid level with odd size");
   static bool attr_set = false;
   if (!attr_set) {
-    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
+    FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     attr_set = true;
   }
   FDBM_REQUIRE(!a.comb_pyr || (a.comb_w && a.comb_b && a.comb_C >= 1 && a.comb_C <= 4 && !a.pyr_out), "conv_igemm: bad Combine epilogue arguments");
@@ -788,6 +809,8 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.n_nblocks = a.Cout / BN;
   p.n_items = ceil_div(p.n_mtiles, MT) * p.n_nblocks;
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
+  p.residual_h16 = a.residual_h16;
+  FDBM_REQUIRE(!(a.residual && a.residual_h16) && !(a.residual_h16 && (a.comb_pyr || a.pyr_out)), "conv_igemm: bad residual arguments");
   p.out_f32 = a.out_f32; p.out_h16 = a.out_h16; p.sums = a.sums;
   p.pyr_out = a.pyr_out; p.pyr_prev = a.pyr_prev; p.pyr_C = a.pyr_C;
   p.comb_pyr = a.comb_pyr; p.comb_w = a.comb_w; p.comb_b = a.comb_b; p.comb_C = a.comb_C;
@@ -796,8 +819,9 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
     FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));
   }
   const int grid = std::min(p.n_items, num_sms());
-  if (a.comb_pyr) conv_igemm_kernel<true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
-  else conv_igemm_kernel<false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
+  if (a.comb_pyr) conv_igemm_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
+  else if (a.residual_h16) conv_igemm_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
+  else conv_igemm_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

@@ -282,7 +282,10 @@ struct Builder {
   void release(const void* p) { if (p && !P->train) arena.release(reinterpret_cast<const uint8_t*>(p) - P->arena); }
   Act new_act(int C, int T, int F) {
     Act a; a.C = C; a.T = T; a.F = F;
-    a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
+    // inference plans keep the residual stream in the 16-bit operand format only: the identity shortcut re-reads the
+    // 16-bit copy (one rounding per block, which the 1/sqrt(2) of every block keeps from accumulating); training plans
+    // keep the fp32 master for the backward pass
+    if (P->train) a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
     a.h16 = alloc<op_t>(static_cast<int64_t>(P->B) * T * F * C);
     a.sums = alloc<double>(static_cast<int64_t>(P->B) * C * 2);
     if (P->train) a.grad = galloc(static_cast<int64_t>(P->B) * T * F * C);
@@ -429,7 +432,8 @@ struct Builder {
           c.seg[c.n_seg++] = seg(xr, Cin, 1);
         }
       }
-      c.wpack = w1; c.bias = bias1; c.residual = shortcut ? nullptr : x1.data;
+      c.wpack = w1; c.bias = bias1;
+      if (!shortcut) { if (train()) c.residual = x1.data; else c.residual_h16 = x1.h16; }
       c.scale = 0.70710678118654752f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
       c.out_f32 = out.data; c.out_h16 = out.h16; c.sums = out.sums;
       if (comb) { c.comb_pyr = comb->pyr; c.comb_w = comb->w; c.comb_b = comb->b; c.comb_C = comb->Cp; }
@@ -548,7 +552,8 @@ struct Builder {
     {
       ConvArgs c;
       c.seg[0] = seg(o, C, 1); c.n_seg = 1;
-      c.wpack = w3; c.bias = b3; c.residual = x.data; c.scale = 0.70710678118654752f;
+      c.wpack = w3; c.bias = b3; c.scale = 0.70710678118654752f;
+      if (train()) c.residual = x.data; else c.residual_h16 = x.h16;
       c.B = B; c.T = T; c.F = F; c.Cout = C; c.out_f32 = out.data; c.out_h16 = out.h16; c.sums = out.sums;
       conv_op(c);
     }
