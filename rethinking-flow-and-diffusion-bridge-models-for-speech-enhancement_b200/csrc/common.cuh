@@ -110,7 +110,7 @@ int launch_gn_resample16(const op_t* src1, int C1, const op_t* src2, int C2, con
 int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2, const float* gamma, const float* beta,
                        int B, int64_t pixels, float2* table, cudaStream_t s);
 int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B, int L,
-                     int C, op_t* o, int ldo, cudaStream_t s);
+                     int C, op_t* o, int ldo, cudaStream_t s, int fp32_probs = 0);   // fp32_probs: CUDA-core kernel with fp32 soft-max weights (training plans: matches attention_bwd)
 
 // One K segment of the implicit GEMM: an activation tensor [B,T,F,C] (16-bit) read with 9 taps (3x3) or 1.
 // norm_tab != nullptr: GroupNorm (+SiLU if act) is applied on load, norm_tab[b * tab_stride + c] = (scale, shift).
@@ -126,6 +126,7 @@ struct ConvArgs {
   float scale = 1.0f; int B = 0, T = 0, F = 0, Cout = 0;
   float* out_f32 = nullptr; op_t* out_h16 = nullptr;
   double* sums = nullptr;
+  bool sums_prezeroed = false;             // the caller zeroes `sums` itself (plans: one memset per forward)
   // pyramid epilogue (ncsnpp_v2.py:338-359): out = conv(...)[:, :pyr_C] + bias + FIR-up x2(pyr_prev); fp32 [B,T,F,pyr_C]
   float* pyr_out = nullptr; const float* pyr_prev = nullptr; int pyr_C = 0;
   // Combine epilogue (layerspp.py:52-59): out += comb_b[n] + sum_k comb_w[n][k] * comb_pyr[b,t,f,k], applied after

@@ -473,8 +473,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
         }
         const float2 sc2 = make_float2(p.scale, p.scale);
+        // bias (+ per-utterance FiLM bias): the L1 left beside 227 KB of shared memory does not keep these lines, so the
+        // loads of chunk ch + 1 are issued while chunk ch is processed
         const float* bias_p = p.bias + n0 + cc * 4;
         const float* biasb_p = p.bias_b ? p.bias_b + static_cast<int64_t>(tc.b) * p.bias_b_stride + n0 + cc * 4 : nullptr;
+        float4 bv = __ldg(reinterpret_cast<const float4*>(bias_p));
+        float4 bvb = biasb_p ? __ldg(reinterpret_cast<const float4*>(biasb_p)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 res[8];
         uint2 res16[8];
         auto load_res16 = [&](int ch) {
@@ -511,11 +515,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                                   p.comb_C > 3 ? __ldg(wr + 3) : 0.f);
             }
           }
-          // bias (+ per-utterance FiLM bias) of this chunk, pre-multiplied by the output scale (L1-resident)
-          float4 bv = __ldg(reinterpret_cast<const float4*>(bias_p + ch * 32));
-          if (biasb_p) {
-            const float4 e = __ldg(reinterpret_cast<const float4*>(biasb_p + ch * 32));
-            bv.x += e.x; bv.y += e.y; bv.z += e.z; bv.w += e.w;
+          float4 bvn = bv, bvbn = bvb;
+          if (ch + 1 < BN / 32) {
+            bvn = __ldg(reinterpret_cast<const float4*>(bias_p + (ch + 1) * 32));
+            if (biasb_p) bvbn = __ldg(reinterpret_cast<const float4*>(biasb_p + (ch + 1) * 32));
           }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
@@ -530,7 +533,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           // packed fp32x2 arithmetic (FFMA2 / FADD2): the single epilogue warp of an SM sub-partition is bound by
           // its own instruction latencies, so halving the instruction count is what speeds it up.
           // out = acc * scale + (bias * scale) (+ residual * scale)
-          const float2 bs_lo = __fmul2_rn(make_float2(bv.x, bv.y), sc2), bs_hi = __fmul2_rn(make_float2(bv.z, bv.w), sc2);
+          const float2 bs_lo = __fmul2_rn(make_float2(bv.x + bvb.x, bv.y + bvb.y), sc2), bs_hi = __fmul2_rn(make_float2(bv.z + bvb.z, bv.w + bvb.w), sc2);
           float2 o_lo[8], o_hi[8];
 #pragma unroll
           for (int it = 0; it < 8; ++it) {                  // eight independent shared-memory reads in flight
@@ -604,6 +607,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
           __syncwarp();                                   // staging tile is rewritten by the next chunk
+          bv = bvn; bvb = bvbn;
         }
         if (do_stats) {                                   // block-uniform
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
@@ -816,7 +820,7 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.comb_pyr = a.comb_pyr; p.comb_w = a.comb_w; p.comb_b = a.comb_b; p.comb_C = a.comb_C;
   if (a.sums) {
     FDBM_REQUIRE(p.n_nblocks <= STAT_SLOTS, "conv_igemm: channel sums support Cout <= %d", STAT_SLOTS * BN);
-    FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));
+    if (!a.sums_prezeroed) FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));
   }
   const int grid = std::min(p.n_items, num_sms());
   if (a.comb_pyr) conv_igemm_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);

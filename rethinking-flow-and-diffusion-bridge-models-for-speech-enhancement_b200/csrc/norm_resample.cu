@@ -383,18 +383,26 @@ __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __restrict__ sums2, int C2,
                    const float* __restrict__ gamma, const float* __restrict__ beta, double pixels,
                    float2* __restrict__ table) {
+  __shared__ double2 s_sq[GN_MAXC];
   __shared__ float s_mean[32], s_rstd[32];
   const int C = C1 + C2, b = blockIdx.x;
   const int G = min(C / 4, 32), cpg = C / G;
-  if (threadIdx.x < G) {
-    double s = 0, q = 0;
-    for (int j = 0; j < cpg; ++j) {
-      const int c = threadIdx.x * cpg + j;
+  // all (sum, sum of squares) entries in one round of independent 16-byte loads (the launch is latency-bound)
+  float gam[GN_MAXC / 256], bet[GN_MAXC / 256];
+#pragma unroll
+  for (int u = 0; u < GN_MAXC / 256; ++u) {
+    const int c = threadIdx.x + u * 256;
+    if (c < C) {
       const double* e = c < C1 ? sums1 + (static_cast<int64_t>(b) * C1 + c) * 2
                                : sums2 + (static_cast<int64_t>(b) * C2 + (c - C1)) * 2;
-      s += e[0];
-      q += e[1];
+      s_sq[c] = *reinterpret_cast<const double2*>(e);
+      gam[u] = __ldg(gamma + c); bet[u] = __ldg(beta + c);
     }
+  }
+  __syncthreads();
+  if (threadIdx.x < G) {
+    double s = 0, q = 0;
+    for (int j = 0; j < cpg; ++j) { const double2 e = s_sq[threadIdx.x * cpg + j]; s += e.x; q += e.y; }
     const double cnt = cpg * pixels;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -403,10 +411,14 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-6));
   }
   __syncthreads();
-  for (int c = threadIdx.x; c < C; c += 256) {
-    const int g = c / cpg;
-    const float a = gamma[c] * s_rstd[g];
-    table[static_cast<int64_t>(b) * C + c] = make_float2(a, beta[c] - s_mean[g] * a);
+#pragma unroll
+  for (int u = 0; u < GN_MAXC / 256; ++u) {
+    const int c = threadIdx.x + u * 256;
+    if (c < C) {
+      const int g = c / cpg;
+      const float a = gam[u] * s_rstd[g];
+      table[static_cast<int64_t>(b) * C + c] = make_float2(a, bet[u] - s_mean[g] * a);
+    }
   }
 }
 
@@ -415,7 +427,7 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
 int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2, const float* gamma, const float* beta,
                        int B, int64_t pixels, float2* table, cudaStream_t s) {
   const int C = C1 + C2;
-  FDBM_REQUIRE(C % std::min(C / 4, 32) == 0 && C >= 4, "gn_finalize: unsupported channels %d+%d", C1, C2);
+  FDBM_REQUIRE(C % std::min(C / 4, 32) == 0 && C >= 4 && C <= GN_MAXC, "gn_finalize: unsupported channels %d+%d", C1, C2);
   gn_finalize_kernel<<<B, 256, 0, s>>>(sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;

@@ -100,6 +100,7 @@ struct fdbm_plan {
   // activations
   uint8_t* arena = nullptr;
   int64_t arena_bytes = 0;
+  int64_t sums_pool_bytes = 0;
   // per-call arguments the recorded ops read
   const float* cur_x = nullptr; const float* cur_y = nullptr; const float* cur_t = nullptr; int cur_t_stride = 1;
   float* cur_out = nullptr;
@@ -181,6 +182,10 @@ struct Builder {
   int64_t wp_off = 0;                  // running offset (bytes) into wpacked
   int dense_off = 0;                   // running row offset into the Dense_0 table
   bool dry = true;                     // first pass: sizes only
+  // inference plans: every GroupNorm-statistics buffer is a slice of one pool that a single memset zeroes at the start of
+  // the forward (the per-convolution memsets were ~100 extra graph nodes on the critical path)
+  uint8_t* sums_pool = nullptr;
+  int64_t sums_used = 0;
 
   // ---------------- training: backward ops are recorded per forward composite ("group") and replayed in reverse
   typedef std::function<int(cudaStream_t)> Op;
@@ -280,6 +285,13 @@ struct Builder {
     return reinterpret_cast<Tp*>(P->arena + off);
   }
   void release(const void* p) { if (p && !P->train) arena.release(reinterpret_cast<const uint8_t*>(p) - P->arena); }
+  double* alloc_sums(int64_t n_doubles) {
+    if (train()) return alloc<double>(n_doubles);
+    const int64_t bytes = (n_doubles * 8 + 255) / 256 * 256;
+    sums_used += bytes;
+    if (dry) return reinterpret_cast<double*>(P->arena);          // sizing pass: only counted (the pool is added to the peak)
+    return reinterpret_cast<double*>(sums_pool + sums_used - bytes);
+  }
   Act new_act(int C, int T, int F) {
     Act a; a.C = C; a.T = T; a.F = F;
     // inference plans keep the residual stream in the 16-bit operand format only: the identity shortcut re-reads the
@@ -287,11 +299,11 @@ struct Builder {
     // keep the fp32 master for the backward pass
     if (P->train) a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
     a.h16 = alloc<op_t>(static_cast<int64_t>(P->B) * T * F * C);
-    a.sums = alloc<double>(static_cast<int64_t>(P->B) * C * 2);
+    a.sums = alloc_sums(static_cast<int64_t>(P->B) * C * 2);
     if (P->train) a.grad = galloc(static_cast<int64_t>(P->B) * T * F * C);
     return a;
   }
-  void free_act(Act& a) { release(a.data); release(a.h16); release(a.sums); a.data = nullptr; a.h16 = nullptr; a.sums = nullptr; }
+  void free_act(Act& a) { release(a.data); release(a.h16); if (train()) release(a.sums); a.data = nullptr; a.h16 = nullptr; a.sums = nullptr; }
   // (scale, shift) table of a GroupNorm over the channel concatenation x1 (+ x2): a tiny launch; the consuming
   // convolution applies it while the operand tile sits in shared memory
   float2* norm_table(const double* q1, int C1, const double* q2, int C2, const float* gamma, const float* beta, int T, int F) {
@@ -320,6 +332,7 @@ struct Builder {
       for (int i = 0; i < c.n_seg; ++i) k += static_cast<double>(c.seg[i].taps) * c.seg[i].C;
       flops = 2.0 * c.B * c.T * c.F * c.Cout * k;
     }
+    c.sums_prezeroed = !train();
     op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV, flops);
   }
   void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
@@ -388,7 +401,7 @@ struct Builder {
     // Conv_0 output only feeds GroupNorm_1: keep it in the 16-bit operand format (its statistics are taken
     // from the fp32 accumulators in the conv epilogue, before rounding)
     op_t* h1 = alloc<op_t>(npx * Cout);
-    double* h1_sums = alloc<double>(static_cast<int64_t>(B) * Cout * 2);
+    double* h1_sums = alloc_sums(static_cast<int64_t>(B) * Cout * 2);
     op_t* a0 = nullptr; op_t* xr = nullptr; float2* tab0 = nullptr;
     ConvArgs c0;
     c0.wpack = w0; c0.bias = c0b; c0.bias_b = dense_row >= 0 ? dense + dense_row : nullptr; c0.bias_b_stride = dense_stride;
@@ -439,7 +452,7 @@ struct Builder {
       if (comb) { c.comb_pyr = comb->pyr; c.comb_w = comb->w; c.comb_b = comb->b; c.comb_C = comb->Cp; }
       conv_op(c);
     }
-    release(h1); release(h1_sums); release(tab1);
+    release(h1); if (train()) release(h1_sums); release(tab1);
     release(xr);
 
     if (train()) {
@@ -546,7 +559,8 @@ struct Builder {
     }
     release(tab);
     op_t* o = alloc<op_t>(npx * C);
-    op([=](cudaStream_t s) { return launch_attention(qkv, qkv + C, qkv + 2 * C, 3 * C, B, T * F, C, o, C, s); }, FDBM_OP_ATTN);
+    const int fp32_probs = train() ? 1 : 0;
+    op([=](cudaStream_t s) { return launch_attention(qkv, qkv + C, qkv + 2 * C, 3 * C, B, T * F, C, o, C, s, fp32_probs); }, FDBM_OP_ATTN);
     release(qkv);
     Act out = new_act(C, T, F);
     {
@@ -606,6 +620,12 @@ struct Builder {
     size_t mi = 0;
     auto next = [&]() -> const Mod& { return pl.mods[mi++]; };
     wp_off = 0; dense_off = 0; wd_off = 0; ws_need = 0; groups.clear();
+    sums_used = 0;
+    if (!train() && !dry && P->sums_pool_bytes > 0) {
+      sums_pool = alloc<uint8_t>(P->sums_pool_bytes);
+      uint8_t* pool = sums_pool; const int64_t pool_bytes = P->sums_pool_bytes;
+      op([=](cudaStream_t s) { FDBM_CUDA(cudaMemsetAsync(pool, 0, pool_bytes, s)); return FDBM_OK; }, FDBM_OP_STATS);
+    }
     if (train()) {
       // shared backward scratch: the largest 16-bit operand of the network is [B, T, F, 2 nf] at level 0
       const int64_t big = static_cast<int64_t>(B) * pl.T * pl.F * 2 * nf;
@@ -859,7 +879,8 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   P->arena = reinterpret_cast<uint8_t*>(uintptr_t(1) << 30);      // fake non-null base for the sizing pass
   b1.arena.reset(int64_t(1) << 40);
   if (int rc = b1.build()) return fail(rc);
-  P->arena_bytes = b1.arena.peak();
+  P->sums_pool_bytes = b1.sums_used;
+  P->arena_bytes = b1.arena.peak() + (P->sums_pool_bytes + 1023) / 1024 * 1024;
   P->arena = nullptr;
   P->wpacked_bytes = b1.wp_off;
   P->wpacked_d_bytes = b1.wd_off;

@@ -324,9 +324,9 @@ int launch_dense_all(const float* temb_act, const float* w, const float* bias, i
 }
 
 int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B, int L,
-                     int C, op_t* o, int ldo, cudaStream_t s) {
+                     int C, op_t* o, int ldo, cudaStream_t s, int fp32_probs) {
   FDBM_REQUIRE(C % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "attention: channels / strides must be multiples of 8");
-  if (C == AT_C) {                                     // the backbone's case: tensor-core kernel
+  if (C == AT_C && !fp32_probs) {                      // the backbone's case: tensor-core kernel
     constexpr int kSmem = (AT_BQ + 2 * AT_BK) * AT_PITCH * 2;
     static bool attr_done = false;
     if (!attr_done) {
@@ -361,5 +361,5 @@ extern "C" int fdbm_attention(const void* q, const void* k, const void* v, int b
   FDBM_REQUIRE(q && k && v && o && batch > 0 && L > 0, "fdbm_attention: bad arguments");
   return launch_attention(reinterpret_cast<const op_t*>(q), reinterpret_cast<const op_t*>(k),
                           reinterpret_cast<const op_t*>(v), C, batch, L, C,
-                          reinterpret_cast<op_t*>(o), C, as_stream(stream));
+                          reinterpret_cast<op_t*>(o), C, as_stream(stream), 0);
 }

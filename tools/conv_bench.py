@@ -19,6 +19,9 @@ shapes = [  # T, F, C1, k, C2, Cout, residual, f32 out, sums
     (32, 32, 256, 3, 0, 256, True, True, True),
     (16, 16, 256, 3, 0, 256, True, True, True),
 ]
+shapes.append((256, 256, 64, 1, 0, 128, False, False, True))      # first conv (im2col K-block): the epilogue alone
+if os.environ.get("CB_ONLY"):
+    shapes = [shapes[int(i)] for i in os.environ["CB_ONLY"].split(",")]
 for (T, F, C1, k, C2, Cout, res, f32o, sm) in shapes:
     x1 = torch.randn(B, T, F, C1).to(h16).cuda()
     x2 = torch.randn(B, T, F, C2).to(h16).cuda() if C2 else None
