@@ -129,6 +129,7 @@ struct ConvArgs {
   bool sums_prezeroed = false;             // the caller zeroes `sums` itself (plans: one memset per forward)
   // pyramid epilogue (ncsnpp_v2.py:338-359): out = conv(...)[:, :pyr_C] + bias + FIR-up x2(pyr_prev); fp32 [B,T,F,pyr_C]
   float* pyr_out = nullptr; const float* pyr_prev = nullptr; int pyr_C = 0;
+  bool narrow_n = false;                   // pyramid convolutions: MMA N = 16 (Cout = 16 zero-padded weight rows) instead of 128
   // Combine epilogue (layerspp.py:52-59): out += comb_b[n] + sum_k comb_w[n][k] * comb_pyr[b,t,f,k], applied after
   // `scale`; comb_pyr is the fp32 input pyramid [B,T,F,comb_C] at the output resolution
   const float* comb_pyr = nullptr; const float* comb_w = nullptr; const float* comb_b = nullptr; int comb_C = 0;

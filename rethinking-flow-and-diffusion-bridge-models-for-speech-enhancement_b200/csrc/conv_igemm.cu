@@ -73,6 +73,7 @@ struct ConvParams {
   int n_seg, n_kb;
   SegParams seg[MAX_SEG];
   int tiles_t, tiles_f, n_mtiles, n_nblocks, n_items;
+  int bn;                                  // MMA N = output channels per item: 128, or 16 for the C -> 4 pyramid convolutions
   const float* bias;
   const float* bias_b;
   int bias_b_stride;
@@ -192,7 +193,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           const int ntaps = p.seg[seg_of(kb)].taps;
           for (int tap = 0; tap < ntaps; ++tap, ++kt) {
             mbar_wait(b_empty + stage, phase ^ 1);
-            mbar_expect_tx(b_full + stage, B_TILE_BYTES);
+            mbar_expect_tx(b_full + stage, p.bn * 128);
             tma_load_2d(sB + stage * B_TILE_BYTES, &map_b, b_full + stage, 0, kt * p.Cout + n0);
             if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
           }
@@ -204,7 +205,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     // The whole warp walks the pipeline (so every operand is provably warp-uniform and the compiler emits
     // no per-thread "waterfall" around the uniform-datapath UTCHMMA); one elected lane issues.  Descriptors
     // are built once: only the 14-bit start-address field changes, by a plain add per MMA.
-    const uint32_t idesc = make_idesc_f16(128, BN, kOperandIsBf16);
+    const uint32_t idesc = make_idesc_f16(128, p.bn, kOperandIsBf16);
     const uint64_t a_hi = make_desc_sw128(0, A_SBO) & 0xFFFFFFFF00000000ull;
     const uint64_t b_hi = make_desc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_const = 1u << 16;                                   // LBO field (unused by swizzled K-major)
@@ -709,12 +710,12 @@ int make_act_map(CUtensorMap* map, const op_t* ptr, int B, int T, int F, int C) 
   return make_act_tile_map(map, ptr, B, T, F, C, HALO_F, HALO_T);
 }
 
-int make_weight_map(CUtensorMap* map, const op_t* ptr, int64_t rows) {
+int make_weight_map(CUtensorMap* map, const op_t* ptr, int64_t rows, int bn) {
   EncodeFn enc = get_encode();
   if (!enc) { set_error("cuTensorMapEncodeTiled entry point not available"); return FDBM_ECUDA; }
   cuuint64_t dims[2] = {64, (cuuint64_t)rows};
   cuuint64_t strides[1] = {128};
-  cuuint32_t box[2] = {64, BN};
+  cuuint32_t box[2] = {64, (cuuint32_t)bn};
   cuuint32_t es[2] = {1, 1};
   CUresult r = enc(map, (kOperandIsBf16 ? CU_TENSOR_MAP_DATA_TYPE_BFLOAT16 : CU_TENSOR_MAP_DATA_TYPE_FLOAT16), 2, const_cast<op_t*>(ptr), dims, strides, box, es,
                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
@@ -774,9 +775,10 @@ int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize,
 
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   FDBM_REQUIRE(a.n_seg >= 1 && a.n_seg <= MAX_SEG, "conv_igemm: 1..%d K segments", MAX_SEG);
-  FDBM_REQUIRE(a.Cout % BN == 0, "conv_igemm: Cout must be a multiple of %d (got %d)", BN, a.Cout);
+  const int bn = a.narrow_n ? 16 : BN;
+  FDBM_REQUIRE(a.Cout % bn == 0 && (!a.narrow_n || (a.Cout == 16 && a.pyr_out)), "conv_igemm: Cout must be a multiple of %d (got %d)", bn, a.Cout);
   FDBM_REQUIRE(a.out_f32 || a.out_h16 || a.pyr_out, "conv_igemm: no output");
-  FDBM_REQUIRE(!a.pyr_out || (a.pyr_C >= 1 && a.pyr_C <= 4 && a.Cout == BN && !a.sums), "conv_igemm: bad pyramid epilogue arguments");
+  FDBM_REQUIRE(!a.pyr_out || (a.pyr_C >= 1 && a.pyr_C <= 4 && a.Cout == bn && !a.sums), "conv_igemm: bad pyramid epilogue arguments");
   FDBM_REQUIRE(!a.pyr_prev || (a.T % 2 == 0 && a.F % 2 == 0), "conv_igemm: pyramid level with odd size");
   static bool attr_set = false;
   if (!attr_set) {
@@ -807,10 +809,11 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
     }
   }
   p.n_kb = kb;
-  if (int rc = make_weight_map(&map_b, a.wpack, static_cast<int64_t>(n_kt) * a.Cout)) return rc;
+  if (int rc = make_weight_map(&map_b, a.wpack, static_cast<int64_t>(n_kt) * a.Cout, bn)) return rc;
+  p.bn = bn;
   p.tiles_t = ceil_div(a.T, TILE_T); p.tiles_f = ceil_div(a.F, TILE_F);
   p.n_mtiles = a.B * p.tiles_t * p.tiles_f;
-  p.n_nblocks = a.Cout / BN;
+  p.n_nblocks = a.Cout / bn;
   p.n_items = ceil_div(p.n_mtiles, MT) * p.n_nblocks;
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
   p.residual_h16 = a.residual_h16;

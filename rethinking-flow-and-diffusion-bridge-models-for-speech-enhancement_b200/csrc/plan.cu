@@ -775,13 +775,13 @@ struct Builder {
         const int64_t o_w = param(pre(mc) + "weight", static_cast<int64_t>(Cp) * C * 9), o_b = param(pre(mc) + "bias", Cp);
         const float* gw = pp(o_gw); const float* gb = pp(o_gb);
         const float* w = pp(o_w); const float* b = pp(o_b);
-        // C -> 4 conv on the tensor cores: weight rows padded with zeros to one 128-wide N block
+        // C -> 4 conv on the tensor cores: weight rows padded with zeros to the narrowest MMA N (16)
         op_t* wp = reinterpret_cast<op_t*>(reinterpret_cast<uint8_t*>(P->wpacked) + wp_off);
-        const int64_t wbytes = conv_wpack_bytes(C, 3, 0, 128);
+        const int64_t wbytes = conv_wpack_bytes(C, 3, 0, 16);
         wp_off += (wbytes + 1023) / 1024 * 1024;
         pack_op([=](cudaStream_t s) {
           FDBM_CUDA(cudaMemsetAsync(wp, 0, wbytes, s));
-          return launch_pack_conv_weights(w, C, 3, nullptr, 0, Cp, 128, 0, wp, s);
+          return launch_pack_conv_weights(w, C, 3, nullptr, 0, Cp, 16, 0, wp, s);
         });
         float* pyr_new = alloc<float>(static_cast<int64_t>(B) * Tc * Fc * Cp);
         float* prev = pyramid;
@@ -789,7 +789,7 @@ struct Builder {
         float2* stats = norm_stats(h.sums, C, nullptr, 0, Tc, Fc);
         ConvArgs c;
         c.seg[0] = seg(h.h16, C, 9, tab, C, 1); c.n_seg = 1;     // GroupNorm + SiLU on load
-        c.wpack = wp; c.bias = b; c.B = B; c.T = Tc; c.F = Fc; c.Cout = 128;
+        c.wpack = wp; c.bias = b; c.B = B; c.T = Tc; c.F = Fc; c.Cout = 16; c.narrow_n = true;
         c.pyr_out = pyr_new; c.pyr_prev = prev; c.pyr_C = Cp;
         conv_op(c, 2.0 * B * Tc * Fc * Cp * 9.0 * C);
         release(tab);
