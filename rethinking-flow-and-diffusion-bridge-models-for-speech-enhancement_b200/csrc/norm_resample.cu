@@ -242,135 +242,155 @@ gn_resample16_kernel(const op_t* __restrict__ src1, int C1, const op_t* __restri
   const bool from2 = c0 >= C1;
   const int Cs = from2 ? C2 : C1;
   const op_t* sp = (from2 ? src2 : src1) + static_cast<int64_t>(b) * T * F * Cs + (from2 ? c0 - C1 : c0);
-  float sc[4], sh[4];
+  // packed fp32x2 arithmetic throughout (FFMA2): the pass is instruction-bound otherwise
+  float2 sc[2], sh[2];
   {
     const float4* tp = reinterpret_cast<const float4*>(tab + static_cast<int64_t>(b) * C + c0);
     const float4 e0 = __ldg(tp), e1 = __ldg(tp + 1);
-    sc[0] = 0.5f * e0.x; sh[0] = 0.5f * e0.y; sc[1] = 0.5f * e0.z; sh[1] = 0.5f * e0.w;
-    sc[2] = 0.5f * e1.x; sh[2] = 0.5f * e1.y; sc[3] = 0.5f * e1.z; sh[3] = 0.5f * e1.w;
+    sc[0] = make_float2(0.5f * e0.x, 0.5f * e0.z); sh[0] = make_float2(0.5f * e0.y, 0.5f * e0.w);
+    sc[1] = make_float2(0.5f * e1.x, 0.5f * e1.z); sh[1] = make_float2(0.5f * e1.y, 0.5f * e1.w);
   }
-  // one pixel: raw values and SiLU(GroupNorm(.)) of this thread's 4 channels; zeros outside the image
-  auto load_px = [&](int t, int f, float (&a)[4], float (&r)[4]) {
-    if (t < 0 || t >= T || f < 0 || f >= F) {
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { a[j] = 0.f; r[j] = 0.f; }
-      return;
-    }
-    const uint2 rawv = __ldg(reinterpret_cast<const uint2*>(sp + (static_cast<int64_t>(t) * F + f) * Cs));
+  // one pixel: raw values and SiLU(GroupNorm(.)) of this thread's 4 channels (two float2 each)
+  auto px_act = [&](const uint2 rawv, float2 (&a)[2], float2 (&r)[2]) {
     const op2_t* h2 = reinterpret_cast<const op2_t*>(&rawv);
 #pragma unroll
     for (int w = 0; w < 2; ++w) {
-      const float2 v = op22f2(h2[w]);
-      r[2 * w] = v.x; r[2 * w + 1] = v.y;
-      const op2_t h = f2op2(fmaf(v.x, sc[2 * w], sh[2 * w]), fmaf(v.y, sc[2 * w + 1], sh[2 * w + 1]));
-      const float2 av = op22f2(__hfma2(h, op2_tanh(h), h));
-      a[2 * w] = av.x; a[2 * w + 1] = av.y;
+      r[w] = op22f2(h2[w]);
+      const float2 y = __ffma2_rn(r[w], sc[w], sh[w]);
+      const op2_t h = f2op2(y.x, y.y);
+      a[w] = op22f2(__hfma2(h, op2_tanh(h), h));
     }
   };
-  auto store_px = [&](int to, int fo, const float (&a)[4], const float (&r)[4]) {
+  auto store_px = [&](int to, int fo, const float2 (&a)[2], const float2 (&r)[2]) {
     if (fo >= Fo) return;
     const int64_t o = ((static_cast<int64_t>(b) * To + to) * Fo + fo) * C + c0;
-    *reinterpret_cast<uint2*>(act_out + o) = make_uint2(pack_op2(a[0], a[1]), pack_op2(a[2], a[3]));
-    *reinterpret_cast<uint2*>(raw_out + o) = make_uint2(pack_op2(r[0], r[1]), pack_op2(r[2], r[3]));
+    *reinterpret_cast<uint2*>(act_out + o) = make_uint2(pack_op2(a[0].x, a[0].y), pack_op2(a[1].x, a[1].y));
+    *reinterpret_cast<uint2*>(raw_out + o) = make_uint2(pack_op2(r[0].x, r[0].y), pack_op2(r[1].x, r[1].y));
   };
+  const float2 zero2 = make_float2(0.f, 0.f);
 
   if (MODE == 1) {
-    // down: o[i] = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8 per axis; output columns fo0, fo0 + 1
+    // down: o[i] = (x[2i-1] + 3 x[2i] + 3 x[2i+1] + x[2i+2]) / 8 per axis; output columns fo0, fo0 + 1 from input
+    // columns fi0 .. fi0 + 5 (zeros outside the image)
     const int fo0 = 2 * strip, fi0 = 2 * fo0 - 1;
-    // horizontally filtered row t -> ha/hr[2 output columns][4 channels]
-    auto hrow = [&](int t, float (&ha)[2][4], float (&hr)[2][4]) {
+    uint32_t okf = 0;
 #pragma unroll
-      for (int j = 0; j < 2; ++j)
+    for (int k = 0; k < 6; ++k) okf |= (fi0 + k >= 0 && fi0 + k < F) ? (1u << k) : 0u;
+    const float2 w1 = make_float2(0.125f, 0.125f), w3 = make_float2(0.375f, 0.375f);
+    // horizontally filtered row t -> ha/hr[2 output columns][2 float2]
+    auto hrow = [&](int t, float2 (&ha)[2][2], float2 (&hr)[2][2]) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { ha[j][c] = 0.f; hr[j][c] = 0.f; }
+      for (int j = 0; j < 2; ++j) { ha[j][0] = zero2; ha[j][1] = zero2; hr[j][0] = zero2; hr[j][1] = zero2; }
       if (t < 0 || t >= T) return;
+      const op_t* rp = sp + (static_cast<int64_t>(t) * F + fi0) * Cs;
+      uint2 raw[6];
+#pragma unroll
+      for (int k = 0; k < 6; ++k) raw[k] = ((okf >> k) & 1) ? __ldg(reinterpret_cast<const uint2*>(rp + k * Cs)) : make_uint2(0u, 0u);
 #pragma unroll
       for (int k = 0; k < 6; ++k) {
-        float a[4], r[4];
-        load_px(t, fi0 + k, a, r);
+        float2 a[2], r[2];
+        px_act(raw[k], a, r);
+        if (!((okf >> k) & 1)) { a[0] = zero2; a[1] = zero2; }           // the activation of a padding zero is not zero
         if (k < 4) {
-          const float w = (k == 0 || k == 3) ? 0.125f : 0.375f;
+          const float2 w = (k == 0 || k == 3) ? w1 : w3;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { ha[0][c] = fmaf(w, a[c], ha[0][c]); hr[0][c] = fmaf(w, r[c], hr[0][c]); }
+          for (int c = 0; c < 2; ++c) { ha[0][c] = __ffma2_rn(w, a[c], ha[0][c]); hr[0][c] = __ffma2_rn(w, r[c], hr[0][c]); }
         }
         if (k >= 2) {
-          const float w = (k == 2 || k == 5) ? 0.125f : 0.375f;
+          const float2 w = (k == 2 || k == 5) ? w1 : w3;
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { ha[1][c] = fmaf(w, a[c], ha[1][c]); hr[1][c] = fmaf(w, r[c], hr[1][c]); }
+          for (int c = 0; c < 2; ++c) { ha[1][c] = __ffma2_rn(w, a[c], ha[1][c]); hr[1][c] = __ffma2_rn(w, r[c], hr[1][c]); }
         }
       }
     };
     const int to0 = chunk * RS_ROWS, to1 = min(To, to0 + RS_ROWS);
-    float ca[2][4], cr[2][4], na[2][4], nr[2][4], ha[2][4], hr[2][4];
+    float2 ca[2][2], cr[2][2], na[2][2], nr[2][2], ha[2][2], hr[2][2];
     hrow(2 * to0 - 1, ha, hr);
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { ca[j][c] = 0.125f * ha[j][c]; cr[j][c] = 0.125f * hr[j][c]; }
+      for (int c = 0; c < 2; ++c) { ca[j][c] = __fmul2_rn(w1, ha[j][c]); cr[j][c] = __fmul2_rn(w1, hr[j][c]); }
     hrow(2 * to0, ha, hr);
 #pragma unroll
     for (int j = 0; j < 2; ++j)
 #pragma unroll
-      for (int c = 0; c < 4; ++c) { ca[j][c] = fmaf(0.375f, ha[j][c], ca[j][c]); cr[j][c] = fmaf(0.375f, hr[j][c], cr[j][c]); }
+      for (int c = 0; c < 2; ++c) { ca[j][c] = __ffma2_rn(w3, ha[j][c], ca[j][c]); cr[j][c] = __ffma2_rn(w3, hr[j][c], cr[j][c]); }
 #pragma unroll 1
     for (int to = to0; to < to1; ++to) {
       hrow(2 * to + 1, ha, hr);
 #pragma unroll
       for (int j = 0; j < 2; ++j)
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          ca[j][c] = fmaf(0.375f, ha[j][c], ca[j][c]); cr[j][c] = fmaf(0.375f, hr[j][c], cr[j][c]);
-          na[j][c] = 0.125f * ha[j][c]; nr[j][c] = 0.125f * hr[j][c];
+        for (int c = 0; c < 2; ++c) {
+          ca[j][c] = __ffma2_rn(w3, ha[j][c], ca[j][c]); cr[j][c] = __ffma2_rn(w3, hr[j][c], cr[j][c]);
+          na[j][c] = __fmul2_rn(w1, ha[j][c]); nr[j][c] = __fmul2_rn(w1, hr[j][c]);
         }
       hrow(2 * to + 2, ha, hr);
 #pragma unroll
       for (int j = 0; j < 2; ++j) {
 #pragma unroll
-        for (int c = 0; c < 4; ++c) {
-          ca[j][c] = fmaf(0.125f, ha[j][c], ca[j][c]); cr[j][c] = fmaf(0.125f, hr[j][c], cr[j][c]);
-          na[j][c] = fmaf(0.375f, ha[j][c], na[j][c]); nr[j][c] = fmaf(0.375f, hr[j][c], nr[j][c]);
+        for (int c = 0; c < 2; ++c) {
+          ca[j][c] = __ffma2_rn(w1, ha[j][c], ca[j][c]); cr[j][c] = __ffma2_rn(w1, hr[j][c], cr[j][c]);
+          na[j][c] = __ffma2_rn(w3, ha[j][c], na[j][c]); nr[j][c] = __ffma2_rn(w3, hr[j][c], nr[j][c]);
         }
         store_px(to, fo0 + j, ca[j], cr[j]);
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { ca[j][c] = na[j][c]; cr[j][c] = nr[j][c]; }
+        for (int c = 0; c < 2; ++c) { ca[j][c] = na[j][c]; cr[j][c] = nr[j][c]; }
       }
     }
   } else {
-    // up: o[2i] = (x[i-1] + 3 x[i]) / 4, o[2i+1] = (3 x[i] + x[i+1]) / 4 per axis; input columns f0, f0 + 1 -> 4 output columns
+    // up: o[2i] = (x[i-1] + 3 x[i]) / 4, o[2i+1] = (3 x[i] + x[i+1]) / 4 per axis; input columns f0 - 1 .. f0 + 2 ->
+    // output columns 2 f0 .. 2 f0 + 3
     const int f0 = 2 * strip;
-    auto hrow = [&](int t, float (&ha)[4][4], float (&hr)[4][4]) {
-      float a[4][4], r[4][4];
+    uint32_t okf = 0;
 #pragma unroll
-      for (int k = 0; k < 4; ++k) load_px(t, f0 - 1 + k, a[k], r[k]);
+    for (int k = 0; k < 4; ++k) okf |= (f0 - 1 + k >= 0 && f0 - 1 + k < F) ? (1u << k) : 0u;
+    const float2 q1 = make_float2(0.25f, 0.25f), q3 = make_float2(0.75f, 0.75f);
+    auto hrow = [&](int t, float2 (&ha)[4][2], float2 (&hr)[4][2]) {
+      float2 a[4][2], r[4][2];
+      if (t < 0 || t >= T) {
 #pragma unroll
-      for (int c = 0; c < 4; ++c) {
-        ha[0][c] = 0.25f * a[0][c] + 0.75f * a[1][c]; hr[0][c] = 0.25f * r[0][c] + 0.75f * r[1][c];
-        ha[1][c] = 0.75f * a[1][c] + 0.25f * a[2][c]; hr[1][c] = 0.75f * r[1][c] + 0.25f * r[2][c];
-        ha[2][c] = 0.25f * a[1][c] + 0.75f * a[2][c]; hr[2][c] = 0.25f * r[1][c] + 0.75f * r[2][c];
-        ha[3][c] = 0.75f * a[2][c] + 0.25f * a[3][c]; hr[3][c] = 0.75f * r[2][c] + 0.25f * r[3][c];
+        for (int k = 0; k < 4; ++k) { ha[k][0] = zero2; ha[k][1] = zero2; hr[k][0] = zero2; hr[k][1] = zero2; }
+        return;
+      }
+      const op_t* rp = sp + (static_cast<int64_t>(t) * F + f0 - 1) * Cs;
+      uint2 raw[4];
+#pragma unroll
+      for (int k = 0; k < 4; ++k) raw[k] = ((okf >> k) & 1) ? __ldg(reinterpret_cast<const uint2*>(rp + k * Cs)) : make_uint2(0u, 0u);
+#pragma unroll
+      for (int k = 0; k < 4; ++k) {
+        px_act(raw[k], a[k], r[k]);
+        if (!((okf >> k) & 1)) { a[k][0] = zero2; a[k][1] = zero2; }
+      }
+#pragma unroll
+      for (int c = 0; c < 2; ++c) {
+        ha[0][c] = __ffma2_rn(q1, a[0][c], __fmul2_rn(q3, a[1][c])); hr[0][c] = __ffma2_rn(q1, r[0][c], __fmul2_rn(q3, r[1][c]));
+        ha[1][c] = __ffma2_rn(q3, a[1][c], __fmul2_rn(q1, a[2][c])); hr[1][c] = __ffma2_rn(q3, r[1][c], __fmul2_rn(q1, r[2][c]));
+        ha[2][c] = __ffma2_rn(q1, a[1][c], __fmul2_rn(q3, a[2][c])); hr[2][c] = __ffma2_rn(q1, r[1][c], __fmul2_rn(q3, r[2][c]));
+        ha[3][c] = __ffma2_rn(q3, a[2][c], __fmul2_rn(q1, a[3][c])); hr[3][c] = __ffma2_rn(q3, r[2][c], __fmul2_rn(q1, r[3][c]));
       }
     };
     const int i0 = chunk * RS_ROWS, i1 = min(T, i0 + RS_ROWS);
-    float pa[4][4], pr[4][4], qa[4][4], qr[4][4];
+    float2 pa[4][2], pr[4][2], qa[4][2], qr[4][2];
     hrow(i0 - 1, pa, pr);
 #pragma unroll 1
     for (int i = i0; i <= i1; ++i) {
       hrow(i, qa, qr);
 #pragma unroll
       for (int k = 0; k < 4; ++k) {
-        float oa[4], orr[4];
+        float2 oa[2], orr[2];
         if (i > i0) {                                    // odd output row of the previous input row
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { oa[c] = 0.75f * pa[k][c] + 0.25f * qa[k][c]; orr[c] = 0.75f * pr[k][c] + 0.25f * qr[k][c]; }
+          for (int c = 0; c < 2; ++c) { oa[c] = __ffma2_rn(q3, pa[k][c], __fmul2_rn(q1, qa[k][c])); orr[c] = __ffma2_rn(q3, pr[k][c], __fmul2_rn(q1, qr[k][c])); }
           store_px(2 * i - 1, 2 * f0 + k, oa, orr);
         }
         if (i < i1) {                                    // even output row of this input row
 #pragma unroll
-          for (int c = 0; c < 4; ++c) { oa[c] = 0.25f * pa[k][c] + 0.75f * qa[k][c]; orr[c] = 0.25f * pr[k][c] + 0.75f * qr[k][c]; }
+          for (int c = 0; c < 2; ++c) { oa[c] = __ffma2_rn(q1, pa[k][c], __fmul2_rn(q3, qa[k][c])); orr[c] = __ffma2_rn(q1, pr[k][c], __fmul2_rn(q3, qr[k][c])); }
           store_px(2 * i, 2 * f0 + k, oa, orr);
         }
 #pragma unroll
-        for (int c = 0; c < 4; ++c) { pa[k][c] = qa[k][c]; pr[k][c] = qr[k][c]; }
+        for (int c = 0; c < 2; ++c) { pa[k][c] = qa[k][c]; pr[k][c] = qr[k][c]; }
       }
     }
   }

@@ -48,26 +48,31 @@ pack_input_kernel(const float2* __restrict__ x, const float2* __restrict__ y, in
 // with k = (kf*3 + kt)*Cin + ci (zero border, zero for k >= 9*Cin).  The convolution itself then runs on
 // the tensor cores as a K=64 GEMM with the fused-statistics epilogue (conv_igemm, ksize 1).
 // ------------------------------------------------------------------------------------------------
+template <int CIN>
 __global__ void __launch_bounds__(256)
-im2col_input_kernel(const float* __restrict__ in, int Cin, int B, int T, int F, uint4* __restrict__ out) {
-  const int64_t total = static_cast<int64_t>(B) * T * F * 8;           // 8 groups of 8 k-values per pixel
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int g = static_cast<int>(i & 7);
-    const int64_t p = i >> 3;
-    const int f = static_cast<int>(p % F);
-    const int t = static_cast<int>((p / F) % T);
-    const int b = static_cast<int>(p / (static_cast<int64_t>(F) * T));
+im2col_input_kernel(const float* __restrict__ in, int B, int T, int F, uint4* __restrict__ out) {
+  constexpr int TPG = 8 / CIN;                                         // taps per group of 8 k-values
+  const int total = B * T * F * 8;                                     // 8 groups of 8 k-values per pixel (host checks < 2^31)
+  for (int i = blockIdx.x * 256 + threadIdx.x; i < total; i += 256 * gridDim.x) {
+    const int g = i & 7;
+    const int p = i >> 3;
+    const int f = p % F;
+    const int bt = p / F;
+    const int t = bt % T;
     float v[8];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
-      const int k = g * 8 + j;
-      const int tap = k / Cin, ci = k % Cin;
-      float x = 0.f;
-      if (tap < 9) {
-        const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
-        if (ff >= 0 && ff < F && tt >= 0 && tt < T) x = in[((static_cast<int64_t>(b) * T + tt) * F + ff) * Cin + ci];
+    for (int u = 0; u < TPG; ++u) {
+      const int tap = g * TPG + u;
+      const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
+      const bool ok = tap < 9 && ff >= 0 && ff < F && tt >= 0 && tt < T;
+      const float* src = in + (static_cast<int64_t>(bt - t + tt) * F + ff) * CIN;
+      if (CIN == 4) {
+        const float4 x = ok ? __ldg(reinterpret_cast<const float4*>(src)) : make_float4(0.f, 0.f, 0.f, 0.f);
+        v[4 * u] = x.x; v[4 * u + 1] = x.y; v[4 * u + 2] = x.z; v[4 * u + 3] = x.w;
+      } else {
+        const float2 x = ok ? __ldg(reinterpret_cast<const float2*>(src)) : make_float2(0.f, 0.f);
+        v[2 * u] = x.x; v[2 * u + 1] = x.y;
       }
-      v[j] = x;
     }
     out[i] = make_uint4(pack_op2(v[0], v[1]), pack_op2(v[2], v[3]), pack_op2(v[4], v[5]), pack_op2(v[6], v[7]));
   }
@@ -274,7 +279,9 @@ int launch_im2col_input(const float* in, int Cin, int B, int T, int F, op_t* out
   FDBM_REQUIRE(Cin == 4 || Cin == 2, "im2col_input: Cin must be 2 or 4");
   const int64_t total = static_cast<int64_t>(B) * T * F * 8;
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), static_cast<int64_t>(num_sms()) * 16));
-  im2col_input_kernel<<<grid, 256, 0, s>>>(in, Cin, B, T, F, reinterpret_cast<uint4*>(out));
+  FDBM_REQUIRE(total < (1ll << 31), "im2col_input: tensor too large");
+  if (Cin == 4) im2col_input_kernel<4><<<grid, 256, 0, s>>>(in, B, T, F, reinterpret_cast<uint4*>(out));
+  else im2col_input_kernel<2><<<grid, 256, 0, s>>>(in, B, T, F, reinterpret_cast<uint4*>(out));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
