@@ -333,6 +333,15 @@ struct Builder {
       flops = 2.0 * c.B * c.T * c.F * c.Cout * k;
     }
     c.sums_prezeroed = !train();
+    if (c.bias_b && !train()) {
+      fdbm_plan* plp = P;
+      op([=](cudaStream_t s) {
+        ConvArgs cc = c;
+        if (plp->cur_t_stride == 0) cc.bias_b_stride = 0;          // uniform time: all utterances share FiLM row 0
+        return launch_conv_igemm(cc, s);
+      }, FDBM_OP_CONV, flops);
+      return;
+    }
     op([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV, flops);
   }
   void pack_op(std::function<int(cudaStream_t)> f) { if (!dry) P->pack_ops.push_back(std::move(f)); }
@@ -661,10 +670,11 @@ struct Builder {
       dense = alloc<float>(static_cast<int64_t>(B) * rows);
       const float* dwp = pp(dw0); const float* dbp = pp(db0);
       fdbm_plan* plp = P;
+      // the sampler passes one time for the whole batch (stride 0): one embedding row, read by every utterance
       op([=](cudaStream_t s) {
-        return launch_temb(plp->cur_t, fw, nf, w1, b1, w2, b2, B, plp->cur_t_stride, temb_act, s);
+        return launch_temb(plp->cur_t, fw, nf, w1, b1, w2, b2, plp->cur_t_stride == 0 ? 1 : B, plp->cur_t_stride, temb_act, s);
       }, FDBM_OP_SMALL);
-      op([=](cudaStream_t s) { return launch_dense_all(temb_act, dwp, dbp, B, 4 * nf, rows, dense, s); }, FDBM_OP_SMALL);
+      op([=](cudaStream_t s) { return launch_dense_all(temb_act, dwp, dbp, plp->cur_t_stride == 0 ? 1 : B, 4 * nf, rows, dense, s); }, FDBM_OP_SMALL);
       if (train()) {
         // first group = last to run in backward: by then every block has left its FiLM gradient in d_dense
         d_dense = alloc<float>(static_cast<int64_t>(B) * rows);
