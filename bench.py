@@ -334,7 +334,7 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "64")))
+    ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "128")))
     ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train"],

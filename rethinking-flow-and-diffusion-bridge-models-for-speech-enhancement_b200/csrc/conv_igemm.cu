@@ -176,7 +176,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           const uint32_t e = p.ksched[i];
           const int sgi = e & 15, c0 = ((e >> 4) & 0xFFF) * 64;
           const int halo = p.seg[sgi].halo;
-          mbar_wait(a_empty + stage, phase ^ 1);
+          mbar_wait_relaxed(a_empty + stage, phase ^ 1);
           mbar_expect_tx(a_full + stage, n_valid * (halo ? A_TILE_BYTES : A_TILE1_BYTES));
           const CUtensorMap* map = sgi == 0 ? &map_a0 : (sgi == 1 ? &map_a1 : &map_a2);
           for (int j = 0; j < MT; ++j) {
@@ -199,7 +199,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           const int ntaps = p.seg[e & 15].taps;
           int kt = e >> 16;
           for (int tap = 0; tap < ntaps; ++tap, ++kt) {
-            mbar_wait(b_empty + stage, phase ^ 1);
+            mbar_wait_relaxed(b_empty + stage, phase ^ 1);
             mbar_expect_tx(b_full + stage, p.bn * 128);
             tma_load_2d(sB + stage * B_TILE_BYTES, &map_b, b_full + stage, 0, kt * p.Cout + n0);
             if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
@@ -302,7 +302,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
         }
-        mbar_wait(a_full + stage, phase);
+        mbar_wait_relaxed(a_full + stage, phase);
         if (sg.norm) {
 #pragma unroll
           for (int j = 0; j < MT; ++j) {
@@ -400,7 +400,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int ct = item / p.n_nblocks;
       const int nblk = item % p.n_nblocks;
       const int n0 = nblk * BN;
-      mbar_wait(acc_full + as, pacc);
+      mbar_wait_relaxed(acc_full + as, pacc);
       fence_after_sync();
       for (int j = eg; j <= eg; ++j) {
         const TileCoord tc = decode_tile(p, ct * MT + j);
