@@ -157,9 +157,9 @@ def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None):
     return seconds / dt, dt * 1e3, sample, cores
 
 
-# dram bytes (read + write) of all conv_igemm launches of ONE forward at micro-batch 32, T=256, from the ncu --set full
-# capture summarised in profiles/r01c_conv_traffic.txt (22.149 GB read + 18.759 GB written)
-NCU_CONV_DRAM_GB_PER_FORWARD_MB32 = 40.908
+# dram bytes (read + write) of all 114 conv_igemm launches of ONE forward at T=256, by micro-batch, from the ncu capture
+# summarised in profiles/r01i_conv_traffic.txt (82.518 GB read + 39.090 GB written at micro-batch 128)
+NCU_CONV_DRAM_GB_PER_FORWARD = {128: 121.608}
 
 
 def hbm_kernel_leg(model, waves, dev, reps=20):
@@ -462,9 +462,10 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                    "traffic": NCU_CONV_DRAM_GB_PER_FORWARD_MB32 * 1e9 / max(1, n_conv) if (mb == 32 and n_frames == 256 and not predictive) else None,
+                    "traffic": NCU_CONV_DRAM_GB_PER_FORWARD[mb] * 1e9 / max(1, n_conv)
+                    if (mb in NCU_CONV_DRAM_GB_PER_FORWARD and n_frames == 256 and not predictive) else None,
                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one "
-                                    "forward at micro-batch 32, ncu --set full, profiles/r01c_conv_traffic.txt) / launches",
+                                    "forward at this micro-batch, ncu, profiles/r01i_conv_traffic.txt) / launches",
                     "launches_per_forward": n_conv,
                     "avg_launch_ms": conv_ms / max(1, n_conv),
                     "algorithmic_gflop_per_forward_per_utt": conv_flops / mb / 1e9}
