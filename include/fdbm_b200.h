@@ -66,6 +66,14 @@ int fdbm_stft_compress(const float* wave, int batch, int64_t n_samples, int64_t 
                        int transform_type, float spec_factor, float abs_exponent,
                        int pad_mode, int n_frames_out, float* spec, void* stream);
 
+/* Variable-length batch (the callers' side of infer_folder.py:91-121: every file has its own length): `lengths`
+ * is a DEVICE int32 [B] of per-utterance sample counts, min/max_samples their host-side bounds; utterance b is framed,
+ * reflect-padded and frame-padded (pad_spec) from ITS OWN length, so each row equals the single-utterance call. */
+int fdbm_stft_compress_var(const float* wave, int batch, const int* lengths, int64_t min_samples, int64_t max_samples,
+                           int64_t wave_stride, const float* window, int n_fft, int hop,
+                           int transform_type, float spec_factor, float abs_exponent,
+                           int pad_mode, int n_frames_out, float* spec, void* stream);
+
 /* Spectral back end.  Replaces BridgeModel.to_audio (fdbm/model.py:376-377) = spec_back
  * (fdbm/data_module.py:188-199) + torch.istft (:227-229): de-compress, irFFT, window,
  * overlap-add, divide by the window-square envelope, drop n_fft/2 samples, cut to `length`.
@@ -74,6 +82,12 @@ int fdbm_decompress_istft(const float* spec, int batch, int n_frames,
                           const float* window, int n_fft, int hop,
                           int transform_type, float spec_factor, float abs_exponent,
                           int64_t length, int64_t wave_stride, float* wave, void* stream);
+
+/* Variable-length batch: utterance b is cut to lengths[b] (device int32 [B]); samples beyond it are not written. */
+int fdbm_decompress_istft_var(const float* spec, int batch, int n_frames,
+                              const float* window, int n_fft, int hop,
+                              int transform_type, float spec_factor, float abs_exponent,
+                              const int* lengths, int64_t max_length, int64_t wave_stride, float* wave, void* stream);
 
 /* Unfused pieces of the same front/back end, for callers that keep the reference's call sequence:
  * spec_fwd / spec_back (fdbm/data_module.py:173-199; inverse = 0 / 1) over n_complex elements, and

@@ -164,7 +164,7 @@ __device__ __forceinline__ void fill_twiddles(float2* tw) {
 }
 
 __global__ void __launch_bounds__(WARPS * 32)
-stft_compress_kernel(const float* __restrict__ wave, int n_samples, int64_t wave_stride,
+stft_compress_kernel(const float* __restrict__ wave, int n_samples, const int* __restrict__ lengths, int64_t wave_stride,
                      const float* __restrict__ window, int hop, int transform, float factor, float expo,
                      int pad_mode, int M, int n_frames_out, float2* __restrict__ spec) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -173,6 +173,10 @@ stft_compress_kernel(const float* __restrict__ wave, int n_samples, int64_t wave
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
   const float* x = wave + static_cast<int64_t>(b) * wave_stride;
+  if (lengths) {                                        // variable-length batch: this utterance's own sample / frame count
+    n_samples = __ldg(lengths + b);
+    M = 1 + n_samples / hop;
+  }
 
   float2* z = sm.work[warp];
   const int ta = t0 + 2 * warp, tb = ta + 1;
@@ -242,12 +246,13 @@ stft_compress_kernel(const float* __restrict__ wave, int n_samples, int64_t wave
 // frames in that buffer for the block's overlap-add.
 __global__ void __launch_bounds__(WARPS * 32)
 decompress_istft_kernel(const float2* __restrict__ spec, int M, const float* __restrict__ window, int hop,
-                        int transform, float factor, float expo, int64_t length, int64_t wave_stride,
-                        float* __restrict__ wave) {
+                        int transform, float factor, float expo, int64_t length, const int* __restrict__ lengths,
+                        int64_t wave_stride, float* __restrict__ wave) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int b = blockIdx.y;
+  if (lengths) length = __ldg(lengths + b);    // variable-length batch: samples beyond this utterance's length are not written
   const int R = NFFT / hop;
   constexpr int NF = 2 * WARPS;                // frames per block
   const int FRB = NF - (R - 1);                // hop segments (padded timeline) completed by this block
@@ -400,18 +405,19 @@ extern "C" int fdbm_pad_spec(const float* in, int64_t rows, int n_frames, int pa
   return FDBM_OK;
 }
 
-extern "C" int fdbm_stft_compress(const float* wave, int batch, int64_t n_samples, int64_t wave_stride,
-                                  const float* window, int n_fft, int hop, int transform_type, float spec_factor,
-                                  float abs_exponent, int pad_mode, int n_frames_out, float* spec, void* stream) {
+static int stft_launch(const char* who, const float* wave, int batch, int64_t max_samples, int64_t min_samples, const int* lengths,
+                       int64_t wave_stride, const float* window, int n_fft, int hop, int transform_type, float spec_factor,
+                       float abs_exponent, int pad_mode, int n_frames_out, float* spec, void* stream) {
   if (int rc = require_sm100()) return rc;
-  FDBM_REQUIRE(n_fft == NFFT, "fdbm_stft_compress: n_fft must be 512 (got %d)", n_fft);
-  FDBM_REQUIRE(hop > 0 && NFFT % hop == 0 && NFFT / hop <= MAXR && NFFT / hop >= 1, "fdbm_stft_compress: hop %d unsupported", hop);
-  FDBM_REQUIRE(batch > 0 && n_samples > NFFT / 2 && n_samples < (1ll << 30), "fdbm_stft_compress: need batch > 0 and n_fft/2 < n_samples < 2^30");
-  FDBM_REQUIRE(transform_type >= 0 && transform_type <= 2 && pad_mode >= 0 && pad_mode <= 2, "fdbm_stft_compress: bad enum");
-  const int M = 1 + static_cast<int>(n_samples / hop);
-  FDBM_REQUIRE(n_frames_out >= M, "fdbm_stft_compress: n_frames_out %d < frame count %d", n_frames_out, M);
-  FDBM_REQUIRE(pad_mode != FDBM_PAD_REFLECTION || n_frames_out - M < M, "fdbm_stft_compress: reflection pad wider than the input");
-  FDBM_REQUIRE(wave && window && spec && wave_stride >= n_samples, "fdbm_stft_compress: null pointer or bad stride");
+  FDBM_REQUIRE(n_fft == NFFT, "%s: n_fft must be 512 (got %d)", who, n_fft);
+  FDBM_REQUIRE(hop > 0 && NFFT % hop == 0 && NFFT / hop <= MAXR && NFFT / hop >= 1, "%s: hop %d unsupported", who, hop);
+  FDBM_REQUIRE(batch > 0 && min_samples > NFFT / 2 && max_samples >= min_samples && max_samples < (1ll << 30),
+               "%s: need batch > 0 and n_fft/2 < n_samples < 2^30", who);
+  FDBM_REQUIRE(transform_type >= 0 && transform_type <= 2 && pad_mode >= 0 && pad_mode <= 2, "%s: bad enum", who);
+  const int M = 1 + static_cast<int>(max_samples / hop), M_min = 1 + static_cast<int>(min_samples / hop);
+  FDBM_REQUIRE(n_frames_out >= M, "%s: n_frames_out %d < frame count %d", who, n_frames_out, M);
+  FDBM_REQUIRE(pad_mode != FDBM_PAD_REFLECTION || n_frames_out - M_min < M_min, "%s: reflection pad wider than the input", who);
+  FDBM_REQUIRE(wave && window && spec && wave_stride >= max_samples, "%s: null pointer or bad stride", who);
   static bool attr_set = false;
   if (!attr_set) {
     FDBM_CUDA(cudaFuncSetAttribute(stft_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem)));
@@ -419,21 +425,37 @@ extern "C" int fdbm_stft_compress(const float* wave, int batch, int64_t n_sample
   }
   dim3 grid(ceil_div(n_frames_out, FR), batch);
   stft_compress_kernel<<<grid, WARPS * 32, sizeof(SpecSmem), as_stream(stream)>>>(
-      wave, static_cast<int>(n_samples), wave_stride, window, hop, transform_type, spec_factor, abs_exponent, pad_mode, M, n_frames_out,
-      reinterpret_cast<float2*>(spec));
+      wave, static_cast<int>(max_samples), lengths, wave_stride, window, hop, transform_type, spec_factor, abs_exponent, pad_mode, M,
+      n_frames_out, reinterpret_cast<float2*>(spec));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
 
-extern "C" int fdbm_decompress_istft(const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
-                                     int transform_type, float spec_factor, float abs_exponent, int64_t length,
-                                     int64_t wave_stride, float* wave, void* stream) {
+extern "C" int fdbm_stft_compress(const float* wave, int batch, int64_t n_samples, int64_t wave_stride,
+                                  const float* window, int n_fft, int hop, int transform_type, float spec_factor,
+                                  float abs_exponent, int pad_mode, int n_frames_out, float* spec, void* stream) {
+  return stft_launch("fdbm_stft_compress", wave, batch, n_samples, n_samples, nullptr, wave_stride, window, n_fft, hop, transform_type,
+                     spec_factor, abs_exponent, pad_mode, n_frames_out, spec, stream);
+}
+
+extern "C" int fdbm_stft_compress_var(const float* wave, int batch, const int* lengths, int64_t min_samples, int64_t max_samples,
+                                      int64_t wave_stride, const float* window, int n_fft, int hop, int transform_type,
+                                      float spec_factor, float abs_exponent, int pad_mode, int n_frames_out, float* spec,
+                                      void* stream) {
+  FDBM_REQUIRE(lengths, "fdbm_stft_compress_var: null lengths");
+  return stft_launch("fdbm_stft_compress_var", wave, batch, max_samples, min_samples, lengths, wave_stride, window, n_fft, hop,
+                     transform_type, spec_factor, abs_exponent, pad_mode, n_frames_out, spec, stream);
+}
+
+static int istft_launch(const char* who, const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
+                        int transform_type, float spec_factor, float abs_exponent, int64_t length, const int* lengths,
+                        int64_t wave_stride, float* wave, void* stream) {
   if (int rc = require_sm100()) return rc;
-  FDBM_REQUIRE(n_fft == NFFT, "fdbm_decompress_istft: n_fft must be 512 (got %d)", n_fft);
-  FDBM_REQUIRE(hop > 0 && NFFT % hop == 0 && NFFT / hop <= MAXR, "fdbm_decompress_istft: hop %d unsupported", hop);
-  FDBM_REQUIRE(batch > 0 && n_frames > 0 && length > 0 && wave_stride >= length, "fdbm_decompress_istft: bad sizes");
-  FDBM_REQUIRE(transform_type >= 0 && transform_type <= 2, "fdbm_decompress_istft: bad transform");
-  FDBM_REQUIRE(spec && window && wave, "fdbm_decompress_istft: null pointer");
+  FDBM_REQUIRE(n_fft == NFFT, "%s: n_fft must be 512 (got %d)", who, n_fft);
+  FDBM_REQUIRE(hop > 0 && NFFT % hop == 0 && NFFT / hop <= MAXR, "%s: hop %d unsupported", who, hop);
+  FDBM_REQUIRE(batch > 0 && n_frames > 0 && length > 0 && wave_stride >= length, "%s: bad sizes", who);
+  FDBM_REQUIRE(transform_type >= 0 && transform_type <= 2, "%s: bad transform", who);
+  FDBM_REQUIRE(spec && window && wave, "%s: null pointer", who);
   static bool attr_set = false;
   if (!attr_set) {
     FDBM_CUDA(cudaFuncSetAttribute(decompress_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem)));
@@ -443,8 +465,23 @@ extern "C" int fdbm_decompress_istft(const float* spec, int batch, int n_frames,
   const int frb = 2 * WARPS - (NFFT / hop - 1);                  // hop segments completed per block
   dim3 grid(static_cast<unsigned>(ceil_div64(n_seg, frb)), batch);
   decompress_istft_kernel<<<grid, WARPS * 32, sizeof(SpecSmem), as_stream(stream)>>>(
-      reinterpret_cast<const float2*>(spec), n_frames, window, hop, transform_type, spec_factor, abs_exponent, length,
+      reinterpret_cast<const float2*>(spec), n_frames, window, hop, transform_type, spec_factor, abs_exponent, length, lengths,
       wave_stride, wave);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
+}
+
+extern "C" int fdbm_decompress_istft(const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
+                                     int transform_type, float spec_factor, float abs_exponent, int64_t length,
+                                     int64_t wave_stride, float* wave, void* stream) {
+  return istft_launch("fdbm_decompress_istft", spec, batch, n_frames, window, n_fft, hop, transform_type, spec_factor, abs_exponent,
+                      length, nullptr, wave_stride, wave, stream);
+}
+
+extern "C" int fdbm_decompress_istft_var(const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
+                                         int transform_type, float spec_factor, float abs_exponent, const int* lengths,
+                                         int64_t max_length, int64_t wave_stride, float* wave, void* stream) {
+  FDBM_REQUIRE(lengths, "fdbm_decompress_istft_var: null lengths");
+  return istft_launch("fdbm_decompress_istft_var", spec, batch, n_frames, window, n_fft, hop, transform_type, spec_factor,
+                      abs_exponent, max_length, lengths, wave_stride, wave, stream);
 }

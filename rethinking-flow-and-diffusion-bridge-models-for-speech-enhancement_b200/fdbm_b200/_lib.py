@@ -18,7 +18,8 @@ FDBM_STEP = {"ode_ei": 0, "sde_ei": 1}
 # every symbol include/fdbm_b200.h declares; tests/test_abi.py checks the library exports all of them
 EXPORTS = [
     "fdbm_last_error", "fdbm_version", "fdbm_check_device", "fdbm_operand_is_bf16",
-    "fdbm_stft_compress", "fdbm_decompress_istft", "fdbm_spec_transform", "fdbm_pad_spec",
+    "fdbm_stft_compress", "fdbm_stft_compress_var", "fdbm_decompress_istft", "fdbm_decompress_istft_var",
+    "fdbm_spec_transform", "fdbm_pad_spec",
     "fdbm_prior_sample", "fdbm_bridge_step",
     "fdbm_plan_create", "fdbm_plan_destroy", "fdbm_plan_load_weights", "fdbm_plan_device_bytes",
     "fdbm_plan_num_launches", "fdbm_ncsnpp_forward", "fdbm_sampler_run", "fdbm_plan_profile_forward",
@@ -62,6 +63,8 @@ def load() -> C.CDLL:
         "fdbm_operand_is_bf16": (i, []),
         "fdbm_stft_compress": (i, [p, i, i64, i64, p, i, i, i, f, f, i, i, p, p]),
         "fdbm_decompress_istft": (i, [p, i, i, p, i, i, i, f, f, i64, i64, p, p]),
+        "fdbm_stft_compress_var": (i, [p, i, p, i64, i64, i64, p, i, i, i, f, f, i, i, p, p]),
+        "fdbm_decompress_istft_var": (i, [p, i, i, p, i, i, i, f, f, p, i64, i64, p, p]),
         "fdbm_spec_transform": (i, [p, p, i64, i, f, f, i, p]),
         "fdbm_pad_spec": (i, [p, i64, i, i, i, p, p]),
         "fdbm_prior_sample": (i, [p, p, f, f, u64, u64, i64, p, p]),

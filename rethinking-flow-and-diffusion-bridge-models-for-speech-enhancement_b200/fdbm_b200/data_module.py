@@ -139,6 +139,37 @@ class SpecsDataModule:
         T_out = padded_frames(M) if n_frames_out is None else n_frames_out
         return self._stft_impl(sig, tr, fac, e, pad_mode, T_out)[:, None]
 
+    def stft_compress_var(self, sig: torch.Tensor, lengths: torch.Tensor, min_len: int, max_len: int,
+                          pad_mode: str = "zero_pad", n_frames_out=None) -> torch.Tensor:
+        """Variable-length batch: row b of `sig` [B, >= max_len] holds lengths[b] samples (device int32 [B]); every row is
+        framed / reflect-padded / frame-padded from its own length, i.e. equals stft_compress of that utterance alone."""
+        if sig.dim() != 2 or not sig.is_cuda or sig.dtype != torch.float32:
+            raise RuntimeError("stft_compress_var expects an fp32 CUDA [B, n_samples] batch")
+        if lengths.dtype != torch.int32 or not lengths.is_cuda or lengths.numel() != sig.shape[0]:
+            raise RuntimeError("stft_compress_var expects device int32 lengths [B]")
+        tr, fac, e = self._transform_args()
+        x = sig.contiguous()
+        B = x.shape[0]
+        T_out = padded_frames(1 + max_len // self.hop_length) if n_frames_out is None else n_frames_out
+        F = self.n_fft // 2 + 1
+        spec = torch.empty(B, F, T_out, dtype=torch.complex64, device=x.device)
+        check(_lib.load().fdbm_stft_compress_var(ptr(x), B, ptr(lengths), int(min_len), int(max_len), x.stride(0),
+                                                 ptr(self._get_window(x)), self.n_fft, self.hop_length, tr, fac, e,
+                                                 FDBM_PAD[pad_mode], T_out, ptr(spec), current_stream()),
+              "fdbm_stft_compress_var")
+        return spec[:, None]
+
+    def to_audio_var(self, spec: torch.Tensor, lengths: torch.Tensor, max_len: int) -> torch.Tensor:
+        """Variable-length to_audio: [B, F, T] -> [B, max_len], row b valid up to lengths[b] (zeros beyond)."""
+        tr, fac, e = self._transform_args()
+        s = _as_cfloat(spec)
+        B, F, M = s.shape
+        wave = torch.zeros(B, max_len, dtype=torch.float32, device=s.device)
+        check(_lib.load().fdbm_decompress_istft_var(ptr(s), B, M, ptr(self._get_window(s)), self.n_fft, self.hop_length,
+                                                    tr, fac, e, ptr(lengths), int(max_len), wave.stride(0), ptr(wave),
+                                                    current_stream()), "fdbm_decompress_istft_var")
+        return wave
+
     def to_audio(self, spec: torch.Tensor, length=None) -> torch.Tensor:
         """istft(spec_back(spec), length) in one kernel (fdbm/model.py:376-377)."""
         tr, fac, e = self._transform_args()

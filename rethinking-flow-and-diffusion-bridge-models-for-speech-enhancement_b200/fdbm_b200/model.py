@@ -129,6 +129,81 @@ class EnhancementModel(nn.Module):
         return out
 
 
+    # ------------------------------------------------------------------ callers' edge: lists of files / waveforms
+    @torch.no_grad()
+    def enhance_list(self, waves: Sequence, micro_batch: int = 32, clip_rescale: Optional[float] = 0.95) -> List[np.ndarray]:
+        """The per-file loop of infer_folder.py:91-121 for waveforms of DIFFERENT lengths, batched: utterances are
+        bucketed by their padded frame count (pad_spec rounds to 64 frames; GroupNorm and attention see the whole padded
+        image, so only utterances with the same padded length may share a batch without changing any result), each
+        bucket runs in micro-batches through peak-normalise -> variable-length STFT -> sampler -> variable-length iSTFT
+        -> rescale -> clip rule (0.95, infer_folder.py:119-120).  Returns the enhanced waveforms in input order."""
+        if self.data_module.normalize != "noisy":
+            raise NotImplementedError("enhance_list implements the default normalize='noisy'")
+        dev = next(self.dnn.parameters()).device
+        hop = self.data_module.hop_length
+        ws = [torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in waves]
+        buckets = {}
+        for i, w in enumerate(ws):
+            if w.numel() <= self.data_module.n_fft // 2:
+                raise RuntimeError(f"utterance {i} is shorter than n_fft/2 samples")
+            buckets.setdefault(padded_frames(1 + w.numel() // hop), []).append(i)
+        out: List[Optional[np.ndarray]] = [None] * len(ws)
+        for T_pad, idx in sorted(buckets.items()):
+            idx.sort(key=lambda i: ws[i].numel())
+            for j0 in range(0, len(idx), micro_batch):
+                grp = idx[j0:j0 + micro_batch]
+                n = len(grp)
+                lens = [ws[i].numel() for i in grp]
+                lens_full = lens + [lens[-1]] * (micro_batch - n)          # pad the batch: one plan / graph per bucket
+                max_len, min_len = max(lens_full), min(lens_full)
+                host = torch.zeros(micro_batch, max_len, dtype=torch.float32).pin_memory()
+                for r in range(micro_batch):
+                    w = ws[grp[min(r, n - 1)]]
+                    host[r, :w.numel()] = w
+                y = host.to(dev, non_blocking=True)
+                lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
+                norm = y.abs().amax(dim=1, keepdim=True)
+                Y = self.data_module.stft_compress_var(y / norm, lengths, min_len, max_len, pad_mode=self.pad_mode,
+                                                       n_frames_out=T_pad)
+                sample = self._sample(Y)
+                x_hat = self.data_module.to_audio_var(sample[:, 0], lengths, max_len) * norm
+                if clip_rescale is not None:
+                    peak = x_hat.abs().amax(dim=1, keepdim=True)
+                    x_hat = torch.where(peak > 1.0, x_hat / peak * clip_rescale, x_hat)
+                res = x_hat[:n].cpu().numpy()
+                for r, i in enumerate(grp):
+                    out[i] = res[r, :lens[r]].copy()
+        return out  # type: ignore[return-value]
+
+    def enhance_files(self, paths: Sequence[str], out_paths: Optional[Sequence[str]] = None, micro_batch: int = 32,
+                      target_sr: int = 16000) -> List[np.ndarray]:
+        """infer_folder.py:91-146 for a list of mono WAV files (16-bit / 32-bit PCM or float): decode, enhance in
+        length buckets, optionally write 16-bit PCM WAVs.  Resampling (librosa in the reference) is not part of the
+        hot path: files at another sample rate are rejected."""
+        from scipy.io import wavfile
+        waves = []
+        for p in paths:
+            sr, x = wavfile.read(p)
+            if sr != target_sr:
+                raise RuntimeError(f"{p}: sample rate {sr} != {target_sr} (resample before calling enhance_files)")
+            if x.ndim != 1:
+                raise RuntimeError(f"{p}: expected a mono file")
+            if x.dtype == np.int16:
+                x = x.astype(np.float32) / 32768.0                      # torchaudio.load's normalisation
+            elif x.dtype == np.int32:
+                x = x.astype(np.float32) / 2147483648.0
+            else:
+                x = x.astype(np.float32)
+            waves.append(x)
+        enhanced = self.enhance_list(waves, micro_batch=micro_batch)
+        if out_paths is not None:
+            import os
+            for p, x in zip(out_paths, enhanced):
+                os.makedirs(os.path.dirname(os.path.abspath(p)), exist_ok=True)
+                wavfile.write(p, target_sr, np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16))
+        return enhanced
+
+
 class PredictiveEnhancementModel(EnhancementModel):
     """PredictiveModel (fdbm/model.py:414-439): one backbone pass, no sampling loop."""
 

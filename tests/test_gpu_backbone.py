@@ -177,3 +177,40 @@ def test_enhance_si_sdr_matches_oracle(nets):
     both = model.enhance_batch(torch.stack([noisy, noisy]).cuda())
     print(f"batched vs single {rel_l2(both[0], got):.2e}, within batch {rel_l2(both[0], both[1]):.2e}")
     assert rel_l2(both[0], got) < 1e-4 and rel_l2(both[0], both[1]) < 1e-4
+
+
+def test_enhance_list_variable_lengths(nets, tmp_path):
+    """Callers' edge (infer_folder.py:91-146): files of different lengths, bucketed by padded frame count and batched with
+    per-utterance lengths in the STFT / iSTFT kernels, must give exactly the per-file result (B = 1 `enhance`, the
+    reference's loop) -- padding a batch never leaks into an utterance -- and match the oracle's per-file enhancement."""
+    O, cfg, sd, net = nets
+    import numpy as np
+    from scipy.io import wavfile
+    from fdbm_b200 import EnhancementModel
+    model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=5, sampler_type="ode_ei"))
+    model.dnn.load_state_dict(sd)
+    model = model.cuda().eval()
+    lens = [19200, 30400, 19911, 40000, 16000]          # padded frame counts 128, 128, 128, 192, 64
+    noisy = [O.synth_pair(10 + i, n_samples=n)[1] for i, n in enumerate(lens)]
+    got = model.enhance_list(noisy, micro_batch=2, clip_rescale=None)
+    assert [g.shape[0] for g in got] == lens
+    for i, w in enumerate(noisy):
+        single = model.enhance(w[None])
+        d = float(np.abs(got[i] - single).max()) / float(np.abs(single).max())
+        print(f"variable-length batch vs per-file, {lens[i]} samples: max rel diff {d:.2e}")
+        assert d < 1e-5
+    ob = O.Bridge("sb", N=5, sampler_type="ode_ei")
+    with torch.no_grad():
+        ref = O.enhance(noisy[2][None], lambda a, b, c: O.ncsnpp_forward(sd, cfg, a, b, c), ob, O.SpecConfig()).numpy()
+    assert O.si_sdr(ref, got[2]) > 35.0
+    # WAV files in, 16-bit PCM WAV files out (decode / encode edge)
+    paths, outs = [], []
+    for i, w in enumerate(noisy[:3]):
+        p = tmp_path / f"in{i}.wav"
+        wavfile.write(p, 16000, np.clip(np.round(w.numpy() / float(w.abs().max()) * 0.5 * 32767), -32768, 32767).astype(np.int16))
+        paths.append(str(p)); outs.append(str(tmp_path / "out" / f"e{i}.wav"))
+    enh = model.enhance_files(paths, outs, micro_batch=2)
+    for i, o in enumerate(outs):
+        sr, x = wavfile.read(o)
+        assert sr == 16000 and x.dtype == np.int16 and x.shape[0] == lens[i]
+        assert np.abs(x.astype(np.float32) / 32767.0 - np.clip(enh[i], -1, 1)).max() < 1e-4
