@@ -328,6 +328,56 @@ def train_main(args):
     return 0
 
 
+def files_main(args):
+    """SURVEY.md 8(f) #2, the callers' I/O edge of infer_folder.py:91-146: a folder of WAV files of DIFFERENT lengths
+    (2-6 s), timed from the file names to the written enhanced files: decode, length bucketing, pinned staging + H2D,
+    variable-length STFT, sampler, iSTFT, D2H, 16-bit PCM encode.  Single process (one GPU)."""
+    import tempfile
+    import numpy as np
+    import torch
+    from scipy.io import wavfile
+    from fdbm_b200 import EnhancementModel, sensitise_, _lib
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.load().fdbm_check_device(), "fdbm_check_device")
+    model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
+    sensitise_(model.dnn, seed=0)
+    model = model.to(dev).eval()
+    mb = min(args.micro_batch, 32)
+    rng = np.random.default_rng(7)
+    tmp = tempfile.mkdtemp(prefix="fdbm_files_")
+    paths, outs, total_s = [], [], 0.0
+    base = synth_batch(8, torch.device("cpu"), seed=99).numpy()                    # [8, 64000]
+    for i in range(args.utts):
+        n = int(rng.integers(2 * SR, 6 * SR))
+        w = np.tile(base[i % 8], 2)[:n]
+        w = w / np.abs(w).max() * 0.7
+        p = os.path.join(tmp, "noisy", f"u{i:04d}.wav")
+        os.makedirs(os.path.dirname(p), exist_ok=True)
+        wavfile.write(p, SR, np.round(w * 32767).astype(np.int16))
+        paths.append(p); outs.append(os.path.join(tmp, "enhanced", f"u{i:04d}.wav")); total_s += n / SR
+    for _ in range(max(1, min(args.warmup, 2))):                                   # builds one plan + graph per length bucket
+        model.enhance_files(paths, outs, micro_batch=mb)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        model.enhance_files(paths, outs, micro_batch=mb)
+    torch.cuda.synchronize()
+    dt = (time.perf_counter() - t0) / args.steps
+    n_bytes = sum(os.path.getsize(p) for p in paths)
+    print(json.dumps({
+        "metric": f"enhanced audio-sec/sec from WAV files of different lengths ({BRIDGE_STEPS}-step SB bridge, ncsnpp_v2)",
+        "value": total_s / dt, "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(1, min(args.warmup, 2)),
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "bf16" if _lib.load().fdbm_operand_is_bf16() else "fp16", "data": "synthetic",
+        "config": {"workload": f"files: {args.utts} synthetic 16 kHz mono 16-bit WAV files of 2-6 s ({total_s:.0f} s of audio), "
+                               f"bucketed by padded frame count, micro-batch {mb}, wall clock from file names to written files",
+                   "micro_batch": mb, "bridge_steps": BRIDGE_STEPS},
+        "e2e": {"value": total_s / dt, "unit": UNIT, "h2d_bytes_per_step": n_bytes * 2, "d2h_bytes_per_step": n_bytes * 2},
+        "timing": "host wall clock around enhance_files (includes file decode / encode); not a device-event number"}))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -337,7 +387,7 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "128")))
     ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train"],
+    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train", "files"],
                     help="BASELINE.json configs[1] (default, the headline metric), configs[2] or configs[3] (training step)")
     ap.add_argument("--train-batch", type=int, default=16, help="training crops per GPU per step (configs[3]: 8 x 16)")
     ap.add_argument("--bridge-steps", type=int, default=5, help="configs[4]: sampling-step sweep 1/5/10/30")
@@ -347,6 +397,8 @@ def main():
     set_workload(args.seconds, args.bridge_steps, predictive)
     if args.workload == "train":
         return train_main(args)
+    if args.workload == "files":
+        return files_main(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

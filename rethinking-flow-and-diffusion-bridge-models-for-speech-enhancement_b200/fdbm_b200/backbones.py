@@ -175,7 +175,10 @@ class _NCSNppBase(nn.Module):
                     h.add("Conv_2.weight", _fan_avg_uniform((cout, cin, 1, 1))); h.add("Conv_2.bias", torch.zeros(cout))
             holders.append(h)
         self.all_modules = nn.ModuleList(holders)
-        self._plans = {}          # (device index, batch, n_frames) -> [plan handle, weight version]
+        self._plans = {}          # (device index, batch, n_frames) -> [plan handle, weight version]; insertion order = LRU order
+        # device memory all cached plans may hold together (each plan owns an arena + a packed copy of the weights); folders
+        # with many distinct padded lengths would otherwise grow without bound -- least recently used plans are destroyed
+        self.max_plan_bytes = 96 << 30
 
     # ---- plan / weight management --------------------------------------------------------------
     def _arch(self) -> Arch:
@@ -193,13 +196,20 @@ class _NCSNppBase(nn.Module):
     def _plan(self, device, batch, n_frames):
         lib = _lib.load()
         key = (device.index, batch, n_frames)
-        entry = self._plans.get(key)
+        entry = self._plans.pop(key, None)
         if entry is None:
             handle = C.c_void_p()
             arch = self._arch()
             check(lib.fdbm_plan_create(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create")
             entry = [handle, None]
-            self._plans[key] = entry
+            used = sum(int(lib.fdbm_plan_device_bytes(h)) for h, _ in self._plans.values()) + int(lib.fdbm_plan_device_bytes(handle))
+            while used > self.max_plan_bytes and self._plans:
+                old_key = next(iter(self._plans))
+                old_handle, _ = self._plans.pop(old_key)
+                used -= int(lib.fdbm_plan_device_bytes(old_handle))
+                torch.cuda.synchronize(device)                      # the evicted plan's arena may still be in flight
+                lib.fdbm_plan_destroy(old_handle)
+        self._plans[key] = entry                                    # (re-)insert as most recently used
         version = self._weight_version()
         if entry[1] != version:
             named = [(n, p) for n, p in self.named_parameters()]

@@ -214,3 +214,22 @@ def test_enhance_list_variable_lengths(nets, tmp_path):
         sr, x = wavfile.read(o)
         assert sr == 16000 and x.dtype == np.int16 and x.shape[0] == lens[i]
         assert np.abs(x.astype(np.float32) / 32767.0 - np.clip(enh[i], -1, 1)).max() < 1e-4
+
+
+def test_plan_cache_is_bounded(nets):
+    """Cached plans (one per batch / frame count) are evicted least-recently-used once they exceed `max_plan_bytes`."""
+    O, cfg, sd, net = nets
+    from fdbm_b200 import BackboneRegistry
+    dnn = BackboneRegistry.get_by_name("ncsnpp_v2")()
+    dnn.load_state_dict(sd)
+    dnn = dnn.cuda().eval()
+    x = torch.view_as_complex(torch.randn(1, 1, 257, 64, 2, device="cuda"))
+    t = torch.full((1,), 0.5, device="cuda")
+    a = dnn(x, x, t)
+    one = dnn.plan_info(1, 64)["device_bytes"]
+    dnn.max_plan_bytes = int(one * 1.5)
+    x2 = torch.view_as_complex(torch.randn(1, 1, 257, 128, 2, device="cuda"))
+    dnn(x2, x2, t)
+    assert len(dnn._plans) == 1 and next(iter(dnn._plans))[2] == 128
+    b = dnn(x, x, t)                                             # rebuilt after eviction: same result
+    assert torch.equal(a, b)
