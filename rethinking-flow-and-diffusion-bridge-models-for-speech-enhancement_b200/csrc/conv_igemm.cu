@@ -22,6 +22,7 @@
 //     overlapping the next tile's main loop through the second accumulator stage.
 #include <cuda.h>
 #include <mutex>
+#include <type_traits>
 #include "common.cuh"
 #include "tc05.cuh"
 
@@ -60,7 +61,10 @@ constexpr int STAGE_BYTES = EPI_GROUPS * 4 * 32 * 32 * 4;       // epilogue tran
 constexpr int STAT_SLOTS = 2;                                  // n-blocks whose statistics a CTA keeps in flight
 constexpr int STAT_BYTES = EPI_GROUPS * 4 * BN * 8;            // per-warp channel (sum, sum of squares) partials
 // no alignment slack: the dynamic segment is declared __align__(1024) and the kernel traps if it is not
-constexpr int SMEM_BYTES = A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + STAGE_BYTES + STAT_BYTES + 256;
+// narrow-N (16 output channels) convolutions cut the same weight ring into 2 KB slots: their MMAs per tap are ~10x shorter,
+// so three weight loads in flight made them TMA-latency-bound
+constexpr int B_STAGES_NARROW = B_STAGES * B_TILE_BYTES / (16 * 128);
+constexpr int SMEM_BYTES = A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYTES + STAGE_BYTES + STAT_BYTES + 512;
 
 // One K segment = one activation tensor contributing C channels (kb = C/64 K-blocks) with 9 taps or 1.
 // norm != 0: GroupNorm (+SiLU when act != 0) is applied to the tile in shared memory between the TMA
@@ -130,8 +134,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* a_full = bars;
   uint64_t* a_empty = a_full + A_STAGES;
   uint64_t* b_full = a_empty + A_STAGES;
-  uint64_t* b_empty = b_full + B_STAGES;
-  uint64_t* acc_full = b_empty + B_STAGES;
+  uint64_t* b_empty = b_full + B_STAGES_NARROW;
+  uint64_t* acc_full = b_empty + B_STAGES_NARROW;
+  const int b_stages = p.bn == 16 ? B_STAGES_NARROW : B_STAGES;
+  const int b_stride = p.bn * 128;                        // bytes per weight slot
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* a_ready = acc_empty + 2;                   // A stage transformed (or passed through) -> MMA may read it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + A_STAGES);
@@ -142,7 +148,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(a_ready + i, 128); }
-    for (int i = 0; i < B_STAGES; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
+    for (int i = 0; i < B_STAGES_NARROW; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * EPI_GROUPS); }
     fence_barrier_init();
   }
@@ -200,9 +206,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           int kt = e >> 16;
           for (int tap = 0; tap < ntaps; ++tap, ++kt) {
             mbar_wait_relaxed(b_empty + stage, phase ^ 1);
-            mbar_expect_tx(b_full + stage, p.bn * 128);
-            tma_load_2d(sB + stage * B_TILE_BYTES, &map_b, b_full + stage, 0, kt * p.Cout + n0);
-            if (++stage == B_STAGES) { stage = 0; phase ^= 1; }
+            mbar_expect_tx(b_full + stage, b_stride);
+            tma_load_2d(sB + stage * b_stride, &map_b, b_full + stage, 0, kt * p.Cout + n0);
+            if (++stage == b_stages) { stage = 0; phase ^= 1; }
           }
         }
       }
@@ -238,7 +244,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           mbar_wait(b_full + sb, pb);
           fence_after_sync();
           const uint32_t a_off = ((dt * HALO_F + df) * 128) >> 4;
-          const uint32_t b_lo = (sB_lo + (sb * B_TILE_BYTES >> 4)) | lo_const;
+          const uint32_t b_lo = (sB_lo + (sb * b_stride >> 4)) | lo_const;
           const uint32_t a_lo0 = (a_base0 + a_off) | lo_const, a_lo1 = (a_base1 + a_off) | lo_const;
           if (elect_one()) {
 #pragma unroll
@@ -256,7 +262,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           __syncwarp();
           accumulate = 1;
           if (++dt == 3) { dt = 0; ++df; }                                 // tap = df * 3 + dt
-          if (++sb == B_STAGES) { sb = 0; pb ^= 1; }
+          if (++sb == b_stages) { sb = 0; pb ^= 1; }
         }
         if (++sa == A_STAGES) { sa = 0; pa ^= 1; }
       }
@@ -288,7 +294,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       for (int i = 0; i < n_kb; ++i) {
         const uint32_t e = p.ksched[i];
         const SegParams& sg = p.seg[e & 15];
-        float sc[MT][8], sh[MT][8];
+        float2 sc[MT][4], sh[MT][4];                      // (scale, shift) of channel pairs: packed fp32x2 affine
         if (sg.norm) {
           const int c0 = ((e >> 4) & 0xFFF) * 64 + g * 8;
           const float pre = sg.act ? 0.5f : 1.0f;
@@ -298,7 +304,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
             for (int u = 0; u < 4; ++u) {
               const float4 e = __ldg(tp + u);
-              sc[j][2 * u] = pre * e.x; sh[j][2 * u] = pre * e.y; sc[j][2 * u + 1] = pre * e.z; sh[j][2 * u + 1] = pre * e.w;
+              sc[j][u] = make_float2(pre * e.x, pre * e.z); sh[j][u] = make_float2(pre * e.y, pre * e.w);
             }
           }
         }
@@ -315,45 +321,69 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             // four pixel slots per pass: all four 16-byte loads are in flight before the first is consumed, and the
             // pass has no branches (a slot-at-a-time loop was one long dependent chain: ~200 cycles per slot)
             constexpr int N_PASS = (HALO_T * HALO_F + 63) / 64;
-#pragma unroll 1
-            for (int pass = 0; pass < N_PASS; ++pass) {
-              uint4 raw[4];
-              uint4* slot[4];
-              bool on[4];
+            auto xform = [&](uint4& rawv, auto act_tag) {
+              constexpr bool ACT = decltype(act_tag)::value;
+              op2_t* h2 = reinterpret_cast<op2_t*>(&rawv);
 #pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                const int px = p_lane + 16 * (pass * 4 + u);
-                on[u] = px < HALO_T * HALO_F;
-                if (!interior) {
-                  const int hr = px / HALO_F, hc = px - hr * HALO_F;
-                  on[u] = on[u] && hr >= r_lo && hr < r_hi && hc >= c_lo && hc < c_hi;
-                }
-                slot[u] = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
-                raw[u] = on[u] ? *slot[u] : make_uint4(0u, 0u, 0u, 0u);
-              }
-#pragma unroll
-              for (int u = 0; u < 4; ++u) {
-                op2_t* h2 = reinterpret_cast<op2_t*>(&raw[u]);
-#pragma unroll
-                for (int w = 0; w < 4; ++w) {
-                  float2 v = op22f2(h2[w]);
-                  if (sg.act) {
+              for (int w = 0; w < 4; ++w) {
+                const float2 y = __ffma2_rn(op22f2(h2[w]), sc[j][w], sh[j][w]);
+                if (ACT) {
 #ifdef FDBM_XF_EXACT
-                    v.x = 2.0f * fmaf(v.x, sc[j][2 * w], sh[j][2 * w]); v.y = 2.0f * fmaf(v.y, sc[j][2 * w + 1], sh[j][2 * w + 1]);
-                    h2[w] = f2op2(__fdividef(v.x, 1.0f + __expf(-v.x)), __fdividef(v.y, 1.0f + __expf(-v.y)));
+                  const float y0 = 2.0f * y.x, y1 = 2.0f * y.y;
+                  h2[w] = f2op2(__fdividef(y0, 1.0f + __expf(-y0)), __fdividef(y1, 1.0f + __expf(-y1)));
 #else
-                    const op2_t h = f2op2(fmaf(v.x, sc[j][2 * w], sh[j][2 * w]), fmaf(v.y, sc[j][2 * w + 1], sh[j][2 * w + 1]));
-                    h2[w] = __hfma2(h, op2_tanh(h), h);
+                  const op2_t h = f2op2(y.x, y.y);
+                  h2[w] = __hfma2(h, op2_tanh(h), h);
 #endif
-                  } else {
-                    h2[w] = f2op2(fmaf(v.x, sc[j][2 * w], sh[j][2 * w]), fmaf(v.y, sc[j][2 * w + 1], sh[j][2 * w + 1]));
-                  }
+                } else {
+                  h2[w] = f2op2(y.x, y.y);
                 }
               }
+            };
+            // tile interior to the image (the common case): the 12 slots of a thread are fixed offsets from one base
+            // address (px & 7 does not depend on the pass), only the last one is conditional (180 = 11 * 16 + 4 pixels)
+            auto run_interior = [&](auto act_tag) {
+              uint8_t* base = tile + p_lane * 128 + ((g ^ (p_lane & 7)) << 4);
 #pragma unroll
-              for (int u = 0; u < 4; ++u)
-                if (on[u]) *slot[u] = raw[u];
-            }
+              for (int pass = 0; pass < N_PASS; ++pass) {
+                uint4 raw[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int i = pass * 4 + u;
+                  if (i < 11 || p_lane < 4) raw[u] = *reinterpret_cast<uint4*>(base + i * 2048);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xform(raw[u], act_tag);
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int i = pass * 4 + u;
+                  if (i < 11 || p_lane < 4) *reinterpret_cast<uint4*>(base + i * 2048) = raw[u];
+                }
+              }
+            };
+            auto run_border = [&](auto act_tag) {
+#pragma unroll 1
+              for (int pass = 0; pass < N_PASS; ++pass) {
+                uint4 raw[4];
+                uint4* slot[4];
+                bool on[4];
+#pragma unroll
+                for (int u = 0; u < 4; ++u) {
+                  const int px = p_lane + 16 * (pass * 4 + u);
+                  const int hr = px / HALO_F, hc = px - hr * HALO_F;
+                  on[u] = px < HALO_T * HALO_F && hr >= r_lo && hr < r_hi && hc >= c_lo && hc < c_hi;
+                  slot[u] = reinterpret_cast<uint4*>(tile + px * 128 + ((g ^ (px & 7)) << 4));
+                  raw[u] = on[u] ? *slot[u] : make_uint4(0u, 0u, 0u, 0u);
+                }
+#pragma unroll
+                for (int u = 0; u < 4; ++u) xform(raw[u], act_tag);
+#pragma unroll
+                for (int u = 0; u < 4; ++u)
+                  if (on[u]) *slot[u] = raw[u];
+              }
+            };
+            if (interior) { if (sg.act) run_interior(std::true_type{}); else run_interior(std::false_type{}); }
+            else { if (sg.act) run_border(std::true_type{}); else run_border(std::false_type{}); }
           }
           fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core's async proxy
         }
@@ -426,18 +456,40 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               const int t_a = (t & 1) ? (t >> 1) : (t >> 1) - 1, f_a = (f & 1) ? (f >> 1) : (f >> 1) - 1;
               const float wt_a = (t & 1) ? 0.75f : 0.25f, wf_a = (f & 1) ? 0.75f : 0.25f;
               const float* pb = p.pyr_prev + static_cast<int64_t>(tc.b) * Tp * Fp * p.pyr_C;
+              if (p.pyr_C == 4) {
+                // the four taps as four independent 16-byte loads (a scalar loop over channels serialised 16 L2 latencies
+                // per pixel and made this epilogue, not the MMA, the bound of the C -> 4 convolutions)
+                float4 tap[4];
+                float wg[4];
 #pragma unroll
-              for (int u = 0; u < 2; ++u) {
-                const int tt = t_a + u;
-                if (tt < 0 || tt >= Tp) continue;
-                const float wt = u ? 1.0f - wt_a : wt_a;
+                for (int u = 0; u < 2; ++u)
 #pragma unroll
-                for (int w = 0; w < 2; ++w) {
-                  const int ff = f_a + w;
-                  if (ff < 0 || ff >= Fp) continue;
-                  const float wgt = wt * (w ? 1.0f - wf_a : wf_a);
-                  const float* src = pb + (static_cast<int64_t>(tt) * Fp + ff) * p.pyr_C;
-                  for (int c = 0; c < p.pyr_C; ++c) o[c] = fmaf(wgt, __ldg(src + c), o[c]);
+                  for (int w = 0; w < 2; ++w) {
+                    const int tt = t_a + u, ff = f_a + w;
+                    const bool ok = tt >= 0 && tt < Tp && ff >= 0 && ff < Fp;
+                    wg[u * 2 + w] = ok ? (u ? 1.0f - wt_a : wt_a) * (w ? 1.0f - wf_a : wf_a) : 0.f;
+                    tap[u * 2 + w] = ok ? __ldg(reinterpret_cast<const float4*>(pb + (static_cast<int64_t>(tt) * Fp + ff) * 4))
+                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+                  }
+#pragma unroll
+                for (int k = 0; k < 4; ++k) {
+                  o[0] = fmaf(wg[k], tap[k].x, o[0]); o[1] = fmaf(wg[k], tap[k].y, o[1]);
+                  o[2] = fmaf(wg[k], tap[k].z, o[2]); o[3] = fmaf(wg[k], tap[k].w, o[3]);
+                }
+              } else {
+#pragma unroll
+                for (int u = 0; u < 2; ++u) {
+                  const int tt = t_a + u;
+                  if (tt < 0 || tt >= Tp) continue;
+                  const float wt = u ? 1.0f - wt_a : wt_a;
+#pragma unroll
+                  for (int w = 0; w < 2; ++w) {
+                    const int ff = f_a + w;
+                    if (ff < 0 || ff >= Fp) continue;
+                    const float wgt = wt * (w ? 1.0f - wf_a : wf_a);
+                    const float* src = pb + (static_cast<int64_t>(tt) * Fp + ff) * p.pyr_C;
+                    for (int c = 0; c < p.pyr_C; ++c) o[c] = fmaf(wgt, __ldg(src + c), o[c]);
+                  }
                 }
               }
             }
