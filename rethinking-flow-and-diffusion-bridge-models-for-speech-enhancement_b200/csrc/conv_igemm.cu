@@ -247,13 +247,29 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           const uint32_t b_lo = (sB_lo + (sb * b_stride >> 4)) | lo_const;
           const uint32_t a_lo0 = (a_base0 + a_off) | lo_const, a_lo1 = (a_base1 + a_off) | lo_const;
           if (elect_one()) {
-#pragma unroll
-            for (int k = 0; k < 4; ++k)
-              mma_f16(d0, a_hi | (a_lo0 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
-            if (valid1) {
+#ifdef FDBM_MMA_WS
+            // weight-stationary MMAs: the four K-slices of the weight tile are parked in collector buffers b0..b3 by the
+            // MMAs of M-tile 0 and re-used by those of M-tile 1 (one pass over the weight tile in shared memory, not two)
+            if (valid1 && p.bn == BN) {
+              mma_f16_ws<0, 0>(d0, a_hi | (a_lo0 + 0), b_hi | (b_lo + 0), idesc, accumulate);
+              mma_f16_ws<1, 0>(d0, a_hi | (a_lo0 + 2), b_hi | (b_lo + 2), idesc, 1u);
+              mma_f16_ws<2, 0>(d0, a_hi | (a_lo0 + 4), b_hi | (b_lo + 4), idesc, 1u);
+              mma_f16_ws<3, 0>(d0, a_hi | (a_lo0 + 6), b_hi | (b_lo + 6), idesc, 1u);
+              mma_f16_ws<0, 1>(d1, a_hi | (a_lo1 + 0), b_hi | (b_lo + 0), idesc, accumulate);
+              mma_f16_ws<1, 1>(d1, a_hi | (a_lo1 + 2), b_hi | (b_lo + 2), idesc, 1u);
+              mma_f16_ws<2, 1>(d1, a_hi | (a_lo1 + 4), b_hi | (b_lo + 4), idesc, 1u);
+              mma_f16_ws<3, 1>(d1, a_hi | (a_lo1 + 6), b_hi | (b_lo + 6), idesc, 1u);
+            } else
+#endif
+            {
 #pragma unroll
               for (int k = 0; k < 4; ++k)
-                mma_f16(d1, a_hi | (a_lo1 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
+                mma_f16(d0, a_hi | (a_lo0 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
+              if (valid1) {
+#pragma unroll
+                for (int k = 0; k < 4; ++k)
+                  mma_f16(d1, a_hi | (a_lo1 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
+              }
             }
             mma_commit(b_empty + sb);
             if (tap == ntaps - 1) mma_commit(a_empty + sa);
