@@ -49,6 +49,22 @@ def gather_waveforms(local: torch.Tensor, counts: Sequence[int], group=None) -> 
     return torch.cat([o[:c] for o, c in zip(out, counts)], dim=0)
 
 
+def length_buckets(n_samples: Sequence[int], hop: int, micro_batch: int) -> List[tuple]:
+    """Batches for utterances of different lengths: [(padded_frames, [indices ...]), ...].  Utterances share a batch only
+    if pad_spec (other.py:76-90) gives them the same padded frame count -- GroupNorm and attention see the whole padded
+    image, so any other grouping would change results -- and every batch has at most `micro_batch` members, shortest
+    first."""
+    buckets = {}
+    for i, n in enumerate(n_samples):
+        buckets.setdefault(padded_frames(1 + int(n) // hop), []).append(i)
+    out = []
+    for T_pad, idx in sorted(buckets.items()):
+        idx.sort(key=lambda i: (n_samples[i], i))
+        for j0 in range(0, len(idx), micro_batch):
+            out.append((T_pad, idx[j0:j0 + micro_batch]))
+    return out
+
+
 class EnhancementModel(nn.Module):
     """Inference-side equivalent of the reference's BridgeModel (fdbm/model.py:25-411): holds `dnn`,
     `bridge`, `data_module` under the same attribute names and offers `forward`, `enhance`, `to_audio`,
@@ -142,37 +158,32 @@ class EnhancementModel(nn.Module):
         dev = next(self.dnn.parameters()).device
         hop = self.data_module.hop_length
         ws = [torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in waves]
-        buckets = {}
         for i, w in enumerate(ws):
             if w.numel() <= self.data_module.n_fft // 2:
                 raise RuntimeError(f"utterance {i} is shorter than n_fft/2 samples")
-            buckets.setdefault(padded_frames(1 + w.numel() // hop), []).append(i)
         out: List[Optional[np.ndarray]] = [None] * len(ws)
-        for T_pad, idx in sorted(buckets.items()):
-            idx.sort(key=lambda i: ws[i].numel())
-            for j0 in range(0, len(idx), micro_batch):
-                grp = idx[j0:j0 + micro_batch]
-                n = len(grp)
-                lens = [ws[i].numel() for i in grp]
-                lens_full = lens + [lens[-1]] * (micro_batch - n)          # pad the batch: one plan / graph per bucket
-                max_len, min_len = max(lens_full), min(lens_full)
-                host = torch.zeros(micro_batch, max_len, dtype=torch.float32).pin_memory()
-                for r in range(micro_batch):
-                    w = ws[grp[min(r, n - 1)]]
-                    host[r, :w.numel()] = w
-                y = host.to(dev, non_blocking=True)
-                lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
-                norm = y.abs().amax(dim=1, keepdim=True)
-                Y = self.data_module.stft_compress_var(y / norm, lengths, min_len, max_len, pad_mode=self.pad_mode,
-                                                       n_frames_out=T_pad)
-                sample = self._sample(Y)
-                x_hat = self.data_module.to_audio_var(sample[:, 0], lengths, max_len) * norm
-                if clip_rescale is not None:
-                    peak = x_hat.abs().amax(dim=1, keepdim=True)
-                    x_hat = torch.where(peak > 1.0, x_hat / peak * clip_rescale, x_hat)
-                res = x_hat[:n].cpu().numpy()
-                for r, i in enumerate(grp):
-                    out[i] = res[r, :lens[r]].copy()
+        for T_pad, grp in length_buckets([w.numel() for w in ws], hop, micro_batch):
+            n = len(grp)
+            lens = [ws[i].numel() for i in grp]
+            lens_full = lens + [lens[-1]] * (micro_batch - n)          # pad the batch: one plan / graph per bucket
+            max_len, min_len = max(lens_full), min(lens_full)
+            host = torch.zeros(micro_batch, max_len, dtype=torch.float32).pin_memory()
+            for r in range(micro_batch):
+                w = ws[grp[min(r, n - 1)]]
+                host[r, :w.numel()] = w
+            y = host.to(dev, non_blocking=True)
+            lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
+            norm = y.abs().amax(dim=1, keepdim=True)
+            Y = self.data_module.stft_compress_var(y / norm, lengths, min_len, max_len, pad_mode=self.pad_mode,
+                                                   n_frames_out=T_pad)
+            sample = self._sample(Y)
+            x_hat = self.data_module.to_audio_var(sample[:, 0], lengths, max_len) * norm
+            if clip_rescale is not None:
+                peak = x_hat.abs().amax(dim=1, keepdim=True)
+                x_hat = torch.where(peak > 1.0, x_hat / peak * clip_rescale, x_hat)
+            res = x_hat[:n].cpu().numpy()
+            for r, i in enumerate(grp):
+                out[i] = res[r, :lens[r]].copy()
         return out  # type: ignore[return-value]
 
     def enhance_files(self, paths: Sequence[str], out_paths: Optional[Sequence[str]] = None, micro_batch: int = 32,

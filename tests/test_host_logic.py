@@ -168,3 +168,19 @@ def test_ddp_gradient_allreduce_world2():
     for _, w, flat in res:
         assert w == 2
         assert flat == [3.0 * i for i in range(10)]
+
+
+def test_length_buckets_group_only_equal_padded_lengths():
+    """Variable-length batching (callers' edge of infer_folder.py:91-146): utterances may share a batch only when pad_spec
+    gives them the same padded frame count; batches are bounded by the micro-batch and cover every utterance once."""
+    from fdbm_b200 import length_buckets, padded_frames
+    lens = [19200, 30400, 19911, 40000, 16000, 64000, 63999, 64256, 16384]
+    b = length_buckets(lens, 256, 2)
+    seen = sorted(i for _, g in b for i in g)
+    assert seen == list(range(len(lens)))
+    for T_pad, g in b:
+        assert 1 <= len(g) <= 2
+        assert all(padded_frames(1 + lens[i] // 256) == T_pad for i in g)
+        assert [lens[i] for i in g] == sorted(lens[i] for i in g)
+    assert [T for T, _ in b] == sorted(T for T, _ in b)
+    assert padded_frames(251) == 256 and padded_frames(256) == 256 and padded_frames(257) == 320
