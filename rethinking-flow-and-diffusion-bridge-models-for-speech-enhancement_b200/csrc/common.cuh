@@ -87,7 +87,7 @@ __device__ __forceinline__ uint32_t pack_op2(float a, float b) {
 int launch_fir_resample(const float* in, int B, int T, int F, int C, int mode, float* out, cudaStream_t s);
 int launch_fir_resample_scaled(const float* in, int B, int T, int F, int C, int mode, float scale, float* out, cudaStream_t s);
 int launch_channel_stats(const float* in, int B, int T, int F, int C, double* sums, cudaStream_t s);
-int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, int C1, const float* src2,
+int launch_groupnorm_act(const void* src1, int src1_h16 /* both sources 16-bit */, const double* sums1, int C1, const void* src2,
                          const double* sums2, int C2, const float* gamma, const float* beta, int B, int T, int F,
                          int silu, int mode, op_t* act_out, op_t* raw_out, cudaStream_t s);
 int launch_pack_input(const float* x, const float* y, int B, int T, int F_in, int F, int Cin, float* out,

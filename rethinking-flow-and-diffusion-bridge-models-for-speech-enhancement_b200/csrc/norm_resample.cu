@@ -114,7 +114,7 @@ constexpr int GN_MAXC = 512;
 template <int MODE, bool SRC16>
 __global__ void __launch_bounds__(256)
 groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ sums1, int C1,
-                     const float* __restrict__ src2, const double* __restrict__ sums2, int C2,
+                     const void* __restrict__ src2, const double* __restrict__ sums2, int C2,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int T, int F, int silu,
                      int px_per_block, uint4* __restrict__ act_out, uint4* __restrict__ raw_out) {
   __shared__ float sA[GN_MAXC], sB[GN_MAXC];
@@ -159,9 +159,11 @@ groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ s
   for (int j = 0; j < 8; ++j) { a[j] = sA[c0 + j]; bb[j] = sB[c0 + j]; }
   const bool from2 = c0 >= C1;
   const int Cs = from2 ? C2 : C1, cs = from2 ? c0 - C1 : c0;
-  const float* sf = from2 ? src2 + static_cast<int64_t>(b) * T * F * C2
+  // SRC16: both sources are 16-bit tensors; otherwise both are fp32
+  const float* sf = from2 ? reinterpret_cast<const float*>(src2) + (SRC16 ? 0 : static_cast<int64_t>(b) * T * F * C2)
                           : reinterpret_cast<const float*>(src1) + (SRC16 ? 0 : static_cast<int64_t>(b) * T * F * C1);
-  const op_t* sh = reinterpret_cast<const op_t*>(src1) + static_cast<int64_t>(b) * T * F * C1;
+  const op_t* sh = from2 ? reinterpret_cast<const op_t*>(src2) + static_cast<int64_t>(b) * T * F * C2
+                         : reinterpret_cast<const op_t*>(src1) + static_cast<int64_t>(b) * T * F * C1;
 
   const int To = out_dim(T, MODE), Fo = out_dim(F, MODE);
   const int n_px = To * Fo;
@@ -183,7 +185,7 @@ groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ s
         const float w = tt.w[u] * tf.w[v];
         const int64_t off = (static_cast<int64_t>(tt.pos[u]) * F + tf.pos[v]) * Cs + cs;
         float x[8];
-        if (SRC16 && !from2) {
+        if (SRC16) {
           const uint4 rawv = *reinterpret_cast<const uint4*>(sh + off);
           const op2_t* h2 = reinterpret_cast<const op2_t*>(&rawv);
 #pragma unroll
@@ -497,7 +499,7 @@ int launch_channel_stats(const float* in, int B, int T, int F, int C, double* su
   return FDBM_OK;
 }
 
-int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, int C1, const float* src2,
+int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, int C1, const void* src2,
                          const double* sums2, int C2, const float* gamma, const float* beta, int B, int T, int F,
                          int silu, int mode, op_t* act_out, op_t* raw_out, cudaStream_t s) {
   const int C = C1 + C2;
@@ -505,7 +507,6 @@ int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, in
                "groupnorm_act: unsupported channels %d+%d", C1, C2);
   FDBM_REQUIRE(mode >= 0 && mode <= 2, "groupnorm_act: bad mode %d", mode);
   FDBM_REQUIRE(mode != 1 || (T % 2 == 0 && F % 2 == 0), "groupnorm_act: down-sampling needs even T, F");
-  FDBM_REQUIRE(!src1_h16 || C2 == 0, "groupnorm_act: a 16-bit source cannot be concatenated");
   const int n_px = out_dim(T, mode) * out_dim(F, mode);
   const int npl = 256 / (C / 8);
   // ~8 resident blocks per SM over the batch; every pixel lane gets at least 4 pixels

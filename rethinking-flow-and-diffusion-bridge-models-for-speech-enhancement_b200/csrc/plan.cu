@@ -245,10 +245,10 @@ struct Builder {
     const Act a1 = x1; const Act a2 = x2 ? *x2 : Act();
     bop([=](cudaStream_t s) {
       FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Ct, s));
-      if (int rc = launch_gn_bwd_reduce(g_a, Ct, 0, a1.data, 0, C1, Ct, 0, tab, stats, act, B, px, S, s)) return rc;
-      if (C2) if (int rc = launch_gn_bwd_reduce(g_a, Ct, C1, a2.data, 0, C2, Ct, C1, tab, stats, act, B, px, S, s)) return rc;
-      if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.data, 0, C1, Ct, 0, tab, stats, gamma, act, B, px, S, a1.grad, nullptr, nullptr, s)) return rc;
-      if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.data, 0, C2, Ct, C1, tab, stats, gamma, act, B, px, S, a2.grad, nullptr, nullptr, s)) return rc;
+      if (int rc = launch_gn_bwd_reduce(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, act, B, px, S, s)) return rc;
+      if (C2) if (int rc = launch_gn_bwd_reduce(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, act, B, px, S, s)) return rc;
+      if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, gamma, act, B, px, S, a1.grad, nullptr, nullptr, s)) return rc;
+      if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, gamma, act, B, px, S, a2.grad, nullptr, nullptr, s)) return rc;
       return launch_gn_param_grad(S, B, Ct, plp->cur_inv, plp->grads + gw_off, plp->grads + gb_off, s);
     });
   }
@@ -294,10 +294,9 @@ struct Builder {
   }
   Act new_act(int C, int T, int F) {
     Act a; a.C = C; a.T = T; a.F = F;
-    // inference plans keep the residual stream in the 16-bit operand format only: the identity shortcut re-reads the
-    // 16-bit copy (one rounding per block, which the 1/sqrt(2) of every block keeps from accumulating); training plans
-    // keep the fp32 master for the backward pass
-    if (P->train) a.data = alloc<float>(static_cast<int64_t>(P->B) * T * F * C);
+    // the residual stream lives in the 16-bit operand format only: the identity shortcut re-reads the 16-bit copy (one
+    // rounding per block, which the 1/sqrt(2) of every block keeps from accumulating), and the backward pass of a training
+    // plan normalises / recomputes from the same 16-bit tensors the forward convolutions consumed
     a.h16 = alloc<op_t>(static_cast<int64_t>(P->B) * T * F * C);
     a.sums = alloc_sums(static_cast<int64_t>(P->B) * C * 2);
     if (P->train) a.grad = galloc(static_cast<int64_t>(P->B) * T * F * C);
@@ -426,13 +425,7 @@ struct Builder {
       // resampling blocks: one pass does GroupNorm_0 + SiLU + FIR up/down of h and the FIR of the raw shortcut operand
       a0 = alloc<op_t>(npx * Cin);
       xr = alloc<op_t>(npx * Cin);
-      const float* s1 = x1.data; const double* q1 = x1.sums;
-      const float* s2 = x2 ? x2->data : nullptr; const double* q2 = x2 ? x2->sums : nullptr;
-      if (train()) {                                  // (the backward pass recomputes from the fp32 stream: keep both sides identical)
-        op([=](cudaStream_t s) {
-          return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, mode, a0, xr, s);
-        }, FDBM_OP_NORM);
-      } else {
+      {
         const op_t* h1s = x1.h16; const op_t* h2s = x2 ? x2->h16 : nullptr;
         op([=](cudaStream_t s) { return launch_gn_resample16(h1s, C1, h2s, C2, tab0, B, T, F, mode, a0, xr, s); }, FDBM_OP_NORM);
       }
@@ -455,7 +448,7 @@ struct Builder {
         }
       }
       c.wpack = w1; c.bias = bias1;
-      if (!shortcut) { if (train()) c.residual = x1.data; else c.residual_h16 = x1.h16; }
+      if (!shortcut) c.residual_h16 = x1.h16;
       c.scale = 0.70710678118654752f; c.B = B; c.T = To; c.F = Fo; c.Cout = Cout;
       c.out_f32 = out.data; c.out_h16 = out.h16; c.sums = out.sums;
       if (comb) { c.comb_pyr = comb->pyr; c.comb_w = comb->w; c.comb_b = comb->b; c.comb_C = comb->Cp; }
@@ -524,8 +517,8 @@ struct Builder {
       // Conv_0: a0 recomputed (or the saved resampled one), wgrad, dgrad, GroupNorm_0 backward into x.grad
       const op_t* a0b = a0;
       if (mode == 0) {
-        const float* s1 = xa.data; const double* q1 = xa.sums; const float* s2 = x2 ? xb.data : nullptr; const double* q2 = x2 ? xb.sums : nullptr;
-        bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 0, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, 0, t2, nullptr, s); });
+        const op_t* s1 = xa.h16; const double* q1 = xa.sums; const op_t* s2 = x2 ? xb.h16 : nullptr; const double* q2 = x2 ? xb.sums : nullptr;
+        bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 1, q1, C1, s2, q2, C2, g0w, g0b, B, T, F, 1, 0, t2, nullptr, s); });
         a0b = t2;
       }
       { WgradCall w; w.dy = t4; w.dy_ld = Cout; w.Cout = Cout; w.x = a0b; w.x_ld = Cin; w.Cin = Cin; w.ksize = 3; w.T = To; w.F = Fo; wgrad_op(w, o_c0w); }
@@ -576,7 +569,7 @@ struct Builder {
       ConvArgs c;
       c.seg[0] = seg(o, C, 1); c.n_seg = 1;
       c.wpack = w3; c.bias = b3; c.scale = 0.70710678118654752f;
-      if (train()) c.residual = x.data; else c.residual_h16 = x.h16;
+      c.residual_h16 = x.h16;
       c.B = B; c.T = T; c.F = F; c.Cout = C; c.out_f32 = out.data; c.out_h16 = out.h16; c.sums = out.sums;
       conv_op(c);
     }
@@ -606,8 +599,8 @@ struct Builder {
         }
         return FDBM_OK;
       });
-      { const float* s1 = xa.data; const double* q1 = xa.sums;
-        bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 0, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, t2, nullptr, s); }); }
+      { const op_t* s1 = xa.h16; const double* q1 = xa.sums;
+        bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 1, q1, C, nullptr, nullptr, 0, gw, gb, B, T, F, 0, 0, t2, nullptr, s); }); }
       const int64_t o_w[3] = {o_w0, o_w1, o_w2};
       for (int i = 0; i < 3; ++i) {
         WgradCall w; w.dy = t4; w.dy_ld = 3 * C; w.dy_coff = i * C; w.Cout = C; w.x = t2; w.x_ld = C; w.Cin = C; w.ksize = 1; w.T = T; w.F = F; w.layout = 1;
@@ -821,8 +814,8 @@ struct Builder {
             return launch_im2col_input(g_new, Cp, B, Tc, Fc, t1, s);
           });
           dgrad_op(t1, 64, 1, wd, C, Tc, Fc, t3, nullptr);
-          { const float* s1 = h.data; const double* q1 = h.sums;
-            bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 0, q1, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, t2, nullptr, s); }); }
+          { const op_t* s1 = h.h16; const double* q1 = h.sums;
+            bop([=](cudaStream_t s) { return launch_groupnorm_act(s1, 1, q1, C, nullptr, nullptr, 0, gw, gb, B, Tc, Fc, 1, 0, t2, nullptr, s); }); }
           WgradCall wc; wc.dy = t2; wc.dy_ld = C; wc.Cout = C; wc.x = t1; wc.x_ld = 64; wc.Cin = 64; wc.ksize = 1; wc.T = Tc; wc.F = Fc;
           wc.layout = 3; wc.aux = Cp;
           wgrad_op(wc, o_w);
