@@ -133,60 +133,73 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   const int cg8 = a.C / 8, npl = 256 / cg8;
   const int g8 = threadIdx.x % cg8, pl = threadIdx.x / cg8;
   const int c0 = g8 * 8;                                   // channel inside this source
-  float sc[8], sh[8], ar[8], br[8], k1[8], k2[8], k3[8];
+  // packed fp32x2 arithmetic (channel pairs): these passes are instruction-bound
+  float2 sc[4], sh[4], ar[4], br[4], k1[4], k2[4], k3[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) {
-    const int c = a.c_off + c0 + j;
-    const float2 t = a.tab[static_cast<int64_t>(b) * a.C_tot + c];
-    const float2 st = a.stats[static_cast<int64_t>(b) * G + c / cpg];
-    sc[j] = t.x; sh[j] = t.y;
-    ar[j] = st.y; br[j] = -st.x * st.y;                    // xhat = x * rstd - mean * rstd
-    if (APPLY) {
-      k1[j] = st.y * a.gamma[c];
-      k2[j] = st.y * s_m1[c / cpg];
-      k3[j] = st.y * s_m2[c / cpg];
+  for (int j = 0; j < 4; ++j) {
+    float v[2][7];
+#pragma unroll
+    for (int u = 0; u < 2; ++u) {
+      const int c = a.c_off + c0 + 2 * j + u;
+      const float2 t = a.tab[static_cast<int64_t>(b) * a.C_tot + c];
+      const float2 st = a.stats[static_cast<int64_t>(b) * G + c / cpg];
+      v[u][0] = t.x; v[u][1] = t.y;
+      v[u][2] = st.y; v[u][3] = -st.x * st.y;              // xhat = x * rstd - mean * rstd
+      v[u][4] = APPLY ? st.y * a.gamma[c] : 0.f;
+      v[u][5] = APPLY ? st.y * s_m1[c / cpg] : 0.f;
+      v[u][6] = APPLY ? st.y * s_m2[c / cpg] : 0.f;
     }
+    sc[j] = make_float2(v[0][0], v[1][0]); sh[j] = make_float2(v[0][1], v[1][1]);
+    ar[j] = make_float2(v[0][2], v[1][2]); br[j] = make_float2(v[0][3], v[1][3]);
+    k1[j] = make_float2(v[0][4], v[1][4]); k2[j] = make_float2(-v[0][5], -v[1][5]); k3[j] = make_float2(-v[0][6], -v[1][6]);
   }
-  float s1[8], s2[8];
+  const float2 half2v = make_float2(0.5f, 0.5f), one2 = make_float2(1.0f, 1.0f), mone2 = make_float2(-1.0f, -1.0f);
+  float2 s1[4], s2[4];
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { s1[j] = 0.f; s2[j] = 0.f; }
+  for (int j = 0; j < 4; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = make_float2(0.f, 0.f); }
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * px_per_block, p1 = min(a.P, p0 + px_per_block);
   if (pl < npl) {
     for (int64_t p = p0 + pl; p < p1; p += npl) {
       const int64_t row = static_cast<int64_t>(b) * a.P + p;
-      float x[8], ga[8];
-      load8(a, row * cg8 + g8, x);
-      {
-        const uint4 raw = *reinterpret_cast<const uint4*>(a.g_a + row * a.g_ld + a.g_coff + c0);
-        const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
+      float xs[8];
+      load8(a, row * cg8 + g8, xs);
+      const uint4 raw = *reinterpret_cast<const uint4*>(a.g_a + row * a.g_ld + a.g_coff + c0);
+      const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
+      float2 gx[4];
 #pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f2 = op22f2(h2[j]); ga[2 * j] = f2.x; ga[2 * j + 1] = f2.y; }
-      }
-      float gx[8];
-#pragma unroll
-      for (int j = 0; j < 8; ++j) {
-        const float y = fmaf(x[j], sc[j], sh[j]);
-        const float gy = ga[j] * act_grad(y, a.act);
-        const float xh = fmaf(x[j], ar[j], br[j]);
+      for (int j = 0; j < 4; ++j) {
+        const float2 x = make_float2(xs[2 * j], xs[2 * j + 1]);
+        float2 gy = op22f2(h2[j]);
+        if (a.act) {                                       // d SiLU / dy = sg + y sg (1 - sg), sg = 1/2 + tanh(y/2)/2
+          const float2 y = __ffma2_rn(x, sc[j], sh[j]);
+          const float2 hy = __fmul2_rn(y, half2v);
+          float2 th;
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th.x) : "f"(hy.x));
+          asm("tanh.approx.f32 %0, %1;" : "=f"(th.y) : "f"(hy.y));
+          const float2 sg = __ffma2_rn(th, half2v, half2v);
+          const float2 d = __ffma2_rn(__fmul2_rn(y, sg), __ffma2_rn(sg, mone2, one2), sg);
+          gy = __fmul2_rn(gy, d);
+        }
+        const float2 xh = __ffma2_rn(x, ar[j], br[j]);
         if (APPLY) {
-          gx[j] = k1[j] * gy - k2[j] - k3[j] * xh;
-          s1[j] += gx[j];
+          gx[j] = __ffma2_rn(k3[j], xh, __ffma2_rn(k1[j], gy, k2[j]));      // k1 gy - k2' - k3' xh (signs folded in)
+          s1[j] = __fadd2_rn(s1[j], gx[j]);
         } else {
-          s1[j] += gy;
-          s2[j] = fmaf(gy, xh, s2[j]);
+          s1[j] = __fadd2_rn(s1[j], gy);
+          s2[j] = __ffma2_rn(gy, xh, s2[j]);
         }
       }
       if (APPLY) {
         if (a.acc_dst) {
           float4* d = reinterpret_cast<float4*>(a.acc_dst) + (row * cg8 + g8) * 2;
           float4 d0 = d[0], d1 = d[1];
-          d0.x += gx[0]; d0.y += gx[1]; d0.z += gx[2]; d0.w += gx[3];
-          d1.x += gx[4]; d1.y += gx[5]; d1.z += gx[6]; d1.w += gx[7];
+          d0.x += gx[0].x; d0.y += gx[0].y; d0.z += gx[1].x; d0.w += gx[1].y;
+          d1.x += gx[2].x; d1.y += gx[2].y; d1.z += gx[3].x; d1.w += gx[3].y;
           d[0] = d0; d[1] = d1;
         }
         if (a.out16)
           reinterpret_cast<uint4*>(a.out16)[row * cg8 + g8] =
-              make_uint4(pack_op2(gx[0], gx[1]), pack_op2(gx[2], gx[3]), pack_op2(gx[4], gx[5]), pack_op2(gx[6], gx[7]));
+              make_uint4(pack_op2(gx[0].x, gx[0].y), pack_op2(gx[1].x, gx[1].y), pack_op2(gx[2].x, gx[2].y), pack_op2(gx[3].x, gx[3].y));
       }
     }
   }
@@ -194,7 +207,10 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   // block reduction over the pixel lanes, then one double atomic per channel and block
   float* red = s_red;
 #pragma unroll
-  for (int j = 0; j < 8; ++j) { red[threadIdx.x * 16 + j] = s1[j]; red[threadIdx.x * 16 + 8 + j] = s2[j]; }
+  for (int j = 0; j < 4; ++j) {
+    red[threadIdx.x * 16 + 2 * j] = s1[j].x; red[threadIdx.x * 16 + 2 * j + 1] = s1[j].y;
+    red[threadIdx.x * 16 + 8 + 2 * j] = s2[j].x; red[threadIdx.x * 16 + 8 + 2 * j + 1] = s2[j].y;
+  }
   __syncthreads();
   if (threadIdx.x < cg8 * 8) {
     const int gg = threadIdx.x / 8, j = threadIdx.x % 8;
