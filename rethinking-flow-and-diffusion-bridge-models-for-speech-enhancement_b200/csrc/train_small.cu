@@ -130,15 +130,39 @@ dense_bwd_w_kernel(const float* __restrict__ d, const float* __restrict__ act, i
     if (k == 0) db[r] += sb;
   }
 }
-// g_act[b][k] = sum_r d[b][r] * w[r][k]     (block per (k-chunk of 256, b, row split); fp32 atomics into a zeroed buffer)
+// g_act[b][k] = sum_r d[b][r] * w[r][k]: block = (256 k-values, a run of rows); the d values of up to 8 utterances for the
+// block's rows sit in shared memory, so every weight is loaded once per 8 utterances (8 FMAs per load, 8 independent
+// accumulators); fp32 atomics into a zeroed buffer combine the row splits.
+constexpr int DBA_ROWS = 128;
 __global__ void __launch_bounds__(256)
-dense_bwd_act_kernel(const float* __restrict__ d, const float* __restrict__ w, int K, int rows, int rows_per_split, float* __restrict__ g_act) {
-  const int b = blockIdx.y, k = blockIdx.x * 256 + threadIdx.x;
-  if (k >= K) return;
-  const int r0 = blockIdx.z * rows_per_split, r1 = min(rows, r0 + rows_per_split);
-  float s = 0.f;
-  for (int r = r0; r < r1; ++r) s = fmaf(d[static_cast<int64_t>(b) * rows + r], w[static_cast<int64_t>(r) * K + k], s);
-  atomicAdd(g_act + static_cast<int64_t>(b) * K + k, s);
+dense_bwd_act_kernel(const float* __restrict__ d, const float* __restrict__ w, int B, int K, int rows, float* __restrict__ g_act) {
+  __shared__ float sd[8][DBA_ROWS];
+  const int k = blockIdx.x * 256 + threadIdx.x;
+  const int r0 = blockIdx.y * DBA_ROWS, nr = min(DBA_ROWS, rows - r0);
+  for (int b0 = 0; b0 < B; b0 += 8) {
+    const int nb = min(8, B - b0);
+    __syncthreads();
+    for (int i = threadIdx.x; i < 8 * DBA_ROWS; i += 256) {
+      const int j = i / DBA_ROWS, r = i % DBA_ROWS;
+      sd[j][r] = (j < nb && r < nr) ? d[static_cast<int64_t>(b0 + j) * rows + r0 + r] : 0.f;
+    }
+    __syncthreads();
+    if (k < K) {
+      float acc[8];
+#pragma unroll
+      for (int j = 0; j < 8; ++j) acc[j] = 0.f;
+      const float* wp = w + static_cast<int64_t>(r0) * K + k;
+#pragma unroll 4
+      for (int r = 0; r < nr; ++r) {
+        const float wv = __ldg(wp + static_cast<int64_t>(r) * K);
+#pragma unroll
+        for (int j = 0; j < 8; ++j) acc[j] = fmaf(sd[j][r], wv, acc[j]);
+      }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (j < nb) atomicAdd(g_act + static_cast<int64_t>(b0 + j) * K + k, acc[j]);
+    }
+  }
 }
 
 // time-embedding MLP backward (layerspp.py:32-41, ncsnpp_v2.py:108-113,252-270): one block per utterance recomputes the
@@ -231,8 +255,7 @@ int launch_dense_temb_bwd(const float* d, const float* act, const float* w, int 
   dense_bwd_w_kernel<<<grid_for(static_cast<int64_t>(rows) * K), 256, 0, s>>>(d, act, B, K, rows, dw, db);
   FDBM_LAUNCH_CHECK();
   FDBM_CUDA(cudaMemsetAsync(g_act, 0, sizeof(float) * B * K, s));
-  const int splits = 32;
-  dense_bwd_act_kernel<<<dim3(ceil_div(K, 256), B, splits), 256, 0, s>>>(d, w, K, rows, ceil_div(rows, splits), g_act);
+  dense_bwd_act_kernel<<<dim3(ceil_div(K, 256), ceil_div(rows, DBA_ROWS)), 256, 0, s>>>(d, w, B, K, rows, g_act);
   FDBM_LAUNCH_CHECK();
   temb_bwd_kernel<<<B, 512, sizeof(float) * (2 * nf + 16 * nf), s>>>(t, fw, nf, w1, b1, w2, b2, t_stride, g_act, dw1, db1, dw2, db2);
   FDBM_LAUNCH_CHECK();
