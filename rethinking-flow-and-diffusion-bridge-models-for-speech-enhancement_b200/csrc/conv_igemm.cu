@@ -1,6 +1,6 @@
 // Implicit-GEMM convolution for the NCSN++ backbone on Blackwell tensor cores.
 //
-//   out[b,t,f,n] = scale * ( sum_{dt,df,c} W[n,c,df,dt] * in1[b,t+dt-1,f+df-1,c]        (3x3 or 1x1)
+//   out[b,t,f,n] = scale * ( sum_{dt,df,c} W[n,c,df,dt] * act(in1)[b,t+dt-1,f+df-1,c]   (3x3 or 1x1; act = GroupNorm(+SiLU) on load)
 //                            (+ sum_c W2[n,c] * in2[b,t,f,c])                             (fused 1x1 shortcut)
 //                            + bias[n] (+ bias_b[b,n]) (+ residual[b,t,f,n]) )
 //
@@ -8,18 +8,22 @@
 // fdbm/backbones/ncsnpp_utils/layers.py:100-124,546-555 and the adds of layerspp.py:263,270-274.
 //
 // Design (B200, sm_100a):
-//   * activations are bf16 [B,T,F,C]; one M-tile = 16 frames x 8 bins = 128 pixels = one UMMA M.
+//   * activations are 16-bit [B,T,F,C]; one M-tile = 16 frames x 8 bins = 128 pixels = one UMMA M.
 //   * per 64-channel K-block ONE TMA box of 18 x 10 pixels (tile + halo, zero-filled outside the
 //     image = the convolution's zero padding) lands in shared memory with the 128-byte swizzle; all
 //     nine taps are fed from it by shifting the UMMA descriptor start address by (dt*10 + df) pixels
 //     (row pitch 10 pixels -> stride-byte-offset 1280).  Validated on hardware by tools/umma_probe.cu.
-//     A traffic per K-block is 180 pixel rows instead of 9 x 128.
-//   * a CTA owns 2 M-tiles x 128 output channels: every weight tile (128 x 64 bf16, TMA, 6-deep ring)
-//     is used by two MMAs; accumulators live in TMEM (2 stages x 2 tiles x 128 columns = 512).
-//   * warp-specialised, persistent: warp0 = A producer, warp1 = B producer, warp2 = MMA issuer,
-//     warp3 = TMEM owner, warps4-7 = epilogue (tcgen05.ld -> smem transpose -> bias / FiLM / residual /
-//     scale -> coalesced global stores, + per-channel sum / sum-of-squares for the next GroupNorm),
-//     overlapping the next tile's main loop through the second accumulator stage.
+//     1-tap (shortcut) segments load the 16 x 8 tile without halo.  The K-blocks of up to three segments are
+//     walked through a per-launch schedule table.
+//   * a CTA owns 2 M-tiles x 128 output channels: every weight tile (128 x 64, TMA, 3-deep ring; 24 slots of
+//     16 rows for the narrow C -> 4 convolutions) is used by two MMAs; accumulators live in TMEM
+//     (2 stages x 2 tiles x 128 columns = 512).
+//   * warp-specialised, persistent, 512 threads: warp0 = A producer, warp1 = B producer, warp2 = MMA issuer,
+//     warp3 = TMEM owner, warps4-7 = epilogue of M-tile 0, warps8-11 = operand transform (GroupNorm+SiLU applied to
+//     the landed tile in shared memory), warps12-15 = epilogue of M-tile 1.  Epilogue: tcgen05.ld -> smem transpose ->
+//     bias / FiLM / 16-bit identity shortcut / scale -> coalesced 16-bit stores + per-channel sum / sum-of-squares for
+//     the next GroupNorm, overlapping the next item's main loop through the second accumulator stage.
+//     setmaxnreg splits the register file 56 / 120 / 168 / 168 per thread between the four warpgroups.
 #include <cuda.h>
 #include <mutex>
 #include <type_traits>
@@ -70,7 +74,7 @@ constexpr int SMEM_BYTES = A_STAGES * MT * A_TILE_STRIDE + B_STAGES * B_TILE_BYT
 // norm != 0: GroupNorm (+SiLU when act != 0) is applied to the tile in shared memory between the TMA
 // landing and the MMA ("normalise on load"); tab[b * tab_stride + c] = (scale, shift) of channel c.
 struct SegParams {
-  int kb_begin, kb_end, taps, norm, act, tab_stride;
+  int taps, norm, act, tab_stride;
   int halo;                                // tile loaded with its 1-pixel halo (9 taps, or normalise-on-load which works on the halo box)
   const float2* tab;
 };
@@ -144,7 +148,6 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_kb = p.n_kb;
-  auto seg_of = [&](int kb) { int sgi = 0; while (sgi + 1 < p.n_seg && kb >= p.seg[sgi].kb_end) ++sgi; return sgi; };
 
   if (threadIdx.x == 0) {
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(a_ready + i, 128); }
@@ -880,13 +883,13 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
       if (int rc = halo ? make_act_map(&map_a[i], sg.in, a.B, a.T, a.F, sg.C)
                         : make_act_tile_map(&map_a[i], sg.in, a.B, a.T, a.F, sg.C, TILE_F, TILE_T)) return rc;
       p.seg[i].halo = halo;
-      p.seg[i].kb_begin = kb; kb += sg.C / 64; p.seg[i].kb_end = kb; p.seg[i].taps = sg.taps;
+      kb += sg.C / 64; p.seg[i].taps = sg.taps;
       p.seg[i].norm = sg.norm_tab != nullptr; p.seg[i].act = sg.act; p.seg[i].tab = sg.norm_tab;
       p.seg[i].tab_stride = sg.tab_stride;
       n_kt += (sg.C / 64) * sg.taps;
     } else {
       map_a[i] = map_a[0];
-      p.seg[i] = SegParams{kb, kb, 1, 0, 0, 0, 0, nullptr};
+      p.seg[i] = SegParams{1, 0, 0, 0, 0, nullptr};
     }
   }
   p.n_kb = kb;

@@ -99,16 +99,8 @@ __device__ __forceinline__ void load8(const GnBwdArgs& a, int64_t idx8, float (&
     x[0] = x0.x; x[1] = x0.y; x[2] = x0.z; x[3] = x0.w; x[4] = x1.x; x[5] = x1.y; x[6] = x1.z; x[7] = x1.w;
   }
 }
-// d SiLU / dy = sg (1 + y (1 - sg)), sg = sigmoid(y) = 1/2 + tanh(y/2)/2: one MUFU.TANH instead of EX2 + an IEEE division
-// (these passes are instruction-bound, not HBM-bound: the division alone was a third of their instructions)
-__device__ __forceinline__ float act_grad(float y, int act) {
-  if (!act) return 1.0f;
-  float th;
-  asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * y));
-  const float sg = fmaf(0.5f, th, 0.5f);
-  return fmaf(y * sg, 1.0f - sg, sg);
-}
-
+// d SiLU / dy = sg + y sg (1 - sg), sg = sigmoid(y) = 1/2 + tanh(y/2)/2: one MUFU.TANH instead of EX2 + an IEEE division
+// (these passes were instruction-bound, not HBM-bound: the division alone was a third of their instructions)
 template <bool APPLY>
 __global__ void __launch_bounds__(256)
 gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
