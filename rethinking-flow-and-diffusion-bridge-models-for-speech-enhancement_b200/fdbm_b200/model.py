@@ -165,10 +165,13 @@ class EnhancementModel(nn.Module):
         for T_pad, grp in length_buckets([w.numel() for w in ws], hop, micro_batch):
             n = len(grp)
             lens = [ws[i].numel() for i in grp]
-            lens_full = lens + [lens[-1]] * (micro_batch - n)          # pad the batch: one plan / graph per bucket
+            # a partial batch is padded (last utterance repeated) to the next multiple of 8: at most four plans / graphs
+            # per padded length instead of one per batch size, at most 7 wasted slots
+            mb = micro_batch if n == micro_batch else min(micro_batch, -(-n // 8) * 8)
+            lens_full = lens + [lens[-1]] * (mb - n)
             max_len, min_len = max(lens_full), min(lens_full)
-            host = torch.zeros(micro_batch, max_len, dtype=torch.float32).pin_memory()
-            for r in range(micro_batch):
+            host = torch.zeros(mb, max_len, dtype=torch.float32).pin_memory()
+            for r in range(mb):
                 w = ws[grp[min(r, n - 1)]]
                 host[r, :w.numel()] = w
             y = host.to(dev, non_blocking=True)
