@@ -121,7 +121,7 @@ class ClockSampler:
         return out
 
 
-def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None):
+def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None, keep_probe=None):
     """The reference's CPU path (oracle port): B=1 utterance loop exactly like infer_folder.py:90-146.
     Returns (audio-s/s, ms per step, description of the sample, cores)."""
     import torch
@@ -138,8 +138,11 @@ def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None):
         _, noisy = O.synth_pair(0, n_samples=n_samples)
         t0 = time.perf_counter()
         with torch.no_grad():
-            O.enhance(noisy[None], model, bridge, O.SpecConfig())
-        return time.perf_counter() - t0
+            out = O.enhance(noisy[None], model, bridge, O.SpecConfig())
+        dt = time.perf_counter() - t0
+        if keep_probe is not None and n_samples == SR:        # the 1 s probe doubles as the SI-SDR parity sample
+            keep_probe.update(sd=sd, noisy=noisy, ref=out.numpy(), si_sdr=O.si_sdr)
+        return dt
 
     # probe with 1 s of audio, then pick the largest utterance length whose K+W repetitions fit the budget
     probe = run(SR)
@@ -530,9 +533,30 @@ def main():
     launches_per_step = n_micro * (1 + 1 + BRIDGE_STEPS * (info["launches"] + 1) + 1)
 
     cpu_baseline = None
+    si_sdr_delta = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, ms, sample, cores = cpu_reference_leg(seconds_budget=25.0)
+        probe = {}
+        v, ms, sample, cores = cpu_reference_leg(seconds_budget=25.0, keep_probe=probe)
         cpu_baseline = {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample, "ms_per_utterance": ms}
+        if probe and not predictive:
+            # SI-SDR delta (the third part of BASELINE.json's metric): the CUDA path with the oracle's weights on the probe
+            # utterance, against a target the reference output scores 15 dB on (the regime of a trained model)
+            import numpy as np
+            pm = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
+            pm.dnn.load_state_dict(probe["sd"])
+            pm = pm.to(dev).eval()
+            got = pm.enhance(probe["noisy"][None])
+            ref = probe["ref"].reshape(-1).astype(np.float64)
+            rng = np.random.default_rng(0)
+            nz = rng.standard_normal(ref.shape)
+            nz -= ref * (nz @ ref) / (ref @ ref)
+            target = ref + nz * np.sqrt((ref @ ref) / (nz @ nz) / 10 ** 1.5)
+            si = probe["si_sdr"]
+            si_sdr_delta = {"delta_db_on_15dB_target": float(abs(si(target, got) - si(target, ref))),
+                            "agreement_db": float(si(ref, got)),
+                            "sample": "1 s synthetic utterance, oracle weights, ours (CUDA) vs the reference port (CPU fp32)"}
+            pm.dnn.release_plans()
+            del pm
 
     if rank == 0:
         config.update({"micro_batch": mb, "parallelism": f"utterance-sharded x{world}",
@@ -548,6 +572,7 @@ def main():
             "per_backbone_forward_ms_per_utt": ms_total / args.steps / (args.utts * BRIDGE_STEPS),
             "model_tflops": GFLOP_PER_FORWARD * BRIDGE_STEPS * args.utts * world * args.steps / (ms_total * 1e-3) / 1e3,
             "roofline": roofline, "kernel_share": shares, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
+            "si_sdr": si_sdr_delta,
             "clocks": clock_info}))
     if world > 1:
         dist.destroy_process_group()
