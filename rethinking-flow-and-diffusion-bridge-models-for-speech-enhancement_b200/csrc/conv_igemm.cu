@@ -454,6 +454,23 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       for (int j = eg; j <= eg; ++j) {
         const TileCoord tc = decode_tile(p, ct * MT + j);
         if (!tc.valid) continue;                          // warp-uniform
+#if defined(FDBM_EPI_TEST)
+        {   // measurement builds only (tools/conv_bench.py): 1 = drain TMEM and discard, 2 = do not even read TMEM
+#if FDBM_EPI_TEST == 1
+          uint32_t acc = 0;
+#pragma unroll
+          for (int ch = 0; ch < BN / 32; ++ch) {
+            uint32_t v[32];
+            tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
+            tmem_ld_wait();
+#pragma unroll
+            for (int u = 0; u < 32; ++u) acc ^= v[u];
+          }
+          if (acc == 0x12345678u && p.out_h16) p.out_h16[0] = op_t(0);
+#endif
+          continue;
+        }
+#endif
         if (do_stats && stat_b != tc.b) {
           if (stat_b >= 0) flush_stats();
           stat_b = tc.b;
