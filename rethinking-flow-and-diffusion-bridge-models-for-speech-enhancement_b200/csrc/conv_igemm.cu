@@ -146,7 +146,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   uint64_t* a_ready = acc_empty + 2;                   // A stage transformed (or passed through) -> MMA may read it
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + A_STAGES);
 
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches and everything
+  // derived from them on the uniform datapath (no per-access R2UR of the memory descriptor in the epilogue)
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;
   const int n_kb = p.n_kb;
 
   if (threadIdx.x == 0) {

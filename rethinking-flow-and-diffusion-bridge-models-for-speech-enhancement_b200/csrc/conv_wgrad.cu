@@ -68,7 +68,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   uint64_t* empty = bars + STAGES;
   uint64_t* done = empty + STAGES;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(done + 1);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
 
   const int split = blockIdx.x;
   const int group = blockIdx.y;                           // df for 3x3; 0 for 1x1
