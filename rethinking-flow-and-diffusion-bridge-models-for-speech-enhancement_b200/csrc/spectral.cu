@@ -169,7 +169,7 @@ stft_compress_kernel(const float* __restrict__ wave, int n_samples, const int* _
                      int pad_mode, int M, int n_frames_out, float2* __restrict__ spec) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int b = blockIdx.y;
   const int t0 = blockIdx.x * FR;
   const float* x = wave + static_cast<int64_t>(b) * wave_stride;
@@ -250,7 +250,7 @@ decompress_istft_kernel(const float2* __restrict__ spec, int M, const float* __r
                         int64_t wave_stride, float* __restrict__ wave) {
   extern __shared__ __align__(16) uint8_t smem_raw[];
   SpecSmem& sm = *reinterpret_cast<SpecSmem*>(smem_raw);
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int b = blockIdx.y;
   if (lengths) length = __ldg(lengths + b);    // variable-length batch: samples beyond this utterance's length are not written
   const int R = NFFT / hop;

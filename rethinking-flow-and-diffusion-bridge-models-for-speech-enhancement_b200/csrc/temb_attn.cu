@@ -52,7 +52,7 @@ __global__ void __launch_bounds__(256)
 dense_all_kernel(const float* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias, int B,
                  int K, int rows, float* __restrict__ out) {
   extern __shared__ float sa[];          // [8][K]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   for (int b0 = 0; b0 < B; b0 += 8) {
     const int nb = min(8, B - b0);
     __syncthreads();
@@ -89,7 +89,7 @@ attention_kernel(const op_t* __restrict__ q, const op_t* __restrict__ k,
                  const op_t* __restrict__ v, int ld, int L, int C, float scale,
                  op_t* __restrict__ o, int ldo) {
   extern __shared__ float sm[];                       // per warp: q[C] | p[L]
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int b = blockIdx.y;
   const int qi = blockIdx.x * ATT_WARPS + warp;
   if (qi >= L) return;
@@ -193,7 +193,7 @@ attention_mma_kernel(const op_t* __restrict__ q, const op_t* __restrict__ k, con
   op_t* sQ = reinterpret_cast<op_t*>(att_smem);
   op_t* sK = sQ + AT_BQ * AT_PITCH;
   op_t* sV = sK + AT_BK * AT_PITCH;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int warp = __shfl_sync(0xffffffffu, static_cast<int>(threadIdx.x >> 5), 0), lane = threadIdx.x & 31;   // warp-uniform for the compiler
   const int g = lane >> 2, t = lane & 3;
   const int b = blockIdx.y, q0 = blockIdx.x * AT_BQ;
   const int64_t base = static_cast<int64_t>(b) * L;
