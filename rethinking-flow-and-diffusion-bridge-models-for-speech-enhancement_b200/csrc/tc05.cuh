@@ -70,10 +70,11 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
 
 // Wait with back-off for warps that are NOT on the MMA issue path (epilogue, operand transform, TMA producers): between
 // polls the warp sleeps, which frees issue slots and power for the warps that do the work.
+template <int NS = 40>
 __device__ __forceinline__ void mbar_wait_relaxed(uint64_t* bar, uint32_t parity) {
   uint32_t spins = 0;
   while (!mbar_try_wait(bar, parity)) {
-    __nanosleep(40);
+    __nanosleep(NS);
     if (++spins > (1u << 22)) __trap();
   }
 }
