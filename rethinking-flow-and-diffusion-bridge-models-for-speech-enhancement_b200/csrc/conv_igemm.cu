@@ -623,7 +623,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
-          if (RES16) load_res16(ch);                      // L2 hits (prefetched one tile ahead), in flight while TMEM is read
+          if (RES16) { if (ch == 0) load_res16(0); }      // chunks 1..3 were requested while the previous chunk was stored
           else if (res_p) load_res(res, ch);
           tmem_ld_wait();
 #pragma unroll
@@ -664,6 +664,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               o_hi[it].y += cbias.w + cw[3].x * p0 + cw[3].y * p1 + cw[3].z * p2 + cw[3].w * p3;
             }
           }
+          // the shortcut registers are free again: request the next chunk's rows now (L2 hits, prefetched one tile ahead), a
+          // whole store + statistics phase ahead of their use, without a second register buffer
+          if (RES16 && ch + 1 < BN / 32) load_res16(ch + 1);
           float2 ssum_lo = make_float2(0.f, 0.f), ssum_hi = ssum_lo, ssq_lo = ssum_lo, ssq_hi = ssum_lo;
           if (full) {                                       // whole tile inside the image: no per-row predicates
             if (of_p) {
