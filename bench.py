@@ -4,9 +4,12 @@
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference]
 
 One "step" = one pass of the whole hot path (fused STFT+compress+pad -> 5-step SB/ode_ei sampler on
-the NCSN++ backbone -> fused decompress+iSTFT) over this GPU's batch of 256 synthetic 4 s / 16 kHz
-utterances (BASELINE.json configs[1], `infer_folder`).  Utterances are independent units: every rank
-enhances its own 256 (weak scaling, no data-path collective); the value is the whole-job aggregate.
+the NCSN++ backbone -> fused decompress+iSTFT) over the batch of 256 synthetic 4 s / 16 kHz utterances
+of BASELINE.json configs[1] (`infer_folder`: "a batch of 256 ... utterance-sharded over 1/2/4/8").
+Utterances are independent units.  With N GPUs the 256 utterances are split into N contiguous shards
+(`split_list`, infer_folder.py:149-152), every rank enhances its shard with no data-path collective,
+and the enhanced waveforms are gathered onto every rank with ONE NCCL all_gather INSIDE the timed
+region (north_star (d)) -- "scaling": "strong".  `--scaling weak` keeps 256 utterances PER GPU instead.
 
 Prints ONE JSON line (see the task contract): value (device-resident inputs), e2e (host buffers,
 H2D/D2H inside the timed region), roofline of the dominant kernel (tcgen05 implicit-GEMM convolution,
@@ -160,9 +163,80 @@ def cpu_reference_leg(seconds_budget=25.0, steps=1, warmup=0, threads=None, keep
     return seconds / dt, dt * 1e3, sample, cores
 
 
-# dram bytes (read + write) of all 114 conv_igemm launches of ONE forward at T=256, by micro-batch, from the ncu capture
-# summarised in profiles/r01i_conv_traffic.txt (82.518 GB read + 39.090 GB written at micro-batch 128)
-NCU_CONV_DRAM_GB_PER_FORWARD = {128: 121.608}
+def ncu_conv_traffic(micro_batch, n_frames):
+    """roofline.traffic: dram__bytes_read.sum + dram__bytes_write.sum of the conv_igemm launches of one forward, per launch,
+    from the committed ncu capture of THIS build (profiles/conv_traffic.json, written by tools/ncu_summary.py from an
+    `ncu --set full` run; it records the sha256 of csrc/conv_igemm.cu it was taken on).  None when there is no capture for
+    this micro-batch / frame count or when the kernel source has changed since the capture."""
+    import hashlib
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "conv_traffic.json")))
+        src = open(os.path.join(PKG, "csrc", "conv_igemm.cu"), "rb").read()
+        if rec.get("conv_igemm_sha256") != hashlib.sha256(src).hexdigest():
+            return None, "profiles/conv_traffic.json was captured on an older conv_igemm.cu"
+        for e in rec.get("captures", []):
+            if e["micro_batch"] == micro_batch and e["n_frames"] == n_frames:
+                return e["dram_bytes"] / e["launches"], rec.get("source", "profiles/conv_traffic.json")
+        return None, "no capture at this micro-batch"
+    except Exception as ex:                                          # no capture committed
+        return None, f"no capture ({type(ex).__name__})"
+
+
+def torch_gpu_baseline_leg(dev, n_batch=16, budget_s=20.0):
+    """The same-box bar SURVEY.md 8(d) asks for: the reference path in stock PyTorch on THIS GPU (cuFFT STFT, cuDNN
+    convolutions, ATen GroupNorm / SiLU / softmax), i.e. the oracle port run on `cuda` instead of `cpu`.  Two precisions:
+    fp32 with TF32 convolutions (PyTorch's default, what the reference gets) and bf16 autocast; two batchings: the
+    reference's B = 1 file loop (infer_folder.py:93-121) and a batch of `n_batch`.  Baseline only -- not on any product path."""
+    import torch
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import fdbm_oracle as O
+    cfg = O.NcsnppConfig()
+    sd = {k: v.to(dev) for k, v in O.sensitised_state_dict(cfg, seed=0).items()}
+    table = O.Bridge("sb", N=BRIDGE_STEPS, sampler_type="ode_ei").coefficient_table().tolist()
+    times = O.Bridge("sb", N=BRIDGE_STEPS, sampler_type="ode_ei").time_grid()[:-1].tolist()
+    win = torch.sqrt(torch.hann_window(512, periodic=True)).to(dev)
+    waves = synth_batch(n_batch, dev, seed=777)
+
+    def enhance(y):                                                  # infer_single.py:80-99 / bridge.py:66-87 in torch ops
+        norm = y.abs().amax(1, keepdim=True)
+        S = torch.stft(y / norm, 512, 256, window=win, center=True, return_complex=True)
+        Y = 0.15 * S.abs() ** 0.5 * torch.exp(1j * S.angle())
+        T = Y.shape[-1]
+        pad = (64 - T % 64) % 64
+        if pad:
+            idx = torch.arange(T + pad, device=dev)
+            Y = Y[..., torch.where(idx < T, idx, 2 * (T - 1) - idx)]
+        Y = Y[:, None]
+        x = Y.clone()
+        for (wx, ws, wy), t in zip(table, times):
+            D = O.ncsnpp_forward(sd, cfg, x, Y, torch.full((y.shape[0],), t, device=dev))
+            x = wx * x + ws * D + wy * Y
+        X = x[:, 0] / 0.15
+        X = X.abs() ** 2 * torch.exp(1j * X.angle())
+        return torch.istft(X, 512, 256, window=win, center=True, length=y.shape[1]) * norm
+
+    out = {"what": "oracle port (= the reference's torch ops) on cuda: cuFFT + cuDNN + ATen, same weights / sampler; "
+                   f"{UTT_SECONDS:g} s utterances, N={BRIDGE_STEPS}"}
+    t_start = time.perf_counter()
+    for label, autocast in (("fp32_tf32conv", False), ("bf16_autocast", True)):
+        for bname, batch in (("B1_loop", waves[:1]), (f"B{n_batch}", waves)):
+            if time.perf_counter() - t_start > budget_s:
+                break
+            try:
+                with torch.no_grad(), torch.autocast("cuda", dtype=torch.bfloat16, enabled=autocast):
+                    enhance(batch); torch.cuda.synchronize()
+                    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                    reps = 3 if batch.shape[0] == 1 else 1
+                    e0.record()
+                    for _ in range(reps):
+                        enhance(batch)
+                    e1.record(); torch.cuda.synchronize()
+                ms = e0.elapsed_time(e1) / reps
+                out[f"{label}_{bname}"] = {"audio_s_per_s": batch.shape[0] * UTT_SECONDS / (ms * 1e-3), "ms": ms}
+            except Exception as ex:                                  # e.g. out of memory at the batched setting
+                out[f"{label}_{bname}"] = {"error": f"{type(ex).__name__}: {str(ex)[:120]}"}
+            torch.cuda.empty_cache()
+    return out
 
 
 def hbm_kernel_leg(model, waves, dev, reps=20):
@@ -395,6 +469,10 @@ def main():
     ap.add_argument("--train-batch", type=int, default=16, help="training crops per GPU per step (configs[3]: 8 x 16)")
     ap.add_argument("--bridge-steps", type=int, default=5, help="configs[4]: sampling-step sweep 1/5/10/30")
     ap.add_argument("--seconds", type=float, default=4.0, help="configs[4]: utterance length (30 s long-form)")
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
+                    help="multi-GPU: 'strong' = --utts utterances in TOTAL, sharded (BASELINE configs[1]); 'weak' = --utts per GPU")
+    ap.add_argument("--no-gather", action="store_true", help="skip the final NCCL all_gather of the enhanced waveforms")
+    ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     args = ap.parse_args()
     predictive = args.workload == "predictive"
     set_workload(args.seconds, args.bridge_steps, predictive)
@@ -406,12 +484,14 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
-    config = {"workload": (f"{args.workload}: {args.utts} synthetic {UTT_SECONDS:g} s 16 kHz utterances per GPU, " +
+    strong = args.scaling == "strong"
+    total_utts = args.utts if strong else args.utts * world
+    config = {"workload": (f"{args.workload}: {total_utts} synthetic {UTT_SECONDS:g} s 16 kHz utterances, " +
                            ("ncsnpp_v2_predictive (random init re-sensitised), one backbone pass, "
                             if predictive else
                             f"ncsnpp_v2 (65.6 M params, random init re-sensitised), Bridge('sb','bb') ode_ei N={BRIDGE_STEPS}, ") +
                            "fused STFT/compress/pad and decompress/iSTFT"),
-              "utterances_per_gpu": args.utts, "bridge_steps": BRIDGE_STEPS}
+              "utterances": total_utts, "bridge_steps": BRIDGE_STEPS}
 
     if args.impl == "reference":
         if rank != 0:
@@ -419,8 +499,9 @@ def main():
         v, ms, sample, cores = cpu_reference_leg(steps=args.steps, warmup=args.warmup)
         print(json.dumps({
             "impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32", "data": "synthetic", "config": config,
+            "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": args.scaling if args.gpus > 1 else "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic", "config": config,
+            "note": "ONE CPU process on this box's host cores whatever --gpus says (rank 0 only); a bounded sample, extrapolated",
             "cpu_baseline": {"value": v, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
             "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}))
@@ -428,7 +509,7 @@ def main():
 
     import torch
     import torch.distributed as dist
-    from fdbm_b200 import EnhancementModel, _lib, sensitise_
+    from fdbm_b200 import EnhancementModel, _lib, gather_waveforms, sensitise_, split_list
     from fdbm_b200.model import PredictiveEnhancementModel
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
@@ -436,27 +517,42 @@ def main():
         dist.init_process_group("nccl", device_id=dev)
     _lib.check(_lib.load().fdbm_check_device(), "fdbm_check_device")
 
-    mb = args.micro_batch
+    # this rank's shard of the utterance list (contiguous chunks, infer_folder.py:149-152)
+    if strong:
+        shards = split_list(list(range(args.utts)), world)
+        my_ids, counts = shards[rank], [len(s) for s in shards]
+    else:
+        my_ids, counts = list(range(rank * args.utts, (rank + 1) * args.utts)), [args.utts] * world
+    n_local = len(my_ids)
+    mb = max(1, min(args.micro_batch, n_local))
+    do_gather = world > 1 and not args.no_gather
     if predictive:
         model = PredictiveEnhancementModel("ncsnpp_v2_predictive")
     else:
         model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
     sensitise_(model.dnn, seed=0)
     model = model.to(dev).eval()
-    waves = synth_batch(args.utts, dev, seed=1234 + 100000 * rank)        # rank r owns its own utterances
+    # utterance i is the same signal whatever the GPU count (the generator is keyed by the utterance id, not the rank)
+    all_waves = synth_batch(total_utts, dev, seed=1234)
+    waves = all_waves[my_ids[0]:my_ids[-1] + 1].contiguous()
+    del all_waves
     host_in = torch.empty(waves.shape, dtype=torch.float32, pin_memory=True).copy_(waves)
-    host_out = torch.empty_like(host_in, pin_memory=True)
+    n_out = total_utts if do_gather else n_local
+    host_out = torch.empty(n_out, waves.shape[1], dtype=torch.float32, pin_memory=True)
+    local_out = torch.empty_like(waves)
 
     def step_device():
-        return model.enhance_many(waves, micro_batch=mb)
+        out = model.enhance_many(waves, micro_batch=mb)
+        return gather_waveforms(out, counts) if do_gather else out
 
     def step_e2e():
-        for i in range(0, args.utts, mb):
+        for i in range(0, n_local, mb):
             chunk = host_in[i:i + mb].to(dev, non_blocking=True)
             n = chunk.shape[0]
             if n < mb:
                 chunk = torch.cat([chunk, chunk[-1:].expand(mb - n, -1)], dim=0)
-            host_out[i:i + n].copy_(model.enhance_batch(chunk)[:n], non_blocking=True)
+            local_out[i:i + n] = model.enhance_batch(chunk)[:n]
+        host_out.copy_(gather_waveforms(local_out, counts) if do_gather else local_out, non_blocking=True)
 
     def barrier():
         if world > 1:
@@ -486,7 +582,7 @@ def main():
     step_e2e()
     ms_e2e = timed(step_e2e, args.steps)
 
-    audio_s = args.utts * UTT_SECONDS * world
+    audio_s = total_utts * UTT_SECONDS
     value = audio_s * args.steps / (ms_total * 1e-3)
     e2e = audio_s * args.steps / (ms_e2e * 1e-3)
 
@@ -517,10 +613,10 @@ def main():
                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak,
                     "peak_source": "MEASURED_PEAKS.json bf16_tflops_sustained (kernel timed inside a long step)"
                     if peaks else "fallback 1.4 PFLOP/s sustained (B200_PROFILING.md)",
-                    "traffic": NCU_CONV_DRAM_GB_PER_FORWARD[mb] * 1e9 / max(1, n_conv)
-                    if (mb in NCU_CONV_DRAM_GB_PER_FORWARD and n_frames == 256 and not predictive) else None,
+                    "traffic": None if predictive else ncu_conv_traffic(mb, n_frames)[0],
+                    "traffic_source": None if predictive else ncu_conv_traffic(mb, n_frames)[1],
                     "traffic_unit": "bytes per launch (dram__bytes_read.sum + dram__bytes_write.sum over the conv launches of one "
-                                    "forward at this micro-batch, ncu, profiles/r01i_conv_traffic.txt) / launches",
+                                    "forward at this micro-batch, ncu --set full) / launches",
                     "launches_per_forward": n_conv,
                     "avg_launch_ms": conv_ms / max(1, n_conv),
                     "algorithmic_gflop_per_forward_per_utt": conv_flops / mb / 1e9}
@@ -529,8 +625,13 @@ def main():
         shares = {names[k]: round(v / tot, 4) for k, v in sorted(kind_ms.items())}
         shares["forward_ms_per_microbatch"] = tot
 
-    n_micro = (args.utts + mb - 1) // mb
+    n_micro = (n_local + mb - 1) // mb
     launches_per_step = n_micro * (1 + 1 + BRIDGE_STEPS * (info["launches"] + 1) + 1)
+    torch_gpu = None
+    if rank == 0 and world == 1 and not args.no_torch_gpu_baseline and not predictive:
+        model.dnn.release_plans()                                   # give the stock-PyTorch leg the memory
+        torch.cuda.empty_cache()
+        torch_gpu = torch_gpu_baseline_leg(dev)
 
     cpu_baseline = None
     si_sdr_delta = None
@@ -545,7 +646,7 @@ def main():
             pm = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
             pm.dnn.load_state_dict(probe["sd"])
             pm = pm.to(dev).eval()
-            got = pm.enhance(probe["noisy"][None])
+            got = pm.enhance(probe["noisy"][None], pad_mode="reflection")
             ref = probe["ref"].reshape(-1).astype(np.float64)
             rng = np.random.default_rng(0)
             nz = rng.standard_normal(ref.shape)
@@ -559,20 +660,23 @@ def main():
             del pm
 
     if rank == 0:
-        config.update({"micro_batch": mb, "parallelism": f"utterance-sharded x{world}",
-                       "l2": f"working set per step >> L2: {info['device_bytes'] / 2**30:.1f} GiB of activations+weights "
-                             f"per micro-batch, {n_micro} micro-batches per step (no explicit flush needed)"})
+        run = {"micro_batch": mb, "parallelism": f"utterance-sharded x{world}", "utterances_per_gpu": counts,
+               "final_gather": ("NCCL all_gather of the enhanced waveforms onto every rank, inside the timed region "
+                                f"({total_utts * N_SAMPLES * 4 / 1e6:.1f} MB)") if do_gather else "none",
+               "l2": f"working set per step >> L2: {info['device_bytes'] / 2**30:.1f} GiB of activations+weights "
+                     f"per micro-batch, {n_micro} micro-batches per step per GPU (no explicit flush needed)"}
         print(json.dumps({
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3),
-            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "bf16" if _lib.load().fdbm_operand_is_bf16() else "fp16", "data": "synthetic", "config": config,
-            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": args.utts * N_SAMPLES * 4,
-                    "d2h_bytes_per_step": args.utts * N_SAMPLES * 4, "ms_per_step": ms_e2e / args.steps},
+            "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": args.scaling if world > 1 else "weak",
+            "vs_baseline": None,
+            "dtype": "bf16" if _lib.load().fdbm_operand_is_bf16() else "fp16", "data": "synthetic", "config": config, "run": run,
+            "e2e": {"value": e2e, "unit": UNIT, "h2d_bytes_per_step": n_local * N_SAMPLES * 4,
+                    "d2h_bytes_per_step": n_out * N_SAMPLES * 4, "ms_per_step": ms_e2e / args.steps},
             "gpu_launches": launches_per_step * args.steps,
-            "per_backbone_forward_ms_per_utt": ms_total / args.steps / (args.utts * BRIDGE_STEPS),
-            "model_tflops": GFLOP_PER_FORWARD * BRIDGE_STEPS * args.utts * world * args.steps / (ms_total * 1e-3) / 1e3,
+            "per_backbone_forward_ms_per_utt": ms_total / args.steps / (max(counts) * BRIDGE_STEPS),
+            "model_tflops": GFLOP_PER_FORWARD * BRIDGE_STEPS * total_utts * args.steps / (ms_total * 1e-3) / 1e3,
             "roofline": roofline, "kernel_share": shares, "hbm_kernels": hbm_kernels, "cpu_baseline": cpu_baseline,
-            "si_sdr": si_sdr_delta,
+            "si_sdr": si_sdr_delta, "torch_gpu_baseline": torch_gpu,
             "clocks": clock_info}))
     if world > 1:
         dist.destroy_process_group()

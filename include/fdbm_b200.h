@@ -89,6 +89,28 @@ int fdbm_decompress_istft_var(const float* spec, int batch, int n_frames,
                               int transform_type, float spec_factor, float abs_exponent,
                               const int* lengths, int64_t max_length, int64_t wave_stride, float* wave, void* stream);
 
+/* The same two kernels with the elementwise glue of `enhance` folded in (fdbm/model.py:391-406, infer_single.py:80-99,
+ * infer_folder.py:100-121), so that no PyTorch elementwise pass is left on the path:
+ *   fdbm_wave_absmax          out[b] = max_n |wave[b, n]|  (norm_factor = y.abs().max(), infer_single.py:83-84)
+ *   fdbm_stft_compress_ex     spec = pad_spec(spec_fwd(stft(wave / norm[b])));  norm NULL = no normalisation; lengths NULL =
+ *                             all rows max_samples long.  The division is applied to the spectrum (the STFT is linear):
+ *                             results agree with dividing the waveform first to rounding (~1e-7 relative).
+ *   fdbm_decompress_istft_ex  wave = istft(spec_back(spec)) * norm[b]  (x_hat * norm_factor, infer_single.py:94) and, when
+ *                             `peak` is given, peak[b] = max |wave[b]| for the clip rule; norm / peak / lengths may be NULL.
+ *   fdbm_clip_rescale         if peak[b] > 1: wave[b] = wave[b] / peak[b] * rescale   (infer_single.py:95-97 with 0.5,
+ *                             infer_folder.py:119-120 with 0.95)
+ * norm / peak: fp32 [B] device. */
+int fdbm_wave_absmax(const float* wave, int batch, int64_t n_samples, const int* lengths, int64_t wave_stride, float* out,
+                     void* stream);
+int fdbm_stft_compress_ex(const float* wave, int batch, const int* lengths, int64_t min_samples, int64_t max_samples,
+                          int64_t wave_stride, const float* window, const float* norm, int n_fft, int hop, int transform_type,
+                          float spec_factor, float abs_exponent, int pad_mode, int n_frames_out, float* spec, void* stream);
+int fdbm_decompress_istft_ex(const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
+                             int transform_type, float spec_factor, float abs_exponent, const int* lengths, int64_t max_length,
+                             int64_t wave_stride, const float* norm, float* peak, float* wave, void* stream);
+int fdbm_clip_rescale(float* wave, int batch, int64_t n_samples, const int* lengths, int64_t wave_stride, const float* peak,
+                      float rescale, void* stream);
+
 /* Unfused pieces of the same front/back end, for callers that keep the reference's call sequence:
  * spec_fwd / spec_back (fdbm/data_module.py:173-199; inverse = 0 / 1) over n_complex elements, and
  * pad_spec (fdbm/util/other.py:76-90) over `rows` = B*1*F rows of n_frames -> n_frames_out frames. */
@@ -111,6 +133,29 @@ int fdbm_pad_spec(const float* in, int64_t rows, int n_frames, int pad_mode, int
  * --------------------------------------------------------------------------------------------- */
 int fdbm_prior_sample(const float* y, const float* z, float b, float sigma, uint64_t seed, uint64_t offset,
                       int64_t n_complex, float* x, void* stream);
+/* Predictor-corrector sampler arithmetic (Bridge.pc_sampler fdbm/bridge.py:142-166; EulerMaruyamaPredictor
+ * util/predictors.py:39-51; LangevinCorrector / AnnealedLangevinDynamics util/correctors.py:36-81).  Every update of that
+ * sampler has the form   x_mean = c0*x + c1*d + c2*y ;  x = x_mean + c3*z   with per-step scalars:
+ *   coef        DEVICE fp32[4] = (c0, c1, c2, c3)
+ *   z           noise cplx like x, or NULL = in-kernel Philox keyed by (seed, offset, element)
+ *   x_mean_out  optional: the noise-free state (`denoise=True` returns it after the last step)
+ * fdbm_langevin_coef computes coef for the Langevin corrector, whose step size depends on the data
+ * (correctors.py:47-50): step = 2 (snr * mean_b |z_b| / (mean_b |grad_b| + 1e-8))^2, grad = -(x - a d - b y) / (sigma^2 + 1e-8),
+ * a, b, sigma = path_param(t); the norms are per utterance (batch x n_per_utt complex elements), z as above with the SAME
+ * (seed, offset) the following fdbm_bridge_update4 call uses; scratch = 2*batch doubles. */
+int fdbm_bridge_update4(float* x, const float* d, const float* y, const float* z, const float* coef, uint64_t seed,
+                        uint64_t offset, int64_t n_complex, float* x_mean_out, void* stream);
+int fdbm_langevin_coef(const float* x, const float* d, const float* y, const float* z, float a, float b, float sigma,
+                       float snr, uint64_t seed, uint64_t offset, int batch, int64_t n_per_utt, double* scratch,
+                       float* coef_out, void* stream);
+/* Adaptive ODE sampler (Bridge.ode_sampler_int fdbm/bridge.py:115-140 -> scipy.integrate.solve_ivp RK45, whose stage
+ * arithmetic the reference runs on the host over the flattened state): out = sum_k coefs[k] * srcs[k] over n_floats
+ * fp32 elements (srcs: HOST array of n_terms <= 8 device pointers, coefs: HOST), and the controller's error measure
+ * *out_sumsq = sum_i |sum_k coefs[k] srcs[k][i]|^2 / (atol + rtol max(|y_i|, |y_new_i|))^2 over n_complex complex
+ * elements (device double; scipy's error_norm = sqrt(out_sumsq / n_complex)). */
+int fdbm_lincomb(float* out, const float* const* srcs, const float* coefs, int n_terms, int64_t n_floats, void* stream);
+int fdbm_rk_error_norm(const float* const* srcs, const float* coefs, int n_terms, const float* y, const float* y_new,
+                       float rtol, float atol, int64_t n_complex, double* out_sumsq, void* stream);
 int fdbm_bridge_step(float* x, const float* d, const float* y_or_z, const float* coef, int kind,
                      uint64_t seed, uint64_t offset, int64_t n_complex, void* stream);
 
@@ -163,8 +208,11 @@ int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float* y, const f
  *   times fp32 [n_steps]     HOST; t_prev of every step (time_steps[:-1]) -- what the backbone sees
  *   coef  fp32 [n_steps,3]   HOST; coefficient table
  *   noise cplx [n_steps, B,1,257,T] device, or NULL (SDE only; NULL = in-kernel Philox with `seed`)
- * y, x (and noise) are staged into plan-owned buffers, so the N-step loop is captured ONCE per
- * (plan, n_steps, kind) as a CUDA graph and replayed for every later call whatever the pointers. */
+ * y and x are staged into buffers fdbm_plan_create allocated, and times / coef / seed travel through a plan-owned ring of
+ * pinned host slots, so the call never allocates and the N-step loop is captured ONCE per (plan, n_steps, kind, noise
+ * address) as a CUDA graph and replayed for every later call.  n_steps <= 1024.  `stream` must not be capturing
+ * (FDBM_ESTATE): the sampler owns its graph.  A plan serves one host thread at a time and only on the device it was
+ * created on (FDBM_ESTATE if another device is current). */
 int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
                      int n_steps, int kind, const float* noise, uint64_t seed, void* stream);
 
@@ -188,8 +236,20 @@ int fdbm_plan_num_backward_launches(const fdbm_plan* plan);
 /* measurement aid: backward of the last forward with a CUDA event pair around every recorded op; returns the op count */
 int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, float loss_scale, float* ms, int* kinds, int max_ops,
                                void* stream);
+/* `step` and `ema_warmup` as in fdbm_adam_ema_step (step 0 = device-side count of applied steps, the normal mode). */
 int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, float lr, float beta1, float beta2,
-                             float eps, int step, float ema_decay, void* stream);
+                             float eps, int step, float ema_decay, int ema_warmup, void* stream);
+/* Adam moments <- 0, EMA <- current parameters (what torch_ema does at construction), counters <- 0. */
+int fdbm_plan_reset_optimizer(fdbm_plan* plan, void* stream);
+/* {applied updates, skipped steps, last gradient norm, reserved} copied to the HOST array `out`.  This call
+ * synchronises `stream` (it is how the host learns about skipped steps to back the loss scale off). */
+int fdbm_plan_optimizer_state(fdbm_plan* plan, double* out, void* stream);
+/* Overwrite the device-side counters (checkpoint restore: torch_ema's num_updates, Adam's step). */
+int fdbm_plan_set_optimizer_state(fdbm_plan* plan, double applied, double skipped, void* stream);
+/* EMA evaluation swap (model.py:146-160 store / copy_to / restore): to_ema != 0 saves the current parameters in a
+ * plan-owned backup and loads the EMA into the live parameters; to_ema == 0 restores the backup.  Packed weights are
+ * rebuilt either way.  FDBM_ESTATE if restore is called without a preceding swap. */
+int fdbm_plan_swap_ema(fdbm_plan* plan, int to_ema, void* stream);
 
 /* Loss head of the training step: BridgeModel._loss, "data_prediction_hybrid" (fdbm/model.py:187-218, pesq_weight 0):
  *   L = 70 mean((|X|^0.3 - |X^|^0.3)^2) + 30 sum |X/|X|^0.7 - X^/|X^|^0.7|^2 / N - mean_b log10 SI-SNR(istft X, istft X^)
@@ -297,12 +357,19 @@ int fdbm_fir_resample_h16(const void* in, int batch, int T, int F, int C, int mo
  * -> g_qkv h16 [B,L,3C].  scratch: 2*B*L*L floats. */
 int fdbm_attention_bwd(const void* qkv, int batch, int L, int C, const void* d_o, float* scratch, void* g_qkv, void* stream);
 /* Adam (model.py:101 configure_optimizers) with clip_grad_norm_ (gradient_clip_val) and the EMA update
- * (model.py:129-132) on flat fp32 buffers.  grads carry a factor grad_div (loss scale x world size) that is divided
- * out; a non-finite gradient norm skips the step.  scratch: 1025 doubles (the squared norm is reduced in a fixed
- * order so that every DDP rank derives the same clipping coefficient). */
+ * (model.py:129-132, torch_ema.ExponentialMovingAverage.update) on flat fp32 buffers.  grads carry a factor grad_div
+ * (loss scale x world size) that is divided out.  scratch: 1025 doubles (the squared norm is reduced in a fixed order so
+ * that every DDP rank derives the same clipping coefficient).
+ *   step        >= 1: the update count (Adam bias correction, EMA warm-up) given by the host;
+ *               0: counted on the device in state[0] -- only APPLIED steps count
+ *   ema_warmup  1: decay = min(ema_decay, (1 + n) / (10 + n)), torch_ema's use_num_updates=True default, which is what the
+ *               reference constructs (model.py:56); 0: constant ema_decay
+ *   state       device double[4] or NULL (required when step == 0): {applied updates, skipped steps, last gradient norm,
+ *               reserved}.  A non-finite gradient norm SKIPS the step (GradScaler semantics): parameters, moments, EMA
+ *               and state[0] stay as they are, state[1] is incremented. */
 int fdbm_adam_ema_step(float* params, const float* grads, float* m, float* v, float* ema, int64_t n, double* scratch,
                        float grad_div, float clip_norm, float lr, float beta1, float beta2, float eps, int step,
-                       float ema_decay, void* stream);
+                       float ema_decay, int ema_warmup, double* state, void* stream);
 
 /* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
  * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]).  Returns bytes via *bytes when wpack==NULL. */

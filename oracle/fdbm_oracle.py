@@ -218,6 +218,40 @@ class PathSB:
         return (torch.where(m, torch.zeros_like(a), a), torch.where(m, torch.ones_like(b), b),
                 torch.where(m, torch.zeros_like(s), s))
 
+    def auxiliary_param(self, t):
+        """bridge.py:240-253."""
+        ns = self.noise_schedule
+        if ns == "ve":
+            return 0.0, torch.sqrt(torch.tensor(self.c)) * self.k ** t
+        if ns == "vp":
+            return (-0.5 * (self.beta_0 + (self.beta_1 - self.beta_0) * t),
+                    torch.sqrt(torch.tensor(self.c) * (self.beta_0 + (self.beta_1 - self.beta_0) * t)))
+        if ns == "gmax":
+            return 0.0, torch.sqrt(torch.as_tensor(self.beta_0 + (self.beta_1 - self.beta_0) * t))
+        return 0.0, self.rho * torch.ones_like(t)
+
+    def ode(self, t, x, s, y):
+        """bridge.py:283-292.  The reference multiplies the [B] weights straight into [B,1,F,T] tensors, which is only a
+        per-utterance scaling for B = 1 (its only caller); the weights are reshaped to [B,1,1,1] here, identical for B = 1."""
+        rho, _, rho_bar, alpha, _, alpha_bar = self.rhos_alphas(t)
+        f, g = self.auxiliary_param(t)
+        w_x = f + g ** 2 * (rho_bar ** 2 - rho ** 2) / (2 * alpha ** 2 * rho ** 2 * rho_bar ** 2 + self.eps)
+        w_s = -g ** 2 / (2 * alpha * rho ** 2 + self.eps)
+        w_y = alpha_bar * g ** 2 / (2 * alpha ** 2 * rho_bar ** 2 + self.eps)
+        v = lambda w: w.reshape(-1, 1, 1, 1) if torch.is_tensor(w) else w
+        return v(w_x) * x + v(w_s) * s + v(w_y) * y
+
+    def sde(self, t, x, s, y):
+        """bridge.py:294-306 with diffusion_coeff_mode 'g' (bridge.py:211 hard-codes it), same broadcasting note as `ode`."""
+        rho, _, rho_bar, alpha, _, alpha_bar = self.rhos_alphas(t)
+        f, g = self.auxiliary_param(t)
+        gd = g
+        w_x = f + ((g ** 2 + gd ** 2) * rho_bar ** 2 - (g ** 2 - gd ** 2) * rho ** 2) / (2 * alpha ** 2 * rho ** 2 * rho_bar ** 2 + self.eps)
+        w_s = -(g ** 2 + gd ** 2) / (2 * alpha * rho ** 2 + self.eps)
+        w_y = alpha_bar * (g ** 2 - gd ** 2) / (2 * alpha ** 2 * rho_bar ** 2 + self.eps)
+        v = lambda w: w.reshape(-1, 1, 1, 1) if torch.is_tensor(w) else w
+        return v(w_x) * x + v(w_s) * s + v(w_y) * y, gd
+
     def sampling_param_ode_ei(self, t_curr, t_prev, batch_size, device="cpu"):
         """bridge.py:308-324."""
         tp = t_prev * torch.ones(batch_size); tc = t_curr * torch.ones(batch_size)
@@ -251,6 +285,11 @@ class PathFM:
 
     def path_param(self, t):
         return t, 1 - t, self.sigma_t(t)
+
+    def ode(self, t, x, s, y):
+        """bridge.py:368-371."""
+        sigma_t = self.sigma_t(t)[:, None, None, None]
+        return ((self.sigma_min - self.sigma_max) * x + self.sigma_max * s - self.sigma_min * y) / (sigma_t + self.eps)
 
     def sampling_param_ode_ei(self, t_curr, t_prev, batch_size, device="cpu"):
         """bridge.py:373-385."""
@@ -289,6 +328,74 @@ class Bridge:
     def time_grid(self):
         """bridge.py:70."""
         return torch.linspace(self.start_time, self.end_time, self.N + 1)
+
+    def score_fn(self, t, x, s, y):
+        """bridge.py:51-54."""
+        mean, sigma = self.probability_path(s, y, t)
+        return -(x - mean) / (sigma[:, None, None, None] ** 2 + 1e-8)
+
+    def pc_sampler(self, model: Callable, y: Tensor, predictor_name="reverse_diffusion", corrector_name="ald", denoise=True,
+                   snr=0.5, corrector_steps=1, z0: Optional[Tensor] = None, zs: Optional[Sequence[Tensor]] = None) -> Tensor:
+        """bridge.py:142-166 with util/predictors.py:39-62 (euler_maruyama, none) and util/correctors.py:36-95 (langevin, ald,
+        none).  `zs`: the noise draws in the reference's call order (per step: one per corrector iteration, drawn after the
+        model call, then the predictor's, drawn before its model call)."""
+        if predictor_name not in ("euler_maruyama", "none"):
+            raise ValueError(f"Predictor with name '{predictor_name}' unknown.")        # util/registry.py:26-31
+        if corrector_name not in ("langevin", "ald", "none"):
+            raise ValueError(f"Corrector with name '{corrector_name}' unknown.")
+        draws = iter(zs) if zs is not None else None
+        draw = (lambda x: next(draws)) if draws is not None else torch.randn_like
+        with torch.no_grad():
+            xt = self.prior_sampling(y, z0)
+            timesteps = torch.linspace(self.start_time, self.end_time, self.N)
+            xt_mean = xt
+            for i in range(self.N):
+                t = timesteps[i]
+                stepsize = t - timesteps[i + 1] if i != len(timesteps) - 1 else timesteps[-1]
+                vec_t = torch.ones(y.shape[0]) * t
+                if corrector_name != "none":
+                    std = self.path.sigma_t(vec_t)
+                    for _ in range(corrector_steps):
+                        s = model(xt, y, vec_t)
+                        grad = self.score_fn(vec_t, xt, s, y)
+                        noise = draw(xt)
+                        if corrector_name == "langevin":
+                            grad_norm = torch.norm(grad.reshape(grad.shape[0], -1), dim=-1).mean()
+                            noise_norm = torch.norm(noise.reshape(noise.shape[0], -1), dim=-1).mean()
+                            step_size = ((snr * noise_norm / (grad_norm + 1e-8)) ** 2 * 2).unsqueeze(0)
+                        else:
+                            step_size = (snr * std) ** 2 * 2
+                        xt_mean = xt + step_size[:, None, None, None] * grad
+                        xt = xt_mean + noise * torch.sqrt(step_size * 2)[:, None, None, None]
+                if predictor_name == "euler_maruyama":
+                    dt = -stepsize
+                    z = draw(xt)
+                    s = model(xt, y, vec_t)
+                    drift, diffusion = self.path.sde(vec_t, xt, s, y)
+                    xt_mean = xt + drift * dt
+                    xt = xt_mean + diffusion[:, None, None, None] * torch.sqrt(-dt) * z
+                else:
+                    xt_mean = xt
+            return xt_mean if denoise else xt
+
+    def ode_sampler_int(self, model: Callable, y: Tensor, rtol=1e-5, atol=1e-5, method="RK45", z0: Optional[Tensor] = None,
+                        stats: Optional[dict] = None, **kwargs) -> Tensor:
+        """bridge.py:115-140: scipy.integrate.solve_ivp over the flattened complex state (util/other.py to/from_flattened_numpy)."""
+        from scipy import integrate
+        with torch.no_grad():
+            x = self.prior_sampling(y, z0)
+            nfev = [0]
+
+            def ode_func(t, xf):
+                nfev[0] += 1
+                xt = torch.from_numpy(xf.reshape(y.shape)).type(torch.complex64)
+                tt = torch.ones(y.shape[0]) * t
+                return self.path.ode(tt, xt, model(xt, y, tt), y).detach().cpu().numpy().reshape((-1,))
+            sol = integrate.solve_ivp(ode_func, (self.start_time, self.end_time), x.detach().cpu().numpy().reshape((-1,)),
+                                      rtol=rtol, atol=atol, method=method, **kwargs)
+            if stats is not None:
+                stats.update(nfev=nfev[0], status=sol.status, n_steps=len(sol.t) - 1)
+            return torch.tensor(sol.y[:, -1]).reshape(y.shape).type(torch.complex64)
 
     def coefficient_table(self, batch_size=1) -> Tensor:
         """[N, 3] fp32 table of (w_x, w_s, w_y|w_z) the sampling loop applies, produced with the
@@ -515,9 +622,52 @@ def _gn(x, sd, p, C):
     return F.group_norm(x, min(C // 4, 32), sd[p + "weight"], sd[p + "bias"], eps=1e-6)
 
 
+# ---- reduced-precision operand emulation (what a tensor-core path does to the SAME fp32 algorithm) ---------------
+# The reference's own GPU path is not fp32: cuDNN convolutions run in TF32 by default (torch.backends.cudnn.allow_tf32 is
+# True), i.e. both operands of every convolution are rounded to a 10-bit mantissa and accumulated in fp32.  To judge
+# how far a 16-bit-operand implementation may legitimately be from the fp32 result, the oracle can replay that:
+# `with operand_rounding("tf32")` rounds both operands of every convolution ("tf32", round-to-nearest-even -- the most
+# favourable reading of TF32), or of every contraction incl. NIN / attention ("fp16", "bf16": operands through that type).
+_ROUND = {"mode": None}
+
+
+class operand_rounding:
+    def __init__(self, mode: Optional[str]):
+        assert mode in (None, "tf32", "fp16", "bf16")
+        self.mode = mode
+
+    def __enter__(self):
+        self.prev = _ROUND["mode"]
+        _ROUND["mode"] = self.mode
+        return self
+
+    def __exit__(self, *a):
+        _ROUND["mode"] = self.prev
+
+
+def round_tf32(x: Tensor) -> Tensor:
+    """fp32 -> TF32 (1+8+10 bits), round to nearest even, returned as fp32."""
+    i = x.contiguous().view(torch.int32)
+    i = (i + 0x0FFF + ((i >> 13) & 1)) & ~0x1FFF
+    return i.view(torch.float32)
+
+
+def _rnd(x: Tensor, contraction: str = "conv") -> Tensor:
+    m = _ROUND["mode"]
+    if m is None or (m == "tf32" and contraction != "conv"):
+        return x
+    if m == "tf32":
+        return round_tf32(x)
+    return x.to(torch.float16 if m == "fp16" else torch.bfloat16).to(torch.float32)
+
+
+def _conv2d(x, w, b=None, padding=0):
+    return F.conv2d(_rnd(x), _rnd(w), b, padding=padding)
+
+
 def _nin(x, W, b):
     """layers.py:546-555: channel mixing x[b,c,h,w] W[c,o] + b[o]."""
-    return torch.einsum("bchw,co->bohw", x, W) + b[None, :, None, None]
+    return torch.einsum("bchw,co->bohw", _rnd(x, "matmul"), _rnd(W, "matmul")) + b[None, :, None, None]
 
 
 def _resblock(sd, m: Mod, x, temb):
@@ -528,13 +678,13 @@ def _resblock(sd, m: Mod, x, temb):
         h, x = fir_up2(h), fir_up2(x)
     elif m.down:
         h, x = fir_down2(h), fir_down2(x)
-    h = F.conv2d(h, sd[p + "Conv_0.weight"], sd[p + "Conv_0.bias"], padding=1)
+    h = _conv2d(h, sd[p + "Conv_0.weight"], sd[p + "Conv_0.bias"], padding=1)
     if temb is not None:
         h = h + F.linear(F.silu(temb), sd[p + "Dense_0.weight"], sd[p + "Dense_0.bias"])[:, :, None, None]
     h = F.silu(_gn(h, sd, p + "GroupNorm_1.", m.cout))
-    h = F.conv2d(h, sd[p + "Conv_1.weight"], sd[p + "Conv_1.bias"], padding=1)
+    h = _conv2d(h, sd[p + "Conv_1.weight"], sd[p + "Conv_1.bias"], padding=1)
     if m.cin != m.cout or m.up or m.down:
-        x = F.conv2d(x, sd[p + "Conv_2.weight"], sd[p + "Conv_2.bias"])
+        x = _conv2d(x, sd[p + "Conv_2.weight"], sd[p + "Conv_2.bias"])
     return (x + h) / np.sqrt(2.0)
 
 
@@ -546,9 +696,9 @@ def _attn(sd, m: Mod, x):
     q = _nin(h, sd[p + "NIN_0.W"], sd[p + "NIN_0.b"]).reshape(B, C, H * W)
     k = _nin(h, sd[p + "NIN_1.W"], sd[p + "NIN_1.b"]).reshape(B, C, H * W)
     v = _nin(h, sd[p + "NIN_2.W"], sd[p + "NIN_2.b"]).reshape(B, C, H * W)
-    w = torch.einsum("bcq,bck->bqk", q, k) * (int(C) ** (-0.5))
+    w = torch.einsum("bcq,bck->bqk", _rnd(q, "matmul"), _rnd(k, "matmul")) * (int(C) ** (-0.5))
     w = F.softmax(w, dim=-1)
-    h = torch.einsum("bqk,bck->bcq", w, v).reshape(B, C, H, W)
+    h = torch.einsum("bqk,bck->bcq", _rnd(w, "matmul"), _rnd(v, "matmul")).reshape(B, C, H, W)
     h = _nin(h, sd[p + "NIN_3.W"], sd[p + "NIN_3.b"])
     return (x + h) / np.sqrt(2.0)
 
@@ -578,7 +728,7 @@ def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NcsnppConfig, x: Tensor, y: Optio
             taps["temb"] = temb
     pyr_in = h_in
     m = nxt()
-    hs = [F.conv2d(h_in, sd[f"all_modules.{m.idx}.weight"], sd[f"all_modules.{m.idx}.bias"], padding=1)]
+    hs = [_conv2d(h_in, sd[f"all_modules.{m.idx}.weight"], sd[f"all_modules.{m.idx}.bias"], padding=1)]
     L = len(cfg.ch_mult)
     for lvl in range(L):
         for _ in range(cfg.num_res_blocks):
@@ -591,7 +741,7 @@ def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NcsnppConfig, x: Tensor, y: Optio
             pyr_in = fir_down2(pyr_in)
             m = nxt()                                                               # Combine, layerspp.py:52-59
             p = f"all_modules.{m.idx}."
-            h = F.conv2d(pyr_in, sd[p + "Conv_0.weight"], sd[p + "Conv_0.bias"]) + h
+            h = _conv2d(pyr_in, sd[p + "Conv_0.weight"], sd[p + "Conv_0.bias"]) + h
             hs.append(h)
     h = hs[-1]
     h = _resblock(sd, nxt(), h, temb)
@@ -607,18 +757,43 @@ def ncsnpp_forward(sd: Dict[str, Tensor], cfg: NcsnppConfig, x: Tensor, y: Optio
             h = _attn(sd, nxt(), h)
         mg = nxt(); mc = nxt()
         ph = F.silu(_gn(h, sd, f"all_modules.{mg.idx}.", mg.cin))
-        ph = F.conv2d(ph, sd[f"all_modules.{mc.idx}.weight"], sd[f"all_modules.{mc.idx}.bias"], padding=1)
+        ph = _conv2d(ph, sd[f"all_modules.{mc.idx}.weight"], sd[f"all_modules.{mc.idx}.bias"], padding=1)
         pyramid = ph if pyramid is None else fir_up2(pyramid) + ph
         if lvl != 0:
             h = _resblock(sd, nxt(), h, temb)
     assert not hs and next(it, None) is None
     if taps is not None:
         taps["pyramid"] = pyramid
-    out = F.conv2d(pyramid, sd["output_layer.weight"], sd["output_layer.bias"])
+    out = _conv2d(pyramid, sd["output_layer.weight"], sd["output_layer.bias"])
     out = torch.view_as_complex(out.permute(0, 2, 3, 1).contiguous())[:, None]
     if ref.shape[2] == 257:
         out = torch.cat((out, torch.zeros_like(out[:, :, :1, :])), dim=2)
     return out
+
+
+def hybrid_loss(x_hat: Tensor, x: Tensor, cfg: SpecConfig) -> Tensor:
+    """BridgeModel._loss, loss_type "data_prediction_hybrid" with pesq_weight = 0 (model.py:187-218):
+    70 * MSE(|X|^0.3) + 30 * ||X/|X|^0.7 - X^/|X^|^0.7||^2 / numel - mean log10 SI-SNR(istft), all on the de-compressed
+    spectrograms.  x_hat, x: complex [B,1,F,T] (compressed domain).  Differentiable (torch autograd), any float width.
+    Pinned against the reference's own `_loss` by oracle/make_golden.py (tests/golden/hybrid_loss.npz)."""
+    B, C, Fq, T = x.shape
+    x_nc, x_hat_nc = spec_back(x, cfg), spec_back(x_hat, cfg)
+    x_mag, x_hat_mag = torch.abs(x_nc + 1e-12), torch.abs(x_hat_nc + 1e-12)
+    losses_mag = torch.mean(torch.square(x_mag.pow(0.3) - x_hat_mag.pow(0.3)))
+    losses_ri = torch.square(torch.norm(x_nc / x_mag.pow(0.7) - x_hat_nc / x_hat_mag.pow(0.7), p=2)) / (B * C * Fq * T)
+    x_hat_td = istft_torch(x_hat_nc.squeeze(1), cfg)                    # model.py:200 to_audio(x_hat.squeeze())
+    x_td = istft_torch(x_nc.squeeze(1), cfg)
+    x_td_norm = torch.sum(x_td * x_hat_td, dim=-1, keepdim=True) * x_td / (torch.sum(x_td.pow(2), dim=-1, keepdim=True) + 1e-12)
+    ratio = torch.sum(x_td_norm.pow(2), dim=-1, keepdim=True) / (torch.sum((x_hat_td - x_td_norm).pow(2), dim=-1, keepdim=True) + 1e-12)
+    sisnr = torch.log10(ratio.clamp(min=1e-12)).mean()
+    return 70 * losses_mag + 30 * losses_ri - sisnr
+
+
+def istft_torch(spec: Tensor, cfg: SpecConfig, length: Optional[int] = None) -> Tensor:
+    """data_module.py:227-229 through torch.istft itself (autograd-capable, any float width); `istft` above is the
+    explicit restatement, the two agree to rounding (tests/test_oracle_golden.py)."""
+    w = make_window(cfg.window, cfg.n_fft).to(device=spec.device, dtype=spec.real.dtype)
+    return torch.istft(spec, n_fft=cfg.n_fft, hop_length=cfg.hop_length, window=w, center=True, length=length)
 
 
 # ----------------------------------------------------------------------------------------------

@@ -42,6 +42,15 @@ def import_reference():
 
     stub("pytorch_lightning", LightningModule=_LM,
          LightningDataModule=type("LDM", (), {"__init__": lambda s: None}))
+    # fdbm.model additionally imports these (only BridgeModel._loss is used from it, as an unbound function)
+    stub("torch_ema", ExponentialMovingAverage=object)
+    stub("librosa", resample=None)
+    stub("soundfile", write=None)
+    stub("torch_pesq", PesqLoss=object)
+    try:
+        import torchaudio  # noqa: F401
+    except Exception:
+        stub("torchaudio", load=None)
     from fdbm.bridge import Bridge
     from fdbm.backbones import BackboneRegistry
     from fdbm.data_module import SpecsDataModule
@@ -56,6 +65,43 @@ def rel(a, b):
 
 def c2n(t):
     return t.detach().cpu().numpy()
+
+
+class reference_tf32_convs:
+    """Run the REFERENCE the way it runs on any Ampere-or-later GPU: cuDNN convolutions in TF32
+    (torch.backends.cudnn.allow_tf32 defaults to True), i.e. both operands of every nn.Conv2d rounded to a 10-bit
+    mantissa, fp32 accumulation; matmuls / einsum stay fp32 (allow_tf32 for matmul defaults to False).  On the CPU this
+    is emulated by rounding the operands (round-to-nearest-even, the most favourable reading of TF32) in front of
+    torch.nn.functional.conv2d.  The deviation of this run from the fp32 run is the yardstick for what a 16-bit-operand
+    implementation may deviate: tests/golden/ref_tf32_deviation.json."""
+
+    def __enter__(self):
+        import fdbm_oracle as O
+        import torch.nn.functional as F
+        self.F, self.orig = F, F.conv2d
+
+        def conv2d(x, w, *a, **k):
+            return self.orig(O.round_tf32(x), O.round_tf32(w), *a, **k)
+        F.conv2d = conv2d
+        return self
+
+    def __exit__(self, *a):
+        self.F.conv2d = self.orig
+
+
+class fixed_noise:
+    """torch.randn_like replaced by a fixed sequence of draws (the samplers call it once per prior / step)."""
+
+    def __init__(self, zs):
+        self.zs = zs
+
+    def __enter__(self):
+        seq = iter(self.zs)
+        self.orig = torch.randn_like
+        torch.randn_like = lambda x, **k: next(seq)
+
+    def __exit__(self, *a):
+        torch.randn_like = self.orig
 
 
 def main():
@@ -85,9 +131,11 @@ def main():
     print("pad_spec  oracle vs ref: equal", bool(torch.equal(Yp_or, Yp_ref)),
           bool(torch.equal(O.pad_spec(Y_or[None], 'zero_pad'), O.pad_spec(Y_ref[None], 'zero_pad'))))
     print("istft     oracle vs ref:", rel(wav_or, wav_ref), float((wav_or - wav_ref).abs().max()))
+    Yr_ref = ref_pad_spec(Y_ref[None], mode="replication")
+    assert torch.equal(O.pad_spec(Y_or[None], "replication"), Yr_ref)
     np.savez_compressed(os.path.join(OUT, "spectral_1s.npz"),
                         wave=c2n(y), stft=c2n(S_ref), spec=c2n(Y_ref), spec_reflect=c2n(Yp_ref),
-                        spec_zero=c2n(Yz_ref), wave_back=c2n(wav_ref))
+                        spec_zero=c2n(Yz_ref), spec_replicate=c2n(Yr_ref), wave_back=c2n(wav_ref))
 
     # ---- (2) coefficient tables --------------------------------------------------------------
     tables = {}
@@ -184,6 +232,101 @@ def main():
                 if st != "ode_ei" or path == "fm":
                     out[f"noise_{path}_{st}"] = c2n(torch.stack(zs))
             np.savez_compressed(os.path.join(OUT, "bridge_T64.npz"), **out)
+
+            # ---- (4b) the other schedules and step counts the reference offers, same weights / input ----------------
+            more = {}
+            f_ref = lambda a, b, c: net(a, b, c)
+            f_or = lambda a, b, c: O.ncsnpp_forward(sd, cfg, a, b, c)
+            zg = torch.Generator().manual_seed(13)
+            zs31 = [torch.view_as_complex(torch.randn(1, 1, 257, 64, 2, generator=zg)) * (0.5 ** 0.5) for _ in range(31)]
+            for tag, path, st, N, kw in (("sb_ve_ode_ei_N5", "sb", "ode_ei", 5, dict(noise_schedule="ve")),
+                                         ("sb_vp_ode_ei_N5", "sb", "ode_ei", 5, dict(noise_schedule="vp", c=0.3)),
+                                         ("sb_gmax_ode_ei_N5", "sb", "ode_ei", 5, dict(noise_schedule="gmax")),
+                                         ("sb_ve_sde_ei_N5", "sb", "sde_ei", 5, dict(noise_schedule="ve")),
+                                         ("sb_bb_ode_ei_N1", "sb", "ode_ei", 1, {}),
+                                         ("sb_bb_ode_ei_N10", "sb", "ode_ei", 10, {}),
+                                         ("sb_bb_ode_ei_N30", "sb", "ode_ei", 30, {})):
+                rb = Bridge(path, N=N, sampler_type=st, **kw)
+                ob = O.Bridge(path, N=N, sampler_type=st, **kw)
+                with fixed_noise(zs31):
+                    s_ref = rb.sampler(f_ref, Y)
+                s_or = ob.sampler(f_or, Y, z0=zs31[0], zs=zs31[1:])
+                print(f"{name} sampler {tag}: oracle vs ref spec rel {rel(s_or, s_ref):.3e}")
+                more["sample_" + tag] = c2n(s_ref)
+            more["noise"] = c2n(torch.stack(zs31[:6]))
+            np.savez_compressed(os.path.join(OUT, "bridge_T64_more.npz"), **more)
+
+            # ---- (4c) the reference in ITS OWN reduced precision (TF32 convolutions) vs its fp32 run -------------------
+            dev = {}
+            with reference_tf32_convs():
+                D_tf = net(xt, Y, t)
+            with O.operand_rounding("tf32"):
+                D_tf_or = O.ncsnpp_forward(sd, cfg, xt, Y, t)
+            dev["forward_T64"] = rel(D_tf, D_ref)
+            dev["forward_T64_oracle_emulation_vs_reference_emulation"] = rel(D_tf_or, D_tf)
+            for path, st in (("sb", "ode_ei"), ("sb", "sde_ei"), ("fm", "ode_ei")):
+                rb = Bridge(path, N=5, sampler_type=st)
+                with fixed_noise(zs):
+                    s32 = rb.sampler(f_ref, Y)
+                with fixed_noise(zs), reference_tf32_convs():
+                    stf = rb.sampler(f_ref, Y)
+                dev[f"sampler_{path}_{st}_N5_T64"] = rel(stf, s32)
+            # the other schedules / step counts of (4b), same inputs and noise draws
+            for tag, path, st, N, kw in (("sb_ve_ode_ei_N5", "sb", "ode_ei", 5, dict(noise_schedule="ve")),
+                                         ("sb_vp_ode_ei_N5", "sb", "ode_ei", 5, dict(noise_schedule="vp", c=0.3)),
+                                         ("sb_gmax_ode_ei_N5", "sb", "ode_ei", 5, dict(noise_schedule="gmax")),
+                                         ("sb_ve_sde_ei_N5", "sb", "sde_ei", 5, dict(noise_schedule="ve")),
+                                         ("sb_bb_ode_ei_N1", "sb", "ode_ei", 1, {}),
+                                         ("sb_bb_ode_ei_N10", "sb", "ode_ei", 10, {}),
+                                         ("sb_bb_ode_ei_N30", "sb", "ode_ei", 30, {})):
+                rb = Bridge(path, N=N, sampler_type=st, **kw)
+                with fixed_noise(zs31), reference_tf32_convs():
+                    stf = rb.sampler(f_ref, Y)
+                dev[f"sampler_{tag}_T64"] = rel(stf, torch.from_numpy(more["sample_" + tag]))
+            # BASELINE's own size: 4 s = 256 frames (utterance 0 of the synthetic set, reflection padding), default sampler and
+            # the step sweep of configs[4]
+            _, noisy4 = O.synth_pair(0)
+            Y4 = ref_pad_spec(dm.spec_fwd(dm.stft((noisy4 / noisy4.abs().max())[None]))[None], mode="reflection")
+            assert Y4.shape == (1, 1, 257, 256)
+            for N in (5, 1, 10, 30):
+                rb = Bridge("sb", N=N, sampler_type="ode_ei")
+                s32 = rb.sampler(f_ref, Y4)
+                with reference_tf32_convs():
+                    stf = rb.sampler(f_ref, Y4)
+                dev[f"sampler_sb_ode_ei_N{N}_T256"] = rel(stf, s32)
+                print(f"  4 s, N={N}: reference TF32 vs fp32 {dev[f'sampler_sb_ode_ei_N{N}_T256']:.3e}", flush=True)
+            import json
+            dev["what"] = ("relative L2 deviation of the reference run with TF32 convolutions (its default GPU precision; emulated on the CPU "
+                           "by rounding both operands of every nn.Conv2d to 10 mantissa bits, RNE) from the same reference run in fp32; "
+                           "sensitised weights seed 0, inputs of bridge_T64.npz")
+            with open(os.path.join(OUT, "ref_tf32_deviation.json"), "w") as fjs:
+                json.dump(dev, fjs, indent=1)
+            print("reference TF32-vs-fp32 deviations:", {k: (f"{v:.3e}" if isinstance(v, float) else "") for k, v in dev.items()})
+    # ---- (5) the training loss head: BridgeModel._loss 'data_prediction_hybrid' (model.py:187-218) and its gradient ----
+    import types as _types
+    import fdbm.model as ref_model
+    gl = torch.Generator().manual_seed(21)
+
+    def spec(B=2, T=64):
+        mag = torch.rand(B, 1, 257, T, generator=gl) ** 3 * 0.6
+        ph = 2 * 3.14159265 * torch.rand(B, 1, 257, T, generator=gl)
+        return torch.polar(mag, ph)
+    x = spec()
+    x_hat = x + 0.3 * spec()
+    x_hat[:, :, 256] = 0
+    fake_self = _types.SimpleNamespace(loss_type="data_prediction_hybrid", pesq_weight=0.0, data_module=dm,
+                                       _backward_transform=dm.spec_back,
+                                       to_audio=lambda s, length=None: dm.istft(dm.spec_back(s), length))
+    leaf = x_hat.clone().requires_grad_(True)
+    loss_ref = ref_model.BridgeModel._loss(fake_self, leaf, None, None, None, None, x)
+    (g_ref,) = torch.autograd.grad(loss_ref, leaf)
+    leaf2 = x_hat.clone().requires_grad_(True)
+    loss_or = O.hybrid_loss(leaf2, x, scfg)
+    (g_or,) = torch.autograd.grad(loss_or, leaf2)
+    g_ref = torch.nan_to_num(g_ref); g_or = torch.nan_to_num(g_or)          # d angle / d z at the exact zeros of row 256
+    print(f"hybrid loss reference {float(loss_ref):.6f} oracle {float(loss_or):.6f}; gradient oracle vs ref {rel(g_or, g_ref):.3e}")
+    np.savez_compressed(os.path.join(OUT, "hybrid_loss.npz"), x=c2n(x), x_hat=c2n(x_hat), loss=np.float64(loss_ref.item()),
+                        grad=c2n(g_ref))
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")

@@ -41,6 +41,11 @@ int require_sm100() {
   return FDBM_OK;
 }
 
+int current_device() {
+  int dev = -1;
+  return cudaGetDevice(&dev) == cudaSuccess ? dev : -1;
+}
+
 int num_sms() {
   int dev = 0;
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;

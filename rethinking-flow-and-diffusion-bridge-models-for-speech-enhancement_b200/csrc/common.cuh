@@ -37,6 +37,15 @@ static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStre
 
 int require_sm100();   // FDBM_OK or FDBM_EARCH (cached per device)
 int num_sms();
+int current_device();  // cudaGetDevice, -1 on failure
+
+// "done once per device" flag for cudaFuncSetAttribute opt-ins: function attributes are per device, so a process that
+// drives several GPUs (infer_folder.py:70-74 spawns workers with .to(f'cuda:{gpu_id}')) must set them on each one.
+struct PerDeviceOnce {
+  bool done[64] = {};
+  // true exactly once per device index (races between host threads only repeat the idempotent attribute call)
+  bool first(int dev) { if (dev < 0 || dev >= 64) return true; if (done[dev]) return false; done[dev] = true; return true; }
+};
 
 __host__ __device__ constexpr int ceil_div(int a, int b) { return (a + b - 1) / b; }
 __host__ __device__ constexpr int64_t ceil_div64(int64_t a, int64_t b) { return (a + b - 1) / b; }
@@ -156,7 +165,7 @@ int launch_col_sums_to(const double* sums, int B, int C, float inv_scale, float*
 int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, float* scratch, op_t* g_qkv, cudaStream_t s);
 int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const unsigned char* trainable, int64_t n,
                     double* sumsq_scratch, float grad_div, float clip, float lr, float beta1, float beta2, float eps, int step,
-                    float ema_decay, cudaStream_t s);
+                    float ema_decay, int ema_warmup, double* state, cudaStream_t s);
 struct WgradCall {
   const op_t* dy = nullptr; int dy_ld = 0, dy_coff = 0, Cout = 0;
   const op_t* x = nullptr; int x_ld = 0, x_coff = 0, Cin = 0;

@@ -883,12 +883,11 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   FDBM_REQUIRE(a.out_f32 || a.out_h16 || a.pyr_out, "conv_igemm: no output");
   FDBM_REQUIRE(!a.pyr_out || (a.pyr_C >= 1 && a.pyr_C <= 4 && a.Cout == bn && !a.sums), "conv_igemm: bad pyramid epilogue arguments");
   FDBM_REQUIRE(!a.pyr_prev || (a.T % 2 == 0 && a.F % 2 == 0), "conv_igemm: pyramid level with odd size");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first(current_device())) {
     FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
     FDBM_CUDA(cudaFuncSetAttribute(conv_igemm_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
   }
   FDBM_REQUIRE(!a.comb_pyr || (a.comb_w && a.comb_b && a.comb_C >= 1 && a.comb_C <= 4 && !a.pyr_out), "conv_igemm: bad Combine epilogue arguments");
   CUtensorMap map_a[MAX_SEG], map_b;

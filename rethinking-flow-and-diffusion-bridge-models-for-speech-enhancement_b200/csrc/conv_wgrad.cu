@@ -213,11 +213,9 @@ int launch_conv_wgrad_ex(const WgradCall& c, cudaStream_t s) {
   FDBM_REQUIRE(c.ksize == 1 || c.ksize == 3, "conv_wgrad: ksize must be 1 or 3");
   FDBM_REQUIRE(c.layout == 0 || c.ksize == 1, "conv_wgrad: layouts 1..3 are for 1x1 only");
   FDBM_REQUIRE(c.dy_coff % 64 == 0 && c.x_coff % 64 == 0, "conv_wgrad: channel offsets must be multiples of 64");
-  static bool attr_set = false;
-  if (!attr_set) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first(current_device()))
     FDBM_CUDA(cudaFuncSetAttribute(conv_wgrad_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_BYTES));
-    attr_set = true;
-  }
   WgradParams p;
   p.B = c.B; p.T = c.T; p.F = c.F; p.Cout = c.Cout; p.Cin = c.Cin; p.taps = c.ksize * c.ksize;
   p.n_cin = c.Cin % 128 == 0 ? 128 : 64;

@@ -123,13 +123,40 @@ struct fdbm_plan {
   const float* cur_gout = nullptr;     // dL/dD of the current backward call (loss-scaled), cplx [B,1,257,T]
   float cur_inv = 1.0f;                // 1 / loss scale
   float* adam_m = nullptr; float* adam_v = nullptr; float* ema = nullptr; double* opt_scratch = nullptr;
+  double* opt_state = nullptr;         // {applied updates, skipped steps, last gradient norm, reserved}
+  float* ema_backup = nullptr;         // live parameters parked here while the EMA is swapped in
+  bool ema_swapped = false;
   int n_bwd_launches = 0;
+  int device = 0;                      // the device the plan's memory lives on; every entry point checks it is current
+  // sampler staging (bridge inference plans, allocated by fdbm_plan_create): the captured graph reads these fixed buffers
+  static constexpr int kMaxSteps = 1024;
+  static constexpr int kRing = 8;
+  float* smp_y = nullptr; float* smp_x = nullptr; float* smp_times = nullptr; float* smp_coef = nullptr; uint64_t* smp_rng = nullptr;
+  uint8_t* smp_pinned = nullptr;       // kRing host slots of {seed[2], times[kMaxSteps], coef[3 kMaxSteps]}
+  cudaEvent_t smp_ev[kRing] = {};
+  int smp_pos = 0;
+  std::vector<float> smp_h_times, smp_h_coef;
   // graph cache
   bool have_graph = false; GraphKey graph_key{}; cudaGraphExec_t graph_exec = nullptr;
   cudaStream_t capture_stream = nullptr;   // private stream: capture works even when the caller is on the legacy stream
+  int64_t extra_bytes = 0;             // device memory outside the arena / params / packs (staging, optimiser, gradients)
 };
 
-void fdbm_plan_release_sampler_state(fdbm_plan* plan);
+namespace {
+constexpr size_t kSlotBytes = 16 + sizeof(float) * 4 * fdbm_plan::kMaxSteps;
+
+// every plan entry point: the plan's device must be the calling thread's current device (allocations, launches and the
+// caller's stream all refer to the current device; a mismatch would fault on foreign pointers)
+int plan_guard(const fdbm_plan* plan, const char* who) {
+  if (!plan) { set_error("%s: null plan", who); return FDBM_EINVAL; }
+  const int dev = current_device();
+  if (dev != plan->device) {
+    set_error("%s: the plan lives on device %d but the current device is %d (select the tensors' device first)", who, plan->device, dev);
+    return FDBM_ESTATE;
+  }
+  return FDBM_OK;
+}
+}  // namespace
 
 namespace {
 
@@ -873,6 +900,7 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   P->arch = *arch; P->B = batch; P->T = n_frames; P->F = arch->image_size; P->F_io = arch->image_size + 1;
   P->Cin = arch->predictive ? 2 : 4;
   P->train = train;
+  P->device = current_device();
   P->mods = build_modules(*arch);
   auto fail = [&](int rc) { fdbm_plan_destroy(P); return rc; };
 
@@ -897,11 +925,35 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   if ((e = cudaMalloc(&P->wpacked, P->wpacked_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wpacked)", __FILE__, __LINE__));
   if ((e = cudaMalloc(&P->d_buf, spec_elems * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(d_buf)", __FILE__, __LINE__));
   if ((e = cudaMemset(P->params, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+  P->extra_bytes = spec_elems * sizeof(float);
   if (train) {
     if ((e = cudaMalloc(&P->grads, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(grads)", __FILE__, __LINE__));
     if ((e = cudaMalloc(&P->wpacked_d, std::max<int64_t>(P->wpacked_d_bytes, 1024))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wpacked_d)", __FILE__, __LINE__));
     if ((e = cudaMalloc(&P->wgrad_ws, std::max<int64_t>(P->wgrad_ws_bytes, 1024))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wgrad_ws)", __FILE__, __LINE__));
     if ((e = cudaMemset(P->grads, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+    // optimiser state: Adam moments, EMA shadow + the backup the evaluation swap parks the live parameters in
+    float** bufs[4] = {&P->adam_m, &P->adam_v, &P->ema, &P->ema_backup};
+    for (float** b : bufs) {
+      if ((e = cudaMalloc(b, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(optimiser)", __FILE__, __LINE__));
+      if ((e = cudaMemset(*b, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+    }
+    if ((e = cudaMalloc(&P->opt_scratch, 1025 * sizeof(double))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(opt_scratch)", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->opt_state, 4 * sizeof(double))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(opt_state)", __FILE__, __LINE__));
+    if ((e = cudaMemset(P->opt_state, 0, 4 * sizeof(double))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
+    P->extra_bytes += params_numel * 4 * 5 + std::max<int64_t>(P->wpacked_d_bytes, 1024) + std::max<int64_t>(P->wgrad_ws_bytes, 1024);
+  } else if (!arch->predictive) {
+    // sampler staging: the graph of the N-step loop reads y / x / times / coefficients / seed from these fixed buffers
+    const size_t spec_bytes = spec_elems * sizeof(float);
+    if ((e = cudaMalloc(&P->smp_y, spec_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(sampler y)", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->smp_x, spec_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(sampler x)", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->smp_times, sizeof(float) * fdbm_plan::kMaxSteps)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->smp_coef, sizeof(float) * 3 * fdbm_plan::kMaxSteps)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
+    if ((e = cudaMalloc(&P->smp_rng, 2 * sizeof(uint64_t))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc", __FILE__, __LINE__));
+    if ((e = cudaMallocHost(&P->smp_pinned, kSlotBytes * fdbm_plan::kRing)) != cudaSuccess) return fail(cuda_fail(e, "cudaMallocHost", __FILE__, __LINE__));
+    for (int i = 0; i < fdbm_plan::kRing; ++i)
+      if ((e = cudaEventCreateWithFlags(&P->smp_ev[i], cudaEventDisableTiming)) != cudaSuccess) return fail(cuda_fail(e, "cudaEventCreate", __FILE__, __LINE__));
+    if ((e = cudaStreamCreateWithFlags(&P->capture_stream, cudaStreamNonBlocking)) != cudaSuccess) return fail(cuda_fail(e, "cudaStreamCreate", __FILE__, __LINE__));
+    P->extra_bytes += 2 * spec_bytes + sizeof(float) * 4 * fdbm_plan::kMaxSteps + 16;
   }
 
   // pass 2: identical walk, now recording launches against real addresses
@@ -932,6 +984,7 @@ extern "C" int fdbm_plan_create_train(const fdbm_arch* arch, int batch, int n_fr
 // dL/dparams of the last fdbm_ncsnpp_forward on a training plan.  g_out = loss_scale * dL/dD, cplx [B,1,257,T].
 extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float loss_scale, int accumulate, void* stream) {
   FDBM_REQUIRE(plan && g_out && loss_scale > 0.f, "fdbm_ncsnpp_backward: bad arguments");
+  if (int rc = plan_guard(plan, "fdbm_ncsnpp_backward")) return rc;
   if (!plan->train) { set_error("fdbm_ncsnpp_backward: not a training plan (use fdbm_plan_create_train)"); return FDBM_ESTATE; }
   if (!plan->weights_ready || !plan->cur_x) { set_error("fdbm_ncsnpp_backward: no forward pass to differentiate"); return FDBM_ESTATE; }
   cudaStream_t s = as_stream(stream);
@@ -946,6 +999,7 @@ extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float l
 extern "C" int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, float loss_scale, float* ms, int* kinds, int max_ops,
                                           void* stream) {
   FDBM_REQUIRE(plan && g_out && ms && kinds && plan->train, "fdbm_plan_profile_backward: bad arguments");
+  if (int rc = plan_guard(plan, "fdbm_plan_profile_backward")) return rc;
   const int n = static_cast<int>(plan->bwd_ops.size());
   FDBM_REQUIRE(max_ops >= n, "fdbm_plan_profile_backward: need room for %d entries", n);
   cudaStream_t s = as_stream(stream);
@@ -987,7 +1041,7 @@ extern "C" int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads,
 // re-derive the packed 16-bit weights (forward and dgrad packs) from the flat fp32 parameter buffer, e.g. after the caller
 // has written it directly (DDP parameter broadcast from rank 0, checkpoint restore)
 extern "C" int fdbm_plan_repack_weights(fdbm_plan* plan, void* stream) {
-  FDBM_REQUIRE(plan, "fdbm_plan_repack_weights: null plan");
+  if (int rc = plan_guard(plan, "fdbm_plan_repack_weights")) return rc;
   if (!plan->weights_ready) { set_error("fdbm_plan_repack_weights: weights not loaded"); return FDBM_ESTATE; }
   for (auto& f : plan->pack_ops) if (int rc = f(as_stream(stream))) return rc;
   return FDBM_OK;
@@ -997,41 +1051,94 @@ extern "C" int fdbm_plan_num_backward_launches(const fdbm_plan* plan) { return p
 
 // Adam + clip + EMA on the flat buffers, then the packed 16-bit weights are rebuilt from the updated parameters.
 extern "C" int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float clip_norm, float lr, float beta1, float beta2,
-                                        float eps, int step, float ema_decay, void* stream) {
-  FDBM_REQUIRE(plan && step >= 1 && grad_div > 0.f, "fdbm_plan_optimizer_step: bad arguments");
+                                        float eps, int step, float ema_decay, int ema_warmup, void* stream) {
+  FDBM_REQUIRE(plan && step >= 0 && grad_div > 0.f, "fdbm_plan_optimizer_step: bad arguments");
+  if (int rc = plan_guard(plan, "fdbm_plan_optimizer_step")) return rc;
   if (!plan->train) { set_error("fdbm_plan_optimizer_step: not a training plan"); return FDBM_ESTATE; }
+  if (plan->ema_swapped) { set_error("fdbm_plan_optimizer_step: the EMA weights are swapped in (restore them first)"); return FDBM_ESTATE; }
   cudaStream_t s = as_stream(stream);
   const int64_t n = plan->params_numel;
-  if (!plan->adam_m) {
-    FDBM_CUDA(cudaMalloc(&plan->adam_m, n * sizeof(float)));
-    FDBM_CUDA(cudaMalloc(&plan->adam_v, n * sizeof(float)));
-    FDBM_CUDA(cudaMalloc(&plan->ema, n * sizeof(float)));
-    FDBM_CUDA(cudaMalloc(&plan->opt_scratch, 1025 * sizeof(double)));
-    FDBM_CUDA(cudaMemsetAsync(plan->adam_m, 0, n * sizeof(float), s));
-    FDBM_CUDA(cudaMemsetAsync(plan->adam_v, 0, n * sizeof(float), s));
-    FDBM_CUDA(cudaMemcpyAsync(plan->ema, plan->params, n * sizeof(float), cudaMemcpyDeviceToDevice, s));
-  }
   if (int rc = launch_adam_ema(plan->params, plan->grads, plan->adam_m, plan->adam_v, plan->ema, nullptr, n, plan->opt_scratch, grad_div,
-                               clip_norm, lr, beta1, beta2, eps, step, ema_decay, s))
+                               clip_norm, lr, beta1, beta2, eps, step, ema_decay, ema_warmup, plan->opt_state, s))
     return rc;
+  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_reset_optimizer(fdbm_plan* plan, void* stream) {
+  if (int rc = plan_guard(plan, "fdbm_plan_reset_optimizer")) return rc;
+  if (!plan->train) { set_error("fdbm_plan_reset_optimizer: not a training plan"); return FDBM_ESTATE; }
+  cudaStream_t s = as_stream(stream);
+  const size_t bytes = plan->params_numel * sizeof(float);
+  FDBM_CUDA(cudaMemsetAsync(plan->adam_m, 0, bytes, s));
+  FDBM_CUDA(cudaMemsetAsync(plan->adam_v, 0, bytes, s));
+  FDBM_CUDA(cudaMemcpyAsync(plan->ema, plan->params, bytes, cudaMemcpyDeviceToDevice, s));
+  FDBM_CUDA(cudaMemsetAsync(plan->opt_state, 0, 4 * sizeof(double), s));
+  plan->ema_swapped = false;
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_optimizer_state(fdbm_plan* plan, double* out, void* stream) {
+  FDBM_REQUIRE(out, "fdbm_plan_optimizer_state: null output");
+  if (int rc = plan_guard(plan, "fdbm_plan_optimizer_state")) return rc;
+  if (!plan->train) { set_error("fdbm_plan_optimizer_state: not a training plan"); return FDBM_ESTATE; }
+  cudaStream_t s = as_stream(stream);
+  FDBM_CUDA(cudaMemcpyAsync(out, plan->opt_state, 4 * sizeof(double), cudaMemcpyDeviceToHost, s));
+  FDBM_CUDA(cudaStreamSynchronize(s));
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_set_optimizer_state(fdbm_plan* plan, double applied, double skipped, void* stream) {
+  if (int rc = plan_guard(plan, "fdbm_plan_set_optimizer_state")) return rc;
+  if (!plan->train) { set_error("fdbm_plan_set_optimizer_state: not a training plan"); return FDBM_ESTATE; }
+  const double h[4] = {applied, skipped, 0.0, 0.0};
+  cudaStream_t s = as_stream(stream);
+  FDBM_CUDA(cudaMemcpyAsync(plan->opt_state, h, sizeof(h), cudaMemcpyHostToDevice, s));
+  FDBM_CUDA(cudaStreamSynchronize(s));                   // `h` is a stack array
+  return FDBM_OK;
+}
+
+extern "C" int fdbm_plan_swap_ema(fdbm_plan* plan, int to_ema, void* stream) {
+  if (int rc = plan_guard(plan, "fdbm_plan_swap_ema")) return rc;
+  if (!plan->train) { set_error("fdbm_plan_swap_ema: not a training plan"); return FDBM_ESTATE; }
+  cudaStream_t s = as_stream(stream);
+  const size_t bytes = plan->params_numel * sizeof(float);
+  if (to_ema) {
+    if (plan->ema_swapped) { set_error("fdbm_plan_swap_ema: the EMA weights are already swapped in"); return FDBM_ESTATE; }
+    FDBM_CUDA(cudaMemcpyAsync(plan->ema_backup, plan->params, bytes, cudaMemcpyDeviceToDevice, s));
+    FDBM_CUDA(cudaMemcpyAsync(plan->params, plan->ema, bytes, cudaMemcpyDeviceToDevice, s));
+    plan->ema_swapped = true;
+  } else {
+    if (!plan->ema_swapped) { set_error("fdbm_plan_swap_ema: nothing to restore"); return FDBM_ESTATE; }
+    FDBM_CUDA(cudaMemcpyAsync(plan->params, plan->ema_backup, bytes, cudaMemcpyDeviceToDevice, s));
+    plan->ema_swapped = false;
+  }
   for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
 }
 
 extern "C" int fdbm_plan_destroy(fdbm_plan* plan) {
   if (!plan) return FDBM_OK;
+  int prev = -1;
+  cudaGetDevice(&prev);
+  if (prev != plan->device) cudaSetDevice(plan->device);          // frees and destroys must run on the owning device
   if (plan->graph_exec) cudaGraphExecDestroy(plan->graph_exec);
   if (plan->capture_stream) cudaStreamDestroy(plan->capture_stream);
-  fdbm_plan_release_sampler_state(plan);
+  for (auto& ev : plan->smp_ev) if (ev) cudaEventDestroy(ev);
+  cudaFree(plan->smp_y); cudaFree(plan->smp_x); cudaFree(plan->smp_times); cudaFree(plan->smp_coef); cudaFree(plan->smp_rng);
+  if (plan->smp_pinned) cudaFreeHost(plan->smp_pinned);
   cudaFree(plan->arena); cudaFree(plan->params); cudaFree(plan->wpacked); cudaFree(plan->d_buf);
   cudaFree(plan->grads); cudaFree(plan->wpacked_d); cudaFree(plan->wgrad_ws);
   cudaFree(plan->adam_m); cudaFree(plan->adam_v); cudaFree(plan->ema); cudaFree(plan->opt_scratch);
+  cudaFree(plan->opt_state); cudaFree(plan->ema_backup);
+  if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   delete plan;
   return FDBM_OK;
 }
 
 extern "C" int fdbm_plan_load_weights(fdbm_plan* plan, const fdbm_tensor_ref* tensors, int n_tensors, void* stream) {
   FDBM_REQUIRE(plan && tensors && n_tensors > 0, "fdbm_plan_load_weights: bad arguments");
+  if (int rc = plan_guard(plan, "fdbm_plan_load_weights")) return rc;
   cudaStream_t s = as_stream(stream);
   for (int i = 0; i < n_tensors; ++i) {
     FDBM_REQUIRE(tensors[i].name && tensors[i].data, "fdbm_plan_load_weights: tensor %d has a null field", i);
@@ -1052,8 +1159,7 @@ extern "C" int fdbm_plan_load_weights(fdbm_plan* plan, const fdbm_tensor_ref* te
 
 extern "C" int64_t fdbm_plan_device_bytes(const fdbm_plan* plan) {
   if (!plan) return 0;
-  return plan->arena_bytes + plan->params_numel * 4 + plan->wpacked_bytes +
-         static_cast<int64_t>(plan->B) * plan->F_io * plan->T * 8;
+  return plan->arena_bytes + plan->params_numel * 4 + plan->wpacked_bytes + plan->extra_bytes;
 }
 
 extern "C" int fdbm_plan_num_launches(const fdbm_plan* plan) { return plan ? plan->n_launches : 0; }
@@ -1061,6 +1167,7 @@ extern "C" int fdbm_plan_num_launches(const fdbm_plan* plan) { return plan ? pla
 extern "C" int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
                                    void* stream) {
   FDBM_REQUIRE(plan && x && out, "fdbm_ncsnpp_forward: null pointer");
+  if (int rc = plan_guard(plan, "fdbm_ncsnpp_forward")) return rc;
   if (!plan->weights_ready) { set_error("fdbm_ncsnpp_forward: weights not loaded"); return FDBM_ESTATE; }
   FDBM_REQUIRE(plan->arch.predictive || (y && t), "fdbm_ncsnpp_forward: y and t are required");
   plan->cur_x = x; plan->cur_y = y; plan->cur_t = t; plan->cur_t_stride = 1; plan->cur_out = out;
@@ -1070,6 +1177,7 @@ extern "C" int fdbm_ncsnpp_forward(fdbm_plan* plan, const float* x, const float*
 extern "C" int fdbm_plan_profile_forward(fdbm_plan* plan, const float* x, const float* y, const float* t, float* out,
                                          float* ms, int* kinds, double* flops, int max_ops, void* stream) {
   FDBM_REQUIRE(plan && x && out && ms && kinds && flops, "fdbm_plan_profile_forward: null pointer");
+  if (int rc = plan_guard(plan, "fdbm_plan_profile_forward")) return rc;
   if (!plan->weights_ready) { set_error("fdbm_plan_profile_forward: weights not loaded"); return FDBM_ESTATE; }
   FDBM_REQUIRE(plan->arch.predictive || (y && t), "fdbm_plan_profile_forward: y and t are required");
   const int n = static_cast<int>(plan->ops.size());
@@ -1094,106 +1202,80 @@ extern "C" int fdbm_plan_profile_forward(fdbm_plan* plan, const float* x, const 
   return rc == FDBM_OK ? n : rc;
 }
 
-namespace {
-
-struct SamplerState {               // plan-owned staging so that one captured graph serves every call
-  float* y = nullptr; float* x = nullptr; float* noise = nullptr; int64_t noise_elems = 0;
-  float* times = nullptr; float* coef = nullptr; uint64_t* rng = nullptr; int cap_steps = 0;
-  std::vector<float> h_times, h_coef;
-};
-std::map<fdbm_plan*, SamplerState>& sampler_states() { static std::map<fdbm_plan*, SamplerState> m; return m; }
-
-}  // namespace
-
 namespace fdbm { int launch_bridge_step_rng(float* x, const float* d, const float* third, const float* coef, int kind,
                                             const uint64_t* rng, uint64_t offset, int64_t n_complex, cudaStream_t s); }
 
+// The N-step loop (fdbm/bridge.py:66-113).  All device memory it needs was allocated by fdbm_plan_create (staging copies
+// of y and x, the per-step time / coefficient tables, the Philox seed) and the per-call host arguments travel through a
+// plan-owned ring of pinned slots, so this call never allocates and never synchronises in the steady state (it waits on
+// a slot's event only if the caller is kRing un-finished calls ahead).  The captured graph reads nothing but plan-owned
+// buffers and, for SDE runs with caller-provided noise, the caller's `noise` tensor: a different `noise` address
+// re-captures the graph.  A plan serves one host thread at a time.
 extern "C" int fdbm_sampler_run(fdbm_plan* plan, const float* y, float* x, const float* times, const float* coef,
                                 int n_steps, int kind, const float* noise, uint64_t seed, void* stream) {
   FDBM_REQUIRE(plan && y && x && times && coef && n_steps > 0, "fdbm_sampler_run: bad arguments");
-  FDBM_REQUIRE(!plan->arch.predictive, "fdbm_sampler_run: predictive plans have no sampling loop");
+  if (int rc = plan_guard(plan, "fdbm_sampler_run")) return rc;
+  FDBM_REQUIRE(!plan->arch.predictive && !plan->train, "fdbm_sampler_run: needs a bridge inference plan (fdbm_plan_create, predictive = 0)");
   FDBM_REQUIRE(kind == FDBM_STEP_ODE || kind == FDBM_STEP_SDE, "fdbm_sampler_run: bad kind");
+  FDBM_REQUIRE(n_steps <= fdbm_plan::kMaxSteps, "fdbm_sampler_run: at most %d steps (got %d)", fdbm_plan::kMaxSteps, n_steps);
   if (!plan->weights_ready) { set_error("fdbm_sampler_run: weights not loaded"); return FDBM_ESTATE; }
   cudaStream_t s = as_stream(stream);
-  const int64_t n_complex = static_cast<int64_t>(plan->B) * plan->F_io * plan->T;
-  const size_t spec_bytes = static_cast<size_t>(n_complex) * 8;
-  SamplerState& st = sampler_states()[plan];
-  if (!st.y) {
-    FDBM_CUDA(cudaMalloc(&st.y, spec_bytes));
-    FDBM_CUDA(cudaMalloc(&st.x, spec_bytes));
-    FDBM_CUDA(cudaMalloc(&st.rng, 2 * sizeof(uint64_t)));
-  }
-  if (st.cap_steps < n_steps) {
-    cudaFree(st.times); cudaFree(st.coef);
-    FDBM_CUDA(cudaMalloc(&st.times, sizeof(float) * n_steps));
-    FDBM_CUDA(cudaMalloc(&st.coef, sizeof(float) * 3 * n_steps));
-    st.cap_steps = n_steps;
-    st.h_times.clear();
-  }
-  const bool want_noise = kind == FDBM_STEP_SDE && noise != nullptr;
-  if (want_noise && st.noise_elems < 2 * n_complex * n_steps) {
-    cudaFree(st.noise);
-    FDBM_CUDA(cudaMalloc(&st.noise, spec_bytes * n_steps));
-    st.noise_elems = 2 * n_complex * n_steps;
-    plan->have_graph = false;
-  }
-  // stage the call's arguments into the plan-owned buffers (all stream-ordered)
-  FDBM_CUDA(cudaMemcpyAsync(st.y, y, spec_bytes, cudaMemcpyDeviceToDevice, s));
-  FDBM_CUDA(cudaMemcpyAsync(st.x, x, spec_bytes, cudaMemcpyDeviceToDevice, s));
-  if (want_noise) FDBM_CUDA(cudaMemcpyAsync(st.noise, noise, spec_bytes * n_steps, cudaMemcpyDeviceToDevice, s));
-  const std::vector<float> ht(times, times + n_steps), hc(coef, coef + 3 * n_steps);
-  if (ht != st.h_times || hc != st.h_coef) {
-    FDBM_CUDA(cudaMemcpyAsync(st.times, times, sizeof(float) * n_steps, cudaMemcpyHostToDevice, s));
-    FDBM_CUDA(cudaMemcpyAsync(st.coef, coef, sizeof(float) * 3 * n_steps, cudaMemcpyHostToDevice, s));
-    FDBM_CUDA(cudaStreamSynchronize(s));                 // the host arrays may be temporaries of the caller
-    st.h_times = ht; st.h_coef = hc;
-  }
-  const uint64_t rng_host[2] = {seed, 0};
-  FDBM_CUDA(cudaMemcpyAsync(st.rng, rng_host, sizeof(rng_host), cudaMemcpyHostToDevice, s));
-
-  auto body = [&](cudaStream_t cs) -> int {
-    for (int i = 0; i < n_steps; ++i) {
-      plan->cur_x = st.x; plan->cur_y = st.y; plan->cur_t = st.times + i; plan->cur_t_stride = 0; plan->cur_out = plan->d_buf;
-      if (int rc = run_ops(plan, cs)) return rc;
-      const float* third = kind == FDBM_STEP_ODE ? st.y : (want_noise ? st.noise + 2 * n_complex * i : nullptr);
-      if (int rc = launch_bridge_step_rng(st.x, plan->d_buf, third, st.coef + 3 * i, kind, st.rng,
-                                          static_cast<uint64_t>(i) + 1, n_complex, cs))
-        return rc;
-    }
-    return FDBM_OK;
-  };
   cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
   FDBM_CUDA(cudaStreamIsCapturing(s, &cap));
-  if (cap != cudaStreamCaptureStatusNone) {                       // caller is capturing: record into its graph
-    if (int rc = body(s)) return rc;
-  } else {
-    GraphKey key{{st.y, st.x, st.times, st.coef, want_noise ? st.noise : nullptr, nullptr}, n_steps, kind, 0};
-    if (!(plan->have_graph && plan->graph_key == key)) {
-      if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; plan->have_graph = false; }
-      cudaGraph_t graph = nullptr;
-      if (!plan->capture_stream) FDBM_CUDA(cudaStreamCreateWithFlags(&plan->capture_stream, cudaStreamNonBlocking));
-      cudaStream_t cs = plan->capture_stream;
-      FDBM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
-      const int rc = body(cs);
-      const cudaError_t e = cudaStreamEndCapture(cs, &graph);
-      if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
-      if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
-      const cudaError_t e2 = cudaGraphInstantiate(&plan->graph_exec, graph, 0);
-      cudaGraphDestroy(graph);
-      if (e2 != cudaSuccess) return cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
-      plan->graph_key = key; plan->have_graph = true;
-    }
-    FDBM_CUDA(cudaGraphLaunch(plan->graph_exec, s));
+  if (cap != cudaStreamCaptureStatusNone) {
+    set_error("fdbm_sampler_run: `stream` is being captured; the sampler owns its CUDA graph and stages host arguments, call it outside a capture");
+    return FDBM_ESTATE;
   }
-  FDBM_CUDA(cudaMemcpyAsync(x, st.x, spec_bytes, cudaMemcpyDeviceToDevice, s));
-  return FDBM_OK;
-}
+  const int64_t n_complex = static_cast<int64_t>(plan->B) * plan->F_io * plan->T;
+  const size_t spec_bytes = static_cast<size_t>(n_complex) * 8;
+  const bool want_noise = kind == FDBM_STEP_SDE && noise != nullptr;
 
-void fdbm_plan_release_sampler_state(fdbm_plan* plan) {
-  auto& m = sampler_states();
-  auto it = m.find(plan);
-  if (it == m.end()) return;
-  SamplerState& st = it->second;
-  cudaFree(st.y); cudaFree(st.x); cudaFree(st.noise); cudaFree(st.times); cudaFree(st.coef); cudaFree(st.rng);
-  m.erase(it);
+  // host arguments -> next pinned slot -> device tables (stream-ordered; the slot is reused kRing calls later)
+  const int slot = plan->smp_pos;
+  plan->smp_pos = (slot + 1) % fdbm_plan::kRing;
+  FDBM_CUDA(cudaEventSynchronize(plan->smp_ev[slot]));
+  uint8_t* hs = plan->smp_pinned + kSlotBytes * slot;
+  uint64_t* h_rng = reinterpret_cast<uint64_t*>(hs);
+  float* h_times = reinterpret_cast<float*>(hs + 16);
+  float* h_coef = h_times + fdbm_plan::kMaxSteps;
+  h_rng[0] = seed; h_rng[1] = 0;
+  FDBM_CUDA(cudaMemcpyAsync(plan->smp_rng, h_rng, 16, cudaMemcpyHostToDevice, s));
+  const std::vector<float> ht(times, times + n_steps), hc(coef, coef + 3 * n_steps);
+  if (ht != plan->smp_h_times || hc != plan->smp_h_coef) {
+    std::copy(ht.begin(), ht.end(), h_times);
+    std::copy(hc.begin(), hc.end(), h_coef);
+    FDBM_CUDA(cudaMemcpyAsync(plan->smp_times, h_times, sizeof(float) * n_steps, cudaMemcpyHostToDevice, s));
+    FDBM_CUDA(cudaMemcpyAsync(plan->smp_coef, h_coef, sizeof(float) * 3 * n_steps, cudaMemcpyHostToDevice, s));
+    plan->smp_h_times = ht; plan->smp_h_coef = hc;
+  }
+  FDBM_CUDA(cudaEventRecord(plan->smp_ev[slot], s));
+  FDBM_CUDA(cudaMemcpyAsync(plan->smp_y, y, spec_bytes, cudaMemcpyDeviceToDevice, s));
+  FDBM_CUDA(cudaMemcpyAsync(plan->smp_x, x, spec_bytes, cudaMemcpyDeviceToDevice, s));
+
+  GraphKey key{{plan->smp_y, plan->smp_x, plan->smp_times, plan->smp_coef, want_noise ? noise : nullptr, nullptr}, n_steps, kind, 0};
+  if (!(plan->have_graph && plan->graph_key == key)) {
+    if (plan->graph_exec) { cudaGraphExecDestroy(plan->graph_exec); plan->graph_exec = nullptr; plan->have_graph = false; }
+    cudaGraph_t graph = nullptr;
+    cudaStream_t cs = plan->capture_stream;
+    FDBM_CUDA(cudaStreamBeginCapture(cs, cudaStreamCaptureModeThreadLocal));
+    int rc = FDBM_OK;
+    for (int i = 0; i < n_steps && rc == FDBM_OK; ++i) {
+      plan->cur_x = plan->smp_x; plan->cur_y = plan->smp_y; plan->cur_t = plan->smp_times + i; plan->cur_t_stride = 0; plan->cur_out = plan->d_buf;
+      rc = run_ops(plan, cs);
+      const float* third = kind == FDBM_STEP_ODE ? plan->smp_y : (want_noise ? noise + 2 * n_complex * i : nullptr);
+      if (rc == FDBM_OK)
+        rc = launch_bridge_step_rng(plan->smp_x, plan->d_buf, third, plan->smp_coef + 3 * i, kind, plan->smp_rng,
+                                    static_cast<uint64_t>(i) + 1, n_complex, cs);
+    }
+    const cudaError_t e = cudaStreamEndCapture(cs, &graph);
+    if (rc) { if (graph) cudaGraphDestroy(graph); return rc; }
+    if (e != cudaSuccess) return cuda_fail(e, "cudaStreamEndCapture", __FILE__, __LINE__);
+    const cudaError_t e2 = cudaGraphInstantiate(&plan->graph_exec, graph, 0);
+    cudaGraphDestroy(graph);
+    if (e2 != cudaSuccess) return cuda_fail(e2, "cudaGraphInstantiate", __FILE__, __LINE__);
+    plan->graph_key = key; plan->have_graph = true;
+  }
+  FDBM_CUDA(cudaGraphLaunch(plan->graph_exec, s));
+  FDBM_CUDA(cudaMemcpyAsync(x, plan->smp_x, spec_bytes, cudaMemcpyDeviceToDevice, s));
+  return FDBM_OK;
 }

@@ -311,11 +311,9 @@ template <int VEC, int CP>
 static int launch_pyr(const op_t* act, const float* w, const float* bias, const float* prev, int B, int T,
                       int F, float* out, cudaStream_t s) {
   const size_t smem = sizeof(float) * 9 * VEC * 32 * CP;
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first(current_device()))
     FDBM_CUDA(cudaFuncSetAttribute(pyramid_conv_kernel<VEC, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-    attr = true;
-  }
   const int64_t n_px = static_cast<int64_t>(B) * T * F;
   const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(n_px, 8), static_cast<int64_t>(num_sms()) * 6));
   pyramid_conv_kernel<VEC, CP><<<grid, 256, smem, s>>>(act, w, bias, prev, B, T, F, out);

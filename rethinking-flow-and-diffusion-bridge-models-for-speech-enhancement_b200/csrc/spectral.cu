@@ -11,7 +11,20 @@
 #include "common.cuh"
 
 namespace fdbm {
+bool spectral_fast_supported(int n_fft, int hop, bool inverse);
+int launch_stft_fast(const float* wave, int batch, int64_t max_samples, const int* lengths, int64_t wave_stride, const float* window,
+                     const float* norm, int hop, int transform, float factor, float expo, int pad_mode, int M, int n_frames_out,
+                     float* spec, cudaStream_t s);
+int launch_istft_fast(const float* spec, int batch, int n_frames, const float* window, int transform, float factor, float expo,
+                      int64_t length, const int* lengths, int64_t wave_stride, const float* norm, float* peak, float* wave, cudaStream_t s);
+int launch_absmax(const float* wave, int batch, int64_t n_samples, const int* lengths, int64_t stride, float* out, cudaStream_t s);
+int launch_clip_rescale(float* wave, int batch, int64_t n_samples, const int* lengths, int64_t stride, const float* peak, float rescale,
+                        cudaStream_t s);
 namespace {
+
+// FDBM_SPECTRAL_V1=1 selects the first-generation kernels below (A/B measurements; they are also the path for hops the
+// fast kernels do not cover)
+bool use_v1() { static const bool v = getenv("FDBM_SPECTRAL_V1") && getenv("FDBM_SPECTRAL_V1")[0] == '1'; return v; }
 
 constexpr int NFFT = 512;
 constexpr int NBIN = NFFT / 2 + 1;
@@ -407,7 +420,7 @@ extern "C" int fdbm_pad_spec(const float* in, int64_t rows, int n_frames, int pa
 
 static int stft_launch(const char* who, const float* wave, int batch, int64_t max_samples, int64_t min_samples, const int* lengths,
                        int64_t wave_stride, const float* window, int n_fft, int hop, int transform_type, float spec_factor,
-                       float abs_exponent, int pad_mode, int n_frames_out, float* spec, void* stream) {
+                       float abs_exponent, int pad_mode, int n_frames_out, float* spec, void* stream, const float* norm = nullptr) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(n_fft == NFFT, "%s: n_fft must be 512 (got %d)", who, n_fft);
   FDBM_REQUIRE(hop > 0 && NFFT % hop == 0 && NFFT / hop <= MAXR && NFFT / hop >= 1, "%s: hop %d unsupported", who, hop);
@@ -418,11 +431,13 @@ static int stft_launch(const char* who, const float* wave, int batch, int64_t ma
   FDBM_REQUIRE(n_frames_out >= M, "%s: n_frames_out %d < frame count %d", who, n_frames_out, M);
   FDBM_REQUIRE(pad_mode != FDBM_PAD_REFLECTION || n_frames_out - M_min < M_min, "%s: reflection pad wider than the input", who);
   FDBM_REQUIRE(wave && window && spec && wave_stride >= max_samples, "%s: null pointer or bad stride", who);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (spectral_fast_supported(n_fft, hop, false) && !use_v1())
+    return launch_stft_fast(wave, batch, max_samples, lengths, wave_stride, window, norm, hop, transform_type, spec_factor, abs_exponent,
+                            pad_mode, M, n_frames_out, spec, as_stream(stream));
+  FDBM_REQUIRE(!norm, "%s: the fused peak normalisation needs hop 128 or 256", who);
+  static PerDeviceOnce attr_once;
+  if (attr_once.first(current_device()))
     FDBM_CUDA(cudaFuncSetAttribute(stft_compress_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem)));
-    attr_set = true;
-  }
   dim3 grid(ceil_div(n_frames_out, FR), batch);
   stft_compress_kernel<<<grid, WARPS * 32, sizeof(SpecSmem), as_stream(stream)>>>(
       wave, static_cast<int>(max_samples), lengths, wave_stride, window, hop, transform_type, spec_factor, abs_exponent, pad_mode, M,
@@ -449,18 +464,20 @@ extern "C" int fdbm_stft_compress_var(const float* wave, int batch, const int* l
 
 static int istft_launch(const char* who, const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
                         int transform_type, float spec_factor, float abs_exponent, int64_t length, const int* lengths,
-                        int64_t wave_stride, float* wave, void* stream) {
+                        int64_t wave_stride, float* wave, void* stream, const float* norm = nullptr, float* peak = nullptr) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(n_fft == NFFT, "%s: n_fft must be 512 (got %d)", who, n_fft);
   FDBM_REQUIRE(hop > 0 && NFFT % hop == 0 && NFFT / hop <= MAXR, "%s: hop %d unsupported", who, hop);
   FDBM_REQUIRE(batch > 0 && n_frames > 0 && length > 0 && wave_stride >= length, "%s: bad sizes", who);
   FDBM_REQUIRE(transform_type >= 0 && transform_type <= 2, "%s: bad transform", who);
   FDBM_REQUIRE(spec && window && wave, "%s: null pointer", who);
-  static bool attr_set = false;
-  if (!attr_set) {
+  if (spectral_fast_supported(n_fft, hop, true) && !use_v1())
+    return launch_istft_fast(spec, batch, n_frames, window, transform_type, spec_factor, abs_exponent, length, lengths, wave_stride, norm,
+                             peak, wave, as_stream(stream));
+  FDBM_REQUIRE(!norm && !peak, "%s: the fused rescale / peak tracking needs hop = n_fft / 2", who);
+  static PerDeviceOnce attr_once;
+  if (attr_once.first(current_device()))
     FDBM_CUDA(cudaFuncSetAttribute(decompress_istft_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sizeof(SpecSmem)));
-    attr_set = true;
-  }
   const int64_t n_seg = ceil_div64(length + NFFT / 2, hop);      // hop segments covering [0, length + n_fft/2)
   const int frb = 2 * WARPS - (NFFT / hop - 1);                  // hop segments completed per block
   dim3 grid(static_cast<unsigned>(ceil_div64(n_seg, frb)), batch);
@@ -484,4 +501,35 @@ extern "C" int fdbm_decompress_istft_var(const float* spec, int batch, int n_fra
   FDBM_REQUIRE(lengths, "fdbm_decompress_istft_var: null lengths");
   return istft_launch("fdbm_decompress_istft_var", spec, batch, n_frames, window, n_fft, hop, transform_type, spec_factor,
                       abs_exponent, max_length, lengths, wave_stride, wave, stream);
+}
+
+// ---- fused glue of `enhance` (fdbm/model.py:391-406, infer_single.py:80-99, infer_folder.py:100-121) ------------------------
+extern "C" int fdbm_wave_absmax(const float* wave, int batch, int64_t n_samples, const int* lengths, int64_t wave_stride, float* out,
+                                void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(wave && out && batch > 0 && n_samples > 0 && wave_stride >= n_samples, "fdbm_wave_absmax: bad arguments");
+  return launch_absmax(wave, batch, n_samples, lengths, wave_stride, out, as_stream(stream));
+}
+
+extern "C" int fdbm_stft_compress_ex(const float* wave, int batch, const int* lengths, int64_t min_samples, int64_t max_samples,
+                                     int64_t wave_stride, const float* window, const float* norm, int n_fft, int hop,
+                                     int transform_type, float spec_factor, float abs_exponent, int pad_mode, int n_frames_out,
+                                     float* spec, void* stream) {
+  return stft_launch("fdbm_stft_compress_ex", wave, batch, max_samples, min_samples, lengths, wave_stride, window, n_fft, hop,
+                     transform_type, spec_factor, abs_exponent, pad_mode, n_frames_out, spec, stream, norm);
+}
+
+extern "C" int fdbm_decompress_istft_ex(const float* spec, int batch, int n_frames, const float* window, int n_fft, int hop,
+                                        int transform_type, float spec_factor, float abs_exponent, const int* lengths,
+                                        int64_t max_length, int64_t wave_stride, const float* norm, float* peak, float* wave,
+                                        void* stream) {
+  return istft_launch("fdbm_decompress_istft_ex", spec, batch, n_frames, window, n_fft, hop, transform_type, spec_factor,
+                      abs_exponent, max_length, lengths, wave_stride, wave, stream, norm, peak);
+}
+
+extern "C" int fdbm_clip_rescale(float* wave, int batch, int64_t n_samples, const int* lengths, int64_t wave_stride, const float* peak,
+                                 float rescale, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(wave && peak && batch > 0 && n_samples > 0 && wave_stride >= n_samples, "fdbm_clip_rescale: bad arguments");
+  return launch_clip_rescale(wave, batch, n_samples, lengths, wave_stride, peak, rescale, as_stream(stream));
 }

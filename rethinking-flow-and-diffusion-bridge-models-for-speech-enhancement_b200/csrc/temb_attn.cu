@@ -328,11 +328,9 @@ int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B,
   FDBM_REQUIRE(C % 8 == 0 && ld % 8 == 0 && ldo % 8 == 0, "attention: channels / strides must be multiples of 8");
   if (C == AT_C && !fp32_probs) {                      // the backbone's case: tensor-core kernel
     constexpr int kSmem = (AT_BQ + 2 * AT_BK) * AT_PITCH * 2;
-    static bool attr_done = false;
-    if (!attr_done) {
+    static PerDeviceOnce attr_once;
+    if (attr_once.first(current_device()))
       FDBM_CUDA(cudaFuncSetAttribute(attention_mma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, kSmem));
-      attr_done = true;
-    }
     dim3 grid(ceil_div(L, AT_BQ), B);
     attention_mma_kernel<<<grid, 128, kSmem, s>>>(q, k, v, ld, L, 1.4426950408889634f / sqrtf(static_cast<float>(C)), o, ldo);
     FDBM_LAUNCH_CHECK();
@@ -340,11 +338,9 @@ int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B,
   }
   const size_t smem = sizeof(float) * ATT_WARPS * (C + L);
   FDBM_REQUIRE(smem <= 200 * 1024, "attention: sequence length %d too long for the shared-memory score buffer", L);
-  static size_t attr_smem = 0;
-  if (smem > 48 * 1024 && smem > attr_smem) {
+  static PerDeviceOnce attr_big;
+  if (smem > 48 * 1024 && attr_big.first(current_device()))
     FDBM_CUDA(cudaFuncSetAttribute(attention_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr_smem = 200 * 1024;
-  }
   dim3 grid(ceil_div(L, ATT_WARPS), B);
   attention_kernel<<<grid, ATT_WARPS * 32, smem, s>>>(q, k, v, ld, L, C, 1.0f / sqrtf(static_cast<float>(C)), o, ldo);
   FDBM_LAUNCH_CHECK();

@@ -492,24 +492,43 @@ sumsq_kernel(const float* __restrict__ g, int64_t n, double* __restrict__ partia
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
   if (threadIdx.x == 0) partial[1 + blockIdx.x] = red[0];
 }
+// state (optional, device): {applied updates, skipped steps, last gradient norm (un-scaled), reserved}.  A step whose
+// gradient norm is not finite (fp16 overflow of a loss-scaled activation gradient) is SKIPPED: it advances neither Adam's
+// bias correction nor torch_ema's num_updates, and is counted so that the host can back the loss scale off.
 __global__ void __launch_bounds__(256)
-sumsq_final_kernel(double* __restrict__ partial, int n_blocks) {
+sumsq_final_kernel(double* __restrict__ partial, int n_blocks, double* __restrict__ state, float grad_div) {
   __shared__ double red[256];
   double s = 0;
   for (int i = threadIdx.x; i < n_blocks; i += 256) s += partial[1 + i];
   red[threadIdx.x] = s;
   __syncthreads();
   for (int k = 128; k > 0; k >>= 1) { if (threadIdx.x < k) red[threadIdx.x] += red[threadIdx.x + k]; __syncthreads(); }
-  if (threadIdx.x == 0) partial[0] = red[0];
+  if (threadIdx.x == 0) {
+    partial[0] = red[0];
+    if (state) {
+      const double norm = sqrt(red[0]) / grad_div;
+      state[2] = norm;
+      if (isfinite(norm)) state[0] += 1.0; else state[1] += 1.0;
+    }
+  }
 }
 
 __global__ void __launch_bounds__(256)
 adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ m, float* __restrict__ v,
                 float* __restrict__ ema, const unsigned char* __restrict__ trainable, int64_t n, const double* __restrict__ sumsq,
-                float grad_div, float clip, float lr, float beta1, float beta2, float eps, float bc1, float bc2, float ema_decay) {
+                float grad_div, float clip, float lr, float beta1, float beta2, float eps, int step_host, const double* __restrict__ state,
+                float ema_decay, int ema_warmup) {
   // torch.nn.utils.clip_grad_norm_: coef = clip / (norm + 1e-6), applied when < 1
   const double norm = sqrt(*sumsq) / grad_div;
   if (!isfinite(norm)) return;                        // overflowed step (loss scale too large): skip, as GradScaler does
+  // update count: the host's when given, else the device-side count of APPLIED steps (already incremented for this one)
+  const double n_upd = step_host > 0 ? static_cast<double>(step_host) : state[0];
+  const float bc1 = static_cast<float>(1.0 - pow(static_cast<double>(beta1), n_upd));
+  const float bc2 = static_cast<float>(1.0 - pow(static_cast<double>(beta2), n_upd));
+  // torch_ema.ExponentialMovingAverage.update (use_num_updates=True, the default the reference constructs it with,
+  // fdbm/model.py:56): decay = min(decay, (1 + n) / (10 + n)); shadow -= (1 - decay) * (shadow - param)
+  float omd = 1.0f - ema_decay;
+  if (ema_warmup) omd = static_cast<float>(1.0 - fmin(static_cast<double>(ema_decay), (1.0 + n_upd) / (10.0 + n_upd)));
   float coef = 1.0f / grad_div;
   if (clip > 0.f) { const double c = clip / (norm + 1e-6); if (c < 1.0) coef *= static_cast<float>(c); }
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
@@ -520,7 +539,7 @@ adam_ema_kernel(float* __restrict__ p, const float* __restrict__ g, float* __res
     m[i] = mi; v[i] = vi;
     const float pi = p[i] - lr * (mi / bc1) / (sqrtf(vi / bc2) + eps);
     p[i] = pi;
-    if (ema) ema[i] = ema_decay * ema[i] + (1.0f - ema_decay) * pi;
+    if (ema) { const float e = ema[i]; ema[i] = e - omd * (e - pi); }
   }
 }
 
@@ -628,11 +647,10 @@ int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, 
   FDBM_REQUIRE(C % 8 == 0, "attention_bwd: channels must be a multiple of 8");
   const size_t smem_a = sizeof(float) * ATT_WARPS * (2 * C + 2 * L), smem_b = sizeof(float) * ATT_WARPS * 2 * L;
   FDBM_REQUIRE(smem_a <= 200 * 1024, "attention_bwd: sequence length %d too long", L);
-  static bool attr = false;
-  if (!attr) {
+  static PerDeviceOnce attr_once;
+  if (attr_once.first(current_device())) {
     FDBM_CUDA(cudaFuncSetAttribute(attention_bwd_q_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
     FDBM_CUDA(cudaFuncSetAttribute(attention_bwd_kv_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
-    attr = true;
   }
   const float scale = 1.0f / sqrtf(static_cast<float>(C));
   float* Pm = scratch;
@@ -647,13 +665,14 @@ int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, 
 
 int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const unsigned char* trainable, int64_t n,
                     double* sumsq_scratch, float grad_div, float clip, float lr, float beta1, float beta2, float eps, int step,
-                    float ema_decay, cudaStream_t s) {
+                    float ema_decay, int ema_warmup, double* state, cudaStream_t s) {
+  FDBM_REQUIRE(step > 0 || state, "adam_ema: step == 0 needs the device-side state block");
   sumsq_kernel<<<SUMSQ_BLOCKS, 256, 0, s>>>(g, n, sumsq_scratch);
   FDBM_LAUNCH_CHECK();
-  sumsq_final_kernel<<<1, 256, 0, s>>>(sumsq_scratch, SUMSQ_BLOCKS);
+  sumsq_final_kernel<<<1, 256, 0, s>>>(sumsq_scratch, SUMSQ_BLOCKS, state, grad_div);
   FDBM_LAUNCH_CHECK();
-  const float bc1 = 1.0f - powf(beta1, static_cast<float>(step)), bc2 = 1.0f - powf(beta2, static_cast<float>(step));
-  adam_ema_kernel<<<grid_for(n), 256, 0, s>>>(p, g, m, v, ema, trainable, n, sumsq_scratch, grad_div, clip, lr, beta1, beta2, eps, bc1, bc2, ema_decay);
+  adam_ema_kernel<<<grid_for(n), 256, 0, s>>>(p, g, m, v, ema, trainable, n, sumsq_scratch, grad_div, clip, lr, beta1, beta2, eps, step, state,
+                                              ema_decay, ema_warmup);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -700,9 +719,9 @@ extern "C" int fdbm_attention_bwd(const void* qkv, int batch, int L, int C, cons
 
 extern "C" int fdbm_adam_ema_step(float* params, const float* grads, float* m, float* v, float* ema, int64_t n, double* scratch,
                                   float grad_div, float clip_norm, float lr, float beta1, float beta2, float eps, int step,
-                                  float ema_decay, void* stream) {
+                                  float ema_decay, int ema_warmup, double* state, void* stream) {
   if (int rc = require_sm100()) return rc;
-  FDBM_REQUIRE(params && grads && m && v && scratch && n > 0 && step >= 1, "fdbm_adam_ema_step: bad arguments");
+  FDBM_REQUIRE(params && grads && m && v && scratch && n > 0 && (step >= 1 || (step == 0 && state)), "fdbm_adam_ema_step: bad arguments");
   return launch_adam_ema(params, grads, m, v, ema, nullptr, n, scratch, grad_div, clip_norm, lr, beta1, beta2, eps, step, ema_decay,
-                         as_stream(stream));
+                         ema_warmup, state, as_stream(stream));
 }

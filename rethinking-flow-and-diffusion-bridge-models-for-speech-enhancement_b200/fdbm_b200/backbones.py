@@ -5,10 +5,16 @@ the reference's names and shapes (`all_modules.<i>.<Layer>.weight`, `output_laye
 the default model) so reference checkpoints load unchanged, and whose `forward(x, y, t)` /
 `forward(y)` (predictive) runs the whole U-Net in libfdbm_b200 (fdbm/backbones/ncsnpp_v2.py:36-401,
 ncsnpp_v2_predictive.py:36-362).  The module itself holds no arithmetic: it owns the parameters and
-a cache of C-side plans keyed by (batch, n_frames); packed weights are refreshed whenever a
-parameter's version counter changes (optimizer step, EMA swap -- fdbm/model.py:146-160).
+a cache of C-side plans keyed by (device, batch, n_frames); packed weights are refreshed whenever a
+parameter's (storage, version) pair changes (optimizer step, load_state_dict) and on every
+train()/eval() switch (the reference swaps EMA weights there through `param.data`, which bumps no
+version counter -- fdbm/model.py:146-160).
 
-Inference only in this round: forward runs under no_grad semantics (outputs carry no autograd graph).
+Training drop-in: in train() mode with autograd enabled, `forward(x, y, t)` of the bridge backbone
+returns a tensor with a grad_fn; `loss.backward()` runs fdbm_ncsnpp_backward on a training plan and
+delivers the parameter gradients to autograd (so `param.grad` is filled exactly as for the
+reference module and BridgeModel.training_step / Lightning / torch.optim work unchanged,
+fdbm/model.py:258-282).  In eval() mode, or under no_grad, the output carries no graph.
 """
 from __future__ import annotations
 
@@ -20,7 +26,7 @@ import torch
 import torch.nn as nn
 
 from . import _lib
-from ._lib import Arch, TensorRef, check, current_stream, ptr
+from ._lib import Arch, TensorRef, check, current_stream, on_device, ptr
 from .registry import BackboneRegistry
 
 
@@ -131,8 +137,12 @@ class _NCSNppBase(nn.Module):
         super().__init__()
         for key, want in (("nonlinearity", "swish"), ("resblock_type", "biggan"), ("progressive", "output_skip"),
                           ("progressive_input", "input_skip"), ("progressive_combine", "sum"),
-                          ("embedding_type", "fourier"), ("fir", True), ("skip_rescale", True)):
-            if key in unused_kwargs and unused_kwargs[key] != want:
+                          ("embedding_type", "fourier"), ("fir", True), ("skip_rescale", True),
+                          ("resamp_with_conv", True), ("fir_kernel", [1, 3, 3, 1]), ("dropout", 0.0)):
+            got = unused_kwargs.get(key, want)
+            if isinstance(want, list):
+                got = list(got)
+            if got != want:
                 raise NotImplementedError(f"fdbm_b200 implements the reference's default NCSN++ variant only ({key}={want!r})")
         attn = [r for r in attn_resolutions if r > 0]
         if len(attn) > 1:
@@ -176,6 +186,9 @@ class _NCSNppBase(nn.Module):
             holders.append(h)
         self.all_modules = nn.ModuleList(holders)
         self._plans = {}          # (device index, batch, n_frames) -> [plan handle, weight version]; insertion order = LRU order
+        self._train_plans = {}    # same key -> [training plan handle, weight version] (autograd drop-in, train() mode)
+        self._param_cache = None  # [(name, parameter)], rebuilt after .to()/.cuda()
+        self.grad_loss_scale = 1024.0   # activation gradients are 16-bit GEMM operands: dL/dD is scaled by this in backward
         # device memory all cached plans may hold together (each plan owns an arena + a packed copy of the weights); folders
         # with many distinct padded lengths would otherwise grow without bound -- least recently used plans are destroyed
         self.max_plan_bytes = 96 << 30
@@ -190,45 +203,66 @@ class _NCSNppBase(nn.Module):
         a.predictive, a.image_size = int(self.predictive), self.image_size
         return a
 
-    def _weight_version(self) -> int:
-        return sum(p._version for p in self.parameters()) + sum(p.data_ptr() % 65537 for p in self.parameters())
+    def _named(self):
+        if self._param_cache is None:
+            self._param_cache = list(self.named_parameters())
+        return self._param_cache
 
-    def _plan(self, device, batch, n_frames):
+    def _apply(self, fn, *a, **k):
+        self._param_cache = None                                    # .to() / .cuda() may replace the Parameter objects
+        return super()._apply(fn, *a, **k)
+
+    def _weight_version(self):
+        """Identity of the current weight state: (storage address, in-place version) of every parameter.  Catches
+        optimizer steps, load_state_dict and re-allocation; writes through `param.data` bump no counter and need
+        `invalidate_weights()` (train()/eval() call it)."""
+        return tuple((p.data_ptr(), p._version) for _, p in self._named())
+
+    def _load_into(self, handle, device):
+        named = self._named()
+        refs = (TensorRef * len(named))()
+        keep = []
+        for i, (n, p) in enumerate(named):
+            if p.device != device or p.dtype != torch.float32:
+                raise RuntimeError(f"parameter {n} must be fp32 on {device}")
+            d = p.detach().contiguous()
+            keep.append(d)
+            refs[i].name, refs[i].data, refs[i].numel = n.encode(), d.data_ptr(), d.numel()
+        check(_lib.load().fdbm_plan_load_weights(handle, refs, len(named), current_stream()), "fdbm_plan_load_weights")
+
+    def _plan(self, device, batch, n_frames, train=False):
+        """Plan for (device, batch, n_frames), created on first use, with the module's current weights loaded.  Must be
+        called with `device` current (the public entry points are wrapped in `on_device`)."""
         lib = _lib.load()
         key = (device.index, batch, n_frames)
-        entry = self._plans.pop(key, None)
+        cache = self._train_plans if train else self._plans
+        entry = cache.pop(key, None)
         if entry is None:
             handle = C.c_void_p()
             arch = self._arch()
-            check(lib.fdbm_plan_create(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create")
+            create = lib.fdbm_plan_create_train if train else lib.fdbm_plan_create
+            check(create(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create")
             entry = [handle, None]
-            used = sum(int(lib.fdbm_plan_device_bytes(h)) for h, _ in self._plans.values()) + int(lib.fdbm_plan_device_bytes(handle))
-            while used > self.max_plan_bytes and self._plans:
-                old_key = next(iter(self._plans))
-                old_handle, _ = self._plans.pop(old_key)
+            everything = list(self._plans.items()) + list(self._train_plans.items())
+            used = sum(int(lib.fdbm_plan_device_bytes(h)) for _, (h, _) in everything) + int(lib.fdbm_plan_device_bytes(handle))
+            while used > self.max_plan_bytes and (self._plans or self._train_plans):
+                victims = self._plans if self._plans else self._train_plans
+                old_key = next(iter(victims))
+                old_handle, _ = victims.pop(old_key)
                 used -= int(lib.fdbm_plan_device_bytes(old_handle))
                 torch.cuda.synchronize(device)                      # the evicted plan's arena may still be in flight
                 lib.fdbm_plan_destroy(old_handle)
-        self._plans[key] = entry                                    # (re-)insert as most recently used
+        cache[key] = entry                                          # (re-)insert as most recently used
         version = self._weight_version()
         if entry[1] != version:
-            named = [(n, p) for n, p in self.named_parameters()]
-            refs = (TensorRef * len(named))()
-            keep = []
-            for i, (n, p) in enumerate(named):
-                if p.device != device or p.dtype != torch.float32:
-                    raise RuntimeError(f"parameter {n} must be fp32 on {device}")
-                d = p.detach().contiguous()
-                keep.append(d)
-                refs[i].name, refs[i].data, refs[i].numel = n.encode(), d.data_ptr(), d.numel()
-            check(lib.fdbm_plan_load_weights(entry[0], refs, len(named), current_stream()), "fdbm_plan_load_weights")
+            self._load_into(entry[0], device)
             entry[1] = version
         return entry[0]
 
     def invalidate_weights(self):
         """Force a re-pack on the next call.  Needed after writes through `param.data` (e.g. torch_ema's
         in-place swap, fdbm/model.py:146-160), which do not bump the parameter's version counter."""
-        for entry in self._plans.values():
+        for entry in list(self._plans.values()) + list(self._train_plans.values()):
             entry[1] = None
 
     def train(self, mode: bool = True):
@@ -237,9 +271,10 @@ class _NCSNppBase(nn.Module):
 
     def release_plans(self):
         lib = _lib.load()
-        for handle, _ in self._plans.values():
-            lib.fdbm_plan_destroy(handle)
+        for handle, _ in list(self._plans.values()) + list(self._train_plans.values()):
+            lib.fdbm_plan_destroy(handle)                           # switches to the plan's own device internally
         self._plans.clear()
+        self._train_plans.clear()
 
     def __del__(self):
         try:
@@ -249,10 +284,12 @@ class _NCSNppBase(nn.Module):
 
     def plan_info(self, batch, n_frames, device=None):
         device = device or next(self.parameters()).device
-        h = self._plan(device, batch, n_frames)
+        with torch.cuda.device(device):
+            h = self._plan(device, batch, n_frames)
         lib = _lib.load()
         return {"device_bytes": lib.fdbm_plan_device_bytes(h), "launches": lib.fdbm_plan_num_launches(h)}
 
+    @on_device
     def profile_forward(self, x, y=None, t=None, max_ops=4096):
         """One forward with a CUDA event pair around every kernel launch (bench.py's roofline leg).
         Returns [(milliseconds, kind, algorithmic_flops), ...] in launch order; kinds are FDBM_OP_*."""
@@ -276,6 +313,7 @@ class _NCSNppBase(nn.Module):
         return s.contiguous()
 
     # ---- sampler hook used by fdbm_b200.bridge.Bridge -----------------------------------------
+    @on_device
     def run_sampler(self, y, x, times, table, kind, noise, seed):
         """In-place N-step sampler on x (fdbm/bridge.py:66-113) as one CUDA graph."""
         if self.predictive:
@@ -292,13 +330,62 @@ class _NCSNppBase(nn.Module):
         return x
 
 
+class _DevBuf:
+    """A plan-owned flat fp32 device buffer as a zero-copy torch tensor (`torch.as_tensor(_DevBuf(ptr, n), device=...)`)."""
+
+    def __init__(self, pointer: int, n: int):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (pointer, False), "version": 2}
+
+
+class _BackboneFunction(torch.autograd.Function):
+    """D = dnn(x_t, y, t) with parameter gradients from the library's own backward pass (tcgen05 dgrad / wgrad, GroupNorm /
+    FIR / attention backward): the autograd seam that makes `BridgeModel.training_step` + `loss.backward()`
+    (fdbm/model.py:258-282) work on the CUDA backbone.  Gradients w.r.t. x_t, y and t are not produced (the reference's
+    `_step` never needs them: x_t is sampled, not learned)."""
+
+    @staticmethod
+    def forward(ctx, net, names, x, y, t, *params):
+        lib = _lib.load()
+        plan = net._plan(x.device, x.shape[0], x.shape[3], train=True)
+        out = torch.empty_like(x)
+        check(lib.fdbm_ncsnpp_forward(plan, ptr(x), ptr(y), ptr(t), ptr(out), current_stream()), "fdbm_ncsnpp_forward")
+        ctx.net, ctx.names, ctx.plan, ctx.device = net, names, plan, x.device
+        ctx.keep = (x, y, t)                                         # the plan reads them again in backward
+        ctx.shapes = [p.shape for p in params]
+        ctx.set_materialize_grads(False)
+        return out
+
+    @staticmethod
+    def backward(ctx, g_out):
+        if g_out is None:
+            return (None,) * (5 + len(ctx.shapes))
+        lib = _lib.load()
+        net, scale = ctx.net, float(ctx.net.grad_loss_scale)
+        with torch.cuda.device(ctx.device):
+            g = (g_out.to(torch.complex64) * scale).contiguous()
+            check(lib.fdbm_ncsnpp_backward(ctx.plan, ptr(torch.view_as_real(g)), scale, 0, current_stream()), "fdbm_ncsnpp_backward")
+            pp_, gp_, ep_, n_ = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+            check(lib.fdbm_plan_buffers(ctx.plan, C.byref(pp_), C.byref(gp_), C.byref(ep_), C.byref(n_)), "fdbm_plan_buffers")
+            flat = torch.as_tensor(_DevBuf(gp_.value, n_.value), device=ctx.device)
+            grads = []
+            off, num = C.c_int64(), C.c_int64()
+            for name, shape in zip(ctx.names, ctx.shapes):
+                check(lib.fdbm_plan_param_info(ctx.plan, name.encode(), C.byref(off), C.byref(num)), "fdbm_plan_param_info")
+                grads.append(flat[off.value:off.value + num.value].view(shape).clone())
+        return (None, None, None, None, None, *grads)
+
+
 @BackboneRegistry.register("ncsnpp_v2")
 class NCSNpp_v2(_NCSNppBase):
     """fdbm/backbones/ncsnpp_v2.py:36-401."""
 
+    @on_device
     def forward(self, x, y, t):
         x, y = self._check_spec(x, "x"), self._check_spec(y, "y")
         t = t.to(device=x.device, dtype=torch.float32).contiguous()
+        if self.training and torch.is_grad_enabled() and any(p.requires_grad for _, p in self._named()):
+            names = [n for n, p in self._named() if p.requires_grad]
+            return _BackboneFunction.apply(self, tuple(names), x, y, t, *[p for _, p in self._named() if p.requires_grad])
         out = torch.empty_like(x)
         plan = self._plan(x.device, x.shape[0], x.shape[3])
         check(_lib.load().fdbm_ncsnpp_forward(plan, ptr(x), ptr(y), ptr(t), ptr(out), current_stream()), "fdbm_ncsnpp_forward")
@@ -310,6 +397,7 @@ class NCSNpp_v2_predictive(_NCSNppBase):
     """fdbm/backbones/ncsnpp_v2_predictive.py:36-362."""
     predictive = True
 
+    @on_device
     def forward(self, x):
         x = self._check_spec(x, "x")
         out = torch.empty_like(x)

@@ -8,14 +8,22 @@ libfdbm_b200 kernels.  With a fdbm_b200 backbone the whole N-step loop is one CU
 (`fdbm_sampler_run`); with any other callable `model(xt, y, t)` the loop stays in Python and only
 the update `x <- wx*x + ws*D + w3*{y|z}` is the fused kernel.
 
-Out of scope: `ode_int` (host-driven scipy RK45) and `pc` samplers.
+`pc` (bridge.py:142-166): Euler-Maruyama predictor + Langevin / annealed-Langevin corrector; all utterances of a batch
+share the step's time, so every update is  x_mean = c0 x + c1 D + c2 y,  x = x_mean + c3 z  with scalar weights --
+one fused kernel per update (`fdbm_bridge_update4`), the Langevin corrector's data-dependent step size being reduced on
+the device (`fdbm_langevin_coef`).  The reference multiplies `[B]` weight vectors straight into `[B,1,F,T]` tensors in
+`path.ode` / `path.sde` (bridge.py:283-306), which only broadcasts correctly for B = 1; here the weights are scalars, so
+any batch size works and B = 1 reproduces the reference.
+`ode_int` (bridge.py:115-140): the reference hands the flattened state to scipy's RK45 on the host; here the same
+Dormand-Prince 5(4) scheme with scipy's step-size controller runs on device tensors (`fdbm_lincomb`, `fdbm_rk_error_norm`),
+one scalar read-back per step.
 """
 from __future__ import annotations
 
 import torch
 
 from . import _lib
-from ._lib import FDBM_STEP, check, current_stream, ptr
+from ._lib import FDBM_STEP, check, current_stream, on_device, ptr
 from .registry import BridgeRegistry
 
 
@@ -24,18 +32,23 @@ class Bridge:
     def add_argparse_args(parser):
         parser.add_argument("--N", type=int, default=5, help="The number of steps during sampling. 5 by default.")
         parser.add_argument("--T", type=float, default=1.0, help="The total time duration of the path. 1.0 by default.")
-        parser.add_argument("--sampler_type", type=str, default="ode_ei", choices=["ode_ei", "sde_ei"],
+        parser.add_argument("--sampler_type", type=str, default="ode_ei", choices=["ode_ei", "sde_ei", "ode_int", "pc"],
                             help="The sampler type to use. 'ode_ei' by default.")
         parser.add_argument("--sampling_eps", type=float, default=1e-4, help="The minimum process time for sampling.")
         return parser
 
-    def __init__(self, path, N=5, T=1.0, sampler_type="ode_ei", sampling_eps=1e-4, noise="torch", seed=0, **kwargs):
+    def __init__(self, path, N=5, T=1.0, sampler_type="ode_ei", sampling_eps=1e-4, noise="torch", seed=0,
+                 match_torch_rng=False, **kwargs):
         self.path = BridgeRegistry.get_by_name(path)(T=T, **kwargs)
         self.N = N
         self.T = T
         self.sampler_type = sampler_type
         self.noise = noise            # "torch": z from torch.randn_like (reference RNG stream); "philox": in-kernel
         self.seed = seed
+        # The reference draws z in prior_sampling even when sigma(t0) = 0 (SB: x_start = y) and discards it.  That draw
+        # is a full-size HBM write per call (135 MB per 256 utterances) whose only effect is on torch's global RNG
+        # stream; it is made only on request (tests that replay the reference's RNG sequence set this).
+        self.match_torch_rng = match_torch_rng
         self._calls = 0
         if self.path.sampling_direction == "forward":
             self.start_time, self.end_time = sampling_eps, self.path.T
@@ -85,14 +98,14 @@ class Bridge:
         self._calls += 1
         return self._calls << 20
 
+    @on_device
     def prior_sampling(self, y: torch.Tensor) -> torch.Tensor:
         """bridge.py:45-49: x_start = b(t0) y + sigma(t0) z."""
         _, b, sig = self.path.path_param(self.start_time * torch.ones(1))
         b, sig = float(b[0]), float(sig[0])
         y = y.contiguous()
         x = torch.empty_like(y)
-        # the reference draws z even when sigma(t0) = 0 (SB); keep torch's RNG stream in step with it
-        z = torch.randn_like(y) if self.noise == "torch" else None
+        z = torch.randn_like(y) if self.noise == "torch" and (sig != 0.0 or self.match_torch_rng) else None
         check(_lib.load().fdbm_prior_sample(ptr(y), ptr(z), b, sig, self.seed, self._next_offset(), y.numel(), ptr(x),
                                             current_stream()), "fdbm_prior_sample")
         return x
@@ -102,7 +115,11 @@ class Bridge:
             return self.ode_sampler_ei(model, y, **kwargs)
         if self.sampler_type == "sde_ei":
             return self.sde_sampler_ei(model, y, **kwargs)
-        raise NotImplementedError(f"sampler_type '{self.sampler_type}' is outside the accelerated path (ode_ei, sde_ei)")
+        if self.sampler_type == "ode_int":
+            return self.ode_sampler_int(model, y, **kwargs)
+        if self.sampler_type == "pc":
+            return self.pc_sampler(model, y, **kwargs)
+        return None                                   # bridge.py:56-64 falls through for unknown names
 
     def ode_sampler_ei(self, model, y, **kwargs):
         """bridge.py:66-87."""
@@ -112,6 +129,7 @@ class Bridge:
         """bridge.py:89-113."""
         return self._run(model, y, "sde_ei")
 
+    @on_device
     def _run(self, model, y, st):
         with torch.no_grad():
             y = y.contiguous()
@@ -135,6 +153,93 @@ class Bridge:
                 check(lib.fdbm_bridge_step(ptr(xt), ptr(est), ptr(third), ptr(table[i]), kind, self.seed + self._calls,
                                            i + 1, xt.numel(), current_stream()), "fdbm_bridge_step")
             return xt
+
+
+    # ---- predictor-corrector sampler (bridge.py:142-166) ---------------------------------------------------------------
+    @on_device
+    def pc_sampler(self, model, y, predictor_name="reverse_diffusion", corrector_name="ald", denoise=True, snr=0.5,
+                   corrector_steps=1, **kwargs):
+        """bridge.py:142-166 with EulerMaruyamaPredictor / NonePredictor (util/predictors.py:39-62) and LangevinCorrector /
+        AnnealedLangevinDynamics / NoneCorrector (util/correctors.py:36-95).  As in the reference the default
+        predictor name 'reverse_diffusion' is not registered and raises ValueError; pass 'euler_maruyama'."""
+        if predictor_name not in ("euler_maruyama", "none"):
+            raise ValueError(f"Predictor with name '{predictor_name}' unknown.")
+        if corrector_name not in ("langevin", "ald", "none"):
+            raise ValueError(f"Corrector with name '{corrector_name}' unknown.")
+        if predictor_name == "euler_maruyama" and not hasattr(self.path, "sde"):
+            raise AttributeError(f"{type(self.path).__name__} object has no attribute 'sde'")
+        lib = _lib.load()
+        with torch.no_grad():
+            y = y.contiguous()
+            xt = self.prior_sampling(y)
+            x_mean = xt.clone()
+            B, n = xt.shape[0], xt.numel()
+            timesteps = torch.linspace(self.start_time, self.end_time, self.N)
+            coef = torch.empty(4, device=y.device)
+            scratch = torch.empty(2 * B, dtype=torch.float64, device=y.device)
+            draw = (lambda: torch.randn_like(xt)) if self.noise == "torch" else (lambda: None)
+            seed = self.seed + self._next_offset()
+            step_id = 0
+
+            def update(est, z):
+                nonlocal step_id
+                step_id += 1
+                check(lib.fdbm_bridge_update4(ptr(xt), ptr(est), ptr(y), ptr(z), ptr(coef), seed, step_id, n, ptr(x_mean),
+                                              current_stream()), "fdbm_bridge_update4")
+
+            for i in range(self.N):
+                t = timesteps[i]
+                stepsize = t - timesteps[i + 1] if i != self.N - 1 else timesteps[-1]
+                vec_t = t * torch.ones(1)
+                dev_t = (t * torch.ones(B)).to(y.device)
+                # ---- corrector (correctors.py:44-81)
+                if corrector_name != "none":
+                    a_t, b_t, sig = (float(v[0]) for v in self.path.path_param(vec_t))
+                    for _ in range(corrector_steps):
+                        est = model(xt, y, dev_t).contiguous()
+                        z = draw()
+                        if corrector_name == "ald":
+                            std = float(self._std(vec_t)[0])
+                            step = (snr * std) ** 2 * 2
+                            k = 1.0 / (sig ** 2 + 1e-8)
+                            coef.copy_(torch.tensor([1.0 - step * k, step * k * a_t, step * k * b_t, (step * 2) ** 0.5]))
+                        else:
+                            check(lib.fdbm_langevin_coef(ptr(xt), ptr(est), ptr(y), ptr(z), a_t, b_t, sig, float(snr), seed, step_id + 1,
+                                                         B, n // B, ptr(scratch), ptr(coef), current_stream()), "fdbm_langevin_coef")
+                        update(est, z)
+                # ---- predictor (predictors.py:39-62)
+                if predictor_name == "euler_maruyama":
+                    dt = -float(stepsize)
+                    z = draw()
+                    est = model(xt, y, dev_t).contiguous()
+                    wx, ws, wy, gd = (float(v[0]) for v in self.path.sde_weights(vec_t))
+                    coef.copy_(torch.tensor([1.0 + wx * dt, ws * dt, wy * dt, gd * (-dt) ** 0.5]))
+                    update(est, z)
+                else:
+                    x_mean.copy_(xt)                   # NonePredictor.update_fn returns (x, x): predictors.py:54-62
+            return x_mean if denoise else xt
+
+    # ---- adaptive ODE sampler (bridge.py:115-140) ----------------------------------------------------------------------
+    @on_device
+    def ode_sampler_int(self, model, y, rtol=1e-5, atol=1e-5, method="RK45", max_nfev=100000, **kwargs):
+        """bridge.py:115-140: integrate dx/dt = path.ode(t, x, model(x, y, t), y) from start_time to end_time with the
+        explicit Runge-Kutta pair scipy.integrate.solve_ivp(method='RK45') uses (Dormand-Prince 5(4), local extrapolation,
+        scipy's initial-step and step-size rules), on device tensors.  The reference integrates the COMPLEX state vector:
+        scipy's error norm is the RMS of |err| / (atol + rtol max(|x|, |x_new|)) over complex elements, reproduced here."""
+        if method != "RK45":
+            raise NotImplementedError("fdbm_b200 implements solve_ivp's default method 'RK45'")
+        from .rk45 import integrate_rk45
+        with torch.no_grad():
+            y = y.contiguous()
+            x = self.prior_sampling(y)
+            B = y.shape[0]
+
+            def flow(t, x_state):
+                vec_t = float(t) * torch.ones(1)
+                est = model(x_state, y, (float(t) * torch.ones(B)).to(y.device)).contiguous()
+                wx, ws, wy = (float(v[0]) for v in self.path.ode_weights(vec_t))
+                return est, (wx, ws, wy)
+            return integrate_rk45(flow, x, y, float(self.start_time), float(self.end_time), rtol, atol, max_nfev)
 
 
 class ProbabilityPath:
@@ -163,6 +268,7 @@ class ProbabilityPathSB(ProbabilityPath):
         self.noise_schedule, self.k, self.c = noise_schedule, k, c
         self.beta_0, self.beta_1, self.rho, self.N, self.eps = beta_0, beta_1, rho, N, eps
         self.sampling_direction = "reverse"
+        self.diffusion_coeff_mode = "g"        # bridge.py:211: fixed, whatever --diffusion_coeff_mode says
 
     def _rhos_alphas(self, t):
         """bridge.py:213-238."""
@@ -208,6 +314,52 @@ class ProbabilityPathSB(ProbabilityPath):
         return (torch.where(at_T, torch.zeros_like(a_t), a_t), torch.where(at_T, torch.ones_like(b_t), b_t),
                 torch.where(at_T, torch.zeros_like(sigma), sigma))
 
+    def auxiliary_param(self, t):
+        """bridge.py:240-253: drift f and diffusion g of the reference SDE."""
+        if self.noise_schedule == "ve":
+            return 0.0, torch.sqrt(torch.tensor(self.c)) * self.k ** t
+        if self.noise_schedule == "vp":
+            lin = self.beta_0 + (self.beta_1 - self.beta_0) * t
+            return -0.5 * lin, torch.sqrt(torch.tensor(self.c) * lin)
+        if self.noise_schedule == "gmax":
+            return 0.0, torch.sqrt(torch.as_tensor(self.beta_0 + (self.beta_1 - self.beta_0) * t))
+        return 0.0, self.rho * torch.ones_like(t)
+
+    def diffusion_coeff(self, g, t):
+        """bridge.py:255-259."""
+        return g if self.diffusion_coeff_mode == "g" else 0.0 * torch.ones_like(g)
+
+    def ode_weights(self, t):
+        """Scalar weights (w_x, w_s, w_y) of the probability-flow ODE, bridge.py:283-292: flow = w_x x + w_s s + w_y y."""
+        rho, _, rho_bar, alpha, _, alpha_bar = self._rhos_alphas(t)
+        f, g = self.auxiliary_param(t)
+        w_x = f + g ** 2 * (rho_bar ** 2 - rho ** 2) / (2 * alpha ** 2 * rho ** 2 * rho_bar ** 2 + self.eps)
+        w_s = -g ** 2 / (2 * alpha * rho ** 2 + self.eps)
+        w_y = alpha_bar * g ** 2 / (2 * alpha ** 2 * rho_bar ** 2 + self.eps)
+        return w_x, w_s, w_y
+
+    def sde_weights(self, t):
+        """Scalar weights (w_x, w_s, w_y, diffusion) of the reverse SDE, bridge.py:294-306."""
+        rho, _, rho_bar, alpha, _, alpha_bar = self._rhos_alphas(t)
+        f, g = self.auxiliary_param(t)
+        gd = self.diffusion_coeff(g, t)
+        w_x = f + ((g ** 2 + gd ** 2) * rho_bar ** 2 - (g ** 2 - gd ** 2) * rho ** 2) / (2 * alpha ** 2 * rho ** 2 * rho_bar ** 2 + self.eps)
+        w_s = -(g ** 2 + gd ** 2) / (2 * alpha * rho ** 2 + self.eps)
+        w_y = alpha_bar * (g ** 2 - gd ** 2) / (2 * alpha ** 2 * rho_bar ** 2 + self.eps)
+        return w_x, w_s, w_y, gd
+
+    def ode(self, t, x, s, y):
+        """bridge.py:283-292 for callers that keep the reference's call (torch arithmetic; the [B] weights are broadcast over
+        [B,1,F,T] correctly for any B, see the module docstring)."""
+        w_x, w_s, w_y = (w.reshape(-1, 1, 1, 1) if torch.is_tensor(w) and w.dim() == 1 else w for w in self.ode_weights(t))
+        return w_x * x + w_s * s + w_y * y
+
+    def sde(self, t, x, s, y):
+        """bridge.py:294-306."""
+        w_x, w_s, w_y, gd = self.sde_weights(t)
+        b = lambda w: w.reshape(-1, 1, 1, 1) if torch.is_tensor(w) and w.dim() == 1 else w
+        return b(w_x) * x + b(w_s) * s + b(w_y) * y, gd
+
     def sampling_param_ode_ei(self, t_curr, t_prev, batch_size, device):
         """bridge.py:308-324."""
         ones = torch.ones(batch_size, device=device)
@@ -249,6 +401,16 @@ class ProbabilityPathFM(ProbabilityPath):
 
     def path_param(self, t):
         return t, 1 - t, self.sigma_t(t)
+
+    def ode_weights(self, t):
+        """bridge.py:368-371 as scalar weights: flow = ((s_min - s_max) x + s_max s - s_min y) / (sigma_t + eps)."""
+        den = self.sigma_t(t) + self.eps
+        return (self.sigma_min - self.sigma_max) / den, self.sigma_max / den, -self.sigma_min / den
+
+    def ode(self, t, x, s, y):
+        """bridge.py:368-371."""
+        sigma_t = self.sigma_t(t)[:, None, None, None]
+        return ((self.sigma_min - self.sigma_max) * x + self.sigma_max * s - self.sigma_min * y) / (sigma_t + self.eps)
 
     def sampling_param_ode_ei(self, t_curr, t_prev, batch_size, device):
         """bridge.py:373-385 (Euler step of OT-CFM)."""

@@ -13,7 +13,7 @@ from __future__ import annotations
 import torch
 
 from . import _lib
-from ._lib import FDBM_PAD, FDBM_TRANSFORM, check, current_stream, ptr
+from ._lib import FDBM_PAD, FDBM_TRANSFORM, check, current_stream, on_device, ptr
 
 
 def get_window(window_type: str, window_length: int) -> torch.Tensor:
@@ -36,6 +36,7 @@ def _as_cfloat(spec: torch.Tensor) -> torch.Tensor:
     return spec.contiguous()
 
 
+@on_device
 def pad_spec(Y: torch.Tensor, mode: str = "zero_pad") -> torch.Tensor:
     """fdbm/util/other.py:76-90 on the GPU: right-pad the frame axis of [B,1,F,T] to a multiple of 64."""
     if mode not in FDBM_PAD:
@@ -113,62 +114,77 @@ class SpecsDataModule:
         """fdbm/data_module.py:188-199."""
         return self._spec_transform(spec, inverse=1)
 
-    # ---- differentiable torch forms (loss head of the training step, fdbm/model.py:187-218) -----
-    def spec_back_torch(self, spec: torch.Tensor) -> torch.Tensor:
-        """fdbm/data_module.py:188-199 with torch ops (autograd-capable; `exponent` transform)."""
-        if self.transform_type != "exponent":
-            raise NotImplementedError("the training loss head supports transform_type='exponent'")
-        spec = spec / self.spec_factor
-        if self.spec_abs_exponent != 1:
-            e = self.spec_abs_exponent
-            spec = spec.abs() ** (1 / e) * torch.exp(1j * spec.angle())
-        return spec
-
-    def istft_torch(self, spec: torch.Tensor, length=None) -> torch.Tensor:
-        """fdbm/data_module.py:227-229 through torch.istft (autograd-capable)."""
-        return torch.istft(spec, n_fft=self.n_fft, hop_length=self.hop_length, window=self._get_window(spec), center=True,
-                           length=length)
-
     # ---- fused forms ---------------------------------------------------------------------------
-    def stft_compress(self, sig: torch.Tensor, pad_mode: str = "zero_pad", n_frames_out=None) -> torch.Tensor:
-        """pad_spec(spec_fwd(stft(sig)))[:, None] in one kernel: [B, Ts] -> [B, 1, F, T_pad]."""
+    def stft_compress(self, sig: torch.Tensor, pad_mode: str = "zero_pad", n_frames_out=None, norm=None) -> torch.Tensor:
+        """pad_spec(spec_fwd(stft(sig / norm)))[:, None] in one kernel: [B, Ts] -> [B, 1, F, T_pad].  `norm`: optional fp32 [B]
+        (the peak normalisation of infer_single.py:83-87, applied to the spectrum -- the STFT is linear)."""
         if sig.dim() != 2:
             raise RuntimeError("stft_compress expects a [B, n_samples] batch")
-        tr, fac, e = self._transform_args()
         M = 1 + sig.shape[-1] // self.hop_length
         T_out = padded_frames(M) if n_frames_out is None else n_frames_out
-        return self._stft_impl(sig, tr, fac, e, pad_mode, T_out)[:, None]
+        return self._stft_ex(sig, None, sig.shape[-1], sig.shape[-1], pad_mode, T_out, norm)
 
     def stft_compress_var(self, sig: torch.Tensor, lengths: torch.Tensor, min_len: int, max_len: int,
-                          pad_mode: str = "zero_pad", n_frames_out=None) -> torch.Tensor:
+                          pad_mode: str = "zero_pad", n_frames_out=None, norm=None) -> torch.Tensor:
         """Variable-length batch: row b of `sig` [B, >= max_len] holds lengths[b] samples (device int32 [B]); every row is
         framed / reflect-padded / frame-padded from its own length, i.e. equals stft_compress of that utterance alone."""
-        if sig.dim() != 2 or not sig.is_cuda or sig.dtype != torch.float32:
-            raise RuntimeError("stft_compress_var expects an fp32 CUDA [B, n_samples] batch")
         if lengths.dtype != torch.int32 or not lengths.is_cuda or lengths.numel() != sig.shape[0]:
             raise RuntimeError("stft_compress_var expects device int32 lengths [B]")
-        tr, fac, e = self._transform_args()
-        x = sig.contiguous()
-        B = x.shape[0]
         T_out = padded_frames(1 + max_len // self.hop_length) if n_frames_out is None else n_frames_out
-        F = self.n_fft // 2 + 1
-        spec = torch.empty(B, F, T_out, dtype=torch.complex64, device=x.device)
-        check(_lib.load().fdbm_stft_compress_var(ptr(x), B, ptr(lengths), int(min_len), int(max_len), x.stride(0),
-                                                 ptr(self._get_window(x)), self.n_fft, self.hop_length, tr, fac, e,
-                                                 FDBM_PAD[pad_mode], T_out, ptr(spec), current_stream()),
-              "fdbm_stft_compress_var")
+        return self._stft_ex(sig, lengths, min_len, max_len, pad_mode, T_out, norm)
+
+    @on_device
+    def _stft_ex(self, sig, lengths, min_len, max_len, pad_mode, T_out, norm):
+        if sig.dim() != 2 or not sig.is_cuda or sig.dtype != torch.float32:
+            raise RuntimeError("fdbm_b200 expects an fp32 CUDA [B, n_samples] batch")
+        tr, fac, e = self._transform_args()
+        x = sig if sig.stride(1) == 1 else sig.contiguous()
+        B = x.shape[0]
+        if norm is not None and (norm.dtype != torch.float32 or norm.numel() != B or not norm.is_contiguous()):
+            raise RuntimeError("norm must be a contiguous fp32 tensor with one entry per utterance")
+        spec = torch.empty(B, self.n_fft // 2 + 1, T_out, dtype=torch.complex64, device=x.device)
+        check(_lib.load().fdbm_stft_compress_ex(ptr(x), B, ptr(lengths), int(min_len), int(max_len), x.stride(0),
+                                                ptr(self._get_window(x)), ptr(norm), self.n_fft, self.hop_length, tr, fac, e,
+                                                FDBM_PAD[pad_mode], T_out, ptr(spec), current_stream()), "fdbm_stft_compress_ex")
         return spec[:, None]
 
-    def to_audio_var(self, spec: torch.Tensor, lengths: torch.Tensor, max_len: int) -> torch.Tensor:
-        """Variable-length to_audio: [B, F, T] -> [B, max_len], row b valid up to lengths[b] (zeros beyond)."""
+    @on_device
+    def wave_absmax(self, sig: torch.Tensor, lengths=None) -> torch.Tensor:
+        """max_n |sig[b, n]| per utterance, fp32 [B] (norm_factor = y.abs().max(), infer_single.py:83-84)."""
+        if sig.dim() != 2 or not sig.is_cuda or sig.dtype != torch.float32 or sig.stride(1) != 1:
+            raise RuntimeError("wave_absmax expects an fp32 CUDA [B, n_samples] batch")
+        out = torch.empty(sig.shape[0], dtype=torch.float32, device=sig.device)
+        check(_lib.load().fdbm_wave_absmax(ptr(sig), sig.shape[0], sig.shape[1], ptr(lengths), sig.stride(0), ptr(out),
+                                           current_stream()), "fdbm_wave_absmax")
+        return out
+
+    @on_device
+    def clip_rescale_(self, wave: torch.Tensor, peak: torch.Tensor, rescale: float, lengths=None) -> torch.Tensor:
+        """In place: rows whose peak exceeds 1 become wave / peak * rescale (infer_single.py:95-97, infer_folder.py:119-120)."""
+        check(_lib.load().fdbm_clip_rescale(ptr(wave), wave.shape[0], wave.shape[1], ptr(lengths), wave.stride(0), ptr(peak),
+                                            float(rescale), current_stream()), "fdbm_clip_rescale")
+        return wave
+
+    @on_device
+    def to_audio_ex(self, spec: torch.Tensor, length: int, lengths=None, norm=None, want_peak=False):
+        """istft(spec_back(spec)) * norm in one kernel: [B, F, T] -> [B, length]; rows of a variable-length batch are valid up to
+        lengths[b] (zeros beyond).  Returns (wave, peak) with peak[b] = max |wave[b]| when `want_peak`."""
         tr, fac, e = self._transform_args()
         s = _as_cfloat(spec)
         B, F, M = s.shape
-        wave = torch.zeros(B, max_len, dtype=torch.float32, device=s.device)
-        check(_lib.load().fdbm_decompress_istft_var(ptr(s), B, M, ptr(self._get_window(s)), self.n_fft, self.hop_length,
-                                                    tr, fac, e, ptr(lengths), int(max_len), wave.stride(0), ptr(wave),
-                                                    current_stream()), "fdbm_decompress_istft_var")
-        return wave
+        if F != self.n_fft // 2 + 1:
+            raise RuntimeError(f"expected {self.n_fft // 2 + 1} frequency bins, got {F}")
+        alloc = torch.zeros if lengths is not None else torch.empty
+        wave = alloc(B, int(length), dtype=torch.float32, device=s.device)
+        peak = torch.empty(B, dtype=torch.float32, device=s.device) if want_peak else None
+        check(_lib.load().fdbm_decompress_istft_ex(ptr(s), B, M, ptr(self._get_window(s)), self.n_fft, self.hop_length, tr, fac, e,
+                                                   ptr(lengths), int(length), wave.stride(0), ptr(norm), ptr(peak), ptr(wave),
+                                                   current_stream()), "fdbm_decompress_istft_ex")
+        return wave, peak
+
+    def to_audio_var(self, spec: torch.Tensor, lengths: torch.Tensor, max_len: int) -> torch.Tensor:
+        """Variable-length to_audio: [B, F, T] -> [B, max_len], row b valid up to lengths[b] (zeros beyond)."""
+        return self.to_audio_ex(spec, max_len, lengths=lengths)[0]
 
     def to_audio(self, spec: torch.Tensor, length=None) -> torch.Tensor:
         """istft(spec_back(spec), length) in one kernel (fdbm/model.py:376-377)."""
@@ -176,6 +192,7 @@ class SpecsDataModule:
         return self._istft_impl(spec, tr, fac, e, length)
 
     # ---- kernels -------------------------------------------------------------------------------
+    @on_device
     def _stft_impl(self, sig, tr, fac, e, pad_mode, n_frames_out):
         if not sig.is_cuda or sig.dtype != torch.float32:
             raise RuntimeError("fdbm_b200 expects fp32 CUDA waveforms")
@@ -191,6 +208,7 @@ class SpecsDataModule:
                                              current_stream()), "fdbm_stft_compress")
         return spec.reshape(*lead, F, T_out)
 
+    @on_device
     def _istft_impl(self, spec, tr, fac, e, length):
         spec = _as_cfloat(spec)
         F, M = spec.shape[-2], spec.shape[-1]
@@ -207,6 +225,7 @@ class SpecsDataModule:
               "fdbm_decompress_istft")
         return wave.reshape(*lead, length)
 
+    @on_device
     def _spec_transform(self, spec, inverse):
         tr, fac, e = self._transform_args()
         spec = _as_cfloat(spec)

@@ -105,30 +105,35 @@ class EnhancementModel(nn.Module):
         return self.bridge.sampler(self, Y)
 
     @torch.no_grad()
-    def enhance_batch(self, y: torch.Tensor, clip_rescale: Optional[float] = None) -> torch.Tensor:
+    def enhance_batch(self, y: torch.Tensor, clip_rescale: Optional[float] = None, pad_mode: Optional[str] = None) -> torch.Tensor:
         """y fp32 CUDA [B, Ts] (un-normalised) -> enhanced fp32 [B, Ts].  Per utterance exactly the
         arithmetic of infer_single.py:80-99; `clip_rescale` (0.5 there, 0.95 in infer_folder.py:120)
-        applies the optional peak rescale, None skips it as model.py:391-406 does."""
-        if self.data_module.normalize == "noisy":
-            norm = y.abs().amax(dim=1, keepdim=True)
-        elif self.data_module.normalize == "std":
-            norm = y.std(dim=1, keepdim=True)
+        applies the optional peak rescale, None skips it as model.py:391-406 does.  `pad_mode` defaults to the
+        infer scripts' choice (`self.pad_mode`: reflection for exactly 'ncsnpp_v2', zeros otherwise)."""
+        pad_mode = pad_mode or self.pad_mode
+        dm = self.data_module
+        y = y if y.stride(1) == 1 else y.contiguous()
+        # norm_factor per utterance; the division / re-multiplication live inside the STFT / iSTFT kernels
+        if dm.normalize == "noisy":
+            norm = dm.wave_absmax(y)
+        elif dm.normalize == "std":
+            norm = y.std(dim=1).contiguous()
         else:
-            norm = torch.ones(y.shape[0], 1, device=y.device)
-        T_orig = y.shape[1]
-        Y = self.data_module.stft_compress(y / norm, pad_mode=self.pad_mode)
+            norm = None
+        Y = dm.stft_compress(y, pad_mode=pad_mode, norm=norm)
         sample = self._sample(Y)
-        x_hat = self.data_module.to_audio(sample[:, 0], T_orig) * norm
+        x_hat, peak = dm.to_audio_ex(sample[:, 0], y.shape[1], norm=norm, want_peak=clip_rescale is not None)
         if clip_rescale is not None:
-            peak = x_hat.abs().amax(dim=1, keepdim=True)
-            x_hat = torch.where(peak > 1.0, x_hat / peak * clip_rescale, x_hat)
+            dm.clip_rescale_(x_hat, peak, clip_rescale)
         return x_hat
 
     @torch.no_grad()
-    def enhance(self, y: torch.Tensor, **sampler_kwargs) -> np.ndarray:
-        """fdbm/model.py:391-406: y [1, Ts] (any device) -> numpy [Ts]."""
+    def enhance(self, y: torch.Tensor, pad_mode: str = "zero_pad", **sampler_kwargs) -> np.ndarray:
+        """fdbm/model.py:391-406: y [1, Ts] (any device) -> numpy [Ts].  Like `BridgeModel.enhance` (the validation-time
+        path) this pads with `pad_spec`'s default, zeros; the infer scripts' reflection padding for 'ncsnpp_v2'
+        (infer_single.py:64-69) is `pad_mode="reflection"` here and the default of `enhance_batch` / `enhance_list`."""
         dev = next(self.dnn.parameters()).device
-        return self.enhance_batch(y.to(dev, torch.float32)).squeeze(0).cpu().numpy()
+        return self.enhance_batch(y.to(dev, torch.float32), pad_mode=pad_mode).squeeze(0).cpu().numpy()
 
     @torch.no_grad()
     def enhance_many(self, waves: torch.Tensor, micro_batch: int = 8) -> torch.Tensor:
@@ -176,14 +181,13 @@ class EnhancementModel(nn.Module):
                 host[r, :w.numel()] = w
             y = host.to(dev, non_blocking=True)
             lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
-            norm = y.abs().amax(dim=1, keepdim=True)
-            Y = self.data_module.stft_compress_var(y / norm, lengths, min_len, max_len, pad_mode=self.pad_mode,
-                                                   n_frames_out=T_pad)
+            dm = self.data_module
+            norm = dm.wave_absmax(y, lengths)                    # rows are zero-padded beyond their length
+            Y = dm.stft_compress_var(y, lengths, min_len, max_len, pad_mode=self.pad_mode, n_frames_out=T_pad, norm=norm)
             sample = self._sample(Y)
-            x_hat = self.data_module.to_audio_var(sample[:, 0], lengths, max_len) * norm
+            x_hat, peak = dm.to_audio_ex(sample[:, 0], max_len, lengths=lengths, norm=norm, want_peak=clip_rescale is not None)
             if clip_rescale is not None:
-                peak = x_hat.abs().amax(dim=1, keepdim=True)
-                x_hat = torch.where(peak > 1.0, x_hat / peak * clip_rescale, x_hat)
+                dm.clip_rescale_(x_hat, peak, clip_rescale, lengths)
             res = x_hat[:n].cpu().numpy()
             for r, i in enumerate(grp):
                 out[i] = res[r, :lens[r]].copy()

@@ -9,10 +9,17 @@
     Adam + clip + EMA                          fdbm_plan_optimizer_step on the flat buffers, weights re-packed
 
 The loss head and its gradient are one library call (fdbm_hybrid_loss: spectral terms, fused de-compress + iSTFT,
-SI-SNR, iSTFT adjoint through the fused STFT kernel); `hybrid_loss` below is the same loss in torch ops, kept as the
-differentiable reference the tests compare against.  Nothing in the step goes through torch autograd.
+SI-SNR, iSTFT adjoint through the fused STFT kernel).  Nothing in the step goes through torch autograd.
 Gradients of activations are 16-bit GEMM operands, so dL/dD is multiplied by `loss_scale` first (divided out of
-the fp32 parameter gradients); a non-finite gradient norm skips the update (GradScaler semantics).
+the fp32 parameter gradients).  A non-finite gradient norm skips the update on the device: parameters, Adam
+moments, the EMA and the update counter (Adam bias correction, torch_ema's num_updates) stay untouched and a skip
+counter is incremented; `update_loss_scale()` reads that counter every `scale_check_interval` steps, halves the
+loss scale after a skip and doubles it after `scale_growth_interval` clean steps (torch.cuda.amp.GradScaler's rule).
+
+EMA (fdbm/model.py:56,129-160): the shadow parameters follow torch_ema.ExponentialMovingAverage.update with
+use_num_updates=True, decay = min(ema_decay, (1 + n) / (10 + n)); `ema_state_dict()` / `load_ema_state_dict()` use
+torch_ema's state_dict layout (the 'ema' entry of the reference's checkpoints), `swap_in_ema()` / `restore_params()`
+are store + copy_to / restore of model.py:146-160.
 """
 from __future__ import annotations
 
@@ -25,27 +32,7 @@ from . import _lib
 from ._lib import check, current_stream, ptr
 
 
-class _DevBuf:
-    def __init__(self, pointer: int, n: int):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<f4", "data": (pointer, False), "version": 2}
-
-
-def hybrid_loss(x_hat: torch.Tensor, x: torch.Tensor, data_module) -> torch.Tensor:
-    """fdbm/model.py:187-218 (`data_prediction_hybrid`, pesq_weight = 0) with torch ops (differentiable)."""
-    B, Cc, F, T = x.shape
-    x_nc = data_module.spec_back_torch(x)
-    x_hat_nc = data_module.spec_back_torch(x_hat)
-    x_mag = torch.abs(x_nc + 1e-12)
-    x_hat_mag = torch.abs(x_hat_nc + 1e-12)
-    losses_mag = torch.mean(torch.square(x_mag.pow(0.3) - x_hat_mag.pow(0.3)))
-    losses_ri = torch.square(torch.norm(x_nc / x_mag.pow(0.7) - x_hat_nc / x_hat_mag.pow(0.7), p=2)) / (B * Cc * F * T)
-    x_hat_td = data_module.istft_torch(x_hat_nc.squeeze(1))
-    x_td = data_module.istft_torch(x_nc.squeeze(1))
-    x_td_norm = torch.sum(x_td * x_hat_td, dim=-1, keepdim=True) * x_td / (torch.sum(x_td.pow(2), dim=-1, keepdim=True) + 1e-12)
-    sisnr = torch.log10((torch.sum(x_td_norm.pow(2), dim=-1, keepdim=True) /
-                         (torch.sum((x_hat_td - x_td_norm).pow(2), dim=-1, keepdim=True) + 1e-12)).clamp(min=1e-12)).mean()
-    return 70 * losses_mag + 30 * losses_ri - sisnr
-
+from .backbones import _DevBuf
 
 def allreduce_gradients_(flat_grads: torch.Tensor, group=None) -> int:
     """DDP gradient exchange (fdbm/model.py trains under Lightning DDP): ONE all-reduce(sum) of the flat gradient buffer
@@ -60,32 +47,55 @@ def allreduce_gradients_(flat_grads: torch.Tensor, group=None) -> int:
     return world
 
 
+def _on_plan_device(fn):
+    """Run a TrainStep method with the plan's device current (the library works on the current device)."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(self, *a, **k):
+        dev = self.device
+        if dev.index == torch.cuda.current_device():
+            return fn(self, *a, **k)
+        with torch.cuda.device(dev):
+            return fn(self, *a, **k)
+    return wrapper
+
+
 class TrainStep:
     """One data-parallel optimisation step; `dnn` is the fdbm_b200 NCSNpp_v2 whose parameters are trained."""
 
     def __init__(self, dnn, bridge, data_module, batch: int, n_frames: int = 256, lr: float = 1e-4, ema_decay: float = 0.999,
-                 clip_norm: float = 3.0, t_eps: float = 0.03, loss_scale: float = 4096.0, betas=(0.9, 0.999), eps: float = 1e-8):
+                 clip_norm: float = 3.0, t_eps: float = 0.03, loss_scale: float = 4096.0, betas=(0.9, 0.999), eps: float = 1e-8,
+                 ema_warmup: bool = True, dynamic_loss_scale: bool = True, scale_check_interval: int = 50,
+                 scale_growth_interval: int = 2000):
         self.dnn, self.bridge, self.dm = dnn, bridge, data_module
         self.batch, self.n_frames = batch, n_frames
         self.lr, self.ema_decay, self.clip_norm, self.t_eps, self.loss_scale = lr, ema_decay, clip_norm, t_eps, loss_scale
         self.betas, self.eps = betas, eps
-        self.step_count = 0
+        self.ema_warmup = ema_warmup                    # torch_ema's use_num_updates=True (what the reference constructs)
+        self.dynamic_loss_scale = dynamic_loss_scale
+        self.scale_check_interval, self.scale_growth_interval = scale_check_interval, scale_growth_interval
+        self.steps_issued = 0                           # optimizer_step() calls, applied or skipped
+        self._seen_skipped, self._clean_since = 0, 0
         self.lib = _lib.load()
         dev = next(dnn.parameters()).device
         if dev.type != "cuda":
             raise RuntimeError("TrainStep needs the backbone on a CUDA device (there is no CPU path)")
         self.device = dev
-        handle = C.c_void_p()
-        arch = dnn._arch()
-        check(self.lib.fdbm_plan_create_train(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create_train")
-        self.plan = handle
-        self._load_from_module()
-        p, g, e, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
-        check(self.lib.fdbm_plan_buffers(self.plan, C.byref(p), C.byref(g), C.byref(e), C.byref(n)), "fdbm_plan_buffers")
-        self.numel = n.value
-        self.flat_params = torch.as_tensor(_DevBuf(p.value, n.value), device=dev)
-        self.flat_grads = torch.as_tensor(_DevBuf(g.value, n.value), device=dev)
-        self.broadcast_parameters()
+        with torch.cuda.device(dev):
+            handle = C.c_void_p()
+            arch = dnn._arch()
+            check(self.lib.fdbm_plan_create_train(C.byref(arch), batch, n_frames, C.byref(handle)), "fdbm_plan_create_train")
+            self.plan = handle
+            self._load_from_module()
+            p, g, e, n = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_int64()
+            check(self.lib.fdbm_plan_buffers(self.plan, C.byref(p), C.byref(g), C.byref(e), C.byref(n)), "fdbm_plan_buffers")
+            self.numel = n.value
+            self.flat_params = torch.as_tensor(_DevBuf(p.value, n.value), device=dev)
+            self.flat_grads = torch.as_tensor(_DevBuf(g.value, n.value), device=dev)
+            self.flat_ema = torch.as_tensor(_DevBuf(e.value, n.value), device=dev)
+            self.broadcast_parameters()
+            check(self.lib.fdbm_plan_reset_optimizer(self.plan, current_stream()), "fdbm_plan_reset_optimizer")   # EMA <- params
 
     def broadcast_parameters(self, src: int = 0):
         """DDP start-up semantics: every replica starts from rank `src`'s parameters."""
@@ -145,6 +155,64 @@ class TrainStep:
                 p.copy_(self.flat_params[off:off + n].view(p.shape))
         self.dnn.invalidate_weights()
 
+    # ---- EMA (fdbm/model.py:56, 129-160; torch_ema.ExponentialMovingAverage) ------------------------------------------
+    def ema_params(self) -> Dict[str, torch.Tensor]:
+        """The EMA shadow of every parameter, by reference-style name (views into the plan's flat EMA buffer)."""
+        out = {}
+        for name, p in self.dnn.named_parameters():
+            off, n = self._slot(name)
+            out[name] = self.flat_ema[off:off + n].view(p.shape)
+        return out
+
+    def optimizer_state(self) -> Dict[str, float]:
+        """{'applied', 'skipped', 'grad_norm'} read from the device (synchronises the stream)."""
+        buf = (C.c_double * 4)()
+        check(self.lib.fdbm_plan_optimizer_state(self.plan, buf, current_stream()), "fdbm_plan_optimizer_state")
+        return {"applied": int(buf[0]), "skipped": int(buf[1]), "grad_norm": float(buf[2])}
+
+    def ema_state_dict(self) -> dict:
+        """torch_ema.ExponentialMovingAverage.state_dict() layout: what on_save_checkpoint stores under 'ema'
+        (model.py:143-144).  shadow_params lists the requires_grad parameters in `parameters()` order."""
+        st = self.optimizer_state()
+        shadow = [self.ema_params()[n].clone() for n, p in self.dnn.named_parameters() if p.requires_grad]
+        return {"decay": self.ema_decay, "num_updates": st["applied"] if self.ema_warmup else None,
+                "shadow_params": shadow, "collected_params": None}
+
+    def load_ema_state_dict(self, state: dict):
+        """model.py:134-141 on_load_checkpoint."""
+        self.ema_decay = float(state["decay"])
+        names = [n for n, p in self.dnn.named_parameters() if p.requires_grad]
+        if len(names) != len(state["shadow_params"]):
+            raise RuntimeError(f"EMA state has {len(state['shadow_params'])} shadow tensors, the backbone {len(names)} trainable ones")
+        dst = self.ema_params()
+        with torch.no_grad():
+            for n, s in zip(names, state["shadow_params"]):
+                dst[n].copy_(s.to(self.device, torch.float32))
+        if state.get("num_updates") is not None:
+            st = self.optimizer_state()
+            check(self.lib.fdbm_plan_set_optimizer_state(self.plan, float(state["num_updates"]), float(st["skipped"]), current_stream()),
+                  "fdbm_plan_set_optimizer_state")
+
+    def swap_in_ema(self):
+        """eval(): ema.store(parameters) + ema.copy_to(parameters) (model.py:149-152); packed weights rebuilt."""
+        check(self.lib.fdbm_plan_swap_ema(self.plan, 1, current_stream()), "fdbm_plan_swap_ema")
+
+    def restore_params(self):
+        """train(): ema.restore(parameters) (model.py:154-156)."""
+        check(self.lib.fdbm_plan_swap_ema(self.plan, 0, current_stream()), "fdbm_plan_swap_ema")
+
+    def update_loss_scale(self):
+        """GradScaler's rule on the device-side skip counter: halve after a skipped step, double after
+        `scale_growth_interval` consecutive applied steps.  Costs one 32-byte read-back (a stream sync)."""
+        st = self.optimizer_state()
+        if st["skipped"] > self._seen_skipped:
+            self.loss_scale = max(self.loss_scale * 0.5 ** (st["skipped"] - self._seen_skipped), 1.0)
+            self._seen_skipped, self._clean_since = st["skipped"], st["applied"]
+        elif st["applied"] - self._clean_since >= self.scale_growth_interval:
+            self.loss_scale = min(self.loss_scale * 2.0, 65536.0)
+            self._clean_since = st["applied"]
+        return self.loss_scale
+
     def sample_prior(self, x, y, t=None, z=None):
         """fdbm/model.py:267-275."""
         if z is None:
@@ -197,11 +265,19 @@ class TrainStep:
     def optimizer_step(self):
         """DDP gradient all-reduce (mean) over the flat buffer, then Adam + clip + EMA and the weight re-pack."""
         world = allreduce_gradients_(self.flat_grads)            # sum over ranks; the mean's 1/world goes into grad_div
-        self.step_count += 1
+        self.steps_issued += 1
+        # step = 0: Adam's bias correction and the EMA warm-up use the device-side count of APPLIED steps
         check(self.lib.fdbm_plan_optimizer_step(self.plan, float(world), self.clip_norm, self.lr, self.betas[0], self.betas[1], self.eps,
-                                                self.step_count, self.ema_decay, current_stream()), "fdbm_plan_optimizer_step")
+                                                0, self.ema_decay, int(self.ema_warmup), current_stream()), "fdbm_plan_optimizer_step")
+        if self.dynamic_loss_scale and self.steps_issued % self.scale_check_interval == 0:
+            self.update_loss_scale()
 
     def training_step(self, x, y) -> torch.Tensor:
         loss = self.loss_and_backward(x, y)
         self.optimizer_step()
         return loss
+
+
+for _name in ("broadcast_parameters", "close", "optimizer_state", "load_ema_state_dict", "swap_in_ema", "restore_params",
+              "update_loss_scale", "forward", "backward", "loss_and_backward", "loss_and_grad", "optimizer_step", "training_step"):
+    setattr(TrainStep, _name, _on_plan_device(getattr(TrainStep, _name)))

@@ -62,7 +62,7 @@ def test_sampler_golden_T64(nets, golden_dir, path, st):
     from fdbm_b200 import Bridge, SpecsDataModule
     g = load_npz(f"{golden_dir}/bridge_T64.npz")
     Y = torch.from_numpy(g["Y"]).cuda()
-    br = Bridge(path, N=5, sampler_type=st)
+    br = Bridge(path, N=5, sampler_type=st, match_torch_rng=True)     # replay the reference's draws incl. the discarded SB prior draw
     noise = torch.from_numpy(g[f"noise_{path}_{st}"]).cuda() if f"noise_{path}_{st}" in g else None
     if noise is not None:                                          # replay the reference's noise draws
         seq = iter(list(noise))
@@ -81,12 +81,13 @@ def test_sampler_golden_T64(nets, golden_dir, path, st):
     wref = g[f"wave_{path}_{st}"].reshape(-1)
     sdr = O.si_sdr(wref, w)
     print(f"sampler {path}/{st}: spec rel L2 {err:.3e}, SI-SDR(new vs ref) {sdr:.1f} dB")
-    # Five passes through a RANDOM-weight (non-contractive) network amplify any perturbation: the fp32
-    # oracle vs the fp32 reference already differ 4x (sb/sde), 6x (sb/ode) and 22x (fm/ode) more after the
-    # loop than after one forward (oracle/make_golden.py output).  Bounds = amplification x one-pass bound.
-    # fm/ode_ei starts from pure noise: 22 x the measured one-pass error (2.0-2.5e-3 = the noise floor of 11-bit operands
-    # through ~100 layers; WHICH rounding realisation one gets moves the looped result by +-50%) = 4.4-5.5e-2.
-    bound = {("sb", "ode_ei"): 2 * TOL_BF16, ("sb", "sde_ei"): 4 * TOL_BF16, ("fm", "ode_ei"): 12 * TOL_BF16}[(path, st)]
+    # Five passes through a RANDOM-weight (non-contractive) network amplify any rounding; the bound is the north-star
+    # 5e-3 wherever the REFERENCE's own TF32 run (its default GPU precision) meets it and twice the reference's own
+    # TF32-vs-fp32 deviation where it does not (tests/golden/ref_tf32_deviation.json, see tests/test_gpu_parity.py).
+    import json
+    dev = json.load(open(f"{golden_dir}/ref_tf32_deviation.json"))
+    bound = max(TOL_BF16, 2.0 * dev[f"sampler_{path}_{st}_N5_T64"])
+    print(f"   bound {bound:.2e} (reference TF32 deviation {dev[f'sampler_{path}_{st}_N5_T64']:.3e})")
     assert err < bound
     assert sdr > (20.0 if path == "fm" else 30.0)
 
@@ -160,7 +161,7 @@ def test_enhance_si_sdr_matches_oracle(nets):
     rng = np.random.default_rng(0)
     for utt in (3, 4, 5, 6):
         clean, noisy = O.synth_pair(utt, n_samples=16000)
-        got = model.enhance(noisy[None])
+        got = model.enhance(noisy[None], pad_mode="reflection")
         with torch.no_grad():
             ref = O.enhance(noisy[None], lambda a, b, c: O.ncsnpp_forward(sd, cfg, a, b, c), ob, O.SpecConfig()).numpy()
         c = clean.numpy()
@@ -195,7 +196,7 @@ def test_enhance_list_variable_lengths(nets, tmp_path):
     got = model.enhance_list(noisy, micro_batch=2, clip_rescale=None)
     assert [g.shape[0] for g in got] == lens
     for i, w in enumerate(noisy):
-        single = model.enhance(w[None])
+        single = model.enhance(w[None], pad_mode="reflection")
         d = float(np.abs(got[i] - single).max()) / float(np.abs(single).max())
         print(f"variable-length batch vs per-file, {lens[i]} samples: max rel diff {d:.2e}")
         assert d < 1e-5

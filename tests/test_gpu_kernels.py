@@ -110,6 +110,70 @@ def test_hop128_and_log_transform(lib):
 # ------------------------------------------------------------------------------------------------
 # bridge arithmetic
 # ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("n_samples", [16000, 16001, 64000, 5000, 70001])
+def test_stft_istft_various_lengths_vs_oracle(lib, n_samples):
+    """Frame counts that are odd / even / not multiples of the 16-frame block, every pad mode, batch 3: the fused kernels
+    against the oracle (data_module.py:173-229, other.py:76-90); iSTFT round trip reproduces the waveform."""
+    import fdbm_oracle as O
+    from fdbm_b200 import SpecsDataModule
+    sc = O.SpecConfig()
+    g = torch.Generator().manual_seed(n_samples)
+    x = torch.randn(3, n_samples, generator=g) * torch.tensor([1.0, 0.03, 7.0])[:, None]
+    dm = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    S = dm.stft(x.cuda())
+    want = O.stft(x, sc)
+    assert S.shape == want.shape and rel_l2(S, want) < 2e-6
+    for mode in ("zero_pad", "reflection", "replication"):
+        got = dm.stft_compress(x.cuda(), pad_mode=mode)
+        ref = O.pad_spec(O.spec_fwd(want, sc)[:, None], mode)
+        assert got.shape == ref.shape and rel_l2(got, ref) < 2e-6, mode
+        if mode == "zero_pad" and ref.shape[-1] > want.shape[-1]:
+            assert float(got[..., want.shape[-1]:].abs().max()) == 0.0            # pad frames are exact zeros
+    back = dm.to_audio(got[:, 0], n_samples)
+    ref_back = O.istft(O.spec_back(ref[:, 0], sc), sc, n_samples)
+    assert rel_l2(back, ref_back) < 3e-6
+    y = dm.istft(S, n_samples)
+    assert rel_l2(y, x) < 3e-6
+
+
+def test_fused_normalise_rescale_clip(lib):
+    """The elementwise glue of `enhance` folded into the kernels (infer_single.py:83-97, infer_folder.py:119-120): peak
+    normalisation inside the STFT, `* norm` and the peak of the result inside the iSTFT, the clip rule as one kernel --
+    against the reference's op sequence in torch, fixed- and variable-length batches."""
+    import fdbm_oracle as O
+    from fdbm_b200 import SpecsDataModule
+    sc = O.SpecConfig()
+    g = torch.Generator().manual_seed(11)
+    lens = [40000, 33333, 25601, 40000]
+    x = torch.zeros(4, 40000)
+    for i, n in enumerate(lens):
+        x[i, :n] = torch.randn(n, generator=g) * (0.2 + 3 * i)
+    dm = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    xd = x.cuda()
+    lengths = torch.tensor(lens, dtype=torch.int32, device="cuda")
+    norm = dm.wave_absmax(xd, lengths)
+    assert torch.equal(norm.cpu(), x.abs().amax(1))
+    assert torch.equal(dm.wave_absmax(xd).cpu(), x.abs().amax(1))
+    Y = dm.stft_compress_var(xd, lengths, min(lens), max(lens), pad_mode="reflection", norm=norm)
+    for i, n in enumerate(lens):
+        yi = x[i:i + 1, :n] / x[i, :n].abs().max()
+        ref = O.pad_spec(O.spec_fwd(O.stft(yi, sc), sc)[:, None], "reflection")
+        T = ref.shape[-1]
+        assert rel_l2(Y[i:i + 1, ..., :T], ref) < 2e-6, i
+    # inverse with rescale + peak, then the clip rule
+    spec = Y[:, 0] * 1.7                                             # push some rows above |x| = 1 after the rescale
+    wave, peak = dm.to_audio_ex(spec, max(lens), lengths=lengths, norm=norm, want_peak=True)
+    plain = dm.to_audio_var(spec, lengths, max(lens))
+    want = plain * norm[:, None]
+    assert rel_l2(wave, want) < 1e-6
+    for i, n in enumerate(lens):
+        assert float(wave[i, n:].abs().max() if n < max(lens) else 0.0) == 0.0
+    assert torch.allclose(peak, wave.abs().amax(1), rtol=0, atol=0)
+    clipped = dm.clip_rescale_(wave.clone(), peak, 0.95, lengths)
+    ref_clip = torch.where(peak[:, None] > 1.0, wave / peak[:, None] * 0.95, wave)
+    assert float(peak.max()) > 1.0 and torch.equal(clipped, ref_clip)
+
+
 def test_bridge_step_bit_exact(lib):
     g = torch.Generator().manual_seed(1)
     shape = (2, 1, 257, 64)

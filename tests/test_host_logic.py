@@ -34,8 +34,18 @@ def test_bridge_api_surface():
     assert (f.start_time, f.end_time, f.path.sampling_direction) == (1e-4, 1.0, "forward")
     b.N, b.sampler_type = 10, "sde_ei"                       # infer_single.py:55-56 mutates these after construction
     assert b.coefficient_table().shape == (10, 3) and float(b.coefficient_table()[-1, 2]) == 0.0
-    with pytest.raises(NotImplementedError):
-        Bridge("sb", sampler_type="pc").sampler(None, None)
+    with pytest.raises(ValueError):                          # the default predictor 'reverse_diffusion' is unregistered, as in
+        Bridge("sb", sampler_type="pc").sampler(None, None)  # the reference (util/predictors.py registers euler_maruyama, none)
+    with pytest.raises(ValueError):
+        Bridge("sb", sampler_type="pc").sampler(None, None, predictor_name="euler_maruyama", corrector_name="bogus")
+    assert Bridge("sb", sampler_type="bogus").sampler(None, None) is None      # bridge.py:56-64 falls through
+    p = Bridge("sb", noise_schedule="ve").path
+    t = torch.tensor([0.4])
+    wx, ws, wy = p.ode_weights(t); sx, ss, sy, gd = p.sde_weights(t)
+    ox = O.PathSB(noise_schedule="ve")
+    one = torch.ones(1, 1, 1, 1)
+    assert torch.allclose(ox.ode(t, one, 0 * one, 0 * one).reshape(-1), wx) and torch.allclose(ox.ode(t, 0 * one, one, 0 * one).reshape(-1), ws)
+    assert torch.allclose(ox.sde(t, 0 * one, 0 * one, one)[0].reshape(-1), sy) and torch.allclose(ox.sde(t, one, one, one)[1], gd)
     with pytest.raises(ValueError):
         Bridge("nope")
     s = torch.randn(2, 1, 3, 4, dtype=torch.complex64); y = torch.randn(2, 1, 3, 4, dtype=torch.complex64)
@@ -184,3 +194,25 @@ def test_length_buckets_group_only_equal_padded_lengths():
         assert [lens[i] for i in g] == sorted(lens[i] for i in g)
     assert [T for T, _ in b] == sorted(T for T, _ in b)
     assert padded_frames(251) == 256 and padded_frames(256) == 256 and padded_frames(257) == 320
+
+
+def test_rk45_tableau_is_dormand_prince():
+    """The constants fdbm_b200.rk45 integrates with are scipy's RK45 tableau (consistency conditions + scipy itself)."""
+    from fdbm_b200 import rk45
+    from scipy.integrate import RK45
+    import numpy as np
+    for s, row in enumerate(rk45._A):
+        assert abs(sum(row) - rk45._C[s]) < 1e-15
+        assert np.allclose(row, RK45.A[s][:s])
+    assert np.allclose(rk45._B, RK45.B) and np.allclose(rk45._C, RK45.C) and np.allclose(rk45._E, RK45.E)
+    assert abs(sum(rk45._B) - 1) < 1e-15 and abs(sum(rk45._E)) < 1e-15
+    assert (rk45.SAFETY, rk45.MIN_FACTOR, rk45.MAX_FACTOR) == (0.9, 0.2, 10.0) and rk45.ERR_EXP == RK45.error_exponent if hasattr(RK45, "error_exponent") else True
+
+
+def test_on_device_rejects_mixed_devices_and_passes_cpu_through():
+    from fdbm_b200._lib import on_device
+
+    @on_device
+    def f(a, b=None):
+        return "ran"
+    assert f(torch.zeros(1), b=torch.zeros(1)) == "ran" and f(None) == "ran"
