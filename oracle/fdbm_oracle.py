@@ -835,3 +835,204 @@ def enhance(y: Tensor, model: Callable, bridge: Optional[Bridge], spec_cfg: Spec
         sample = bridge.sampler(model, Y, z0=z0, zs=zs)
     x_hat = istft(spec_back(sample.squeeze(), spec_cfg), spec_cfg, T_orig)
     return x_hat * norm
+
+
+# ----------------------------------------------------------------------------------------------
+# 5. TF-GridNet backbones (functional, from a flat state_dict)
+#    fdbm/backbones/tfgridnet.py:126-229 (TFGridNet), :236-427 (GridNetV3Block), :430-484 (LayerNormalization,
+#    AllHeadPReLULayerNormalization4DC); tfgridnet_predictive.py (2 input channels, no time embedding)
+# ----------------------------------------------------------------------------------------------
+
+@dataclass
+class TFGridNetConfig:
+    """tfgridnet_5l32c100 (tfgridnet.py:487-497) by default; tfgridnet_4l32c80 = (4, 32, 80)."""
+    n_layers: int = 5
+    emb_dim: int = 32
+    lstm_hidden_units: int = 100
+    attn_n_head: int = 4
+    attn_qk_output_channel: int = 2
+    emb_ks: int = 4
+    emb_hs: int = 1
+    eps: float = 1.0e-5
+    fourier_scale: float = 16.0
+    predictive: bool = False           # tfgridnet_5l32c100_predictive: forward(y), no time embedding
+
+    @property
+    def in_channels(self):
+        return 2 if self.predictive else 4
+
+
+def tfgridnet_param_shapes(cfg: TFGridNetConfig) -> Dict[str, Tuple[int, ...]]:
+    """state_dict key -> shape of the reference module (tfgridnet.py:143-192, 241-317)."""
+    C, H, I, nh, E = cfg.emb_dim, cfg.lstm_hidden_units, cfg.emb_ks, cfg.attn_n_head, cfg.attn_qk_output_channel
+    out: Dict[str, Tuple[int, ...]] = {
+        "conv.0.weight": (C, cfg.in_channels, 3, 3), "conv.0.bias": (C,), "conv.1.weight": (C,), "conv.1.bias": (C,)}
+    for b in range(cfg.n_layers):
+        p = f"blocks.{b}."
+        for name in ("intra", "inter"):
+            out[p + f"{name}_norm.weight"] = (C,); out[p + f"{name}_norm.bias"] = (C,)
+            for sfx in ("", "_reverse"):
+                out[p + f"{name}_rnn.weight_ih_l0{sfx}"] = (4 * H, C * I)
+                out[p + f"{name}_rnn.weight_hh_l0{sfx}"] = (4 * H, H)
+                out[p + f"{name}_rnn.bias_ih_l0{sfx}"] = (4 * H,)
+                out[p + f"{name}_rnn.bias_hh_l0{sfx}"] = (4 * H,)
+            out[p + f"{name}_linear.weight"] = (2 * H, C, I); out[p + f"{name}_linear.bias"] = (C,)
+        for name, ch in (("Q", nh * E), ("K", nh * E), ("V", C)):
+            out[p + f"attn_conv_{name}.weight"] = (ch, C, 1, 1); out[p + f"attn_conv_{name}.bias"] = (ch,)
+            out[p + f"attn_norm_{name}.gamma"] = (1, nh, ch // nh, 1, 1); out[p + f"attn_norm_{name}.beta"] = (1, nh, ch // nh, 1, 1)
+            out[p + f"attn_norm_{name}.act.weight"] = (nh,)
+        out[p + "attn_concat_proj.0.weight"] = (C, C, 1, 1); out[p + "attn_concat_proj.0.bias"] = (C,)
+        out[p + "attn_concat_proj.1.weight"] = (1,)
+        out[p + "attn_concat_proj.2.gamma"] = (1, C, 1, 1); out[p + "attn_concat_proj.2.beta"] = (1, C, 1, 1)
+    out["deconv.weight"] = (C, 2, 3, 3); out["deconv.bias"] = (2,)
+    if not cfg.predictive:
+        out["get_time_emb.W"] = (C,)
+        out["time_emb_fc.0.weight"] = (4 * C, 2 * C); out["time_emb_fc.0.bias"] = (4 * C,)
+        out["time_emb_fc.2.weight"] = (4 * C, 4 * C); out["time_emb_fc.2.bias"] = (4 * C,)
+        for b in range(cfg.n_layers):
+            out[f"time_emb_blocks.{b}.weight"] = (C, 4 * C); out[f"time_emb_blocks.{b}.bias"] = (C,)
+    return out
+
+
+def tfgridnet_state_dict(cfg: TFGridNetConfig, seed: int = 0) -> Dict[str, Tensor]:
+    """Deterministic random weights with the reference's own scales (PyTorch default initialisation: uniform
+    +-1/sqrt(fan_in) for conv / linear / LSTM), norm affine 1 + N(0, 0.1) / N(0, 0.1), PReLU slopes 0.25 + N(0, 0.05).
+    Nothing in TF-GridNet is zero-initialised, so no 'sensitising' is needed; a fixed draw keeps goldens reproducible."""
+    sd: Dict[str, Tensor] = {}
+    for name, shape in tfgridnet_param_shapes(cfg).items():
+        g = torch.Generator().manual_seed((seed * 1000003 + zlib.crc32(("tfg." + name).encode())) % (2 ** 31))
+        if name == "get_time_emb.W":
+            t = torch.randn(shape, generator=g) * cfg.fourier_scale
+        elif "norm" in name or name.startswith("conv.1.") or name.endswith((".gamma", ".beta")):
+            if name.endswith("act.weight"):
+                t = 0.25 + 0.05 * torch.randn(shape, generator=g)
+            else:
+                is_scale = name.endswith(("weight", "gamma"))
+                t = torch.randn(shape, generator=g) * 0.1 + (1.0 if is_scale else 0.0)
+        elif name.endswith("attn_concat_proj.1.weight"):
+            t = 0.25 + 0.05 * torch.randn(shape, generator=g)
+        else:
+            if "rnn" in name:
+                fan = cfg.lstm_hidden_units
+            elif name.endswith("_linear.weight") or name.endswith("_linear.bias"):
+                fan = cfg.emb_dim * cfg.emb_ks                        # ConvTranspose1d: weight.size(1) * kernel
+            elif name.startswith("deconv"):
+                fan = 2 * 9
+            else:
+                w = shape if len(shape) > 1 else tfgridnet_param_shapes(cfg)[name.replace("bias", "weight")]
+                fan = int(np.prod(w[1:]))
+            t = (torch.rand(shape, generator=g) * 2 - 1) / math.sqrt(fan)
+        sd[name] = t.float()
+    return sd
+
+
+def _lstm_direction(x: Tensor, w_ih: Tensor, w_hh: Tensor, b_ih: Tensor, b_hh: Tensor, reverse: bool) -> Tensor:
+    """One direction of nn.LSTM (batch_first): gates in PyTorch's order i, f, g, o.  x [N, L, In] -> [N, L, H]."""
+    N, L, _ = x.shape
+    H = w_hh.shape[1]
+    xp = _rnd(x, "matmul") @ _rnd(w_ih, "matmul").t() + (b_ih + b_hh)
+    h = torch.zeros(N, H); c = torch.zeros(N, H)
+    out = torch.empty(N, L, H)
+    steps = range(L - 1, -1, -1) if reverse else range(L)
+    whh_t = _rnd(w_hh, "matmul").t()
+    for s in steps:
+        gates = xp[:, s] + _rnd(h, "matmul") @ whh_t
+        i, f, g, o = gates.chunk(4, dim=1)
+        c = torch.sigmoid(f) * c + torch.sigmoid(i) * torch.tanh(g)
+        h = torch.sigmoid(o) * torch.tanh(c)
+        out[:, s] = h
+    return out
+
+
+def _bilstm(x: Tensor, sd, p: str) -> Tensor:
+    fw = _lstm_direction(x, sd[p + "weight_ih_l0"], sd[p + "weight_hh_l0"], sd[p + "bias_ih_l0"], sd[p + "bias_hh_l0"], False)
+    bw = _lstm_direction(x, sd[p + "weight_ih_l0_reverse"], sd[p + "weight_hh_l0_reverse"], sd[p + "bias_ih_l0_reverse"],
+                         sd[p + "bias_hh_l0_reverse"], True)
+    return torch.cat([fw, bw], dim=-1)
+
+
+def _rnn_path(x: Tensor, sd, p: str, name: str, cfg: TFGridNetConfig) -> Tensor:
+    """tfgridnet.py:335-352 (intra) / :360-377 (inter) for emb_ks != emb_hs: LayerNorm over channels, unfold emb_ks
+    neighbouring positions (stride emb_hs) into one LSTM input, BiLSTM, ConvTranspose1d back, residual.  x [B, S, L, C]
+    (S independent sequences of length L) -> same shape."""
+    B, S, L, C = x.shape
+    I, hs = cfg.emb_ks, cfg.emb_hs
+    h = F.layer_norm(x, (C,), sd[p + name + "_norm.weight"], sd[p + name + "_norm.bias"], cfg.eps)
+    h = h.reshape(B * S, L, C).transpose(1, 2)                                    # [BS, C, L]
+    h = F.unfold(h[..., None], (I, 1), stride=(hs, 1)).transpose(1, 2)              # [BS, L', C*I], feature = c * I + i
+    h = _bilstm(h, sd, p + name + "_rnn.")                                         # [BS, L', 2H]
+    h = F.conv_transpose1d(_rnd(h.transpose(1, 2), "matmul"), _rnd(sd[p + name + "_linear.weight"], "matmul"),
+                           sd[p + name + "_linear.bias"], stride=hs)               # [BS, C, L]
+    return h.reshape(B, S, C, L).transpose(-2, -1) + x
+
+
+def _allhead_prelu_ln(x: Tensor, sd, p: str, nh: int, eps: float) -> Tensor:
+    """AllHeadPReLULayerNormalization4DC (tfgridnet.py:458-484): per-head PReLU, then normalisation over the E channels of each
+    head at every (t, f) -- stat_dim = (2,) -- with a [1,H,E,1,1] affine.  x [B, H*E, T, F] -> [B, H, E, T, F]."""
+    B, HE, T, Fq = x.shape
+    x = x.view(B, nh, HE // nh, T, Fq)
+    a = sd[p + "act.weight"].view(1, nh, 1, 1, 1)
+    x = torch.where(x >= 0, x, a * x)
+    mu = x.mean(dim=2, keepdim=True)
+    std = torch.sqrt(x.var(dim=2, unbiased=False, keepdim=True) + eps)
+    return ((x - mu) / std) * sd[p + "gamma"] + sd[p + "beta"]
+
+
+def _gridnet_block(x: Tensor, sd, p: str, cfg: TFGridNetConfig) -> Tensor:
+    """GridNetV3Block.forward (tfgridnet.py:319-427).  x [B, C, T, Q] -> same."""
+    B, C, old_T, old_Q = x.shape
+    I, hs, nh = cfg.emb_ks, cfg.emb_hs, cfg.attn_n_head
+    olp = I - hs
+    T = math.ceil((old_T + 2 * olp - I) / hs) * hs + I
+    Q = math.ceil((old_Q + 2 * olp - I) / hs) * hs + I
+    h = F.pad(x.permute(0, 2, 3, 1), (0, 0, olp, Q - old_Q - olp, olp, T - old_T - olp))     # [B, T, Q, C]
+    h = _rnn_path(h, sd, p, "intra", cfg)                                         # sequences along Q for every (b, t)
+    h = _rnn_path(h.transpose(1, 2), sd, p, "inter", cfg)                         # [B, Q, T, C]: sequences along T
+    inter = h.permute(0, 3, 2, 1)[..., olp:olp + old_T, olp:olp + old_Q]           # [B, C, T, Q]
+    return _gridnet_attention(inter, sd, p, cfg)
+
+
+def _gridnet_attention(inter: Tensor, sd, p: str, cfg: TFGridNetConfig) -> Tensor:
+    """The full-band self-attention half of GridNetV3Block.forward (tfgridnet.py:383-427).  inter [B, C, T, Q] -> same."""
+    B, C, old_T, old_Q = inter.shape
+    nh = cfg.attn_n_head
+    q = _allhead_prelu_ln(_conv2d(inter, sd[p + "attn_conv_Q.weight"], sd[p + "attn_conv_Q.bias"]), sd, p + "attn_norm_Q.", nh, cfg.eps)
+    k = _allhead_prelu_ln(_conv2d(inter, sd[p + "attn_conv_K.weight"], sd[p + "attn_conv_K.bias"]), sd, p + "attn_norm_K.", nh, cfg.eps)
+    v = _allhead_prelu_ln(_conv2d(inter, sd[p + "attn_conv_V.weight"], sd[p + "attn_conv_V.bias"]), sd, p + "attn_norm_V.", nh, cfg.eps)
+    q = q.reshape(B * nh, -1, old_T, old_Q).transpose(1, 2).flatten(start_dim=2)    # [B', T, E*Q]
+    k = k.reshape(B * nh, -1, old_T, old_Q).transpose(2, 3).contiguous().view(B * nh, -1, old_T)   # [B', E*Q, T]
+    v = v.reshape(B * nh, -1, old_T, old_Q).transpose(1, 2)                         # [B', T, C/nh, Q]
+    vshape = v.shape
+    v = v.flatten(start_dim=2)
+    att = F.softmax(torch.matmul(_rnd(q, "matmul"), _rnd(k, "matmul")) / (q.shape[-1] ** 0.5), dim=2)
+    o = torch.matmul(_rnd(att, "matmul"), _rnd(v, "matmul")).reshape(vshape).transpose(1, 2)     # [B', C/nh, T, Q]
+    o = o.contiguous().view(B, C, old_T, old_Q)
+    o = _conv2d(o, sd[p + "attn_concat_proj.0.weight"], sd[p + "attn_concat_proj.0.bias"])
+    o = torch.where(o >= 0, o, sd[p + "attn_concat_proj.1.weight"] * o)
+    mu = o.mean(dim=1, keepdim=True)
+    std = torch.sqrt(o.var(dim=1, unbiased=False, keepdim=True) + cfg.eps)
+    o = ((o - mu) / std) * sd[p + "attn_concat_proj.2.gamma"] + sd[p + "attn_concat_proj.2.beta"]
+    return o + inter
+
+
+def tfgridnet_forward(sd: Dict[str, Tensor], cfg: TFGridNetConfig, x: Tensor, y: Optional[Tensor] = None,
+                      t: Optional[Tensor] = None) -> Tensor:
+    """TFGridNet.forward (tfgridnet.py:194-229; tfgridnet_predictive.py:173-200 when cfg.predictive: forward(y)).
+    x, y complex64 [B,1,F,T]; t fp32 [B] -> complex64 [B,1,F,T]."""
+    if cfg.predictive:
+        inp = torch.cat((x.real, x.imag), dim=1)
+    else:
+        inp = torch.cat((x.real, x.imag, y.real, y.imag), dim=1)
+        proj = torch.log(t)[:, None] * sd["get_time_emb.W"][None, :] * 2 * np.pi
+        temb = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
+        temb = F.silu(F.linear(temb, sd["time_emb_fc.0.weight"], sd["time_emb_fc.0.bias"]))
+        temb = F.silu(F.linear(temb, sd["time_emb_fc.2.weight"], sd["time_emb_fc.2.bias"]))
+    h = inp.permute(0, 1, 3, 2)                                                     # [B, Cin, T, F]
+    h = F.group_norm(_conv2d(h, sd["conv.0.weight"], sd["conv.0.bias"], padding=1), 1, sd["conv.1.weight"], sd["conv.1.bias"], cfg.eps)
+    for b in range(cfg.n_layers):
+        if not cfg.predictive:
+            h = F.linear(temb, sd[f"time_emb_blocks.{b}.weight"], sd[f"time_emb_blocks.{b}.bias"])[:, :, None, None] + h
+        h = _gridnet_block(h, sd, f"blocks.{b}.", cfg)
+    h = F.conv_transpose2d(_rnd(h), _rnd(sd["deconv.weight"]), sd["deconv.bias"], padding=1)     # [B, 2, T, F]
+    h = h.reshape(h.shape[0], 1, 2, h.shape[2], h.shape[3])
+    return torch.view_as_complex(h.permute(0, 1, 4, 3, 2).contiguous())              # [B, 1, F, T]

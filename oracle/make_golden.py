@@ -327,10 +327,49 @@ def main():
     print(f"hybrid loss reference {float(loss_ref):.6f} oracle {float(loss_or):.6f}; gradient oracle vs ref {rel(g_or, g_ref):.3e}")
     np.savez_compressed(os.path.join(OUT, "hybrid_loss.npz"), x=c2n(x), x_hat=c2n(x_hat), loss=np.float64(loss_ref.item()),
                         grad=c2n(g_ref))
+    tfgridnet_goldens(BackboneRegistry)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
 
 
+def tfgridnet_goldens(BackboneRegistry=None):
+    """(6) TF-GridNet: the reference's tfgridnet_5l32c100 / _predictive forward on [2,1,257,24] with the oracle's fixed weights,
+    and the deviation a 10-bit-mantissa-operand run has from fp32 (cuDNN runs the reference's LSTMs and convolutions in TF32 on
+    a GPU; emulated by the oracle's fp16-operand mode, whose NCSN++ counterpart is validated against the reference above)."""
+    import json
+    import fdbm_oracle as O
+    if BackboneRegistry is None:
+        BackboneRegistry = import_reference()[1]
+    torch.set_num_threads(os.cpu_count())
+    g = torch.Generator().manual_seed(5)
+    Y = torch.view_as_complex(torch.randn(2, 1, 257, 24, 2, generator=g)) * 0.3
+    X = Y + 0.2 * torch.view_as_complex(torch.randn(2, 1, 257, 24, 2, generator=g))
+    t = torch.tensor([0.6, 0.31])
+    out = dict(Y=c2n(Y), X=c2n(X), t=c2n(t))
+    dev_path = os.path.join(OUT, "ref_tf32_deviation.json")
+    dev = json.load(open(dev_path)) if os.path.exists(dev_path) else {}
+    for name, pred in (("tfgridnet_5l32c100", False), ("tfgridnet_5l32c100_predictive", True)):
+        cfg = O.TFGridNetConfig(predictive=pred)
+        sd = O.tfgridnet_state_dict(cfg, seed=0)
+        net = BackboneRegistry.get_by_name(name)().eval()
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+        net.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            want = net(Y) if pred else net(X, Y, t)
+            got = O.tfgridnet_forward(sd, cfg, Y) if pred else O.tfgridnet_forward(sd, cfg, X, Y, t)
+            with O.operand_rounding("fp16"):
+                low = O.tfgridnet_forward(sd, cfg, Y) if pred else O.tfgridnet_forward(sd, cfg, X, Y, t)
+        print(f"{name}: oracle vs ref {rel(got, want):.3e}; 10-bit-operand emulation vs fp32 {rel(low, got):.3e}; out std {float(want.abs().std()):.3f}")
+        out["D_pred" if pred else "D"] = c2n(want)
+        dev[name + "_forward_T24"] = rel(low, got)
+    np.savez_compressed(os.path.join(OUT, "tfgridnet_T24.npz"), **out)
+    json.dump(dev, open(dev_path, "w"), indent=1)
+
+
 if __name__ == "__main__":
-    main()
+    if len(sys.argv) > 1 and sys.argv[1] == "tfgridnet":
+        os.makedirs(OUT, exist_ok=True)
+        tfgridnet_goldens()
+    else:
+        main()

@@ -25,9 +25,17 @@ namespace {
 
 constexpr int NFFT = 512;
 constexpr int NBIN = NFFT / 2 + 1;
-constexpr int FWARPS = 4;                 // warps per block
+// Warps per block.  A block stages [257 bins][4 * FWARPS frames] and moves it with 32 * FWARPS contiguous bytes per bin.  With
+// 4 warps (128-byte pieces at the 2 KB row pitch of the [B,1,257,T] layout) the kernels ran at the same 2.2 / 1.3 TB/s as the
+// first generation although they issue 2.6 x / 4 x fewer instructions: HBM sees one row activation per 128 bytes.  16 warps
+// move 512 contiguous bytes per bin.
+#ifndef FDBM_SPEC_WARPS
+#define FDBM_SPEC_WARPS 16
+#endif
+constexpr int FWARPS = FDBM_SPEC_WARPS;
 constexpr int FPW = 4;                    // frames per warp
-constexpr int FRB = FWARPS * FPW;         // 16 frames per block = one 128-byte line of the frame axis per bin
+constexpr int FRB = FWARPS * FPW;         // frames per block
+constexpr int LPL = FRB / 2;              // lanes (16-byte pieces = 2 frames) per bin line; 32 * FWARPS / LPL = 16 bins per pass
 constexpr int WPITCH = 34;                // exchange buffer: 16 rows of 32 + 2 (float4 units)
 constexpr int G1_OFF = 260;               // second-stage layout: g0[idx] at idx, g1[idx] at 260 + idx (conflict-free both ways)
 constexpr int TILE_PITCH = FRB + 2;       // staging tile [257][18] float2: 144-byte rows -> conflict-free 16-byte accesses
@@ -323,7 +331,7 @@ stft_fast_kernel(const float* __restrict__ wave, int n_samples, const int* __res
   const int n_valid = min(FRB, n_frames_out - t0);             // frames of this block inside the output
   float2* out = spec + static_cast<int64_t>(b) * NBIN * n_frames_out + t0;
   if ((n_frames_out & 1) == 0) {
-    const int c = (threadIdx.x & 7) * 2, kb = threadIdx.x >> 3;
+    const int c = (threadIdx.x % LPL) * 2, kb = threadIdx.x / LPL;
     if (c < n_valid) {                                         // n_valid is even here
       const float4* tp = reinterpret_cast<const float4*>(&sm.u.tile[kb][c]);
       float4* gp = reinterpret_cast<float4*>(out + static_cast<int64_t>(kb) * n_frames_out + c);
@@ -333,8 +341,8 @@ stft_fast_kernel(const float* __restrict__ wave, int n_samples, const int* __res
       if (kb == 0) gp[16 * gstep] = tp[16 * (16 * TILE_PITCH / 2)];       // bin 256
     }
   } else {
-    for (int e = threadIdx.x; e < NBIN * 16; e += FWARPS * 32) {
-      const int k = e >> 4, c = e & 15;
+    for (int e = threadIdx.x; e < NBIN * FRB; e += FWARPS * 32) {
+      const int k = e / FRB, c = e % FRB;
       if (c < n_valid) out[static_cast<int64_t>(k) * n_frames_out + c] = sm.u.tile[k][c];
     }
   }
@@ -391,17 +399,17 @@ istft_fast_kernel(const float2* __restrict__ spec, int M, const float* __restric
   };
   if ((M & 1) == 0) {
     // 16-byte loads of frame pairs (m, m + 1), m even; blocks with an odd first frame start one frame early (9 pairs per bin)
-    const int shift = m0 & 1, ncol = 8 + shift;
+    const int shift = m0 & 1, ncol = LPL + shift;
     for (int e = threadIdx.x; e < NBIN * ncol; e += FWARPS * 32) {
-      const int k = shift ? e / 9 : e >> 3, c = (shift ? e - k * 9 : (e & 7)) * 2 - shift, m = m0 + c;
+      const int k = shift ? e / (LPL + 1) : e / LPL, c = (e - k * ncol) * 2 - shift, m = m0 + c;
       float4 val = make_float4(0.f, 0.f, 0.f, 0.f);
       if (m >= 0 && m + 1 < M) val = __ldg(reinterpret_cast<const float4*>(in + static_cast<int64_t>(k) * M + m));
       if (c >= 0) sm.u.tile[k][c] = prep(make_float2(val.x, val.y), k);
       if (c + 1 < FRB) sm.u.tile[k][c + 1] = prep(make_float2(val.z, val.w), k);
     }
   } else {
-    for (int e = threadIdx.x; e < NBIN * 16; e += FWARPS * 32) {
-      const int k = e >> 4, c = e & 15, m = m0 + c;
+    for (int e = threadIdx.x; e < NBIN * FRB; e += FWARPS * 32) {
+      const int k = e / FRB, c = e % FRB, m = m0 + c;
       sm.u.tile[k][c] = (m >= 0 && m < M) ? prep(__ldg(in + static_cast<int64_t>(k) * M + m), k) : make_float2(0.f, 0.f);
     }
   }

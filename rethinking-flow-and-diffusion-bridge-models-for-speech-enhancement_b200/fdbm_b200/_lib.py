@@ -34,6 +34,8 @@ EXPORTS = [
     "fdbm_plan_num_backward_launches", "fdbm_plan_optimizer_step", "fdbm_plan_profile_backward", "fdbm_plan_repack_weights",
     "fdbm_plan_reset_optimizer", "fdbm_plan_optimizer_state", "fdbm_plan_set_optimizer_state", "fdbm_plan_swap_ema",
     "fdbm_hybrid_loss_workspace_bytes", "fdbm_hybrid_loss",
+    "fdbm_tfg_lstm_pack_bytes", "fdbm_tfg_lstm_pack", "fdbm_tfg_lstm_sweep", "fdbm_tfg_pad_add_norm", "fdbm_tfg_sweep_post",
+    "fdbm_tfg_input", "fdbm_tfg_time_embedding", "fdbm_tfg_attention_workspace_bytes", "fdbm_tfg_attention", "fdbm_tfg_output",
 ]
 
 
@@ -118,6 +120,16 @@ def load() -> C.CDLL:
         "fdbm_plan_set_optimizer_state": (i, [p, d, d, p]),
         "fdbm_plan_swap_ema": (i, [p, i, p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
+        "fdbm_tfg_lstm_pack_bytes": (i64, []),
+        "fdbm_tfg_lstm_pack": (i, [p, p, p, p, p, i, i, p, p]),
+        "fdbm_tfg_lstm_sweep": (i, [p, i, i, i64, i64, i64, i, p, p, p, p, p]),
+        "fdbm_tfg_pad_add_norm": (i, [p, p, p, p, i, i, i, f, p, p, p]),
+        "fdbm_tfg_sweep_post": (i, [p, p, p, p, i, i, i, i, p, p, f, p, p, p, p]),
+        "fdbm_tfg_input": (i, [p, p, p, p, p, p, i, i, i, i, f, p, p, p]),
+        "fdbm_tfg_time_embedding": (i, [p, i, p, p, p, p, p, p, p, i, i, p, p]),
+        "fdbm_tfg_attention_workspace_bytes": (i64, [i, i, i]),
+        "fdbm_tfg_attention": (i, [p, C.POINTER(p), i, i, i, f, p, p, p]),
+        "fdbm_tfg_output": (i, [p, p, p, i, i, i, p, p]),
     }
     for name, (res, args) in sig.items():
         if not hasattr(lib, name) and os.environ.get("FDBM_B200_LIB"):

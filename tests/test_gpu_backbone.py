@@ -82,11 +82,11 @@ def test_sampler_golden_T64(nets, golden_dir, path, st):
     sdr = O.si_sdr(wref, w)
     print(f"sampler {path}/{st}: spec rel L2 {err:.3e}, SI-SDR(new vs ref) {sdr:.1f} dB")
     # Five passes through a RANDOM-weight (non-contractive) network amplify any rounding; the bound is the north-star
-    # 5e-3 wherever the REFERENCE's own TF32 run (its default GPU precision) meets it and twice the reference's own
+    # 5e-3 wherever the REFERENCE's own TF32 run (its default GPU precision) meets it and three times the reference's own
     # TF32-vs-fp32 deviation where it does not (tests/golden/ref_tf32_deviation.json, see tests/test_gpu_parity.py).
     import json
     dev = json.load(open(f"{golden_dir}/ref_tf32_deviation.json"))
-    bound = max(TOL_BF16, 2.0 * dev[f"sampler_{path}_{st}_N5_T64"])
+    bound = max(TOL_BF16, 3.0 * dev[f"sampler_{path}_{st}_N5_T64"])
     print(f"   bound {bound:.2e} (reference TF32 deviation {dev[f'sampler_{path}_{st}_N5_T64']:.3e})")
     assert err < bound
     assert sdr > (20.0 if path == "fm" else 30.0)

@@ -123,7 +123,9 @@ def test_stft_istft_various_lengths_vs_oracle(lib, n_samples):
     S = dm.stft(x.cuda())
     want = O.stft(x, sc)
     assert S.shape == want.shape and rel_l2(S, want) < 2e-6
-    for mode in ("zero_pad", "reflection", "replication"):
+    n_pad = (64 - want.shape[-1] % 64) % 64
+    modes = ("zero_pad", "reflection", "replication") if n_pad < want.shape[-1] else ("zero_pad", "replication")   # reflection needs pad < frames
+    for mode in modes:
         got = dm.stft_compress(x.cuda(), pad_mode=mode)
         ref = O.pad_spec(O.spec_fwd(want, sc)[:, None], mode)
         assert got.shape == ref.shape and rel_l2(got, ref) < 2e-6, mode

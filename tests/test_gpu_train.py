@@ -283,6 +283,12 @@ def test_training_loss_decreases_over_ten_steps():
     (fdbm/model.py:28): the loss of the same batch must go down."""
     O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z = _train_setup(seed=2)
     B, T = x.shape[0], x.shape[3]
+    # the reference's OWN initialisation (init_scale = 0 on every block's Conv_1 and on the output pyramid, ncsnpp_v2.py): that
+    # is the state training starts from; the 'sensitised' weights of the parity tests put the network output at std 1.7 on
+    # targets of std 0.1, a regime in which the first Adam steps of any implementation overshoot wildly
+    from fdbm_b200 import BackboneRegistry
+    torch.manual_seed(0)
+    net = BackboneRegistry.get_by_name("ncsnpp_v2")().cuda()
     ts = TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_scale=1024.0, lr=1e-4)
     xc, yc, tc, zc = x.cuda(), y.cuda(), t.cuda(), z.cuda()
     losses = []

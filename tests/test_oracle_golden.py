@@ -1,5 +1,6 @@
 """The CPU oracle against the golden vectors produced by the reference itself
 (oracle/make_golden.py, run in the build container where /root/reference exists)."""
+import pytest
 import numpy as np
 import torch
 
@@ -91,3 +92,25 @@ def test_si_sdr_and_synth():
     assert -1.0 < O.si_sdr(c.numpy(), n.numpy()) < 16.0                # SNR drawn from U(0, 15) dB
     c2, _ = O.synth_pair(0, 16000)
     assert torch.equal(c, c2)
+
+
+@pytest.mark.parametrize("pred", [False, True])
+def test_tfgridnet_oracle_matches_reference_golden(golden_dir, pred):
+    """The oracle's restatement of tfgridnet.py / tfgridnet_predictive.py against the reference's own output (make_golden.py)."""
+    g = load_npz(f"{golden_dir}/tfgridnet_T24.npz")
+    cfg = O.TFGridNetConfig(predictive=pred)
+    sd = O.tfgridnet_state_dict(cfg, seed=0)
+    Y, X, t = (torch.from_numpy(g[k]) for k in ("Y", "X", "t"))
+    with torch.no_grad():
+        got = O.tfgridnet_forward(sd, cfg, Y) if pred else O.tfgridnet_forward(sd, cfg, X, Y, t)
+    assert rel_l2(got, g["D_pred" if pred else "D"]) < 1e-4
+
+
+def test_hybrid_loss_oracle_matches_reference_golden(golden_dir):
+    """O.hybrid_loss against BridgeModel._loss of the reference (value and autograd gradient, tests/golden/hybrid_loss.npz)."""
+    g = load_npz(f"{golden_dir}/hybrid_loss.npz")
+    x, xh = torch.from_numpy(g["x"]), torch.from_numpy(g["x_hat"]).requires_grad_(True)
+    loss = O.hybrid_loss(xh, x, O.SpecConfig())
+    (grad,) = torch.autograd.grad(loss, xh)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert rel_l2(torch.nan_to_num(grad), g["grad"]) < 1e-5
