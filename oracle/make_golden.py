@@ -328,6 +328,7 @@ def main():
     np.savez_compressed(os.path.join(OUT, "hybrid_loss.npz"), x=c2n(x), x_hat=c2n(x_hat), loss=np.float64(loss_ref.item()),
                         grad=c2n(g_ref))
     tfgridnet_goldens(BackboneRegistry)
+    variant_goldens(BackboneRegistry)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
@@ -367,9 +368,31 @@ def tfgridnet_goldens(BackboneRegistry=None):
     json.dump(dev, open(dev_path, "w"), indent=1)
 
 
+def variant_goldens(BackboneRegistry=None):
+    """(7) the nf = 64 size variant ncsnpp_v2_16M (ncsnpp_v2.py:418-433): reference forward at T = 64 with sensitised weights."""
+    import fdbm_oracle as O
+    if BackboneRegistry is None:
+        BackboneRegistry = import_reference()[1]
+    torch.set_num_threads(os.cpu_count())
+    cfg = O.NcsnppConfig(nf=64, attn_resolutions=(0,))
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    net = BackboneRegistry.get_by_name("ncsnpp_v2_16M")().eval()
+    assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+    net.load_state_dict(sd, strict=True)
+    g = np.load(os.path.join(OUT, "bridge_T64.npz"))
+    xt, Y, t = (torch.from_numpy(g[k]) for k in ("xt", "Y", "t"))
+    with torch.no_grad():
+        want = net(xt, Y, t)
+        got = O.ncsnpp_forward(sd, cfg, xt, Y, t)
+    print(f"ncsnpp_v2_16M forward oracle vs ref: {rel(got, want):.3e}  out std {float(want.abs().std()):.3f}  params {sum(v.numel() for v in sd.values())}")
+    np.savez_compressed(os.path.join(OUT, "ncsnpp_16M_T64.npz"), D=c2n(want))
+
+
 if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tfgridnet":
         os.makedirs(OUT, exist_ok=True)
         tfgridnet_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "variants":
+        variant_goldens()
     else:
         main()

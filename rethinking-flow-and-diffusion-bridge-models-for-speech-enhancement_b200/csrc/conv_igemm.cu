@@ -440,9 +440,11 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
 #pragma unroll
       for (int u = 0; u < STAT_SLOTS; ++u) {
         if (u < p.n_nblocks) {
-          double* dst = p.sums + (static_cast<int64_t>(stat_b) * p.Cout + u * BN + et) * 2;
-          atomicAdd(dst, acc_s[u]);
-          atomicAdd(dst + 1, acc_q[u]);
+          if (et < p.bn) {                              // bn = 64 (C_out = 64 layers): half of the group's threads own a channel
+            double* dst = p.sums + (static_cast<int64_t>(stat_b) * p.Cout + u * BN + et) * 2;
+            atomicAdd(dst, acc_s[u]);
+            atomicAdd(dst + 1, acc_q[u]);
+          }
         }
         acc_s[u] = 0.0; acc_q[u] = 0.0;
       }
@@ -603,8 +605,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
                                            : make_float4(0.f, 0.f, 0.f, 0.f);
           }
         };
+        const int n_chunks = p.bn >> 5;                   // 4, or 2 for the 64-channel layers of the nf = 64 variant
 #pragma unroll
         for (int ch = 0; ch < BN / 32; ++ch) {
+          if (ch >= n_chunks) break;                        // warp-uniform
           float4 cw[4], cbias = make_float4(0.f, 0.f, 0.f, 0.f);
           if constexpr (COMB) {                               // Combine: 1x1 conv of the <=4-channel input pyramid
             const int c = n0 + ch * 32 + cc * 4;
@@ -617,7 +621,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             }
           }
           float4 bvn = bv, bvbn = bvb;
-          if (ch + 1 < BN / 32) {
+          if (ch + 1 < n_chunks) {
             bvn = __ldg(reinterpret_cast<const float4*>(bias_p + (ch + 1) * 32));
             if (biasb_p) bvbn = __ldg(reinterpret_cast<const float4*>(biasb_p + (ch + 1) * 32));
           }
@@ -666,7 +670,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           // the shortcut registers are free again: request the next chunk's rows now (L2 hits, prefetched one tile ahead), a
           // whole store + statistics phase ahead of their use, without a second register buffer
-          if (RES16 && ch + 1 < BN / 32) load_res16(ch + 1);
+          if (RES16 && ch + 1 < n_chunks) load_res16(ch + 1);
           float2 ssum_lo = make_float2(0.f, 0.f), ssum_hi = ssum_lo, ssq_lo = ssum_lo, ssq_hi = ssum_lo;
           if (full) {                                       // whole tile inside the image: no per-row predicates
             if (of_p) {
@@ -717,7 +721,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
           double s = 0.0, sq = 0.0;
 #pragma unroll
-          for (int w = 0; w < 4; ++w) { const float2 e = wstat[w * BN + et]; s += e.x; sq += e.y; }
+          for (int w = 0; w < 4; ++w) { const float2 e = et < p.bn ? wstat[w * BN + et] : make_float2(0.f, 0.f); s += e.x; sq += e.y; }
 #pragma unroll
           for (int u = 0; u < STAT_SLOTS; ++u) if (u == nblk) { acc_s[u] += s; acc_q[u] += sq; }
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
@@ -878,7 +882,7 @@ int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize,
 
 int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   FDBM_REQUIRE(a.n_seg >= 1 && a.n_seg <= MAX_SEG, "conv_igemm: 1..%d K segments", MAX_SEG);
-  const int bn = a.narrow_n ? 16 : BN;
+  const int bn = a.narrow_n ? 16 : (a.Cout == 64 ? 64 : BN);      // MMA N: 128; 64 for the C_out = 64 layers of ncsnpp_v2_16M; 16 for C -> 4
   FDBM_REQUIRE(a.Cout % bn == 0 && (!a.narrow_n || (a.Cout == 16 && a.pyr_out)), "conv_igemm: Cout must be a multiple of %d (got %d)", bn, a.Cout);
   FDBM_REQUIRE(a.out_f32 || a.out_h16 || a.pyr_out, "conv_igemm: no output");
   FDBM_REQUIRE(!a.pyr_out || (a.pyr_C >= 1 && a.pyr_C <= 4 && a.Cout == bn && !a.sums), "conv_igemm: bad pyramid epilogue arguments");
@@ -928,9 +932,20 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
     // 9-tap blocks first, back to back: the load + transform of each one hides behind the nine taps of the previous
     // one.  (Interleaving the 1-tap blocks between them was measured 5 % slower: the next 9-tap block then has only
     // two short blocks of MMA work to hide behind.)
+    // FDBM_KSCHED (measurement aid): 1 = 1-tap blocks first, 2 = 1-tap blocks after the first 9-tap block
+    static const int order = getenv("FDBM_KSCHED") ? atoi(getenv("FDBM_KSCHED")) : 0;
     int n = 0;
-    for (int i = 0; i < n9; ++i) p.ksched[n++] = nine[i];
-    for (int i = 0; i < n1; ++i) p.ksched[n++] = one[i];
+    if (order == 1) {
+      for (int i = 0; i < n1; ++i) p.ksched[n++] = one[i];
+      for (int i = 0; i < n9; ++i) p.ksched[n++] = nine[i];
+    } else if (order == 2 && n9 > 0) {
+      p.ksched[n++] = nine[0];
+      for (int i = 0; i < n1; ++i) p.ksched[n++] = one[i];
+      for (int i = 1; i < n9; ++i) p.ksched[n++] = nine[i];
+    } else {
+      for (int i = 0; i < n9; ++i) p.ksched[n++] = nine[i];
+      for (int i = 0; i < n1; ++i) p.ksched[n++] = one[i];
+    }
     for (; n < MAX_KB; ++n) p.ksched[n] = 0;
   }
   if (int rc = make_weight_map(&map_b, a.wpack, static_cast<int64_t>(n_kt) * a.Cout, bn)) return rc;

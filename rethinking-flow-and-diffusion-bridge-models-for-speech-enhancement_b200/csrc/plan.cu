@@ -889,12 +889,15 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   FDBM_REQUIRE(arch && out, "fdbm_plan_create: null pointer");
   FDBM_REQUIRE(batch > 0 && n_frames > 0, "fdbm_plan_create: batch and n_frames must be positive");
   FDBM_REQUIRE(arch->n_levels >= 1 && arch->n_levels <= 8, "fdbm_plan_create: n_levels out of range");
-  FDBM_REQUIRE(arch->nf % 64 == 0 && arch->nf >= 128, "fdbm_plan_create: nf must be a multiple of 64 and >= 128 (got %d)", arch->nf);
+  FDBM_REQUIRE(arch->nf % 64 == 0 && arch->nf >= 64, "fdbm_plan_create: nf must be a multiple of 64 (got %d); the nf = 96 variants need 32-channel K-blocks", arch->nf);
   FDBM_REQUIRE(arch->image_size == 256, "fdbm_plan_create: image_size must be 256 (n_fft = 512 with the Nyquist bin dropped)");
   const int down = 1 << (arch->n_levels - 1);
   FDBM_REQUIRE(n_frames % down == 0, "fdbm_plan_create: n_frames %d must be a multiple of %d (pad_spec pads to 64)", n_frames, down);
-  for (int i = 0; i < arch->n_levels; ++i)
-    FDBM_REQUIRE((arch->nf * arch->ch_mult[i]) % 128 == 0, "fdbm_plan_create: level %d channel count must be a multiple of 128", i);
+  for (int i = 0; i < arch->n_levels; ++i) {
+    const int c = arch->nf * arch->ch_mult[i];
+    FDBM_REQUIRE(c == 64 || c % 128 == 0, "fdbm_plan_create: level %d has %d channels; supported: 64 or a multiple of 128", i, c);
+  }
+  FDBM_REQUIRE(!train || arch->nf >= 128, "fdbm_plan_create_train: the training step is built for nf >= 128");
 
   fdbm_plan* P = new fdbm_plan();
   P->arch = *arch; P->B = batch; P->T = n_frames; P->F = arch->image_size; P->F_io = arch->image_size + 1;

@@ -30,7 +30,15 @@ constexpr int NBIN = NFFT / 2 + 1;
 // first generation although they issue 2.6 x / 4 x fewer instructions: HBM sees one row activation per 128 bytes.  16 warps
 // move 512 contiguous bytes per bin.
 #ifndef FDBM_SPEC_WARPS
-#define FDBM_SPEC_WARPS 16
+#define FDBM_SPEC_WARPS 4
+#endif
+// FDBM_SPEC_TW_GLOBAL: read the packed twiddle table from global memory (L1-resident, 9 KB) instead of a per-block shared copy;
+// FDBM_SPEC_MINBLOCKS: resident blocks per SM the register allocation must allow
+#ifndef FDBM_SPEC_TW_GLOBAL
+#define FDBM_SPEC_TW_GLOBAL 0
+#endif
+#ifndef FDBM_SPEC_MINBLOCKS
+#define FDBM_SPEC_MINBLOCKS 1
 #endif
 constexpr int FWARPS = FDBM_SPEC_WARPS;
 constexpr int FPW = 4;                    // frames per warp
@@ -46,11 +54,15 @@ __device__ const float2 kTw512[NFFT] = {
 #include "tw512.inc"
 };
 
+__device__ float4 g_tw_packed[2][NFFT + 64];       // [0] forward, [1] inverse (filled once per device)
+
 struct FastSmem {
+#if !FDBM_SPEC_TW_GLOBAL
   // packed-pair twiddles (c, c, s, s) of exp(-+2 pi i m / 512):  [32 k1 + lane] = W_512^(lane k1) (inter-stage, one row per k1 so
   // that a lane's 15 reads are immediate offsets from one address);  [512 + 16 h + K] = h ? W_32^K : 1 (radix-2 split of the last
   // stage);  [544 + M] = W_32^M (the 16-point transform's constants)
   float4 tw[NFFT + 64];
+#endif
   union {
     float4 work[FWARPS][WORK_F4];
     float2 tile[NBIN][TILE_PITCH];
@@ -162,6 +174,18 @@ DI void fft512_pair(PC (&v)[16], float4* work, const float4* tw, int lane) {
   __syncwarp();
 }
 
+__global__ void fill_tw_global_kernel() {
+  for (int m = threadIdx.x; m < NFFT + 64; m += blockDim.x) {
+    int idx;
+    if (m < NFFT) idx = ((m & 31) * (m >> 5)) & 511;
+    else if (m < NFFT + 32) idx = m < NFFT + 16 ? 0 : 16 * (m - NFFT - 16);
+    else idx = 16 * (m - NFFT - 32);
+    const float2 w = kTw512[idx];
+    g_tw_packed[0][m] = make_float4(w.x, w.x, w.y, w.y);
+    g_tw_packed[1][m] = make_float4(w.x, w.x, -w.y, -w.y);
+  }
+}
+
 DI void fill_tw(float4* tw, bool inv) {
   for (int m = threadIdx.x; m < NFFT + 64; m += FWARPS * 32) {
     int idx;
@@ -205,7 +229,7 @@ DI float compress_scale(float m2, int transform, float factor, float expo, float
 // STFT + compression.  HS = hop / 32 (8 for hop 256, 4 for hop 128).
 // ------------------------------------------------------------------------------------------------------------------
 template <int HS, int MODE>
-__global__ void __launch_bounds__(FWARPS * 32)
+__global__ void __launch_bounds__(FWARPS * 32, FDBM_SPEC_MINBLOCKS)
 stft_fast_kernel(const float* __restrict__ wave, int n_samples, const int* __restrict__ lengths, int64_t wave_stride,
                  const float* __restrict__ window, const float* __restrict__ norm, int transform, float factor, float expo,
                  int pad_mode, int M, int n_frames_out, float2* __restrict__ spec) {
@@ -273,10 +297,15 @@ stft_fast_kernel(const float* __restrict__ wave, int n_samples, const int* __res
       __syncwarp();
     }
   }
+#if FDBM_SPEC_TW_GLOBAL
+  const float4* twp = g_tw_packed[0];
+#else
   fill_tw(sm.tw, false);
   __syncthreads();
+  const float4* twp = sm.tw;
+#endif
   float4* work = sm.u.work[warp];
-  if (any) fft512_pair<false>(v, work, sm.tw, lane);
+  if (any) fft512_pair<false>(v, work, twp, lane);
   // Hermitian separation + compression, results kept in registers until every warp has finished reading its exchange buffer
   // (the staging tile aliases those buffers).  With Z = (frame0 + i frame1): F0[k] = (Z[k] + conj Z[N-k]) / 2,
   // F1[k] = (Z[k] - conj Z[N-k]) / (2i); the 1/2 goes into the compression scale.
@@ -377,7 +406,7 @@ DI float2 decompress1(float2 z, float inv, int transform, float factor, float ex
 }
 
 template <int MODE>
-__global__ void __launch_bounds__(FWARPS * 32)
+__global__ void __launch_bounds__(FWARPS * 32, FDBM_SPEC_MINBLOCKS)
 istft_fast_kernel(const float2* __restrict__ spec, int M, const float* __restrict__ window, int transform, float factor, float expo,
                   int64_t length, const int* __restrict__ lengths, int64_t wave_stride, const float* __restrict__ norm,
                   float* __restrict__ peak, float* __restrict__ wave) {
@@ -413,7 +442,12 @@ istft_fast_kernel(const float2* __restrict__ spec, int M, const float* __restric
       sm.u.tile[k][c] = (m >= 0 && m < M) ? prep(__ldg(in + static_cast<int64_t>(k) * M + m), k) : make_float2(0.f, 0.f);
     }
   }
+#if FDBM_SPEC_TW_GLOBAL
+  const float4* twp = g_tw_packed[1];
+#else
   fill_tw(sm.tw, true);
+  const float4* twp = sm.tw;
+#endif
   __syncthreads();
   // ---- Z_A = F0 + i F1, Z_B = F2 + i F3 with Hermitian extension: bins k > 256 are the conjugates of bin 512 - k
   PC v[16];
@@ -436,7 +470,7 @@ istft_fast_kernel(const float2* __restrict__ spec, int M, const float* __restric
   }
   __syncthreads();                                // tile consumed by every warp: the exchange buffers may overwrite it
   float4* work = sm.u.work[warp];
-  fft512_pair<true>(v, work, sm.tw, lane);
+  fft512_pair<true>(v, work, twp, lane);
   // ---- time samples n = 32 j + lane (j < 8) and n + 256 of the four frames, windowed, 1/N
   float w[16];
 #pragma unroll
@@ -533,6 +567,15 @@ bool spectral_fast_supported(int n_fft, int hop, bool inverse) {
   return inverse ? hop == NFFT / 2 : (hop == 256 || hop == 128);
 }
 
+static int ensure_tw_table(cudaStream_t s) {
+  static PerDeviceOnce once;
+  if (once.first(current_device())) {
+    fill_tw_global_kernel<<<1, 256, 0, s>>>();
+    FDBM_LAUNCH_CHECK();
+  }
+  return FDBM_OK;
+}
+
 static int transform_mode(int transform, float expo) {
   return transform == FDBM_TRANSFORM_NONE ? 0 : (transform == FDBM_TRANSFORM_EXPONENT ? (expo == 1.0f ? 1 : (expo == 0.5f ? 2 : 3)) : 3);
 }
@@ -554,6 +597,7 @@ int launch_stft_fast(const float* wave, int batch, int64_t max_samples, const in
                      const float* norm, int hop, int transform, float factor, float expo, int pad_mode, int M, int n_frames_out,
                      float* spec, cudaStream_t s) {
   dim3 grid(ceil_div(n_frames_out, FRB), batch);
+  if (int rc = ensure_tw_table(s)) return rc;
   const int mode = transform_mode(transform, expo), ns = static_cast<int>(max_samples);
   float2* out = reinterpret_cast<float2*>(spec);
 #define FDBM_STFT_CASE(HS_, MODE_)                                                                                                     \
@@ -584,6 +628,7 @@ int launch_istft_fast(const float* spec, int batch, int n_frames, const float* w
   const int64_t n_seg = ceil_div64(length + NFFT / 2, NFFT / 2);
   dim3 grid(static_cast<unsigned>(ceil_div64(n_seg + 1, FRB - 1)), batch);
   if (peak) FDBM_CUDA(cudaMemsetAsync(peak, 0, sizeof(float) * batch, s));
+  if (int rc = ensure_tw_table(s)) return rc;
   const float2* in = reinterpret_cast<const float2*>(spec);
   switch (transform_mode(transform, expo)) {
     case 0: return istft_fast_launch<0>(grid, s, in, n_frames, window, transform, factor, expo, length, lengths, wave_stride, norm, peak, wave);

@@ -392,6 +392,44 @@ class NCSNpp_v2(_NCSNppBase):
         return out
 
 
+@BackboneRegistry.register("ncsnpp_v2_16M")
+class NCSNpp_v2_16M(NCSNpp_v2):
+    """fdbm/backbones/ncsnpp_v2.py:418-433: nf = 64 (64 / 128 channels), no attention besides the bottleneck's."""
+
+    def __init__(self, **kwargs):
+        for k in ("nf", "ch_mult", "num_res_blocks", "attn_resolutions"):
+            kwargs.pop(k, None)
+        super().__init__(nf=64, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=[0], **kwargs)
+
+    @staticmethod
+    def add_argparse_args(parser):
+        return parser
+
+
+class _Nf96Variant(NCSNpp_v2):
+    """ncsnpp_v2_5M / ncsnpp_v2_37M (fdbm/backbones/ncsnpp_v2.py:404-415, 436-448) have nf = 96: 96- and 192-channel tensors, which the
+    tensor-core convolution (64-channel K-blocks, 64 / 128-channel N tiles) does not tile.  The names resolve so that configuration
+    errors are explicit; constructing one raises."""
+
+    def __init__(self, **kwargs):
+        raise NotImplementedError(f"{type(self).__name__}: nf = 96 needs 32-channel K-block tails in libfdbm_b200's convolution; "
+                                  "supported NCSN++ sizes are ncsnpp_v2 (nf 128) and ncsnpp_v2_16M (nf 64)")
+
+    @staticmethod
+    def add_argparse_args(parser):
+        return parser
+
+
+@BackboneRegistry.register("ncsnpp_v2_5M")
+class NCSNpp_v2_5M(_Nf96Variant):
+    pass
+
+
+@BackboneRegistry.register("ncsnpp_v2_37M")
+class NCSNpp_v2_37M(_Nf96Variant):
+    pass
+
+
 @BackboneRegistry.register("ncsnpp_v2_predictive")
 class NCSNpp_v2_predictive(_NCSNppBase):
     """fdbm/backbones/ncsnpp_v2_predictive.py:36-362."""

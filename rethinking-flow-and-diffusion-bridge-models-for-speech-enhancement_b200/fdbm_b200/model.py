@@ -151,74 +151,110 @@ class EnhancementModel(nn.Module):
 
 
     # ------------------------------------------------------------------ callers' edge: lists of files / waveforms
+    def _staging(self, slot: int, rows: int, cols: int):
+        """Persistent pinned host staging (input, output) of one pipeline slot, grown on demand; allocating pinned memory per
+        bucket (cudaHostAlloc is a synchronising driver call) cost more than the copies themselves."""
+        ring = self.__dict__.setdefault("_pinned_ring", {})
+        need = rows * cols
+        bufs = ring.get(slot)
+        if bufs is None or bufs[0].numel() < need:
+            bufs = (torch.empty(need, dtype=torch.float32).pin_memory(), torch.empty(need, dtype=torch.float32).pin_memory())
+            ring[slot] = bufs
+        return bufs[0][:need].view(rows, cols), bufs[1][:need].view(rows, cols)
+
     @torch.no_grad()
     def enhance_list(self, waves: Sequence, micro_batch: int = 32, clip_rescale: Optional[float] = 0.95) -> List[np.ndarray]:
         """The per-file loop of infer_folder.py:91-121 for waveforms of DIFFERENT lengths, batched: utterances are
         bucketed by their padded frame count (pad_spec rounds to 64 frames; GroupNorm and attention see the whole padded
         image, so only utterances with the same padded length may share a batch without changing any result), each
         bucket runs in micro-batches through peak-normalise -> variable-length STFT -> sampler -> variable-length iSTFT
-        -> rescale -> clip rule (0.95, infer_folder.py:119-120).  Returns the enhanced waveforms in input order."""
+        -> rescale -> clip rule (0.95, infer_folder.py:119-120).  Returns the enhanced waveforms in input order.
+
+        Two-slot software pipeline: while the GPU works on micro-batch k the host packs micro-batch k + 1 into the other
+        pinned staging slot and unpacks the results of micro-batch k - 1; the only host waits are on per-slot events."""
         if self.data_module.normalize != "noisy":
             raise NotImplementedError("enhance_list implements the default normalize='noisy'")
         dev = next(self.dnn.parameters()).device
         hop = self.data_module.hop_length
-        ws = [torch.as_tensor(w, dtype=torch.float32).reshape(-1) for w in waves]
+        dm = self.data_module
+        ws = [np.ascontiguousarray(np.asarray(w, dtype=np.float32).reshape(-1)) if not torch.is_tensor(w)
+              else w.detach().to("cpu", torch.float32).reshape(-1).contiguous().numpy() for w in waves]
         for i, w in enumerate(ws):
-            if w.numel() <= self.data_module.n_fft // 2:
+            if w.shape[0] <= dm.n_fft // 2:
                 raise RuntimeError(f"utterance {i} is shorter than n_fft/2 samples")
         out: List[Optional[np.ndarray]] = [None] * len(ws)
-        for T_pad, grp in length_buckets([w.numel() for w in ws], hop, micro_batch):
-            n = len(grp)
-            lens = [ws[i].numel() for i in grp]
-            # a partial batch is padded (last utterance repeated) to the next multiple of 8: at most four plans / graphs
-            # per padded length instead of one per batch size, at most 7 wasted slots
-            mb = micro_batch if n == micro_batch else min(micro_batch, -(-n // 8) * 8)
-            lens_full = lens + [lens[-1]] * (mb - n)
-            max_len, min_len = max(lens_full), min(lens_full)
-            host = torch.zeros(mb, max_len, dtype=torch.float32).pin_memory()
-            for r in range(mb):
-                w = ws[grp[min(r, n - 1)]]
-                host[r, :w.numel()] = w
-            y = host.to(dev, non_blocking=True)
-            lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
-            dm = self.data_module
-            norm = dm.wave_absmax(y, lengths)                    # rows are zero-padded beyond their length
-            Y = dm.stft_compress_var(y, lengths, min_len, max_len, pad_mode=self.pad_mode, n_frames_out=T_pad, norm=norm)
-            sample = self._sample(Y)
-            x_hat, peak = dm.to_audio_ex(sample[:, 0], max_len, lengths=lengths, norm=norm, want_peak=clip_rescale is not None)
-            if clip_rescale is not None:
-                dm.clip_rescale_(x_hat, peak, clip_rescale, lengths)
-            res = x_hat[:n].cpu().numpy()
-            for r, i in enumerate(grp):
-                out[i] = res[r, :lens[r]].copy()
+        pending = []                                               # (event, host_out view, group indices, lengths)
+
+        def drain(keep: int):
+            while len(pending) > keep:
+                ev, host_out, grp, lens = pending.pop(0)
+                ev.synchronize()
+                for r, i in enumerate(grp):
+                    out[i] = host_out[r, :lens[r]].numpy().copy()
+
+        with torch.cuda.device(dev):
+            for k, (T_pad, grp) in enumerate(length_buckets([w.shape[0] for w in ws], hop, micro_batch)):
+                n = len(grp)
+                lens = [ws[i].shape[0] for i in grp]
+                # a partial batch is padded (last utterance repeated) to the next multiple of 8: at most four plans / graphs
+                # per padded length instead of one per batch size, at most 7 wasted slots
+                mb = micro_batch if n == micro_batch else min(micro_batch, -(-n // 8) * 8)
+                lens_full = lens + [lens[-1]] * (mb - n)
+                max_len, min_len = max(lens_full), min(lens_full)
+                drain(1)                                           # slot k % 2 was used by micro-batch k - 2: its results are out
+                host_in, host_out = self._staging(k % 2, mb, max_len)
+                hin = host_in.numpy()
+                for r in range(mb):
+                    w = ws[grp[min(r, n - 1)]]
+                    hin[r, :w.shape[0]] = w
+                    hin[r, w.shape[0]:] = 0.0
+                y = host_in.to(dev, non_blocking=True)
+                lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
+                norm = dm.wave_absmax(y, lengths)                    # rows are zero-padded beyond their length
+                Y = dm.stft_compress_var(y, lengths, min_len, max_len, pad_mode=self.pad_mode, n_frames_out=T_pad, norm=norm)
+                sample = self._sample(Y)
+                x_hat, peak = dm.to_audio_ex(sample[:, 0], max_len, lengths=lengths, norm=norm, want_peak=clip_rescale is not None)
+                if clip_rescale is not None:
+                    dm.clip_rescale_(x_hat, peak, clip_rescale, lengths)
+                host_out.copy_(x_hat, non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record()
+                pending.append((ev, host_out, grp, lens))
+            drain(0)
         return out  # type: ignore[return-value]
 
     def enhance_files(self, paths: Sequence[str], out_paths: Optional[Sequence[str]] = None, micro_batch: int = 32,
-                      target_sr: int = 16000) -> List[np.ndarray]:
+                      target_sr: int = 16000, io_threads: int = 8) -> List[np.ndarray]:
         """infer_folder.py:91-146 for a list of mono WAV files (16-bit / 32-bit PCM or float): decode, enhance in
-        length buckets, optionally write 16-bit PCM WAVs.  Resampling (librosa in the reference) is not part of the
-        hot path: files at another sample rate are rejected."""
+        length buckets, optionally write 16-bit PCM WAVs.  Decoding and encoding run on a thread pool (file I/O and the numpy
+        conversions release the GIL).  Resampling (librosa in the reference) is not part of the hot path: files at another
+        sample rate are rejected."""
+        import os
+        from concurrent.futures import ThreadPoolExecutor
         from scipy.io import wavfile
-        waves = []
-        for p in paths:
+
+        def decode(p):
             sr, x = wavfile.read(p)
             if sr != target_sr:
                 raise RuntimeError(f"{p}: sample rate {sr} != {target_sr} (resample before calling enhance_files)")
             if x.ndim != 1:
                 raise RuntimeError(f"{p}: expected a mono file")
             if x.dtype == np.int16:
-                x = x.astype(np.float32) / 32768.0                      # torchaudio.load's normalisation
-            elif x.dtype == np.int32:
-                x = x.astype(np.float32) / 2147483648.0
-            else:
-                x = x.astype(np.float32)
-            waves.append(x)
-        enhanced = self.enhance_list(waves, micro_batch=micro_batch)
-        if out_paths is not None:
-            import os
-            for p, x in zip(out_paths, enhanced):
-                os.makedirs(os.path.dirname(os.path.abspath(p)), exist_ok=True)
-                wavfile.write(p, target_sr, np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16))
+                return x.astype(np.float32) / 32768.0                      # torchaudio.load's normalisation
+            if x.dtype == np.int32:
+                return x.astype(np.float32) / 2147483648.0
+            return x.astype(np.float32)
+
+        def encode(args):
+            p, x = args
+            os.makedirs(os.path.dirname(os.path.abspath(p)), exist_ok=True)
+            wavfile.write(p, target_sr, np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16))
+
+        with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
+            waves = list(pool.map(decode, paths))
+            enhanced = self.enhance_list(waves, micro_batch=micro_batch)
+            if out_paths is not None:
+                list(pool.map(encode, zip(out_paths, enhanced)))
         return enhanced
 
 

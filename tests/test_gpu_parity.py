@@ -343,3 +343,27 @@ def test_second_device_without_set_device(env):
         m1.dnn(torch.zeros(1, 1, 257, 64, dtype=torch.complex64, device="cuda:0"),
                torch.zeros(1, 1, 257, 64, dtype=torch.complex64, device="cuda:1"), torch.ones(1, device="cuda:1"))
     m0.dnn.release_plans(); m1.dnn.release_plans()
+
+
+def test_ncsnpp_v2_16M_golden(golden_dir):
+    """The nf = 64 size variant (ncsnpp_v2.py:418-433; 64-channel levels run the convolution with MMA N = 64, the bottleneck's
+    128-channel attention the generic kernel) against the reference's own forward."""
+    import fdbm_oracle as O
+    from fdbm_b200 import BackboneRegistry
+    cfg = O.NcsnppConfig(nf=64, attn_resolutions=(0,))
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    net = BackboneRegistry.get_by_name("ncsnpp_v2_16M")()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    g = load_npz(f"{golden_dir}/bridge_T64.npz")
+    xt, Y, t = (torch.from_numpy(g[k]).cuda() for k in ("xt", "Y", "t"))
+    D = net(xt, Y, t)
+    err = rel_l2(D, load_npz(f"{golden_dir}/ncsnpp_16M_T64.npz")["D"])
+    print(f"ncsnpp_v2_16M T=64 rel L2 vs reference golden: {err:.3e}")
+    assert err < TOL_16BIT
+    D2 = net(xt.repeat(3, 1, 1, 1), Y.repeat(3, 1, 1, 1), t.repeat(3))
+    assert max(rel_l2(D2[i], D[0]) for i in range(3)) < 2e-5
+    for name in ("ncsnpp_v2_5M", "ncsnpp_v2_37M"):
+        with pytest.raises(NotImplementedError):
+            BackboneRegistry.get_by_name(name)()
+    net.release_plans()

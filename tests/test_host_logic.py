@@ -56,7 +56,10 @@ def test_bridge_api_surface():
 
 def test_backbone_registry_and_state_dict_names():
     from fdbm_b200 import BackboneRegistry
-    assert set(BackboneRegistry.get_all_names()) >= {"ncsnpp_v2", "ncsnpp_v2_predictive"}
+    assert set(BackboneRegistry.get_all_names()) >= {"ncsnpp_v2", "ncsnpp_v2_predictive", "ncsnpp_v2_16M", "ncsnpp_v2_5M", "ncsnpp_v2_37M",
+                                                     "tfgridnet_5l32c100", "tfgridnet_4l32c80", "tfgridnet_5l32c100_predictive"}   # backbones/__init__.py
+    n16 = BackboneRegistry.get_by_name("ncsnpp_v2_16M")(nf=128)                # the variant fixes its own size (ncsnpp_v2.py:418-427)
+    assert {k: tuple(v.shape) for k, v in n16.state_dict().items()} == O.param_shapes(O.NcsnppConfig(nf=64, attn_resolutions=(0,)))
     for name, pred, n_par in (("ncsnpp_v2", False, 65590822), ("ncsnpp_v2_predictive", True, None)):
         net = BackboneRegistry.get_by_name(name)(unused_option=1)           # accepts/ignores extra kwargs
         want = O.param_shapes(O.NcsnppConfig(predictive=pred))
