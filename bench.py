@@ -405,6 +405,89 @@ def train_main(args):
     return 0
 
 
+def tfgridnet_main(args):
+    """the backbones config.yaml / config_predictive.yaml actually select.  `--workload tfgridnet`: 5-step SB
+    sampler on tfgridnet_5l32c100; `--workload tfgridnet_predictive`: one pass of tfgridnet_5l32c100_predictive.  Same 256 synthetic
+    4 s utterances, zero padding to 64 frames (infer_single.py:64-69).  Single process (one GPU)."""
+    import torch
+    from fdbm_b200 import EnhancementModel, _lib
+    from fdbm_b200.model import PredictiveEnhancementModel
+    pred = args.workload == "tfgridnet_predictive"
+    dev = torch.device("cuda:0")
+    torch.cuda.set_device(dev)
+    _lib.check(_lib.load().fdbm_check_device(), "fdbm_check_device")
+    torch.manual_seed(0)
+    if pred:
+        model = PredictiveEnhancementModel("tfgridnet_5l32c100_predictive")
+    else:
+        model = EnhancementModel("tfgridnet_5l32c100", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
+    model = model.to(dev).eval()
+    mb = min(args.micro_batch, 32)
+    waves = synth_batch(args.utts, dev, seed=1234)
+    host_in = torch.empty(waves.shape, dtype=torch.float32, pin_memory=True).copy_(waves)
+    host_out = torch.empty_like(host_in, pin_memory=True)
+
+    def step_device():
+        return model.enhance_many(waves, micro_batch=mb)
+
+    def step_e2e():
+        for i in range(0, args.utts, mb):
+            chunk = host_in[i:i + mb].to(dev, non_blocking=True)
+            n = chunk.shape[0]
+            if n < mb:
+                chunk = torch.cat([chunk, chunk[-1:].expand(mb - n, -1)], dim=0)
+            host_out[i:i + n].copy_(model.enhance_batch(chunk)[:n], non_blocking=True)
+
+    def timed(fn, steps):
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1)
+
+    for _ in range(max(args.warmup, 3)):
+        step_device()
+    clocks = ClockSampler(0)
+    clocks.start()
+    ms = timed(step_device, args.steps)
+    clock_info = clocks.stop()
+    ms_e2e = timed(step_e2e, args.steps)
+    n_fwd = 1 if pred else BRIDGE_STEPS
+    T, Q = 256, 257
+    # algorithmic MACs of the ten BiLSTM sweeps of one forward (input + recurrent projections + ConvTranspose1d), per utterance
+    steps_intra, steps_inter = (T + 6) * (Q + 3), (Q + 6) * (T + 3)
+    gflop_fwd = 2 * 5 * 2 * (steps_intra + steps_inter) * (128 * 400 + 100 * 400 + 100 * 128) / 1e9
+    audio_s = args.utts * UTT_SECONDS
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
+    achieved = gflop_fwd * n_fwd * args.utts * args.steps / (ms * 1e-3) / 1e3
+    print(json.dumps({
+        "metric": ("enhanced audio-sec/sec (predictive tfgridnet_5l32c100_predictive, single pass)" if pred
+                   else f"enhanced audio-sec/sec ({BRIDGE_STEPS}-step SB bridge, tfgridnet_5l32c100)"),
+        "value": audio_s * args.steps / (ms * 1e-3), "unit": UNIT, "n_gpus": 1, "steps": args.steps, "warmup": max(args.warmup, 3),
+        "ms_per_step": ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "fp16", "data": "synthetic",
+        "config": {"workload": f"{args.workload}: {args.utts} synthetic 4 s 16 kHz utterances, " +
+                               ("tfgridnet_5l32c100_predictive (2.11 M params, PyTorch default init), one pass" if pred else
+                                f"tfgridnet_5l32c100 (2.16 M params, PyTorch default init), Bridge('sb','bb') ode_ei N={BRIDGE_STEPS}"),
+                   "utterances": args.utts, "bridge_steps": n_fwd},
+        "run": {"micro_batch": mb, "l2": "ConvTranspose1d partials of one sweep are > 1 GB at micro-batch 32 (>> L2)"},
+        "e2e": {"value": audio_s * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": args.utts * N_SAMPLES * 4,
+                "d2h_bytes_per_step": args.utts * N_SAMPLES * 4, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": ((args.utts + mb - 1) // mb) * (3 + n_fwd * (4 + 5 * 10 + 1)) * args.steps,
+        "roofline": {"bound": "tensor", "kernel": "lstm_sweep_kernel (persistent BiLSTM, mma.sync m16n8k16 fp16, weights resident in shared memory)",
+                     "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
+                     "note": f"algorithmic {gflop_fwd:.1f} GFLOP of LSTM + ConvTranspose1d work per forward per utterance over the WHOLE step time"},
+        "clocks": clock_info}))
+    return 0
+
+
 def files_main(args):
     """SURVEY.md 8(f) #2, the callers' I/O edge of infer_folder.py:91-146: a folder of WAV files of DIFFERENT lengths
     (2-6 s), timed from the file names to the written enhanced files: decode, length bucketing, pinned staging + H2D,
@@ -420,7 +503,7 @@ def files_main(args):
     model = EnhancementModel("ncsnpp_v2", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
     sensitise_(model.dnn, seed=0)
     model = model.to(dev).eval()
-    mb = min(args.micro_batch, 32)
+    mb = min(args.micro_batch, 64)                # five padded-length buckets of ~50 files each: one micro-batch per bucket
     rng = np.random.default_rng(7)
     tmp = tempfile.mkdtemp(prefix="fdbm_files_")
     paths, outs, total_s = [], [], 0.0
@@ -464,7 +547,7 @@ def main():
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "128")))
     ap.add_argument("--utts", type=int, default=UTTS_PER_GPU, help="utterances per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train", "files"],
+    ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train", "files", "tfgridnet", "tfgridnet_predictive"],
                     help="BASELINE.json configs[1] (default, the headline metric), configs[2] or configs[3] (training step)")
     ap.add_argument("--train-batch", type=int, default=16, help="training crops per GPU per step (configs[3]: 8 x 16)")
     ap.add_argument("--bridge-steps", type=int, default=5, help="configs[4]: sampling-step sweep 1/5/10/30")
@@ -480,6 +563,8 @@ def main():
         return train_main(args)
     if args.workload == "files":
         return files_main(args)
+    if args.workload.startswith("tfgridnet"):
+        return tfgridnet_main(args)
 
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))

@@ -25,20 +25,22 @@ namespace {
 
 constexpr int NFFT = 512;
 constexpr int NBIN = NFFT / 2 + 1;
-// Warps per block.  A block stages [257 bins][4 * FWARPS frames] and moves it with 32 * FWARPS contiguous bytes per bin.  With
-// 4 warps (128-byte pieces at the 2 KB row pitch of the [B,1,257,T] layout) the kernels ran at the same 2.2 / 1.3 TB/s as the
-// first generation although they issue 2.6 x / 4 x fewer instructions: HBM sees one row activation per 128 bytes.  16 warps
-// move 512 contiguous bytes per bin.
+// Warps per block.  A block stages [257 bins][4 * FWARPS frames] and moves it with 32 * FWARPS contiguous bytes per bin.
+// Measured (256 x 4 s, B200): 2 / 4 / 8 / 16 warps -> STFT 89 / 88 / 102-118 / 133 us, iSTFT 162 / 136-155 / 157-178 / 145 us.  The
+// kernels issue 2.5 x / 4 x fewer instructions than the first generation (ncu: 25.9 M vs 64 M warp instructions for the STFT)
+// but are now latency-bound: ~100 registers per thread allow 16-20 warps per SM, issue slots are 20 % busy, a warp issues
+// every 20 cycles, 37 % of the stall cycles are the block barriers around the staging tile -- larger blocks make that worse,
+// more resident blocks (FDBM_SPEC_MINBLOCKS 5, 6) change nothing or spill.
 #ifndef FDBM_SPEC_WARPS
 #define FDBM_SPEC_WARPS 4
 #endif
 // FDBM_SPEC_TW_GLOBAL: read the packed twiddle table from global memory (L1-resident, 9 KB) instead of a per-block shared copy;
 // FDBM_SPEC_MINBLOCKS: resident blocks per SM the register allocation must allow
 #ifndef FDBM_SPEC_TW_GLOBAL
-#define FDBM_SPEC_TW_GLOBAL 0
+#define FDBM_SPEC_TW_GLOBAL 1
 #endif
 #ifndef FDBM_SPEC_MINBLOCKS
-#define FDBM_SPEC_MINBLOCKS 1
+#define FDBM_SPEC_MINBLOCKS 5
 #endif
 constexpr int FWARPS = FDBM_SPEC_WARPS;
 constexpr int FPW = 4;                    // frames per warp
