@@ -383,20 +383,25 @@ int fdbm_attention(const void* q, const void* k, const void* v, int batch, int L
 /* ---------------------------------------------------------------------------------------------
  * TF-GridNet backbones (fdbm/backbones/tfgridnet.py:126-229 TFGridNet.forward, :236-427 GridNetV3Block, :430-484 the
  * normalisation layers; tfgridnet_predictive.py): tfgridnet_5l32c100 is the backbone config.yaml selects.  Geometry:
- * emb_dim 32, emb_ks 4, emb_hs 1, 4 heads, E = 2, hidden <= 104.  Activations are fp32 [B, T, Q, 32] (Q = 257 bins, channels
+ * emb_dim 32, emb_ks 4, emb_hs 1, 4 heads, E = 2, hidden <= 112.  Activations are fp32 [B, T, Q, 32] (Q = 257 bins, channels
  * innermost); "padded" tensors are [B, T+6, Q+6, 32] (tfgridnet.py:329-334).  One block of the network is
  *   fdbm_tfg_pad_add_norm -> fdbm_tfg_lstm_sweep (intra) -> fdbm_tfg_sweep_post(mode 0) -> fdbm_tfg_lstm_sweep (inter)
  *   -> fdbm_tfg_sweep_post(mode 1) -> fdbm_tfg_attention.
- *   fdbm_tfg_lstm_pack   one direction (0 forward, 1 reverse) of an nn.LSTM layer (weight_ih [4H,128], weight_hh [4H,H], biases,
- *                        PyTorch gate order i,f,g,o) + that direction's half of the ConvTranspose1d weight [2H,32,4]
- *                        (tfgridnet.py:257-259) -> fp16 tensor-core fragments, fdbm_tfg_lstm_pack_bytes() bytes
+ *   fdbm_tfg_lstm_pack   both directions of an nn.LSTM layer (weight_ih [4H,128], weight_hh [4H,H], biases, PyTorch gate order
+ *                        i,f,g,o; w = 8 device pointers, forward w_ih w_hh b_ih b_hh then reverse, as a HOST array) + the
+ *                        ConvTranspose1d weight [2H,32,4] (tfgridnet.py:257-259) -> the four shared-memory images
+ *                        [direction][cta rank] of the sweep, fdbm_tfg_lstm_pack_bytes() bytes; hidden <= 112
  *   fdbm_tfg_lstm_sweep  the bidirectional LSTM over n_seq sequences of L steps whose input at step s is the 4 x 32 window
- *                        xn[pos s .. s+3] of the LayerNorm-ed fp16 tensor (F.unfold, tfgridnet.py:337-341); sequence
- *                        seq = outer * n_inner + inner starts at outer * outer_stride + inner * inner_stride, positions are
- *                        pos_stride apart (elements).  Output per direction: fp16 [n_seq][L][4 taps * 32] = h_s W_lin.
- *   fdbm_tfg_sweep_post  ConvTranspose1d's tap sum + bias + residual (tfgridnet.py:346-350, :371-375); mode 0 (after intra):
- *                        full padded tensor out_full + its LayerNorm xn (fp16) for the inter sweep; mode 1 (after inter): the
- *                        crop [B,T,Q,32] (tfgridnet.py:381)
+ *                        xn[pos s .. s+3] of the LayerNorm-ed fp16 tensor (F.unfold, tfgridnet.py:337-341), xn contiguous
+ *                        [n_seq][L+3][32].  tcgen05: a cluster of two CTAs owns 128 sequences of one direction, each holds the
+ *                        gate columns of 56 of the 112 padded hidden units in shared memory, the gate GEMM of a step is UMMA
+ *                        M=128 N=224 K=256 into TMEM, the new hidden state is exchanged through distributed shared memory.
+ *                        Output per direction: fp16 [n_seq][L+3][32] = ConvTranspose1d(h) with its four taps overlap-added
+ *                        (bias not included).
+ *   fdbm_tfg_sweep_post  both directions' outputs + bias + residual (tfgridnet.py:346-350, :371-375); mode 0 (after intra):
+ *                        full padded tensor out_full + its LayerNorm xn (fp16) for the inter sweep, written [B,Q+6,T+6,32] when
+ *                        xn_transposed (the inter sweep's sequences contiguous), else [B,T+6,Q+6,32]; mode 1 (after inter):
+ *                        the crop [B,T,Q,32] (tfgridnet.py:381)
  *   fdbm_tfg_pad_add_norm  xp = pad(h + emb[b, :]) (tfgridnet.py:217, :334), xn = fp16 LayerNorm(xp) (intra_norm); emb may be NULL
  *   fdbm_tfg_input       Conv2d(Cin -> 32, 3x3) + GroupNorm(1, 32) on complex [B,1,Q,T] inputs (tfgridnet.py:152-155, 201-214);
  *                        Cin = 4 (x.re, x.im, y.re, y.im) or 2 (predictive: pass the input as x, y = NULL); sums: 2*B doubles
@@ -408,14 +413,13 @@ int fdbm_attention(const void* q, const void* k, const void* v, int batch, int L
  *                        (a HOST array).  workspace: fdbm_tfg_attention_workspace_bytes(), 256-byte aligned.
  *   fdbm_tfg_output      ConvTranspose2d(32 -> 2, 3x3, padding 1) -> complex [B,1,Q,T] (tfgridnet.py:175, 221-226) */
 int64_t fdbm_tfg_lstm_pack_bytes(void);
-int fdbm_tfg_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_lin, int hidden,
-                       int dir, void* packed, void* stream);
-int fdbm_tfg_lstm_sweep(const void* xn, int n_seq, int n_inner, int64_t outer_stride, int64_t inner_stride, int64_t pos_stride, int L,
-                        const void* packed_fw, const void* packed_bw, void* y_fw, void* y_bw, void* stream);
+int fdbm_tfg_lstm_pack(const float* const* w, const float* w_lin, int hidden, void* packed, void* stream);
+int fdbm_tfg_lstm_sweep(const void* xn, int n_seq, int L, const void* packed, void* y_fw, void* y_bw, void* stream);
 int fdbm_tfg_pad_add_norm(const float* h, const float* emb, const float* gamma, const float* beta, int batch, int T, int Q, float eps,
                           float* xp, void* xn, void* stream);
 int fdbm_tfg_sweep_post(const void* y_fw, const void* y_bw, const float* lin_bias, const float* resid, int batch, int T, int Q, int mode,
-                        const float* gamma, const float* beta, float eps, float* out_full, void* xn, float* out_crop, void* stream);
+                        const float* gamma, const float* beta, float eps, float* out_full, void* xn, float* out_crop, int xn_transposed,
+                        void* stream);
 int fdbm_tfg_input(const float* x, const float* y, const float* w, const float* bias, const float* gn_w, const float* gn_b, int batch,
                    int T, int Q, int Cin, float eps, double* sums, float* out, void* stream);
 int fdbm_tfg_time_embedding(const float* t, int t_stride, const float* fourier_w, const float* w1, const float* b1, const float* w2,

@@ -3,22 +3,10 @@
 //
 // 97 % of the arithmetic is the ten bidirectional LSTM sweeps of a forward (intra: one sequence of 260 unfolded positions
 // along frequency per (utterance, frame); inter: one sequence along time per (utterance, bin)); a 4 s utterance is
-// ~250 GFLOP.  The recurrence is sequential in the position, so the sweep is a PERSISTENT kernel: one CTA owns 128 sequences
-// of one direction for all steps, keeps the whole gate matrix [K = 128 inputs + 112 hidden] x [N = 416 gate columns]
-// (fp16, pre-swizzled into mma B-fragments, 195 KB) and the ConvTranspose1d matrix (28 KB) in shared memory, the hidden
-// state as mma A-fragments and the cell state in registers, and issues per step 780 + 112 tensor-core MMAs per warp:
-//   * gate columns are ordered [unit group of 8][gate i,f,g,o][unit]: a thread's accumulator fragments of the four gate
-//     tiles of a group hold all four gates of the same two units, so the point-wise cell update needs no shuffles, and the
-//     new hidden values ARE next step's A-fragment (C-fragment columns 2tq,2tq+1 of group G = A-fragment columns of k-tile
-//     G/2): the recurrent operand never leaves registers;
-//   * the unfolded LSTM input (emb_ks = 4 neighbouring positions x 32 channels, tfgridnet.py:337-341) is a sliding window
-//     over the LayerNorm-ed sequence: with the input columns ordered [tap][channel] a step shifts the window by two k-tiles,
-//     so only the 32 channels of ONE new position are loaded per step (prefetched a step ahead);
-//   * ConvTranspose1d (tfgridnet.py:346 / :371) is applied to the fresh hidden state in the same step (h_t W_lin ->
-//     [4 taps x 32 channels], fp16 to HBM); a light pass adds the four shifted taps of both directions, the bias and the
-//     residual, and produces the next LayerNorm.
-// Everything else (3x3 input conv + GroupNorm, time embedding, the attention's 1x1 convs / PReLU-LayerNorms, two batched
-// tensor-core GEMMs for Q K^T and P V, the output ConvTranspose2d) is small and HBM / latency bound.
+// ~250 GFLOP.  The sweep is the tcgen05 cluster kernel in tfg_lstm_tc.cu; this file holds everything around it: the fused
+// pad + time-embedding add + LayerNorm pass, the pass after a sweep (bias + both directions + residual + next LayerNorm / crop),
+// the 3x3 input conv + GroupNorm, the time embedding, the attention (1x1 convs / PReLU-LayerNorms, two batched tensor-core
+// GEMMs for Q K^T and P V, projection) and the output ConvTranspose2d -- all HBM / latency bound.
 #include <mma.h>
 #include "common.cuh"
 
@@ -26,206 +14,13 @@ namespace fdbm {
 namespace {
 
 constexpr int TC = 32;            // emb_dim
-constexpr int TKS = 4;            // emb_ks (emb_hs = 1)
 constexpr int OLP = 3;            // emb_ks - emb_hs
-constexpr int HPAD = 112;         // hidden units padded to 7 k-tiles
-constexpr int NGRP = 13;          // unit groups of 8 (104 >= 100 units)
-constexpr int KT_IN = 8, KT_H = 7, KT = KT_IN + KT_H;
-constexpr int NT = NGRP * 4;      // 52 gate n-tiles
-constexpr int NT_LIN = 16;        // 128 = 4 taps x 32 channels
-constexpr int SEQ_PER_CTA = 128;
-constexpr int LSTM_THREADS = 256;
-constexpr size_t WG_BYTES = static_cast<size_t>(KT) * NT * 32 * 8;            // 199680
-constexpr size_t WL_BYTES = static_cast<size_t>(KT_H) * NT_LIN * 32 * 8;      // 28672
-constexpr size_t BIAS_BYTES = NT * 8 * 4;                                     // 1664
-constexpr size_t LSTM_SMEM = WG_BYTES + WL_BYTES + BIAS_BYTES;
-
 __device__ __forceinline__ void mma16816(float (&c)[4], const uint32_t (&a)[4], uint2 b) {
   asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b.x), "r"(b.y));
 }
-__device__ __forceinline__ float tanh_fast(float x) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
-
-// ---- weight packing: reference layout -> mma B-fragments ------------------------------------------------------------
-// gates: wfrag[kt][nt][lane] = (half2 B[k0..k0+1][n], half2 B[k0+8..k0+9][n]),  k0 = 16 kt + 2 (lane & 3), n = lane >> 2
-//   k < 128: input feature f' = tap * 32 + c  <- weight_ih[row][c * 4 + tap];  k >= 128: hidden unit k - 128 <- weight_hh
-//   column (nt, n): group G = nt / 4, gate = nt % 4, unit = 8 G + n  <- row = gate * H + unit  (PyTorch gate order i, f, g, o)
-__global__ void pack_lstm_kernel(const float* __restrict__ w_ih, const float* __restrict__ w_hh, const float* __restrict__ b_ih,
-                                 const float* __restrict__ b_hh, const float* __restrict__ w_lin, int H, int dir,
-                                 uint2* __restrict__ wg, uint2* __restrict__ wl, float* __restrict__ bias) {
-  const int total = KT * NT * 32;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total; e += gridDim.x * blockDim.x) {
-    const int lane = e & 31, nt = (e >> 5) % NT, kt = (e >> 5) / NT;
-    const int n = lane >> 2, tq = lane & 3;
-    const int G = nt >> 2, gate = nt & 3, unit = 8 * G + n;
-    auto val = [&](int k) -> float {
-      if (unit >= H) return 0.f;
-      const int row = gate * H + unit;
-      if (k < 128) { const int tap = k >> 5, c = k & 31; return w_ih[row * (TC * TKS) + c * TKS + tap]; }
-      const int j = k - 128;
-      return j < H ? w_hh[row * H + j] : 0.f;
-    };
-    const int k0 = 16 * kt + 2 * tq;
-    wg[e] = make_uint2(pack_h2(val(k0), val(k0 + 1)), pack_h2(val(k0 + 8), val(k0 + 9)));
-  }
-  // ConvTranspose1d weight [2H, C, ks]: this direction's rows dir * H + unit; column = tap * 32 + c
-  const int total_l = KT_H * NT_LIN * 32;
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < total_l; e += gridDim.x * blockDim.x) {
-    const int lane = e & 31, nt = (e >> 5) % NT_LIN, kt = (e >> 5) / NT_LIN;
-    const int n = lane >> 2, tq = lane & 3;
-    const int col = nt * 8 + n, tap = col >> 5, c = col & 31;
-    auto val = [&](int j) -> float { return j < H ? w_lin[((dir * H + j) * TC + c) * TKS + tap] : 0.f; };
-    const int k0 = 16 * kt + 2 * tq;
-    wl[e] = make_uint2(pack_h2(val(k0), val(k0 + 1)), pack_h2(val(k0 + 8), val(k0 + 9)));
-  }
-  for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NT * 8; e += gridDim.x * blockDim.x) {
-    const int nt = e >> 3, n = e & 7, G = nt >> 2, gate = nt & 3, unit = 8 * G + n;
-    bias[e] = unit < H ? b_ih[gate * H + unit] + b_hh[gate * H + unit] : 0.f;
-  }
-}
-
-// ---- the persistent BiLSTM sweep -------------------------------------------------------------------------------------
-struct LstmArgs {
-  const __half* xn;          // LayerNorm-ed input, fp16; element (seq, pos, c) at seq_base(seq) + pos * pos_stride + c
-  int n_seq, n_inner;        // sequences; seq = outer * n_inner + inner
-  int64_t outer_stride, inner_stride, pos_stride;
-  int L;                     // steps (positions - 3)
-  const uint2* wg[2]; const uint2* wl[2]; const float* bias[2];
-  __half* y[2];              // per direction [n_seq][L][128] fp16: h_t W_lin
-};
-
-__global__ void __launch_bounds__(LSTM_THREADS, 1) lstm_sweep_kernel(const LstmArgs a) {
-  extern __shared__ __align__(16) uint8_t smem[];
-  uint2* s_wg = reinterpret_cast<uint2*>(smem);
-  uint2* s_wl = reinterpret_cast<uint2*>(smem + WG_BYTES);
-  float* s_bias = reinterpret_cast<float*>(smem + WG_BYTES + WL_BYTES);
-  const int dir = blockIdx.y;
-  {
-    const uint4* src = reinterpret_cast<const uint4*>(a.wg[dir]);
-    uint4* dst = reinterpret_cast<uint4*>(s_wg);
-    for (int i = threadIdx.x; i < static_cast<int>(WG_BYTES / 16); i += LSTM_THREADS) dst[i] = __ldg(src + i);
-    const uint4* src2 = reinterpret_cast<const uint4*>(a.wl[dir]);
-    uint4* dst2 = reinterpret_cast<uint4*>(s_wl);
-    for (int i = threadIdx.x; i < static_cast<int>(WL_BYTES / 16); i += LSTM_THREADS) dst2[i] = __ldg(src2 + i);
-    for (int i = threadIdx.x; i < NT * 8; i += LSTM_THREADS) s_bias[i] = __ldg(a.bias[dir] + i);
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, tq = lane & 3;
-  const int seq0 = blockIdx.x * SEQ_PER_CTA + warp * 16;
-  int row_seq[2] = {seq0 + g, seq0 + g + 8};
-  bool ok[2];
-  const __half* base[2];
-#pragma unroll
-  for (int r = 0; r < 2; ++r) {
-    ok[r] = row_seq[r] < a.n_seq;
-    const int sq = ok[r] ? row_seq[r] : 0;
-    base[r] = a.xn + static_cast<int64_t>(sq / a.n_inner) * a.outer_stride + static_cast<int64_t>(sq % a.n_inner) * a.inner_stride;
-  }
-  // A-fragments: u[kt] for the 8 input k-tiles (tap = kt / 2, channels 16 (kt & 1) ..), h[kt] for the 7 hidden k-tiles
-  uint32_t u[KT_IN][4], h[KT_H][4];
-  float c[NGRP][4];                       // cell state: rows g / g+8 x units (8G + 2tq, +1)
-#pragma unroll
-  for (int kt = 0; kt < KT_H; ++kt) { h[kt][0] = h[kt][1] = h[kt][2] = h[kt][3] = 0u; }
-#pragma unroll
-  for (int G = 0; G < NGRP; ++G) { c[G][0] = c[G][1] = c[G][2] = c[G][3] = 0.f; }
-  // loads of one position's 32 channels as two k-tiles of A-fragments
-  auto load_pos = [&](int pos, uint32_t (&t0)[4], uint32_t (&t1)[4]) {
-#pragma unroll
-    for (int r = 0; r < 2; ++r) {
-      const uint32_t* p = reinterpret_cast<const uint32_t*>(base[r] + static_cast<int64_t>(pos) * a.pos_stride);
-      // channels 2tq,2tq+1 | +8 of each 16-channel half
-      const uint32_t v0 = ok[r] ? __ldg(p + tq) : 0u, v1 = ok[r] ? __ldg(p + tq + 4) : 0u;
-      const uint32_t v2 = ok[r] ? __ldg(p + 8 + tq) : 0u, v3 = ok[r] ? __ldg(p + 12 + tq) : 0u;
-      t0[r] = v0; t0[2 + r] = v1; t1[r] = v2; t1[2 + r] = v3;
-    }
-  };
-  const int L = a.L;
-  const bool rev = dir == 1;
-  // first step's window: positions s .. s + 3
-  {
-    const int s = rev ? L - 1 : 0;
-#pragma unroll
-    for (int tap = 0; tap < 4; ++tap) load_pos(s + tap, u[2 * tap], u[2 * tap + 1]);
-  }
-  uint32_t nx0[4], nx1[4];                // the one new position of the NEXT step
-  for (int step = 0; step < L; ++step) {
-    const int s = rev ? L - 1 - step : step;
-    const bool more = step + 1 < L;
-    if (more) load_pos(rev ? s - 1 : s + 4, nx0, nx1);
-    uint32_t hn[KT_H][4];
-#pragma unroll
-    for (int kt = 0; kt < KT_H; ++kt) { hn[kt][0] = hn[kt][1] = hn[kt][2] = hn[kt][3] = 0u; }
-#pragma unroll
-    for (int G = 0; G < NGRP; ++G) {
-      float acc[4][4];
-#pragma unroll
-      for (int gate = 0; gate < 4; ++gate) {
-        const float2 b = *reinterpret_cast<const float2*>(s_bias + (G * 4 + gate) * 8 + 2 * tq);
-        acc[gate][0] = b.x; acc[gate][1] = b.y; acc[gate][2] = b.x; acc[gate][3] = b.y;
-      }
-#pragma unroll
-      for (int kt = 0; kt < KT; ++kt) {
-        const uint2* wrow = s_wg + (static_cast<size_t>(kt) * NT + G * 4) * 32 + lane;
-#pragma unroll
-        for (int gate = 0; gate < 4; ++gate) {
-          if (kt < KT_IN) mma16816(acc[gate], u[kt], wrow[gate * 32]);
-          else mma16816(acc[gate], h[kt - KT_IN], wrow[gate * 32]);
-        }
-      }
-      // point-wise cell update of units (8G + 2tq, +1), rows g and g+8  (tfgridnet uses nn.LSTM: i, f, g, o)
-      float hv[4];
-#pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float ig = sigmoid_fast(acc[0][e]), fg = sigmoid_fast(acc[1][e]), gg = tanh_fast(acc[2][e]), og = sigmoid_fast(acc[3][e]);
-        const float cn = fmaf(fg, c[G][e], ig * gg);
-        c[G][e] = cn;
-        hv[e] = og * tanh_fast(cn);
-      }
-      // C-fragment (rows g | g+8, cols 2tq, 2tq+1 of group G) -> A-fragment of k-tile G / 2, left (G even) or right half
-      hn[G >> 1][(G & 1) * 2 + 0] = pack_h2(hv[0], hv[1]);
-      hn[G >> 1][(G & 1) * 2 + 1] = pack_h2(hv[2], hv[3]);
-    }
-#pragma unroll
-    for (int kt = 0; kt < KT_H; ++kt) { h[kt][0] = hn[kt][0]; h[kt][1] = hn[kt][1]; h[kt][2] = hn[kt][2]; h[kt][3] = hn[kt][3]; }
-    // y_s = h_s W_lin  -> fp16 [seq][s][tap * 32 + c]
-#pragma unroll
-    for (int nb = 0; nb < NT_LIN; nb += 4) {
-      float acc[4][4];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) { acc[j][0] = acc[j][1] = acc[j][2] = acc[j][3] = 0.f; }
-#pragma unroll
-      for (int kt = 0; kt < KT_H; ++kt) {
-        const uint2* wrow = s_wl + (static_cast<size_t>(kt) * NT_LIN + nb) * 32 + lane;
-#pragma unroll
-        for (int j = 0; j < 4; ++j) mma16816(acc[j], h[kt], wrow[j * 32]);
-      }
-#pragma unroll
-      for (int r = 0; r < 2; ++r) {
-        if (!ok[r]) continue;
-        uint32_t* dst = reinterpret_cast<uint32_t*>(a.y[dir] + (static_cast<int64_t>(row_seq[r]) * L + s) * 128);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) dst[(nb + j) * 4 + tq] = pack_h2(acc[j][2 * r], acc[j][2 * r + 1]);
-      }
-    }
-    // slide the input window by one position
-    if (more) {
-      if (!rev) {
-#pragma unroll
-        for (int kt = 0; kt < KT_IN - 2; ++kt) { u[kt][0] = u[kt + 2][0]; u[kt][1] = u[kt + 2][1]; u[kt][2] = u[kt + 2][2]; u[kt][3] = u[kt + 2][3]; }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { u[KT_IN - 2][e] = nx0[e]; u[KT_IN - 1][e] = nx1[e]; }
-      } else {
-#pragma unroll
-        for (int kt = KT_IN - 1; kt >= 2; --kt) { u[kt][0] = u[kt - 2][0]; u[kt][1] = u[kt - 2][1]; u[kt][2] = u[kt - 2][2]; u[kt][3] = u[kt - 2][3]; }
-#pragma unroll
-        for (int e = 0; e < 4; ++e) { u[0][e] = nx0[e]; u[1][e] = nx1[e]; }
-      }
-    }
-  }
-}
 
 // ---- per-position passes ---------------------------------------------------------------------------------------------
 // LayerNorm over the 32 channels of one position: one warp per position, lane = channel
@@ -234,11 +29,23 @@ __device__ __forceinline__ float warp_sum(float v) {
   for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
   return v;
 }
-__device__ __forceinline__ float ln32(float v, float gamma, float beta, float eps) {
-  const float mu = warp_sum(v) * (1.0f / 32.0f);
-  const float d = v - mu;
-  const float var = warp_sum(d * d) * (1.0f / 32.0f);
-  return d * rsqrtf(var + eps) * gamma + beta;
+
+// Position-wise kernels below: 8 lanes own one position (4 channels each, 16-byte accesses), a warp four positions per
+// iteration, so a warp instruction moves 512 contiguous bytes and LayerNorm(32) is a 3-step shuffle inside the 8-lane group.
+__device__ __forceinline__ float group8_sum(float v) {
+  v += __shfl_xor_sync(0xffffffffu, v, 1); v += __shfl_xor_sync(0xffffffffu, v, 2); v += __shfl_xor_sync(0xffffffffu, v, 4);
+  return v;
+}
+__device__ __forceinline__ float4 ln32_q(float4 v, float4 ga, float4 be, float eps) {
+  const float mu = group8_sum(v.x + v.y + v.z + v.w) * (1.0f / 32.0f);
+  const float4 d = make_float4(v.x - mu, v.y - mu, v.z - mu, v.w - mu);
+  const float r = rsqrtf(group8_sum(d.x * d.x + d.y * d.y + d.z * d.z + d.w * d.w) * (1.0f / 32.0f) + eps);
+  return make_float4(d.x * r * ga.x + be.x, d.y * r * ga.y + be.y, d.z * r * ga.z + be.z, d.w * r * ga.w + be.w);
+}
+__device__ __forceinline__ uint2 pack_h4(float4 v) { return make_uint2(pack_h2(v.x, v.y), pack_h2(v.z, v.w)); }
+__device__ __forceinline__ float4 unpack_h4(uint2 u) {
+  const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&u.x)), b = __half22float2(*reinterpret_cast<const __half2*>(&u.y));
+  return make_float4(a.x, a.y, b.x, b.y);
 }
 
 // xp[b, t', q', c] = (inside ? h[b, t, q, c] + emb[b, c] : 0);  xn = fp16 LayerNorm(xp)   (tfgridnet.py:206, :329-334)
@@ -247,54 +54,51 @@ pad_add_norm_kernel(const float* __restrict__ hcur, const float* __restrict__ em
                     int B, int T, int Q, float eps, float* __restrict__ xp, __half* __restrict__ xn) {
   const int Tp = T + 2 * OLP, Qp = Q + 2 * OLP;
   const int64_t n_pos = static_cast<int64_t>(B) * Tp * Qp;
-  const int lane = threadIdx.x & 31;
-  const float ga = __ldg(gamma + lane), be = __ldg(beta + lane);
-  for (int64_t p = blockIdx.x * 8ll + (threadIdx.x >> 5); p < n_pos; p += 8ll * gridDim.x) {
+  const int lane = threadIdx.x & 31, cq = lane & 7;
+  const float4 ga = __ldg(reinterpret_cast<const float4*>(gamma) + cq), be = __ldg(reinterpret_cast<const float4*>(beta) + cq);
+  for (int64_t p = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * 4 + (lane >> 3); p < n_pos; p += 32ll * gridDim.x) {
     const int qp = static_cast<int>(p % Qp), tp = static_cast<int>((p / Qp) % Tp), b = static_cast<int>(p / (static_cast<int64_t>(Qp) * Tp));
     const int t = tp - OLP, q = qp - OLP;
-    float v = 0.f;
-    if (t >= 0 && t < T && q >= 0 && q < Q)
-      v = hcur[((static_cast<int64_t>(b) * T + t) * Q + q) * TC + lane] + (emb ? __ldg(emb + b * TC + lane) : 0.f);
-    xp[p * TC + lane] = v;
-    xn[p * TC + lane] = __float2half_rn(ln32(v, ga, be, eps));
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T && q >= 0 && q < Q) {
+      v = __ldg(reinterpret_cast<const float4*>(hcur + ((static_cast<int64_t>(b) * T + t) * Q + q) * TC) + cq);
+      if (emb) { const float4 e = __ldg(reinterpret_cast<const float4*>(emb + b * TC) + cq); v.x += e.x; v.y += e.y; v.z += e.z; v.w += e.w; }
+    }
+    reinterpret_cast<float4*>(xp + p * TC)[cq] = v;
+    reinterpret_cast<uint2*>(xn + p * TC)[cq] = pack_h4(ln32_q(v, ga, be, eps));
   }
 }
 
-// After a sweep: out[seq, pos, c] = bias[c] + sum_tap (yf + yb)[seq, pos - tap, tap * 32 + c] + resid[seq, pos, c]
-// (ConvTranspose1d with stride 1 + residual, tfgridnet.py:346-350 / :371-375).  intra (mode 0): writes the full padded
-// tensor and its LayerNorm for the inter sweep.  inter (mode 1): writes only the un-padded crop [B,T,Q,C] (:381).
+// After a sweep: out[b, t', q', c] = bias[c] + yf + yb + resid, where yf / yb are the sweep's per-direction ConvTranspose1d
+// outputs [seq][pos][32] (taps already overlap-added; tfgridnet.py:346-350 / :371-375).  intra (mode 0, seq = (b, t'), pos = q'):
+// writes the full padded tensor and its LayerNorm for the inter sweep.  inter (mode 1, seq = (b, q'), pos = t'): writes only the
+// un-padded crop [B,T,Q,C] (:381).
 __global__ void __launch_bounds__(256)
 sweep_post_kernel(const __half* __restrict__ yf, const __half* __restrict__ yb, const float* __restrict__ lin_bias, const float* __restrict__ resid,
                   int B, int T, int Q, int mode, const float* __restrict__ gamma, const float* __restrict__ beta, float eps,
-                  float* __restrict__ out_full, __half* __restrict__ xn, float* __restrict__ out_crop) {
+                  float* __restrict__ out_full, __half* __restrict__ xn, float* __restrict__ out_crop, int xn_transposed) {
   const int Tp = T + 2 * OLP, Qp = Q + 2 * OLP;
-  const int lane = threadIdx.x & 31;
-  const float lb = __ldg(lin_bias + lane);
-  const float ga = gamma ? __ldg(gamma + lane) : 1.f, be = beta ? __ldg(beta + lane) : 0.f;
-  const int L = (mode == 0 ? Qp : Tp) - OLP;
+  const int lane = threadIdx.x & 31, cq = lane & 7;
+  const float4 lb = __ldg(reinterpret_cast<const float4*>(lin_bias) + cq);
+  const float4 one = make_float4(1.f, 1.f, 1.f, 1.f), zero = make_float4(0.f, 0.f, 0.f, 0.f);
+  const float4 ga = gamma ? __ldg(reinterpret_cast<const float4*>(gamma) + cq) : one, be = beta ? __ldg(reinterpret_cast<const float4*>(beta) + cq) : zero;
   const int64_t n_pos = mode == 0 ? static_cast<int64_t>(B) * Tp * Qp : static_cast<int64_t>(B) * T * Q;
-  for (int64_t p = blockIdx.x * 8ll + (threadIdx.x >> 5); p < n_pos; p += 8ll * gridDim.x) {
+  for (int64_t p = (blockIdx.x * 8ll + (threadIdx.x >> 5)) * 4 + (lane >> 3); p < n_pos; p += 32ll * gridDim.x) {
     int b, tp, qp;
     if (mode == 0) { qp = static_cast<int>(p % Qp); tp = static_cast<int>((p / Qp) % Tp); b = static_cast<int>(p / (static_cast<int64_t>(Qp) * Tp)); }
     else { qp = static_cast<int>(p % Q) + OLP; tp = static_cast<int>((p / Q) % T) + OLP; b = static_cast<int>(p / (static_cast<int64_t>(Q) * T)); }
-    const int64_t seq = mode == 0 ? static_cast<int64_t>(b) * Tp + tp : static_cast<int64_t>(b) * Qp + qp;
-    const int pos = mode == 0 ? qp : tp;
-    float acc = lb;
-#pragma unroll
-    for (int tap = 0; tap < TKS; ++tap) {
-      const int s = pos - tap;
-      if (s >= 0 && s < L) {
-        const int64_t o = (seq * L + s) * 128 + tap * 32 + lane;
-        acc += __half2float(yf[o]) + __half2float(yb[o]);
-      }
-    }
     const int64_t pfull = (static_cast<int64_t>(b) * Tp + tp) * Qp + qp;
-    acc += resid[pfull * TC + lane];
+    const int64_t ptr = (static_cast<int64_t>(b) * Qp + qp) * Tp + tp;
+    const int64_t py = mode == 0 ? pfull : ptr;
+    const float4 f = unpack_h4(__ldg(reinterpret_cast<const uint2*>(yf + py * TC) + cq)), r = unpack_h4(__ldg(reinterpret_cast<const uint2*>(yb + py * TC) + cq));
+    const float4 x = __ldg(reinterpret_cast<const float4*>(resid + pfull * TC) + cq);
+    const float4 acc = make_float4(lb.x + f.x + r.x + x.x, lb.y + f.y + r.y + x.y, lb.z + f.z + r.z + x.z, lb.w + f.w + r.w + x.w);
     if (mode == 0) {
-      out_full[pfull * TC + lane] = acc;
-      xn[pfull * TC + lane] = __float2half_rn(ln32(acc, ga, be, eps));
+      reinterpret_cast<float4*>(out_full + pfull * TC)[cq] = acc;
+      // xn_transposed: [B, Q', T', C], the inter sweep's sequences (one per padded bin) contiguous along time
+      reinterpret_cast<uint2*>(xn + (xn_transposed ? ptr : pfull) * TC)[cq] = pack_h4(ln32_q(acc, ga, be, eps));
     } else {
-      out_crop[p * TC + lane] = acc;
+      reinterpret_cast<float4*>(out_crop + p * TC)[cq] = acc;
     }
   }
 }
@@ -389,60 +193,117 @@ tfg_temb_kernel(const float* __restrict__ t, int t_stride, const float* __restri
 }
 
 // attention front: 1x1 convs Q (8), K (8), V (32) + per-head PReLU + normalisation over the head's E channels + affine
-// (tfgridnet.py:383-385, 458-484).  One warp per position; outputs fp16 operands of the two batched GEMMs:
+// (tfgridnet.py:383-385, 458-484).  Outputs are the fp16 operands of the two batched GEMMs:
 //   Qh, Kh [B*4][T][E*F] with feature e * F + f  (tfgridnet.py:392-396);  Vt [B*4][8*F][T] (feature c8 * F + f, frames contiguous)
+// A block owns 16 frames x 32 bins of one utterance; a thread owns one bin of two frames, so the whole per-position chain
+// (48 dot products, the head statistics) is register-local, Q / K stores are contiguous along bins across the warp, and V goes
+// through a shared-memory transpose so that Vt is written in 32-byte runs along frames.  (The first version, one warp per
+// position with 2-byte scattered stores, took 3.2 ms per call at B = 16.)
+constexpr int QKV_TT = 16, QKV_TQ = 32, QKV_PITCH = 18;
 __global__ void __launch_bounds__(256)
 tfg_qkv_kernel(const float* __restrict__ z, const float* __restrict__ wq, const float* __restrict__ bq, const float* __restrict__ wk,
                const float* __restrict__ bk, const float* __restrict__ wv, const float* __restrict__ bv, const float* __restrict__ aq,
                const float* __restrict__ ak, const float* __restrict__ av, const float* __restrict__ gq, const float* __restrict__ betq,
                const float* __restrict__ gk, const float* __restrict__ betk, const float* __restrict__ gv, const float* __restrict__ betv,
                int B, int T, int Q, float eps, int ldf, int ldt, __half* __restrict__ Qh, __half* __restrict__ Kh, __half* __restrict__ Vt) {
-  __shared__ float sw[48 * 32];
-  __shared__ float sb[48];
+  __shared__ __align__(16) float sw[48 * 32];
+  __shared__ float sb[48], s_slope[12], s_ga[48], s_be[48];
+  __shared__ __align__(16) __half sv[32 * QKV_TQ * QKV_PITCH];
   for (int i = threadIdx.x; i < 48 * 32; i += 256) sw[i] = i < 256 ? wq[i] : (i < 512 ? wk[i - 256] : wv[i - 512]);
-  if (threadIdx.x < 48) sb[threadIdx.x] = threadIdx.x < 8 ? bq[threadIdx.x] : (threadIdx.x < 16 ? bk[threadIdx.x - 8] : bv[threadIdx.x - 16]);
+  if (threadIdx.x < 48) {
+    const int i = threadIdx.x;
+    sb[i] = i < 8 ? bq[i] : (i < 16 ? bk[i - 8] : bv[i - 16]);
+    s_ga[i] = i < 8 ? gq[i] : (i < 16 ? gk[i - 8] : gv[i - 16]);
+    s_be[i] = i < 8 ? betq[i] : (i < 16 ? betk[i - 8] : betv[i - 16]);
+    if (i < 12) s_slope[i] = i < 4 ? aq[i] : (i < 8 ? ak[i - 4] : av[i - 8]);
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int64_t n_pos = static_cast<int64_t>(B) * T * Q;
-  const int EF = ldf, VF = 8 * Q;                  // row pitches: ldf >= 2 Q, ldt >= T, multiples of 8 (pad columns pre-zeroed)
-  for (int64_t p = blockIdx.x * 8ll + wrp; p < n_pos; p += 8ll * gridDim.x) {
-    const int q = static_cast<int>(p % Q), t = static_cast<int>((p / Q) % T), b = static_cast<int>(p / (static_cast<int64_t>(Q) * T));
-    const float zv = z[p * TC + lane];
-    // output o of this lane: lanes 0..15 -> Q/K channel `lane`, all lanes -> V channel `lane`
-    float accv = sb[16 + lane], accqk = lane < 16 ? sb[lane] : 0.f;
+  const int b = blockIdx.z, t0 = blockIdx.y * QKV_TT, q = blockIdx.x * QKV_TQ + lane;
+  const int tl[2] = {wrp, wrp + 8};
+  bool ok[2];
+  float zv[2][32];
 #pragma unroll
-    for (int k = 0; k < 32; ++k) {
-      const float zk = __shfl_sync(0xffffffffu, zv, k);
-      accv = fmaf(sw[(16 + lane) * 32 + k], zk, accv);
-      if (lane < 16) accqk = fmaf(sw[lane * 32 + k], zk, accqk);
+  for (int r = 0; r < 2; ++r) {
+    const int t = t0 + tl[r];
+    ok[r] = t < T && q < Q;
+    const float4* src = reinterpret_cast<const float4*>(z + ((static_cast<int64_t>(b) * T + (ok[r] ? t : 0)) * Q + (ok[r] ? q : 0)) * TC);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const float4 v = ok[r] ? __ldg(src + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
+      zv[r][4 * k4] = v.x; zv[r][4 * k4 + 1] = v.y; zv[r][4 * k4 + 2] = v.z; zv[r][4 * k4 + 3] = v.w;
     }
-    // Q / K: head = (lane & 7) / 2, E = 2: normalise over the pair (lane, lane ^ 1)
-    {
-      const int ch = lane & 7, hd = ch >> 1;
-      const float slope = lane < 8 ? __ldg(aq + hd) : __ldg(ak + hd);
-      float v = accqk >= 0.f ? accqk : slope * accqk;
-      const float o = __shfl_xor_sync(0xffffffffu, v, 1);
-      const float mu = 0.5f * (v + o), d = v - mu, var = d * d;        // two elements: var = ((v - o) / 2)^2
-      const float ga = lane < 8 ? __ldg(gq + ch) : __ldg(gk + ch), be = lane < 8 ? __ldg(betq + ch) : __ldg(betk + ch);
-      const float r = d * rsqrtf(var + eps) * ga + be;
-      if (lane < 16) {
-        __half* dst = lane < 8 ? Qh : Kh;
-        const int e = ch & 1;
-        dst[((static_cast<int64_t>(b) * 4 + hd) * T + t) * EF + e * Q + q] = __float2half_rn(r);
+  }
+  // six groups of 8 outputs: Q (heads x E), K, then the four V heads
+#pragma unroll 1
+  for (int grp = 0; grp < 6; ++grp) {
+    float acc[2][8];
+#pragma unroll
+    for (int o = 0; o < 8; ++o) { acc[0][o] = acc[1][o] = sb[grp * 8 + o]; }
+#pragma unroll
+    for (int o = 0; o < 8; ++o) {
+      const float4* wrow = reinterpret_cast<const float4*>(sw + (grp * 8 + o) * 32);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 w = wrow[k4];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+          acc[r][o] = fmaf(w.x, zv[r][4 * k4], acc[r][o]); acc[r][o] = fmaf(w.y, zv[r][4 * k4 + 1], acc[r][o]);
+          acc[r][o] = fmaf(w.z, zv[r][4 * k4 + 2], acc[r][o]); acc[r][o] = fmaf(w.w, zv[r][4 * k4 + 3], acc[r][o]);
+        }
       }
     }
-    // V: head = lane / 8, 8 channels per head
-    {
-      const int hd = lane >> 3, c8 = lane & 7;
-      const float slope = __ldg(av + hd);
-      const float v = accv >= 0.f ? accv : slope * accv;
-      float s = v;
-      s += __shfl_xor_sync(0xffffffffu, s, 1); s += __shfl_xor_sync(0xffffffffu, s, 2); s += __shfl_xor_sync(0xffffffffu, s, 4);
-      const float mu = s * 0.125f, d = v - mu;
-      float vs = d * d;
-      vs += __shfl_xor_sync(0xffffffffu, vs, 1); vs += __shfl_xor_sync(0xffffffffu, vs, 2); vs += __shfl_xor_sync(0xffffffffu, vs, 4);
-      const float r = d * rsqrtf(vs * 0.125f + eps) * __ldg(gv + lane) + __ldg(betv + lane);
-      Vt[((static_cast<int64_t>(b) * 4 + hd) * VF + c8 * Q + q) * ldt + t] = __float2half_rn(r);
+    if (grp < 2) {
+      // Q / K: channel o = head * 2 + e; PReLU(head) then normalise over the head's two channels
+      __half* dst = grp == 0 ? Qh : Kh;
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+#pragma unroll
+        for (int hd = 0; hd < 4; ++hd) {
+          const float slope = s_slope[grp * 4 + hd];
+          float v0 = acc[r][2 * hd], v1 = acc[r][2 * hd + 1];
+          v0 = v0 >= 0.f ? v0 : slope * v0; v1 = v1 >= 0.f ? v1 : slope * v1;
+          const float mu = 0.5f * (v0 + v1), d0 = v0 - mu, d1 = v1 - mu;
+          const float rs = rsqrtf(d0 * d0 + eps);                        // two elements: var = ((v0 - v1) / 2)^2 = d0^2
+          if (ok[r]) {
+            __half* row = dst + ((static_cast<int64_t>(b) * 4 + hd) * T + t0 + tl[r]) * ldf + q;
+            row[0] = __float2half_rn(d0 * rs * s_ga[grp * 8 + 2 * hd] + s_be[grp * 8 + 2 * hd]);
+            row[Q] = __float2half_rn(d1 * rs * s_ga[grp * 8 + 2 * hd + 1] + s_be[grp * 8 + 2 * hd + 1]);
+          }
+        }
+      }
+    } else {
+      const int hd = grp - 2;
+      const float slope = s_slope[8 + hd];
+#pragma unroll
+      for (int r = 0; r < 2; ++r) {
+        float v[8], mu = 0.f, var = 0.f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { v[o] = acc[r][o] >= 0.f ? acc[r][o] : slope * acc[r][o]; mu += v[o]; }
+        mu *= 0.125f;
+#pragma unroll
+        for (int o = 0; o < 8; ++o) { v[o] -= mu; var = fmaf(v[o], v[o], var); }
+        const float rs = rsqrtf(var * 0.125f + eps);
+#pragma unroll
+        for (int o = 0; o < 8; ++o)
+          sv[((hd * 8 + o) * QKV_TQ + lane) * QKV_PITCH + tl[r]] = __float2half_rn(v[o] * rs * s_ga[16 + hd * 8 + o] + s_be[16 + hd * 8 + o]);
+      }
+    }
+  }
+  __syncthreads();
+  // Vt rows (channel, bin): 16 frames = 32 contiguous bytes
+  const int n_t = min(QKV_TT, T - t0);
+  for (int row = threadIdx.x; row < 32 * QKV_TQ; row += 256) {
+    const int c = row >> 5, qq = blockIdx.x * QKV_TQ + (row & 31);
+    if (qq >= Q) continue;
+    __half* dst = Vt + ((static_cast<int64_t>(b) * 4 + (c >> 3)) * (8 * Q) + static_cast<int64_t>(c & 7) * Q + qq) * ldt + t0;
+    const uint32_t* src = reinterpret_cast<const uint32_t*>(sv + row * QKV_PITCH);
+    if (n_t == QKV_TT) {
+      reinterpret_cast<uint4*>(dst)[0] = make_uint4(src[0], src[1], src[2], src[3]);
+      reinterpret_cast<uint4*>(dst)[1] = make_uint4(src[4], src[5], src[6], src[7]);
+    } else {
+      const __half* sh = sv + row * QKV_PITCH;
+      for (int t = 0; t < n_t; ++t) dst[t] = sh[t];
     }
   }
 }
@@ -541,18 +402,44 @@ __global__ void __launch_bounds__(256)
 tfg_attn_proj_kernel(const float* __restrict__ o, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ slope,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ resid, int64_t n_pos, float eps,
                      float* __restrict__ out) {
-  __shared__ float sw[32 * 33];
-  for (int i = threadIdx.x; i < 1024; i += 256) sw[(i >> 5) * 33 + (i & 31)] = w[i];
+  // thread = position: the 32 x 32 product, PReLU and LayerNorm are register-local (weights broadcast from shared memory)
+  __shared__ __align__(16) float sw[32 * 32];
+  __shared__ float sp[3 * 32];
+  for (int i = threadIdx.x; i < 1024; i += 256) sw[i] = w[i];
+  if (threadIdx.x < 32) { sp[threadIdx.x] = bias[threadIdx.x]; sp[32 + threadIdx.x] = gamma[threadIdx.x]; sp[64 + threadIdx.x] = beta[threadIdx.x]; }
   __syncthreads();
-  const int lane = threadIdx.x & 31;
-  const float a = __ldg(slope), ga = __ldg(gamma + lane), be = __ldg(beta + lane), bi = __ldg(bias + lane);
-  for (int64_t p = blockIdx.x * 8ll + (threadIdx.x >> 5); p < n_pos; p += 8ll * gridDim.x) {
-    const float ov = o[p * TC + lane];
-    float acc = bi;
+  const float a = __ldg(slope);
+  for (int64_t p = blockIdx.x * 256ll + threadIdx.x; p < n_pos; p += 256ll * gridDim.x) {
+    float x[32], acc[32];
+    const float4* src = reinterpret_cast<const float4*>(o + p * TC);
 #pragma unroll
-    for (int k = 0; k < 32; ++k) acc = fmaf(sw[lane * 33 + k], __shfl_sync(0xffffffffu, ov, k), acc);
-    acc = acc >= 0.f ? acc : a * acc;
-    out[p * TC + lane] = ln32(acc, ga, be, eps) + resid[p * TC + lane];
+    for (int k4 = 0; k4 < 8; ++k4) { const float4 v = __ldg(src + k4); x[4 * k4] = v.x; x[4 * k4 + 1] = v.y; x[4 * k4 + 2] = v.z; x[4 * k4 + 3] = v.w; }
+    float mu = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) {
+      float s = sp[c];
+      const float4* wrow = reinterpret_cast<const float4*>(sw + c * 32);
+#pragma unroll
+      for (int k4 = 0; k4 < 8; ++k4) {
+        const float4 wv = wrow[k4];
+        s = fmaf(wv.x, x[4 * k4], s); s = fmaf(wv.y, x[4 * k4 + 1], s); s = fmaf(wv.z, x[4 * k4 + 2], s); s = fmaf(wv.w, x[4 * k4 + 3], s);
+      }
+      s = s >= 0.f ? s : a * s;
+      acc[c] = s; mu += s;
+    }
+    mu *= (1.0f / 32.0f);
+    float var = 0.f;
+#pragma unroll
+    for (int c = 0; c < 32; ++c) { acc[c] -= mu; var = fmaf(acc[c], acc[c], var); }
+    const float rs = rsqrtf(var * (1.0f / 32.0f) + eps);
+    const float4* rsrc = reinterpret_cast<const float4*>(resid + p * TC);
+    float4* dst = reinterpret_cast<float4*>(out + p * TC);
+#pragma unroll
+    for (int k4 = 0; k4 < 8; ++k4) {
+      const float4 r = __ldg(rsrc + k4);
+      dst[k4] = make_float4(acc[4 * k4] * rs * sp[32 + 4 * k4] + sp[64 + 4 * k4] + r.x, acc[4 * k4 + 1] * rs * sp[33 + 4 * k4] + sp[65 + 4 * k4] + r.y,
+                            acc[4 * k4 + 2] * rs * sp[34 + 4 * k4] + sp[66 + 4 * k4] + r.z, acc[4 * k4 + 3] * rs * sp[35 + 4 * k4] + sp[67 + 4 * k4] + r.w);
+    }
   }
 }
 
@@ -595,45 +482,6 @@ int grid8(int64_t n_pos) { return static_cast<int>(std::min<int64_t>(ceil_div64(
 using namespace fdbm;
 
 // ---- C ABI ------------------------------------------------------------------------------------------------------------
-extern "C" int64_t fdbm_tfg_lstm_pack_bytes(void) { return static_cast<int64_t>(LSTM_SMEM); }
-
-// pack one direction (dir 0 forward / 1 reverse) of one BiLSTM + its ConvTranspose1d into `packed` (fdbm_tfg_lstm_pack_bytes())
-extern "C" int fdbm_tfg_lstm_pack(const float* w_ih, const float* w_hh, const float* b_ih, const float* b_hh, const float* w_lin,
-                                  int hidden, int dir, void* packed, void* stream) {
-  if (int rc = require_sm100()) return rc;
-  FDBM_REQUIRE(w_ih && w_hh && b_ih && b_hh && w_lin && packed, "fdbm_tfg_lstm_pack: null pointer");
-  FDBM_REQUIRE(hidden >= 8 && hidden <= 104, "fdbm_tfg_lstm_pack: hidden units must be in 8..104 (got %d)", hidden);
-  uint8_t* p = reinterpret_cast<uint8_t*>(packed);
-  pack_lstm_kernel<<<64, 256, 0, as_stream(stream)>>>(w_ih, w_hh, b_ih, b_hh, w_lin, hidden, dir, reinterpret_cast<uint2*>(p),
-                                                      reinterpret_cast<uint2*>(p + WG_BYTES), reinterpret_cast<float*>(p + WG_BYTES + WL_BYTES));
-  FDBM_LAUNCH_CHECK();
-  return FDBM_OK;
-}
-
-// one bidirectional sweep.  xn fp16: element (seq = outer * n_inner + inner, pos, c) at outer * outer_stride + inner * inner_stride +
-// pos * pos_stride + c;  y_fw / y_bw fp16 [n_seq][L][128]
-extern "C" int fdbm_tfg_lstm_sweep(const void* xn, int n_seq, int n_inner, int64_t outer_stride, int64_t inner_stride, int64_t pos_stride,
-                                   int L, const void* packed_fw, const void* packed_bw, void* y_fw, void* y_bw, void* stream) {
-  if (int rc = require_sm100()) return rc;
-  FDBM_REQUIRE(xn && packed_fw && packed_bw && y_fw && y_bw && n_seq > 0 && n_inner > 0 && L > 0, "fdbm_tfg_lstm_sweep: bad arguments");
-  static PerDeviceOnce attr_once;
-  if (attr_once.first(current_device()))
-    FDBM_CUDA(cudaFuncSetAttribute(lstm_sweep_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(LSTM_SMEM)));
-  LstmArgs a;
-  a.xn = reinterpret_cast<const __half*>(xn); a.n_seq = n_seq; a.n_inner = n_inner;
-  a.outer_stride = outer_stride; a.inner_stride = inner_stride; a.pos_stride = pos_stride; a.L = L;
-  const uint8_t* pk[2] = {reinterpret_cast<const uint8_t*>(packed_fw), reinterpret_cast<const uint8_t*>(packed_bw)};
-  for (int d = 0; d < 2; ++d) {
-    a.wg[d] = reinterpret_cast<const uint2*>(pk[d]); a.wl[d] = reinterpret_cast<const uint2*>(pk[d] + WG_BYTES);
-    a.bias[d] = reinterpret_cast<const float*>(pk[d] + WG_BYTES + WL_BYTES);
-  }
-  a.y[0] = reinterpret_cast<__half*>(y_fw); a.y[1] = reinterpret_cast<__half*>(y_bw);
-  dim3 grid(ceil_div(n_seq, SEQ_PER_CTA), 2);
-  lstm_sweep_kernel<<<grid, LSTM_THREADS, LSTM_SMEM, as_stream(stream)>>>(a);
-  FDBM_LAUNCH_CHECK();
-  return FDBM_OK;
-}
-
 extern "C" int fdbm_tfg_pad_add_norm(const float* h, const float* emb, const float* gamma, const float* beta, int batch, int T, int Q, float eps,
                                      float* xp, void* xn, void* stream) {
   if (int rc = require_sm100()) return rc;
@@ -645,12 +493,14 @@ extern "C" int fdbm_tfg_pad_add_norm(const float* h, const float* emb, const flo
 }
 
 extern "C" int fdbm_tfg_sweep_post(const void* y_fw, const void* y_bw, const float* lin_bias, const float* resid, int batch, int T, int Q, int mode,
-                                   const float* gamma, const float* beta, float eps, float* out_full, void* xn, float* out_crop, void* stream) {
+                                   const float* gamma, const float* beta, float eps, float* out_full, void* xn, float* out_crop, int xn_transposed,
+                                   void* stream) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(y_fw && y_bw && lin_bias && resid && (mode == 0 ? (out_full && xn && gamma && beta) : out_crop != nullptr), "fdbm_tfg_sweep_post: bad arguments");
   const int64_t n_pos = mode == 0 ? static_cast<int64_t>(batch) * (T + 2 * OLP) * (Q + 2 * OLP) : static_cast<int64_t>(batch) * T * Q;
   sweep_post_kernel<<<grid8(n_pos), 256, 0, as_stream(stream)>>>(reinterpret_cast<const __half*>(y_fw), reinterpret_cast<const __half*>(y_bw), lin_bias,
-                                                                 resid, batch, T, Q, mode, gamma, beta, eps, out_full, reinterpret_cast<__half*>(xn), out_crop);
+                                                                 resid, batch, T, Q, mode, gamma, beta, eps, out_full, reinterpret_cast<__half*>(xn), out_crop,
+                                                                 xn_transposed);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -708,7 +558,7 @@ extern "C" int fdbm_tfg_attention(const float* z, const float* const* params /* 
   const float* const* p = params;
   // order: wq bq wk bk wv bv | aq ak av | gq betq gk betk gv betv | wproj bproj slope gproj betproj
   const int64_t n_pos = static_cast<int64_t>(batch) * T * Q;
-  tfg_qkv_kernel<<<grid8(n_pos), 256, 0, s>>>(z, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[12], p[13], p[14], batch, T,
+  tfg_qkv_kernel<<<dim3(ceil_div(Q, QKV_TQ), ceil_div(T, QKV_TT), batch), 256, 0, s>>>(z, p[0], p[1], p[2], p[3], p[4], p[5], p[6], p[7], p[8], p[9], p[10], p[11], p[12], p[13], p[14], batch, T,
                                               Q, eps, ldf, ldt, Qh, Kh, Vt);
   FDBM_LAUNCH_CHECK();
   GemmArgs g;
@@ -722,7 +572,7 @@ extern "C" int fdbm_tfg_attention(const float* z, const float* const* params /* 
   g.lda = ldt; g.ldb = ldt; g.ldc = 0; g.scale = 1.0f; g.out_mode = 2;
   gemm_tn_kernel<<<dim3(ceil_div(8 * Q, 64), ceil_div(T, 64), static_cast<unsigned>(bh)), 128, 0, s>>>(g);
   FDBM_LAUNCH_CHECK();
-  tfg_attn_proj_kernel<<<grid8(n_pos), 256, 0, s>>>(O, p[15], p[16], p[17], p[18], p[19], z, n_pos, eps, out);
+  tfg_attn_proj_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(n_pos, 256), static_cast<int64_t>(num_sms()) * 8)), 256, 0, s>>>(O, p[15], p[16], p[17], p[18], p[19], z, n_pos, eps, out);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

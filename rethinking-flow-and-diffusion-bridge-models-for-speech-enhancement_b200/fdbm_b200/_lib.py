@@ -121,10 +121,10 @@ def load() -> C.CDLL:
         "fdbm_plan_swap_ema": (i, [p, i, p]),
         "fdbm_attention": (i, [p, p, p, i, i, i, p, p]),
         "fdbm_tfg_lstm_pack_bytes": (i64, []),
-        "fdbm_tfg_lstm_pack": (i, [p, p, p, p, p, i, i, p, p]),
-        "fdbm_tfg_lstm_sweep": (i, [p, i, i, i64, i64, i64, i, p, p, p, p, p]),
+        "fdbm_tfg_lstm_pack": (i, [p, p, i, p, p]),
+        "fdbm_tfg_lstm_sweep": (i, [p, i, i, p, p, p, p]),
         "fdbm_tfg_pad_add_norm": (i, [p, p, p, p, i, i, i, f, p, p, p]),
-        "fdbm_tfg_sweep_post": (i, [p, p, p, p, i, i, i, i, p, p, f, p, p, p, p]),
+        "fdbm_tfg_sweep_post": (i, [p, p, p, p, i, i, i, i, p, p, f, p, p, p, i, p]),
         "fdbm_tfg_input": (i, [p, p, p, p, p, p, i, i, i, i, f, p, p, p]),
         "fdbm_tfg_time_embedding": (i, [p, i, p, p, p, p, p, p, p, i, i, p, p]),
         "fdbm_tfg_attention_workspace_bytes": (i64, [i, i, i]),

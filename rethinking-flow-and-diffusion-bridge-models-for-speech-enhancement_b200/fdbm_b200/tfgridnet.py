@@ -5,8 +5,8 @@
 The module tree below consists of stock torch.nn layers used ONLY as parameter containers, arranged exactly like the
 reference's, so `state_dict()` keys / shapes and the default initialisation are the reference's and its checkpoints load
 unchanged; none of those layers is ever called.  `forward` runs the network as libfdbm_b200 kernels (csrc/tfgridnet.cu):
-per block one fused pad + time-embedding-add + LayerNorm pass, the persistent tensor-core BiLSTM sweep along frequency, a
-pass that folds ConvTranspose1d's four taps + residual + the next LayerNorm, the sweep along time, the crop, and the
+per block one fused pad + time-embedding-add + LayerNorm pass, the tcgen05 BiLSTM sweep along frequency (csrc/tfg_lstm_tc.cu,
+ConvTranspose1d folded in), a pass that adds both directions + residual and takes the next LayerNorm, the sweep along time, the crop, and the
 full-band self-attention (1x1 convs + PReLU-LayerNorm front, two batched tensor-core GEMMs, projection + PReLU + LayerNorm).
 Inference only (outputs carry no autograd graph); there is no CPU or PyTorch fallback.
 """
@@ -78,8 +78,8 @@ class _TFGridNetBase(nn.Module):
         n_imics = (1 if self.predictive else 2) if n_imics is None else n_imics
         if (emb_dim, emb_ks, emb_hs, attn_n_head, attn_qk_output_channel, n_srcs) != (32, 4, 1, 4, 2, 1) or activation != "prelu":
             raise NotImplementedError("fdbm_b200 implements the shipped TF-GridNet geometry: emb_dim 32, emb_ks 4, emb_hs 1, 4 heads, E = 2")
-        if not 8 <= lstm_hidden_units <= 104:
-            raise NotImplementedError("lstm_hidden_units must be in 8..104 (the gate matrix lives in one SM's shared memory)")
+        if not 8 <= lstm_hidden_units <= 112:
+            raise NotImplementedError("lstm_hidden_units must be in 8..112 (the gate matrix lives in the shared memory of a two-SM cluster)")
         if n_imics != (1 if self.predictive else 2) or (not self.predictive and time_embedding_type != "fourier"):
             raise NotImplementedError("unsupported n_imics / time_embedding_type")
         self.n_layers, self.emb_dim, self.hidden, self.eps = n_layers, emb_dim, lstm_hidden_units, eps
@@ -120,14 +120,13 @@ class _TFGridNetBase(nn.Module):
         for b in range(self.n_layers):
             for name in ("intra", "inter"):
                 pre = f"blocks.{b}.{name}_rnn."
-                for d, sfx in enumerate(("", "_reverse")):
-                    buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
-                    w = [sd[pre + f"{n}_l0{sfx}"].contiguous() for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-                    wl = sd[f"blocks.{b}.{name}_linear.weight"].contiguous()
-                    check(lib.fdbm_tfg_lstm_pack(ptr(w[0]), ptr(w[1]), ptr(w[2]), ptr(w[3]), ptr(wl), self.hidden, d, ptr(buf), current_stream()),
-                          "fdbm_tfg_lstm_pack")
-                    P["lstm"][(b, name, d)] = buf
-                    P["keep"] += w + [wl]
+                wl = sd[f"blocks.{b}.{name}_linear.weight"].contiguous()
+                w = [sd[pre + f"{n}_l0{sfx}"].contiguous() for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+                buf = torch.empty(nbytes, dtype=torch.uint8, device=dev)
+                arr = (C.c_void_p * 8)(*[t.data_ptr() for t in w])
+                check(lib.fdbm_tfg_lstm_pack(arr, ptr(wl), self.hidden, ptr(buf), current_stream()), "fdbm_tfg_lstm_pack")
+                P["lstm"][(b, name)] = buf
+                P["keep"] += w + [wl]
         if not self.predictive:
             P["wb"] = torch.stack([sd[f"time_emb_blocks.{b}.weight"] for b in range(self.n_layers)]).contiguous()
             P["bb"] = torch.stack([sd[f"time_emb_blocks.{b}.bias"] for b in range(self.n_layers)]).contiguous()
@@ -155,7 +154,7 @@ class _TFGridNetBase(nn.Module):
             Tp, Qp = T + 6, F + 6
             f32 = dict(dtype=torch.float32, device=dev)
             f16 = dict(dtype=torch.float16, device=dev)
-            n_y = max(B * Tp * (Qp - 3), B * Qp * (Tp - 3)) * 128
+            n_y = B * Tp * Qp * 32
             ws = dict(h=torch.empty(B, T, F, 32, **f32), h2=torch.empty(B, T, F, 32, **f32), xp=torch.empty(B, Tp, Qp, 32, **f32),
                       xp2=torch.empty(B, Tp, Qp, 32, **f32), xn=torch.empty(B, Tp, Qp, 32, **f16), yf=torch.empty(n_y, **f16),
                       yb=torch.empty(n_y, **f16), sums=torch.empty(2 * B, dtype=torch.float64, device=dev),
@@ -164,6 +163,11 @@ class _TFGridNetBase(nn.Module):
             self._ws.clear()                                                    # one geometry at a time (the buffers are GBs at B = 32)
             self._ws[key] = ws
         return ws
+
+    @staticmethod
+    def _sweep(lib, P, b, name, ws, n_seq, L, st):
+        """One bidirectional sweep over `n_seq` contiguous sequences [n_seq][L + 3][32] of ws["xn"] -> ws["yf"], ws["yb"] (same shape)."""
+        check(lib.fdbm_tfg_lstm_sweep(ptr(ws["xn"]), n_seq, L, ptr(P["lstm"][(b, name)]), ptr(ws["yf"]), ptr(ws["yb"]), st), "fdbm_tfg_lstm_sweep")
 
     # ---- forward -----------------------------------------------------------------------------------------------------
     def _run(self, x, y, t):
@@ -193,17 +197,15 @@ class _TFGridNetBase(nn.Module):
             emb = None if self.predictive else ws["emb"][b]
             check(lib.fdbm_tfg_pad_add_norm(ptr(h), ptr(emb), ptr(sd[p + "intra_norm.weight"]), ptr(sd[p + "intra_norm.bias"]), B, T, F, eps,
                                             ptr(ws["xp"]), ptr(ws["xn"]), st), "fdbm_tfg_pad_add_norm")
-            # intra: sequences along frequency, one per (utterance, padded frame)
-            check(lib.fdbm_tfg_lstm_sweep(ptr(ws["xn"]), B * Tp, Tp, Tp * Qp * 32, Qp * 32, 32, Qp - 3, ptr(P["lstm"][(b, "intra", 0)]),
-                                          ptr(P["lstm"][(b, "intra", 1)]), ptr(ws["yf"]), ptr(ws["yb"]), st), "fdbm_tfg_lstm_sweep")
+            # intra: sequences along frequency, one per (utterance, padded frame): xn [B, T', Q', 32]
+            self._sweep(lib, P, b, "intra", ws, B * Tp, Qp - 3, st)
             check(lib.fdbm_tfg_sweep_post(ptr(ws["yf"]), ptr(ws["yb"]), ptr(sd[p + "intra_linear.bias"]), ptr(ws["xp"]), B, T, F, 0,
                                           ptr(sd[p + "inter_norm.weight"]), ptr(sd[p + "inter_norm.bias"]), eps, ptr(ws["xp2"]), ptr(ws["xn"]),
-                                          None, st), "fdbm_tfg_sweep_post")
-            # inter: sequences along time, one per (utterance, padded bin)
-            check(lib.fdbm_tfg_lstm_sweep(ptr(ws["xn"]), B * Qp, Qp, Tp * Qp * 32, 32, Qp * 32, Tp - 3, ptr(P["lstm"][(b, "inter", 0)]),
-                                          ptr(P["lstm"][(b, "inter", 1)]), ptr(ws["yf"]), ptr(ws["yb"]), st), "fdbm_tfg_lstm_sweep")
+                                          None, 1, st), "fdbm_tfg_sweep_post")
+            # inter: sequences along time, one per (utterance, padded bin): xn transposed to [B, Q', T', 32]
+            self._sweep(lib, P, b, "inter", ws, B * Qp, Tp - 3, st)
             check(lib.fdbm_tfg_sweep_post(ptr(ws["yf"]), ptr(ws["yb"]), ptr(sd[p + "inter_linear.bias"]), ptr(ws["xp2"]), B, T, F, 1, None, None,
-                                          eps, None, None, ptr(h2), st), "fdbm_tfg_sweep_post")
+                                          eps, None, None, ptr(h2), 0, st), "fdbm_tfg_sweep_post")
             base = ws["attn"].data_ptr()
             aligned = (base + 255) // 256 * 256
             check(lib.fdbm_tfg_attention(ptr(h2), P["attn"][b][0], B, T, F, eps, aligned, ptr(h), st), "fdbm_tfg_attention")

@@ -44,15 +44,16 @@ def test_state_dict_and_registry():
         BackboneRegistry.get_by_name("tfgridnet_5l32c100")(emb_ks=4, emb_hs=4)
 
 
-@pytest.mark.parametrize("inter", [False, True])
-def test_lstm_sweep_and_post_vs_oracle(env, inter):
+@pytest.mark.parametrize("inter,B", [(False, 2), (True, 2), (False, 10)])
+def test_lstm_sweep_and_post_vs_oracle(env, inter, B):
     """One BiLSTM path (LayerNorm -> unfold 4 -> BiLSTM(128 -> 100 x 2) -> ConvTranspose1d -> + residual, tfgridnet.py:335-375)
-    on a small padded tensor: sequences along Q (intra) or along T (inter), including a partial 128-sequence CTA."""
+    on a small padded tensor: sequences along Q (intra) or along T (inter), including a partial 128-sequence tile (B = 10: 150
+    sequences = one full tile + 22)."""
     O, lib, _lib = env
     cfg = O.TFGridNetConfig()
     sd = O.tfgridnet_state_dict(cfg, seed=3)
     g = torch.Generator().manual_seed(7)
-    B, T, Q = 2, 9, 14                                       # padded 15 x 20
+    T, Q = 9, 14                                             # padded 15 x 20
     Tp, Qp = T + 6, Q + 6
     xp = torch.randn(B, Tp, Qp, 32, generator=g)
     name = "inter" if inter else "intra"
@@ -61,38 +62,34 @@ def test_lstm_sweep_and_post_vs_oracle(env, inter):
         ref = O._rnn_path(xp.transpose(1, 2), sd, p, name, cfg).transpose(1, 2) if inter else O._rnn_path(xp, sd, p, name, cfg)
     xpd = xp.cuda()
     xn = F.layer_norm(xpd, (32,), sd[p + name + "_norm.weight"].cuda(), sd[p + name + "_norm.bias"].cuda(), cfg.eps).half().contiguous()
-    nbytes = int(lib.fdbm_tfg_lstm_pack_bytes())
-    packs = []
-    for d, sfx in enumerate(("", "_reverse")):
-        buf = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
-        w = [sd[p + f"{name}_rnn.{n}_l0{sfx}"].cuda().contiguous() for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
-        wl = sd[p + f"{name}_linear.weight"].cuda().contiguous()
-        _ck(_lib, lib.fdbm_tfg_lstm_pack(w[0].data_ptr(), w[1].data_ptr(), w[2].data_ptr(), w[3].data_ptr(), wl.data_ptr(), 100, d, buf.data_ptr(), _stream()))
-        packs.append(buf)
-    if inter:
-        n_seq, n_inner, L = B * Qp, Qp, Tp - 3
-        strides = (Tp * Qp * 32, 32, Qp * 32)
-    else:
-        n_seq, n_inner, L = B * Tp, Tp, Qp - 3
-        strides = (Tp * Qp * 32, Qp * 32, 32)
-    yf = torch.zeros(n_seq * L * 128, dtype=torch.float16, device="cuda"); yb = torch.zeros_like(yf)
-    _ck(_lib, lib.fdbm_tfg_lstm_sweep(xn.data_ptr(), n_seq, n_inner, *strides, L, packs[0].data_ptr(), packs[1].data_ptr(), yf.data_ptr(),
-                                      yb.data_ptr(), _stream()))
+    w = [sd[p + f"{name}_rnn.{n}_l0{sfx}"].cuda().contiguous() for sfx in ("", "_reverse") for n in ("weight_ih", "weight_hh", "bias_ih", "bias_hh")]
+    wl = sd[p + f"{name}_linear.weight"].cuda().contiguous()
+    n_seq, L = (B * Qp, Tp - 3) if inter else (B * Tp, Qp - 3)
+    yf = torch.zeros(n_seq * (L + 3) * 32, dtype=torch.float16, device="cuda"); yb = torch.zeros_like(yf)
+    buf = torch.empty(int(lib.fdbm_tfg_lstm_pack_bytes()), dtype=torch.uint8, device="cuda")
+    arr = (C.c_void_p * 8)(*[t.data_ptr() for t in w])
+    _ck(_lib, lib.fdbm_tfg_lstm_pack(arr, wl.data_ptr(), 100, buf.data_ptr(), _stream()))
+    xs = xn.transpose(1, 2).contiguous() if inter else xn              # sequences contiguous: [n_seq][L + 3][32]
+    _ck(_lib, lib.fdbm_tfg_lstm_sweep(xs.data_ptr(), n_seq, L, buf.data_ptr(), yf.data_ptr(), yb.data_ptr(), _stream()))
+    torch.cuda.synchronize()
     lb = sd[p + name + "_linear.bias"].cuda()
     if inter:
         out = torch.empty(B, T, Q, 32, device="cuda")
         _ck(_lib, lib.fdbm_tfg_sweep_post(yf.data_ptr(), yb.data_ptr(), lb.data_ptr(), xpd.data_ptr(), B, T, Q, 1, None, None, cfg.eps, None, None,
-                                          out.data_ptr(), _stream()))
+                                          out.data_ptr(), 0, _stream()))
         want = ref[:, 3:3 + T, 3:3 + Q]
     else:
         out = torch.empty(B, Tp, Qp, 32, device="cuda")
         xn2 = torch.empty(B, Tp, Qp, 32, dtype=torch.float16, device="cuda")
+        xn2t = torch.empty(B, Qp, Tp, 32, dtype=torch.float16, device="cuda")
         gam, bet = sd[p + "inter_norm.weight"].cuda(), sd[p + "inter_norm.bias"].cuda()
-        _ck(_lib, lib.fdbm_tfg_sweep_post(yf.data_ptr(), yb.data_ptr(), lb.data_ptr(), xpd.data_ptr(), B, T, Q, 0, gam.data_ptr(), bet.data_ptr(), cfg.eps,
-                                          out.data_ptr(), xn2.data_ptr(), None, _stream()))
+        for buf2, tr in ((xn2, 0), (xn2t, 1)):
+            _ck(_lib, lib.fdbm_tfg_sweep_post(yf.data_ptr(), yb.data_ptr(), lb.data_ptr(), xpd.data_ptr(), B, T, Q, 0, gam.data_ptr(), bet.data_ptr(),
+                                              cfg.eps, out.data_ptr(), buf2.data_ptr(), None, tr, _stream()))
         want = ref
         ln = F.layer_norm(out, (32,), gam, bet, cfg.eps)
         assert rel_l2(xn2.float(), ln) < 1e-3
+        assert torch.equal(xn2t, xn2.transpose(1, 2).contiguous())
     torch.cuda.synchronize()
     # the residual dominates `out`; compare the LSTM path's own contribution
     err = rel_l2(out.cpu() - (want - want + (xp[:, 3:3 + T, 3:3 + Q] if inter else xp)), want - (xp[:, 3:3 + T, 3:3 + Q] if inter else xp))
