@@ -8,14 +8,17 @@
 //     operands (4 x 112 x 241 fp16 = 211 KB), so each CTA holds the gate columns of 56 of the 112 (padded) hidden units
 //     (N = 224, 105 KB) and both hold the full A operand [u_s | h_{s-1}]: every step a CTA computes its 56 units' gates
 //     (UMMA M = 128, N = 224, K = 128 + 128), updates their cell state and writes the 56 new hidden values of every sequence
-//     into its OWN and its PEER's shared-memory h tile (st.shared::cluster).
-//   * per-step hand-shake, no cluster barrier: tcgen05.commit is MULTICAST to both CTAs' `mma_done` barriers (count 2), so a
-//     point-wise warp overwrites h only when both tensor cores are done reading it; each point-wise warp arrives on both CTAs'
-//     `h_ready` barriers (count 16) after its stores, and the MMA lane waits on its own.
+//     into its OWN h tile and ships them to its PEER's: the h tile's K-block r (64 columns) holds exactly CTA r's units, so the
+//     exchange is four 4 KB cp.async.bulk shared::cta -> shared::cluster copies per step (one per 32 rows, issued by the warp
+//     pair that wrote them) completing on the peer's `h_ready` barrier -- no generic remote stores, no cluster-scope fences.
+//   * per-step hand-shake, no cluster barrier: tcgen05.commit is MULTICAST to both CTAs' `mma_done` / `y_done` barriers
+//     (count 2), so h is overwritten only when both tensor cores are done reading it.  The MMA lane issues the K-block it
+//     owns as soon as its 4 row groups have arrived (`h_local`) and the peer's when its 16 KB have landed (`h_peer`); the gate
+//     columns are committed in two slices so the first half of the point-wise warps starts while the second slice computes.
 //   * u_s (the unfolded input, 4 taps x 32 channels) is a ring of six single-position tiles [128 seq x 32 ch] (64-byte rows,
 //     SWIZZLE_64B) filled by TMA one position per step; the four taps of a step are four K = 32 UMMA pairs on ring slots.  They
 //     do not depend on h, so step i + 1's are issued right behind step i's commit into the second gate accumulator (EARLY).
-//   * the bias rides in the GEMM: column 112 of the h tile is the constant 1, row 112 of W_hh holds b_ih + b_hh.  The rows of
+//   * the bias rides in the GEMM: column 120 of the h tile is the constant 1, that row of W_hh holds b_ih + b_hh.  The rows of
 //     the i, f, o gates are pre-scaled by 1/2 (exact): sigmoid(x) = 0.5 tanh(x / 2) + 0.5 costs one MUFU and no multiply.
 //   * ConvTranspose1d: y_{s-1} = h_{s-1} W_lin is issued together with the gates of step s (both read h_{s-1}); a point-wise
 //     thread owns 8 output channels x 4 taps (one 32-column TMEM load) and overlap-adds them in registers over four consecutive
@@ -67,22 +70,15 @@ __device__ __forceinline__ uint32_t cluster_rank() { uint32_t r; asm volatile("m
 __device__ __forceinline__ uint32_t map_to_peer(uint32_t local_addr, uint32_t rank) {
   uint32_t r; asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank)); return r;
 }
-__device__ __forceinline__ void st_cluster_v4(uint32_t addr, uint4 v) {
-  asm volatile("st.shared::cluster.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint4 v) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(v.x), "r"(v.y), "r"(v.z), "r"(v.w) : "memory");
 }
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {       // release at cluster scope: the h stores before it
-  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+// 4 KB of this CTA's shared memory -> the same offset in the peer's, completing on the peer's mbarrier (async proxy on both sides)
+__device__ __forceinline__ void bulk_copy_to_peer(uint32_t dst_cluster, uint32_t src_cta, uint32_t bytes, uint32_t bar_cluster) {
+  asm volatile("cp.async.bulk.shared::cluster.shared::cta.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst_cluster), "r"(src_cta), "r"(bytes),
+               "r"(bar_cluster) : "memory");
 }
-__device__ __forceinline__ void mbar_wait_cluster(uint64_t* bar, uint32_t parity) {   // acquire at cluster scope, bounded like mbar_wait
-  uint32_t ok = 0, spins = 0;
-  const uint32_t addr = smem_u32(bar);
-  while (true) {
-    asm volatile("{\n\t.reg .pred P;\n\tmbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P, [%1], %2;\n\tselp.u32 %0, 1, 0, P;\n\t}\n"
-                 : "=r"(ok) : "r"(addr), "r"(parity) : "memory");
-    if (ok) break;
-    if (++spins > (1u << 22)) __trap();
-  }
-}
+__device__ __forceinline__ void named_bar_sync(int id, int threads) { asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(threads) : "memory"); }
 __device__ __forceinline__ void mma_commit_pair(uint64_t* bar) {                    // arrive on this barrier in BOTH CTAs of the cluster
   const uint16_t mask = 3;
   asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(smem_u32(bar)), "h"(mask)
@@ -94,12 +90,15 @@ __device__ __forceinline__ void cluster_sync_all() {
 }
 __device__ __forceinline__ void fence_proxy_all() { asm volatile("fence.proxy.async;" ::: "memory"); }
 __device__ __forceinline__ float tanh_fast(float x) { float r; asm("tanh.approx.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
-__device__ __forceinline__ float sigmoid_fast(float x) { return fmaf(tanh_fast(0.5f * x), 0.5f, 0.5f); }
 __device__ __forceinline__ uint32_t pack_h2(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 
 // byte offset of (row, 16-byte chunk) inside a K-major tile with 64-byte rows (SWIZZLE_64B) / 128-byte rows (SWIZZLE_128B)
 __host__ __device__ inline int sw64_off(int row, int chunk) { return row * 64 + ((chunk ^ ((row >> 1) & 3)) << 4); }
 __host__ __device__ inline int sw128_off(int row, int chunk) { return row * 128 + ((chunk ^ (row & 7)) << 4); }
+
+// column of the h tile (K index of the recurrent GEMM) that holds hidden unit u: K-block r = the 56 units CTA r computes (+ 8 pad
+// columns), so each 16 KB K-block is written by ONE CTA and travels to the peer as plain bulk copies; u = 112: the constant 1
+__host__ __device__ inline int h_col(int u) { return u == 112 ? 120 : 64 * (u / UPC) + u % UPC; }
 
 // ---- weight image: reference layout -> the shared-memory image of one (direction, cta rank) ----------------------------------
 // gate column n = chunk * 32 + gate * 8 + j  <->  unit = 56 rank + 8 chunk + j, PyTorch row gate * H + unit (i, f, g, o)
@@ -107,7 +106,7 @@ __global__ void pack_lstm_tc_kernel(const float* __restrict__ w_ih, const float*
                                     const float* __restrict__ b_hh, const float* __restrict__ w_lin, int H, int dir, int rank,
                                     uint8_t* __restrict__ img) {
   // (the image was zeroed by the caller: pad rows / columns stay 0)
-  // one thread per (n, k) of the gate matrix, k in 0..239 (+ the bias row k = 240 -> h column 112)
+  // one thread per (n, k) of the gate matrix, k in 0..239 (+ the bias row k = 240 -> h column 120)
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NG * 241; e += gridDim.x * blockDim.x) {
     const int n = e / 241, k = e % 241;
     const int chunk = n >> 5, gate = (n >> 3) & 3, j = n & 7;
@@ -119,8 +118,9 @@ __global__ void pack_lstm_tc_kernel(const float* __restrict__ w_ih, const float*
       if (unit < H) v = w_ih[(gate * H + unit) * 128 + c * 4 + tap];
       off = OFF_WU + tap * WU_TILE + sw64_off(n, c >> 3) + (c & 7) * 2;
     } else {
-      const int hk = k - 128;                        // hidden unit 0..111, or 112 = the bias row
-      if (unit < H) v = hk < H ? w_hh[(gate * H + unit) * H + hk] : (hk == 112 ? b_ih[gate * H + unit] + b_hh[gate * H + unit] : 0.f);
+      const int hu = k - 128;                        // hidden unit 0..111, or 112 = the bias row
+      if (unit < H) v = hu < H ? w_hh[(gate * H + unit) * H + hu] : (hu == 112 ? b_ih[gate * H + unit] + b_hh[gate * H + unit] : 0.f);
+      const int hk = h_col(hu);
       off = OFF_WH + (hk >> 6) * WH_TILE + sw128_off(n, (hk & 63) >> 3) + (hk & 7) * 2;
     }
     if (gate != 2) v *= 0.5f;                        // i, f, o: the kernel evaluates sigmoid(x) as 0.5 tanh(x / 2) + 0.5
@@ -129,9 +129,9 @@ __global__ void pack_lstm_tc_kernel(const float* __restrict__ w_ih, const float*
   // ConvTranspose1d [2H, C, ks]: rows dir * H + unit; this CTA's columns n = half * 32 + tap * 8 + j for channels
   // c = 8 (2 rank + half) + j: one 32-column TMEM load = the four taps of 8 channels
   for (int e = blockIdx.x * blockDim.x + threadIdx.x; e < NY * 112; e += gridDim.x * blockDim.x) {
-    const int n = e / 112, hk = e % 112;
+    const int n = e / 112, hu = e % 112, hk = h_col(hu);
     const int tap = (n >> 3) & 3, c = 8 * (2 * rank + (n >> 5)) + (n & 7);
-    const float v = hk < H ? w_lin[((dir * H + hk) * 32 + c) * 4 + tap] : 0.f;
+    const float v = hu < H ? w_lin[((dir * H + hu) * 32 + c) * 4 + tap] : 0.f;
     *reinterpret_cast<__half*>(img + OFF_WL + (hk >> 6) * WL_TILE + sw128_off(n, (hk & 63) >> 3) + (hk & 7) * 2) = __float2half_rn(v);
   }
 }
@@ -154,9 +154,11 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + OFF_BAR);
   uint64_t* u_full = bars;                         // [RING]  TMA -> MMA lane
-  uint64_t* mma_done = bars + RING;                // both CTAs' tcgen05.commit of a step -> point-wise warps
-  uint64_t* h_ready = bars + RING + 1;             // 8 local + 8 peer point-wise warps have stored h_i -> MMA lane
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + RING + 2);
+  uint64_t* mma_done = bars + RING;                // [2] both CTAs' gate MMAs of a step are complete, per column slice -> point-wise warps
+  uint64_t* y_done = bars + RING + 2;              // both CTAs' ConvTranspose1d MMAs (the last readers of h_{i-1}) are complete
+  uint64_t* h_local = bars + RING + 3;             // this CTA's K-block of h_i is stored (4 row groups) -> MMA lane
+  uint64_t* h_peer = bars + RING + 4;              // the peer's K-block of h_i has arrived (16 KB of bulk copies) -> MMA lane
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + RING + 5);
   const int L = a.L, n_loads = L + 3;
   const bool rev = dir == 1;
 
@@ -169,15 +171,19 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
     for (int i = threadIdx.x; i < 2 * H_TILE / 16; i += TC_THREADS) hz[i] = make_uint4(0u, 0u, 0u, 0u);
   }
   __syncthreads();
-  if (threadIdx.x < 128) {                         // h column 112 (K-block 1, chunk 6, element 0) = 1.0 for every row
+  if (threadIdx.x < 128) {                         // h column 120 (K-block 1, chunk 7, element 0) = 1.0 for every row
     const int r = threadIdx.x;
-    *reinterpret_cast<__half*>(smem + OFF_H + H_TILE + sw128_off(r, 6)) = __float2half(1.0f);
+    *reinterpret_cast<__half*>(smem + OFF_H + H_TILE + sw128_off(r, 7)) = __float2half(1.0f);
   }
   if (threadIdx.x == 0) {
     for (int i = 0; i < RING; ++i) mbar_init(u_full + i, 1);
     mbar_init(mma_done, 2);
-    mbar_init(h_ready, 16);
+    mbar_init(mma_done + 1, 2);
+    mbar_init(y_done, 2);
+    mbar_init(h_local, 4);
+    mbar_init(h_peer, 1);                          // the arming arrive; the data counts as transaction bytes
     fence_barrier_init();
+    mbar_expect_tx(h_peer, H_TILE);                // phase 0: the peer's K-block arrives as 4 x 4 KB bulk copies
     tma_prefetch_desc(&map_x);
   }
   if (warp == 1) { tmem_alloc(tmem_slot, 512); tmem_relinquish(); }
@@ -197,7 +203,11 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
 
   if (warp == 0) {
     // ------------------------------------------------------------------ TMA producer + MMA issuer (whole warp walks, one lane issues)
+    // gate columns in two slices (chunks 0..3 / 4..6 = the two point-wise warp sets), each with its own commit: the first
+    // set starts on its columns while the tensor core still computes the second's
+    constexpr int N0 = 128, N1 = NG - N0;
     constexpr uint32_t idesc_g = make_idesc_f16(128, NG, 0), idesc_y = make_idesc_f16(128, NY, 0);
+    constexpr uint32_t idesc_s[2] = {make_idesc_f16(128, N0, 0), make_idesc_f16(128, N1, 0)};
     auto load_u = [&](int q) {
       if (q < n_loads) {
         mbar_expect_tx(u_full + q % RING, U_TILE);
@@ -218,17 +228,15 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
         }
       }
     };
-    auto issue_h_part = [&](int i) {               // += [h_{i-1} | 1] [W_hh ; b]
+    auto issue_h_part = [&](int i, int kb, int slice) {      // columns of `slice` += K-block kb of [h_{i-1} | 1] [W_hh ; b]
 #pragma unroll
-      for (int kb = 0; kb < 2; ++kb)
-#pragma unroll
-        for (int k = 0; k < 4; ++k)
-          mma_f16(gate_acc(i), make_desc(s_base + OFF_H + kb * H_TILE + 32 * k, 1024, 2), make_desc(s_base + OFF_WH + kb * WH_TILE + 32 * k, 1024, 2),
-                  idesc_g, 1u);
+      for (int k = 0; k < 4; ++k)
+        mma_f16(gate_acc(i) + slice * N0, make_desc(s_base + OFF_H + kb * H_TILE + 32 * k, 1024, 2),
+                make_desc(s_base + OFF_WH + kb * WH_TILE + slice * N0 * 128 + 32 * k, 1024, 2), idesc_s[slice], 1u);
     };
-    auto issue_y = [&]() {                         // y = h W_lin (k = 0..111: 4 + 3 k16 steps)
+    auto issue_y = [&]() {                         // y = h W_lin
 #pragma unroll
-      for (int kk = 0; kk < 7; ++kk) {
+      for (int kk = 0; kk < 8; ++kk) {
         const int kb = kk >> 2, k = kk & 3;
         mma_f16(tmem_y, make_desc(s_base + OFF_H + kb * H_TILE + 32 * k, 1024, 2), make_desc(s_base + OFF_WL + kb * WL_TILE + 32 * k, 1024, 2),
                 idesc_y, kk > 0 ? 1u : 0u);
@@ -241,20 +249,32 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
     fence_after_sync();
     if (EARLY) { if (elect_one()) issue_u_part(0); __syncwarp(); }
     for (int i = 0; i < L; ++i) {
-      if (i > 0) {
-        // h_{i-1} is in this CTA's tile (both halves) and every point-wise warp of the pair has read its accumulators of step i - 1
-        mbar_wait_cluster(h_ready, (i - 1) & 1);
-        // the ring slot of load i - 1 + ahead was last read by input MMAs that completed before the commit those warps waited on
-        if (elect_one()) load_u(i - 1 + ahead);
-        __syncwarp();
-      }
+      const int mine = static_cast<int>(rank), theirs = mine ^ 1;
       if (!EARLY && i > 0) wait_u(i + 3);
+      // this CTA's own K-block of h_{i-1} is complete first (no transfer): its MMAs run while the peer's K-block is in flight.
+      // (h_local also says this CTA's point-wise warps have read their accumulators of step i - 1.)
+      if (i > 0) mbar_wait(h_local, (i - 1) & 1);
       fence_after_sync();
       if (elect_one()) {
         if (!EARLY) issue_u_part(i);
-        issue_h_part(i);
-        if (i > 0) issue_y();
+        issue_h_part(i, mine, 0);
+        issue_h_part(i, mine, 1);
+      }
+      __syncwarp();
+      if (i > 0) {
+        mbar_wait(h_peer, (i - 1) & 1);
+        // the ring slot of load i - 1 + ahead was last read by input MMAs that completed before the commit the point-wise warps waited on
+        if (elect_one()) { mbar_expect_tx(h_peer, H_TILE); load_u(i - 1 + ahead); }
+        __syncwarp();
+      }
+      fence_after_sync();
+      if (elect_one()) {
+        issue_h_part(i, theirs, 0);
         mma_commit_pair(mma_done);
+        issue_h_part(i, theirs, 1);
+        mma_commit_pair(mma_done + 1);
+        if (i > 0) issue_y();                                     // y_{i-1}: behind the gates, off the recurrence
+        mma_commit_pair(y_done);                                  // = every reader of h_{i-1} (both slices, y) is done
       }
       __syncwarp();
       if (EARLY && i + 1 < L) {
@@ -264,9 +284,10 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
         __syncwarp();
       }
     }
-    mbar_wait_cluster(h_ready, (L - 1) & 1);
+    mbar_wait(h_local, (L - 1) & 1);
+    mbar_wait(h_peer, (L - 1) & 1);
     fence_after_sync();
-    if (elect_one()) { issue_y(); mma_commit_pair(mma_done); }    // tail: y_{L-1}
+    if (elect_one()) { issue_y(); mma_commit_pair(y_done); }      // tail: y_{L-1}
     __syncwarp();
   } else if (warp >= 2) {
     // ------------------------------------------------------------------ point-wise update: thread = (sequence row, half of the units)
@@ -276,8 +297,10 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
     const int seq = seq0 + row;
     const bool ok = seq < a.n_seq;
     const uint32_t lane_sel = (static_cast<uint32_t>(qd) * 32u) << 16;
-    const uint32_t h_local = s_base + OFF_H, h_peer = map_to_peer(s_base + OFF_H, rank ^ 1);
-    const uint32_t ready_local = smem_u32(h_ready), ready_peer = map_to_peer(smem_u32(h_ready), rank ^ 1);
+    // this CTA's K-block of the h tile, the 4 KB of this warp pair's 32 rows in it, and the same place in the peer
+    const uint32_t h_mine = s_base + OFF_H + rank * H_TILE;
+    const uint32_t h_rows = h_mine + qd * 4096, h_rows_peer = map_to_peer(h_rows, rank ^ 1);
+    const uint32_t ready_peer = map_to_peer(smem_u32(h_peer), rank ^ 1);
     float c[32];
 #pragma unroll
     for (int u = 0; u < 32; ++u) c[u] = 0.f;
@@ -309,7 +332,7 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
     };
     uint32_t yv[32];
     for (int i = 0; i < L; ++i) {
-      mbar_wait(mma_done, i & 1);
+      mbar_wait(mma_done + half, i & 1);
       fence_after_sync();
       const uint32_t t_g = gate_acc(i) + lane_sel;
 #pragma unroll
@@ -330,21 +353,22 @@ lstm_sweep_tc_kernel(const __grid_constant__ CUtensorMap map_x, const TcArgs a) 
             hv[j] = og * tanh_fast(cn);
           }
           const uint4 pk = make_uint4(pack_h2(hv[0], hv[1]), pack_h2(hv[2], hv[3]), pack_h2(hv[4], hv[5]), pack_h2(hv[6], hv[7]));
-          // hidden units 56 rank + 8 ch .. + 7  ->  K index, K-block, 16-byte chunk
-          const int k0 = UPC * static_cast<int>(rank) + 8 * ch;
-          const int off = (k0 >> 6) * H_TILE + sw128_off(row, (k0 & 63) >> 3);
-          st_cluster_v4(h_peer + off, pk);
-          st_cluster_v4(h_local + off, pk);
+          // h_{i-1} may be overwritten once both CTAs' MMAs of this step (the other slice, y_{i-1}) are done with it
+          if (c4 == 0) { mbar_wait(y_done, i & 1); fence_after_sync(); }
+          st_shared_v4(h_mine + sw128_off(row, ch), pk);          // hidden units 56 rank + 8 ch .. + 7 = chunk ch of this CTA's K-block
         }
       }
       if (i > 0) { tmem_ld_32x32(tmem_y + lane_sel + 32 * half, yv); tmem_ld_wait(); }
       fence_before_sync();                         // TMEM reads done before the next MMAs overwrite the accumulators
-      fence_proxy_all();                           // h stores (generic proxy, own + peer CTA) -> visible to the tensor cores' async proxy
-      __syncwarp();
-      if (lane == 0) { mbar_arrive_cluster(ready_peer); mbar_arrive_cluster(ready_local); }
-      if (i > 0) emit(i - 1, yv);                  // the global store sits behind the arrive: its latency is off the recurrence
+      fence_proxy_async();                         // h stores (generic proxy) -> visible to the async proxy (UMMA, bulk copy)
+      named_bar_sync(1 + qd, 64);                  // both warps of this row group
+      if (half == 0 && lane == 0) {
+        bulk_copy_to_peer(h_rows_peer, h_rows, 4096, ready_peer);
+        mbar_arrive(h_local);
+      }
+      if (i > 0) emit(i - 1, yv);                  // the global store sits behind the hand-off: its latency is off the recurrence
     }
-    mbar_wait(mma_done, L & 1);
+    mbar_wait(y_done, L & 1);
     fence_after_sync();
     tmem_ld_32x32(tmem_y + lane_sel + 32 * half, yv);
     tmem_ld_wait();
