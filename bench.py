@@ -481,9 +481,9 @@ def tfgridnet_main(args):
         "e2e": {"value": audio_s * args.steps / (ms_e2e * 1e-3), "unit": UNIT, "h2d_bytes_per_step": args.utts * N_SAMPLES * 4,
                 "d2h_bytes_per_step": args.utts * N_SAMPLES * 4, "ms_per_step": ms_e2e / args.steps},
         "gpu_launches": ((args.utts + mb - 1) // mb) * (3 + n_fwd * (4 + 5 * 10 + 1)) * args.steps,
-        "roofline": {"bound": "tensor", "kernel": "lstm_sweep_kernel (persistent BiLSTM, mma.sync m16n8k16 fp16, weights resident in shared memory)",
+        "roofline": {"bound": "tensor", "kernel": "lstm_sweep_tc_kernel (BiLSTM sweep: tcgen05 UMMA M=128 N=224 per CTA of a 2-CTA cluster, fp16 operands, fp32 TMEM accumulators, hidden state exchanged by cp.async.bulk over DSMEM)",
                      "achieved": achieved, "peak": peak, "unit": "TFLOP/s", "frac": achieved / peak, "traffic": None,
-                     "note": f"algorithmic {gflop_fwd:.1f} GFLOP of LSTM + ConvTranspose1d work per forward per utterance over the WHOLE step time"},
+                     "note": f"algorithmic {gflop_fwd:.1f} GFLOP of LSTM + ConvTranspose1d work per forward per utterance over the WHOLE step time; the recurrence is latency-bound (one dependent step every ~2.7 us), see DESIGN.md section 4"},
         "clocks": clock_info}))
     return 0
 
