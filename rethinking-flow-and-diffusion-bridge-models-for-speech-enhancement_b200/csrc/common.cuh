@@ -150,12 +150,13 @@ int64_t conv_wgrad_workspace_bytes(int Cout, int Cin, int ksize, int B, int T, i
 int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksize, int B, int T, int F, float scale,
                       int io_layout, float* dw, float* workspace, cudaStream_t s);
 // ---- training-step passes (train_kernels.cu)
-int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s);
+int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s,
+                        bool acc_first = false);   // acc_first: acc_dst = value instead of +=
 int launch_gn_bwd_reduce(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
                          const float2* tab, const float2* stats, int act, int B, int64_t P, double* S, cudaStream_t s);
 int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
                         const float2* tab, const float2* stats, const float* gamma, int act, int B, int64_t P, const double* S,
-                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s);
+                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s, bool acc_first = false);
 int launch_gn_param_grad(const double* S, int B, int C, float inv_scale, float* dgamma, float* dbeta, cudaStream_t s);
 int launch_gn_stats(const double* sums1, int C1, const double* sums2, int C2, int B, int64_t pixels, float2* stats, cudaStream_t s);
 int launch_fir_resample16(const op_t* in, int in_ld, int in_coff, int B, int T, int F, int C, int mode, float scale,
@@ -188,5 +189,18 @@ int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout);
 // ksize 3 / 1: OIHW; -1: NIN matrix [in][out]; -2: first conv, OIHW [Cout][C1<=4][3][3] as one im2col K-block of 64
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,
                              int row_offset, op_t* wpack, cudaStream_t s);
+// All weight packs of a plan in ONE launch (a training step re-packs ~300 weight tensors after Adam; one launch each was 1.9 ms
+// of launch latency): a descriptor per pack, blocks of kPackChunk consecutive output elements, the block looks its descriptor up.
+struct PackDesc {
+  const float* w1; const float* w2; op_t* out;
+  int kind;                                  // 0: forward pack (launch_pack_conv_weights), 1: dgrad pack (launch_pack_conv_weights_dgrad)
+  int C1, ksize, io, C2, Cout, rows_total, row_offset;      // kind 1: C1 = Cin, C2 = Cin_total, row_offset = ci_off
+  long long total;                           // elements this pack writes
+  long long first_block;                     // filled by the plan: first block of the batched launch that belongs to this pack
+};
+constexpr int kPackChunk = 2048;
+PackDesc pack_desc_fwd(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total, int row_offset, op_t* wpack);
+PackDesc pack_desc_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, int Cin_total, int ci_off);
+int launch_pack_batch(const PackDesc* descs_dev, int n_descs, long long n_blocks, cudaStream_t s);
 
 }  // namespace fdbm

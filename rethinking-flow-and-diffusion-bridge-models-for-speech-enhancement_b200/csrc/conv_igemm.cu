@@ -741,58 +741,66 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   if (warp == 3) tmem_dealloc(tmem_base, 512);
 }
 
-// weight packing: fp32 (OIHW, or [in][out] for NIN) -> bf16 [kt][rows_total][64]
-__global__ void __launch_bounds__(256)
-pack_weights_kernel(const float* __restrict__ w1, int C1, int ksize, int io_layout, const float* __restrict__ w2,
-                    int C2, int Cout, int rows_total, int row_offset, op_t* __restrict__ out) {
+// weight packing: fp32 (OIHW, or [in][out] for NIN) -> 16-bit [kt][rows_total][64]
+__device__ __forceinline__ void pack_fwd_element(const PackDesc& d, int64_t i) {
+  const int C1 = d.C1, C2 = d.C2, Cout = d.Cout, ksize = d.ksize, io_layout = d.io;
   const int taps = ksize * ksize;
-  const int n_kt = io_layout == 2 ? 1 : (C1 / 64) * taps + C2 / 64;
-  const int64_t total = static_cast<int64_t>(n_kt) * Cout * 64;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int j = static_cast<int>(i % 64);
-    const int co = static_cast<int>((i / 64) % Cout);
-    const int kt = static_cast<int>(i / (64ll * Cout));
-    float v;
-    if (io_layout == 2) {                           // first conv: k = tap * C1 + ci, zero beyond 9 * C1
-      const int tap = j / C1, ci = j % C1;
-      v = tap < 9 ? w1[((static_cast<int64_t>(co) * C1 + ci) * 3 + tap / 3) * 3 + tap % 3] : 0.f;
-    } else if (kt < (C1 / 64) * taps) {
-      const int kb = kt / taps, tap = kt % taps;
-      const int ci = kb * 64 + j;
-      if (io_layout) v = w1[static_cast<int64_t>(ci) * Cout + co];
-      else {
-        const int kf = ksize == 3 ? tap / 3 : 0, ktm = ksize == 3 ? tap % 3 : 0;
-        v = w1[((static_cast<int64_t>(co) * C1 + ci) * ksize + kf) * ksize + ktm];
-      }
-    } else {
-      const int ci = (kt - (C1 / 64) * taps) * 64 + j;
-      v = w2[static_cast<int64_t>(co) * C2 + ci];
+  const int j = static_cast<int>(i % 64);
+  const int co = static_cast<int>((i / 64) % Cout);
+  const int kt = static_cast<int>(i / (64ll * Cout));
+  float v;
+  if (io_layout == 2) {                           // first conv: k = tap * C1 + ci, zero beyond 9 * C1
+    const int tap = j / C1, ci = j % C1;
+    v = tap < 9 ? d.w1[((static_cast<int64_t>(co) * C1 + ci) * 3 + tap / 3) * 3 + tap % 3] : 0.f;
+  } else if (kt < (C1 / 64) * taps) {
+    const int kb = kt / taps, tap = kt % taps;
+    const int ci = kb * 64 + j;
+    if (io_layout) v = d.w1[static_cast<int64_t>(ci) * Cout + co];
+    else {
+      const int kf = ksize == 3 ? tap / 3 : 0, ktm = ksize == 3 ? tap % 3 : 0;
+      v = d.w1[((static_cast<int64_t>(co) * C1 + ci) * ksize + kf) * ksize + ktm];
     }
-    out[(static_cast<int64_t>(kt) * rows_total + row_offset + co) * 64 + j] = f2op(v);
+  } else {
+    const int ci = (kt - (C1 / 64) * taps) * 64 + j;
+    v = d.w2[static_cast<int64_t>(co) * C2 + ci];
   }
+  d.out[(static_cast<int64_t>(kt) * d.rows_total + d.row_offset + co) * 64 + j] = f2op(v);
 }
 
 // dgrad packing: the input gradient of a convolution is itself a convolution of dY with the weights transposed
 // (in <-> out) and flipped (tap (df,dt) -> (2-df,2-dt)):  W'[ci][co][df'][dt'] = W[co][ci][2-df'][2-dt'].
 // Output rows = Cin of the forward conv, K = Cout of the forward conv.
-__global__ void __launch_bounds__(256)
-pack_weights_dgrad_kernel(const float* __restrict__ w, int Cout, int Cin, int ksize, int io_layout, int Cin_total, int ci_off,
-                          op_t* __restrict__ out) {
+__device__ __forceinline__ void pack_dgrad_element(const PackDesc& d, int64_t i) {
+  const int Cin = d.C1, Cin_total = d.C2, Cout = d.Cout, ksize = d.ksize, ci_off = d.row_offset;
   const int taps = ksize * ksize;
-  const int64_t total = static_cast<int64_t>(Cout / 64) * taps * Cin * 64;
-  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < total; i += 256ll * gridDim.x) {
-    const int j = static_cast<int>(i % 64);
-    const int ci = static_cast<int>((i / 64) % Cin);
-    const int kt = static_cast<int>(i / (64ll * Cin));
-    const int kb = kt / taps, tap = kt % taps;
-    const int co = kb * 64 + j;
-    float v;
-    if (io_layout) v = w[static_cast<int64_t>(ci_off + ci) * Cout + co];          // NIN [in][out]
-    else {
-      const int kf = ksize == 3 ? 2 - tap / 3 : 0, ktm = ksize == 3 ? 2 - tap % 3 : 0;
-      v = w[((static_cast<int64_t>(co) * Cin_total + ci_off + ci) * ksize + kf) * ksize + ktm];
-    }
-    out[i] = f2op(v);
+  const int j = static_cast<int>(i % 64);
+  const int ci = static_cast<int>((i / 64) % Cin);
+  const int kt = static_cast<int>(i / (64ll * Cin));
+  const int kb = kt / taps, tap = kt % taps;
+  const int co = kb * 64 + j;
+  float v;
+  if (d.io) v = d.w1[static_cast<int64_t>(ci_off + ci) * Cout + co];          // NIN [in][out]
+  else {
+    const int kf = ksize == 3 ? 2 - tap / 3 : 0, ktm = ksize == 3 ? 2 - tap % 3 : 0;
+    v = d.w1[((static_cast<int64_t>(co) * Cin_total + ci_off + ci) * ksize + kf) * ksize + ktm];
+  }
+  d.out[i] = f2op(v);
+}
+
+__global__ void __launch_bounds__(256)
+pack_batch_kernel(const PackDesc* __restrict__ descs, int n) {
+  __shared__ PackDesc d;
+  if (threadIdx.x == 0) {
+    int lo = 0, hi = n - 1;                                   // last descriptor whose first_block <= blockIdx.x
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (descs[mid].first_block <= static_cast<long long>(blockIdx.x)) lo = mid; else hi = mid - 1; }
+    d = descs[lo];
+  }
+  __syncthreads();
+  const int64_t i0 = (static_cast<int64_t>(blockIdx.x) - d.first_block) * kPackChunk;
+#pragma unroll 1
+  for (int u = 0; u < kPackChunk / 256; ++u) {
+    const int64_t i = i0 + u * 256 + threadIdx.x;
+    if (i < d.total) { if (d.kind == 0) pack_fwd_element(d, i); else pack_dgrad_element(d, i); }
   }
 }
 
@@ -852,17 +860,45 @@ int64_t conv_wpack_bytes(int C1, int ksize, int C2, int Cout) {
   return (static_cast<int64_t>(C1 / 64) * ksize * ksize + C2 / 64) * Cout * 64 * 2;
 }
 
+PackDesc pack_desc_fwd(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total, int row_offset, op_t* wpack) {
+  const int io = ksize == -1 ? 1 : (ksize == -2 ? 2 : 0);   // -1: NIN [in][out];  -2: first conv as one im2col K-block
+  const int k = io ? 1 : ksize;
+  PackDesc d{};
+  d.w1 = w1; d.w2 = w2; d.out = wpack; d.kind = 0; d.C1 = C1; d.ksize = k; d.io = io; d.C2 = C2; d.Cout = Cout;
+  d.rows_total = n_rows_total; d.row_offset = row_offset;
+  d.total = io == 2 ? static_cast<long long>(Cout) * 64 : (static_cast<long long>(C1 / 64) * k * k + C2 / 64) * Cout * 64;
+  return d;
+}
+PackDesc pack_desc_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, int Cin_total, int ci_off) {
+  const int k = ksize == -1 ? 1 : ksize;
+  PackDesc d{};
+  d.w1 = w; d.w2 = nullptr; d.out = wpack; d.kind = 1; d.C1 = Cin; d.ksize = k; d.io = ksize == -1; d.C2 = Cin_total ? Cin_total : Cin; d.Cout = Cout;
+  d.rows_total = 0; d.row_offset = ci_off;
+  d.total = static_cast<long long>(Cout / 64) * k * k * Cin * 64;
+  return d;
+}
+int launch_pack_batch(const PackDesc* descs_dev, int n_descs, long long n_blocks, cudaStream_t s) {
+  if (n_descs <= 0 || n_blocks <= 0) return FDBM_OK;
+  pack_batch_kernel<<<static_cast<unsigned>(n_blocks), 256, 0, s>>>(descs_dev, n_descs);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+// single packs (tests, one-off packs): a one-descriptor batch through a small device staging copy is not worth it -- these build
+// the descriptor on the host and pass it by value
+__global__ void __launch_bounds__(256) pack_one_kernel(const PackDesc d) {
+  for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < d.total; i += 256ll * gridDim.x) {
+    if (d.kind == 0) pack_fwd_element(d, i); else pack_dgrad_element(d, i);
+  }
+}
+
 int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total,
                              int row_offset, op_t* wpack, cudaStream_t s) {
   FDBM_REQUIRE((ksize == -2 && C1 <= 4 && C2 == 0) ||
                (C1 % 64 == 0 && C2 % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1)),
                "pack_conv_weights: channels must be multiples of 64, ksize 1 or 3");
-  const int io = ksize == -1 ? 1 : (ksize == -2 ? 2 : 0);   // -1: NIN [in][out];  -2: first conv as one im2col K-block
-  const int k = io ? 1 : ksize;
-  const int64_t total = io == 2 ? static_cast<int64_t>(Cout) * 64
-                                : (static_cast<int64_t>(C1 / 64) * k * k + C2 / 64) * Cout * 64;
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096));
-  pack_weights_kernel<<<grid, 256, 0, s>>>(w1, C1, k, io, w2, C2, Cout, n_rows_total, row_offset, wpack);
+  const PackDesc d = pack_desc_fwd(w1, C1, ksize, w2, C2, Cout, n_rows_total, row_offset, wpack);
+  pack_one_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(d.total, 256), 4096)), 256, 0, s>>>(d);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -873,9 +909,8 @@ int launch_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2
 int launch_pack_conv_weights_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, cudaStream_t s, int Cin_total, int ci_off) {
   FDBM_REQUIRE(Cout % 64 == 0 && Cin % 64 == 0 && (ksize == 1 || ksize == 3 || ksize == -1),
                "pack_conv_weights_dgrad: channels must be multiples of 64, ksize 1, 3 or -1 (NIN)");
-  const int k = ksize == -1 ? 1 : ksize;
-  const int64_t total = static_cast<int64_t>(Cout / 64) * k * k * Cin * 64;
-  pack_weights_dgrad_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(total, 256), 4096)), 256, 0, s>>>(w, Cout, Cin, k, ksize == -1, Cin_total ? Cin_total : Cin, ci_off, wpack);
+  const PackDesc d = pack_desc_dgrad(w, Cout, Cin, ksize, wpack, Cin_total, ci_off);
+  pack_one_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(d.total, 256), 4096)), 256, 0, s>>>(d);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

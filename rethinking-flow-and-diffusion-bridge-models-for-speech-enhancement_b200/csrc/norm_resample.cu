@@ -197,7 +197,11 @@ groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ s
 #pragma unroll
         for (int j = 0; j < 8; ++j) {
           float y = fmaf(x[j], a[j], bb[j]);
-          if (silu) y = __fdividef(y, 1.0f + __expf(-y));
+          if (silu) {                                     // y sigmoid(y), sigmoid(y) = 1/2 + tanh(y/2)/2: one MUFU instead of EX2 + RCP
+            float th;
+            asm("tanh.approx.f32 %0, %1;" : "=f"(th) : "f"(0.5f * y));
+            y *= fmaf(th, 0.5f, 0.5f);
+          }
           acc[j] = fmaf(w, y, acc[j]);
           raw[j] = fmaf(w, x[j], raw[j]);
         }

@@ -108,7 +108,9 @@ struct fdbm_plan {
   std::vector<std::function<int(cudaStream_t)>> ops;        // one forward: exactly one kernel launch per entry
   std::vector<int> op_kind;                                  // FDBM_OP_* of every entry
   std::vector<double> op_flops;                              // algorithmic FLOPs (2*MAC) of every entry (convs)
-  std::vector<std::function<int(cudaStream_t)>> pack_ops;   // weight packing after load_weights
+  std::vector<std::function<int(cudaStream_t)>> pack_ops;   // weight packing after load_weights (the few odd ones)
+  std::vector<PackDesc> pack_descs;                          // ... and all regular conv packs, run as ONE launch
+  PackDesc* pack_descs_d = nullptr; long long pack_blocks = 0;
   int n_launches = 0;
   // training (fdbm_plan_create_train): nothing in the arena is reused, every forward tensor stays live for backward
   bool train = false;
@@ -119,7 +121,25 @@ struct fdbm_plan {
   int64_t wgrad_ws_bytes = 0;
   std::vector<std::function<int(cudaStream_t)>> bwd_ops;
   std::vector<int> bwd_kind;
-  std::vector<std::pair<void*, size_t>> zero_list;      // activation-gradient buffers cleared when backward starts
+  // Activation-gradient accumulators (fp32, one per residual-stream tensor).  They are not cleared up front: the FIRST
+  // contribution of a backward pass writes instead of adding (saves the memset and one read of every tensor per step); an
+  // op that can only add, or an op that reads a buffer nobody wrote, clears it on demand.
+  std::vector<std::pair<void*, size_t>> zero_list;
+  std::unordered_map<const void*, int> gz_index;
+  std::vector<uint8_t> gz_written;
+  void grads_begin() { gz_written.assign(zero_list.size(), 0); }
+  bool grad_first(const float* g) {                     // true exactly once per backward pass and buffer
+    auto it = gz_index.find(g);
+    if (it == gz_index.end() || gz_written[it->second]) return false;
+    gz_written[it->second] = 1;
+    return true;
+  }
+  int grad_ensure(const float* g, cudaStream_t s) {     // before an add-only writer or a reader
+    if (!grad_first(g)) return FDBM_OK;
+    const auto& z = zero_list[gz_index[g]];
+    FDBM_CUDA(cudaMemsetAsync(z.first, 0, z.second, s));
+    return FDBM_OK;
+  }
   const float* cur_gout = nullptr;     // dL/dD of the current backward call (loss-scaled), cplx [B,1,257,T]
   float cur_inv = 1.0f;                // 1 / loss scale
   float* adam_m = nullptr; float* adam_v = nullptr; float* ema = nullptr; double* opt_scratch = nullptr;
@@ -229,7 +249,7 @@ struct Builder {
   float* gp(int64_t off) const { return P->grads + off; }
   float* galloc(int64_t n) {
     float* g = alloc<float>(n);
-    if (!dry) P->zero_list.emplace_back(g, static_cast<size_t>(n) * sizeof(float));
+    if (!dry) { P->gz_index[g] = static_cast<int>(P->zero_list.size()); P->zero_list.emplace_back(g, static_cast<size_t>(n) * sizeof(float)); }
     return g;
   }
   op_t* pack_d(int64_t w_off, int Cout, int Cin, int ksize, int Cin_total = 0, int ci_off = 0, op_t* into = nullptr) {
@@ -240,7 +260,7 @@ struct Builder {
       wd_off += (conv_wpack_bytes(Cout, k, 0, Cin) + 1023) / 1024 * 1024;
     }
     const float* w = pp(w_off);
-    pack_op([=](cudaStream_t s) { return launch_pack_conv_weights_dgrad(w, Cout, Cin, ksize, dst, s, Cin_total, ci_off); });
+    if (!dry) P->pack_descs.push_back(pack_desc_dgrad(w, Cout, Cin, ksize, dst, Cin_total, ci_off));
     return dst;
   }
   // dX (+)= conv(dY, W'): 16-bit output and/or fp32 in-place accumulation
@@ -249,7 +269,12 @@ struct Builder {
     c.seg[0] = seg(dy, Cdy, taps); c.n_seg = 1;
     c.wpack = wd; c.bias = zero_bias; c.residual = acc; c.scale = 1.0f;
     c.B = P->B; c.T = T; c.F = F; c.Cout = Cdx; c.out_f32 = acc; c.out_h16 = out16;
-    bop([=](cudaStream_t s) { return launch_conv_igemm(c, s); }, FDBM_OP_CONV);
+    fdbm_plan* plp = P;
+    bop([=](cudaStream_t s) {
+      ConvArgs cc = c;
+      if (acc && plp->grad_first(acc)) cc.residual = nullptr;     // first contribution: write, do not read-add
+      return launch_conv_igemm(cc, s);
+    }, FDBM_OP_CONV);
   }
   void wgrad_op(WgradCall c, int64_t dw_off) {
     c.B = P->B;
@@ -274,8 +299,10 @@ struct Builder {
       FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Ct, s));
       if (int rc = launch_gn_bwd_reduce(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, act, B, px, S, s)) return rc;
       if (C2) if (int rc = launch_gn_bwd_reduce(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, act, B, px, S, s)) return rc;
-      if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, gamma, act, B, px, S, a1.grad, nullptr, nullptr, s)) return rc;
-      if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, gamma, act, B, px, S, a2.grad, nullptr, nullptr, s)) return rc;
+      if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, gamma, act, B, px, S, a1.grad, nullptr, nullptr, s,
+                                       plp->grad_first(a1.grad))) return rc;
+      if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, gamma, act, B, px, S, a2.grad, nullptr, nullptr, s,
+                                               plp->grad_first(a2.grad))) return rc;
       return launch_gn_param_grad(S, B, Ct, plp->cur_inv, plp->grads + gw_off, plp->grads + gb_off, s);
     });
   }
@@ -384,9 +411,7 @@ struct Builder {
     }
     const float* p1 = pp(param(w1, static_cast<int64_t>(Cout) * C1 * k * k));
     const float* p2 = C2 ? pp(param(w2, static_cast<int64_t>(Cout) * C2)) : nullptr;
-    pack_op([=](cudaStream_t s) {
-      return launch_pack_conv_weights(p1, C1, ksize, p2, C2, Cout, rows_total, row_off, dst, s);
-    });
+    if (!dry) P->pack_descs.push_back(pack_desc_fwd(p1, C1, ksize, p2, C2, Cout, rows_total, row_off, dst));
     return dst;
   }
 
@@ -501,7 +526,8 @@ struct Builder {
       {   // gs = dL/d(out) / sqrt(2) as a 16-bit operand; identity shortcut: x.grad += gs; bias gradients
         const float* og = out.grad; float* xg = shortcut ? nullptr : xa.grad;
         bop([=](cudaStream_t s) {
-          if (int rc = launch_grad_prepare(og, B, pxo, Cout, 0.70710678118654752f, t1, xg, sA, s)) return rc;
+          if (int rc = plp->grad_ensure(og, s)) return rc;
+          if (int rc = launch_grad_prepare(og, B, pxo, Cout, 0.70710678118654752f, t1, xg, sA, s, xg && plp->grad_first(xg))) return rc;
           if (int rc = launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c1b, nullptr, 0, s)) return rc;
           if (o_c2b >= 0) return launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c2b, nullptr, 0, s);
           return FDBM_OK;
@@ -525,7 +551,10 @@ struct Builder {
           dgrad_op(t1, Cout, 1, wd, Cin, To, Fo, t3, nullptr);
           float* xg = xa.grad;
           // adjoint of the FIR on the shortcut operand: adjoint(down) = up / 4, adjoint(up) = 4 * down
-          bop([=](cudaStream_t s) { return launch_fir_resample16(t3, Cin, 0, B, To, Fo, Cin, mode == 1 ? 2 : 1, mode == 1 ? 0.25f : 4.0f, nullptr, xg, s); });
+          bop([=](cudaStream_t s) {
+            if (int rc = plp->grad_ensure(xg, s)) return rc;                 // this kernel only adds
+            return launch_fir_resample16(t3, Cin, 0, B, To, Fo, Cin, mode == 1 ? 2 : 1, mode == 1 ? 0.25f : 4.0f, nullptr, xg, s);
+          });
           WgradCall w; w.dy = t1; w.dy_ld = Cout; w.Cout = Cout; w.x = xr; w.x_ld = Cin; w.Cin = Cin; w.ksize = 1; w.T = To; w.F = Fo;
           wgrad_op(w, o_c2w);
         }
@@ -610,7 +639,8 @@ struct Builder {
       const Act xa = x;
       { const float* og = out.grad; float* xg = xa.grad;
         bop([=](cudaStream_t s) {
-          if (int rc = launch_grad_prepare(og, B, px, C, 0.70710678118654752f, t1, xg, sA, s)) return rc;
+          if (int rc = plp->grad_ensure(og, s)) return rc;
+          if (int rc = launch_grad_prepare(og, B, px, C, 0.70710678118654752f, t1, xg, sA, s, plp->grad_first(xg))) return rc;
           return launch_col_sums_to(sA, B, C, plp->cur_inv, plp->grads + o_b3, nullptr, 0, s);
         }); }
       { WgradCall w; w.dy = t1; w.dy_ld = C; w.Cout = C; w.x = o; w.x_ld = C; w.Cin = C; w.ksize = 1; w.T = T; w.F = F; w.layout = 1; wgrad_op(w, o_w3); }
@@ -740,6 +770,7 @@ struct Builder {
         fdbm_plan* plp = P; op_t* t1 = T1; double* sA = sumsA; const float* g0 = h0.grad;
         const int64_t px = static_cast<int64_t>(T) * F;
         bop([=](cudaStream_t s) {
+          if (int rc = plp->grad_ensure(g0, s)) return rc;
           if (int rc = launch_grad_prepare(g0, B, px, nf, 1.0f, t1, nullptr, sA, s)) return rc;
           return launch_col_sums_to(sA, B, nf, plp->cur_inv, plp->grads + o_b, nullptr, 0, s);
         });
@@ -967,11 +998,26 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   b2.arena.reset(P->arena_bytes);
   if (int rc = b2.build()) return fail(rc);
   P->n_bwd_launches = static_cast<int>(P->bwd_ops.size());
+  if (!P->pack_descs.empty()) {
+    long long nb = 0;
+    for (auto& d : P->pack_descs) { d.first_block = nb; nb += (d.total + kPackChunk - 1) / kPackChunk; }
+    P->pack_blocks = nb;
+    if ((e = cudaMalloc(&P->pack_descs_d, P->pack_descs.size() * sizeof(PackDesc))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(pack descriptors)", __FILE__, __LINE__));
+    if ((e = cudaMemcpy(P->pack_descs_d, P->pack_descs.data(), P->pack_descs.size() * sizeof(PackDesc), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail(cuda_fail(e, "cudaMemcpy(pack descriptors)", __FILE__, __LINE__));
+  }
   if (P->params_numel != params_numel || b2.wp_off != P->wpacked_bytes || b2.wd_off != P->wpacked_d_bytes) {
     set_error("plan: second pass diverged from the sizing pass");
     return fail(FDBM_EINVAL);
   }
   *out = P;
+  return FDBM_OK;
+}
+
+// packed 16-bit weights (forward and dgrad) <- the flat fp32 parameter buffer
+static int run_pack_ops(fdbm_plan* plan, cudaStream_t s) {
+  if (int rc = launch_pack_batch(plan->pack_descs_d, static_cast<int>(plan->pack_descs.size()), plan->pack_blocks, s)) return rc;
+  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
 }
 
@@ -993,7 +1039,7 @@ extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float l
   cudaStream_t s = as_stream(stream);
   plan->cur_gout = g_out; plan->cur_inv = 1.0f / loss_scale;
   if (!accumulate) FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
-  for (auto& z : plan->zero_list) FDBM_CUDA(cudaMemsetAsync(z.first, 0, z.second, s));
+  plan->grads_begin();
   for (auto& f : plan->bwd_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
 }
@@ -1008,7 +1054,7 @@ extern "C" int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, f
   cudaStream_t s = as_stream(stream);
   plan->cur_gout = g_out; plan->cur_inv = 1.0f / loss_scale;
   FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
-  for (auto& z : plan->zero_list) FDBM_CUDA(cudaMemsetAsync(z.first, 0, z.second, s));
+  plan->grads_begin();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) FDBM_CUDA(cudaEventCreate(&e));
   int rc = FDBM_OK;
@@ -1046,7 +1092,7 @@ extern "C" int fdbm_plan_buffers(fdbm_plan* plan, float** params, float** grads,
 extern "C" int fdbm_plan_repack_weights(fdbm_plan* plan, void* stream) {
   if (int rc = plan_guard(plan, "fdbm_plan_repack_weights")) return rc;
   if (!plan->weights_ready) { set_error("fdbm_plan_repack_weights: weights not loaded"); return FDBM_ESTATE; }
-  for (auto& f : plan->pack_ops) if (int rc = f(as_stream(stream))) return rc;
+  if (int rc = run_pack_ops(plan, as_stream(stream))) return rc;
   return FDBM_OK;
 }
 
@@ -1064,7 +1110,7 @@ extern "C" int fdbm_plan_optimizer_step(fdbm_plan* plan, float grad_div, float c
   if (int rc = launch_adam_ema(plan->params, plan->grads, plan->adam_m, plan->adam_v, plan->ema, nullptr, n, plan->opt_scratch, grad_div,
                                clip_norm, lr, beta1, beta2, eps, step, ema_decay, ema_warmup, plan->opt_state, s))
     return rc;
-  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
+  if (int rc = run_pack_ops(plan, s)) return rc;
   return FDBM_OK;
 }
 
@@ -1116,7 +1162,7 @@ extern "C" int fdbm_plan_swap_ema(fdbm_plan* plan, int to_ema, void* stream) {
     FDBM_CUDA(cudaMemcpyAsync(plan->params, plan->ema_backup, bytes, cudaMemcpyDeviceToDevice, s));
     plan->ema_swapped = false;
   }
-  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
+  if (int rc = run_pack_ops(plan, s)) return rc;
   return FDBM_OK;
 }
 
@@ -1133,7 +1179,7 @@ extern "C" int fdbm_plan_destroy(fdbm_plan* plan) {
   cudaFree(plan->arena); cudaFree(plan->params); cudaFree(plan->wpacked); cudaFree(plan->d_buf);
   cudaFree(plan->grads); cudaFree(plan->wpacked_d); cudaFree(plan->wgrad_ws);
   cudaFree(plan->adam_m); cudaFree(plan->adam_v); cudaFree(plan->ema); cudaFree(plan->opt_scratch);
-  cudaFree(plan->opt_state); cudaFree(plan->ema_backup);
+  cudaFree(plan->opt_state); cudaFree(plan->ema_backup); cudaFree(plan->pack_descs_d);
   if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   delete plan;
   return FDBM_OK;
@@ -1155,7 +1201,7 @@ extern "C" int fdbm_plan_load_weights(fdbm_plan* plan, const fdbm_tensor_ref* te
   }
   for (auto& kv : plan->slots)
     FDBM_REQUIRE(kv.second.loaded, "fdbm_plan_load_weights: tensor '%s' was never provided", kv.first.c_str());
-  for (auto& f : plan->pack_ops) if (int rc = f(s)) return rc;
+  if (int rc = run_pack_ops(plan, s)) return rc;
   plan->weights_ready = true;
   return FDBM_OK;
 }

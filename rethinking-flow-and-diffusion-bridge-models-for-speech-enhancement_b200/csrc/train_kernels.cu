@@ -26,7 +26,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
 grad_prepare_kernel(const float* __restrict__ g, int64_t P, int C, int64_t px_per_block, float scale,
-                    op_t* __restrict__ g16, float* __restrict__ acc_dst, double* __restrict__ sums) {
+                    op_t* __restrict__ g16, float* __restrict__ acc_dst, double* __restrict__ sums, int acc_first) {
   __shared__ float4 red[256];
   const int cg = C / 4, pl = 256 / cg;
   const int ci = threadIdx.x % cg, pi = threadIdx.x / cg;
@@ -35,13 +35,14 @@ grad_prepare_kernel(const float* __restrict__ g, int64_t P, int C, int64_t px_pe
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
   if (pi < pl) {
     const int64_t base = static_cast<int64_t>(b) * P * cg + ci;
+#pragma unroll 4
     for (int64_t p = p0 + pi; p < p1; p += pl) {
       float4 v = reinterpret_cast<const float4*>(g)[base + p * cg];
       v.x *= scale; v.y *= scale; v.z *= scale; v.w *= scale;
       if (g16) reinterpret_cast<uint2*>(g16)[base + p * cg] = make_uint2(pack_op2(v.x, v.y), pack_op2(v.z, v.w));
       if (acc_dst) {
-        float4 d = reinterpret_cast<float4*>(acc_dst)[base + p * cg];
-        d.x += v.x; d.y += v.y; d.z += v.z; d.w += v.w;
+        float4 d = v;
+        if (!acc_first) { const float4 o = reinterpret_cast<float4*>(acc_dst)[base + p * cg]; d.x += o.x; d.y += o.y; d.z += o.z; d.w += o.w; }
         reinterpret_cast<float4*>(acc_dst)[base + p * cg] = d;
       }
       s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -83,6 +84,7 @@ struct GnBwdArgs {
   double* S;                                   // [B,C_tot,2]
   // apply outputs
   float* acc_dst;                              // fp32 [B,P,C]: += g_x   (or nullptr)
+  int acc_first;                               // ... = g_x: the first contribution of this backward pass to that buffer
   op_t* out16;                                 // 16-bit [B,P,C] = g_x   (or nullptr)
   double* out_sums;                            // [B,C]: += sum_px g_x   (with out16; or nullptr)
   double inv_count;                            // 1 / (channels per group * P)
@@ -102,7 +104,7 @@ __device__ __forceinline__ void load8(const GnBwdArgs& a, int64_t idx8, float (&
 // d SiLU / dy = sg + y sg (1 - sg), sg = sigmoid(y) = 1/2 + tanh(y/2)/2: one MUFU.TANH instead of EX2 + an IEEE division
 // (these passes were instruction-bound, not HBM-bound: the division alone was a third of their instructions)
 template <bool APPLY>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 4)
 gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   __shared__ float s_m1[32], s_m2[32];
   __shared__ float s_red[256 * 16];
@@ -125,25 +127,23 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   const int cg8 = a.C / 8, npl = 256 / cg8;
   const int g8 = threadIdx.x % cg8, pl = threadIdx.x / cg8;
   const int c0 = g8 * 8;                                   // channel inside this source
-  // packed fp32x2 arithmetic (channel pairs): these passes are instruction-bound
-  float2 sc[4], sh[4], ar[4], br[4], k1[4], k2[4], k3[4];
+  // packed fp32x2 arithmetic (channel pairs).  Per-channel constants: (scale, shift) of y = GN(x); the rest is per GROUP, and a
+  // group has a multiple of 4 channels, so channels c0..c0+3 and c0+4..c0+7 each share one set (register diet: 4 blocks per SM)
+  float2 sc[4], sh[4];
+  float ar[2], br[2], k2[2], k3[2];
 #pragma unroll
   for (int j = 0; j < 4; ++j) {
-    float v[2][7];
+    const int c = a.c_off + c0 + 2 * j;
+    const float2 t0 = a.tab[static_cast<int64_t>(b) * a.C_tot + c], t1 = a.tab[static_cast<int64_t>(b) * a.C_tot + c + 1];
+    sc[j] = make_float2(t0.x, t1.x); sh[j] = make_float2(t0.y, t1.y);    // scale = gamma * rstd: also the k1 of the apply pass
+  }
 #pragma unroll
-    for (int u = 0; u < 2; ++u) {
-      const int c = a.c_off + c0 + 2 * j + u;
-      const float2 t = a.tab[static_cast<int64_t>(b) * a.C_tot + c];
-      const float2 st = a.stats[static_cast<int64_t>(b) * G + c / cpg];
-      v[u][0] = t.x; v[u][1] = t.y;
-      v[u][2] = st.y; v[u][3] = -st.x * st.y;              // xhat = x * rstd - mean * rstd
-      v[u][4] = APPLY ? st.y * a.gamma[c] : 0.f;
-      v[u][5] = APPLY ? st.y * s_m1[c / cpg] : 0.f;
-      v[u][6] = APPLY ? st.y * s_m2[c / cpg] : 0.f;
-    }
-    sc[j] = make_float2(v[0][0], v[1][0]); sh[j] = make_float2(v[0][1], v[1][1]);
-    ar[j] = make_float2(v[0][2], v[1][2]); br[j] = make_float2(v[0][3], v[1][3]);
-    k1[j] = make_float2(v[0][4], v[1][4]); k2[j] = make_float2(-v[0][5], -v[1][5]); k3[j] = make_float2(-v[0][6], -v[1][6]);
+  for (int hf = 0; hf < 2; ++hf) {
+    const int g = (a.c_off + c0 + 4 * hf) / cpg;
+    const float2 st = a.stats[static_cast<int64_t>(b) * G + g];
+    ar[hf] = st.y; br[hf] = -st.x * st.y;                  // xhat = x * rstd - mean * rstd
+    k2[hf] = APPLY ? -st.y * s_m1[g] : 0.f;
+    k3[hf] = APPLY ? -st.y * s_m2[g] : 0.f;
   }
   const float2 half2v = make_float2(0.5f, 0.5f), one2 = make_float2(1.0f, 1.0f), mone2 = make_float2(-1.0f, -1.0f);
   float2 s1[4], s2[4];
@@ -172,9 +172,11 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
           const float2 d = __ffma2_rn(__fmul2_rn(y, sg), __ffma2_rn(sg, mone2, one2), sg);
           gy = __fmul2_rn(gy, d);
         }
-        const float2 xh = __ffma2_rn(x, ar[j], br[j]);
+        const int hf = j >> 1;
+        const float2 xh = __ffma2_rn(x, make_float2(ar[hf], ar[hf]), make_float2(br[hf], br[hf]));
         if (APPLY) {
-          gx[j] = __ffma2_rn(k3[j], xh, __ffma2_rn(k1[j], gy, k2[j]));      // k1 gy - k2' - k3' xh (signs folded in)
+          // gamma rstd gy - rstd m1 - rstd m2 xh (signs folded in)
+          gx[j] = __ffma2_rn(make_float2(k3[hf], k3[hf]), xh, __ffma2_rn(sc[j], gy, make_float2(k2[hf], k2[hf])));
           s1[j] = __fadd2_rn(s1[j], gx[j]);
         } else {
           s1[j] = __fadd2_rn(s1[j], gy);
@@ -184,9 +186,12 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
       if (APPLY) {
         if (a.acc_dst) {
           float4* d = reinterpret_cast<float4*>(a.acc_dst) + (row * cg8 + g8) * 2;
-          float4 d0 = d[0], d1 = d[1];
-          d0.x += gx[0].x; d0.y += gx[0].y; d0.z += gx[1].x; d0.w += gx[1].y;
-          d1.x += gx[2].x; d1.y += gx[2].y; d1.z += gx[3].x; d1.w += gx[3].y;
+          float4 d0 = make_float4(gx[0].x, gx[0].y, gx[1].x, gx[1].y), d1 = make_float4(gx[2].x, gx[2].y, gx[3].x, gx[3].y);
+          if (!a.acc_first) {
+            const float4 o0 = d[0], o1 = d[1];
+            d0.x += o0.x; d0.y += o0.y; d0.z += o0.z; d0.w += o0.w;
+            d1.x += o1.x; d1.y += o1.y; d1.z += o1.z; d1.w += o1.w;
+          }
           d[0] = d0; d[1] = d1;
         }
         if (a.out16)
@@ -547,7 +552,8 @@ int grid_for(int64_t n) { return static_cast<int>(std::min<int64_t>(ceil_div64(n
 
 }  // namespace
 
-int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s) {
+int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s,
+                        bool acc_first) {
   FDBM_REQUIRE(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "grad_prepare: unsupported channel count %d", C);
   if (sums) FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C, s));
   const int pl = 256 / (C / 4);
@@ -555,7 +561,7 @@ int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op
   blocks_x = std::min<int64_t>(blocks_x, std::max<int64_t>(1, P / (pl * 8)));
   const int64_t ppb = ceil_div64(P, blocks_x);
   dim3 grid(static_cast<unsigned>(ceil_div64(P, ppb)), B);
-  grad_prepare_kernel<<<grid, 256, 0, s>>>(g, P, C, ppb, scale, g16, acc_dst, sums);
+  grad_prepare_kernel<<<grid, 256, 0, s>>>(g, P, C, ppb, scale, g16, acc_dst, sums, acc_first ? 1 : 0);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -586,11 +592,11 @@ int launch_gn_bwd_reduce(const op_t* g_a, int g_ld, int g_coff, const void* x, i
 
 int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
                         const float2* tab, const float2* stats, const float* gamma, int act, int B, int64_t P, const double* S,
-                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s) {
+                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s, bool acc_first) {
   GnBwdArgs a{};
   a.g_a = g_a; a.g_ld = g_ld; a.g_coff = g_coff; a.x = x; a.x16 = x16; a.C = C; a.C_tot = C_tot; a.c_off = c_off;
   a.tab = tab; a.stats = stats; a.gamma = gamma; a.act = act; a.P = P; a.S = const_cast<double*>(S);
-  a.acc_dst = acc_dst; a.out16 = out16; a.out_sums = out_sums;
+  a.acc_dst = acc_dst; a.out16 = out16; a.out_sums = out_sums; a.acc_first = acc_first ? 1 : 0;
   const int G = std::min(C_tot / 4, 32);
   a.inv_count = 1.0 / (static_cast<double>(C_tot / G) * static_cast<double>(P));
   if (out_sums) FDBM_CUDA(cudaMemsetAsync(out_sums, 0, sizeof(double) * B * C, s));
