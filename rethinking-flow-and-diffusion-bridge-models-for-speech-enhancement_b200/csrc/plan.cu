@@ -295,17 +295,24 @@ struct Builder {
     double* S = Sbuf;
     fdbm_plan* plp = P;
     const Act a1 = x1; const Act a2 = x2 ? *x2 : Act();
+    const int cb = gn_chunk(Ct, px);
     bop([=](cudaStream_t s) {
       FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Ct, s));
-      if (int rc = launch_gn_bwd_reduce(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, act, B, px, S, s)) return rc;
-      if (C2) if (int rc = launch_gn_bwd_reduce(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, act, B, px, S, s)) return rc;
-      if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, gamma, act, B, px, S, a1.grad, nullptr, nullptr, s,
-                                       plp->grad_first(a1.grad))) return rc;
-      if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, gamma, act, B, px, S, a2.grad, nullptr, nullptr, s,
-                                               plp->grad_first(a2.grad))) return rc;
+      const bool f1 = plp->grad_first(a1.grad), f2 = C2 ? plp->grad_first(a2.grad) : false;
+      for (int b0 = 0; b0 < B; b0 += cb) {
+        const int nb = std::min(cb, B - b0);
+        if (int rc = launch_gn_bwd_reduce(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, act, nb, px, S, s, b0)) return rc;
+        if (C2) if (int rc = launch_gn_bwd_reduce(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, act, nb, px, S, s, b0)) return rc;
+        if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, gamma, act, nb, px, S, a1.grad, nullptr, nullptr, s, f1, b0)) return rc;
+        if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, gamma, act, nb, px, S, a2.grad, nullptr, nullptr, s, f2, b0)) return rc;
+      }
       return launch_gn_param_grad(S, B, Ct, plp->cur_inv, plp->grads + gw_off, plp->grads + gb_off, s);
     });
   }
+  // utterances per reduce/apply chunk.  Measured: chunks small enough for the apply pass to re-read x and g_a from L2 (one
+  // utterance at level 0) make the level-0 GroupNorm backward 2x SLOWER (1.90 vs 0.93 ms: 64 short launches with their tails
+  // instead of 4), so the whole batch is one chunk; the chunked launch path stays for plans with very large batches.
+  int gn_chunk(int Ct, int64_t px) const { (void)Ct; (void)px; return P->B; }
   float2* norm_stats(const double* q1, int C1, const double* q2, int C2, int T, int F) {
     if (!train()) return nullptr;
     const int B = P->B;
@@ -563,10 +570,14 @@ struct Builder {
       bop([=](cudaStream_t s) { return launch_groupnorm_act(h1, 1, h1_sums, Cout, nullptr, nullptr, 0, g1w, g1b, B, To, Fo, 1, 0, t2, nullptr, s); });
       { WgradCall w; w.dy = t1; w.dy_ld = Cout; w.Cout = Cout; w.x = t2; w.x_ld = Cout; w.Cin = Cout; w.ksize = 3; w.T = To; w.F = Fo; wgrad_op(w, o_c1w); }
       dgrad_op(t1, Cout, 9, pack_d(o_c1w, Cout, Cout, 3), Cout, To, Fo, t3, nullptr);
+      const int cb1 = gn_chunk(Cout, pxo);
       bop([=](cudaStream_t s) {     // GroupNorm_1 backward: g_h1 (16-bit) + its per-(b,c) sums (Conv_0 bias and FiLM gradients)
         FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Cout, s));
-        if (int rc = launch_gn_bwd_reduce(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, 1, B, pxo, S, s)) return rc;
-        if (int rc = launch_gn_bwd_apply(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, g1w, 1, B, pxo, S, nullptr, t4, sA, s)) return rc;
+        for (int b0 = 0; b0 < B; b0 += cb1) {            // chunks that fit the L2, see gn_bwd()
+          const int nb = std::min(cb1, B - b0);
+          if (int rc = launch_gn_bwd_reduce(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, 1, nb, pxo, S, s, b0)) return rc;
+          if (int rc = launch_gn_bwd_apply(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, g1w, 1, nb, pxo, S, nullptr, t4, sA, s, false, b0)) return rc;
+        }
         if (int rc = launch_gn_param_grad(S, B, Cout, plp->cur_inv, plp->grads + o_g1w, plp->grads + o_g1b, s)) return rc;
         return launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c0b, dense_row >= 0 ? dd + dense_row : nullptr, dense_stride, s);
       });
