@@ -104,40 +104,66 @@ sweep_post_kernel(const __half* __restrict__ yf, const __half* __restrict__ yb, 
 }
 
 // input conv 3x3 (Cin = 4: x.re, x.im, y.re, y.im; or 2) over the [T, F] plane of complex [B,1,F,T] inputs (tfgridnet.py:152,201-214)
-// + the sums for GroupNorm(1, C) (a LayerNorm over the whole (C, T, F) of an utterance)
+// + the sums for GroupNorm(1, C) (a LayerNorm over the whole (C, T, F) of an utterance).
+// A block owns 32 frames x 8 bins of one utterance: the input patch (frames contiguous in memory) is staged in shared memory,
+// a thread computes the 32 channels of one position, and the outputs leave through shared memory so that a warp store is one
+// position's 128 contiguous bytes.  (First version: one warp per position, 784 us at B = 16.)
+constexpr int IC_TT = 32, IC_TQ = 8;
 __global__ void __launch_bounds__(256)
 tfg_input_conv_kernel(const float2* __restrict__ x, const float2* __restrict__ y, const float* __restrict__ w, const float* __restrict__ bias,
                       int B, int T, int Q, int Cin, float* __restrict__ out, double* __restrict__ sums) {
-  __shared__ float sw[TC * 4 * 9];
+  __shared__ __align__(16) float sw[4 * 9 * TC];                 // [ci * 9 + tap][c]
+  __shared__ float2 sx[2][IC_TQ + 2][IC_TT + 2];                  // [x | y][bin][frame]
+  __shared__ float so[256][TC + 1];
   __shared__ double red[2][8];
-  for (int i = threadIdx.x; i < TC * Cin * 9; i += 256) sw[i] = w[i];
+  // conv weight [C, Cin, kh = time, kw = freq] on input [B, Cin, T, F]
+  for (int i = threadIdx.x; i < TC * Cin * 9; i += 256) { const int c = i / (Cin * 9), r = i % (Cin * 9); sw[r * TC + c] = w[i]; }
+  const int b = blockIdx.z, t0 = blockIdx.y * IC_TT, q0 = blockIdx.x * IC_TQ;
+  const int n_src = Cin == 4 ? 2 : 1;
+  for (int i = threadIdx.x; i < n_src * (IC_TQ + 2) * (IC_TT + 2); i += 256) {
+    const int tl = i % (IC_TT + 2), ql = (i / (IC_TT + 2)) % (IC_TQ + 2), sidx = i / ((IC_TT + 2) * (IC_TQ + 2));
+    const int t = t0 + tl - 1, q = q0 + ql - 1;
+    float2 v = make_float2(0.f, 0.f);
+    if (t >= 0 && t < T && q >= 0 && q < Q) v = __ldg((sidx ? y : x) + (static_cast<int64_t>(b) * Q + q) * T + t);
+    sx[sidx][ql][tl] = v;
+  }
   __syncthreads();
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int b = blockIdx.y;
-  const int64_t n_pos = static_cast<int64_t>(T) * Q;
-  double s1 = 0.0, s2 = 0.0;
-  for (int64_t p = blockIdx.x * 8ll + wrp; p < n_pos; p += 8ll * gridDim.x) {
-    const int q = static_cast<int>(p % Q), t = static_cast<int>(p / Q);
-    float acc = __ldg(bias + lane);
+  const int ql = threadIdx.x & 7, tl = threadIdx.x >> 3;          // position of this thread: bins fastest (the output's order)
+  float acc[TC];
 #pragma unroll
-    for (int dt = 0; dt < 3; ++dt) {
-      const int tt = t + dt - 1;
-      if (tt < 0 || tt >= T) continue;
+  for (int c = 0; c < TC; ++c) acc[c] = __ldg(bias + c);
 #pragma unroll
-      for (int dq = 0; dq < 3; ++dq) {
-        const int qq = q + dq - 1;
-        if (qq < 0 || qq >= Q) continue;
-        const int64_t si = (static_cast<int64_t>(b) * Q + qq) * T + tt;           // [B,1,F,T]
-        const float2 xv = __ldg(x + si);
-        // conv weight [C, Cin, kh = time, kw = freq] on input [B, Cin, T, F]
-        const float* wp = sw + lane * Cin * 9 + dt * 3 + dq;
-        acc = fmaf(xv.x, wp[0], acc); acc = fmaf(xv.y, wp[9], acc);
-        if (Cin == 4) { const float2 yv = __ldg(y + si); acc = fmaf(yv.x, wp[18], acc); acc = fmaf(yv.y, wp[27], acc); }
+  for (int dt = 0; dt < 3; ++dt)
+#pragma unroll
+    for (int dq = 0; dq < 3; ++dq) {
+      float in[4];
+      const float2 xv = sx[0][ql + dq][tl + dt];
+      in[0] = xv.x; in[1] = xv.y;
+      if (Cin == 4) { const float2 yv = sx[1][ql + dq][tl + dt]; in[2] = yv.x; in[3] = yv.y; }
+#pragma unroll
+      for (int ci = 0; ci < 4; ++ci) {
+        if (ci >= Cin) break;
+        const float4* wr = reinterpret_cast<const float4*>(sw + (ci * 9 + dt * 3 + dq) * TC);
+#pragma unroll
+        for (int c4 = 0; c4 < 8; ++c4) {
+          const float4 wv = wr[c4];
+          acc[4 * c4] = fmaf(in[ci], wv.x, acc[4 * c4]); acc[4 * c4 + 1] = fmaf(in[ci], wv.y, acc[4 * c4 + 1]);
+          acc[4 * c4 + 2] = fmaf(in[ci], wv.z, acc[4 * c4 + 2]); acc[4 * c4 + 3] = fmaf(in[ci], wv.w, acc[4 * c4 + 3]);
+        }
       }
     }
-    out[((static_cast<int64_t>(b) * T + t) * Q + q) * TC + lane] = acc;
-    s1 += acc; s2 += static_cast<double>(acc) * acc;
+  const bool ok = t0 + tl < T && q0 + ql < Q;
+  float f1 = 0.f, f2 = 0.f;
+#pragma unroll
+  for (int c = 0; c < TC; ++c) { so[threadIdx.x][c] = acc[c]; if (ok) { f1 += acc[c]; f2 = fmaf(acc[c], acc[c], f2); } }
+  __syncthreads();
+  // warp w stores positions 32 w .. 32 w + 31, one position (128 contiguous bytes) per instruction
+  for (int r = 0; r < 32; ++r) {
+    const int pos = wrp * 32 + r, pq = q0 + (pos & 7), pt = t0 + (pos >> 3);
+    if (pt < T && pq < Q) out[((static_cast<int64_t>(b) * T + pt) * Q + pq) * TC + lane] = so[pos][lane];
   }
+  double s1 = f1, s2 = f2;
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) { s1 += __shfl_xor_sync(0xffffffffu, s1, o); s2 += __shfl_xor_sync(0xffffffffu, s2, o); }
   if (lane == 0) { red[0][wrp] = s1; red[1][wrp] = s2; }
@@ -148,7 +174,6 @@ tfg_input_conv_kernel(const float2* __restrict__ x, const float2* __restrict__ y
     atomicAdd(sums + 2 * b, a); atomicAdd(sums + 2 * b + 1, c);
   }
 }
-
 __global__ void __launch_bounds__(256)
 tfg_groupnorm1_kernel(float* __restrict__ h, const double* __restrict__ sums, const float* __restrict__ gamma, const float* __restrict__ beta,
                       int64_t per_utt, float eps) {
@@ -444,34 +469,43 @@ tfg_attn_proj_kernel(const float* __restrict__ o, const float* __restrict__ w, c
 }
 
 // output ConvTranspose2d(C -> 2, 3x3, padding 1) (tfgridnet.py:175, 221-226): out[o, t, f] = b[o] + sum h[c, t+1-dt, f+1-dq] W[c, o, dt, dq],
-// written as complex [B,1,F,T]
+// written as complex [B,1,F,T].  A block owns 32 frames x 8 bins: the h patch (34 x 10 positions x 32 channels) is staged in
+// shared memory (frame rows padded by 4 words: the per-lane 16-byte reads of a warp, whose lanes run along frames, then hit
+// distinct banks), a thread computes one output position, and a warp stores 32 consecutive frames = 256 contiguous bytes.
+constexpr int DC_TT = 32, DC_TQ = 8, DC_ROW = (DC_TQ + 2) * TC + 4;
 __global__ void __launch_bounds__(256)
 tfg_deconv_out_kernel(const float* __restrict__ h, const float* __restrict__ w, const float* __restrict__ bias, int B, int T, int Q,
                       float2* __restrict__ out) {
-  __shared__ float sw[TC * 2 * 9];
-  for (int i = threadIdx.x; i < TC * 18; i += 256) sw[i] = w[i];
+  __shared__ __align__(16) float sh[(DC_TT + 2) * DC_ROW];
+  __shared__ __align__(16) float sw[9 * 2 * TC];                  // [tap][o][c]
+  for (int i = threadIdx.x; i < TC * 18; i += 256) { const int c = i / 18, o = (i / 9) % 2, tap = i % 9; sw[(tap * 2 + o) * TC + c] = w[i]; }
+  const int b = blockIdx.z, t0 = blockIdx.y * DC_TT, q0 = blockIdx.x * DC_TQ;
+  for (int i = threadIdx.x; i < (DC_TT + 2) * (DC_TQ + 2) * 8; i += 256) {
+    const int c4 = i & 7, ql = (i >> 3) % (DC_TQ + 2), tl = (i >> 3) / (DC_TQ + 2);
+    const int t = t0 + tl - 1, q = q0 + ql - 1;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (t >= 0 && t < T && q >= 0 && q < Q) v = __ldg(reinterpret_cast<const float4*>(h + ((static_cast<int64_t>(b) * T + t) * Q + q) * TC) + c4);
+    *reinterpret_cast<float4*>(sh + tl * DC_ROW + ql * TC + c4 * 4) = v;
+  }
   __syncthreads();
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int64_t n_pos = static_cast<int64_t>(B) * T * Q;
-  for (int64_t p = blockIdx.x * 8ll + wrp; p < n_pos; p += 8ll * gridDim.x) {
-    const int q = static_cast<int>(p % Q), t = static_cast<int>((p / Q) % T), b = static_cast<int>(p / (static_cast<int64_t>(Q) * T));
-    float re = 0.f, im = 0.f;
+  const int tl = threadIdx.x & 31, ql = threadIdx.x >> 5;         // lanes along frames: the output's contiguous axis
+  float re = __ldg(bias), im = __ldg(bias + 1);
 #pragma unroll
-    for (int dt = 0; dt < 3; ++dt) {
-      const int tt = t + 1 - dt;
-      if (tt < 0 || tt >= T) continue;
+  for (int dt = 0; dt < 3; ++dt)
 #pragma unroll
-      for (int dq = 0; dq < 3; ++dq) {
-        const int qq = q + 1 - dq;
-        if (qq < 0 || qq >= Q) continue;
-        const float hv = h[((static_cast<int64_t>(b) * T + tt) * Q + qq) * TC + lane];
-        re = fmaf(hv, sw[(lane * 2 + 0) * 9 + dt * 3 + dq], re);
-        im = fmaf(hv, sw[(lane * 2 + 1) * 9 + dt * 3 + dq], im);
+    for (int dq = 0; dq < 3; ++dq) {
+      // source position (t + 1 - dt, q + 1 - dq) = patch index (tl + 2 - dt, ql + 2 - dq)
+      const float4* hp = reinterpret_cast<const float4*>(sh + (tl + 2 - dt) * DC_ROW + (ql + 2 - dq) * TC);
+      const float4* wr = reinterpret_cast<const float4*>(sw + (dt * 3 + dq) * 2 * TC);
+#pragma unroll
+      for (int c4 = 0; c4 < 8; ++c4) {
+        const float4 hv = hp[c4], w0 = wr[c4], w1 = wr[8 + c4];
+        re = fmaf(hv.x, w0.x, re); re = fmaf(hv.y, w0.y, re); re = fmaf(hv.z, w0.z, re); re = fmaf(hv.w, w0.w, re);
+        im = fmaf(hv.x, w1.x, im); im = fmaf(hv.y, w1.y, im); im = fmaf(hv.z, w1.z, im); im = fmaf(hv.w, w1.w, im);
       }
     }
-    re = warp_sum(re); im = warp_sum(im);
-    if (lane == 0) out[(static_cast<int64_t>(b) * Q + q) * T + t] = make_float2(re + __ldg(bias), im + __ldg(bias + 1));
-  }
+  const int t = t0 + tl, q = q0 + ql;
+  if (t < T && q < Q) out[(static_cast<int64_t>(b) * Q + q) * T + t] = make_float2(re, im);
 }
 
 int grid8(int64_t n_pos) { return static_cast<int>(std::min<int64_t>(ceil_div64(n_pos, 8), static_cast<int64_t>(num_sms()) * 16)); }
@@ -511,8 +545,7 @@ extern "C" int fdbm_tfg_input(const float* x, const float* y, const float* w, co
   FDBM_REQUIRE(x && w && bias && gn_w && gn_b && sums && out && (Cin == 2 || (Cin == 4 && y)), "fdbm_tfg_input: bad arguments");
   cudaStream_t s = as_stream(stream);
   FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * 2 * batch, s));
-  const int bx = std::max(1, std::min<int>(static_cast<int>(ceil_div64(static_cast<int64_t>(T) * Q, 8 * 8)), num_sms() * 8 / batch + 1));
-  tfg_input_conv_kernel<<<dim3(bx, batch), 256, 0, s>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y), w, bias, batch, T, Q,
+  tfg_input_conv_kernel<<<dim3(ceil_div(Q, IC_TQ), ceil_div(T, IC_TT), batch), 256, 0, s>>>(reinterpret_cast<const float2*>(x), reinterpret_cast<const float2*>(y), w, bias, batch, T, Q,
                                                         Cin, out, sums);
   FDBM_LAUNCH_CHECK();
   const int64_t per = static_cast<int64_t>(T) * Q * TC;
@@ -580,7 +613,7 @@ extern "C" int fdbm_tfg_attention(const float* z, const float* const* params /* 
 extern "C" int fdbm_tfg_output(const float* h, const float* w, const float* bias, int batch, int T, int Q, float* out, void* stream) {
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(h && w && bias && out && batch > 0, "fdbm_tfg_output: bad arguments");
-  tfg_deconv_out_kernel<<<grid8(static_cast<int64_t>(batch) * T * Q), 256, 0, as_stream(stream)>>>(h, w, bias, batch, T, Q, reinterpret_cast<float2*>(out));
+  tfg_deconv_out_kernel<<<dim3(ceil_div(Q, DC_TQ), ceil_div(T, DC_TT), batch), 256, 0, as_stream(stream)>>>(h, w, bias, batch, T, Q, reinterpret_cast<float2*>(out));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
