@@ -219,7 +219,8 @@ tfg_temb_kernel(const float* __restrict__ t, int t_stride, const float* __restri
 
 // attention front: 1x1 convs Q (8), K (8), V (32) + per-head PReLU + normalisation over the head's E channels + affine
 // (tfgridnet.py:383-385, 458-484).  Outputs are the fp16 operands of the two batched GEMMs:
-//   Qh, Kh [B*4][T][E*F] with feature e * F + f  (tfgridnet.py:392-396);  Vt [B*4][8*F][T] (feature c8 * F + f, frames contiguous)
+//   Qh, Kh [B*4][T][E*F] with feature e * F + f  (tfgridnet.py:392-396);  Vt [B*4][8*F][T] (feature f * 8 + c8, frames contiguous:
+//   the order of V's features only has to match the un-flattening of P V, and this one makes those stores contiguous)
 // A block owns 16 frames x 32 bins of one utterance; a thread owns one bin of two frames, so the whole per-position chain
 // (48 dot products, the head statistics) is register-local, Q / K stores are contiguous along bins across the warp, and V goes
 // through a shared-memory transpose so that Vt is written in 32-byte runs along frames.  (The first version, one warp per
@@ -321,7 +322,7 @@ tfg_qkv_kernel(const float* __restrict__ z, const float* __restrict__ wq, const 
   for (int row = threadIdx.x; row < 32 * QKV_TQ; row += 256) {
     const int c = row >> 5, qq = blockIdx.x * QKV_TQ + (row & 31);
     if (qq >= Q) continue;
-    __half* dst = Vt + ((static_cast<int64_t>(b) * 4 + (c >> 3)) * (8 * Q) + static_cast<int64_t>(c & 7) * Q + qq) * ldt + t0;
+    __half* dst = Vt + ((static_cast<int64_t>(b) * 4 + (c >> 3)) * (8 * Q) + static_cast<int64_t>(qq) * 8 + (c & 7)) * ldt + t0;
     const uint32_t* src = reinterpret_cast<const uint32_t*>(sv + row * QKV_PITCH);
     if (n_t == QKV_TT) {
       reinterpret_cast<uint4*>(dst)[0] = make_uint4(src[0], src[1], src[2], src[3]);
@@ -335,13 +336,14 @@ tfg_qkv_kernel(const float* __restrict__ z, const float* __restrict__ wq, const 
 
 // batched C[m, n] = scale * sum_k A[m, k] B[n, k]   (both operands K-contiguous fp16, fp32 accumulate, mma.sync m16n8k16)
 // CTA tile 64 x 64, 4 warps of 32 x 32.  out_mode 0: fp32 C[batch][m][n];  1: fp16 C[batch][m][n];
-// 2: attention output scattered into the [B, T, Q, C] activation layout: batch = b * 4 + head, m = t, n = c8 * Q + f.
+// 2: attention output into the [B, T, Q, C] activation layout: batch = b * 4 + head, m = t, n = f * 8 + c8 (a thread's two
+// adjacent columns are one 8-byte store, a quad's eight columns one 32-byte run).
 struct GemmArgs {
   const __half* A; const __half* Bm; void* C;
   int M, N, K; int64_t sA, sB, sC; int lda, ldb, ldc; float scale; int out_mode; int Q;
 };
 __global__ void __launch_bounds__(128) gemm_tn_kernel(const GemmArgs g) {
-  constexpr int BM = 64, BN = 64, BK = 32, PITCH = BK + 8;
+  constexpr int BM = 64, BN = 64, BK = 64, PITCH = BK + 8, NLD = BM * (BK / 8) / 128;
   __shared__ __align__(16) __half sA[BM][PITCH];
   __shared__ __align__(16) __half sB[BN][PITCH];
   const int bz = blockIdx.z, m0 = blockIdx.y * BM, n0 = blockIdx.x * BN;
@@ -353,16 +355,29 @@ __global__ void __launch_bounds__(128) gemm_tn_kernel(const GemmArgs g) {
   for (int i = 0; i < 2; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) { acc[i][j][0] = acc[i][j][1] = acc[i][j][2] = acc[i][j][3] = 0.f; }
-  for (int k0 = 0; k0 < g.K; k0 += BK) {
-    // 64 rows x 32 halves per operand as 16-byte pieces (K, lda, ldb are multiples of 8 halves; pad columns hold zeros)
-    for (int e = threadIdx.x; e < BM * (BK / 8); e += 128) {
-      const int r = e >> 2, kk = (e & 3) * 8;
-      const int m = m0 + r, n = n0 + r, k = k0 + kk;
+  // 64 rows x 64 halves per operand as 16-byte pieces (K, lda, ldb are multiples of 8 halves; pad columns hold zeros); the next
+  // K-slice is fetched into registers while the current one is multiplied
+  uint4 ra[NLD], rb[NLD];
+  auto fetch = [&](int k0) {
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int e = threadIdx.x + u * 128, r = e >> 3, k = k0 + (e & 7) * 8;
+      const int m = m0 + r, n = n0 + r;
       const uint4 zero = make_uint4(0u, 0u, 0u, 0u);
-      *reinterpret_cast<uint4*>(&sA[r][kk]) = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const uint4*>(A + static_cast<int64_t>(m) * g.lda + k)) : zero;
-      *reinterpret_cast<uint4*>(&sB[r][kk]) = (n < g.N && k < g.K) ? __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(n) * g.ldb + k)) : zero;
+      ra[u] = (m < g.M && k < g.K) ? __ldg(reinterpret_cast<const uint4*>(A + static_cast<int64_t>(m) * g.lda + k)) : zero;
+      rb[u] = (n < g.N && k < g.K) ? __ldg(reinterpret_cast<const uint4*>(Bm + static_cast<int64_t>(n) * g.ldb + k)) : zero;
+    }
+  };
+  fetch(0);
+  for (int k0 = 0; k0 < g.K; k0 += BK) {
+#pragma unroll
+    for (int u = 0; u < NLD; ++u) {
+      const int e = threadIdx.x + u * 128, r = e >> 3, kk = (e & 7) * 8;
+      *reinterpret_cast<uint4*>(&sA[r][kk]) = ra[u];
+      *reinterpret_cast<uint4*>(&sB[r][kk]) = rb[u];
     }
     __syncthreads();
+    if (k0 + BK < g.K) fetch(k0 + BK);
 #pragma unroll
     for (int ks = 0; ks < BK; ks += 16) {
       uint32_t af[2][4], bf[4][2];
@@ -392,15 +407,15 @@ __global__ void __launch_bounds__(128) gemm_tn_kernel(const GemmArgs g) {
 #pragma unroll
     for (int j = 0; j < 4; ++j)
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const int m = m0 + wm + i * 16 + gq + (e >> 1) * 8, n = n0 + wn + j * 8 + 2 * tq + (e & 1);
+      for (int e2 = 0; e2 < 2; ++e2) {
+        const int m = m0 + wm + i * 16 + gq + e2 * 8, n = n0 + wn + j * 8 + 2 * tq;      // columns n, n + 1 (N and ldc are even)
         if (m >= g.M || n >= g.N) continue;
-        const float v = acc[i][j][e] * g.scale;
-        if (g.out_mode == 0) reinterpret_cast<float*>(g.C)[bz * g.sC + static_cast<int64_t>(m) * g.ldc + n] = v;
-        else if (g.out_mode == 1) reinterpret_cast<__half*>(g.C)[bz * g.sC + static_cast<int64_t>(m) * g.ldc + n] = __float2half_rn(v);
+        const float v0 = acc[i][j][2 * e2] * g.scale, v1 = acc[i][j][2 * e2 + 1] * g.scale;
+        if (g.out_mode == 0) *reinterpret_cast<float2*>(reinterpret_cast<float*>(g.C) + bz * g.sC + static_cast<int64_t>(m) * g.ldc + n) = make_float2(v0, v1);
+        else if (g.out_mode == 1) *reinterpret_cast<__half2*>(reinterpret_cast<__half*>(g.C) + bz * g.sC + static_cast<int64_t>(m) * g.ldc + n) = __floats2half2_rn(v0, v1);
         else {
-          const int b = bz >> 2, hd = bz & 3, c8 = n / g.Q, f = n - c8 * g.Q;
-          reinterpret_cast<float*>(g.C)[((static_cast<int64_t>(b) * g.M + m) * g.Q + f) * TC + hd * 8 + c8] = v;
+          const int b = bz >> 2, hd = bz & 3, f = n >> 3, c8 = n & 7;
+          *reinterpret_cast<float2*>(reinterpret_cast<float*>(g.C) + ((static_cast<int64_t>(b) * g.M + m) * g.Q + f) * TC + hd * 8 + c8) = make_float2(v0, v1);
         }
       }
 }
