@@ -260,6 +260,13 @@ int64_t fdbm_hybrid_loss_workspace_bytes(int batch, int n_frames, int n_fft, int
 int fdbm_hybrid_loss(const float* x_hat, const float* x, int batch, int n_frames, const float* window, int n_fft, int hop,
                      int transform_type, float spec_factor, float abs_exponent, float loss_scale, void* workspace,
                      float* loss, float* g_out, void* stream);
+/* "data_prediction" (fdbm/model.py:163-185, the reference's argparse default, pesq_weight 0):
+ *   L = mean_b 0.5 sum_{f,t} |x_hat - x|^2 / (F T)  +  l1_weight * mean_b 0.5 sum_n |istft X^ - istft X| / target_len,
+ * target_len = (T - 1) * hop; the first term on the COMPRESSED spectrograms, the second on the waveforms of the de-compressed
+ * ones.  Same conventions, constraints and workspace as fdbm_hybrid_loss. */
+int fdbm_data_prediction_loss(const float* x_hat, const float* x, int batch, int n_frames, const float* window, int n_fft, int hop,
+                              int transform_type, float spec_factor, float abs_exponent, float l1_weight, float loss_scale,
+                              void* workspace, float* loss, float* g_out, void* stream);
 
 /* Measurement aid for bench.py: run one forward launch by launch with a CUDA event pair around every
  * kernel.  ms[i] = device time, kinds[i] = FDBM_OP_*, flops[i] = algorithmic FLOPs (2*MAC, convolutions

@@ -789,6 +789,22 @@ def hybrid_loss(x_hat: Tensor, x: Tensor, cfg: SpecConfig) -> Tensor:
     return 70 * losses_mag + 30 * losses_ri - sisnr
 
 
+def data_prediction_loss(x_hat: Tensor, x: Tensor, cfg: SpecConfig, l1_weight: float = 0.001) -> Tensor:
+    """BridgeModel._loss, loss_type "data_prediction" (the argparse default) with pesq_weight = 0 (model.py:163-185):
+    mean_b 0.5 sum |x_hat - x|^2 / (F T) on the compressed spectrograms + l1_weight * mean_b 0.5 sum |x_hat_td - x_td| / target_len
+    on the waveforms, target_len = (num_frames - 1) * hop with num_frames = T.  Differentiable (torch autograd).
+    Pinned against the reference's own `_loss` by oracle/make_golden.py (tests/golden/data_prediction_loss.npz)."""
+    B, C, Fq, T = x.shape
+    losses_tf = (1 / (Fq * T)) * torch.square(torch.abs(x_hat - x))
+    losses_tf = torch.mean(0.5 * torch.sum(losses_tf.reshape(B, -1), dim=-1))
+    target_len = (T - 1) * cfg.hop_length
+    x_hat_td = istft_torch(spec_back(x_hat, cfg).squeeze(1), cfg, target_len)
+    x_td = istft_torch(spec_back(x, cfg).squeeze(1), cfg, target_len)
+    losses_l1 = (1 / target_len) * torch.abs(x_hat_td - x_td)
+    losses_l1 = torch.mean(0.5 * torch.sum(losses_l1.reshape(B, -1), dim=-1))
+    return losses_tf + l1_weight * losses_l1
+
+
 def istft_torch(spec: Tensor, cfg: SpecConfig, length: Optional[int] = None) -> Tensor:
     """data_module.py:227-229 through torch.istft itself (autograd-capable, any float width); `istft` above is the
     explicit restatement, the two agree to rounding (tests/test_oracle_golden.py)."""

@@ -327,11 +327,48 @@ def main():
     print(f"hybrid loss reference {float(loss_ref):.6f} oracle {float(loss_or):.6f}; gradient oracle vs ref {rel(g_or, g_ref):.3e}")
     np.savez_compressed(os.path.join(OUT, "hybrid_loss.npz"), x=c2n(x), x_hat=c2n(x_hat), loss=np.float64(loss_ref.item()),
                         grad=c2n(g_ref))
+    loss_goldens_data_prediction(ref_model, dm, x, x_hat, scfg)
     tfgridnet_goldens(BackboneRegistry)
     variant_goldens(BackboneRegistry)
     print("golden fixtures written to", OUT)
     for f in sorted(os.listdir(OUT)):
         print("  ", f, os.path.getsize(os.path.join(OUT, f)) // 1024, "KiB")
+
+
+def loss_goldens_data_prediction(ref_model=None, dm=None, x=None, x_hat=None, scfg=None):
+    """BridgeModel._loss 'data_prediction' (model.py:163-185, the argparse default; l1_weight 0.001, pesq_weight 0) and its gradient.
+    Stand-alone: `python oracle/make_golden.py loss`."""
+    import types as _types
+    import fdbm_oracle as O
+    if ref_model is None:
+        import_reference()
+        import fdbm.model as ref_model
+        from fdbm.data_module import SpecsDataModule
+        dm = SpecsDataModule(base_dir="/unused", n_fft=512, hop_length=256, num_frames=64, window="sqrthann", gpu=False)
+        scfg = O.SpecConfig()
+        gl = torch.Generator().manual_seed(21)
+
+        def spec(B=2, T=64):
+            mag = torch.rand(B, 1, 257, T, generator=gl) ** 3 * 0.6
+            ph = 2 * 3.14159265 * torch.rand(B, 1, 257, T, generator=gl)
+            return torch.polar(mag, ph)
+        x = spec()
+        x_hat = x + 0.3 * spec()
+        x_hat[:, :, 256] = 0
+    T = x.shape[-1]
+    fake_dm = _types.SimpleNamespace(num_frames=T, hop_length=dm.hop_length)
+    fake_self = _types.SimpleNamespace(loss_type="data_prediction", pesq_weight=0.0, l1_weight=0.001, data_module=fake_dm,
+                                       to_audio=lambda s, length=None: dm.istft(dm.spec_back(s), length))
+    leaf = x_hat.clone().requires_grad_(True)
+    loss_ref = ref_model.BridgeModel._loss(fake_self, leaf, None, None, None, None, x)
+    (g_ref,) = torch.autograd.grad(loss_ref, leaf)
+    leaf2 = x_hat.clone().requires_grad_(True)
+    loss_or = O.data_prediction_loss(leaf2, x, scfg, 0.001)
+    (g_or,) = torch.autograd.grad(loss_or, leaf2)
+    g_ref = torch.nan_to_num(g_ref); g_or = torch.nan_to_num(g_or)
+    print(f"data_prediction loss reference {float(loss_ref):.6f} oracle {float(loss_or):.6f}; gradient oracle vs ref {rel(g_or, g_ref):.3e}")
+    np.savez_compressed(os.path.join(OUT, "data_prediction_loss.npz"), x=c2n(x), x_hat=c2n(x_hat), loss=np.float64(loss_ref.item()),
+                        grad=c2n(g_ref))
 
 
 def tfgridnet_goldens(BackboneRegistry=None):
@@ -392,6 +429,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tfgridnet":
         os.makedirs(OUT, exist_ok=True)
         tfgridnet_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "loss":
+        loss_goldens_data_prediction()
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":
         variant_goldens()
     else:

@@ -67,7 +67,15 @@ class TrainStep:
     def __init__(self, dnn, bridge, data_module, batch: int, n_frames: int = 256, lr: float = 1e-4, ema_decay: float = 0.999,
                  clip_norm: float = 3.0, t_eps: float = 0.03, loss_scale: float = 4096.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  ema_warmup: bool = True, dynamic_loss_scale: bool = True, scale_check_interval: int = 50,
-                 scale_growth_interval: int = 2000):
+                 scale_growth_interval: int = 2000, loss_type: str = "data_prediction_hybrid", l1_weight: float = 0.001,
+                 pesq_weight: float = 0.0):
+        # BridgeModel.__init__(loss_type, l1_weight, pesq_weight) (model.py:41): the two heads that have kernels
+        if loss_type not in ("data_prediction_hybrid", "data_prediction"):
+            raise NotImplementedError(f"loss_type {loss_type!r}: fdbm_b200 implements 'data_prediction_hybrid' (config.yaml) and "
+                                      "'data_prediction' (the argparse default); the mel / mel+phase heads are not built")
+        if pesq_weight != 0.0:
+            raise NotImplementedError("pesq_weight > 0 (torch_pesq loss term) is not implemented")
+        self.loss_type, self.l1_weight = loss_type, float(l1_weight)
         self.dnn, self.bridge, self.dm = dnn, bridge, data_module
         self.batch, self.n_frames = batch, n_frames
         self.lr, self.ema_decay, self.clip_norm, self.t_eps, self.loss_scale = lr, ema_decay, clip_norm, t_eps, loss_scale
@@ -246,7 +254,7 @@ class TrainStep:
         return loss
 
     def loss_and_grad(self, D: torch.Tensor, x: torch.Tensor):
-        """fdbm/model.py:187-218 and its gradient w.r.t. D, already multiplied by the loss scale: one library call."""
+        """fdbm/model.py:163-218 (`_loss`, the configured head) and its gradient w.r.t. D, already multiplied by the loss scale: one library call."""
         from ._lib import FDBM_TRANSFORM
         B, _, Fb, T = D.shape
         dm = self.dm
@@ -256,6 +264,12 @@ class TrainStep:
         loss = torch.empty((), device=D.device)
         g = torch.empty_like(D)
         D, x = D.contiguous(), x.contiguous()
+        if self.loss_type == "data_prediction":
+            check(self.lib.fdbm_data_prediction_loss(ptr(torch.view_as_real(D)), ptr(torch.view_as_real(x)), B, T, ptr(dm._get_window(D)), dm.n_fft,
+                                                     dm.hop_length, FDBM_TRANSFORM[dm.transform_type], float(dm.spec_factor),
+                                                     float(dm.spec_abs_exponent), self.l1_weight, self.loss_scale, ptr(self._loss_ws), ptr(loss),
+                                                     ptr(torch.view_as_real(g)), current_stream()), "fdbm_data_prediction_loss")
+            return loss, g
         check(self.lib.fdbm_hybrid_loss(ptr(torch.view_as_real(D)), ptr(torch.view_as_real(x)), B, T, ptr(dm._get_window(D)), dm.n_fft,
                                         dm.hop_length, FDBM_TRANSFORM[dm.transform_type], float(dm.spec_factor), float(dm.spec_abs_exponent),
                                         self.loss_scale, ptr(self._loss_ws), ptr(loss), ptr(torch.view_as_real(g)), current_stream()),

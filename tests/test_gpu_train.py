@@ -159,13 +159,40 @@ def test_adam_ema_step_matches_torch(lib, device_count):
     assert state[0].item() == len(grads) and state[1].item() == (1.0 if device_count else 0.0)
 
 
-def _hybrid_loss_cuda(lib, xh, x, scale=512.0):
+def _loss_cuda(lib, kind, xh, x, scale=512.0, l1_weight=0.001):
+    """One of the CUDA loss heads on (x_hat, x): returns (loss, dL/dx_hat) with the loss scale divided out again."""
     from fdbm_b200 import SpecsDataModule
     B, T = x.shape[0], x.shape[3]
-    loss, got = _hybrid_loss_cuda(lib, xh, x)
-    print(f"hybrid loss ours {float(loss):.6f} ref {float(ref):.6f}; gradient rel L2 {rel_l2(torch.view_as_real(got), torch.view_as_real(gref.to(torch.complex64))):.3e}")
-    assert abs(float(loss) - float(ref)) < 1e-4 * abs(float(ref)) + 1e-5
-    assert rel_l2(torch.view_as_real(got), torch.view_as_real(gref.to(torch.complex64))) < 1e-3
+    dm32 = SpecsDataModule(n_fft=512, hop_length=256, window="sqrthann")
+    ws = torch.empty(lib.fdbm_hybrid_loss_workspace_bytes(B, T, 512, 256), dtype=torch.uint8, device="cuda")
+    loss = torch.empty((), device="cuda")
+    xd, xhd = x.cuda().contiguous(), xh.cuda().contiguous()
+    gout = torch.empty_like(xhd)
+    args = (torch.view_as_real(xhd).data_ptr(), torch.view_as_real(xd).data_ptr(), B, T, dm32._get_window(xd).data_ptr(), 512, 256, 0, 0.15, 0.5)
+    tail = (scale, ws.data_ptr(), loss.data_ptr(), torch.view_as_real(gout).data_ptr(), _stream())
+    if kind == "data_prediction_hybrid":
+        _check(lib, lib.fdbm_hybrid_loss(*args, *tail))
+    else:
+        _check(lib, lib.fdbm_data_prediction_loss(*args, l1_weight, *tail))
+    torch.cuda.synchronize()
+    return loss.cpu(), gout.cpu() / scale
+
+
+@pytest.mark.parametrize("kind,fixture", [("data_prediction_hybrid", "hybrid_loss.npz"), ("data_prediction", "data_prediction_loss.npz")])
+def test_loss_heads_match_reference_golden(lib, golden_dir, kind, fixture):
+    """fdbm_hybrid_loss / fdbm_data_prediction_loss (value and gradient w.r.t. the backbone output) against the reference's own
+    BridgeModel._loss under torch autograd (fdbm/model.py:163-218; fixtures written by oracle/make_golden.py)."""
+    from helpers import load_npz
+    g = load_npz(f"{golden_dir}/{fixture}")
+    x, xh, gref, ref = torch.from_numpy(g["x"]), torch.from_numpy(g["x_hat"]), torch.from_numpy(g["grad"]).clone(), float(g["loss"])
+    loss, got = _loss_cuda(lib, kind, xh, x)
+    # row 256 (Nyquist) of the backbone output is exactly zero and dropped by the output layer's backward: not compared
+    got[:, :, 256] = 0
+    gref[:, :, 256] = 0
+    err = rel_l2(torch.view_as_real(got), torch.view_as_real(gref.to(torch.complex64)))
+    print(f"{kind}: loss ours {float(loss):.6f} reference {ref:.6f}; gradient rel L2 {err:.3e}")
+    assert abs(float(loss) - ref) < 1e-4 * abs(ref) + 1e-6
+    assert err < 1e-3
 
 
 # ------------------------------------------------------------------------------------------------
@@ -234,6 +261,31 @@ def test_training_step_gradients_match_autograd():
     big = [w for w in worst if w[2] > 1e-3 * den ** 0.5]
     assert max(w[0] for w in big) < 0.1, "a parameter tensor with a significant gradient is off"
     ts.close()
+
+
+def test_training_step_with_the_default_loss_head():
+    """TrainStep(loss_type='data_prediction'), the reference's argparse default (model.py:32,41): the loss of a step against the
+    oracle's forward + restated loss on the same (x, y, t, z), a non-zero update, and the heads that have no kernel are refused."""
+    O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z = _train_setup()
+    B, T = x.shape[0], x.shape[3]
+    with torch.no_grad():
+        mean, std = bridge.probability_path(x, y, t)
+        D_ref = O.ncsnpp_forward(sd, cfg, mean + std[:, None, None, None] * z, y, t)
+        loss_ref = O.data_prediction_loss(D_ref, x, O.SpecConfig(), 0.001)
+    ts = TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_scale=1024.0, loss_type="data_prediction")
+    loss = ts.loss_and_backward(x.cuda(), y.cuda(), t.cuda(), z.cuda())
+    before = ts.flat_params.clone()
+    ts.optimizer_step()
+    torch.cuda.synchronize()
+    print(f"data_prediction step: loss ours {float(loss):.6f} oracle {float(loss_ref):.6f}")
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref)) + 1e-5
+    assert float((ts.flat_params - before).abs().max()) > 0 and bool(torch.isfinite(ts.flat_params).all())
+    ts.close()
+    for bad in ("data_prediction_mel", "data_prediction_melphase"):
+        with pytest.raises(NotImplementedError):
+            TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_type=bad)
+    with pytest.raises(NotImplementedError):
+        TrainStep(net, bridge, dm, batch=B, n_frames=T, pesq_weight=0.1)
 
 
 def test_training_step_updates_like_torch_adam():

@@ -114,3 +114,14 @@ def test_hybrid_loss_oracle_matches_reference_golden(golden_dir):
     (grad,) = torch.autograd.grad(loss, xh)
     assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
     assert rel_l2(torch.nan_to_num(grad), g["grad"]) < 1e-5
+
+
+def test_data_prediction_loss_oracle_matches_reference_golden(golden_dir):
+    """O.data_prediction_loss against BridgeModel._loss 'data_prediction' of the reference (value and autograd gradient,
+    tests/golden/data_prediction_loss.npz)."""
+    g = load_npz(f"{golden_dir}/data_prediction_loss.npz")
+    x, xh = torch.from_numpy(g["x"]), torch.from_numpy(g["x_hat"]).requires_grad_(True)
+    loss = O.data_prediction_loss(xh, x, O.SpecConfig(), 0.001)
+    (grad,) = torch.autograd.grad(loss, xh)
+    assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
+    assert rel_l2(torch.nan_to_num(grad), g["grad"]) < 1e-5

@@ -24,6 +24,9 @@ timeout 600 ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_d
   python tools/forward_profile.py 128 256 > $O/${P}_ncu_traffic.log 2>&1
 timeout 400 ncu --set full --clock-control none --import-source on -k regex:conv_igemm --launch-skip 232 --launch-count 6 -o $O/${P}_conv_full \
   python tools/forward_profile.py 128 256 > $O/${P}_ncu_conv_full.log 2>&1
-timeout 300 ncu --set full --clock-control none --import-source on -k regex:lstm_sweep --launch-skip 4 --launch-count 1 -o $O/${P}_lstm_full \
+timeout 300 ncu --set full --clock-control none --import-source on -k regex:lstm_sweep_tc --launch-skip 4 --launch-count 1 -o $O/${P}_lstm_full \
   python tools/tfg_bench.py 16 > $O/${P}_ncu_lstm_full.log 2>&1
+timeout 300 python tools/backward_profile.py 16 > $O/${P}_bwd_profile.txt 2>&1
+timeout 200 python tools/tfg_bench.py 4 16 32 > $O/${P}_tfg_forward.txt 2>&1
+timeout 300 ncu --metrics gpu__time_duration.sum --clock-control none --csv --log-file $O/${P}_tfg_launches.csv python tools/tfg_bench.py 16 > $O/${P}_ncu_tfg.log 2>&1
 tail -3 $O/${P}_pytest.log
