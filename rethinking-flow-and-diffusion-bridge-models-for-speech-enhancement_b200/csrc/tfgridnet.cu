@@ -249,17 +249,30 @@ tfg_qkv_kernel(const float* __restrict__ z, const float* __restrict__ wq, const 
   const int tl[2] = {wrp, wrp + 8};
   bool ok[2];
   float zv[2][32];
+  // a warp's 32 positions (one frame, 32 consecutive bins) are 4 KB contiguous: read them as fully used 16-byte pieces into a
+  // per-warp [32][33] tile (aliased onto the V transpose buffer, which is not written before the barrier below), then each lane
+  // takes its own row
+  float* stw = reinterpret_cast<float*>(sv) + wrp * (32 * 33);
+  static_assert(sizeof(sv) >= 8 * 32 * 33 * sizeof(float), "z staging aliases the V transpose buffer");
+  const int qw0 = blockIdx.x * QKV_TQ;
 #pragma unroll
   for (int r = 0; r < 2; ++r) {
     const int t = t0 + tl[r];
     ok[r] = t < T && q < Q;
-    const float4* src = reinterpret_cast<const float4*>(z + ((static_cast<int64_t>(b) * T + (ok[r] ? t : 0)) * Q + (ok[r] ? q : 0)) * TC);
+    const int n_q = t < T ? min(32, Q - qw0) : 0;             // valid bins of this warp's row
+    const float4* src = reinterpret_cast<const float4*>(z + ((static_cast<int64_t>(b) * T + (t < T ? t : 0)) * Q + qw0) * TC);
+    __syncwarp();
 #pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      const float4 v = ok[r] ? __ldg(src + k4) : make_float4(0.f, 0.f, 0.f, 0.f);
-      zv[r][4 * k4] = v.x; zv[r][4 * k4 + 1] = v.y; zv[r][4 * k4 + 2] = v.z; zv[r][4 * k4 + 3] = v.w;
+    for (int j = 0; j < 8; ++j) {
+      const int idx = j * 32 + lane, pos = idx >> 3, c4 = idx & 7;
+      const float4 v = pos < n_q ? __ldg(src + idx) : make_float4(0.f, 0.f, 0.f, 0.f);
+      stw[pos * 33 + 4 * c4] = v.x; stw[pos * 33 + 4 * c4 + 1] = v.y; stw[pos * 33 + 4 * c4 + 2] = v.z; stw[pos * 33 + 4 * c4 + 3] = v.w;
     }
+    __syncwarp();
+#pragma unroll
+    for (int k = 0; k < 32; ++k) zv[r][k] = stw[lane * 33 + k];
   }
+  __syncthreads();                                            // staging reads done before the V transpose writes
   // six groups of 8 outputs: Q (heads x E), K, then the four V heads
 #pragma unroll 1
   for (int grp = 0; grp < 6; ++grp) {
@@ -442,43 +455,60 @@ __global__ void __launch_bounds__(256)
 tfg_attn_proj_kernel(const float* __restrict__ o, const float* __restrict__ w, const float* __restrict__ bias, const float* __restrict__ slope,
                      const float* __restrict__ gamma, const float* __restrict__ beta, const float* __restrict__ resid, int64_t n_pos, float eps,
                      float* __restrict__ out) {
-  // thread = position: the 32 x 32 product, PReLU and LayerNorm are register-local (weights broadcast from shared memory)
+  // thread = position: the 32 x 32 product, PReLU and LayerNorm are register-local (weights broadcast from shared memory).
+  // Positions enter and leave through a shared-memory tile [256][33] so that every global access is a fully used 16-byte
+  // piece of a contiguous 32 KB run (per-thread 128-byte rows straight from global memory ran at 2.2 TB/s).
   __shared__ __align__(16) float sw[32 * 32];
   __shared__ float sp[3 * 32];
+  __shared__ float st[256][TC + 1];
   for (int i = threadIdx.x; i < 1024; i += 256) sw[i] = w[i];
   if (threadIdx.x < 32) { sp[threadIdx.x] = bias[threadIdx.x]; sp[32 + threadIdx.x] = gamma[threadIdx.x]; sp[64 + threadIdx.x] = beta[threadIdx.x]; }
-  __syncthreads();
   const float a = __ldg(slope);
-  for (int64_t p = blockIdx.x * 256ll + threadIdx.x; p < n_pos; p += 256ll * gridDim.x) {
-    float x[32], acc[32];
-    const float4* src = reinterpret_cast<const float4*>(o + p * TC);
+  for (int64_t p0 = blockIdx.x * 256ll; p0 < n_pos; p0 += 256ll * gridDim.x) {
+    __syncthreads();                                   // weights visible (first pass); previous tile's store phase done
+    const int n_here = n_pos - p0 < 256 ? static_cast<int>(n_pos - p0) : 256;
+    const float4* src = reinterpret_cast<const float4*>(o + p0 * TC);
 #pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) { const float4 v = __ldg(src + k4); x[4 * k4] = v.x; x[4 * k4 + 1] = v.y; x[4 * k4 + 2] = v.z; x[4 * k4 + 3] = v.w; }
-    float mu = 0.f;
-#pragma unroll
-    for (int c = 0; c < 32; ++c) {
-      float s = sp[c];
-      const float4* wrow = reinterpret_cast<const float4*>(sw + c * 32);
-#pragma unroll
-      for (int k4 = 0; k4 < 8; ++k4) {
-        const float4 wv = wrow[k4];
-        s = fmaf(wv.x, x[4 * k4], s); s = fmaf(wv.y, x[4 * k4 + 1], s); s = fmaf(wv.z, x[4 * k4 + 2], s); s = fmaf(wv.w, x[4 * k4 + 3], s);
-      }
-      s = s >= 0.f ? s : a * s;
-      acc[c] = s; mu += s;
+    for (int j = 0; j < 8; ++j) {
+      const int idx = j * 256 + threadIdx.x, pos = idx >> 3, c4 = idx & 7;
+      if (pos < n_here) { const float4 v = __ldg(src + idx); st[pos][4 * c4] = v.x; st[pos][4 * c4 + 1] = v.y; st[pos][4 * c4 + 2] = v.z; st[pos][4 * c4 + 3] = v.w; }
     }
-    mu *= (1.0f / 32.0f);
-    float var = 0.f;
+    __syncthreads();
+    if (threadIdx.x < n_here) {
+      float x[32], acc[32];
 #pragma unroll
-    for (int c = 0; c < 32; ++c) { acc[c] -= mu; var = fmaf(acc[c], acc[c], var); }
-    const float rs = rsqrtf(var * (1.0f / 32.0f) + eps);
-    const float4* rsrc = reinterpret_cast<const float4*>(resid + p * TC);
-    float4* dst = reinterpret_cast<float4*>(out + p * TC);
+      for (int k = 0; k < 32; ++k) x[k] = st[threadIdx.x][k];
+      float mu = 0.f;
 #pragma unroll
-    for (int k4 = 0; k4 < 8; ++k4) {
-      const float4 r = __ldg(rsrc + k4);
-      dst[k4] = make_float4(acc[4 * k4] * rs * sp[32 + 4 * k4] + sp[64 + 4 * k4] + r.x, acc[4 * k4 + 1] * rs * sp[33 + 4 * k4] + sp[65 + 4 * k4] + r.y,
-                            acc[4 * k4 + 2] * rs * sp[34 + 4 * k4] + sp[66 + 4 * k4] + r.z, acc[4 * k4 + 3] * rs * sp[35 + 4 * k4] + sp[67 + 4 * k4] + r.w);
+      for (int c = 0; c < 32; ++c) {
+        float s = sp[c];
+        const float4* wrow = reinterpret_cast<const float4*>(sw + c * 32);
+#pragma unroll
+        for (int k4 = 0; k4 < 8; ++k4) {
+          const float4 wv = wrow[k4];
+          s = fmaf(wv.x, x[4 * k4], s); s = fmaf(wv.y, x[4 * k4 + 1], s); s = fmaf(wv.z, x[4 * k4 + 2], s); s = fmaf(wv.w, x[4 * k4 + 3], s);
+        }
+        s = s >= 0.f ? s : a * s;
+        acc[c] = s; mu += s;
+      }
+      mu *= (1.0f / 32.0f);
+      float var = 0.f;
+#pragma unroll
+      for (int c = 0; c < 32; ++c) { acc[c] -= mu; var = fmaf(acc[c], acc[c], var); }
+      const float rs = rsqrtf(var * (1.0f / 32.0f) + eps);
+#pragma unroll
+      for (int c = 0; c < 32; ++c) st[threadIdx.x][c] = acc[c] * rs * sp[32 + c] + sp[64 + c];      // own row: no hazard with other threads
+    }
+    __syncthreads();
+    const float4* rsrc = reinterpret_cast<const float4*>(resid + p0 * TC);
+    float4* dst = reinterpret_cast<float4*>(out + p0 * TC);
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+      const int idx = j * 256 + threadIdx.x, pos = idx >> 3, c4 = idx & 7;
+      if (pos < n_here) {
+        const float4 r = __ldg(rsrc + idx);
+        dst[idx] = make_float4(st[pos][4 * c4] + r.x, st[pos][4 * c4 + 1] + r.y, st[pos][4 * c4 + 2] + r.z, st[pos][4 * c4 + 3] + r.w);
+      }
     }
   }
 }
