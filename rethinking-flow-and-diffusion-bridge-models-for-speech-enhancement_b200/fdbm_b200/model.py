@@ -163,7 +163,8 @@ class EnhancementModel(nn.Module):
         return bufs[0][:need].view(rows, cols), bufs[1][:need].view(rows, cols)
 
     @torch.no_grad()
-    def enhance_list(self, waves: Sequence, micro_batch: int = 32, clip_rescale: Optional[float] = 0.95) -> List[np.ndarray]:
+    def enhance_list(self, waves: Sequence, micro_batch: int = 32, clip_rescale: Optional[float] = 0.95,
+                     lengths: Optional[Sequence[int]] = None, on_done=None) -> List[np.ndarray]:
         """The per-file loop of infer_folder.py:91-121 for waveforms of DIFFERENT lengths, batched: utterances are
         bucketed by their padded frame count (pad_spec rounds to 64 frames; GroupNorm and attention see the whole padded
         image, so only utterances with the same padded length may share a batch without changing any result), each
@@ -171,16 +172,33 @@ class EnhancementModel(nn.Module):
         -> rescale -> clip rule (0.95, infer_folder.py:119-120).  Returns the enhanced waveforms in input order.
 
         Two-slot software pipeline: while the GPU works on micro-batch k the host packs micro-batch k + 1 into the other
-        pinned staging slot and unpacks the results of micro-batch k - 1; the only host waits are on per-slot events."""
+        pinned staging slot and unpacks the results of micro-batch k - 1; the only host waits are on per-slot events.
+
+        Streaming form (used by `enhance_files`): with `lengths` given, an entry of `waves` may be a `concurrent.futures.Future`
+        that resolves to the waveform (it is awaited when its micro-batch is packed), and `on_done(i, x)` is called as soon as
+        utterance i has left the GPU, so decoding, the GPU and encoding overlap."""
         if self.data_module.normalize != "noisy":
             raise NotImplementedError("enhance_list implements the default normalize='noisy'")
         dev = next(self.dnn.parameters()).device
         hop = self.data_module.hop_length
         dm = self.data_module
-        ws = [np.ascontiguousarray(np.asarray(w, dtype=np.float32).reshape(-1)) if not torch.is_tensor(w)
-              else w.detach().to("cpu", torch.float32).reshape(-1).contiguous().numpy() for w in waves]
-        for i, w in enumerate(ws):
-            if w.shape[0] <= dm.n_fft // 2:
+        def as_array(w):
+            if hasattr(w, "result"):
+                w = w.result()
+            if torch.is_tensor(w):
+                return w.detach().to("cpu", torch.float32).reshape(-1).contiguous().numpy()
+            return np.ascontiguousarray(np.asarray(w, dtype=np.float32).reshape(-1))
+
+        if lengths is None:
+            ws = [as_array(w) for w in waves]
+            n_samples = [w.shape[0] for w in ws]
+        else:
+            ws = list(waves)                                       # resolved lazily, micro-batch by micro-batch
+            n_samples = [int(n) for n in lengths]
+            if len(n_samples) != len(ws):
+                raise ValueError("enhance_list: `lengths` must have one entry per waveform")
+        for i, n in enumerate(n_samples):
+            if n <= dm.n_fft // 2:
                 raise RuntimeError(f"utterance {i} is shorter than n_fft/2 samples")
         out: List[Optional[np.ndarray]] = [None] * len(ws)
         pending = []                                               # (event, host_out view, group indices, lengths)
@@ -191,11 +209,13 @@ class EnhancementModel(nn.Module):
                 ev.synchronize()
                 for r, i in enumerate(grp):
                     out[i] = host_out[r, :lens[r]].numpy().copy()
+                    if on_done is not None:
+                        on_done(i, out[i])
 
         with torch.cuda.device(dev):
-            for k, (T_pad, grp) in enumerate(length_buckets([w.shape[0] for w in ws], hop, micro_batch)):
+            for k, (T_pad, grp) in enumerate(length_buckets(n_samples, hop, micro_batch)):
                 n = len(grp)
-                lens = [ws[i].shape[0] for i in grp]
+                lens = [n_samples[i] for i in grp]
                 # a partial batch is padded (last utterance repeated) to the next multiple of 8: at most four plans / graphs
                 # per padded length instead of one per batch size, at most 7 wasted slots
                 mb = micro_batch if n == micro_batch else min(micro_batch, -(-n // 8) * 8)
@@ -205,9 +225,14 @@ class EnhancementModel(nn.Module):
                 host_in, host_out = self._staging(k % 2, mb, max_len)
                 hin = host_in.numpy()
                 for r in range(mb):
-                    w = ws[grp[min(r, n - 1)]]
+                    i = grp[min(r, n - 1)]
+                    w = ws[i] = as_array(ws[i])
+                    if w.shape[0] != n_samples[i]:
+                        raise RuntimeError(f"utterance {i}: {w.shape[0]} samples, `lengths` said {n_samples[i]}")
                     hin[r, :w.shape[0]] = w
                     hin[r, w.shape[0]:] = 0.0
+                for i in grp:
+                    ws[i] = None                                    # the staged copy is the only one needed from here on
                 y = host_in.to(dev, non_blocking=True)
                 lengths = torch.tensor(lens_full, dtype=torch.int32).to(dev, non_blocking=True)
                 norm = dm.wave_absmax(y, lengths)                    # rows are zero-padded beyond their length
@@ -250,11 +275,21 @@ class EnhancementModel(nn.Module):
             os.makedirs(os.path.dirname(os.path.abspath(p)), exist_ok=True)
             wavfile.write(p, target_sr, np.clip(np.round(x * 32767.0), -32768, 32767).astype(np.int16))
 
+        def n_samples_of(p):                                       # header only (memory-mapped): the buckets need the lengths first
+            sr, x = wavfile.read(p, mmap=True)
+            return int(x.shape[0])
+
+        hop = self.data_module.hop_length
         with ThreadPoolExecutor(max_workers=max(1, io_threads)) as pool:
-            waves = list(pool.map(decode, paths))
-            enhanced = self.enhance_list(waves, micro_batch=micro_batch)
-            if out_paths is not None:
-                list(pool.map(encode, zip(out_paths, enhanced)))
+            lens = list(pool.map(n_samples_of, paths))
+            # decode in the order the buckets consume the files; encode every utterance as soon as it has left the GPU
+            order = [i for _, grp in length_buckets(lens, hop, micro_batch) for i in grp]
+            fut = {i: pool.submit(decode, paths[i]) for i in order}
+            writes = []
+            on_done = None if out_paths is None else (lambda i, x: writes.append(pool.submit(encode, (out_paths[i], x))))
+            enhanced = self.enhance_list([fut[i] for i in range(len(paths))], micro_batch=micro_batch, lengths=lens, on_done=on_done)
+            for w in writes:
+                w.result()
         return enhanced
 
 
