@@ -25,3 +25,16 @@ for ms, fl, i in convs[:40]:
 print("non-conv ops > 60 us:")
 for i, (ms, k, fl) in enumerate(prof):
     if k != 0 and ms > 0.06: print(f"   op {i:3d} {names[k]:7s} {ms*1e3:8.1f} us")
+# where the conv time goes relative to the sustained tensor peak: buckets by algorithmic GFLOP of the launch
+PEAK = 1398.0
+buckets = {}
+for ms, fl, i in convs:
+    g = fl / 1e9
+    key = ">=1000" if g >= 1000 else (">=300" if g >= 300 else (">=100" if g >= 100 else (">=30" if g >= 30 else (">=10" if g >= 10 else "<10"))))
+    b = buckets.setdefault(key, [0, 0.0, 0.0]); b[0] += 1; b[1] += ms; b[2] += fl
+conv_ms = sum(c[0] for c in convs)
+print("conv launches by size (GFLOP per launch): count, ms, share of conv time, TFLOP/s, ms lost against the sustained peak")
+for key in (">=1000", ">=300", ">=100", ">=30", ">=10", "<10"):
+    if key in buckets:
+        n, ms, fl = buckets[key]
+        print(f"   {key:7s} n={n:3d} {ms:8.3f} ms {100*ms/conv_ms:5.1f}%  {fl/ms/1e9:7.1f} TFLOP/s  lost {ms - fl/1e9/PEAK:7.3f} ms")
