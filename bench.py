@@ -423,7 +423,9 @@ def tfgridnet_main(args):
     else:
         model = EnhancementModel("tfgridnet_5l32c100", "sb", bridge_kwargs=dict(N=BRIDGE_STEPS, sampler_type="ode_ei"))
     model = model.to(dev).eval()
-    mb = min(args.micro_batch, 32)
+    # 36 utterances = 74 tiles of 128 sequences per sweep = 296 CTAs (two directions x two CTAs per tile) = exactly two waves of
+    # the 148 SMs; 32 would leave the second wave 78 % full
+    mb = min(args.micro_batch, 36)
     waves = synth_batch(args.utts, dev, seed=1234)
     host_in = torch.empty(waves.shape, dtype=torch.float32, pin_memory=True).copy_(waves)
     host_out = torch.empty_like(host_in, pin_memory=True)

@@ -14,8 +14,8 @@ for n in 1 10 30; do timeout 300 python bench.py --bridge-steps $n $B > $O/${P}_
 timeout 300 python bench.py --seconds 30 --utts 32 --micro-batch 16 $B > $O/${P}_bench_30s.json 2>> $O/${P}_bench.err
 timeout 300 python bench.py --workload files > $O/${P}_bench_files.json 2>> $O/${P}_bench.err
 timeout 300 python bench.py --workload train > $O/${P}_bench_train_n1.json 2>> $O/${P}_bench.err
-timeout 400 python bench.py --workload tfgridnet --utts 64 > $O/${P}_bench_tfgridnet.json 2>> $O/${P}_bench.err
-timeout 300 python bench.py --workload tfgridnet_predictive --utts 64 > $O/${P}_bench_tfgridnet_pred.json 2>> $O/${P}_bench.err
+timeout 400 python bench.py --workload tfgridnet --utts 72 > $O/${P}_bench_tfgridnet.json 2>> $O/${P}_bench.err
+timeout 300 python bench.py --workload tfgridnet_predictive --utts 72 > $O/${P}_bench_tfgridnet_pred.json 2>> $O/${P}_bench.err
 # ncu: launch list of one timed step (128 utterances = one micro-batch), conv DRAM traffic of one forward, full captures
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none --launch-skip 1270 --launch-count 1270 --csv --log-file $O/${P}_launches.csv \
   python bench.py --utts 128 --steps 1 --warmup 3 $B > $O/${P}_ncu_launches.log 2>&1
