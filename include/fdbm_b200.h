@@ -267,6 +267,21 @@ int fdbm_hybrid_loss(const float* x_hat, const float* x, int batch, int n_frames
 int fdbm_data_prediction_loss(const float* x_hat, const float* x, int batch, int n_frames, const float* window, int n_fft, int hop,
                               int transform_type, float spec_factor, float abs_exponent, float l1_weight, float loss_scale,
                               void* workspace, float* loss, float* g_out, void* stream);
+/* "data_prediction_mel" (fdbm/model.py:220-233) and, with_phase != 0, "data_prediction_melphase" (:235-251):
+ *   L = 0.5 mean |x_hat - x|^2 + 0.1 MelSpectrogramLoss(istft X^, istft X) (+ 0.01 PhaseLoss(x_hat, x))
+ * MelSpectrogramLoss as BridgeModel builds it (model.py:77-92, fdbm/loss.py:213-289): seven resolutions n_fft = 32..2048 (Hann,
+ * hop n_fft/4, centred, reflection), n_mels = 5,10,20,40,80,160,210, L1 of log10(clamp(mel, 1e-5)^2), mag_weight 0; PhaseLoss =
+ * loss.py:9-33 (instantaneous phase, group delay, phase time difference, anti-wrapped L1).  Forward and gradient in one call.
+ * `tables`: fdbm_mel_tables_bytes() bytes of device memory the caller owns, filled once by fdbm_mel_tables_init (windows,
+ * twiddles, the librosa-convention Slaney filterbanks of `sample_rate`; the call synchronises `stream`).  Same conventions and
+ * constraints as fdbm_hybrid_loss; additionally target_len = (T - 1) * hop > 1024.  workspace: fdbm_mel_loss_workspace_bytes
+ * (256-byte aligned). */
+int64_t fdbm_mel_tables_bytes(void);
+int fdbm_mel_tables_init(void* tables, int sample_rate, void* stream);
+int64_t fdbm_mel_loss_workspace_bytes(int batch, int n_frames, int n_fft, int hop);
+int fdbm_mel_loss(const float* x_hat, const float* x, int batch, int n_frames, const float* window, int n_fft, int hop,
+                  int transform_type, float spec_factor, float abs_exponent, int with_phase, float loss_scale,
+                  const void* tables, void* workspace, float* loss, float* g_out, void* stream);
 
 /* Measurement aid for bench.py: run one forward launch by launch with a CUDA event pair around every
  * kernel.  ms[i] = device time, kinds[i] = FDBM_OP_*, flops[i] = algorithmic FLOPs (2*MAC, convolutions

@@ -805,6 +805,80 @@ def data_prediction_loss(x_hat: Tensor, x: Tensor, cfg: SpecConfig, l1_weight: f
     return losses_tf + l1_weight * losses_l1
 
 
+MEL_N_MELS = (5, 10, 20, 40, 80, 160, 210)          # model.py:77-92: the seven resolutions of the mel heads
+MEL_N_FFTS = (32, 64, 128, 256, 512, 1024, 2048)      # win_length = n_fft, hop = n_fft / 4
+
+
+def mel_filterbank(sr: int, n_fft: int, n_mels: int, fmin: float = 0.0, fmax: Optional[float] = None) -> Tensor:
+    """`librosa.filters.mel(sr, n_fft, n_mels, fmin, fmax)` with its defaults (Slaney mel scale, htk=False, norm='slaney',
+    float32) -- the call of loss.py:265-273.  librosa is a third-party dependency of the reference that is absent from
+    /root/reference and from this image (version unpinned by the reference): this is a restatement of its published algorithm
+    (librosa 0.10: `mel_frequencies`, triangular weights `max(0, min(lower, upper))`, area normalisation `2 / (f[i+2] - f[i])`),
+    NOT pinned against librosa itself."""
+    fmax = sr / 2.0 if fmax is None else fmax
+    f_sp, min_log_hz = 200.0 / 3, 1000.0
+    min_log_mel, logstep = min_log_hz / f_sp, math.log(6.4) / 27.0
+
+    def hz_to_mel(f):
+        return f / f_sp if f < min_log_hz else min_log_mel + math.log(f / min_log_hz) / logstep
+
+    mels = torch.linspace(hz_to_mel(fmin), hz_to_mel(fmax), n_mels + 2, dtype=torch.float64)
+    freqs = torch.where(mels >= min_log_mel, min_log_hz * torch.exp(logstep * (mels - min_log_mel)), f_sp * mels)
+    fftfreqs = torch.linspace(0, sr / 2.0, 1 + n_fft // 2, dtype=torch.float64)
+    fdiff = freqs[1:] - freqs[:-1]
+    ramps = freqs[:, None] - fftfreqs[None, :]
+    lower = -ramps[:-2] / fdiff[:-1, None]
+    upper = ramps[2:] / fdiff[1:, None]
+    w = torch.clamp(torch.minimum(lower, upper), min=0.0)
+    w = w * (2.0 / (freqs[2:n_mels + 2] - freqs[:n_mels]))[:, None]
+    return w.to(torch.float32)                                            # [n_mels, 1 + n_fft / 2]
+
+
+def mel_spectrogram_loss(x_td: Tensor, y_td: Tensor, sr: int = 16000) -> Tensor:
+    """MelSpectrogramLoss.forward (loss.py:244-262) as BridgeModel constructs it (model.py:77-92: seven resolutions, mag_weight 0,
+    log_weight 1, pow 2, clamp_eps 1e-5, L1): sum over resolutions of L1(log10 clamp(mel |STFT x|)^2, same of y)."""
+    loss = x_td.new_zeros(())
+    for n_mels, n_fft in zip(MEL_N_MELS, MEL_N_FFTS):
+        window = torch.hann_window(n_fft, dtype=x_td.dtype, device=x_td.device)
+        kw = dict(n_fft=n_fft, hop_length=n_fft // 4, win_length=n_fft, window=window, return_complex=True)
+        X = torch.stft(x_td.reshape(-1, x_td.shape[-1]), **kw)
+        Y = torch.stft(y_td.reshape(-1, y_td.shape[-1]), **kw)
+        basis = mel_filterbank(sr, n_fft, n_mels).to(dtype=x_td.dtype, device=x_td.device)
+        xm = (torch.abs(X).transpose(-2, -1) @ basis.T).transpose(-1, -2)
+        ym = (torch.abs(Y).transpose(-2, -1) @ basis.T).transpose(-1, -2)
+        loss = loss + torch.mean(torch.abs(xm.clamp(min=1e-5).pow(2).log10() - ym.clamp(min=1e-5).pow(2).log10()))
+    return loss
+
+
+def phase_loss(spec_est: Tensor, spec_ref: Tensor) -> Tensor:
+    """PhaseLoss.forward (loss.py:9-33): instantaneous phase + group delay (difference along frequency) + phase time difference
+    (along frames), each as mean |anti-wrapped difference|.  The reference's difference matrices give d[j] = p[j-1] - p[j], d[0] = -p[0]."""
+    def unwrap(v):
+        return torch.abs(v - 2 * math.pi * torch.round(v / (2 * math.pi)))
+
+    def diff_last(p):
+        return torch.cat((-p[..., :1], p[..., :-1] - p[..., 1:]), dim=-1)
+
+    pg, pr = torch.angle(spec_est).squeeze(1), torch.angle(spec_ref).squeeze(1)          # [B, F, T]
+    gd_r, gd_g = diff_last(pr.permute(0, 2, 1)), diff_last(pg.permute(0, 2, 1))            # along frequency
+    ptd_r, ptd_g = diff_last(pr), diff_last(pg)                                            # along frames
+    return torch.mean(torch.abs(unwrap(pr - pg))) + torch.mean(torch.abs(unwrap(gd_r - gd_g))) + torch.mean(torch.abs(unwrap(ptd_r - ptd_g)))
+
+
+def data_prediction_mel_loss(x_hat: Tensor, x: Tensor, cfg: SpecConfig, with_phase: bool = False) -> Tensor:
+    """BridgeModel._loss, loss_type "data_prediction_mel" (model.py:220-233) / "data_prediction_melphase" (:235-251):
+    0.5 mean |x_hat - x|^2 + 0.1 mel loss of the waveforms (+ 0.01 phase loss of the compressed spectrograms)."""
+    B, C, Fq, T = x.shape
+    losses_tf = torch.mean(torch.square(torch.abs(x_hat - x))) * 0.5
+    target_len = (T - 1) * cfg.hop_length
+    x_hat_td = istft_torch(spec_back(x_hat, cfg).squeeze(1), cfg, target_len)
+    x_td = istft_torch(spec_back(x, cfg).squeeze(1), cfg, target_len)
+    loss = losses_tf + 0.1 * mel_spectrogram_loss(x_hat_td, x_td)
+    if with_phase:
+        loss = loss + 0.01 * phase_loss(x_hat, x)
+    return loss
+
+
 def istft_torch(spec: Tensor, cfg: SpecConfig, length: Optional[int] = None) -> Tensor:
     """data_module.py:227-229 through torch.istft itself (autograd-capable, any float width); `istft` above is the
     explicit restatement, the two agree to rounding (tests/test_oracle_golden.py)."""

@@ -371,6 +371,55 @@ def loss_goldens_data_prediction(ref_model=None, dm=None, x=None, x_hat=None, sc
                         grad=c2n(g_ref))
 
 
+def loss_goldens_mel(seed=23):
+    """BridgeModel._loss 'data_prediction_mel' / 'data_prediction_melphase' (model.py:220-251) through the reference's own
+    MelSpectrogramLoss / PhaseLoss classes (loss.py), and their gradients.  The one substitution: `librosa.filters.mel` (absent
+    here) is the oracle's restatement `mel_filterbank`, so these fixtures pin everything except the filterbank formula.
+    Stand-alone: `python oracle/make_golden.py mel`."""
+    import types as _types
+    import fdbm_oracle as O
+    import_reference()
+    lib_filters = types.ModuleType("librosa.filters")
+    lib_filters.mel = lambda sr, n_fft, n_mels, fmin=0.0, fmax=None: O.mel_filterbank(sr, n_fft, n_mels, fmin, fmax).numpy()
+    sys.modules["librosa.filters"] = lib_filters
+    sys.modules["librosa"].filters = lib_filters
+    import fdbm.model as ref_model
+    import fdbm.loss as ref_loss
+    from fdbm.data_module import SpecsDataModule
+    T = 64
+    dm = SpecsDataModule(base_dir="/unused", n_fft=512, hop_length=256, num_frames=T, window="sqrthann", gpu=False)
+    scfg = O.SpecConfig()
+    gl = torch.Generator().manual_seed(seed)
+
+    def spec(B=2):
+        mag = torch.rand(B, 1, 257, T, generator=gl) ** 3 * 0.6
+        ph = 2 * 3.14159265 * torch.rand(B, 1, 257, T, generator=gl)
+        return torch.polar(mag, ph)
+    x = spec()
+    x_hat = x + 0.3 * spec()
+    x_hat[:, :, 256] = 0
+    mel_args = dict(n_mels=list(O.MEL_N_MELS), win_lengths=list(O.MEL_N_FFTS), hop_lengths=[n // 4 for n in O.MEL_N_FFTS],
+                    n_ffts=list(O.MEL_N_FFTS), mag_weight=0.0, log_weight=1.0)
+    out = {"x": c2n(x), "x_hat": c2n(x_hat)}
+    for kind, with_phase in (("data_prediction_mel", False), ("data_prediction_melphase", True)):
+        fake_dm = _types.SimpleNamespace(num_frames=T, hop_length=dm.hop_length, n_fft=512)
+        fake_self = _types.SimpleNamespace(loss_type=kind, pesq_weight=0.0, l1_weight=0.001, data_module=fake_dm,
+                                           to_audio=lambda s, length=None: dm.istft(dm.spec_back(s), length),
+                                           loss_fn=ref_loss.MelSpectrogramLoss(**mel_args), loss_fn_mel=ref_loss.MelSpectrogramLoss(**mel_args),
+                                           loss_fn_phase=ref_loss.PhaseLoss(nfreqs=257, frames=T))
+        leaf = x_hat.clone().requires_grad_(True)
+        loss_ref = ref_model.BridgeModel._loss(fake_self, leaf, None, None, None, None, x)
+        (g_ref,) = torch.autograd.grad(loss_ref, leaf)
+        leaf2 = x_hat.clone().requires_grad_(True)
+        loss_or = O.data_prediction_mel_loss(leaf2, x, scfg, with_phase)
+        (g_or,) = torch.autograd.grad(loss_or, leaf2)
+        g_ref = torch.nan_to_num(g_ref); g_or = torch.nan_to_num(g_or)
+        print(f"{kind}: loss reference {float(loss_ref):.6f} oracle {float(loss_or):.6f}; gradient oracle vs ref {rel(g_or, g_ref):.3e}")
+        tag = "melphase" if with_phase else "mel"
+        out["loss_" + tag] = np.float64(loss_ref.item()); out["grad_" + tag] = c2n(g_ref)
+    np.savez_compressed(os.path.join(OUT, "mel_loss.npz"), **out)
+
+
 def tfgridnet_goldens(BackboneRegistry=None):
     """(6) TF-GridNet: the reference's tfgridnet_5l32c100 / _predictive forward on [2,1,257,24] with the oracle's fixed weights,
     and the deviation a 10-bit-mantissa-operand run has from fp32 (cuDNN runs the reference's LSTMs and convolutions in TF32 on
@@ -429,6 +478,8 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "tfgridnet":
         os.makedirs(OUT, exist_ok=True)
         tfgridnet_goldens()
+    elif len(sys.argv) > 1 and sys.argv[1] == "mel":
+        loss_goldens_mel()
     elif len(sys.argv) > 1 and sys.argv[1] == "loss":
         loss_goldens_data_prediction()
     elif len(sys.argv) > 1 and sys.argv[1] == "variants":

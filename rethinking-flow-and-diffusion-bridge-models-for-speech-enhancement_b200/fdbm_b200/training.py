@@ -68,14 +68,14 @@ class TrainStep:
                  clip_norm: float = 3.0, t_eps: float = 0.03, loss_scale: float = 4096.0, betas=(0.9, 0.999), eps: float = 1e-8,
                  ema_warmup: bool = True, dynamic_loss_scale: bool = True, scale_check_interval: int = 50,
                  scale_growth_interval: int = 2000, loss_type: str = "data_prediction_hybrid", l1_weight: float = 0.001,
-                 pesq_weight: float = 0.0):
-        # BridgeModel.__init__(loss_type, l1_weight, pesq_weight) (model.py:41): the two heads that have kernels
-        if loss_type not in ("data_prediction_hybrid", "data_prediction"):
-            raise NotImplementedError(f"loss_type {loss_type!r}: fdbm_b200 implements 'data_prediction_hybrid' (config.yaml) and "
-                                      "'data_prediction' (the argparse default); the mel / mel+phase heads are not built")
+                 pesq_weight: float = 0.0, sr: int = 16000):
+        # BridgeModel.__init__(loss_type, l1_weight, pesq_weight, sr) (model.py:41): the four loss types of `_loss` (model.py:162-254)
+        if loss_type not in ("data_prediction_hybrid", "data_prediction", "data_prediction_mel", "data_prediction_melphase"):
+            raise ValueError("Invalid loss type: {}".format(loss_type))
         if pesq_weight != 0.0:
             raise NotImplementedError("pesq_weight > 0 (torch_pesq loss term) is not implemented")
-        self.loss_type, self.l1_weight = loss_type, float(l1_weight)
+        self.loss_type, self.l1_weight, self.sr = loss_type, float(l1_weight), int(sr)
+        self._mel_tables = None
         self.dnn, self.bridge, self.dm = dnn, bridge, data_module
         self.batch, self.n_frames = batch, n_frames
         self.lr, self.ema_decay, self.clip_norm, self.t_eps, self.loss_scale = lr, ema_decay, clip_norm, t_eps, loss_scale
@@ -258,12 +258,22 @@ class TrainStep:
         from ._lib import FDBM_TRANSFORM
         B, _, Fb, T = D.shape
         dm = self.dm
-        need = self.lib.fdbm_hybrid_loss_workspace_bytes(B, T, dm.n_fft, dm.hop_length)
+        mel = self.loss_type in ("data_prediction_mel", "data_prediction_melphase")
+        need = (self.lib.fdbm_mel_loss_workspace_bytes if mel else self.lib.fdbm_hybrid_loss_workspace_bytes)(B, T, dm.n_fft, dm.hop_length)
         if getattr(self, "_loss_ws", None) is None or self._loss_ws.numel() < need:
             self._loss_ws = torch.empty(need, dtype=torch.uint8, device=D.device)
         loss = torch.empty((), device=D.device)
         g = torch.empty_like(D)
         D, x = D.contiguous(), x.contiguous()
+        if mel:
+            if self._mel_tables is None:              # windows, twiddles, mel filterbanks of the seven resolutions: built once
+                self._mel_tables = torch.empty(self.lib.fdbm_mel_tables_bytes(), dtype=torch.uint8, device=D.device)
+                check(self.lib.fdbm_mel_tables_init(ptr(self._mel_tables), self.sr, current_stream()), "fdbm_mel_tables_init")
+            check(self.lib.fdbm_mel_loss(ptr(torch.view_as_real(D)), ptr(torch.view_as_real(x)), B, T, ptr(dm._get_window(D)), dm.n_fft,
+                                         dm.hop_length, FDBM_TRANSFORM[dm.transform_type], float(dm.spec_factor), float(dm.spec_abs_exponent),
+                                         int(self.loss_type == "data_prediction_melphase"), self.loss_scale, ptr(self._mel_tables),
+                                         ptr(self._loss_ws), ptr(loss), ptr(torch.view_as_real(g)), current_stream()), "fdbm_mel_loss")
+            return loss, g
         if self.loss_type == "data_prediction":
             check(self.lib.fdbm_data_prediction_loss(ptr(torch.view_as_real(D)), ptr(torch.view_as_real(x)), B, T, ptr(dm._get_window(D)), dm.n_fft,
                                                      dm.hop_length, FDBM_TRANSFORM[dm.transform_type], float(dm.spec_factor),

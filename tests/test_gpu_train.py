@@ -172,19 +172,27 @@ def _loss_cuda(lib, kind, xh, x, scale=512.0, l1_weight=0.001):
     tail = (scale, ws.data_ptr(), loss.data_ptr(), torch.view_as_real(gout).data_ptr(), _stream())
     if kind == "data_prediction_hybrid":
         _check(lib, lib.fdbm_hybrid_loss(*args, *tail))
+    elif kind in ("data_prediction_mel", "data_prediction_melphase"):
+        tables = torch.empty(lib.fdbm_mel_tables_bytes(), dtype=torch.uint8, device="cuda")
+        _check(lib, lib.fdbm_mel_tables_init(tables.data_ptr(), 16000, _stream()))
+        ws = torch.empty(lib.fdbm_mel_loss_workspace_bytes(B, T, 512, 256), dtype=torch.uint8, device="cuda")
+        _check(lib, lib.fdbm_mel_loss(*args, int(kind.endswith("phase")), scale, tables.data_ptr(), ws.data_ptr(), *tail[2:]))
     else:
         _check(lib, lib.fdbm_data_prediction_loss(*args, l1_weight, *tail))
     torch.cuda.synchronize()
     return loss.cpu(), gout.cpu() / scale
 
 
-@pytest.mark.parametrize("kind,fixture", [("data_prediction_hybrid", "hybrid_loss.npz"), ("data_prediction", "data_prediction_loss.npz")])
+@pytest.mark.parametrize("kind,fixture", [("data_prediction_hybrid", "hybrid_loss.npz"), ("data_prediction", "data_prediction_loss.npz"),
+                                          ("data_prediction_mel", "mel_loss.npz"), ("data_prediction_melphase", "mel_loss.npz")])
 def test_loss_heads_match_reference_golden(lib, golden_dir, kind, fixture):
-    """fdbm_hybrid_loss / fdbm_data_prediction_loss (value and gradient w.r.t. the backbone output) against the reference's own
-    BridgeModel._loss under torch autograd (fdbm/model.py:163-218; fixtures written by oracle/make_golden.py)."""
+    """fdbm_hybrid_loss / fdbm_data_prediction_loss / fdbm_mel_loss (value and gradient w.r.t. the backbone output) against the
+    reference's own BridgeModel._loss under torch autograd (fdbm/model.py:163-251 with fdbm/loss.py's MelSpectrogramLoss / PhaseLoss;
+    fixtures written by oracle/make_golden.py)."""
     from helpers import load_npz
     g = load_npz(f"{golden_dir}/{fixture}")
-    x, xh, gref, ref = torch.from_numpy(g["x"]), torch.from_numpy(g["x_hat"]), torch.from_numpy(g["grad"]).clone(), float(g["loss"])
+    tag = {"data_prediction_mel": "_mel", "data_prediction_melphase": "_melphase"}.get(kind, "")
+    x, xh, gref, ref = torch.from_numpy(g["x"]), torch.from_numpy(g["x_hat"]), torch.from_numpy(g["grad" + tag]).clone(), float(g["loss" + tag])
     loss, got = _loss_cuda(lib, kind, xh, x)
     # row 256 (Nyquist) of the backbone output is exactly zero and dropped by the output layer's backward: not compared
     got[:, :, 256] = 0
@@ -265,7 +273,7 @@ def test_training_step_gradients_match_autograd():
 
 def test_training_step_with_the_default_loss_head():
     """TrainStep(loss_type='data_prediction'), the reference's argparse default (model.py:32,41): the loss of a step against the
-    oracle's forward + restated loss on the same (x, y, t, z), a non-zero update, and the heads that have no kernel are refused."""
+    oracle's forward + restated loss on the same (x, y, t, z), a non-zero update; an unknown loss type and the PESQ term (torch_pesq) are refused."""
     O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z = _train_setup()
     B, T = x.shape[0], x.shape[3]
     with torch.no_grad():
@@ -281,11 +289,31 @@ def test_training_step_with_the_default_loss_head():
     assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref)) + 1e-5
     assert float((ts.flat_params - before).abs().max()) > 0 and bool(torch.isfinite(ts.flat_params).all())
     ts.close()
-    for bad in ("data_prediction_mel", "data_prediction_melphase"):
-        with pytest.raises(NotImplementedError):
-            TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_type=bad)
+    with pytest.raises(ValueError):                       # model.py:253-254
+        TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_type="score_matching")
     with pytest.raises(NotImplementedError):
         TrainStep(net, bridge, dm, batch=B, n_frames=T, pesq_weight=0.1)
+
+
+@pytest.mark.parametrize("loss_type", ["data_prediction_mel", "data_prediction_melphase"])
+def test_training_step_with_the_mel_loss_heads(loss_type):
+    """TrainStep(loss_type='data_prediction_mel' / '_melphase') (model.py:220-251): the loss of a step against the oracle's forward +
+    restated loss (pinned to the reference's MelSpectrogramLoss / PhaseLoss by tests/golden/mel_loss.npz) on the same (x, y, t, z)."""
+    O, cfg, sd, net, dm, bridge, TrainStep, x, y, t, z = _train_setup(T=128)
+    B, T = x.shape[0], x.shape[3]
+    with torch.no_grad():
+        mean, std = bridge.probability_path(x, y, t)
+        D_ref = O.ncsnpp_forward(sd, cfg, mean + std[:, None, None, None] * z, y, t)
+        loss_ref = O.data_prediction_mel_loss(D_ref, x, O.SpecConfig(), loss_type.endswith("phase"))
+    ts = TrainStep(net, bridge, dm, batch=B, n_frames=T, loss_scale=1024.0, loss_type=loss_type)
+    loss = ts.loss_and_backward(x.cuda(), y.cuda(), t.cuda(), z.cuda())
+    before = ts.flat_params.clone()
+    ts.optimizer_step()
+    torch.cuda.synchronize()
+    print(f"{loss_type} step: loss ours {float(loss):.6f} oracle {float(loss_ref):.6f}")
+    assert abs(float(loss) - float(loss_ref)) < 2e-2 * abs(float(loss_ref)) + 1e-5
+    assert float((ts.flat_params - before).abs().max()) > 0 and bool(torch.isfinite(ts.flat_params).all())
+    ts.close()
 
 
 def test_training_step_updates_like_torch_adam():

@@ -125,3 +125,33 @@ def test_data_prediction_loss_oracle_matches_reference_golden(golden_dir):
     (grad,) = torch.autograd.grad(loss, xh)
     assert abs(float(loss) - float(g["loss"])) < 1e-5 * abs(float(g["loss"]))
     assert rel_l2(torch.nan_to_num(grad), g["grad"]) < 1e-5
+
+
+def test_mel_loss_oracle_matches_reference_golden(golden_dir):
+    """O.data_prediction_mel_loss (mel and mel + phase) against BridgeModel._loss 'data_prediction_mel' / '_melphase' of the
+    reference run through its own MelSpectrogramLoss / PhaseLoss (tests/golden/mel_loss.npz; librosa's filterbank is the oracle's
+    restatement there, so the fixture pins everything except the filterbank formula)."""
+    g = load_npz(f"{golden_dir}/mel_loss.npz")
+    for tag, with_phase in (("mel", False), ("melphase", True)):
+        x, xh = torch.from_numpy(g["x"]), torch.from_numpy(g["x_hat"]).requires_grad_(True)
+        loss = O.data_prediction_mel_loss(xh, x, O.SpecConfig(), with_phase)
+        (grad,) = torch.autograd.grad(loss, xh)
+        assert abs(float(loss) - float(g["loss_" + tag])) < 1e-5 * abs(float(g["loss_" + tag]))
+        assert rel_l2(torch.nan_to_num(grad), g["grad_" + tag]) < 1e-5
+
+
+def test_mel_filterbank_properties():
+    """The restated librosa.filters.mel (Slaney scale, area-normalised triangles): shape, non-negativity, every filter non-empty at
+    the seven resolutions of model.py:77-92, unit area in Hz, and the known centre frequencies of the Slaney scale (linear 66.67 Hz
+    per mel below 1 kHz)."""
+    for n_mels, n_fft in zip(O.MEL_N_MELS, O.MEL_N_FFTS):
+        w = O.mel_filterbank(16000, n_fft, n_mels)
+        assert w.shape == (n_mels, n_fft // 2 + 1) and bool((w >= 0).all())
+        if n_fft >= 4 * n_mels:
+            assert bool((w.sum(1) > 0).all())
+    w = O.mel_filterbank(16000, 2048, 80).double()
+    area = w.sum(1) * (8000.0 / 1024)                       # integral over frequency of an area-normalised triangle = 1
+    assert float((area - 1).abs().max()) < 0.05
+    peaks = w.argmax(1).double() * (8000.0 / 1024)
+    mel_step = (15 + 27 * __import__("math").log(8.0) / __import__("math").log(6.4)) / 81      # hz_to_mel(8000) / (n_mels + 1)
+    assert abs(float(peaks[0]) - mel_step * 200.0 / 3) < 8.0 and abs(float(peaks[9]) - 10 * mel_step * 200.0 / 3) < 8.0
