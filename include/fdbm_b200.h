@@ -187,6 +187,10 @@ typedef struct fdbm_arch {
   int attn_resolution;    /* 16 (0 = none)                                   */
   int predictive;         /* 0: forward(x,y,t), 4 input ch;  1: forward(y)   */
   int image_size;         /* 256 (frequency bins seen by the backbone)       */
+  int channel_block_real; /* 0: every channel is real.  96: the nf = 96 size variants (ncsnpp_v2.py:404-415, 436-448) run as
+                           * nf = 128 with every 128-channel block = 96 real channels followed by 32 zero channels; the host
+                           * zero-pads the weights (fdbm_b200/backbones.py), the only arithmetic that depends on it is the
+                           * GroupNorm group structure (groups and counts follow the REAL channel index).  Inference plans only. */
 } fdbm_arch;
 
 int fdbm_plan_create(const fdbm_arch* arch, int batch, int n_frames, fdbm_plan** out);

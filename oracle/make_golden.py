@@ -472,6 +472,21 @@ def variant_goldens(BackboneRegistry=None):
         got = O.ncsnpp_forward(sd, cfg, xt, Y, t)
     print(f"ncsnpp_v2_16M forward oracle vs ref: {rel(got, want):.3e}  out std {float(want.abs().std()):.3f}  params {sum(v.numel() for v in sd.values())}")
     np.savez_compressed(os.path.join(OUT, "ncsnpp_16M_T64.npz"), D=c2n(want))
+    # the nf = 96 variants ncsnpp_v2_5M (ncsnpp_v2.py:404-415) and ncsnpp_v2_37M (:436-448): 96 / 192-channel tensors, GroupNorm
+    # groups of 4, 6, 9 and 12 channels
+    out = {}
+    for name, cfg in (("ncsnpp_v2_5M", O.NcsnppConfig(nf=96, ch_mult=(1, 1, 1, 1), num_res_blocks=1, attn_resolutions=(0,))),
+                      ("ncsnpp_v2_37M", O.NcsnppConfig(nf=96))):
+        sd = O.sensitised_state_dict(cfg, seed=0)
+        net = BackboneRegistry.get_by_name(name)().eval()
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == {k: tuple(v.shape) for k, v in sd.items()}
+        net.load_state_dict(sd, strict=True)
+        with torch.no_grad():
+            want = net(xt, Y, t)
+            got = O.ncsnpp_forward(sd, cfg, xt, Y, t)
+        print(f"{name} forward oracle vs ref: {rel(got, want):.3e}  out std {float(want.abs().std()):.3f}  params {sum(v.numel() for v in sd.values())}")
+        out[name] = c2n(want)
+    np.savez_compressed(os.path.join(OUT, "ncsnpp_nf96_T64.npz"), **out)
 
 
 if __name__ == "__main__":

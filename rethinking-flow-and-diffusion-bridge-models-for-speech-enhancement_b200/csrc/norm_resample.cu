@@ -405,14 +405,17 @@ gn_resample16_kernel(const op_t* __restrict__ src1, int C1, const op_t* __restri
 // (scale, shift) per (utterance, channel) of a GroupNorm over the concatenation of up to two tensors:
 // scale = gamma * rstd(group), shift = beta - mean(group) * scale.  Consumed by the convolution's
 // normalise-on-load stage.  One block per utterance.
+// blk_real != 0 (fdbm_arch.channel_block_real): every 128-channel block holds blk_real real channels followed by zero
+// channels; groups and counts follow the real channel index r = (c / 128) * blk_real + c % 128, padding gets (0, 0).
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __restrict__ sums2, int C2,
                    const float* __restrict__ gamma, const float* __restrict__ beta, double pixels,
-                   float2* __restrict__ table) {
+                   float2* __restrict__ table, int blk_real) {
   __shared__ double2 s_sq[GN_MAXC];
   __shared__ float s_mean[32], s_rstd[32];
   const int C = C1 + C2, b = blockIdx.x;
-  const int G = min(C / 4, 32), cpg = C / G;
+  const int Cr = blk_real ? C / 128 * blk_real : C;
+  const int G = min(Cr / 4, 32), cpg = Cr / G;
   // all (sum, sum of squares) entries in one round of independent 16-byte loads (the launch is latency-bound)
   float gam[GN_MAXC / 256], bet[GN_MAXC / 256];
 #pragma unroll
@@ -428,7 +431,11 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
   __syncthreads();
   if (threadIdx.x < G) {
     double s = 0, q = 0;
-    for (int j = 0; j < cpg; ++j) { const double2 e = s_sq[threadIdx.x * cpg + j]; s += e.x; q += e.y; }
+    for (int j = 0; j < cpg; ++j) {
+      const int r = threadIdx.x * cpg + j;
+      const double2 e = s_sq[blk_real ? r / blk_real * 128 + r % blk_real : r];
+      s += e.x; q += e.y;
+    }
     const double cnt = cpg * pixels;
     const double mean = s / cnt;
     double var = q / cnt - mean * mean;
@@ -441,7 +448,8 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
   for (int u = 0; u < GN_MAXC / 256; ++u) {
     const int c = threadIdx.x + u * 256;
     if (c < C) {
-      const int g = c / cpg;
+      if (blk_real && (c & 127) >= blk_real) { table[static_cast<int64_t>(b) * C + c] = make_float2(0.f, 0.f); continue; }
+      const int g = (blk_real ? (c >> 7) * blk_real + (c & 127) : c) / cpg;
       const float a = gam[u] * s_rstd[g];
       table[static_cast<int64_t>(b) * C + c] = make_float2(a, bet[u] - s_mean[g] * a);
     }
@@ -451,10 +459,13 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
 }  // namespace
 
 int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2, const float* gamma, const float* beta,
-                       int B, int64_t pixels, float2* table, cudaStream_t s) {
+                       int B, int64_t pixels, float2* table, cudaStream_t s, int blk_real) {
   const int C = C1 + C2;
-  FDBM_REQUIRE(C % std::min(C / 4, 32) == 0 && C >= 4 && C <= GN_MAXC, "gn_finalize: unsupported channels %d+%d", C1, C2);
-  gn_finalize_kernel<<<B, 256, 0, s>>>(sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table);
+  FDBM_REQUIRE(blk_real == 0 || (blk_real > 0 && blk_real < 128 && blk_real % 4 == 0 && C1 % 128 == 0 && C2 % 128 == 0),
+               "gn_finalize: channel_block_real %d needs 128-channel blocks (%d+%d)", blk_real, C1, C2);
+  const int Cr = blk_real ? C / 128 * blk_real : C;
+  FDBM_REQUIRE(Cr % std::min(Cr / 4, 32) == 0 && C >= 4 && C <= GN_MAXC, "gn_finalize: unsupported channels %d+%d", C1, C2);
+  gn_finalize_kernel<<<B, 256, 0, s>>>(sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table, blk_real);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

@@ -370,7 +370,8 @@ struct Builder {
     const int B = P->B;
     float2* tab = alloc<float2>(static_cast<int64_t>(B) * (C1 + C2));
     const int64_t px = static_cast<int64_t>(T) * F;
-    op([=](cudaStream_t s) { return launch_gn_finalize(q1, C1, q2, C2, gamma, beta, B, px, tab, s); }, FDBM_OP_STATS);
+    const int blk_real = P->arch.channel_block_real;
+    op([=](cudaStream_t s) { return launch_gn_finalize(q1, C1, q2, C2, gamma, beta, B, px, tab, s, blk_real); }, FDBM_OP_STATS);
     return tab;
   }
   static ConvSeg seg(const op_t* in, int C, int taps, const float2* tab = nullptr, int tab_stride = 0, int act = 0) {
@@ -939,6 +940,9 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
     const int c = arch->nf * arch->ch_mult[i];
     FDBM_REQUIRE(c == 64 || c % 128 == 0, "fdbm_plan_create: level %d has %d channels; supported: 64 or a multiple of 128", i, c);
   }
+  FDBM_REQUIRE(arch->channel_block_real == 0 || (arch->channel_block_real == 96 && arch->nf == 128 && !train),
+               "fdbm_plan_create: channel_block_real must be 0, or 96 with nf = 128 on an inference plan (got %d, nf %d)",
+               arch->channel_block_real, arch->nf);
   FDBM_REQUIRE(!train || arch->nf >= 128, "fdbm_plan_create_train: the training step is built for nf >= 128");
 
   fdbm_plan* P = new fdbm_plan();

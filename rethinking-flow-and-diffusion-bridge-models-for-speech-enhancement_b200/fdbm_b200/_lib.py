@@ -46,7 +46,7 @@ class TensorRef(C.Structure):
 
 class Arch(C.Structure):
     _fields_ = [("nf", C.c_int), ("n_levels", C.c_int), ("ch_mult", C.c_int * 8), ("num_res_blocks", C.c_int),
-                ("attn_resolution", C.c_int), ("predictive", C.c_int), ("image_size", C.c_int)]
+                ("attn_resolution", C.c_int), ("predictive", C.c_int), ("image_size", C.c_int), ("channel_block_real", C.c_int)]
 
 
 _lib = None

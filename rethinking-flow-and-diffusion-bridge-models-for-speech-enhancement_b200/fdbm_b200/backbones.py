@@ -101,6 +101,31 @@ def sensitise_(net: nn.Module, seed: int = 0) -> nn.Module:
     return net
 
 
+def _pad_channel_blocks(name, w, real=96, block=128):
+    """Zero-padded copy of a parameter of an nf = 96 network in the channel layout of the nf = 128 plan that runs it
+    (fdbm_arch.channel_block_real): along every dimension whose size is a multiple of 96, real channel r moves to
+    block * (r // 96) + r % 96 and the 32 channels that end each block are zero.  Concatenated inputs (skip connections) need no
+    special case: every tensor of the network is a whole number of 96-channel blocks.  Zero weights, biases, FiLM rows and
+    GroupNorm gains keep the padding channels exactly zero through every layer, so the result is that of the nf = 96 network;
+    the two places where a channel count enters the arithmetic are the GroupNorm group structure (handled in gn_finalize) and the
+    attention logit scale C^-1/2 (layerspp.py:83), folded into the query projection NIN_0 here."""
+    if name.endswith("NIN_0.W") or name.endswith("NIN_0.b"):
+        w = w * (block / real) ** 0.5
+    for dim, size in enumerate(w.shape):
+        if size % real or size == 0:
+            continue
+        nb = size // real
+        shape = list(w.shape)
+        shape[dim:dim + 1] = [nb, real]
+        v = w.reshape(shape)
+        shape[dim + 1] = block
+        out = w.new_zeros(shape)
+        out.narrow(dim + 1, 0, real).copy_(v)
+        shape[dim:dim + 2] = [nb * block]
+        w = out.reshape(shape)
+    return w.contiguous()
+
+
 def _is_gn_entry(net, name):
     parts = name.split(".")
     if parts[0] != "all_modules":
@@ -197,6 +222,8 @@ class _NCSNppBase(nn.Module):
     def _arch(self) -> Arch:
         a = Arch()
         a.nf, a.n_levels, a.num_res_blocks = self.nf, len(self.ch_mult), self.num_res_blocks
+        if self.nf == 96:                       # ncsnpp_v2_5M / _37M: run as nf = 128 with 96 real channels per 128-channel block
+            a.nf, a.channel_block_real = 128, 96
         for i, m in enumerate(self.ch_mult):
             a.ch_mult[i] = m
         a.attn_resolution = self.attn_resolutions[0] if self.attn_resolutions else 0
@@ -226,6 +253,8 @@ class _NCSNppBase(nn.Module):
             if p.device != device or p.dtype != torch.float32:
                 raise RuntimeError(f"parameter {n} must be fp32 on {device}")
             d = p.detach().contiguous()
+            if self.nf == 96:
+                d = _pad_channel_blocks(n, d)
             keep.append(d)
             refs[i].name, refs[i].data, refs[i].numel = n.encode(), d.data_ptr(), d.numel()
         check(_lib.load().fdbm_plan_load_weights(handle, refs, len(named), current_stream()), "fdbm_plan_load_weights")
@@ -408,12 +437,21 @@ class NCSNpp_v2_16M(NCSNpp_v2):
 
 class _Nf96Variant(NCSNpp_v2):
     """ncsnpp_v2_5M / ncsnpp_v2_37M (fdbm/backbones/ncsnpp_v2.py:404-415, 436-448) have nf = 96: 96- and 192-channel tensors, which the
-    tensor-core convolution (64-channel K-blocks, 64 / 128-channel N tiles) does not tile.  The names resolve so that configuration
-    errors are explicit; constructing one raises."""
+    tensor-core convolution (64-channel K-blocks, 64 / 128-channel N tiles) does not tile.  They run on an nf = 128 plan with
+    zero-padded weights (`_pad_channel_blocks`): (128 / 96)^2 = 1.78 x the algorithmic FLOPs, same results.  Inference only: the
+    training plan (flat gradient buffers in the parameters' own layout) is not built for the padded layout."""
+    _variant = {}
 
     def __init__(self, **kwargs):
-        raise NotImplementedError(f"{type(self).__name__}: nf = 96 needs 32-channel K-block tails in libfdbm_b200's convolution; "
-                                  "supported NCSN++ sizes are ncsnpp_v2 (nf 128) and ncsnpp_v2_16M (nf 64)")
+        for k in ("nf", "ch_mult", "num_res_blocks", "attn_resolutions"):
+            kwargs.pop(k, None)
+        super().__init__(**self._variant, **kwargs)
+
+    def _plan(self, device, batch, n_frames, train=False):
+        if train:
+            raise NotImplementedError(f"{type(self).__name__}: training plans are built for nf = 64 / 128 (the nf = 96 variants run "
+                                      "inference on a zero-padded nf = 128 plan)")
+        return super()._plan(device, batch, n_frames)
 
     @staticmethod
     def add_argparse_args(parser):
@@ -422,12 +460,12 @@ class _Nf96Variant(NCSNpp_v2):
 
 @BackboneRegistry.register("ncsnpp_v2_5M")
 class NCSNpp_v2_5M(_Nf96Variant):
-    pass
+    _variant = dict(nf=96, ch_mult=(1, 1, 1, 1), num_res_blocks=1, attn_resolutions=[0])
 
 
 @BackboneRegistry.register("ncsnpp_v2_37M")
 class NCSNpp_v2_37M(_Nf96Variant):
-    pass
+    _variant = dict(nf=96, ch_mult=(1, 1, 2, 2, 2, 2, 2), num_res_blocks=2, attn_resolutions=[16])
 
 
 @BackboneRegistry.register("ncsnpp_v2_predictive")

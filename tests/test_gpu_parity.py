@@ -363,7 +363,30 @@ def test_ncsnpp_v2_16M_golden(golden_dir):
     assert err < TOL_16BIT
     D2 = net(xt.repeat(3, 1, 1, 1), Y.repeat(3, 1, 1, 1), t.repeat(3))
     assert max(rel_l2(D2[i], D[0]) for i in range(3)) < 2e-5
-    for name in ("ncsnpp_v2_5M", "ncsnpp_v2_37M"):
-        with pytest.raises(NotImplementedError):
-            BackboneRegistry.get_by_name(name)()
+    net.release_plans()
+
+
+@pytest.mark.parametrize("name", ["ncsnpp_v2_5M", "ncsnpp_v2_37M"])
+def test_ncsnpp_v2_nf96_variants_golden(golden_dir, name):
+    """The nf = 96 size variants (ncsnpp_v2.py:404-415, 436-448: 96 / 192-channel tensors, GroupNorm groups of 4, 6, 9 and 12
+    channels, four levels x one block for _5M) against the reference's own forward.  They run on an nf = 128 plan with zero-padded
+    weights and the real-channel GroupNorm grouping (fdbm_arch.channel_block_real = 96)."""
+    import fdbm_oracle as O
+    from fdbm_b200 import BackboneRegistry
+    cfg = (O.NcsnppConfig(nf=96, ch_mult=(1, 1, 1, 1), num_res_blocks=1, attn_resolutions=(0,)) if name.endswith("5M") else O.NcsnppConfig(nf=96))
+    sd = O.sensitised_state_dict(cfg, seed=0)
+    net = BackboneRegistry.get_by_name(name)()
+    net.load_state_dict(sd, strict=True)
+    net = net.cuda().eval()
+    g = load_npz(f"{golden_dir}/bridge_T64.npz")
+    xt, Y, t = (torch.from_numpy(g[k]).cuda() for k in ("xt", "Y", "t"))
+    D = net(xt, Y, t)
+    err = rel_l2(D, load_npz(f"{golden_dir}/ncsnpp_nf96_T64.npz")[name])
+    print(f"{name} T=64 rel L2 vs reference golden: {err:.3e}")
+    assert err < TOL_16BIT
+    D2 = net(xt.repeat(3, 1, 1, 1), Y.repeat(3, 1, 1, 1), t.repeat(3))
+    assert max(rel_l2(D2[i], D[0]) for i in range(3)) < 2e-5
+    net.train()
+    with pytest.raises(NotImplementedError):                 # no training plan in the padded layout
+        net(xt, Y, t)
     net.release_plans()

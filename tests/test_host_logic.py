@@ -68,6 +68,23 @@ def test_backbone_registry_and_state_dict_names():
         if n_par:
             assert sum(p.numel() for p in net.parameters()) == n_par
         assert not dict(net.named_parameters())["all_modules.0.W"].requires_grad if not pred else True
+    # the nf = 96 variants: reference parameter names / shapes, and the zero-padded image the nf = 128 plan is loaded with
+    from fdbm_b200.backbones import _pad_channel_blocks
+    for name, cfg in (("ncsnpp_v2_5M", O.NcsnppConfig(nf=96, ch_mult=(1, 1, 1, 1), num_res_blocks=1, attn_resolutions=(0,))),
+                      ("ncsnpp_v2_37M", O.NcsnppConfig(nf=96))):
+        net = BackboneRegistry.get_by_name(name)(nf=128, ch_mult=(1,))
+        assert {k: tuple(v.shape) for k, v in net.state_dict().items()} == O.param_shapes(cfg)
+        big = O.param_shapes(O.NcsnppConfig(nf=128, ch_mult=cfg.ch_mult, num_res_blocks=cfg.num_res_blocks, attn_resolutions=cfg.attn_resolutions))
+        arch = net._arch()
+        assert (arch.nf, arch.channel_block_real) == (128, 96)
+        for k, v in net.state_dict().items():
+            p = _pad_channel_blocks(k, v)
+            assert tuple(p.shape) == big[k], k
+            scale = (128 / 96) ** 0.5 if k.endswith(("NIN_0.W", "NIN_0.b")) else 1.0
+            assert abs(float(p.double().sum()) - scale * float(v.double().sum())) <= 1e-6 * float(v.double().abs().sum()) + 1e-12   # only zeros were added
+    w = torch.arange(192.0)
+    p = _pad_channel_blocks("x", w)
+    assert torch.equal(p[:96], w[:96]) and torch.equal(p[128:224], w[96:]) and not p[96:128].any() and not p[224:].any()
     with pytest.raises(ValueError):
         BackboneRegistry.get_by_name("ncsnpp")                              # unregistered name, as in the reference
     with pytest.raises(NotImplementedError):
