@@ -30,7 +30,10 @@ constexpr int NBIN = NFFT / 2 + 1;
 // kernels issue 2.5 x / 4 x fewer instructions than the first generation (ncu: 25.9 M vs 64 M warp instructions for the STFT)
 // but are now latency-bound: ~100 registers per thread allow 16-20 warps per SM, issue slots are 20 % busy, a warp issues
 // every 20 cycles, 37 % of the stall cycles are the block barriers around the staging tile -- larger blocks make that worse,
-// more resident blocks (FDBM_SPEC_MINBLOCKS 5, 6) change nothing or spill.
+// more resident blocks (FDBM_SPEC_MINBLOCKS 5, 6) change nothing or spill.  Dropping the staging tile and its two block barriers
+// (every lane writing the 32 contiguous bytes = 4 frames of its bins straight from registers) was measured too: 1.79 TB/s
+// instead of 2.16 (96 registers), 1.53 with 80 registers / 6 blocks, 1.69 / 1.76 with 8 / 2 warps -- 16-byte pieces of 32
+// different lines per store instruction cost more than the barriers they remove.
 #ifndef FDBM_SPEC_WARPS
 #define FDBM_SPEC_WARPS 4
 #endif
