@@ -320,7 +320,7 @@ def train_main(args):
     net = sensitise_(BackboneRegistry.get_by_name("ncsnpp_v2")(), seed=0).to(dev)
     dm = SpecsDataModule(n_fft=512, hop_length=256, num_frames=256, window="sqrthann")
     bridge = Bridge("sb", N=BRIDGE_STEPS, sampler_type="ode_ei")
-    ts = TrainStep(net, bridge, dm, batch=B, n_frames=256, loss_scale=1024.0)
+    ts = TrainStep(net, bridge, dm, batch=B, n_frames=256, loss_scale=1024.0, loss_type=args.loss_type)
     global N_SAMPLES
     N_SAMPLES = crop
     noisy = synth_batch(B, dev, seed=4321 + 1000 * rank)
@@ -384,12 +384,12 @@ def train_main(args):
         peak = float(peaks.get("bf16_tflops_sustained", 1400.0))
         achieved = gflop_step / world / (ms / args.steps * 1e-3) / 1e3
         print(json.dumps({
-            "metric": "bridge training step throughput (ncsnpp_v2, hybrid loss, Adam+EMA, DDP)", "value": value, "unit": "crops/s",
+            "metric": f"bridge training step throughput (ncsnpp_v2, {args.loss_type} loss, Adam+EMA, DDP)", "value": value, "unit": "crops/s",
             "n_gpus": world, "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "bf16" if lib.fdbm_operand_is_bf16() else "fp16 (loss-scaled gradients, fp32 master weights)", "data": "synthetic",
             "config": {"workload": f"train: {B} crops of 65 280 samples (256 frames) per GPU, ncsnpp_v2 65.6 M params, "
-                                   "data_prediction_hybrid loss, Adam lr 1e-4, clip 3.0, EMA 0.999", "global_batch": B * world,
+                                   f"{args.loss_type} loss, Adam lr 1e-4, clip 3.0, EMA 0.999", "global_batch": B * world,
                        "parallelism": f"dp{world}", "l2": "activations kept for backward >> L2"},
             "e2e": {"value": samples / (ms_e2e * 1e-3), "unit": "crops/s", "h2d_bytes_per_step": 2 * X.numel() * 8,
                     "d2h_bytes_per_step": 4, "ms_per_step": ms_e2e / args.steps},
@@ -553,6 +553,9 @@ def main():
     ap.add_argument("--workload", default="infer_folder", choices=["infer_folder", "predictive", "train", "files", "tfgridnet", "tfgridnet_predictive"],
                     help="BASELINE.json configs[1] (default, the headline metric), configs[2] or configs[3] (training step)")
     ap.add_argument("--train-batch", type=int, default=16, help="training crops per GPU per step (configs[3]: 8 x 16)")
+    ap.add_argument("--loss-type", default="data_prediction_hybrid",
+                    choices=["data_prediction_hybrid", "data_prediction", "data_prediction_mel", "data_prediction_melphase"],
+                    help="--workload train: BridgeModel's loss head (model.py:162-254); config.yaml trains with the hybrid one")
     ap.add_argument("--bridge-steps", type=int, default=5, help="configs[4]: sampling-step sweep 1/5/10/30")
     ap.add_argument("--seconds", type=float, default=4.0, help="configs[4]: utterance length (30 s long-form)")
     ap.add_argument("--scaling", default="strong", choices=["strong", "weak"],
