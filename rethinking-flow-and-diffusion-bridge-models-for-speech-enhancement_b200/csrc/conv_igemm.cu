@@ -61,6 +61,9 @@ constexpr int A_TILE1_BYTES = TILE_T * TILE_F * 128;           // 1-tap segments
 // 512 threads start at 128 registers each; setmaxnreg moves registers from the pipeline and transform
 // warpgroups to the two epilogue warpgroups (128 * (56 + 120 + 2 * 168) = 65536)
 constexpr int PIPE_REGS = 56, EPI_REGS = 168, XFORM_REGS = 120;
+#ifndef FDBM_EPI_RES2
+#define FDBM_EPI_RES2 1          // 16-bit shortcut rows double-buffered in registers (0: the single-buffer epilogue, 10 % slower on Conv_1)
+#endif
 constexpr int STAGE_BYTES = EPI_GROUPS * 4 * 32 * 32 * 4;       // epilogue transposition tiles, one per warp
 constexpr int STAT_SLOTS = 2;                                  // n-blocks whose statistics a CTA keeps in flight
 constexpr int STAT_BYTES = EPI_GROUPS * 4 * BN * 8;            // per-warp channel (sum, sum of squares) partials
@@ -583,6 +586,25 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         float4 bv = __ldg(reinterpret_cast<const float4*>(bias_p));
         float4 bvb = biasb_p ? __ldg(reinterpret_cast<const float4*>(biasb_p)) : make_float4(0.f, 0.f, 0.f, 0.f);
         float4 res[8];
+#if FDBM_EPI_RES2
+        // two register buffers for the 16-bit shortcut rows: chunk ch + 1 is requested BEFORE chunk ch's accumulators are read, a
+        // whole chunk ahead of its use (with one buffer the compiler hoisted the fp16 -> fp32 conversions of the freshly requested
+        // rows to the top of the next chunk, in front of the TMEM read and the transposition: the warp sat on the L2 latency there)
+        uint2 res16_buf[2][8];
+#define res16 res16_buf[ch & 1]
+        auto load_res16 = [&](int ch) {
+          uint2 (&dst)[8] = res16_buf[ch & 1];
+          if (full) {
+#pragma unroll
+            for (int it = 0; it < 8; ++it) dst[it] = __ldg(reinterpret_cast<const uint2*>(res16_p + roff(it) + ch * 32));
+          } else {
+#pragma unroll
+            for (int it = 0; it < 8; ++it)
+              dst[it] = ((okmask >> it) & 1) ? __ldg(reinterpret_cast<const uint2*>(res16_p + roff(it) + ch * 32)) : make_uint2(0u, 0u);
+          }
+        };
+        if (RES16) load_res16(0);
+#else
         uint2 res16[8];
         auto load_res16 = [&](int ch) {
           if (full) {
@@ -594,6 +616,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
               res16[it] = ((okmask >> it) & 1) ? __ldg(reinterpret_cast<const uint2*>(res16_p + roff(it) + ch * 32)) : make_uint2(0u, 0u);
           }
         };
+#endif
         auto load_res = [&](float4 (&r)[8], int ch) {
           if (full) {
 #pragma unroll
@@ -627,8 +650,14 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           uint32_t v[32];
           tmem_ld_32x32(tmem_base + ((q * 32u) << 16) + (as * MT + j) * BN + ch * 32, v);
+#if FDBM_EPI_RES2
+          // (also requesting chunk 0 of the warpgroup's NEXT tile during the last chunk was measured: spills, 5 % slower)
+          if (RES16) { if (ch + 1 < n_chunks) load_res16(ch + 1); }
+          else if (res_p) load_res(res, ch);
+#else
           if (RES16) { if (ch == 0) load_res16(0); }      // chunks 1..3 were requested while the previous chunk was stored
           else if (res_p) load_res(res, ch);
+#endif
           tmem_ld_wait();
 #pragma unroll
           for (int g = 0; g < 8; ++g)
@@ -670,7 +699,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           }
           // the shortcut registers are free again: request the next chunk's rows now (L2 hits, prefetched one tile ahead), a
           // whole store + statistics phase ahead of their use, without a second register buffer
+#if !FDBM_EPI_RES2
           if (RES16 && ch + 1 < n_chunks) load_res16(ch + 1);
+#endif
           float2 ssum_lo = make_float2(0.f, 0.f), ssum_hi = ssum_lo, ssq_lo = ssum_lo, ssq_hi = ssum_lo;
           if (full) {                                       // whole tile inside the image: no per-row predicates
             if (of_p) {
@@ -717,6 +748,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           __syncwarp();                                   // staging tile is rewritten by the next chunk
           bv = bvn; bvb = bvbn;
         }
+#if FDBM_EPI_RES2
+#undef res16
+#endif
         if (do_stats) {                                   // block-uniform
           asm volatile("bar.sync %0, 128;" ::"r"(1 + eg) : "memory");
           double s = 0.0, sq = 0.0;
