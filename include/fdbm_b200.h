@@ -287,6 +287,25 @@ int fdbm_mel_loss(const float* x_hat, const float* x, int batch, int n_frames, c
                   int transform_type, float spec_factor, float abs_exponent, int with_phase, float loss_scale,
                   const void* tables, void* workspace, float* loss, float* g_out, void* stream);
 
+/* The skinny layers of NCSN++, exported for kernel-level parity tests and other hosts.  Activations are
+ * [B,T,F,C] (channels innermost), spectrograms cplx [B,1,f_in,T].
+ *   fdbm_pack_input      ncsnpp_v2.py:247-250  x (, y) cplx -> fp32 [B,T,f_used,c_in] = (Re x, Im x (, Re y, Im y)), rows >= f_used dropped
+ *   fdbm_im2col_input    ncsnpp_v2.py:278      [B,T,F,c_in] fp32 -> 16-bit [B,T,F,64], k = (kf*3 + kt)*c_in + ci: the 3x3 input convolution as
+ *                                              one K-block of fdbm_conv_igemm (ksize 1 with weights packed by fdbm_pack_conv_weights ksize -2)
+ *   fdbm_time_embedding  layerspp.py:32-41, ncsnpp_v2.py:252-270   t [B] -> SiLU(temb) [B,4 nf]
+ *   fdbm_film_rows       layerspp.py:263       all Dense_0 layers at once: out [B,rows] = act [B,k] . weight[rows,k]^T + bias
+ *   fdbm_combine         layerspp.py:52-59     h += conv1x1(c_pyr -> C)(pyramid) (progressive_combine 'sum'); weight [C,c_pyr]
+ *   fdbm_output_layer    ncsnpp_v2.py:392-399  conv1x1(c_pyr -> 2) -> cplx [B,1,f_out,T], rows >= n_freq zero (the Nyquist row) */
+int fdbm_pack_input(const float* x, const float* y, int batch, int n_frames, int f_in, int f_used, int c_in, float* out, void* stream);
+int fdbm_im2col_input(const float* in, int c_in, int batch, int n_frames, int n_freq, void* out_h16, void* stream);
+int fdbm_time_embedding(const float* t, const float* fourier_w, int nf, const float* w1, const float* b1, const float* w2,
+                        const float* b2, int batch, float* out, void* stream);
+int fdbm_film_rows(const float* temb_act, const float* weight, const float* bias, int batch, int k, int rows, float* out, void* stream);
+int fdbm_combine(float* h, const float* pyramid, int c_pyr, const float* weight, const float* bias, int batch, int n_frames, int n_freq,
+                 int channels, void* stream);
+int fdbm_output_layer(const float* pyramid, int c_pyr, const float* weight, const float* bias, int batch, int n_frames, int n_freq,
+                      int f_out, float* out, void* stream);
+
 /* Measurement aid for bench.py: run one forward launch by launch with a CUDA event pair around every
  * kernel.  ms[i] = device time, kinds[i] = FDBM_OP_*, flops[i] = algorithmic FLOPs (2*MAC, convolutions
  * only) of launch i.  Returns the number of launches (<= max_ops) or a negative error.  Synchronises. */
@@ -398,7 +417,8 @@ int fdbm_adam_ema_step(float* params, const float* grads, float* m, float* v, fl
                        float ema_decay, int ema_warmup, double* state, void* stream);
 
 /* w1 fp32 OIHW [Cout,C1,k,k] (H = frequency, W = frames as in the reference), w2 fp32 [Cout,C2,1,1] or NULL
- * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]).  Returns bytes via *bytes when wpack==NULL. */
+ * -> h16 [ (k*k*C1 + C2)/64 ][Cout][64] K-blocked, tap-major (ksize -1: w1 is a NIN matrix [C1][Cout]; ksize -2: the 3x3 input
+ * convolution with 9 * C1 <= 64 as ONE K-block, k = tap * C1 + ci, for fdbm_im2col_input's columns).  Returns bytes via *bytes when wpack==NULL. */
 int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,
                            void* wpack, int64_t* bytes, void* stream);
 

@@ -102,12 +102,8 @@ int launch_groupnorm_act(const void* src1, int src1_h16 /* both sources 16-bit *
 int launch_pack_input(const float* x, const float* y, int B, int T, int F_in, int F, int Cin, float* out,
                       cudaStream_t s);
 int launch_im2col_input(const float* in, int Cin, int B, int T, int F, op_t* out, cudaStream_t s);
-int launch_conv_in(const float* in, int Cin, const float* w, const float* bias, int B, int T, int F, int Cout,
-                   float* out, cudaStream_t s);
 int launch_combine(float* h, const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F,
                    int C, cudaStream_t s);
-int launch_pyramid_conv(const op_t* act, int C, const float* w, const float* bias, const float* prev,
-                        int Cp, int B, int T, int F, float* out, cudaStream_t s);
 int launch_output_layer(const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F,
                         int F_out, float* out, cudaStream_t s);
 int launch_temb(const float* t, const float* fourier_w, int nf, const float* w1, const float* b1, const float* w2,

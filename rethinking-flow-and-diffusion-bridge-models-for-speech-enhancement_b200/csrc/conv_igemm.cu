@@ -1050,10 +1050,12 @@ using namespace fdbm;
 extern "C" int fdbm_pack_conv_weights(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout,
                                       void* wpack, int64_t* bytes, void* stream) {
   const int k = ksize == -1 ? 1 : ksize;
-  if (bytes) *bytes = conv_wpack_bytes(C1, k, C2, Cout);
+  // ksize -2: the 3x3 input convolution (C1 <= 7 channels) as ONE 64-wide K-block over fdbm_im2col_input's columns
+  if (bytes) *bytes = ksize == -2 ? static_cast<int64_t>(Cout) * 64 * 2 : conv_wpack_bytes(C1, k, C2, Cout);
   if (!wpack) return FDBM_OK;
   if (int rc = require_sm100()) return rc;
   FDBM_REQUIRE(w1 && ((C2 == 0) == (w2 == nullptr)), "fdbm_pack_conv_weights: null pointer");
+  FDBM_REQUIRE(ksize != -2 || (C1 >= 1 && 9 * C1 <= 64 && C2 == 0), "fdbm_pack_conv_weights: ksize -2 needs 9 * C1 <= 64 and no second operand");
   return launch_pack_conv_weights(w1, C1, ksize, w2, C2, Cout, Cout, 0, reinterpret_cast<op_t*>(wpack),
                                   as_stream(stream));
 }

@@ -1,8 +1,8 @@
 // "Skinny" layers of NCSN++ whose GEMM K or N is <= 4: HBM-bound, CUDA-core kernels.
 //   pack_input     ncsnpp_v2.py:247-250   complex [B,1,257,T] x,y -> fp32 [B,T,256,4]
-//   conv_in        ncsnpp_v2.py:278       conv3x3 4 -> nf
+//   im2col_input   ncsnpp_v2.py:278       conv3x3 4 -> nf as one 64-wide K-block for the tensor-core kernel
 //   combine        layerspp.py:52-59      h += conv1x1(4 -> C)(input pyramid)
-//   pyramid_conv   ncsnpp_v2.py:338-359   pyramid = FIR-up(pyramid) + conv3x3(C -> 4)(act)
+//   (the C -> 4 pyramid convolutions run in conv_igemm with MMA N = 16 and a progressive-output epilogue)
 //   output_layer   ncsnpp_v2.py:392-399   conv1x1(4 -> 2) -> complex [B,1,257,T], Nyquist row = 0
 // Reference conv weights are OIHW with H = frequency, W = frames; activations here are [B,T,F,C].
 #include "common.cuh"
@@ -79,51 +79,6 @@ im2col_input_kernel(const float* __restrict__ in, int B, int T, int F, uint4* __
 }
 
 // ------------------------------------------------------------------------------------------------
-// conv_in: a warp computes one pixel; lane l owns output channels 4l..4l+3 (+128 per repeat).
-// Weights sit in shared memory as [tap*Cin + ci][Cout].
-// ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(256)
-conv_in_kernel(const float* __restrict__ in, int Cin, const float* __restrict__ w, const float* __restrict__ bias,
-               int B, int T, int F, int Cout, float* __restrict__ out) {
-  extern __shared__ float ws[];                  // [9*Cin][Cout]
-  for (int i = threadIdx.x; i < 9 * Cin * Cout; i += 256) {
-    const int co = i % Cout, k = i / Cout;
-    const int ci = k % Cin, tap = k / Cin;
-    const int kf = tap / 3, kt = tap % 3;         // OIHW: H = frequency, W = frames
-    ws[i] = w[((co * Cin + ci) * 3 + kf) * 3 + kt];
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_px = static_cast<int64_t>(B) * T * F;
-  for (int64_t p = blockIdx.x * 8ll + warp; p < n_px; p += 8ll * gridDim.x) {
-    const int f = static_cast<int>(p % F);
-    const int t = static_cast<int>((p / F) % T);
-    const int b = static_cast<int>(p / (static_cast<int64_t>(F) * T));
-    float xin[36];
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
-      const bool ok = ff >= 0 && ff < F && tt >= 0 && tt < T;
-      const float* src = in + ((static_cast<int64_t>(b) * T + tt) * F + ff) * Cin;
-      for (int ci = 0; ci < 4; ++ci) xin[tap * 4 + ci] = (ok && ci < Cin) ? src[ci] : 0.f;
-    }
-    for (int c0 = lane * 4; c0 < Cout; c0 += 128) {
-      float4 acc = *reinterpret_cast<const float4*>(bias + c0);
-#pragma unroll
-      for (int tap = 0; tap < 9; ++tap) {
-        for (int ci = 0; ci < Cin; ++ci) {
-          const float4 wv = *reinterpret_cast<const float4*>(ws + (tap * Cin + ci) * Cout + c0);
-          const float xv = xin[tap * 4 + ci];
-          acc.x = fmaf(xv, wv.x, acc.x); acc.y = fmaf(xv, wv.y, acc.y);
-          acc.z = fmaf(xv, wv.z, acc.z); acc.w = fmaf(xv, wv.w, acc.w);
-        }
-      }
-      *reinterpret_cast<float4*>(out + p * Cout + c0) = acc;
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
 // combine: h[b,p,c] += sum_k w[c][k] * pyr[b,p,k] + bias[c]
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
@@ -146,92 +101,6 @@ combine_kernel(float4* __restrict__ h, const float* __restrict__ pyr, int Cp, co
       o[j] += acc;
     }
     h[i] = make_float4(o[0], o[1], o[2], o[3]);
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// pyramid_conv: a warp computes one pixel; lane l owns VEC = C/32 consecutive input channels.
-// Shared weights are laid out [tap][j][lane][Cp] so that a warp reads consecutive float4s.
-// ------------------------------------------------------------------------------------------------
-template <int VEC, int CP>
-__global__ void __launch_bounds__(256)
-pyramid_conv_kernel(const op_t* __restrict__ act, const float* __restrict__ w, const float* __restrict__ bias,
-                    const float* __restrict__ prev, int B, int T, int F, float* __restrict__ out) {
-  constexpr int C = VEC * 32;
-  extern __shared__ float ws[];                  // [9][VEC][32][CP]
-  for (int i = threadIdx.x; i < 9 * C * CP; i += 256) {
-    const int o = i % CP;
-    const int l = (i / CP) % 32;
-    const int j = (i / (CP * 32)) % VEC;
-    const int tap = i / (CP * 32 * VEC);
-    const int c = l * VEC + j;
-    const int kf = tap / 3, kt = tap % 3;
-    ws[i] = w[((o * C + c) * 3 + kf) * 3 + kt];
-  }
-  __syncthreads();
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int64_t n_px = static_cast<int64_t>(B) * T * F;
-  for (int64_t p = blockIdx.x * 8ll + warp; p < n_px; p += 8ll * gridDim.x) {
-    const int f = static_cast<int>(p % F);
-    const int t = static_cast<int>((p / F) % T);
-    const int b = static_cast<int>(p / (static_cast<int64_t>(F) * T));
-    float acc[CP];
-#pragma unroll
-    for (int o = 0; o < CP; ++o) acc[o] = 0.f;
-#pragma unroll
-    for (int tap = 0; tap < 9; ++tap) {
-      const int ff = f + tap / 3 - 1, tt = t + tap % 3 - 1;
-      if (ff < 0 || ff >= F || tt < 0 || tt >= T) continue;
-      const op_t* src = act + ((static_cast<int64_t>(b) * T + tt) * F + ff) * C + lane * VEC;
-      float xv[VEC];
-      if (VEC == 8) {
-        const uint4 raw = *reinterpret_cast<const uint4*>(src);
-        const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
-#pragma unroll
-        for (int j = 0; j < 4; ++j) { const float2 f2 = op22f2(h2[j]); xv[2 * j] = f2.x; xv[2 * j + 1] = f2.y; }
-      } else {
-        const uint2 raw = *reinterpret_cast<const uint2*>(src);
-        const op2_t* h2 = reinterpret_cast<const op2_t*>(&raw);
-#pragma unroll
-        for (int j = 0; j < 2; ++j) { const float2 f2 = op22f2(h2[j]); xv[2 * j] = f2.x; xv[2 * j + 1] = f2.y; }
-      }
-#pragma unroll
-      for (int j = 0; j < VEC; ++j) {
-        const float* wp = ws + ((tap * VEC + j) * 32 + lane) * CP;
-#pragma unroll
-        for (int o = 0; o < CP; ++o) acc[o] = fmaf(xv[j], wp[o], acc[o]);
-      }
-    }
-#pragma unroll
-    for (int o = 0; o < CP; ++o) {
-#pragma unroll
-      for (int sft = 16; sft >= 1; sft >>= 1) acc[o] += __shfl_xor_sync(0xffffffffu, acc[o], sft);
-    }
-    if (lane < CP) {
-      float v = bias[lane];
-#pragma unroll
-      for (int o = 0; o < CP; ++o) if (o == lane) v += acc[o];
-      if (prev) {                                  // + FIR-up x2 of the coarser pyramid level at (t, f)
-        const int Tp = T / 2, Fp = F / 2;
-        const int it = t >> 1, jf = f >> 1;
-        const int t_a = (t & 1) ? it : it - 1, t_b = t_a + 1;
-        const float wt_a = (t & 1) ? 0.75f : 0.25f, wt_b = 1.0f - wt_a;
-        const int f_a = (f & 1) ? jf : jf - 1, f_b = f_a + 1;
-        const float wf_a = (f & 1) ? 0.75f : 0.25f, wf_b = 1.0f - wf_a;
-        const float* pb = prev + static_cast<int64_t>(b) * Tp * Fp * CP + lane;
-        float up = 0.f;
-        if (t_a >= 0 && t_a < Tp) {
-          if (f_a >= 0 && f_a < Fp) up += wt_a * wf_a * pb[(static_cast<int64_t>(t_a) * Fp + f_a) * CP];
-          if (f_b >= 0 && f_b < Fp) up += wt_a * wf_b * pb[(static_cast<int64_t>(t_a) * Fp + f_b) * CP];
-        }
-        if (t_b >= 0 && t_b < Tp) {
-          if (f_a >= 0 && f_a < Fp) up += wt_b * wf_a * pb[(static_cast<int64_t>(t_b) * Fp + f_a) * CP];
-          if (f_b >= 0 && f_b < Fp) up += wt_b * wf_b * pb[(static_cast<int64_t>(t_b) * Fp + f_b) * CP];
-        }
-        v += up;
-      }
-      out[p * CP + lane] = v;
-    }
   }
 }
 
@@ -286,17 +155,6 @@ int launch_im2col_input(const float* in, int Cin, int B, int T, int F, op_t* out
   return FDBM_OK;
 }
 
-int launch_conv_in(const float* in, int Cin, const float* w, const float* bias, int B, int T, int F, int Cout,
-                   float* out, cudaStream_t s) {
-  FDBM_REQUIRE(Cin <= 4 && Cout % 128 == 0, "conv_in: unsupported channels %d -> %d", Cin, Cout);
-  const size_t smem = sizeof(float) * 9 * Cin * Cout;
-  const int64_t n_px = static_cast<int64_t>(B) * T * F;
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(n_px, 8), static_cast<int64_t>(num_sms()) * 8));
-  conv_in_kernel<<<grid, 256, smem, s>>>(in, Cin, w, bias, B, T, F, Cout, out);
-  FDBM_LAUNCH_CHECK();
-  return FDBM_OK;
-}
-
 int launch_combine(float* h, const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F, int C,
                    cudaStream_t s) {
   FDBM_REQUIRE(Cp <= 4 && C % 4 == 0, "combine: unsupported channels");
@@ -305,30 +163,6 @@ int launch_combine(float* h, const float* pyr, int Cp, const float* w, const flo
   combine_kernel<<<grid, 256, 0, s>>>(reinterpret_cast<float4*>(h), pyr, Cp, w, bias, n_px, C);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
-}
-
-template <int VEC, int CP>
-static int launch_pyr(const op_t* act, const float* w, const float* bias, const float* prev, int B, int T,
-                      int F, float* out, cudaStream_t s) {
-  const size_t smem = sizeof(float) * 9 * VEC * 32 * CP;
-  static PerDeviceOnce attr_once;
-  if (attr_once.first(current_device()))
-    FDBM_CUDA(cudaFuncSetAttribute(pyramid_conv_kernel<VEC, CP>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-  const int64_t n_px = static_cast<int64_t>(B) * T * F;
-  const int grid = static_cast<int>(std::min<int64_t>(ceil_div64(n_px, 8), static_cast<int64_t>(num_sms()) * 6));
-  pyramid_conv_kernel<VEC, CP><<<grid, 256, smem, s>>>(act, w, bias, prev, B, T, F, out);
-  FDBM_LAUNCH_CHECK();
-  return FDBM_OK;
-}
-
-int launch_pyramid_conv(const op_t* act, int C, const float* w, const float* bias, const float* prev, int Cp,
-                        int B, int T, int F, float* out, cudaStream_t s) {
-  FDBM_REQUIRE((C == 128 || C == 256) && (Cp == 4 || Cp == 2), "pyramid_conv: unsupported channels %d -> %d", C, Cp);
-  FDBM_REQUIRE(prev == nullptr || (T % 2 == 0 && F % 2 == 0), "pyramid_conv: odd size with a coarser level");
-  if (C == 128 && Cp == 4) return launch_pyr<4, 4>(act, w, bias, prev, B, T, F, out, s);
-  if (C == 256 && Cp == 4) return launch_pyr<8, 4>(act, w, bias, prev, B, T, F, out, s);
-  if (C == 128 && Cp == 2) return launch_pyr<4, 2>(act, w, bias, prev, B, T, F, out, s);
-  return launch_pyr<8, 2>(act, w, bias, prev, B, T, F, out, s);
 }
 
 int launch_output_layer(const float* pyr, int Cp, const float* w, const float* bias, int B, int T, int F, int F_out,
@@ -340,3 +174,30 @@ int launch_output_layer(const float* pyr, int Cp, const float* w, const float* b
 }
 
 }  // namespace fdbm
+
+using namespace fdbm;
+
+// C ABI of the skinny layers (kernel-level parity tests and other hosts; the backbone plan calls the launchers directly)
+extern "C" int fdbm_pack_input(const float* x, const float* y, int batch, int n_frames, int f_in, int f_used, int c_in, float* out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(x && out && batch > 0 && n_frames > 0 && f_used > 0 && f_used <= f_in && (c_in == 2 || (c_in == 4 && y)), "fdbm_pack_input: bad arguments");
+  return launch_pack_input(x, c_in == 4 ? y : nullptr, batch, n_frames, f_in, f_used, c_in, out, as_stream(stream));
+}
+extern "C" int fdbm_im2col_input(const float* in, int c_in, int batch, int n_frames, int n_freq, void* out_h16, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(in && out_h16 && batch > 0 && n_frames > 0 && n_freq > 0, "fdbm_im2col_input: bad arguments");
+  return launch_im2col_input(in, c_in, batch, n_frames, n_freq, reinterpret_cast<op_t*>(out_h16), as_stream(stream));
+}
+extern "C" int fdbm_combine(float* h, const float* pyramid, int c_pyr, const float* weight, const float* bias, int batch, int n_frames, int n_freq,
+                            int channels, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(h && pyramid && weight && bias && batch > 0 && n_frames > 0 && n_freq > 0 && c_pyr >= 1, "fdbm_combine: bad arguments");
+  return launch_combine(h, pyramid, c_pyr, weight, bias, batch, n_frames, n_freq, channels, as_stream(stream));
+}
+extern "C" int fdbm_output_layer(const float* pyramid, int c_pyr, const float* weight, const float* bias, int batch, int n_frames, int n_freq,
+                                 int f_out, float* out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(pyramid && weight && bias && out && batch > 0 && n_frames > 0 && n_freq > 0 && f_out >= n_freq && c_pyr >= 1 && c_pyr <= 4,
+               "fdbm_output_layer: bad arguments");
+  return launch_output_layer(pyramid, c_pyr, weight, bias, batch, n_frames, n_freq, f_out, out, as_stream(stream));
+}

@@ -351,6 +351,21 @@ int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B,
 
 using namespace fdbm;
 
+// time embedding (layerspp.py:32-41, ncsnpp_v2.py:252-270): out[b] = SiLU(W2 SiLU(W1 [sin, cos](2 pi W log t_b) + b1) + b2), [B, 4 nf]
+// (every consumer is `Dense_0(act(temb))`, so the activated vector is what is kept)
+extern "C" int fdbm_time_embedding(const float* t, const float* fourier_w, int nf, const float* w1, const float* b1, const float* w2,
+                                   const float* b2, int batch, float* out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(t && fourier_w && w1 && b1 && w2 && b2 && out && batch > 0 && nf > 0 && nf <= 1024, "fdbm_time_embedding: bad arguments");
+  return launch_temb(t, fourier_w, nf, w1, b1, w2, b2, batch, 1, out, as_stream(stream));
+}
+// the FiLM rows of all residual blocks at once (layerspp.py:263 `Dense_0(act(temb))`, 49 layers): out[b][r] = w[r] . act[b] + bias[r]
+extern "C" int fdbm_film_rows(const float* temb_act, const float* weight, const float* bias, int batch, int k, int rows, float* out, void* stream) {
+  if (int rc = require_sm100()) return rc;
+  FDBM_REQUIRE(temb_act && weight && bias && out && batch > 0 && k > 0 && k <= 1536 && rows > 0, "fdbm_film_rows: bad arguments");
+  return launch_dense_all(temb_act, weight, bias, batch, k, rows, out, as_stream(stream));
+}
+
 extern "C" int fdbm_attention(const void* q, const void* k, const void* v, int batch, int L, int C, void* o,
                               void* stream) {
   if (int rc = require_sm100()) return rc;

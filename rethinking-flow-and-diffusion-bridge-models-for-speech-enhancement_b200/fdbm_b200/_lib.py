@@ -34,6 +34,7 @@ EXPORTS = [
     "fdbm_plan_num_backward_launches", "fdbm_plan_optimizer_step", "fdbm_plan_profile_backward", "fdbm_plan_repack_weights",
     "fdbm_plan_reset_optimizer", "fdbm_plan_optimizer_state", "fdbm_plan_set_optimizer_state", "fdbm_plan_swap_ema",
     "fdbm_hybrid_loss_workspace_bytes", "fdbm_hybrid_loss", "fdbm_data_prediction_loss",
+    "fdbm_pack_input", "fdbm_im2col_input", "fdbm_time_embedding", "fdbm_film_rows", "fdbm_combine", "fdbm_output_layer",
     "fdbm_mel_tables_bytes", "fdbm_mel_tables_init", "fdbm_mel_loss_workspace_bytes", "fdbm_mel_loss",
     "fdbm_tfg_lstm_pack_bytes", "fdbm_tfg_lstm_pack", "fdbm_tfg_lstm_sweep", "fdbm_tfg_pad_add_norm", "fdbm_tfg_sweep_post",
     "fdbm_tfg_input", "fdbm_tfg_time_embedding", "fdbm_tfg_attention_workspace_bytes", "fdbm_tfg_attention", "fdbm_tfg_output",
@@ -115,6 +116,12 @@ def load() -> C.CDLL:
         "fdbm_hybrid_loss_workspace_bytes": (i64, [i, i, i, i]),
         "fdbm_hybrid_loss": (i, [p, p, i, i, p, i, i, i, f, f, f, p, p, p, p]),
         "fdbm_data_prediction_loss": (i, [p, p, i, i, p, i, i, i, f, f, f, f, p, p, p, p]),
+        "fdbm_pack_input": (i, [p, p, i, i, i, i, i, p, p]),
+        "fdbm_im2col_input": (i, [p, i, i, i, i, p, p]),
+        "fdbm_time_embedding": (i, [p, p, i, p, p, p, p, i, p, p]),
+        "fdbm_film_rows": (i, [p, p, p, i, i, i, p, p]),
+        "fdbm_combine": (i, [p, p, i, p, p, i, i, i, i, p]),
+        "fdbm_output_layer": (i, [p, i, p, p, i, i, i, i, p, p]),
         "fdbm_mel_tables_bytes": (i64, []),
         "fdbm_mel_tables_init": (i, [p, i, p]),
         "fdbm_mel_loss_workspace_bytes": (i64, [i, i, i, i]),

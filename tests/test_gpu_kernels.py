@@ -477,3 +477,90 @@ def test_conv_dgrad(lib, B, T, Fq, Cin, k, Cout):
     torch.cuda.synchronize()
     err = rel_l2(ntfc_to_nchw(acc).cpu(), ref)
     assert err < 2e-5, f"dgrad differs from autograd: rel L2 {err}"
+
+
+# ------------------------------------------------------------------------------------------------
+# the skinny layers of NCSN++ at kernel level, against the torch ops the reference runs
+# ------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("c_in", [4, 2])
+def test_pack_and_im2col_input_first_convolution(lib, c_in):
+    """ncsnpp_v2.py:247-250 + :278 (ncsnpp_v2_predictive.py for 2 channels): input packing (bit-exact), the im2col K-block (exact up to
+    the 16-bit rounding of its entries) and the whole 3x3 input convolution through fdbm_conv_igemm against F.conv2d."""
+    g = torch.Generator().manual_seed(11)
+    B, T, Fb, nf = 2, 48, 257, 128
+    x = torch.view_as_complex(torch.randn(B, 1, Fb, T, 2, generator=g)).cuda()
+    y = torch.view_as_complex(torch.randn(B, 1, Fb, T, 2, generator=g)).cuda()
+    packed = torch.empty(B, T, 256, c_in, device="cuda")
+    _check(lib, lib.fdbm_pack_input(torch.view_as_real(x).data_ptr(), torch.view_as_real(y).data_ptr() if c_in == 4 else None, B, T, Fb, 256, c_in,
+                                    packed.data_ptr(), _stream()))
+    parts = (x.real, x.imag, y.real, y.imag) if c_in == 4 else (x.real, x.imag)
+    h_in = torch.cat(parts, dim=1)[:, :, :256, :]                                # [B, c_in, 256, T]
+    assert torch.equal(packed, nchw_to_ntfc(h_in))
+    cols = torch.empty(B, T, 256, 64, dtype=_h16(), device="cuda")
+    _check(lib, lib.fdbm_im2col_input(packed.data_ptr(), c_in, B, T, 256, cols.data_ptr(), _stream()))
+    ref_cols = F.unfold(h_in, 3, padding=1).reshape(B, c_in, 9, 256, T)           # [B, ci, kf*3+kt, F, T]
+    ref_cols = ref_cols.permute(0, 4, 3, 2, 1).reshape(B, T, 256, 9 * c_in)       # k = tap * c_in + ci
+    torch.cuda.synchronize()
+    assert torch.equal(cols[..., :9 * c_in].float(), ref_cols.to(_h16()).float()) and not cols[..., 9 * c_in:].any()
+    # the convolution: weights OIHW (H = frequency, W = frames) packed with ksize -2, one 64-wide K-block
+    w = (torch.randn(nf, c_in, 3, 3, generator=g) * 0.2).cuda(); bias = torch.randn(nf, generator=g).cuda()
+    nb = C.c_int64(); lib.fdbm_pack_conv_weights(None, c_in, -2, None, 0, nf, None, C.byref(nb), None)
+    wp = torch.empty(nb.value // 2, dtype=_h16(), device="cuda")
+    _check(lib, lib.fdbm_pack_conv_weights(w.data_ptr(), c_in, -2, None, 0, nf, wp.data_ptr(), C.byref(nb), _stream()))
+    out = torch.empty(B, T, 256, nf, device="cuda")
+    _check(lib, lib.fdbm_conv_igemm(cols.data_ptr(), 64, 1, None, 0, wp.data_ptr(), bias.data_ptr(), None, None, 1.0, B, T, 256, nf,
+                                    out.data_ptr(), None, None, _stream()))
+    want = F.conv2d(h_in, w, bias, padding=1)
+    err = rel_l2(ntfc_to_nchw(out), want)
+    print(f"input convolution {c_in} -> {nf}: rel L2 {err:.2e}")
+    assert err < 1e-3
+
+
+def test_time_embedding_and_film_rows(lib):
+    """layerspp.py:32-41 + ncsnpp_v2.py:252-270 + layerspp.py:263: Fourier features of log t, the two-layer MLP, and all Dense_0 FiLM
+    rows at once, in fp32 against the same torch ops."""
+    g = torch.Generator().manual_seed(12)
+    B, nf, rows = 5, 128, 49 * 128 + 64
+    t = (0.03 + 0.97 * torch.rand(B, generator=g)).cuda()
+    W = (torch.randn(nf, generator=g) * 16).cuda()
+    w1 = (torch.randn(4 * nf, 2 * nf, generator=g) * 0.05).cuda(); b1 = torch.randn(4 * nf, generator=g).cuda() * 0.1
+    w2 = (torch.randn(4 * nf, 4 * nf, generator=g) * 0.05).cuda(); b2 = torch.randn(4 * nf, generator=g).cuda() * 0.1
+    act = torch.empty(B, 4 * nf, device="cuda")
+    _check(lib, lib.fdbm_time_embedding(t.data_ptr(), W.data_ptr(), nf, w1.data_ptr(), b1.data_ptr(), w2.data_ptr(), b2.data_ptr(), B,
+                                        act.data_ptr(), _stream()))
+    proj = torch.log(t)[:, None] * W[None, :] * 2 * np.pi
+    emb = torch.cat([torch.sin(proj), torch.cos(proj)], dim=-1)
+    temb = F.linear(F.silu(F.linear(emb, w1, b1)), w2, b2)
+    want = F.silu(temb)
+    e1 = rel_l2(act, want)
+    dw = (torch.randn(rows, 4 * nf, generator=g) * 0.05).cuda(); db = torch.randn(rows, generator=g).cuda()
+    film = torch.empty(B, rows, device="cuda")
+    _check(lib, lib.fdbm_film_rows(act.data_ptr(), dw.data_ptr(), db.data_ptr(), B, 4 * nf, rows, film.data_ptr(), _stream()))
+    e2 = rel_l2(film, F.linear(act, dw, db))
+    print(f"time embedding rel L2 {e1:.2e}, FiLM rows {e2:.2e}")
+    # |2 pi W log t| reaches ~1e2 rad: an fp32 rounding of the argument is ~1e-5 rad, which is what sin / cos can agree to
+    assert e1 < 2e-4 and e2 < 1e-5
+
+
+@pytest.mark.parametrize("c_pyr", [4, 2])
+def test_combine_and_output_layer(lib, c_pyr):
+    """layerspp.py:52-59 (Combine, 'sum') and ncsnpp_v2.py:392-399 (output 1x1 convolution, un-packing to the complex layout with the
+    zero Nyquist row) against F.conv2d."""
+    g = torch.Generator().manual_seed(13)
+    B, T, Fq, Cc = 2, 40, 64, 256
+    h = torch.randn(B, Cc, Fq, T, generator=g).cuda(); pyr = torch.randn(B, c_pyr, Fq, T, generator=g).cuda()
+    w = (torch.randn(Cc, c_pyr, 1, 1, generator=g) * 0.3).cuda(); b = torch.randn(Cc, generator=g).cuda()
+    hk = nchw_to_ntfc(h); pk = nchw_to_ntfc(pyr)
+    _check(lib, lib.fdbm_combine(hk.data_ptr(), pk.data_ptr(), c_pyr, w.reshape(Cc, c_pyr).contiguous().data_ptr(), b.data_ptr(), B, T, Fq, Cc, _stream()))
+    e1 = rel_l2(ntfc_to_nchw(hk), F.conv2d(pyr, w, b) + h)
+    T2, Fq2 = 72, 256
+    pyr2 = torch.randn(B, c_pyr, Fq2, T2, generator=g).cuda()
+    wo = (torch.randn(2, c_pyr, 1, 1, generator=g) * 0.5).cuda(); bo = torch.randn(2, generator=g).cuda()
+    out = torch.full((B, 1, 257, T2), 7.0, dtype=torch.complex64, device="cuda")
+    _check(lib, lib.fdbm_output_layer(nchw_to_ntfc(pyr2).data_ptr(), c_pyr, wo.reshape(2, c_pyr).contiguous().data_ptr(), bo.data_ptr(), B, T2, Fq2, 257,
+                                      torch.view_as_real(out).data_ptr(), _stream()))
+    o = F.conv2d(pyr2, wo, bo)
+    want = torch.view_as_complex(o.permute(0, 2, 3, 1).contiguous())[:, None]
+    e2 = rel_l2(out[:, :, :256], want)
+    print(f"combine rel L2 {e1:.2e}, output layer {e2:.2e}")
+    assert e1 < 1e-6 and e2 < 1e-6 and not torch.view_as_real(out[:, :, 256]).any()
