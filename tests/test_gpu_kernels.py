@@ -510,7 +510,7 @@ def test_pack_and_im2col_input_first_convolution(lib, c_in):
     out = torch.empty(B, T, 256, nf, device="cuda")
     _check(lib, lib.fdbm_conv_igemm(cols.data_ptr(), 64, 1, None, 0, wp.data_ptr(), bias.data_ptr(), None, None, 1.0, B, T, 256, nf,
                                     out.data_ptr(), None, None, _stream()))
-    want = F.conv2d(h_in, w, bias, padding=1)
+    want = F.conv2d(h_in.double(), w.double(), bias.double(), padding=1).float()
     err = rel_l2(ntfc_to_nchw(out), want)
     print(f"input convolution {c_in} -> {nf}: rel L2 {err:.2e}")
     assert err < 1e-3
@@ -552,14 +552,15 @@ def test_combine_and_output_layer(lib, c_pyr):
     w = (torch.randn(Cc, c_pyr, 1, 1, generator=g) * 0.3).cuda(); b = torch.randn(Cc, generator=g).cuda()
     hk = nchw_to_ntfc(h); pk = nchw_to_ntfc(pyr)
     _check(lib, lib.fdbm_combine(hk.data_ptr(), pk.data_ptr(), c_pyr, w.reshape(Cc, c_pyr).contiguous().data_ptr(), b.data_ptr(), B, T, Fq, Cc, _stream()))
-    e1 = rel_l2(ntfc_to_nchw(hk), F.conv2d(pyr, w, b) + h)
+    # (fp64 references: cuDNN convolutions run in TF32 by default, these kernels are fp32 FMA)
+    e1 = rel_l2(ntfc_to_nchw(hk), (F.conv2d(pyr.double(), w.double(), b.double()) + h.double()).float())
     T2, Fq2 = 72, 256
     pyr2 = torch.randn(B, c_pyr, Fq2, T2, generator=g).cuda()
     wo = (torch.randn(2, c_pyr, 1, 1, generator=g) * 0.5).cuda(); bo = torch.randn(2, generator=g).cuda()
     out = torch.full((B, 1, 257, T2), 7.0, dtype=torch.complex64, device="cuda")
     _check(lib, lib.fdbm_output_layer(nchw_to_ntfc(pyr2).data_ptr(), c_pyr, wo.reshape(2, c_pyr).contiguous().data_ptr(), bo.data_ptr(), B, T2, Fq2, 257,
                                       torch.view_as_real(out).data_ptr(), _stream()))
-    o = F.conv2d(pyr2, wo, bo)
+    o = F.conv2d(pyr2.double(), wo.double(), bo.double()).float()
     want = torch.view_as_complex(o.permute(0, 2, 3, 1).contiguous())[:, None]
     e2 = rel_l2(out[:, :, :256], want)
     print(f"combine rel L2 {e1:.2e}, output layer {e2:.2e}")
