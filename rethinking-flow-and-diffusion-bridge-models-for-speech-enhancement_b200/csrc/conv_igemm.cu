@@ -61,6 +61,9 @@ constexpr int A_TILE1_BYTES = TILE_T * TILE_F * 128;           // 1-tap segments
 // 512 threads start at 128 registers each; setmaxnreg moves registers from the pipeline and transform
 // warpgroups to the two epilogue warpgroups (128 * (56 + 120 + 2 * 168) = 65536)
 constexpr int PIPE_REGS = 56, EPI_REGS = 168, XFORM_REGS = 120;
+#ifndef FDBM_SIDE_RING_DEFAULT
+#define FDBM_SIDE_RING_DEFAULT 1   // fused 1x1 shortcut operands on their own A slot (FDBM_SIDE_RING=0 in the environment: A/B against the single ring)
+#endif
 #ifndef FDBM_EPI_RES2
 #define FDBM_EPI_RES2 1          // 16-bit shortcut rows double-buffered in registers (0: the single-buffer epilogue, 10 % slower on Conv_1)
 #endif
@@ -90,6 +93,10 @@ struct ConvParams {
   uint32_t ksched[MAX_KB];
   int tiles_t, tiles_f, n_mtiles, n_nblocks, n_items;
   int bn;                                  // MMA N = output channels per item: 128, or 16 for the C -> 4 pyramid convolutions
+  // side ring (fused 1x1 shortcut operands): ksched[0 .. n_main) are the main-ring K-blocks, the rest 1-tap blocks without halo
+  // that travel through A stage A_STAGES - 1 on their own (the main ring then has A_STAGES - 1 stages); in MMA order one of
+  // them follows every side_gap main taps.  n_steps = weight tiles per item.
+  int side_ring, n_main, side_gap, n_steps;
   const float* bias;
   const float* bias_b;
   int bias_b_stride;
@@ -121,6 +128,22 @@ __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int mi) {
   return c;
 }
 
+// MMA-order walk over the weight tiles (= steps) of one item when the 1-tap blocks run on the side ring: the main K-blocks tap
+// by tap, a side block after every side_gap main taps, what is left of them at the end.  f(side, ksched index, tap, taps of the block).
+template <typename F>
+__device__ __forceinline__ void walk_steps(const ConvParams& p, F&& f) {
+  const int n_side = p.n_kb - p.n_main;
+  int sd = 0, cnt = 0;
+  for (int m = 0; m < p.n_main; ++m) {
+    const int ntaps = p.seg[p.ksched[m] & 15].taps;
+    for (int tap = 0; tap < ntaps; ++tap) {
+      f(false, m, tap, ntaps);
+      if (++cnt == p.side_gap && sd < n_side) { f(true, p.n_main + sd, 0, 1); ++sd; cnt = 0; }
+    }
+  }
+  for (; sd < n_side; ++sd) f(true, p.n_main + sd, 0, 1);
+}
+
 // COMB: the epilogue also applies the Combine 1x1 convolution of the input pyramid (kept out of the standard
 // instantiation: even as a not-taken branch it doubled the epilogue's time).
 // RES16: the identity-shortcut operand is the 16-bit copy of the residual stream (inference plans)
@@ -147,7 +170,12 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   const int b_stride = p.bn * 128;                        // bytes per weight slot
   uint64_t* acc_empty = acc_full + 2;
   uint64_t* a_ready = acc_empty + 2;                   // A stage transformed (or passed through) -> MMA may read it
-  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(a_ready + A_STAGES);
+  uint64_t* side_full = a_ready + A_STAGES;            // side ring (one slot = both tiles of a 1-tap K-block)
+  uint64_t* side_empty = side_full + 1;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(side_empty + 1);
+  static_assert((3 * A_STAGES + 2 * B_STAGES_NARROW + 4 + 2) * 8 + 4 <= 512, "barrier region");
+  const int a_stages = p.side_ring ? A_STAGES - 1 : A_STAGES;      // main-ring depth
+  const int n_main = p.side_ring ? p.n_main : p.n_kb;
 
   // warp index through a shuffle: the compiler then knows it is warp-uniform, keeps the role branches and everything
   // derived from them on the uniform datapath (no per-access R2UR of the memory descriptor in the epilogue)
@@ -158,6 +186,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     for (int i = 0; i < A_STAGES; ++i) { mbar_init(a_full + i, 1); mbar_init(a_empty + i, 1); mbar_init(a_ready + i, 128); }
     for (int i = 0; i < B_STAGES_NARROW; ++i) { mbar_init(b_full + i, 1); mbar_init(b_empty + i, 1); }
     for (int i = 0; i < 2; ++i) { mbar_init(acc_full + i, 1); mbar_init(acc_empty + i, 4 * EPI_GROUPS); }
+    mbar_init(side_full, 1); mbar_init(side_empty, 1);
     fence_barrier_init();
   }
   if (warp == 0 && lane == 0) {
@@ -186,7 +215,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
         TileCoord tc[MT];
         int n_valid = 0;
         for (int j = 0; j < MT; ++j) { tc[j] = decode_tile(p, ct * MT + j); n_valid += tc[j].valid; }
-        for (int i = 0; i < n_kb; ++i) {
+        for (int i = 0; i < n_main; ++i) {
           const uint32_t e = p.ksched[i];
           const int sgi = e & 15, c0 = ((e >> 4) & 0xFFF) * 64;
           const int halo = p.seg[sgi].halo;
@@ -198,7 +227,33 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
             tma_load_4d(sA + (stage * MT + j) * A_TILE_STRIDE, map, a_full + stage, c0, tc[j].f0 - halo, tc[j].t0 - halo,
                         tc[j].b);
           }
-          if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+          if (++stage == a_stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 3) {
+    // ------------------------------------------------------------------ side-ring producer (fused 1x1 shortcut operands)
+    // A 1-tap K-block is 0.35 us of MMA work behind ~1.2 us of TMA latency: in the main ring four of them in a row starved the
+    // MMA warp and kept the next item's first 9-tap block from being requested (5 us of a 14 us item).  Here they have their own
+    // slot (the third A stage), are requested as soon as the previous one is consumed and are consumed between the 9-tap taps.
+    if (lane == 0 && p.side_ring) {
+      uint32_t phase = 0;
+      for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
+        const int ct = item / p.n_nblocks;
+        TileCoord tc[MT];
+        int n_valid = 0;
+        for (int j = 0; j < MT; ++j) { tc[j] = decode_tile(p, ct * MT + j); n_valid += tc[j].valid; }
+        for (int i = n_main; i < n_kb; ++i) {
+          const uint32_t e = p.ksched[i];
+          const int sgi = e & 15, c0 = ((e >> 4) & 0xFFF) * 64;
+          mbar_wait_relaxed<128>(side_empty, phase ^ 1);
+          mbar_expect_tx(side_full, n_valid * A_TILE1_BYTES);
+          const CUtensorMap* map = sgi == 0 ? &map_a0 : (sgi == 1 ? &map_a1 : &map_a2);
+          for (int j = 0; j < MT; ++j) {
+            if (!tc[j].valid) continue;
+            tma_load_4d(sA + ((A_STAGES - 1) * MT + j) * A_TILE_STRIDE, map, side_full, c0, tc[j].f0, tc[j].t0, tc[j].b);
+          }
+          phase ^= 1;
         }
       }
     }
@@ -208,6 +263,16 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
         const int n0 = (item % p.n_nblocks) * BN;
+        if (p.side_ring) {                                   // weight tiles in MMA order
+          walk_steps(p, [&](bool, int idx, int tap, int) {
+            const int kt = static_cast<int>(p.ksched[idx] >> 16) + tap;
+            mbar_wait_relaxed<128>(b_empty + stage, phase ^ 1);
+            mbar_expect_tx(b_full + stage, b_stride);
+            tma_load_2d(sB + stage * b_stride, &map_b, b_full + stage, 0, kt * p.Cout + n0);
+            if (++stage == b_stages) { stage = 0; phase ^= 1; }
+          });
+          continue;
+        }
         for (int i = 0; i < n_kb; ++i) {
           const uint32_t e = p.ksched[i];
           const int ntaps = p.seg[e & 15].taps;
@@ -232,7 +297,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const uint64_t b_hi = make_desc_sw128(0, 1024) & 0xFFFFFFFF00000000ull;
     const uint32_t lo_const = 1u << 16;                                   // LBO field (unused by swizzled K-major)
     const uint32_t sA_lo = (smem_u32(sA) & 0x3FFFF) >> 4, sB_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
-    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0;
+    uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0, ps = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
       const int ct = item / p.n_nblocks;
       const bool valid1 = (ct * MT + 1) < p.n_mtiles;                    // M-tile 0 of an item is always valid
@@ -240,6 +305,54 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       fence_after_sync();
       uint32_t accumulate = 0;
       const uint32_t d0 = tmem_base + (as * MT) * BN, d1 = d0 + BN;
+      if (p.side_ring) {
+        int step = 0;
+        walk_steps(p, [&](bool side, int idx, int tap, int ntaps) {
+          const SegParams& sg = p.seg[p.ksched[idx] & 15];
+          uint32_t a_base0, a_off = 0;
+          if (side) {
+            mbar_wait(side_full, ps);
+            fence_after_sync();
+            a_base0 = sA_lo + (((A_STAGES - 1) * MT) * A_TILE_STRIDE >> 4);
+          } else {
+            if (tap == 0) {
+              mbar_wait(sg.norm ? a_ready + sa : a_full + sa, pa);
+              fence_after_sync();
+            }
+            a_base0 = sA_lo + ((sa * MT) * A_TILE_STRIDE >> 4);
+            const int df = ntaps == 9 ? tap / 3 : sg.halo, dt = ntaps == 9 ? tap - 3 * (tap / 3) : sg.halo;
+            a_off = ((dt * HALO_F + df) * 128) >> 4;
+          }
+          const uint64_t a_hi = sg.halo ? a_hi9 : a_hi1;
+          mbar_wait(b_full + sb, pb);
+          fence_after_sync();
+          const uint32_t b_lo = (sB_lo + (sb * b_stride >> 4)) | lo_const;
+          const uint32_t a_lo0 = (a_base0 + a_off) | lo_const, a_lo1 = (a_base0 + (A_TILE_STRIDE >> 4) + a_off) | lo_const;
+          const bool last_tap = tap == ntaps - 1;
+          if (elect_one()) {
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+              mma_f16(d0, a_hi | (a_lo0 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
+            if (valid1) {
+#pragma unroll
+              for (int k = 0; k < 4; ++k)
+                mma_f16(d1, a_hi | (a_lo1 + 2 * k), b_hi | (b_lo + 2 * k), idesc, k == 0 ? accumulate : 1u);
+            }
+            mma_commit(b_empty + sb);
+            if (side) mma_commit(side_empty);
+            else if (last_tap) mma_commit(a_empty + sa);
+            if (step == p.n_steps - 1) mma_commit(acc_full + as);
+          }
+          __syncwarp();
+          accumulate = 1;
+          ++step;
+          if (++sb == b_stages) { sb = 0; pb ^= 1; }
+          if (side) ps ^= 1;
+          else if (last_tap && ++sa == a_stages) { sa = 0; pa ^= 1; }
+        });
+        if (++as == 2) { as = 0; pacc ^= 1; }
+        continue;
+      }
       for (int i = 0; i < n_kb; ++i) {
         const SegParams& sg = p.seg[p.ksched[i] & 15];
         const int ntaps = sg.taps;
@@ -315,7 +428,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       const int ct = item / p.n_nblocks;
       TileCoord tc[MT];
       for (int j = 0; j < MT; ++j) tc[j] = decode_tile(p, ct * MT + j);
-      for (int i = 0; i < n_kb; ++i) {
+      for (int i = 0; i < n_main; ++i) {
         const uint32_t e = p.ksched[i];
         const SegParams& sg = p.seg[e & 15];
         float2 sc[MT][4], sh[MT][4];                      // (scale, shift) of channel pairs: packed fp32x2 affine
@@ -412,7 +525,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           fence_proxy_async();                            // generic-proxy writes -> visible to the tensor core's async proxy
         }
         mbar_arrive(a_ready + stage);
-        if (++stage == A_STAGES) { stage = 0; phase ^= 1; }
+        if (++stage == a_stages) { stage = 0; phase ^= 1; }
       }
     }
   } else {
@@ -1001,8 +1114,8 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
         kt += a.seg[i].taps;
       }
     // 9-tap blocks first, back to back: the load + transform of each one hides behind the nine taps of the previous
-    // one.  (Interleaving the 1-tap blocks between them was measured 5 % slower: the next 9-tap block then has only
-    // two short blocks of MMA work to hide behind.)
+    // one.  (Interleaving the 1-tap blocks between them IN THE SAME RING was measured 5 % slower: the next 9-tap block then
+    // has only two short blocks of MMA work to hide behind.  The side ring below interleaves them without that cost.)
     // FDBM_KSCHED (measurement aid): 1 = 1-tap blocks first, 2 = 1-tap blocks after the first 9-tap block
     static const int order = getenv("FDBM_KSCHED") ? atoi(getenv("FDBM_KSCHED")) : 0;
     int n = 0;
@@ -1018,6 +1131,14 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
       for (int i = 0; i < n1; ++i) p.ksched[n++] = one[i];
     }
     for (; n < MAX_KB; ++n) p.ksched[n] = 0;
+    // side ring: every 1-tap block is a raw operand without halo (the fused 1x1 shortcut) and there is 9-tap work to hide behind
+    bool side_ok = order == 0 && n1 > 0 && n9 > 0;
+    for (int i = 0; i < a.n_seg; ++i) side_ok = side_ok && (a.seg[i].taps == 9 || !p.seg[i].halo);
+    static const int side_env = getenv("FDBM_SIDE_RING") ? atoi(getenv("FDBM_SIDE_RING")) : FDBM_SIDE_RING_DEFAULT;
+    p.side_ring = side_ok && side_env ? 1 : 0;
+    p.n_main = p.side_ring ? n9 : kb;
+    p.side_gap = p.side_ring ? std::max(3, ceil_div(9 * n9, n1)) : 0;
+    p.n_steps = n_kt;
   }
   if (int rc = make_weight_map(&map_b, a.wpack, static_cast<int64_t>(n_kt) * a.Cout, bn)) return rc;
   p.bn = bn;
