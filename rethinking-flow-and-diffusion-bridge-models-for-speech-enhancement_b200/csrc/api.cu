@@ -1,6 +1,7 @@
 // Error reporting and device checks behind the C ABI (include/fdbm_b200.h).
 #include <stdarg.h>
 #include "common.cuh"
+#include <stdlib.h>
 
 namespace fdbm {
 
@@ -51,6 +52,11 @@ int num_sms() {
   if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return 148;
   if (g_sms[dev] == 0) require_sm100();
   return g_sms[dev] > 0 ? g_sms[dev] : 148;
+}
+
+bool pdl_enabled() {
+  static const bool on = !(getenv("FDBM_PDL") && atoi(getenv("FDBM_PDL")) == 0);
+  return on;
 }
 
 }  // namespace fdbm

@@ -203,6 +203,10 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
   __syncthreads();
   fence_after_sync();
   const uint32_t tmem_base = *tmem_slot;
+  // programmatic dependent launch: everything above (barrier init, descriptor prefetch, TMEM allocation) may overlap the tail of
+  // the previous kernel in the stream; its results are only touched after this point.  The next kernel may start launching now.
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
 
   if (warp < 4) {
   reg_dec<PIPE_REGS>();
@@ -1157,9 +1161,17 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
     if (!a.sums_prezeroed) FDBM_CUDA(cudaMemsetAsync(a.sums, 0, sizeof(double) * 2 * a.B * a.Cout, s));
   }
   const int grid = std::min(p.n_items, num_sms());
-  if (a.comb_pyr) conv_igemm_kernel<true, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
-  else if (a.residual_h16) conv_igemm_kernel<false, true><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
-  else conv_igemm_kernel<false, false><<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_a[0], map_a[1], map_a[2], map_b, p);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(grid); cfg.blockDim = dim3(NUM_THREADS); cfg.dynamicSmemBytes = SMEM_BYTES; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  // measured: 256 x 4 s utterances 1321-1323 -> 1307 audio-s/s WITH the attribute, one utterance 18.78 -> 18.28 ms: it pays where the
+  // launches are short (launch-bound small batches), so it is only requested there
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && a.B <= 8 ? 1 : 0;
+  if (a.comb_pyr) FDBM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, map_a[0], map_a[1], map_a[2], map_b, p));
+  else if (a.residual_h16) FDBM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, map_a[0], map_a[1], map_a[2], map_b, p));
+  else FDBM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, map_a[0], map_a[1], map_a[2], map_b, p));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

@@ -413,6 +413,8 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
                    float2* __restrict__ table, int blk_real) {
   __shared__ double2 s_sq[GN_MAXC];
   __shared__ float s_mean[32], s_rstd[32];
+  asm volatile("griddepcontrol.wait;" ::: "memory");            // programmatic dependent launch: the producer's sums are final from here
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const int C = C1 + C2, b = blockIdx.x;
   const int Cr = blk_real ? C / 128 * blk_real : C;
   const int G = min(Cr / 4, 32), cpg = Cr / G;
@@ -465,7 +467,13 @@ int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2,
                "gn_finalize: channel_block_real %d needs 128-channel blocks (%d+%d)", blk_real, C1, C2);
   const int Cr = blk_real ? C / 128 * blk_real : C;
   FDBM_REQUIRE(Cr % std::min(Cr / 4, 32) == 0 && C >= 4 && C <= GN_MAXC, "gn_finalize: unsupported channels %d+%d", C1, C2);
-  gn_finalize_kernel<<<B, 256, 0, s>>>(sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table, blk_real);
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(B); cfg.blockDim = dim3(256); cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && B <= 8 ? 1 : 0;      // small batches only, see launch_conv_igemm
+  FDBM_CUDA(cudaLaunchKernelEx(&cfg, gn_finalize_kernel, sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table, blk_real));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
