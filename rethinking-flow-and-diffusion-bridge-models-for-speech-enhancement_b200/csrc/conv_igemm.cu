@@ -92,6 +92,9 @@ struct ConvParams {
   // K-block schedule: entry i = segment | channel block << 4 | first weight tile (kt) << 16
   uint32_t ksched[MAX_KB];
   int tiles_t, tiles_f, n_mtiles, n_nblocks, n_items;
+  // ceil(2^32 / d) of the three divisors the persistent loops divide by (every role decodes item -> tile -> (b, t0, f0) per item;
+  // the compiler's 32-bit division is ~35 instructions each: 16 % of the epilogue's instructions went there)
+  uint32_t mg_tiles_t, mg_tiles_f, mg_nblocks;
   int bn;                                  // MMA N = output channels per item: 128, or 16 for the C -> 4 pyramid convolutions
   // side ring (fused 1x1 shortcut operands): ksched[0 .. n_main) are the main-ring K-blocks, the rest 1-tap blocks without halo
   // that travel through A stage A_STAGES - 1 on their own (the main ring then has A_STAGES - 1 stages); in MMA order one of
@@ -117,14 +120,19 @@ struct ConvParams {
 
 struct TileCoord { int b, t0, f0; bool valid; };
 
+// n / d for n * d < 2^32 (host-checked) with mg = ceil(2^32 / d): one IMAD.HI; d == 1 has no 32-bit multiplier
+__device__ __forceinline__ int fast_div(int n, int d, uint32_t mg) { return d == 1 ? n : static_cast<int>(__umulhi(static_cast<uint32_t>(n), mg)); }
+__device__ __forceinline__ int item_tile(const ConvParams& p, int item) { return fast_div(item, p.n_nblocks, p.mg_nblocks); }
+__device__ __forceinline__ int item_nblk(const ConvParams& p, int item) { return item - item_tile(p, item) * p.n_nblocks; }
+
 __device__ __forceinline__ TileCoord decode_tile(const ConvParams& p, int mi) {
   TileCoord c;
   c.valid = mi < p.n_mtiles;
-  const int tt = mi % p.tiles_t;
-  const int rest = mi / p.tiles_t;
+  const int rest = fast_div(mi, p.tiles_t, p.mg_tiles_t);
+  const int tt = mi - rest * p.tiles_t;
   c.t0 = tt * TILE_T;
-  c.f0 = (rest % p.tiles_f) * TILE_F;
-  c.b = rest / p.tiles_f;
+  c.b = fast_div(rest, p.tiles_f, p.mg_tiles_f);
+  c.f0 = (rest - c.b * p.tiles_f) * TILE_F;
   return c;
 }
 
@@ -215,7 +223,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int ct = item / p.n_nblocks;
+        const int ct = item_tile(p, item);
         TileCoord tc[MT];
         int n_valid = 0;
         for (int j = 0; j < MT; ++j) { tc[j] = decode_tile(p, ct * MT + j); n_valid += tc[j].valid; }
@@ -243,7 +251,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (lane == 0 && p.side_ring) {
       uint32_t phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int ct = item / p.n_nblocks;
+        const int ct = item_tile(p, item);
         TileCoord tc[MT];
         int n_valid = 0;
         for (int j = 0; j < MT; ++j) { tc[j] = decode_tile(p, ct * MT + j); n_valid += tc[j].valid; }
@@ -266,7 +274,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     if (lane == 0) {
       uint32_t stage = 0, phase = 0;
       for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-        const int n0 = (item % p.n_nblocks) * BN;
+        const int n0 = item_nblk(p, item) * BN;
         if (p.side_ring) {                                   // weight tiles in MMA order
           walk_steps(p, [&](bool, int idx, int tap, int) {
             const int kt = static_cast<int>(p.ksched[idx] >> 16) + tap;
@@ -303,7 +311,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     const uint32_t sA_lo = (smem_u32(sA) & 0x3FFFF) >> 4, sB_lo = (smem_u32(sB) & 0x3FFFF) >> 4;
     uint32_t sa = 0, pa = 0, sb = 0, pb = 0, as = 0, pacc = 0, ps = 0;
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int ct = item / p.n_nblocks;
+      const int ct = item_tile(p, item);
       const bool valid1 = (ct * MT + 1) < p.n_mtiles;                    // M-tile 0 of an item is always valid
       mbar_wait(acc_empty + as, pacc ^ 1);
       fence_after_sync();
@@ -429,7 +437,7 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
     uint32_t stage = 0, phase = 0;
     const bool any_norm = (p.seg[0].norm | p.seg[1].norm | p.seg[2].norm) != 0;   // else: the MMA warp never waits on a_ready
     for (int item = blockIdx.x; any_norm && item < p.n_items; item += gridDim.x) {
-      const int ct = item / p.n_nblocks;
+      const int ct = item_tile(p, item);
       TileCoord tc[MT];
       for (int j = 0; j < MT; ++j) tc[j] = decode_tile(p, ct * MT + j);
       for (int i = 0; i < n_main; ++i) {
@@ -570,8 +578,8 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
       }
     };
     for (int item = blockIdx.x; item < p.n_items; item += gridDim.x) {
-      const int ct = item / p.n_nblocks;
-      const int nblk = item % p.n_nblocks;
+      const int ct = item_tile(p, item);
+      const int nblk = item - ct * p.n_nblocks;
       const int n0 = nblk * BN;
       mbar_wait_relaxed(acc_full + as, pacc);
       fence_after_sync();
@@ -680,8 +688,9 @@ conv_igemm_kernel(const __grid_constant__ CUtensorMap map_a0, const __grid_const
           // pull the NEXT tile's residual rows (512 or 256 B per pixel) into L2 now: by the time its epilogue runs,
           // the register loads below see L2 latency instead of HBM latency
           const int nitem = item + gridDim.x;
-          const int nmi = nitem < p.n_items ? (nitem / p.n_nblocks) * MT + j : p.n_mtiles;
-          const int nblk_n = nitem % p.n_nblocks;
+          const int nct = item_tile(p, nitem);
+          const int nmi = nitem < p.n_items ? nct * MT + j : p.n_mtiles;
+          const int nblk_n = nitem - nct * p.n_nblocks;
           const TileCoord nt = decode_tile(p, nmi);
           const int t = nt.t0 + (et >> 3), f = nt.f0 + (et & 7);
           if (nt.valid && t < p.T && f < p.F) {
@@ -1150,6 +1159,12 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   p.n_mtiles = a.B * p.tiles_t * p.tiles_f;
   p.n_nblocks = a.Cout / bn;
   p.n_items = ceil_div(p.n_mtiles, MT) * p.n_nblocks;
+  {
+    auto magic = [](int d) { return static_cast<uint32_t>((0x100000000ull + d - 1) / static_cast<uint64_t>(d)); };   // d == 1: unused
+    p.mg_tiles_t = magic(p.tiles_t); p.mg_tiles_f = magic(p.tiles_f); p.mg_nblocks = magic(p.n_nblocks);
+    const int64_t dmax = std::max(std::max(p.tiles_t, p.tiles_f), p.n_nblocks);
+    FDBM_REQUIRE((2 * (static_cast<int64_t>(p.n_items) + num_sms()) + 2) * dmax < 0x100000000ll, "conv_igemm: %d items exceed the range of the index arithmetic", p.n_items);
+  }
   p.bias = a.bias; p.bias_b = a.bias_b; p.bias_b_stride = a.bias_b_stride; p.residual = a.residual; p.scale = a.scale;
   p.residual_h16 = a.residual_h16;
   FDBM_REQUIRE(!(a.residual && a.residual_h16) && !(a.residual_h16 && (a.comb_pyr || a.pyr_out)), "conv_igemm: bad residual arguments");
