@@ -104,8 +104,14 @@ __device__ __forceinline__ void load8(const GnBwdArgs& a, int64_t idx8, float (&
 }
 // d SiLU / dy = sg + y sg (1 - sg), sg = sigmoid(y) = 1/2 + tanh(y/2)/2: one MUFU.TANH instead of EX2 + an IEEE division
 // (these passes were instruction-bound, not HBM-bound: the division alone was a third of their instructions)
+#ifndef FDBM_GNBWD_BLOCKS
+#define FDBM_GNBWD_BLOCKS 4      // resident blocks per SM the register allocation must allow
+#endif
+#ifndef FDBM_GNBWD_UNROLL
+#define FDBM_GNBWD_UNROLL 2      // pixels of a thread's lane in flight per loop trip (measured, norm + elementwise part of a 16-crop backward: 1 -> 24.45 ms, 2 -> 24.00; with 3 or 2 blocks per SM and 80 - 96 registers 25.5 - 26.0)
+#endif
 template <bool APPLY>
-__global__ void __launch_bounds__(256, 4)
+__global__ void __launch_bounds__(256, FDBM_GNBWD_BLOCKS)
 gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   __shared__ float s_m1[32], s_m2[32];
   __shared__ float s_red[256 * 16];
@@ -152,6 +158,8 @@ gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
   for (int j = 0; j < 4; ++j) { s1[j] = make_float2(0.f, 0.f); s2[j] = make_float2(0.f, 0.f); }
   const int64_t p0 = static_cast<int64_t>(blockIdx.x) * px_per_block, p1 = min(a.P, p0 + px_per_block);
   if (pl < npl) {
+    constexpr int kUnroll = FDBM_GNBWD_UNROLL;
+#pragma unroll kUnroll
     for (int64_t p = p0 + pl; p < p1; p += npl) {
       const int64_t row = static_cast<int64_t>(b) * a.P + p;
       float xs[8];
