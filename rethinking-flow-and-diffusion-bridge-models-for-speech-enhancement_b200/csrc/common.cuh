@@ -148,18 +148,19 @@ int launch_conv_wgrad(const op_t* dy, int Cout, const op_t* x, int Cin, int ksiz
                       int io_layout, float* dw, float* workspace, cudaStream_t s);
 // ---- training-step passes (train_kernels.cu)
 int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s,
-                        bool acc_first = false);   // acc_first: acc_dst = value instead of +=
+                        bool acc_first = false, bool sums_prezeroed = false);   // acc_first: acc_dst = value instead of +=
 int launch_gn_bwd_reduce(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
                          const float2* tab, const float2* stats, int act, int B, int64_t P, double* S, cudaStream_t s, int b0 = 0);
 // (B, b0): the launch covers utterances b0 .. b0 + B - 1 (all pointers are those of the whole batch)
 int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
                         const float2* tab, const float2* stats, const float* gamma, int act, int B, int64_t P, const double* S,
-                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s, bool acc_first = false, int b0 = 0);
+                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s, bool acc_first = false, int b0 = 0,
+                        bool sums_prezeroed = false);
 int launch_gn_param_grad(const double* S, int B, int C, float inv_scale, float* dgamma, float* dbeta, cudaStream_t s);
 int launch_gn_stats(const double* sums1, int C1, const double* sums2, int C2, int B, int64_t pixels, float2* stats, cudaStream_t s);
 int launch_fir_resample16(const op_t* in, int in_ld, int in_coff, int B, int T, int F, int C, int mode, float scale,
                           op_t* out16, float* acc_dst, cudaStream_t s);
-int launch_col_sums16(const op_t* in, int ld, int c_off, int B, int64_t P, int C, double* sums, cudaStream_t s);
+int launch_col_sums16(const op_t* in, int ld, int c_off, int B, int64_t P, int C, double* sums, cudaStream_t s, bool sums_prezeroed = false);
 int launch_col_sums_to(const double* sums, int B, int C, float inv_scale, float* dst, float* per_b, int per_b_ld, cudaStream_t s);
 int launch_attention_bwd(const op_t* qkv, int B, int L, int C, const op_t* d_o, float* scratch, op_t* g_qkv, cudaStream_t s);
 int launch_adam_ema(float* p, const float* g, float* m, float* v, float* ema, const unsigned char* trainable, int64_t n,
@@ -196,6 +197,16 @@ struct PackDesc {
   long long total;                           // elements this pack writes
   long long first_block;                     // filled by the plan: first block of the batched launch that belongs to this pack
 };
+// Deferred per-channel gradient sums of a training backward: every site leaves its per-(utterance, channel) double sums in its own
+// slice of one pool (zeroed by ONE memset at the start of the backward) and the ~390 tiny reductions into the parameter-gradient
+// buffer (conv / NIN biases, FiLM rows, GroupNorm gamma / beta) run as ONE launch at the end instead of one 4-7 us launch each
+// between the big kernels.  kind 0: src [B,C] -> dst0[c] += inv * sum_b, per_b[b*ld + c] = inv * src[b,c] (optional);
+// kind 1: src [B,C,2] (GroupNorm backward S) -> dst0 = dgamma[c] += inv * sum_b S[b,c,1], dst1 = dbeta[c] += inv * sum_b S[b,c,0]
+struct DeferDesc {
+  const double* src; int B, C, kind;
+  float* dst0; float* dst1; float* per_b; int per_b_ld;
+};
+int launch_deferred_sums(const DeferDesc* descs_dev, int n_descs, float inv_scale, cudaStream_t s);
 constexpr int kPackChunk = 2048;
 PackDesc pack_desc_fwd(const float* w1, int C1, int ksize, const float* w2, int C2, int Cout, int n_rows_total, int row_offset, op_t* wpack);
 PackDesc pack_desc_dgrad(const float* w, int Cout, int Cin, int ksize, op_t* wpack, int Cin_total, int ci_off);

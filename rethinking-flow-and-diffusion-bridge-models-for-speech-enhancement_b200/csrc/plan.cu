@@ -109,6 +109,9 @@ struct fdbm_plan {
   std::vector<int> op_kind;                                  // FDBM_OP_* of every entry
   std::vector<double> op_flops;                              // algorithmic FLOPs (2*MAC) of every entry (convs)
   std::vector<std::function<int(cudaStream_t)>> pack_ops;   // weight packing after load_weights (the few odd ones)
+  // training: per-site gradient sums (common.cuh DeferDesc): one pool, one memset per backward, one reduction launch
+  double* defer_pool = nullptr; int64_t defer_pool_bytes = 0;
+  std::vector<DeferDesc> defer_descs; DeferDesc* defer_descs_d = nullptr;
   std::vector<PackDesc> pack_descs;                          // ... and all regular conv packs, run as ONE launch
   PackDesc* pack_descs_d = nullptr; long long pack_blocks = 0;
   int n_launches = 0;
@@ -244,6 +247,19 @@ struct Builder {
   float *att_scratch = nullptr, *d_dense = nullptr, *g_temb = nullptr;
   const float* zero_bias = nullptr;
   bool train() const { return P->train; }
+  int64_t defer_used = 0;
+  double* site_sums(int64_t n_doubles) {                 // this site's slice of the deferred-sums pool (zero at the start of a backward)
+    const int64_t bytes = (n_doubles * 8 + 255) / 256 * 256;
+    defer_used += bytes;
+    if (dry) return reinterpret_cast<double*>(P->arena);  // sizing pass: only counted
+    return reinterpret_cast<double*>(reinterpret_cast<uint8_t*>(P->defer_pool) + defer_used - bytes);
+  }
+  void defer_col_sums(const double* src, int C, int64_t dst_off, float* per_b = nullptr, int per_b_ld = 0) {
+    if (!dry) P->defer_descs.push_back(DeferDesc{src, P->B, C, 0, dst_off >= 0 ? P->grads + dst_off : nullptr, nullptr, per_b, per_b_ld});
+  }
+  void defer_gn_param(const double* S, int C, int64_t gamma_off, int64_t beta_off) {
+    if (!dry) P->defer_descs.push_back(DeferDesc{S, P->B, C, 1, P->grads + gamma_off, P->grads + beta_off, nullptr, 0});
+  }
   void bgroup() { if (train()) groups.emplace_back(); }
   void bop(Op f, int kind = FDBM_OP_NORM) { if (train() && !dry) groups.back().emplace_back(std::move(f), kind); }
   float* gp(int64_t off) const { return P->grads + off; }
@@ -292,12 +308,12 @@ struct Builder {
     const int B = P->B, C1 = x1.C, C2 = x2 ? x2->C : 0, Ct = C1 + C2;
     const int64_t px = static_cast<int64_t>(x1.T) * x1.F;
     const float* gamma = pp(gw_off);
-    double* S = Sbuf;
+    double* S = site_sums(static_cast<int64_t>(B) * Ct * 2);
+    defer_gn_param(S, Ct, gw_off, gb_off);
     fdbm_plan* plp = P;
     const Act a1 = x1; const Act a2 = x2 ? *x2 : Act();
     const int cb = gn_chunk(Ct, px);
     bop([=](cudaStream_t s) {
-      FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Ct, s));
       const bool f1 = plp->grad_first(a1.grad), f2 = C2 ? plp->grad_first(a2.grad) : false;
       for (int b0 = 0; b0 < B; b0 += cb) {
         const int nb = std::min(cb, B - b0);
@@ -306,7 +322,7 @@ struct Builder {
         if (int rc = launch_gn_bwd_apply(g_a, Ct, 0, a1.h16, 1, C1, Ct, 0, tab, stats, gamma, act, nb, px, S, a1.grad, nullptr, nullptr, s, f1, b0)) return rc;
         if (C2) if (int rc = launch_gn_bwd_apply(g_a, Ct, C1, a2.h16, 1, C2, Ct, C1, tab, stats, gamma, act, nb, px, S, a2.grad, nullptr, nullptr, s, f2, b0)) return rc;
       }
-      return launch_gn_param_grad(S, B, Ct, plp->cur_inv, plp->grads + gw_off, plp->grads + gb_off, s);
+      return FDBM_OK;
     });
   }
   // utterances per reduce/apply chunk.  Measured: chunks small enough for the apply pass to re-read x and g_a from L2 (one
@@ -524,7 +540,14 @@ struct Builder {
       const int64_t pxo = static_cast<int64_t>(To) * Fo;
       const Act xa = x1; const Act xb = x2 ? *x2 : Act();
       op_t *t1 = T1, *t2 = T2, *t3 = T3, *t4 = T4, *t5 = T5;
-      double* sA = sumsA; double* S = Sbuf; float* dd = d_dense;
+      double* sA = site_sums(static_cast<int64_t>(B) * Cout);       // dL/d(out) column sums: Conv_1 (and Conv_2) bias gradients
+      double* sA1 = site_sums(static_cast<int64_t>(B) * Cout);      // g_h1 column sums: Conv_0 bias and FiLM gradients
+      double* S = site_sums(static_cast<int64_t>(B) * Cout * 2);    // GroupNorm_1 backward sums
+      float* dd = d_dense;
+      defer_col_sums(sA, Cout, o_c1b);
+      if (o_c2b >= 0) defer_col_sums(sA, Cout, o_c2b);
+      defer_gn_param(S, Cout, o_g1w, o_g1b);
+      defer_col_sums(sA1, Cout, o_c0b, dense_row >= 0 ? dd + dense_row : nullptr, dense_stride);
       if (comb) {
         const CombineArgs cb = *comb; const float* og = out.grad;
         bop([=](cudaStream_t s) {
@@ -535,10 +558,7 @@ struct Builder {
         const float* og = out.grad; float* xg = shortcut ? nullptr : xa.grad;
         bop([=](cudaStream_t s) {
           if (int rc = plp->grad_ensure(og, s)) return rc;
-          if (int rc = launch_grad_prepare(og, B, pxo, Cout, 0.70710678118654752f, t1, xg, sA, s, xg && plp->grad_first(xg))) return rc;
-          if (int rc = launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c1b, nullptr, 0, s)) return rc;
-          if (o_c2b >= 0) return launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c2b, nullptr, 0, s);
-          return FDBM_OK;
+          return launch_grad_prepare(og, B, pxo, Cout, 0.70710678118654752f, t1, xg, sA, s, xg && plp->grad_first(xg), true);
         });
       }
       if (shortcut) {
@@ -573,14 +593,12 @@ struct Builder {
       dgrad_op(t1, Cout, 9, pack_d(o_c1w, Cout, Cout, 3), Cout, To, Fo, t3, nullptr);
       const int cb1 = gn_chunk(Cout, pxo);
       bop([=](cudaStream_t s) {     // GroupNorm_1 backward: g_h1 (16-bit) + its per-(b,c) sums (Conv_0 bias and FiLM gradients)
-        FDBM_CUDA(cudaMemsetAsync(S, 0, sizeof(double) * 2 * B * Cout, s));
         for (int b0 = 0; b0 < B; b0 += cb1) {            // chunks that fit the L2, see gn_bwd()
           const int nb = std::min(cb1, B - b0);
           if (int rc = launch_gn_bwd_reduce(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, 1, nb, pxo, S, s, b0)) return rc;
-          if (int rc = launch_gn_bwd_apply(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, g1w, 1, nb, pxo, S, nullptr, t4, sA, s, false, b0)) return rc;
+          if (int rc = launch_gn_bwd_apply(t3, Cout, 0, h1, 1, Cout, Cout, 0, tab1, stats1, g1w, 1, nb, pxo, S, nullptr, t4, sA1, s, false, b0, true)) return rc;
         }
-        if (int rc = launch_gn_param_grad(S, B, Cout, plp->cur_inv, plp->grads + o_g1w, plp->grads + o_g1b, s)) return rc;
-        return launch_col_sums_to(sA, B, Cout, plp->cur_inv, plp->grads + o_c0b, dense_row >= 0 ? dd + dense_row : nullptr, dense_stride, s);
+        return FDBM_OK;
       });
       // Conv_0: a0 recomputed (or the saved resampled one), wgrad, dgrad, GroupNorm_0 backward into x.grad
       const op_t* a0b = a0;
@@ -647,25 +665,25 @@ struct Builder {
       fdbm_plan* plp = P;
       const int64_t px = static_cast<int64_t>(T) * F;
       op_t *t1 = T1, *t2 = T2, *t3 = T3, *t4 = T4;
-      double* sA = sumsA; float* asc = att_scratch;
+      double* sA = site_sums(static_cast<int64_t>(B) * C); float* asc = att_scratch;
+      double* sQ[3] = {site_sums(static_cast<int64_t>(B) * C), site_sums(static_cast<int64_t>(B) * C), site_sums(static_cast<int64_t>(B) * C)};
+      defer_col_sums(sA, C, o_b3);
       const Act xa = x;
       { const float* og = out.grad; float* xg = xa.grad;
         bop([=](cudaStream_t s) {
           if (int rc = plp->grad_ensure(og, s)) return rc;
-          if (int rc = launch_grad_prepare(og, B, px, C, 0.70710678118654752f, t1, xg, sA, s, plp->grad_first(xg))) return rc;
-          return launch_col_sums_to(sA, B, C, plp->cur_inv, plp->grads + o_b3, nullptr, 0, s);
+          return launch_grad_prepare(og, B, px, C, 0.70710678118654752f, t1, xg, sA, s, plp->grad_first(xg), true);
         }); }
       { WgradCall w; w.dy = t1; w.dy_ld = C; w.Cout = C; w.x = o; w.x_ld = C; w.Cin = C; w.ksize = 1; w.T = T; w.F = F; w.layout = 1; wgrad_op(w, o_w3); }
       dgrad_op(t1, C, 1, pack_d(o_w3, C, C, -1), C, T, F, t3, nullptr);
       const int64_t o_b[3] = {o_b0, o_b1, o_b2};
-      const int64_t ob0 = o_b[0], ob1 = o_b[1], ob2 = o_b[2];
+      for (int i = 0; i < 3; ++i) defer_col_sums(sQ[i], C, o_b[i]);
+      double *sq0 = sQ[0], *sq1 = sQ[1], *sq2 = sQ[2];
       bop([=](cudaStream_t s) {
         if (int rc = launch_attention_bwd(qkv, B, T * F, C, t3, asc, t4, s)) return rc;
-        const int64_t obs[3] = {ob0, ob1, ob2};
-        for (int i = 0; i < 3; ++i) {
-          if (int rc = launch_col_sums16(t4, 3 * C, i * C, B, px, C, sA, s)) return rc;
-          if (int rc = launch_col_sums_to(sA, B, C, plp->cur_inv, plp->grads + obs[i], nullptr, 0, s)) return rc;
-        }
+        double* const sq[3] = {sq0, sq1, sq2};
+        for (int i = 0; i < 3; ++i)
+          if (int rc = launch_col_sums16(t4, 3 * C, i * C, B, px, C, sq[i], s, true)) return rc;
         return FDBM_OK;
       });
       { const op_t* s1 = xa.h16; const double* q1 = xa.sums;
@@ -744,6 +762,9 @@ struct Builder {
         float* dd = d_dense; float* gt = g_temb;
         bgroup();
         bop([=](cudaStream_t s) {
+          // last group of the backward: every site has left its sums; reduce them into the parameter gradients (and the FiLM
+          // rows of d_dense that the time-embedding backward below consumes) in one launch
+          if (int rc = launch_deferred_sums(plp->defer_descs_d, static_cast<int>(plp->defer_descs.size()), plp->cur_inv, s)) return rc;
           return launch_dense_temb_bwd(dd, temb_act, dwp, B, 4 * nf, rows, plp->grads + dw0, plp->grads + db0, gt, plp->cur_t, fw, nf, w1, b1, w2,
                                        b2, plp->cur_t_stride, plp->grads + o_w1, plp->grads + o_b1, plp->grads + o_w2, plp->grads + o_b2, s);
         });
@@ -779,12 +800,12 @@ struct Builder {
       release(cols);
       if (train()) {
         bgroup();
-        fdbm_plan* plp = P; op_t* t1 = T1; double* sA = sumsA; const float* g0 = h0.grad;
+        fdbm_plan* plp = P; op_t* t1 = T1; double* sA = site_sums(static_cast<int64_t>(B) * nf); const float* g0 = h0.grad;
+        defer_col_sums(sA, nf, o_b);
         const int64_t px = static_cast<int64_t>(T) * F;
         bop([=](cudaStream_t s) {
           if (int rc = plp->grad_ensure(g0, s)) return rc;
-          if (int rc = launch_grad_prepare(g0, B, px, nf, 1.0f, t1, nullptr, sA, s)) return rc;
-          return launch_col_sums_to(sA, B, nf, plp->cur_inv, plp->grads + o_b, nullptr, 0, s);
+          return launch_grad_prepare(g0, B, px, nf, 1.0f, t1, nullptr, sA, s, false, true);
         });
         WgradCall wc; wc.dy = t1; wc.dy_ld = nf; wc.Cout = nf; wc.x = cols; wc.x_ld = 64; wc.Cin = 64; wc.ksize = 1; wc.T = T; wc.F = F;
         wc.layout = 2; wc.aux = Cp;
@@ -960,6 +981,7 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   b1.arena.reset(int64_t(1) << 40);
   if (int rc = b1.build()) return fail(rc);
   P->sums_pool_bytes = b1.sums_used;
+  P->defer_pool_bytes = b1.defer_used;
   P->arena_bytes = b1.arena.peak() + (P->sums_pool_bytes + 1023) / 1024 * 1024;
   P->arena = nullptr;
   P->wpacked_bytes = b1.wp_off;
@@ -977,6 +999,7 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   P->extra_bytes = spec_elems * sizeof(float);
   if (train) {
     if ((e = cudaMalloc(&P->grads, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(grads)", __FILE__, __LINE__));
+    if (P->defer_pool_bytes && (e = cudaMalloc(&P->defer_pool, P->defer_pool_bytes)) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(deferred sums pool)", __FILE__, __LINE__));
     if ((e = cudaMalloc(&P->wpacked_d, std::max<int64_t>(P->wpacked_d_bytes, 1024))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wpacked_d)", __FILE__, __LINE__));
     if ((e = cudaMalloc(&P->wgrad_ws, std::max<int64_t>(P->wgrad_ws_bytes, 1024))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(wgrad_ws)", __FILE__, __LINE__));
     if ((e = cudaMemset(P->grads, 0, params_numel * sizeof(float))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
@@ -989,7 +1012,7 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
     if ((e = cudaMalloc(&P->opt_scratch, 1025 * sizeof(double))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(opt_scratch)", __FILE__, __LINE__));
     if ((e = cudaMalloc(&P->opt_state, 4 * sizeof(double))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(opt_state)", __FILE__, __LINE__));
     if ((e = cudaMemset(P->opt_state, 0, 4 * sizeof(double))) != cudaSuccess) return fail(cuda_fail(e, "cudaMemset", __FILE__, __LINE__));
-    P->extra_bytes += params_numel * 4 * 5 + std::max<int64_t>(P->wpacked_d_bytes, 1024) + std::max<int64_t>(P->wgrad_ws_bytes, 1024);
+    P->extra_bytes += P->defer_pool_bytes + params_numel * 4 * 5 + std::max<int64_t>(P->wpacked_d_bytes, 1024) + std::max<int64_t>(P->wgrad_ws_bytes, 1024);
   } else if (!arch->predictive) {
     // sampler staging: the graph of the N-step loop reads y / x / times / coefficients / seed from these fixed buffers
     const size_t spec_bytes = spec_elems * sizeof(float);
@@ -1013,6 +1036,12 @@ static int plan_create_impl(const fdbm_arch* arch, int batch, int n_frames, bool
   b2.arena.reset(P->arena_bytes);
   if (int rc = b2.build()) return fail(rc);
   P->n_bwd_launches = static_cast<int>(P->bwd_ops.size());
+  if (!P->defer_descs.empty()) {
+    if ((e = cudaMalloc(&P->defer_descs_d, P->defer_descs.size() * sizeof(DeferDesc))) != cudaSuccess) return fail(cuda_fail(e, "cudaMalloc(deferred sums)", __FILE__, __LINE__));
+    if ((e = cudaMemcpy(P->defer_descs_d, P->defer_descs.data(), P->defer_descs.size() * sizeof(DeferDesc), cudaMemcpyHostToDevice)) != cudaSuccess)
+      return fail(cuda_fail(e, "cudaMemcpy(deferred sums)", __FILE__, __LINE__));
+  }
+  if (b2.defer_used != P->defer_pool_bytes) { set_error("plan: deferred-sums pool diverged from the sizing pass"); return fail(FDBM_EINVAL); }
   if (!P->pack_descs.empty()) {
     long long nb = 0;
     for (auto& d : P->pack_descs) { d.first_block = nb; nb += (d.total + kPackChunk - 1) / kPackChunk; }
@@ -1054,6 +1083,7 @@ extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float l
   cudaStream_t s = as_stream(stream);
   plan->cur_gout = g_out; plan->cur_inv = 1.0f / loss_scale;
   if (!accumulate) FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
+  if (plan->defer_pool_bytes) FDBM_CUDA(cudaMemsetAsync(plan->defer_pool, 0, plan->defer_pool_bytes, s));
   plan->grads_begin();
   for (auto& f : plan->bwd_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
@@ -1069,6 +1099,7 @@ extern "C" int fdbm_plan_profile_backward(fdbm_plan* plan, const float* g_out, f
   cudaStream_t s = as_stream(stream);
   plan->cur_gout = g_out; plan->cur_inv = 1.0f / loss_scale;
   FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
+  if (plan->defer_pool_bytes) FDBM_CUDA(cudaMemsetAsync(plan->defer_pool, 0, plan->defer_pool_bytes, s));
   plan->grads_begin();
   std::vector<cudaEvent_t> ev(n + 1);
   for (auto& e : ev) FDBM_CUDA(cudaEventCreate(&e));
@@ -1194,7 +1225,7 @@ extern "C" int fdbm_plan_destroy(fdbm_plan* plan) {
   cudaFree(plan->arena); cudaFree(plan->params); cudaFree(plan->wpacked); cudaFree(plan->d_buf);
   cudaFree(plan->grads); cudaFree(plan->wpacked_d); cudaFree(plan->wgrad_ws);
   cudaFree(plan->adam_m); cudaFree(plan->adam_v); cudaFree(plan->ema); cudaFree(plan->opt_scratch);
-  cudaFree(plan->opt_state); cudaFree(plan->ema_backup); cudaFree(plan->pack_descs_d);
+  cudaFree(plan->opt_state); cudaFree(plan->ema_backup); cudaFree(plan->pack_descs_d); cudaFree(plan->defer_descs_d); cudaFree(plan->defer_pool);
   if (prev >= 0 && prev != plan->device) cudaSetDevice(prev);
   delete plan;
   return FDBM_OK;

@@ -562,9 +562,9 @@ int grid_for(int64_t n) { return static_cast<int>(std::min<int64_t>(ceil_div64(n
 }  // namespace
 
 int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op_t* g16, float* acc_dst, double* sums, cudaStream_t s,
-                        bool acc_first) {
+                        bool acc_first, bool sums_prezeroed) {
   FDBM_REQUIRE(C % 4 == 0 && C / 4 <= 256 && 256 % (C / 4) == 0, "grad_prepare: unsupported channel count %d", C);
-  if (sums) FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C, s));
+  if (sums && !sums_prezeroed) FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C, s));
   const int pl = 256 / (C / 4);
   int64_t blocks_x = std::max<int64_t>(1, (static_cast<int64_t>(num_sms()) * 8) / B);
   blocks_x = std::min<int64_t>(blocks_x, std::max<int64_t>(1, P / (pl * 8)));
@@ -602,7 +602,7 @@ int launch_gn_bwd_reduce(const op_t* g_a, int g_ld, int g_coff, const void* x, i
 
 int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, int x16, int C, int C_tot, int c_off,
                         const float2* tab, const float2* stats, const float* gamma, int act, int B, int64_t P, const double* S,
-                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s, bool acc_first, int b0) {
+                        float* acc_dst, op_t* out16, double* out_sums, cudaStream_t s, bool acc_first, int b0, bool sums_prezeroed) {
   GnBwdArgs a{};
   a.b0 = b0;
   a.g_a = g_a; a.g_ld = g_ld; a.g_coff = g_coff; a.x = x; a.x16 = x16; a.C = C; a.C_tot = C_tot; a.c_off = c_off;
@@ -610,7 +610,7 @@ int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, in
   a.acc_dst = acc_dst; a.out16 = out16; a.out_sums = out_sums; a.acc_first = acc_first ? 1 : 0;
   const int G = std::min(C_tot / 4, 32);
   a.inv_count = 1.0 / (static_cast<double>(C_tot / G) * static_cast<double>(P));
-  if (out_sums) FDBM_CUDA(cudaMemsetAsync(out_sums + static_cast<int64_t>(b0) * C, 0, sizeof(double) * B * C, s));
+  if (out_sums && !sums_prezeroed) FDBM_CUDA(cudaMemsetAsync(out_sums + static_cast<int64_t>(b0) * C, 0, sizeof(double) * B * C, s));
   dim3 grid; int ppb;
   if (int rc = gn_bwd_grid(a, B, &grid, &ppb)) return rc;
   gn_bwd_kernel<true><<<grid, 256, 0, s>>>(a, ppb);
@@ -640,15 +640,43 @@ int launch_fir_resample16(const op_t* in, int in_ld, int in_coff, int B, int T, 
   return FDBM_OK;
 }
 
-int launch_col_sums16(const op_t* in, int ld, int c_off, int B, int64_t P, int C, double* sums, cudaStream_t s) {
+int launch_col_sums16(const op_t* in, int ld, int c_off, int B, int64_t P, int C, double* sums, cudaStream_t s, bool sums_prezeroed) {
   FDBM_REQUIRE(C % 8 == 0 && C / 8 <= 256, "col_sums16: unsupported channel count %d", C);
-  FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C, s));
+  if (!sums_prezeroed) FDBM_CUDA(cudaMemsetAsync(sums, 0, sizeof(double) * B * C, s));
   const int npl = 256 / (C / 8);
   int64_t bx = std::max<int64_t>(1, (static_cast<int64_t>(num_sms()) * 4) / B);
   bx = std::min<int64_t>(bx, std::max<int64_t>(1, P / (npl * 4)));
   const int64_t ppb = ceil_div64(P, bx);
   dim3 grid(static_cast<unsigned>(ceil_div64(P, ppb)), B);
   col_sums16_kernel<<<grid, 256, 0, s>>>(in, ld, c_off, P, C, ppb, sums);
+  FDBM_LAUNCH_CHECK();
+  return FDBM_OK;
+}
+
+// every deferred reduction of a backward pass in one launch: block = one descriptor (same arithmetic as col_sums_to_kernel /
+// gn_param_grad_kernel: double sum over the utterances, one float conversion, scaled add into the gradient buffer)
+__global__ void __launch_bounds__(256) deferred_sums_kernel(const DeferDesc* __restrict__ descs, float inv_scale) {
+  const DeferDesc d = descs[blockIdx.x];
+  for (int c = threadIdx.x; c < d.C; c += 256) {
+    if (d.kind == 0) {
+      double s = 0;
+      for (int b = 0; b < d.B; ++b) {
+        const double v = d.src[static_cast<int64_t>(b) * d.C + c];
+        s += v;
+        if (d.per_b) d.per_b[static_cast<int64_t>(b) * d.per_b_ld + c] = inv_scale * static_cast<float>(v);
+      }
+      if (d.dst0) atomicAdd(d.dst0 + c, inv_scale * static_cast<float>(s));
+    } else {
+      double s1 = 0, s2 = 0;
+      for (int b = 0; b < d.B; ++b) { s1 += d.src[(static_cast<int64_t>(b) * d.C + c) * 2]; s2 += d.src[(static_cast<int64_t>(b) * d.C + c) * 2 + 1]; }
+      atomicAdd(d.dst1 + c, inv_scale * static_cast<float>(s1));
+      atomicAdd(d.dst0 + c, inv_scale * static_cast<float>(s2));
+    }
+  }
+}
+int launch_deferred_sums(const DeferDesc* descs_dev, int n_descs, float inv_scale, cudaStream_t s) {
+  if (n_descs <= 0) return FDBM_OK;
+  deferred_sums_kernel<<<n_descs, 256, 0, s>>>(descs_dev, inv_scale);
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
