@@ -75,7 +75,7 @@ def synth_batch(n, device, seed=1234):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+    """nvidia-smi clocks / throttle reasons sampled every 100 ms while the timed region runs."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
@@ -88,7 +88,7 @@ class ClockSampler:
             fd, self.path = tempfile.mkstemp(suffix=".csv")
             os.close(fd)
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}",
-                                          "--format=csv,noheader,nounits", "-lms", "200"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=open(self.path, "w"), stderr=subprocess.DEVNULL)
         except Exception:
             self.proc = None
@@ -361,8 +361,9 @@ def train_main(args):
     if rank == 0:
         clocks.start()
     ms = timed(step_device, args.steps)
-    clock_info = clocks.stop() if rank == 0 else None
     ms_e2e = timed(step_e2e, args.steps)
+    # a few 56 ms steps end before nvidia-smi prints its first line: the sampler covers both timed regions (same step, same load)
+    clock_info = clocks.stop() if rank == 0 else None
     # phase split of one step (events around forward / backward / optimiser)
     for _ in range(2):                                  # the second pass is the one reported (the first re-warms allocator paths)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
@@ -544,7 +545,7 @@ def files_main(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=None, help="timed steps (default 3; 20 for --workload train, whose step is 56 ms)")
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--micro-batch", type=int, default=int(os.environ.get("FDBM_MICRO_BATCH", "128")))
@@ -563,6 +564,8 @@ def main():
     ap.add_argument("--no-gather", action="store_true", help="skip the final NCCL all_gather of the enhanced waveforms")
     ap.add_argument("--no-torch-gpu-baseline", action="store_true")
     args = ap.parse_args()
+    if args.steps is None:
+        args.steps = 20 if args.workload == "train" else 3
     predictive = args.workload == "predictive"
     set_workload(args.seconds, args.bridge_steps, predictive)
     if args.workload == "train":
