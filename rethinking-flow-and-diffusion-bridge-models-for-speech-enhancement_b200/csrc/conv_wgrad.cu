@@ -89,6 +89,7 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the split-K reduction behind this kernel may become resident (it waits for this grid's completion)
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -176,6 +177,9 @@ __global__ void __launch_bounds__(256)
 wgrad_reduce_kernel(const float* __restrict__ partial, int n_splits, int taps, int Cout, int Cin, float scale, int layout,
                     int Cin_total, int ci_off, int aux, float* __restrict__ dw) {
   const int64_t n = static_cast<int64_t>(taps) * Cout * Cin;
+  // programmatic dependent launch: this grid may be resident before the wgrad kernel in front of it has finished; its partials are
+  // complete and visible from here on (a no-op when launched without the attribute)
+  asm volatile("griddepcontrol.wait;" ::: "memory");
   for (int64_t i = blockIdx.x * 256ll + threadIdx.x; i < n; i += 256ll * gridDim.x) {
     float acc = 0.f;
     for (int s = 0; s < n_splits; ++s) acc += partial[s * n + i];
@@ -235,8 +239,16 @@ int launch_conv_wgrad_ex(const WgradCall& c, cudaStream_t s) {
   conv_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_dy, map_x, p);
   FDBM_LAUNCH_CHECK();
   const int64_t n = static_cast<int64_t>(p.taps) * c.Cout * c.Cin;
-  wgrad_reduce_kernel<<<static_cast<int>(std::min<int64_t>(ceil_div64(n, 256), 2048)), 256, 0, s>>>(
-      c.workspace, p.n_splits, p.taps, c.Cout, c.Cin, c.scale, c.layout, c.Cin_total ? c.Cin_total : c.Cin, c.ci_off, c.aux, c.dw);
+  // the reduction is launched with programmatic stream serialisation: its launch latency and ramp overlap the tail of the wgrad
+  // kernel (228 such pairs per training step); FDBM_PDL=0 launches it plainly
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3(static_cast<unsigned>(std::min<int64_t>(ceil_div64(n, 256), 2048))); cfg.blockDim = dim3(256); cfg.dynamicSmemBytes = 0; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() ? 1 : 0;
+  FDBM_CUDA(cudaLaunchKernelEx(&cfg, wgrad_reduce_kernel, static_cast<const float*>(c.workspace), p.n_splits, p.taps, c.Cout, c.Cin, c.scale, c.layout,
+                               c.Cin_total ? c.Cin_total : c.Cin, c.ci_off, c.aux, c.dw));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
