@@ -36,6 +36,8 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int require_sm100();   // FDBM_OK or FDBM_EARCH (cached per device)
+int pdl_batch_limit();   // see api.cu
+struct PdlBatchScope { int prev; explicit PdlBatchScope(int limit); ~PdlBatchScope(); PdlBatchScope(const PdlBatchScope&) = delete; };
 bool pdl_enabled();    // programmatic dependent launch of the convolution / GroupNorm-table kernels (FDBM_PDL=0 in the environment disables it)
 int num_sms();
 int current_device();  // cudaGetDevice, -1 on failure

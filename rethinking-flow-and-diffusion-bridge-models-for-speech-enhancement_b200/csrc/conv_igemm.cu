@@ -1183,7 +1183,7 @@ int launch_conv_igemm(const ConvArgs& a, cudaStream_t s) {
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   // measured: 256 x 4 s utterances 1321-1323 -> 1307 audio-s/s WITH the attribute, one utterance 18.78 -> 18.28 ms: it pays where the
   // launches are short (launch-bound small batches), so it is only requested there
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && a.B <= 8 ? 1 : 0;
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && a.B <= pdl_batch_limit() ? 1 : 0;
   if (a.comb_pyr) FDBM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<true, false>, map_a[0], map_a[1], map_a[2], map_b, p));
   else if (a.residual_h16) FDBM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, true>, map_a[0], map_a[1], map_a[2], map_b, p));
   else FDBM_CUDA(cudaLaunchKernelEx(&cfg, conv_igemm_kernel<false, false>, map_a[0], map_a[1], map_a[2], map_b, p));

@@ -484,7 +484,7 @@ int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2,
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
-  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && B <= 8 ? 1 : 0;      // small batches only, see launch_conv_igemm
+  cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && B <= pdl_batch_limit() ? 1 : 0;      // small batches only, see launch_conv_igemm
   FDBM_CUDA(cudaLaunchKernelEx(&cfg, gn_finalize_kernel, sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table, blk_real));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;

@@ -942,6 +942,7 @@ struct Builder {
 };
 
 int run_ops(fdbm_plan* plan, cudaStream_t s) {
+  PdlBatchScope pdl(plan->train ? std::min(std::max(plan->B, 8), 32) : 8);   // training plans: short launches at every level (api.cu)
   for (auto& f : plan->ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
 }
@@ -1085,6 +1086,7 @@ extern "C" int fdbm_ncsnpp_backward(fdbm_plan* plan, const float* g_out, float l
   if (!accumulate) FDBM_CUDA(cudaMemsetAsync(plan->grads, 0, plan->params_numel * sizeof(float), s));
   if (plan->defer_pool_bytes) FDBM_CUDA(cudaMemsetAsync(plan->defer_pool, 0, plan->defer_pool_bytes, s));
   plan->grads_begin();
+  PdlBatchScope pdl(std::min(std::max(plan->B, 8), 32));
   for (auto& f : plan->bwd_ops) if (int rc = f(s)) return rc;
   return FDBM_OK;
 }
