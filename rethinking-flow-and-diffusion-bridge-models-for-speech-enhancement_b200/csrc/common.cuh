@@ -36,6 +36,24 @@ int cuda_fail(cudaError_t e, const char* what, const char* file, int line);
 static inline cudaStream_t as_stream(void* s) { return reinterpret_cast<cudaStream_t>(s); }
 
 int require_sm100();   // FDBM_OK or FDBM_EARCH (cached per device)
+// Kernels that may be launched with programmatic stream serialisation call this FIRST: nothing of the previous kernel in the
+// stream is read or overwritten before it has completed, and the kernel behind this one may become resident (it waits the same way).
+__device__ __forceinline__ void pdl_wait_then_trigger() {
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
+// launch `kernel` with the programmatic-stream-serialisation attribute when `pdl` (short launches: the launch latency and block
+// ramp-up overlap the previous kernel's tail), plainly otherwise.  The kernel must start with pdl_wait_then_trigger().
+template <typename... KArgs, typename... Args>
+inline cudaError_t launch_maybe_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = 1;
+  cfg.attrs = attr; cfg.numAttrs = pdl ? 1 : 0;
+  return cudaLaunchKernelEx(&cfg, kernel, static_cast<KArgs>(args)...);
+}
 int pdl_batch_limit();   // see api.cu
 struct PdlBatchScope { int prev; explicit PdlBatchScope(int limit); ~PdlBatchScope(); PdlBatchScope(const PdlBatchScope&) = delete; };
 bool pdl_enabled();    // programmatic dependent launch of the convolution / GroupNorm-table kernels (FDBM_PDL=0 in the environment disables it)

@@ -89,7 +89,10 @@ conv_wgrad_kernel(const __grid_constant__ CUtensorMap map_dy, const __grid_const
   fence_before_sync();
   __syncthreads();
   fence_after_sync();
-  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");   // the split-K reduction behind this kernel may become resident (it waits for this grid's completion)
+  // programmatic dependent launch: the prologue above overlapped the tail of the previous kernel; its results (and buffers it still
+  // read) are only touched from here on.  The split-K reduction behind this kernel may become resident (it waits the same way).
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+  asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
   const uint32_t tmem_base = *tmem_slot;
 
   if (warp == 0) {
@@ -236,7 +239,7 @@ int launch_conv_wgrad_ex(const WgradCall& c, cudaStream_t s) {
   if (int rc = make_act_tile_map(&map_dy, c.dy, c.B, c.T, c.F, c.dy_ld, TILE_F, TILE_T)) return rc;
   if (int rc = make_act_tile_map(&map_x, c.x, c.B, c.T, c.F, c.x_ld, HALO_F, HALO_T)) return rc;
   dim3 grid(p.n_splits, groups, blocks);
-  conv_wgrad_kernel<<<grid, NUM_THREADS, SMEM_BYTES, s>>>(map_dy, map_x, p);
+  FDBM_CUDA(launch_maybe_pdl(conv_wgrad_kernel, grid, dim3(NUM_THREADS), SMEM_BYTES, s, pdl_enabled() && c.B <= pdl_batch_limit(), map_dy, map_x, p));
   FDBM_LAUNCH_CHECK();
   const int64_t n = static_cast<int64_t>(p.taps) * c.Cout * c.Cin;
   // the reduction is launched with programmatic stream serialisation: its launch latency and ramp overlap the tail of the wgrad

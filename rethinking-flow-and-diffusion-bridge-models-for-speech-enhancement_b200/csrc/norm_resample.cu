@@ -117,6 +117,7 @@ groupnorm_act_kernel(const void* __restrict__ src1, const double* __restrict__ s
                      const void* __restrict__ src2, const double* __restrict__ sums2, int C2,
                      const float* __restrict__ gamma, const float* __restrict__ beta, int T, int F, int silu,
                      int px_per_block, uint4* __restrict__ act_out, uint4* __restrict__ raw_out) {
+  pdl_wait_then_trigger();
   __shared__ float sA[GN_MAXC], sB[GN_MAXC];
   __shared__ float s_mean[32], s_rstd[32];
   const int C = C1 + C2;
@@ -552,7 +553,8 @@ int launch_groupnorm_act(const void* src1, int src1_h16, const double* sums1, in
   uint4* ao = reinterpret_cast<uint4*>(act_out);
   uint4* ro = reinterpret_cast<uint4*>(raw_out);
 #define FDBM_GN_LAUNCH(M, H) \
-  groupnorm_act_kernel<M, H><<<grid, 256, 0, s>>>(src1, sums1, C1, src2, sums2, C2, gamma, beta, T, F, silu, ppb, ao, ro)
+  FDBM_CUDA(launch_maybe_pdl(groupnorm_act_kernel<M, H>, grid, dim3(256), 0, s, pdl_enabled() && B <= pdl_batch_limit(), src1, sums1, C1, src2, sums2, C2, \
+                             gamma, beta, T, F, silu, ppb, ao, ro))
   if (src1_h16) {
     if (mode == 0) FDBM_GN_LAUNCH(0, true); else if (mode == 1) FDBM_GN_LAUNCH(1, true); else FDBM_GN_LAUNCH(2, true);
   } else {

@@ -27,6 +27,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 __global__ void __launch_bounds__(256)
 grad_prepare_kernel(const float* __restrict__ g, int64_t P, int C, int64_t px_per_block, float scale,
                     op_t* __restrict__ g16, float* __restrict__ acc_dst, double* __restrict__ sums, int acc_first) {
+  pdl_wait_then_trigger();
   __shared__ float4 red[256];
   const int cg = C / 4, pl = 256 / cg;
   const int ci = threadIdx.x % cg, pi = threadIdx.x / cg;
@@ -113,6 +114,7 @@ __device__ __forceinline__ void load8(const GnBwdArgs& a, int64_t idx8, float (&
 template <bool APPLY>
 __global__ void __launch_bounds__(256, FDBM_GNBWD_BLOCKS)
 gn_bwd_kernel(const GnBwdArgs a, int px_per_block) {
+  pdl_wait_then_trigger();
   __shared__ float s_m1[32], s_m2[32];
   __shared__ float s_red[256 * 16];
   const int b = a.b0 + blockIdx.y;
@@ -284,6 +286,7 @@ __device__ __forceinline__ void taps1d(int o, int mode, int (&pos)[4], float (&w
 __global__ void __launch_bounds__(256)
 fir_resample16_kernel(const op_t* __restrict__ in, int in_ld, int in_coff, int B, int T, int F, int C, int mode, float scale,
                       op_t* __restrict__ out16, float* __restrict__ acc_dst) {
+  pdl_wait_then_trigger();
   const int To = mode == 1 ? T / 2 : T * 2, Fo = mode == 1 ? F / 2 : F * 2;
   const int cg8 = C / 8;
   const int64_t total = static_cast<int64_t>(B) * To * Fo * cg8;
@@ -570,7 +573,8 @@ int launch_grad_prepare(const float* g, int B, int64_t P, int C, float scale, op
   blocks_x = std::min<int64_t>(blocks_x, std::max<int64_t>(1, P / (pl * 8)));
   const int64_t ppb = ceil_div64(P, blocks_x);
   dim3 grid(static_cast<unsigned>(ceil_div64(P, ppb)), B);
-  grad_prepare_kernel<<<grid, 256, 0, s>>>(g, P, C, ppb, scale, g16, acc_dst, sums, acc_first ? 1 : 0);
+  FDBM_CUDA(launch_maybe_pdl(grad_prepare_kernel, grid, dim3(256), 0, s, pdl_enabled() && B <= pdl_batch_limit(), g, P, C, ppb, scale, g16, acc_dst, sums,
+                             acc_first ? 1 : 0));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -595,7 +599,7 @@ int launch_gn_bwd_reduce(const op_t* g_a, int g_ld, int g_coff, const void* x, i
   a.tab = tab; a.stats = stats; a.gamma = nullptr; a.act = act; a.P = P; a.S = S;
   dim3 grid; int ppb;
   if (int rc = gn_bwd_grid(a, B, &grid, &ppb)) return rc;
-  gn_bwd_kernel<false><<<grid, 256, 0, s>>>(a, ppb);
+  FDBM_CUDA(launch_maybe_pdl(gn_bwd_kernel<false>, grid, dim3(256), 0, s, pdl_enabled() && B <= pdl_batch_limit(), a, ppb));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -613,7 +617,7 @@ int launch_gn_bwd_apply(const op_t* g_a, int g_ld, int g_coff, const void* x, in
   if (out_sums && !sums_prezeroed) FDBM_CUDA(cudaMemsetAsync(out_sums + static_cast<int64_t>(b0) * C, 0, sizeof(double) * B * C, s));
   dim3 grid; int ppb;
   if (int rc = gn_bwd_grid(a, B, &grid, &ppb)) return rc;
-  gn_bwd_kernel<true><<<grid, 256, 0, s>>>(a, ppb);
+  FDBM_CUDA(launch_maybe_pdl(gn_bwd_kernel<true>, grid, dim3(256), 0, s, pdl_enabled() && B <= pdl_batch_limit(), a, ppb));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
@@ -635,7 +639,8 @@ int launch_fir_resample16(const op_t* in, int in_ld, int in_coff, int B, int T, 
   FDBM_REQUIRE(C % 8 == 0 && in_ld % 8 == 0 && in_coff % 8 == 0 && (mode == 1 || mode == 2), "fir_resample16: bad arguments");
   FDBM_REQUIRE(mode != 1 || (T % 2 == 0 && F % 2 == 0), "fir_resample16: down-sampling needs even T, F");
   const int To = mode == 1 ? T / 2 : T * 2, Fo = mode == 1 ? F / 2 : F * 2;
-  fir_resample16_kernel<<<grid_for(static_cast<int64_t>(B) * To * Fo * (C / 8)), 256, 0, s>>>(in, in_ld, in_coff, B, T, F, C, mode, scale, out16, acc_dst);
+  FDBM_CUDA(launch_maybe_pdl(fir_resample16_kernel, dim3(grid_for(static_cast<int64_t>(B) * To * Fo * (C / 8))), dim3(256), 0, s,
+                             pdl_enabled() && B <= pdl_batch_limit(), in, in_ld, in_coff, B, T, F, C, mode, scale, out16, acc_dst));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }
