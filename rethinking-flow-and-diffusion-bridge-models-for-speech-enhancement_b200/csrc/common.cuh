@@ -134,7 +134,7 @@ int launch_dense_all(const float* temb_act, const float* w, const float* bias, i
 int launch_gn_resample16(const op_t* src1, int C1, const op_t* src2, int C2, const float2* tab, int B, int T, int F,
                          int mode, op_t* act_out, op_t* raw_out, cudaStream_t s);
 int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2, const float* gamma, const float* beta,
-                       int B, int64_t pixels, float2* table, cudaStream_t s, int blk_real = 0);
+                       int B, int64_t pixels, float2* table, cudaStream_t s, int blk_real = 0, float2* stats = nullptr);   // stats: also [B,G] (mean, rstd)
 int launch_attention(const op_t* q, const op_t* k, const op_t* v, int ld, int B, int L,
                      int C, op_t* o, int ldo, cudaStream_t s, int fp32_probs = 0);   // fp32_probs: CUDA-core kernel with fp32 soft-max weights (training plans: matches attention_bwd)
 

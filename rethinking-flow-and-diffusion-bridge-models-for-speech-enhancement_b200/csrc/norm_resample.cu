@@ -423,7 +423,7 @@ gn_resample16_kernel(const op_t* __restrict__ src1, int C1, const op_t* __restri
 __global__ void __launch_bounds__(256)
 gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __restrict__ sums2, int C2,
                    const float* __restrict__ gamma, const float* __restrict__ beta, double pixels,
-                   float2* __restrict__ table, int blk_real) {
+                   float2* __restrict__ table, int blk_real, float2* __restrict__ stats) {
   __shared__ double2 s_sq[GN_MAXC];
   __shared__ float s_mean[32], s_rstd[32];
   asm volatile("griddepcontrol.wait;" ::: "memory");            // programmatic dependent launch: the producer's sums are final from here
@@ -457,6 +457,8 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
     if (var < 0) var = 0;
     s_mean[threadIdx.x] = static_cast<float>(mean);
     s_rstd[threadIdx.x] = static_cast<float>(1.0 / sqrt(var + 1e-6));
+    // training plans: the backward's per-group (mean, rstd), formerly a launch of its own per GroupNorm (gn_stats_kernel)
+    if (stats) stats[static_cast<int64_t>(b) * G + threadIdx.x] = make_float2(s_mean[threadIdx.x], s_rstd[threadIdx.x]);
   }
   __syncthreads();
 #pragma unroll
@@ -474,7 +476,7 @@ gn_finalize_kernel(const double* __restrict__ sums1, int C1, const double* __res
 }  // namespace
 
 int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2, const float* gamma, const float* beta,
-                       int B, int64_t pixels, float2* table, cudaStream_t s, int blk_real) {
+                       int B, int64_t pixels, float2* table, cudaStream_t s, int blk_real, float2* stats) {
   const int C = C1 + C2;
   FDBM_REQUIRE(blk_real == 0 || (blk_real > 0 && blk_real < 128 && blk_real % 4 == 0 && C1 % 128 == 0 && C2 % 128 == 0),
                "gn_finalize: channel_block_real %d needs 128-channel blocks (%d+%d)", blk_real, C1, C2);
@@ -486,7 +488,7 @@ int launch_gn_finalize(const double* sums1, int C1, const double* sums2, int C2,
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
   attr[0].val.programmaticStreamSerializationAllowed = 1;
   cfg.attrs = attr; cfg.numAttrs = pdl_enabled() && B <= pdl_batch_limit() ? 1 : 0;      // small batches only, see launch_conv_igemm
-  FDBM_CUDA(cudaLaunchKernelEx(&cfg, gn_finalize_kernel, sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table, blk_real));
+  FDBM_CUDA(cudaLaunchKernelEx(&cfg, gn_finalize_kernel, sums1, C1, sums2, C2, gamma, beta, static_cast<double>(pixels), table, blk_real, stats));
   FDBM_LAUNCH_CHECK();
   return FDBM_OK;
 }

@@ -331,11 +331,9 @@ struct Builder {
   int gn_chunk(int Ct, int64_t px) const { (void)Ct; (void)px; return P->B; }
   float2* norm_stats(const double* q1, int C1, const double* q2, int C2, int T, int F) {
     if (!train()) return nullptr;
-    const int B = P->B;
-    float2* st = alloc<float2>(static_cast<int64_t>(B) * 32);
-    const int64_t px = static_cast<int64_t>(T) * F;
-    op([=](cudaStream_t s) { return launch_gn_stats(q1, C1, q2, C2, B, px, st, s); }, FDBM_OP_STATS);
-    return st;
+    (void)C1; (void)q2; (void)C2; (void)T; (void)F;
+    if (q1 != last_stats_q1) return nullptr;            // always called right behind norm_table() of the same GroupNorm (build() checks)
+    return last_stats;
   }
 
   // ---------------- parameters
@@ -387,9 +385,13 @@ struct Builder {
     float2* tab = alloc<float2>(static_cast<int64_t>(B) * (C1 + C2));
     const int64_t px = static_cast<int64_t>(T) * F;
     const int blk_real = P->arch.channel_block_real;
-    op([=](cudaStream_t s) { return launch_gn_finalize(q1, C1, q2, C2, gamma, beta, B, px, tab, s, blk_real); }, FDBM_OP_STATS);
+    // training plans: the same launch leaves the per-group (mean, rstd) the backward needs (norm_stats() hands them out)
+    float2* st = train() ? alloc<float2>(static_cast<int64_t>(B) * 32) : nullptr;
+    last_stats = st; last_stats_q1 = q1;
+    op([=](cudaStream_t s) { return launch_gn_finalize(q1, C1, q2, C2, gamma, beta, B, px, tab, s, blk_real, st); }, FDBM_OP_STATS);
     return tab;
   }
+  float2* last_stats = nullptr; const double* last_stats_q1 = nullptr;
   static ConvSeg seg(const op_t* in, int C, int taps, const float2* tab = nullptr, int tab_stride = 0, int act = 0) {
     ConvSeg sg; sg.in = in; sg.C = C; sg.taps = taps; sg.norm_tab = tab; sg.tab_stride = tab_stride; sg.act = act;
     return sg;
