@@ -232,8 +232,8 @@ struct Builder {
   int64_t wp_off = 0;                  // running offset (bytes) into wpacked
   int dense_off = 0;                   // running row offset into the Dense_0 table
   bool dry = true;                     // first pass: sizes only
-  // inference plans: every GroupNorm-statistics buffer is a slice of one pool that a single memset zeroes at the start of
-  // the forward (the per-convolution memsets were ~100 extra graph nodes on the critical path)
+  // every GroupNorm-statistics buffer is a slice of one pool that a single memset zeroes at the start of the forward (the
+  // per-convolution memsets were ~100 extra stream operations on the critical path; training plans keep the slices for the backward)
   uint8_t* sums_pool = nullptr;
   int64_t sums_used = 0;
 
@@ -361,7 +361,6 @@ struct Builder {
   }
   void release(const void* p) { if (p && !P->train) arena.release(reinterpret_cast<const uint8_t*>(p) - P->arena); }
   double* alloc_sums(int64_t n_doubles) {
-    if (train()) return alloc<double>(n_doubles);
     const int64_t bytes = (n_doubles * 8 + 255) / 256 * 256;
     sums_used += bytes;
     if (dry) return reinterpret_cast<double*>(P->arena);          // sizing pass: only counted (the pool is added to the peak)
@@ -411,7 +410,7 @@ struct Builder {
       for (int i = 0; i < c.n_seg; ++i) k += static_cast<double>(c.seg[i].taps) * c.seg[i].C;
       flops = 2.0 * c.B * c.T * c.F * c.Cout * k;
     }
-    c.sums_prezeroed = !train();
+    c.sums_prezeroed = true;                          // every statistics buffer is a slice of the pool zeroed at the start of the forward
     if (c.bias_b && !train()) {
       fdbm_plan* plp = P;
       op([=](cudaStream_t s) {
@@ -712,7 +711,7 @@ struct Builder {
     auto next = [&]() -> const Mod& { return pl.mods[mi++]; };
     wp_off = 0; dense_off = 0; wd_off = 0; ws_need = 0; groups.clear();
     sums_used = 0;
-    if (!train() && !dry && P->sums_pool_bytes > 0) {
+    if (!dry && P->sums_pool_bytes > 0) {
       sums_pool = alloc<uint8_t>(P->sums_pool_bytes);
       uint8_t* pool = sums_pool; const int64_t pool_bytes = P->sums_pool_bytes;
       op([=](cudaStream_t s) { FDBM_CUDA(cudaMemsetAsync(pool, 0, pool_bytes, s)); return FDBM_OK; }, FDBM_OP_STATS);
