@@ -713,11 +713,21 @@ def main():
                                     "forward at this micro-batch, ncu --set full) / launches",
                     "launches_per_forward": n_conv,
                     "avg_launch_ms": conv_ms / max(1, n_conv),
+                    # the same quantity from the TIMED region itself: the convolutions' share of a forward (from the per-launch event
+                    # pass) x the device-timed step, i.e. without the event records between the launches of the profile pass
+                    "achieved_from_timed_step": None, "frac_from_timed_step": None,
                     "algorithmic_gflop_per_forward_per_utt": conv_flops / mb / 1e9}
         tot = sum(kind_ms.values())
         names = {0: "conv_igemm", 1: "groupnorm_act", 2: "channel_stats", 3: "skinny", 4: "attention", 5: "temb"}
         shares = {names[k]: round(v / tot, 4) for k, v in sorted(kind_ms.items())}
         shares["forward_ms_per_microbatch"] = tot
+        if tot > 0 and conv_ms > 0 and n_local % mb == 0:
+            n_fwd = (n_local // mb) * (1 if predictive else BRIDGE_STEPS)          # forwards of this rank per step
+            hbm_ms = sum(k["ms"] for k in (hbm_kernels or {}).values() if isinstance(k, dict) and "ms" in k) if not predictive else 0.0
+            step_ms = ms_total / args.steps
+            conv_ms_step = max(step_ms - hbm_ms, 1e-6) * (conv_ms / tot)             # the step is forwards + the three HBM kernels
+            roofline["achieved_from_timed_step"] = conv_flops * n_fwd / (conv_ms_step * 1e-3) / 1e12
+            roofline["frac_from_timed_step"] = roofline["achieved_from_timed_step"] / peak
 
     n_micro = (n_local + mb - 1) // mb
     launches_per_step = n_micro * (1 + 1 + BRIDGE_STEPS * (info["launches"] + 1) + 1)
